@@ -1,0 +1,386 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU oracle for the MAGE sampling path.
+
+A functional fp32 restatement, on torch CPU ops, of what the reference computes on the
+path `main_mage.py --split test` -> `MAGE.autoregressive_generate`
+(/root/reference/modules/mage_model.py:641-693) and `VectorQuantizedVAE.encode/decode`
+(/root/reference/modules/vqvae_model.py:233-242).  It takes a plain `state_dict` with the
+reference's key names instead of nn.Modules.
+
+Parity status: PINNED.  `oracle/make_golden.py` runs the unmodified reference in the
+authoring container (via oracle/ref_shims.py) on seeded synthetic checkpoints/batches and
+commits the outputs under tests/golden/; tests/test_oracle_golden.py holds this file to
+those vectors (bit-exact tokens/VQ indices, pixels to 1e-6), and, where /root/reference is
+present, to the reference itself.  The reference has no tests or golden vectors of its own
+(SURVEY.md §4).
+
+Only tests/, `__graft_entry__.smoke()` and bench.py's `cpu_baseline` / `--impl reference`
+legs may import this package.  The product (mage_b200/) never does.
+
+Two evaluation orders are provided:
+  * `generate`             -- the reference's own order: every step re-runs the 3x3 conv and
+                              the 6-block decoder over all L positions (mage_model.py:673-684).
+  * `generate_incremental` -- App. D of SURVEY.md: one position per step with a K/V cache for
+                              the two temporal blocks.  Mathematically identical because the
+                              temporal blocks are causal; used for full-length parity runs.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+SD = Dict[str, torch.Tensor]
+
+
+# --------------------------------------------------------------------------------------
+# VQ-VAE  (vqvae_model.py)
+# --------------------------------------------------------------------------------------
+def _conv(sd: SD, name: str, x, stride=1, padding=0):
+    return F.conv2d(x, sd[name + ".weight"], sd.get(name + ".bias"), stride=stride, padding=padding)
+
+
+def _bn(sd: SD, name: str, x):
+    # eval-mode BatchNorm2d (first stage is frozen in eval: mage_model.py:518-519)
+    return F.batch_norm(x, sd[name + ".running_mean"], sd[name + ".running_var"],
+                        sd[name + ".weight"], sd[name + ".bias"], training=False, eps=1e-5)
+
+
+def _res_block(sd: SD, name: str, x):
+    """vqvae_model.py:111-124.  The leading ReLU is in-place, so the skip adds relu(x)."""
+    x = F.relu(x)
+    h = _bn(sd, name + ".block.2", _conv(sd, name + ".block.1", x, padding=1))
+    h = _bn(sd, name + ".block.5", _conv(sd, name + ".block.4", F.relu(h)))
+    return x + h
+
+
+def _enc_block(sd: SD, name: str, x):
+    """vqvae_model.py:126-145 (3x3, 3x3, 3x3, 1x1; non-in-place ReLUs)."""
+    idp = _conv(sd, name + ".id_path", x) if (name + ".id_path.weight") in sd else x
+    h = _conv(sd, name + ".block.1", F.relu(x), padding=1)
+    h = _conv(sd, name + ".block.3", F.relu(h), padding=1)
+    h = _conv(sd, name + ".block.5", F.relu(h), padding=1)
+    h = _conv(sd, name + ".block.7", F.relu(h))
+    return idp + h
+
+
+def _dec_block(sd: SD, name: str, x):
+    """vqvae_model.py:147-166 (1x1, 3x3, 3x3, 3x3)."""
+    idp = _conv(sd, name + ".id_path", x) if (name + ".id_path.weight") in sd else x
+    h = _conv(sd, name + ".block.1", F.relu(x))
+    h = _conv(sd, name + ".block.3", F.relu(h), padding=1)
+    h = _conv(sd, name + ".block.5", F.relu(h), padding=1)
+    h = _conv(sd, name + ".block.7", F.relu(h), padding=1)
+    return idp + h
+
+
+def vqvae_down_ratio(sd: SD) -> int:
+    return 4 if "encoder.1.running_mean" in sd else 8
+
+
+def vqvae_encoder(sd: SD, x: torch.Tensor) -> torch.Tensor:
+    """x [N,C,H,W] -> z_e [N,D,h,w].  f4: vqvae_model.py:172-179, f8: :192-202."""
+    if vqvae_down_ratio(sd) == 4:
+        h = F.relu(_bn(sd, "encoder.1", _conv(sd, "encoder.0", x, stride=2, padding=1)))
+        h = _conv(sd, "encoder.3", h, stride=2, padding=1)
+        h = _res_block(sd, "encoder.4", h)
+        return _res_block(sd, "encoder.5", h)
+    h = _conv(sd, "encoder.0", x, padding=3)
+    h = F.max_pool2d(_enc_block(sd, "encoder.1", h), 2)
+    h = F.max_pool2d(_enc_block(sd, "encoder.3", h), 2)
+    h = F.max_pool2d(_enc_block(sd, "encoder.5", h), 2)
+    return F.relu(_enc_block(sd, "encoder.7", h))
+
+
+def vq_distances(z_flat: torch.Tensor, codebook: torch.Tensor) -> torch.Tensor:
+    """vqvae_model.py:14-19: ||c||^2 + ||z||^2 - 2 z.c^T through one addmm."""
+    c_sqr = torch.sum(codebook ** 2, dim=1)
+    z_sqr = torch.sum(z_flat ** 2, dim=1, keepdim=True)
+    return torch.addmm(c_sqr + z_sqr, z_flat, codebook.t(), alpha=-2.0, beta=1.0)
+
+
+def vq_argmin(z_flat: torch.Tensor, codebook: torch.Tensor) -> torch.Tensor:
+    """vqvae_model.py:21: indices of the row minima (int64)."""
+    return torch.min(vq_distances(z_flat, codebook), dim=1)[1]
+
+
+def vqvae_quantize(sd: SD, z_e: torch.Tensor) -> torch.Tensor:
+    """VQEmbedding.forward (vqvae_model.py:93-96): NCHW -> NHWC -> nearest code, int64 [N,h,w]."""
+    cb = sd["codebook.embedding.weight"]
+    z = z_e.permute(0, 2, 3, 1).contiguous()
+    return vq_argmin(z.view(-1, cb.shape[1]), cb).view(*z.shape[:-1])
+
+
+def vqvae_encode(sd: SD, x: torch.Tensor) -> torch.Tensor:
+    """VectorQuantizedVAE.encode (vqvae_model.py:233-237)."""
+    return vqvae_quantize(sd, vqvae_encoder(sd, x))
+
+
+def vqvae_decode(sd: SD, latents: torch.Tensor) -> torch.Tensor:
+    """VectorQuantizedVAE.decode (vqvae_model.py:239-242); f4 decoder :180-189, f8 :203-214."""
+    z = F.embedding(latents, sd["codebook.embedding.weight"]).permute(0, 3, 1, 2)
+    if vqvae_down_ratio(sd) == 4:
+        h = _res_block(sd, "decoder.0", z.contiguous())
+        h = F.relu(_res_block(sd, "decoder.1", h))
+        h = F.conv_transpose2d(h, sd["decoder.3.weight"], sd["decoder.3.bias"], stride=2, padding=1)
+        h = F.relu(_bn(sd, "decoder.4", h))
+        h = F.conv_transpose2d(h, sd["decoder.6.weight"], sd["decoder.6.bias"], stride=2, padding=1)
+        return torch.tanh(h)
+    up = lambda t: F.interpolate(t, scale_factor=2, mode="nearest")
+    h = up(_dec_block(sd, "decoder.0", z))
+    h = up(_dec_block(sd, "decoder.2", h))
+    h = up(_dec_block(sd, "decoder.4", h))
+    h = _dec_block(sd, "decoder.6", h)
+    return torch.tanh(_conv(sd, "decoder.8", F.relu(h)))
+
+
+def _sub(sd: SD, prefix: str) -> SD:
+    n = len(prefix)
+    return {k[n:]: v for k, v in sd.items() if k.startswith(prefix)}
+
+
+# --------------------------------------------------------------------------------------
+# transformer pieces  (mage_model.py)
+# --------------------------------------------------------------------------------------
+def _mha(sd: SD, name: str, q, k, v, n_head: int, attn_mask=None, key_padding_mask=None):
+    """nn.MultiheadAttention.forward, seq-first (batch_first=False everywhere in the
+    reference: mage_model.py:20,75,193-199), need_weights=False -> SDPA."""
+    return F.multi_head_attention_forward(
+        q, k, v, q.shape[-1], n_head,
+        sd[name + ".in_proj_weight"], sd[name + ".in_proj_bias"], None, None, False, 0.0,
+        sd[name + ".out_proj.weight"], sd[name + ".out_proj.bias"],
+        training=False, key_padding_mask=key_padding_mask, need_weights=False, attn_mask=attn_mask)[0]
+
+
+def _ln(sd: SD, name: str, x, eps=1e-5):
+    return F.layer_norm(x, (x.shape[-1],), sd[name + ".weight"], sd[name + ".bias"], eps)
+
+
+def _quick_gelu(x):
+    return x * torch.sigmoid(1.702 * x)  # mage_model.py:11-13
+
+
+def _mlp(sd: SD, name: str, x):
+    h = F.linear(x, sd[name + ".c_fc.weight"], sd[name + ".c_fc.bias"])
+    return F.linear(_quick_gelu(h), sd[name + ".c_proj.weight"], sd[name + ".c_proj.bias"])
+
+
+def text_encoder(sd: SD, text: torch.Tensor, padding_idx: int = 0) -> torch.Tensor:
+    """TransformerTextEncoder.forward (mage_model.py:223-250).  text i64 [B,T] -> [B,T,C]."""
+    p = "text_encoder."
+    width = sd[p + "token_embedding.weight"].shape[1]
+    n_head = width // 32
+    B, T = text.shape
+    text_length = (text != padding_idx).float().sum(-1)
+    pos = torch.arange(T, dtype=text.dtype).unsqueeze(0).expand(B, T)
+    x = F.embedding(text, sd[p + "token_embedding.weight"], padding_idx=padding_idx)
+    x = _ln(sd, p + "layer_norm", x + F.embedding(pos, sd[p + "positions.weight"]), eps=1e-8)
+    x = x * (text != padding_idx).unsqueeze(-1).type(x.dtype)
+    caption_mask = text_length.unsqueeze(1) < torch.ones_like(text).cumsum(dim=1)  # True = padded key
+    x = x.permute(1, 0, 2)
+    i = 0
+    while (p + f"transformer.layers.{i}.linear1.weight") in sd:  # post-norm nn.TransformerEncoderLayer, exact GELU
+        lp = p + f"transformer.layers.{i}"
+        x = _ln(sd, lp + ".norm1", x + _mha(sd, lp + ".self_attn", x, x, x, n_head, key_padding_mask=caption_mask))
+        h = F.linear(F.gelu(F.linear(x, sd[lp + ".linear1.weight"], sd[lp + ".linear1.bias"])),
+                     sd[lp + ".linear2.weight"], sd[lp + ".linear2.bias"])
+        x = _ln(sd, lp + ".norm2", x + h)
+        i += 1
+    x = _ln(sd, p + "ln_text_final", x.permute(1, 0, 2))
+    return F.linear(x, sd[p + "text_projection.weight"], sd[p + "text_projection.bias"])
+
+
+def ma_encoder(sd: SD, q: torch.Tensor, kv: torch.Tensor) -> torch.Tensor:
+    """MAEncoder.forward (mage_model.py:114-117) with the shipped TransformerBlock line 92:
+    no LayerNorm on q/kv and no key-padding mask.  q [HW,B,C], kv [T,B,C] seq-first."""
+    i = 0
+    x = q
+    while f"ma_encoder.blocks.{i}.attn.in_proj_weight" in sd:
+        p = f"ma_encoder.blocks.{i}"
+        x = x + _mha(sd, p + ".attn", x, kv, kv, x.shape[-1] // 32)
+        x = x + _mlp(sd, p + ".mlp", _ln(sd, p + ".ln_2", x))
+        i += 1
+    return x
+
+
+def adain(sd: SD, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """ADAIN2D.forward (mage_model.py:309-314): InstanceNorm(x) * conv_mu(y) + conv_var(y)."""
+    out = F.instance_norm(x, eps=1e-5)
+    g = _conv(sd, "adain.conv_mu.1", _conv(sd, "adain.conv_mu.0", y, padding=1), padding=1)
+    b = _conv(sd, "adain.conv_var.1", _conv(sd, "adain.conv_var.0", y, padding=1), padding=1)
+    return g * out + b
+
+
+def axial_block(sd: SD, name: str, x: torch.Tensor, axial_dim: int, attn_mask=None) -> torch.Tensor:
+    """AxialAttentionBlock.forward (mage_model.py:35-53) on x [B,L,H,W,C]: move `axial_dim`
+    next to the channel dim, flatten the rest into the MHA batch, pre-LN attention + MLP."""
+    nd = x.dim()
+    rest = [d for d in range(nd) if d not in (axial_dim, nd - 1)]
+    perm = rest + [axial_dim, nd - 1]
+    inv = [perm.index(d) for d in range(nd)]
+    xp = x.permute(perm).contiguous()
+    shp = xp.shape
+    s = xp.view(-1, shp[-2], shp[-1]).transpose(0, 1)  # [S, N, C]
+    u = _ln(sd, name + ".ln_1", s)
+    s = s + _mha(sd, name + ".attn", u, u, u, shp[-1] // 32, attn_mask=attn_mask)
+    s = s + _mlp(sd, name + ".mlp", _ln(sd, name + ".ln_2", s))
+    return s.transpose(0, 1).reshape(shp).permute(inv).contiguous()
+
+
+def flat_axial_decoder(sd: SD, motion: torch.Tensor, imgs: torch.Tensor, return_hidden: bool = False):
+    """FlatAxialDecoder.forward (mage_model.py:374-390).  motion [B,H,W,C] takes temporal
+    position 0, imgs [B,F,H,W,C] positions 1..F; logits come from positions 1.. only."""
+    p = "generate_model."
+    x = torch.cat([F.linear(motion, sd[p + "context_linear.weight"], sd[p + "context_linear.bias"]).unsqueeze(1),
+                   F.linear(imgs, sd[p + "in_linear.weight"], sd[p + "in_linear.bias"])], 1)
+    Lmax = sd[p + "T_positional_embedding"].shape[0]
+    assert x.shape[1] == Lmax, "reference adds the full T_positional_embedding (needs F == frames_length-1)"
+    x = x + sd[p + "T_positional_embedding"]
+    mask = torch.full((Lmax, Lmax), float("-inf")).triu_(1)  # mage_model.py:367-372
+    i = 0
+    while (p + f"blocks.{i}.ln_1.weight") in sd:
+        x = axial_block(sd, p + f"blocks.{i}", x, i % 3 + 1, mask if i % 3 == 0 else None)
+        i += 1
+    logits = F.linear(x[:, 1:], sd[p + "out.weight"], sd[p + "out.bias"])
+    return (logits, x) if return_hidden else logits
+
+
+def token_features(sd: SD, x_emb: torch.Tensor) -> torch.Tensor:
+    """3x3 bias-free conv over token embeddings + H/W positional embeddings
+    (mage_model.py:648-649 / :674-676).  x_emb [B,F,C,H,W] -> [B,F,H,W,C]."""
+    B, Fr, C, H, W = x_emb.shape
+    f = F.conv2d(x_emb.reshape(-1, C, H, W), sd["conv.0.weight"], None, padding=1)
+    f = f.view(B, Fr, C, H, W).permute(0, 1, 3, 4, 2).contiguous()
+    return f + sd["H_positional_embedding"] + sd["W_positional_embedding"]
+
+
+def embed_tokens(sd: SD, tok: torch.Tensor) -> torch.Tensor:
+    """visual_token_embedding gather, [..,H,W] i64 -> [..,C,H,W] (mage_model.py:644,682)."""
+    e = F.embedding(tok, sd["visual_token_embedding.weight"])
+    nd = e.dim()
+    return e.permute(*range(nd - 3), nd - 1, nd - 3, nd - 2).contiguous()
+
+
+def motion_anchor(sd: SD, tok0: torch.Tensor, text: torch.Tensor, speed: Optional[torch.Tensor],
+                  noise: Optional[torch.Tensor], trace: Optional[dict] = None) -> torch.Tensor:
+    """Prelude of autoregressive_generate (mage_model.py:644-668).  tok0 [B,H,W] i64,
+    noise [B,64,H,W] or None (randomness=False) -> anchor [B,H,W,C]."""
+    B, H, W = tok0.shape
+    x_emb = embed_tokens(sd, tok0).unsqueeze(1)
+    C = x_emb.shape[2]
+    first = token_features(sd, x_emb)[:, 0].reshape(B, -1, C).permute(1, 0, 2).contiguous()
+    t = text_encoder(sd, text).permute(1, 0, 2).contiguous()
+    a = ma_encoder(sd, first, t).permute(1, 0, 2).contiguous().view(B, H, W, C)
+    if trace is not None:
+        trace["text_emb"], trace["first_img"], trace["anchor_ma"] = t, first, a
+    if noise is not None:
+        y = F.conv2d(noise, sd["conv_d2.weight"], None, padding=1)
+        a = adain(sd, a.permute(0, 3, 1, 2).contiguous(), y).permute(0, 2, 3, 1).contiguous()
+    if speed is not None:
+        a = a + (speed.view(B, 1) @ sd["speed_embedding"]).unsqueeze(1).unsqueeze(1)
+    if trace is not None:
+        trace["anchor"] = a
+    return a
+
+
+def _top2_gap(logits: torch.Tensor) -> torch.Tensor:
+    t = torch.topk(logits, 2, dim=-1)[0]
+    return t[..., 0] - t[..., 1]
+
+
+@torch.no_grad()
+def generate(sd: SD, batch: Dict[str, torch.Tensor], noise: Optional[torch.Tensor] = None,
+             trace: Optional[dict] = None) -> torch.Tensor:
+    """MAGE.autoregressive_generate in the reference's own evaluation order
+    (mage_model.py:641-693).  Returns [B,L,C,H,W]; `trace` (if given) receives tokens
+    [B,L-1,h,w], the final-step logit top1-top2 gaps and intermediates."""
+    fsd = _sub(sd, "first_stage_model.")
+    L = sd["generate_model.T_positional_embedding"].shape[0]
+    img0 = batch["images"][:, 0]
+    tok0 = vqvae_encode(fsd, img0)
+    anchor = motion_anchor(sd, tok0, batch["text"], batch.get("speed"), noise, trace)
+    x_emb = embed_tokens(sd, tok0).unsqueeze(1)
+    inp = x_emb.repeat(1, L - 1, 1, 1, 1)
+    prediction = None
+    for i in range(L - 1):
+        prediction = flat_axial_decoder(sd, anchor, token_features(sd, inp))
+        if i != L - 2:
+            ids = torch.max(prediction, -1)[1]
+            inp[:, i + 1] = embed_tokens(sd, ids[:, i])
+    tokens = torch.max(prediction, -1)[1]
+    if trace is not None:
+        trace["tok0"], trace["tokens"], trace["gap"] = tok0, tokens, _top2_gap(prediction)
+    B = tokens.shape[0]
+    pix = vqvae_decode(fsd, tokens.view(-1, *tokens.shape[-2:]))
+    pix = pix.view(B, L - 1, *pix.shape[1:])
+    return torch.cat([batch["images"][:, 0:1], pix], 1)
+
+
+# --------------------------------------------------------------------------------------
+# incremental evaluation order
+# --------------------------------------------------------------------------------------
+def _heads(t: torch.Tensor, n_head: int) -> torch.Tensor:
+    return t.view(*t.shape[:-1], n_head, t.shape[-1] // n_head)
+
+
+def _block_step(sd: SD, name: str, x: torch.Tensor, kind: int, cache: Optional[list]) -> torch.Tensor:
+    """One axial block on ONE temporal position.  x [B,H,W,C]; kind 0 = temporal (attend
+    the cache of positions 0..p), 1 = along H, 2 = along W."""
+    C = x.shape[-1]
+    nh = C // 32
+    u = _ln(sd, name + ".ln_1", x)
+    qkv = F.linear(u, sd[name + ".attn.in_proj_weight"], sd[name + ".attn.in_proj_bias"])
+    q, k, v = [_heads(t, nh) for t in qkv.split(C, dim=-1)]  # [B,H,W,nh,32]
+    if kind == 0:
+        cache.append((k, v))
+        K = torch.stack([c[0] for c in cache], dim=-2)  # [B,H,W,nh,S,32]
+        V = torch.stack([c[1] for c in cache], dim=-2)
+        a = F.scaled_dot_product_attention(q.unsqueeze(-2), K, V).squeeze(-2)
+    else:
+        ax = 1 if kind == 1 else 2  # attended spatial dim of [B,H,W,nh,32]
+        mv = lambda t: t.movedim(ax, -2)  # [B,other,nh,S,32]
+        a = F.scaled_dot_product_attention(mv(q), mv(k), mv(v)).movedim(-2, ax)
+    a = a.reshape(*x.shape)
+    x = x + F.linear(a, sd[name + ".attn.out_proj.weight"], sd[name + ".attn.out_proj.bias"])
+    return x + _mlp(sd, name + ".mlp", _ln(sd, name + ".ln_2", x))
+
+
+@torch.no_grad()
+def generate_incremental(sd: SD, batch: Dict[str, torch.Tensor], noise: Optional[torch.Tensor] = None,
+                         trace: Optional[dict] = None, frames_length: Optional[int] = None) -> torch.Tensor:
+    """Same result as `generate`, O(L) work: per step only the newest temporal position is
+    evaluated; temporal blocks (i % 3 == 0) keep K/V of earlier positions."""
+    p = "generate_model."
+    fsd = _sub(sd, "first_stage_model.")
+    Tp = sd[p + "T_positional_embedding"]
+    L = frames_length or Tp.shape[0]
+    n_blocks = 0
+    while (p + f"blocks.{n_blocks}.ln_1.weight") in sd:
+        n_blocks += 1
+    tok0 = vqvae_encode(fsd, batch["images"][:, 0])
+    anchor = motion_anchor(sd, tok0, batch["text"], batch.get("speed"), noise, trace)
+    caches = [[] for _ in range(n_blocks)]
+
+    def step(pos: int, x: torch.Tensor) -> torch.Tensor:
+        x = x + Tp[pos]
+        for i in range(n_blocks):
+            x = _block_step(sd, p + f"blocks.{i}", x, i % 3, caches[i])
+        return x
+
+    step(0, F.linear(anchor, sd[p + "context_linear.weight"], sd[p + "context_linear.bias"]))
+    tok = tok0
+    toks, gaps = [], []
+    for j in range(L - 1):
+        f = token_features(sd, embed_tokens(sd, tok).unsqueeze(1))[:, 0]
+        h = step(j + 1, F.linear(f, sd[p + "in_linear.weight"], sd[p + "in_linear.bias"]))
+        logits = F.linear(h, sd[p + "out.weight"], sd[p + "out.bias"])
+        tok = torch.max(logits, -1)[1]
+        toks.append(tok)
+        gaps.append(_top2_gap(logits))
+    tokens = torch.stack(toks, 1)
+    if trace is not None:
+        trace["tok0"], trace["tokens"], trace["gap"] = tok0, tokens, torch.stack(gaps, 1)
+    B = tokens.shape[0]
+    pix = vqvae_decode(fsd, tokens.view(-1, *tokens.shape[-2:]))
+    pix = pix.view(B, L - 1, *pix.shape[1:])
+    return torch.cat([batch["images"][:, 0:1], pix], 1)

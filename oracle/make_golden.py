@@ -1,0 +1,137 @@
+"""TEST INFRASTRUCTURE ONLY -- generate tests/golden/* by running the UNMODIFIED reference
+(/root/reference, imported through oracle/ref_shims.py) on seeded synthetic inputs.
+
+Run in the authoring container (the GPU box has no /root/reference):
+
+    python -m oracle.make_golden codebooks   # conditioned codebook fixtures (uses the oracle encoder)
+    python -m oracle.make_golden goldens     # reference outputs -> tests/golden/*.npz
+
+Every case is fully determined by (family, frames_length, batch, seeds) recorded inside the
+.npz, so tests can rebuild the checkpoint/batch with mage_b200.synthetic and compare.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+from mage_b200 import synthetic as syn
+from oracle import mage_oracle as orc
+from oracle import ref_shims
+
+GOLDEN_DIR = syn.GOLDEN_DIR
+
+# (name, family, frames_length, batch, text_len, padded, with_speed, noise_seed)
+CASES = [
+    ("cater_L4_b2", "caterv2", 4, 2, 12, False, True, 99),
+    ("cater_L4_b2_pad", "caterv2", 4, 2, 14, True, True, 98),
+    ("caterv1_L3_b1_norand", "caterv1", 3, 1, 10, False, False, None),
+    ("mnist_L5_b2", "mnist", 5, 2, 9, False, True, None),
+    ("cater_L10_b1", "caterv2", 10, 1, 20, False, True, 97),
+]
+
+
+def farthest_point_sample(x: torch.Tensor, k: int) -> torch.Tensor:
+    """Greedy farthest-point sampling in fp64 (SURVEY.md H1 recipe)."""
+    x = x.double()
+    n = x.shape[0]
+    chosen = [int(torch.argmax((x - x.mean(0)).pow(2).sum(1)))]
+    d = (x - x[chosen[0]]).pow(2).sum(1)
+    for _ in range(k - 1):
+        i = int(torch.argmax(d))
+        chosen.append(i)
+        d = torch.minimum(d, (x - x[i]).pow(2).sum(1))
+    return torch.tensor(chosen)
+
+
+def make_codebooks():
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    for family in ("caterv2", "mnist"):
+        params = syn.model_params(family)
+        fs = params["first_stage_config"]["params"]
+        sd = syn.make_vqvae_state_dict(fs, conditioned=False)
+        C, res = fs["input_dim"], 16 * fs["down_ratio"]
+        lo, hi = (-0.5, 0.5) if fs["down_ratio"] == 4 else (-1.0, 1.0)
+        imgs = syn.structured_images(16, C, res, seed=555, lo=lo, hi=hi)
+        with torch.no_grad():
+            z = orc.vqvae_encoder(sd, imgs).permute(0, 2, 3, 1).reshape(-1, sd["codebook.embedding.weight"].shape[1])
+        idx = farthest_point_sample(z, fs["K"])
+        cb = z[idx].half()  # fp16-representable values: the fixture is exact in any float width
+        d = torch.cdist(cb.double(), cb.double()) + torch.eye(cb.shape[0], dtype=torch.float64) * 1e9
+        print(f"{family}: codebook {tuple(cb.shape)} min inter-code distance {d.min():.4f} |z| mean {z.norm(dim=1).mean():.3f}")
+        np.save(os.path.join(GOLDEN_DIR, f"codebook_f{fs['down_ratio']}.npy"), cb.numpy())
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def make_goldens():
+    assert ref_shims.reference_available(), "needs /root/reference"
+    out = {}
+    # ---- VQ-VAE round trips (config C1 and the f8 equivalent) ----
+    for family in ("mnist", "caterv2"):
+        params = syn.model_params(family)
+        fs = params["first_stage_config"]["params"]
+        sd = syn.make_vqvae_state_dict(fs)
+        ref = ref_shims.build_reference_vqvae(fs, sd)
+        C, res = fs["input_dim"], 16 * fs["down_ratio"]
+        lo, hi = (-0.5, 0.5) if fs["down_ratio"] == 4 else (-1.0, 1.0)
+        x = syn.structured_images(2, C, res, seed=4242, lo=lo, hi=hi)
+        with torch.no_grad():
+            idx = ref.encode(x.clone())
+            rec = ref.decode(idx)
+            z = ref.encoder(x.clone()).permute(0, 2, 3, 1).reshape(-1, sd["codebook.embedding.weight"].shape[1])
+            dist = orc.vq_distances(z, sd["codebook.embedding.weight"])
+            top2 = torch.topk(dist, 2, dim=1, largest=False)[0]
+        np.savez_compressed(os.path.join(GOLDEN_DIR, f"vqvae_f{fs['down_ratio']}.npz"),
+                            family=family, image_seed=4242, idx=_np(idx).astype(np.int16),
+                            rec=_np(rec), vq_gap=_np(top2[:, 1] - top2[:, 0]).astype(np.float32),
+                            z_sample=_np(z[::37, ::13]))
+        print(f"vqvae {family}: {idx.unique().numel()} codes used, min VQ gap {float((top2[:,1]-top2[:,0]).min()):.4g}")
+
+    # ---- MAGE sampling ----
+    for name, family, L, B, T, padded, with_speed, noise_seed in CASES:
+        params = syn.model_params(family, frames_length=L, randomness=noise_seed is not None)
+        sd = syn.make_mage_state_dict(params)
+        batch = syn.make_batch(params, B, seed=1234, text_len=T, padded=padded, with_speed=with_speed)
+        model = ref_shims.build_reference_mage(params, sd)
+        captured = {}
+        # capture the final prediction (for the top1-top2 gaps) without touching reference code
+        h = model.generate_model.register_forward_hook(lambda m, i, o: captured.__setitem__("pred", o.detach()))
+        t0 = time.time()
+        with torch.no_grad():
+            if noise_seed is not None:
+                torch.manual_seed(noise_seed)  # reference draws torch.randn([B,64,H,W]) on the CPU generator (:661)
+            video = model.autoregressive_generate({k: v.clone() for k, v in batch.items()})
+        dt = time.time() - t0
+        h.remove()
+        pred = captured["pred"]
+        tokens = torch.max(pred, -1)[1]
+        top2 = torch.topk(pred, 2, dim=-1)[0]
+        with torch.no_grad():
+            tok0 = model.first_stage_encode(batch["images"][:, 0:1])[:, 0]
+        rec = dict(family=family, frames_length=L, batch=B, text_len=T, padded=padded, with_speed=with_speed,
+                   noise_seed=-1 if noise_seed is None else noise_seed,
+                   tok0=_np(tok0).astype(np.int16), tokens=_np(tokens).astype(np.int16),
+                   gap=_np(top2[..., 0] - top2[..., 1]).astype(np.float32),
+                   logits_sample=_np(pred[:, :, ::5, ::5, ::16]).astype(np.float32))
+        # pixels: full for the small cases, strided for the long one
+        gen = video[:, 1:]
+        rec["pixels"] = _np(gen if L <= 5 else gen[:, :, :, ::4, ::4]).astype(np.float32)
+        rec["pixel_stride"] = 1 if L <= 5 else 4
+        np.savez_compressed(os.path.join(GOLDEN_DIR, f"mage_{name}.npz"), **rec)
+        print(f"mage {name}: {dt:.1f}s, tokens {tuple(tokens.shape)}, {tokens.unique().numel()} codes, "
+              f"min logit gap {float(rec['gap'].min()):.3g}, logit std {float(pred.std()):.3f}")
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(os.cpu_count())
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what in ("codebooks", "all"):
+        make_codebooks()
+    if what in ("goldens", "all"):
+        make_goldens()

@@ -1,0 +1,129 @@
+"""TEST INFRASTRUCTURE ONLY.  Import the *unmodified* reference (/root/reference) in this
+container so the oracle can be pinned against it and golden vectors can be generated.
+
+The reference's `modules/mage_model.py` imports three packages that are not installed
+here (`pytorch_transformers`, `omegaconf`, `ldm`).  None of them is touched
+on the VQ sampling path, so three empty shims in `sys.modules` are enough to run
+`MAGE.autoregressive_generate` as shipped.  /root/reference does not exist on the GPU box:
+nothing outside oracle/make_golden.py and the `needs_reference` CPU tests may call this.
+"""
+from __future__ import annotations
+
+import importlib
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("MAGE_REFERENCE_ROOT", "/root/reference")
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "modules", "mage_model.py"))
+
+
+class _DictConfig(dict):
+    """Hashable dict: utils/util.py:53 puts configs in a *set literal* before merging."""
+    __hash__ = object.__hash__  # type: ignore[assignment]
+
+
+def _install_shims() -> None:
+    if "pytorch_transformers" not in sys.modules:
+        sys.modules["pytorch_transformers"] = types.ModuleType("pytorch_transformers")
+    if "omegaconf" not in sys.modules:
+        m = types.ModuleType("omegaconf")
+
+        class OmegaConf:  # noqa: D401 - only .merge is used (utils/util.py:53)
+            @staticmethod
+            def merge(*cfgs):
+                out = {}
+                # key sets never overlap in the reference's callers (mage_model.py:475-477)
+                for c in cfgs:
+                    out.update(dict(c))
+                return out
+
+        m.OmegaConf = OmegaConf
+        m.DictConfig = _DictConfig
+        sys.modules["omegaconf"] = m
+    if "ldm" not in sys.modules:
+        ldm = types.ModuleType("ldm")
+        models = types.ModuleType("ldm.models")
+        ae = types.ModuleType("ldm.models.autoencoder")
+
+        class DiagonalGaussianDistribution:  # only used in an isinstance test (mage_model.py:543)
+            pass
+
+        ae.DiagonalGaussianDistribution = DiagonalGaussianDistribution
+        ldm.models = models
+        models.autoencoder = ae
+        sys.modules["ldm"] = ldm
+        sys.modules["ldm.models"] = models
+        sys.modules["ldm.models.autoencoder"] = ae
+
+
+def load_reference():
+    """Returns (mage_model module, vqvae_model module) of the real reference."""
+    if not reference_available():
+        raise RuntimeError(f"reference not found at {REFERENCE_ROOT}")
+    _install_shims()
+    # the reference addresses its packages as top-level `modules.*` / `utils.*`; this repo
+    # has same-named drop-in packages, so temporarily make /root/reference win.
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "modules" or k.startswith("modules.")
+             or k == "utils" or k.startswith("utils.")}
+    sys.path.insert(0, REFERENCE_ROOT)
+    try:
+        mm = importlib.import_module("modules.mage_model")
+        vq = importlib.import_module("modules.vqvae_model")
+        ref_mods = {k: sys.modules[k] for k in list(sys.modules) if k == "modules" or k.startswith("modules.")
+                    or k == "utils" or k.startswith("utils.")}
+    finally:
+        sys.path.remove(REFERENCE_ROOT)
+        for k in list(sys.modules):
+            if k == "modules" or k.startswith("modules.") or k == "utils" or k.startswith("utils."):
+                del sys.modules[k]
+        sys.modules.update(saved)
+    # keep the reference modules alive under private names (their functions still work)
+    for k, v in ref_mods.items():
+        sys.modules["_mage_reference." + k] = v
+    return mm, vq
+
+
+def to_dictconfig(obj):
+    """Nested plain dict -> nested hashable DictConfig (what the shimmed util expects)."""
+    if isinstance(obj, dict):
+        return _DictConfig({k: to_dictconfig(v) for k, v in obj.items()})
+    return obj
+
+
+def build_reference_mage(params: dict, state_dict: dict):
+    """Instantiate the reference's MAGE with `params`, load the synthetic sampling subset
+    (strict=False: the train-only conv3d/conv_mu2/conv_var2 keep their default init)."""
+    import torch
+
+    mm, _ = load_reference()
+    # instantiate_from_config inside the reference resolves `modules.*` targets by import;
+    # expose the reference modules under those names for the duration of construction.
+    saved = {k: sys.modules.get(k) for k in ("modules", "modules.mage_model", "modules.vqvae_model", "utils", "utils.util")}
+    for k in saved:
+        sys.modules[k] = sys.modules["_mage_reference." + k]
+    try:
+        torch.manual_seed(0)
+        model = mm.MAGE(**to_dictconfig(params))
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    missing, unexpected = model.load_state_dict(state_dict, strict=False)
+    assert not unexpected, unexpected
+    bad = [k for k in missing if not (k.startswith("conv3d.") or k.startswith("conv_mu2") or k.startswith("conv_var2"))]
+    assert not bad, f"synthetic checkpoint misses sampling-path keys: {bad}"
+    return model.eval()
+
+
+def build_reference_vqvae(fs_params: dict, state_dict: dict):
+    _, vq = load_reference()
+    p = {k: v for k, v in fs_params.items() if k != "ckpt_path"}
+    model = vq.VectorQuantizedVAE(**p)
+    model.load_state_dict(state_dict, strict=True)
+    return model.eval()

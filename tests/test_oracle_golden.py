@@ -1,0 +1,85 @@
+"""CPU: pin the oracle (oracle/mage_oracle.py) to the golden vectors produced by the
+unmodified reference (oracle/make_golden.py), and -- where /root/reference exists -- to the
+reference itself."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from mage_b200 import synthetic as syn
+from oracle import mage_oracle as orc
+from oracle import ref_shims
+from tests.helpers import GOLDEN_DIR, MAGE_CASES, load_case, tie_aware_token_check
+
+
+@pytest.mark.parametrize("ratio", [4, 8])
+def test_vqvae_round_trip_matches_reference_golden(ratio):
+    g = np.load(os.path.join(GOLDEN_DIR, f"vqvae_f{ratio}.npz"))
+    params = syn.model_params(str(g["family"]))
+    fs = params["first_stage_config"]["params"]
+    sd = syn.make_vqvae_state_dict(fs)
+    lo, hi = (-0.5, 0.5) if ratio == 4 else (-1.0, 1.0)
+    x = syn.structured_images(2, fs["input_dim"], 16 * ratio, seed=int(g["image_seed"]), lo=lo, hi=hi)
+    with torch.no_grad():
+        idx = orc.vqvae_encode(sd, x)
+        rec = orc.vqvae_decode(sd, idx)
+    gap = g["vq_gap"].reshape(idx.shape)
+    neq = idx.numpy() != g["idx"]
+    assert not (neq & (gap >= 1e-4)).any(), "VQ indices differ from the reference away from ties"
+    if not neq.any():
+        np.testing.assert_allclose(rec.numpy(), g["rec"], rtol=0, atol=2e-6)
+
+
+@pytest.mark.parametrize("name", MAGE_CASES)
+def test_generate_matches_reference_golden(name):
+    params, sd, batch, noise, g = load_case(name)
+    tr = {}
+    video = orc.generate(sd, batch, noise, tr)
+    assert np.array_equal(tr["tok0"].numpy(), g["tok0"]), "first-frame VQ indices differ from the reference"
+    _, excused = tie_aware_token_check(tr["tokens"].numpy(), g["tokens"], g["gap"], eps=1e-5)
+    if excused == 0:
+        s = int(g["pixel_stride"])
+        pix = video[:, 1:][..., ::s, ::s].numpy()
+        np.testing.assert_allclose(pix, g["pixels"], rtol=0, atol=2e-6)
+        np.testing.assert_allclose(tr["gap"].numpy(), g["gap"], rtol=0, atol=2e-5)
+
+
+@pytest.mark.parametrize("name", ["cater_L4_b2_pad", "mnist_L5_b2", "cater_L10_b1"])
+def test_incremental_order_equals_reference_order(name):
+    params, sd, batch, noise, g = load_case(name)
+    tr = {}
+    video = orc.generate_incremental(sd, batch, noise, tr)
+    _, excused = tie_aware_token_check(tr["tokens"].numpy(), g["tokens"], g["gap"], eps=1e-5)
+    if excused == 0:
+        s = int(g["pixel_stride"])
+        np.testing.assert_allclose(video[:, 1:][..., ::s, ::s].numpy(), g["pixels"], rtol=0, atol=2e-6)
+
+
+def test_incremental_can_run_longer_than_checkpoint_positions_is_rejected():
+    params, sd, batch, noise, _ = load_case("caterv1_L3_b1_norand")
+    with pytest.raises(IndexError):
+        orc.generate_incremental(sd, batch, noise, frames_length=5)
+
+
+@pytest.mark.needs_reference
+def test_oracle_bit_identical_to_live_reference():
+    params = syn.model_params("caterv2", frames_length=3)
+    sd = syn.make_mage_state_dict(params)
+    batch = syn.make_batch(params, 1, seed=77, text_len=9)
+    model = ref_shims.build_reference_mage(params, sd)
+    assert set(sd) <= set(model.state_dict()), "synthetic checkpoint has keys the reference does not"
+    torch.manual_seed(5)
+    with torch.no_grad():
+        ref = model.autoregressive_generate({k: v.clone() for k, v in batch.items()})
+    torch.manual_seed(5)
+    noise = torch.randn(1, 64, 16, 16)
+    out = orc.generate(sd, batch, noise)
+    assert torch.equal(ref, out)
+
+
+@pytest.mark.needs_reference
+def test_synthetic_state_dict_loads_strict_into_reference_vqvae():
+    for family in ("mnist", "caterv2"):
+        fs = syn.model_params(family)["first_stage_config"]["params"]
+        ref_shims.build_reference_vqvae(fs, syn.make_vqvae_state_dict(fs))
