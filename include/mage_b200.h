@@ -1,0 +1,156 @@
+/*
+ * mage_b200 -- C ABI of libmage_sm100.so: hand-written sm_100a kernels for the MAGE
+ * autoregressive video-token sampling path.
+ *
+ * The reference (Youncy-Hu/MAGE) has no FFI: its hot path is Python calling torch.nn
+ * modules.  Each entry point below replaces the torch call(s) cited beside
+ * it (file:line in /root/reference); INTEGRATION.md shows the ctypes binding a maintainer
+ * of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch allocator); nothing is
+ *     allocated, freed or cached by the library, so it is re-entrant;
+ *   - activations are channels-last fp32 (`[rows, C]`, images `[N,H,W,C]`); token / code
+ *     indices are int64 (what the reference's `torch.max`/`torch.min` return);
+ *   - kernels are enqueued on `stream` (a cudaStream_t passed as void*) and return at once;
+ *   - return value: 0 on success, a positive cudaError_t from the launch, or a negative
+ *     MAGE_E* code for an unsupported argument.  Nothing throws across the ABI;
+ *   - there is no CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef MAGE_B200_H
+#define MAGE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAGE_EINVAL (-1)   /* shape / alignment not supported */
+#define MAGE_ENOTSUP (-2)  /* variant not built */
+
+/* epilogue activations */
+#define MAGE_ACT_NONE 0
+#define MAGE_ACT_RELU 1
+#define MAGE_ACT_QUICKGELU 2 /* x*sigmoid(1.702x): mage_model.py:11-13 */
+#define MAGE_ACT_GELU 3      /* exact erf GELU: nn.TransformerEncoderLayer(activation="gelu"), mage_model.py:192-199 */
+#define MAGE_ACT_TANH 4      /* vqvae_model.py:188,213 */
+
+/* flags OR-ed into `act` of mage_gemm_f32 / mage_conv2d_nhwc_f32 */
+#define MAGE_ACT_POST_RES 0x100 /* apply the activation after the residual add: act(x + bias + residual) */
+#define MAGE_RES_RELU 0x200     /* read the residual through a ReLU (in-place ReLU skip of ResBlock, vqvae_model.py:114-124) */
+
+/* GEMM back ends (mage_set_gemm_backend) */
+#define MAGE_GEMM_SIMT 0     /* fp32 FFMA register-tiled */
+#define MAGE_GEMM_TCGEN05 1  /* tcgen05.mma kind::tf32, 3xTF32 split, TMEM accumulators, TMA operands */
+
+/* Library info / bookkeeping */
+int mage_abi_version(void);
+/* Number of kernels launched through this library by the calling process so far. */
+int64_t mage_launch_count(void);
+int mage_set_gemm_backend(int backend);
+int mage_get_gemm_backend(void);
+
+/* C[M,N] = act(relu_a?(A)[M,K] . W[N,K]^T + bias[N]) + residual
+ * residual row for output row m is (res_mod > 0 ? m % res_mod : m), leading dim ldr; may alias C.
+ * Replaces nn.Linear / MHA in-proj / out-proj / MLP (mage_model.py:20-26,33,50-51,375-376,385),
+ * and 1x1 convolutions on NHWC data (vqvae_model.py:131,142,150,153).  K % 4 == 0, lda/ldw % 4 == 0. */
+int mage_gemm_f32(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
+                  const float* residual, int64_t ldr, int res_mod, float* C, int64_t ldc,
+                  int M, int N, int K, int act, int relu_a, void* stream);
+
+/* Implicit-GEMM 2-D convolution, NHWC fp32, weights packed [Cout][KH][KW][Cin] (Cin % 4 == 0).
+ *   out[n, oy*out_sy+out_oy, ox*out_sx+out_ox, :] =
+ *        act( sum_{ky,kx,c} relu_in?(in_up(in))[n, oy*stride-pad_y+ky, ox*stride-pad_x+kx, c] * w[:,ky,kx,c] + bias )
+ *        + residual
+ *   in_up = 1 reads the stored [Hin,Win] input through a nearest x2 upsample (nn.Upsample,
+ *   vqvae_model.py:205-209) without materialising it; res_mode: 0 none, 1 same shape as out,
+ *   2 stored at half resolution and read through nearest x2, 3 one [Hout,Wout,Cout] map shared
+ *   by all images (H/W positional embeddings, mage_model.py:649,676).
+ *   The out_s / out_o scatter writes one sub-pixel phase of a ConvTranspose2d(4,2,1)
+ *   (vqvae_model.py:184,187) into the full [Hfull,Wfull] output; out_img_stride is in elements.
+ * Replaces nn.Conv2d / nn.ConvTranspose2d calls of vqvae_model.py:111-166,172-214 and
+ * mage_model.py:485-488,304-305,504. */
+int mage_conv2d_nhwc_f32(const float* in, const float* w, const float* bias, const float* residual, float* out,
+                         int n_img, int Hin, int Win, int Cin, int Hout, int Wout, int Cout,
+                         int KH, int KW, int stride, int pad_y, int pad_x,
+                         int in_up, int res_mode, int relu_in, int act,
+                         int out_sy, int out_sx, int out_oy, int out_ox, int Hfull, int Wfull,
+                         int64_t out_img_stride, void* stream);
+
+/* First-layer convolution from a planar NCHW image with a tiny channel count (Cin <= 4):
+ * in [N,Cin,H,W], w_t [Cin*KH*KW][Cout] (transposed), out NHWC [N,Hout,Wout,Cout], optional ReLU.
+ * Replaces vqvae_model.py:172-173 (4x4 s2, BN folded by the caller) and :193 (7x7 pad 3). */
+int mage_conv2d_first_f32(const float* in, const float* w_t, const float* bias, float* out,
+                          int n_img, int Cin, int H, int W, int Hout, int Wout, int Cout,
+                          int KH, int KW, int stride, int pad, int act, void* stream);
+
+/* Last f8 decoder layer: out[n,c,y,x] = tanh(sum_k relu(in[n,y,x,k]) * w[c,k] + bias[c]), planar
+ * output with image stride out_img_stride elements (vqvae_model.py:211-213). Cin % 128 == 0, Cout <= 4. */
+int mage_conv1x1_tanh_nchw_f32(const float* in, const float* w, const float* bias, float* out,
+                               int n_img, int HW, int Cin, int Cout, int64_t out_img_stride, void* stream);
+
+/* 2x2 max pooling, NHWC (vqvae_model.py:195,197,199). */
+int mage_maxpool2x2_nhwc_f32(const float* in, float* out, int n_img, int Hin, int Win, int C, void* stream);
+
+/* Row LayerNorm over the last dim C (C % 128 == 0, C <= 1024); in may alias out.
+ * Replaces nn.LayerNorm (mage_model.py:21,27,84,204,206). */
+int mage_layernorm_f32(const float* in, const float* gamma, const float* beta, float* out,
+                       int rows, int C, float eps, void* stream);
+
+/* Multi-head attention core, head_dim 32: for every (outer, inner, head, query)
+ *   out = softmax(scale * q . K^T [keys >= key_len[outer] masked]) . V        (Sk <= 64)
+ * Element strides address q/k/v/out as base + outer*X_outer + inner*X_inner + s*X_seq + head*32.
+ * Covers the SDPA inside every nn.MultiheadAttention on the path (mage_model.py:33,89,193-199):
+ * temporal attention over the K/V cache, H-/W-axial attention, text self-attention (key padding),
+ * motion-anchor cross-attention. */
+int mage_mha_f32(const float* q, const float* k, const float* v, float* out,
+                 int n_outer, int n_inner, int n_head, int Sq, int Sk,
+                 int64_t q_outer, int64_t q_inner, int64_t q_seq,
+                 int64_t k_outer, int64_t k_inner, int64_t k_seq,
+                 int64_t v_outer, int64_t v_inner, int64_t v_seq,
+                 int64_t o_outer, int64_t o_inner, int64_t o_seq,
+                 const int32_t* key_len, float scale, void* stream);
+
+/* Temporal attention for one decode step with a TMA-staged K/V cache (bulk async copies into
+ * shared memory).  qkv [M, 3C] holds this position's q|k|v; k,v are appended to the caches
+ * [M, Lmax, C] at `pos` and q attends positions 0..pos.  out [M, C].  C = 512, 16 heads x 32. */
+int mage_temporal_attn_step_f32(const float* qkv, float* kcache, float* vcache, float* out,
+                                int M, int pos, int Lmax, float scale, void* stream);
+
+/* Append this step's K and V (columns C..3C of qkv [M,3C]) at position `pos` of caches [M,Lmax,C]. */
+int mage_kv_append_f32(const float* qkv, float* kcache, float* vcache, int M, int C, int pos, int Lmax, void* stream);
+
+/* L2 nearest-code search of the VectorQuantizer (vqvae_model.py:8-25):
+ *   idx[n] = argmin_k ( (|c_k|^2 + |z_n|^2) - 2 z_n.c_k ),   z [N,D], codebook [K,D], D % 16 == 0, K % 128 == 0.
+ * csq_scratch: K floats of scratch.  Ties resolve to the lowest index. */
+int mage_vq_argmin_f32(const float* z, const float* codebook, float* csq_scratch, int64_t* idx,
+                       int N, int D, int K, void* stream);
+
+/* idx[r] = argmax_n x[r, n] (lowest index on ties); greedy decode, mage_model.py:681,687. */
+int mage_argmax_rows_f32(const float* x, int64_t ldx, int64_t* idx, int rows, int N, void* stream);
+
+/* out[r, :] = table[idx[r], :]  (nn.Embedding: mage_model.py:644,682; vqvae_model.py:240). C % 4 == 0. */
+int mage_embedding_f32(const int64_t* idx, const float* table, float* out, int rows, int C, void* stream);
+
+/* Text-encoder front end (mage_model.py:224-237): x[b,t,:] = LN_eps(tok_emb[text[b,t]] + pos_emb[t]) * (text[b,t] != pad);
+ * key_len[b] = #non-pad tokens.  C = 512. */
+int mage_text_embed_f32(const int64_t* text, const float* tok_emb, const float* pos_emb,
+                        const float* gamma, const float* beta, float* x, int32_t* key_len,
+                        int B, int T, int C, int pad_idx, float eps, void* stream);
+
+/* AdaIN (mage_model.py:309-314): out = gamma * InstanceNorm(x) + beta over the HW positions of each
+ * (image, channel); x/gamma/beta/out NHWC [N,HW,C]; out may alias x. */
+int mage_adain_nhwc_f32(const float* x, const float* gamma, const float* beta, float* out,
+                        int n_img, int HW, int C, float eps, void* stream);
+
+/* x[n, p, :] += s[n] * vec[:]  (speed embedding, mage_model.py:666-668). */
+int mage_add_scaled_vec_f32(float* x, const float* s, const float* vec, int n_img, int HW, int C, void* stream);
+
+/* out[n,h,w,c] = in[n,c,h,w]  (noise [B,64,16,16] -> NHWC). */
+int mage_nchw_to_nhwc_f32(const float* in, float* out, int n_img, int C, int HW, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAGE_B200_H */

@@ -1,0 +1,82 @@
+"""ctypes binding of libmage_sm100.so (the C ABI in include/mage_b200.h).
+
+There is no Python or CPU fallback: if the shared library is missing the import of any
+product module fails with instructions to build it.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
+LIB_PATH = os.path.join(CSRC, "libmage_sm100.so")
+
+_c_f = ctypes.c_void_p  # device pointers travel as integers
+_i = ctypes.c_int
+_i64 = ctypes.c_int64
+_f32 = ctypes.c_float
+
+# name -> argtypes (restype is int for all but the two bookkeeping calls)
+SIGNATURES = {
+    "mage_abi_version": [],
+    "mage_launch_count": [],
+    "mage_set_gemm_backend": [_i],
+    "mage_get_gemm_backend": [],
+    "mage_gemm_f32": [_c_f, _i64, _c_f, _i64, _c_f, _c_f, _i64, _i, _c_f, _i64, _i, _i, _i, _i, _i, _c_f],
+    "mage_conv2d_nhwc_f32": [_c_f] * 5 + [_i] * 22 + [_i64, _c_f],
+    "mage_conv2d_first_f32": [_c_f] * 4 + [_i] * 12 + [_c_f],
+    "mage_conv1x1_tanh_nchw_f32": [_c_f] * 4 + [_i] * 4 + [_i64, _c_f],
+    "mage_maxpool2x2_nhwc_f32": [_c_f, _c_f, _i, _i, _i, _i, _c_f],
+    "mage_layernorm_f32": [_c_f] * 4 + [_i, _i, _f32, _c_f],
+    "mage_mha_f32": [_c_f] * 4 + [_i] * 5 + [_i64] * 12 + [_c_f, _f32, _c_f],
+    "mage_temporal_attn_step_f32": [_c_f] * 4 + [_i, _i, _i, _f32, _c_f],
+    "mage_kv_append_f32": [_c_f] * 3 + [_i] * 4 + [_c_f],
+    "mage_vq_argmin_f32": [_c_f] * 4 + [_i] * 3 + [_c_f],
+    "mage_argmax_rows_f32": [_c_f, _i64, _c_f, _i, _i, _c_f],
+    "mage_embedding_f32": [_c_f] * 3 + [_i, _i, _c_f],
+    "mage_text_embed_f32": [_c_f] * 7 + [_i] * 4 + [_f32, _c_f],
+    "mage_adain_nhwc_f32": [_c_f] * 4 + [_i] * 3 + [_f32, _c_f],
+    "mage_add_scaled_vec_f32": [_c_f] * 3 + [_i] * 3 + [_c_f],
+    "mage_nchw_to_nhwc_f32": [_c_f, _c_f, _i, _i, _i, _c_f],
+}
+
+
+def build(verbose: bool = False) -> str:
+    """Compile libmage_sm100.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-C", CSRC, "-j8"], capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout)
+        print(r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError("building libmage_sm100.so failed (see output above)")
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: the MAGE sampling path has no CPU/PyTorch fallback. "
+                "Build it with `python -c 'import __graft_entry__ as g; g.build()'` or `make -C mage_b200/csrc`.")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, args in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
+            fn.argtypes = args
+            fn.restype = _i64 if name == "mage_launch_count" else _i
+        _lib = L
+    return _lib
+
+
+class MageCudaError(RuntimeError):
+    pass
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        kind = {-1: "MAGE_EINVAL (unsupported shape/alignment)", -2: "MAGE_ENOTSUP"}.get(code, f"cudaError {code}")
+        raise MageCudaError(f"{what} failed: {kind}")

@@ -1,0 +1,400 @@
+// Bandwidth-bound helper kernels of the MAGE sampling path: LayerNorm, greedy argmax, embedding
+// gathers, pooling, AdaIN, first/last VQ-VAE layers.  All fp32, channels-last, float4 accesses.
+#include "common.cuh"
+
+int64_t g_mage_launches = 0;
+
+extern "C" int mage_abi_version(void) { return 1; }
+extern "C" int64_t mage_launch_count(void) { return g_mage_launches; }
+
+namespace {
+
+// ------------------------------------------------------------------ LayerNorm
+// one warp per row; the row lives in registers (NV float4 per lane), two-pass statistics.
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ in, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float* __restrict__ out,
+                                                        int rows, float eps) {
+  constexpr int C = NV * 128;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* src = reinterpret_cast<const float4*>(in + (int64_t)row * C);
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i] = src[i * 32 + lane];
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) * (1.f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + eps);
+  float4* dst = reinterpret_cast<float4*>(out + (int64_t)row * C);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + i * 32 + lane);
+    float4 o;
+    o.x = (v[i].x - mean) * rstd * g.x + b.x;
+    o.y = (v[i].y - mean) * rstd * g.y + b.y;
+    o.z = (v[i].z - mean) * rstd * g.z + b.z;
+    o.w = (v[i].w - mean) * rstd * g.w + b.w;
+    dst[i * 32 + lane] = o;
+  }
+}
+
+// ------------------------------------------------------------------ argmax over rows
+__global__ void __launch_bounds__(256) argmax_rows_kernel(const float* __restrict__ x, int64_t ldx,
+                                                          int64_t* __restrict__ idx, int rows, int N) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* r = x + (int64_t)row * ldx;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int n = lane; n < N; n += 32) {
+    const float v = r[n];
+    if (v > best || (v == best && n < bi) || bi == 0x7fffffff) { best = v; bi = n; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  if (lane == 0) idx[row] = bi;
+}
+
+// ------------------------------------------------------------------ embedding gather
+__global__ void __launch_bounds__(256) embedding_kernel(const int64_t* __restrict__ idx, const float* __restrict__ table,
+                                                        float* __restrict__ out, int rows, int C4) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)rows * C4) return;
+  const int row = (int)(t / C4), c = (int)(t - (int64_t)row * C4);
+  reinterpret_cast<float4*>(out)[t] = __ldg(reinterpret_cast<const float4*>(table) + idx[row] * C4 + c);
+}
+
+// ------------------------------------------------------------------ 2x2 max pool NHWC
+__global__ void __launch_bounds__(256) maxpool_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                      int n_img, int Hin, int Win, int C4) {
+  const int Ho = Hin >> 1, Wo = Win >> 1;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)n_img * Ho * Wo * C4) return;
+  const int c = (int)(t % C4);
+  int64_t r = t / C4;
+  const int ox = (int)(r % Wo); r /= Wo;
+  const int oy = (int)(r % Ho);
+  const int n = (int)(r / Ho);
+  const float4* src = reinterpret_cast<const float4*>(in) + (((int64_t)n * Hin + oy * 2) * Win + ox * 2) * C4 + c;
+  const float4 a = __ldg(src), b = __ldg(src + C4), d = __ldg(src + (int64_t)Win * C4), e = __ldg(src + (int64_t)Win * C4 + C4);
+  float4 o;
+  o.x = fmaxf(fmaxf(a.x, b.x), fmaxf(d.x, e.x));
+  o.y = fmaxf(fmaxf(a.y, b.y), fmaxf(d.y, e.y));
+  o.z = fmaxf(fmaxf(a.z, b.z), fmaxf(d.z, e.z));
+  o.w = fmaxf(fmaxf(a.w, b.w), fmaxf(d.w, e.w));
+  reinterpret_cast<float4*>(out)[t] = o;
+}
+
+// ------------------------------------------------------------------ text-encoder front end
+// one warp per (b,t): gather + add + LayerNorm(eps) + pad masking; warp 0 of each b also counts tokens.
+__global__ void __launch_bounds__(256) text_embed_kernel(const int64_t* __restrict__ text, const float* __restrict__ tok_emb,
+                                                         const float* __restrict__ pos_emb, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, float* __restrict__ x,
+                                                         int32_t* __restrict__ key_len, int B, int T, int pad_idx, float eps) {
+  constexpr int NV = 4, C = 512;
+  const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (w >= B * T) return;
+  const int b = w / T, t = w - b * T;
+  const int64_t tok = text[w];
+  if (t == 0) {
+    int cnt = 0;
+    for (int i = lane; i < T; i += 32) cnt += (text[b * T + i] != pad_idx) ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) key_len[b] = cnt;
+  }
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(tok_emb + tok * C) + i * 32 + lane);
+    const float4 p = __ldg(reinterpret_cast<const float4*>(pos_emb + (int64_t)t * C) + i * 32 + lane);
+    v[i] = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) * (1.f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + bb * bb) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + eps);
+  const float keep = (tok != pad_idx) ? 1.f : 0.f;
+  float4* dst = reinterpret_cast<float4*>(x + (int64_t)w * C);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
+    const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + i * 32 + lane);
+    float4 o;
+    o.x = ((v[i].x - mean) * rstd * g.x + be.x) * keep;
+    o.y = ((v[i].y - mean) * rstd * g.y + be.y) * keep;
+    o.z = ((v[i].z - mean) * rstd * g.z + be.z) * keep;
+    o.w = ((v[i].w - mean) * rstd * g.w + be.w) * keep;
+    dst[i * 32 + lane] = o;
+  }
+}
+
+// ------------------------------------------------------------------ AdaIN (instance norm + modulation)
+// block = 32 channels x 8 position groups; statistics over the HW positions of one (image, channel).
+__global__ void __launch_bounds__(256) adain_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                    const float* __restrict__ beta, float* __restrict__ out,
+                                                    int HW, int C, float eps) {
+  __shared__ float red[8][33];
+  const int n = blockIdx.y;
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int g = threadIdx.x >> 5;
+  const float* xb = x + (int64_t)n * HW * C + c;
+  float s = 0.f;
+  for (int p = g; p < HW; p += 8) s += xb[(int64_t)p * C];
+  red[g][threadIdx.x & 31] = s;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += red[i][threadIdx.x & 31];
+  const float mean = tot / HW;
+  __syncthreads();
+  float q = 0.f;
+  for (int p = g; p < HW; p += 8) {
+    const float d = xb[(int64_t)p * C] - mean;
+    q += d * d;
+  }
+  red[g][threadIdx.x & 31] = q;
+  __syncthreads();
+  tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += red[i][threadIdx.x & 31];
+  const float rstd = rsqrtf(tot / HW + eps);
+  const float* gb = gamma + (int64_t)n * HW * C + c;
+  const float* bb = beta + (int64_t)n * HW * C + c;
+  float* ob = out + (int64_t)n * HW * C + c;
+  for (int p = g; p < HW; p += 8) {
+    const int64_t o = (int64_t)p * C;
+    ob[o] = gb[o] * ((xb[o] - mean) * rstd) + bb[o];
+  }
+}
+
+__global__ void __launch_bounds__(256) add_scaled_vec_kernel(float* __restrict__ x, const float* __restrict__ s,
+                                                             const float* __restrict__ vec, int HW, int C, int64_t total) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int c = (int)(t % C);
+  const int n = (int)(t / ((int64_t)HW * C));
+  x[t] = x[t] + __fmul_rn(s[n], vec[c]);
+}
+
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                           int C, int HW, int64_t total) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int c = (int)(t % C);
+  const int64_t r = t / C;
+  const int p = (int)(r % HW);
+  const int64_t n = r / HW;
+  out[t] = in[(n * C + c) * HW + p];
+}
+
+// ------------------------------------------------------------------ first conv layer (tiny Cin, planar input)
+// block: one output row segment of PX pixels x all Cout channels; the input patch sits in shared memory,
+// each thread owns one output channel and PX accumulators; weights stream through L1 (transposed [K][Cout]).
+template <int PX>
+__global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict__ in, const float* __restrict__ w_t,
+                                                         const float* __restrict__ bias, float* __restrict__ out,
+                                                         int Cin, int H, int W, int Hout, int Wout, int Cout,
+                                                         int KH, int KW, int stride, int pad, int act) {
+  extern __shared__ float patch[];  // [Cin][KH][PW]
+  const int PW = (PX - 1) * stride + KW;
+  const int segs = (Wout + PX - 1) / PX;
+  int b = blockIdx.x;
+  const int seg = b % segs; b /= segs;
+  const int oy = b % Hout;
+  const int n = b / Hout;
+  const int ox0 = seg * PX;
+  const int iy0 = oy * stride - pad, ix0 = ox0 * stride - pad;
+  for (int i = threadIdx.x; i < Cin * KH * PW; i += blockDim.x) {
+    const int px = i % PW;
+    const int ky = (i / PW) % KH;
+    const int c = i / (PW * KH);
+    const int iy = iy0 + ky, ix = ix0 + px;
+    patch[i] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? in[(((int64_t)n * Cin + c) * H + iy) * W + ix] : 0.f;
+  }
+  __syncthreads();
+  for (int co = threadIdx.x; co < Cout; co += blockDim.x) {
+    float acc[PX];
+#pragma unroll
+    for (int p = 0; p < PX; ++p) acc[p] = 0.f;
+    for (int c = 0; c < Cin; ++c)
+      for (int ky = 0; ky < KH; ++ky) {
+        const float* prow = patch + (c * KH + ky) * PW;
+        for (int kx = 0; kx < KW; ++kx) {
+          const float wv = __ldg(w_t + (int64_t)((c * KH + ky) * KW + kx) * Cout + co);
+#pragma unroll
+          for (int p = 0; p < PX; ++p) acc[p] = fmaf(wv, prow[p * stride + kx], acc[p]);
+        }
+      }
+    const float bv = bias ? bias[co] : 0.f;
+#pragma unroll
+    for (int p = 0; p < PX; ++p) {
+      const int ox = ox0 + p;
+      if (ox < Wout) out[(((int64_t)n * Hout + oy) * Wout + ox) * Cout + co] = mage_act(acc[p] + bv, act);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ last f8 decoder layer
+// warp per pixel: relu -> 1x1 conv to <=4 channels -> tanh, planar output.
+__global__ void __launch_bounds__(256) conv1x1_tanh_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, float* __restrict__ out,
+                                                           int64_t n_pix, int HW, int Cin, int Cout, int64_t out_img_stride) {
+  const int64_t pix = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (pix >= n_pix) return;
+  const float4* src = reinterpret_cast<const float4*>(in + pix * Cin);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int i = lane; i < Cin / 4; i += 32) {
+    float4 v = __ldg(src + i);
+    v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (c < Cout) {
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(w + (int64_t)c * Cin) + i);
+        acc[c] += (v.x * wv.x + v.y * wv.y) + (v.z * wv.z + v.w * wv.w);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) acc[c] = warp_sum(acc[c]);
+  if (lane < Cout) {
+    const int64_t n = pix / HW, p = pix - n * HW;
+    float v = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
+    out[n * out_img_stride + (int64_t)lane * HW + p] = tanhf(v + bias[lane]);
+  }
+}
+
+__global__ void __launch_bounds__(256) kv_append_kernel(const float* __restrict__ qkv, float* __restrict__ kc,
+                                                        float* __restrict__ vc, int M, int C4, int pos, int Lmax) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)M * C4) return;
+  const int m = (int)(t / C4), c = (int)(t - (int64_t)m * C4);
+  const float4* src = reinterpret_cast<const float4*>(qkv) + (int64_t)m * 3 * C4;
+  const int64_t dst = ((int64_t)m * Lmax + pos) * C4 + c;
+  reinterpret_cast<float4*>(kc)[dst] = src[C4 + c];
+  reinterpret_cast<float4*>(vc)[dst] = src[2 * C4 + c];
+}
+
+}  // namespace
+
+extern "C" int mage_layernorm_f32(const float* in, const float* gamma, const float* beta, float* out, int rows, int C,
+                                  float eps, void* stream) {
+  MAGE_CHECK_ARG(rows > 0 && C % 128 == 0 && C <= 1024 && aligned16(in) && aligned16(out) && aligned16(gamma) && aligned16(beta));
+  const dim3 g((rows + 7) / 8);
+  cudaStream_t st = as_stream(stream);
+  switch (C / 128) {
+    case 1: layernorm_kernel<1><<<g, 256, 0, st>>>(in, gamma, beta, out, rows, eps); break;
+    case 2: layernorm_kernel<2><<<g, 256, 0, st>>>(in, gamma, beta, out, rows, eps); break;
+    case 4: layernorm_kernel<4><<<g, 256, 0, st>>>(in, gamma, beta, out, rows, eps); break;
+    case 8: layernorm_kernel<8><<<g, 256, 0, st>>>(in, gamma, beta, out, rows, eps); break;
+    default: return MAGE_EINVAL;
+  }
+  return mage_post_launch();
+}
+
+extern "C" int mage_argmax_rows_f32(const float* x, int64_t ldx, int64_t* idx, int rows, int N, void* stream) {
+  MAGE_CHECK_ARG(rows > 0 && N > 0);
+  argmax_rows_kernel<<<(rows + 7) / 8, 256, 0, as_stream(stream)>>>(x, ldx, idx, rows, N);
+  return mage_post_launch();
+}
+
+extern "C" int mage_embedding_f32(const int64_t* idx, const float* table, float* out, int rows, int C, void* stream) {
+  MAGE_CHECK_ARG(rows > 0 && C % 4 == 0 && aligned16(table) && aligned16(out));
+  const int64_t total = (int64_t)rows * (C / 4);
+  embedding_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(idx, table, out, rows, C / 4);
+  return mage_post_launch();
+}
+
+extern "C" int mage_maxpool2x2_nhwc_f32(const float* in, float* out, int n_img, int Hin, int Win, int C, void* stream) {
+  MAGE_CHECK_ARG(n_img > 0 && Hin % 2 == 0 && Win % 2 == 0 && C % 4 == 0 && aligned16(in) && aligned16(out));
+  const int64_t total = (int64_t)n_img * (Hin / 2) * (Win / 2) * (C / 4);
+  maxpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(in, out, n_img, Hin, Win, C / 4);
+  return mage_post_launch();
+}
+
+extern "C" int mage_text_embed_f32(const int64_t* text, const float* tok_emb, const float* pos_emb, const float* gamma,
+                                   const float* beta, float* x, int32_t* key_len, int B, int T, int C, int pad_idx,
+                                   float eps, void* stream) {
+  MAGE_CHECK_ARG(B > 0 && T > 0 && C == 512 && aligned16(tok_emb) && aligned16(pos_emb) && aligned16(x));
+  text_embed_kernel<<<(B * T + 7) / 8, 256, 0, as_stream(stream)>>>(text, tok_emb, pos_emb, gamma, beta, x, key_len, B, T,
+                                                                   pad_idx, eps);
+  return mage_post_launch();
+}
+
+extern "C" int mage_adain_nhwc_f32(const float* x, const float* gamma, const float* beta, float* out, int n_img, int HW,
+                                   int C, float eps, void* stream) {
+  MAGE_CHECK_ARG(n_img > 0 && HW > 0 && C % 32 == 0);
+  adain_kernel<<<dim3(C / 32, n_img), 256, 0, as_stream(stream)>>>(x, gamma, beta, out, HW, C, eps);
+  return mage_post_launch();
+}
+
+extern "C" int mage_add_scaled_vec_f32(float* x, const float* s, const float* vec, int n_img, int HW, int C, void* stream) {
+  MAGE_CHECK_ARG(n_img > 0 && HW > 0 && C > 0);
+  const int64_t total = (int64_t)n_img * HW * C;
+  add_scaled_vec_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(x, s, vec, HW, C, total);
+  return mage_post_launch();
+}
+
+extern "C" int mage_nchw_to_nhwc_f32(const float* in, float* out, int n_img, int C, int HW, void* stream) {
+  MAGE_CHECK_ARG(n_img > 0 && C > 0 && HW > 0);
+  const int64_t total = (int64_t)n_img * HW * C;
+  nchw_to_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(in, out, C, HW, total);
+  return mage_post_launch();
+}
+
+extern "C" int mage_conv2d_first_f32(const float* in, const float* w_t, const float* bias, float* out, int n_img, int Cin,
+                                     int H, int W, int Hout, int Wout, int Cout, int KH, int KW, int stride, int pad,
+                                     int act, void* stream) {
+  MAGE_CHECK_ARG(n_img > 0 && Cin > 0 && Cin <= 4 && Cout > 0 && KH > 0 && KW > 0 && stride > 0);
+  constexpr int PX = 16;
+  const int PW = (PX - 1) * stride + KW;
+  const size_t smem = (size_t)Cin * KH * PW * sizeof(float);
+  MAGE_CHECK_ARG(smem <= 48 * 1024);
+  const int segs = (Wout + PX - 1) / PX;
+  const int64_t blocks = (int64_t)n_img * Hout * segs;
+  MAGE_CHECK_ARG(blocks < ((int64_t)1 << 31));
+  conv_first_kernel<PX><<<(unsigned)blocks, 256, smem, as_stream(stream)>>>(in, w_t, bias, out, Cin, H, W, Hout, Wout, Cout,
+                                                                           KH, KW, stride, pad, act);
+  return mage_post_launch();
+}
+
+extern "C" int mage_conv1x1_tanh_nchw_f32(const float* in, const float* w, const float* bias, float* out, int n_img, int HW,
+                                          int Cin, int Cout, int64_t out_img_stride, void* stream) {
+  MAGE_CHECK_ARG(n_img > 0 && HW > 0 && Cin % 4 == 0 && Cout >= 1 && Cout <= 4 && aligned16(in) && aligned16(w) && bias);
+  const int64_t n_pix = (int64_t)n_img * HW;
+  conv1x1_tanh_kernel<<<(unsigned)((n_pix + 7) / 8), 256, 0, as_stream(stream)>>>(in, w, bias, out, n_pix, HW, Cin, Cout,
+                                                                                 out_img_stride);
+  return mage_post_launch();
+}
+
+extern "C" int mage_kv_append_f32(const float* qkv, float* kcache, float* vcache, int M, int C, int pos, int Lmax,
+                                  void* stream) {
+  MAGE_CHECK_ARG(M > 0 && C % 4 == 0 && pos >= 0 && pos < Lmax && aligned16(qkv) && aligned16(kcache) && aligned16(vcache));
+  const int64_t total = (int64_t)M * (C / 4);
+  kv_append_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(qkv, kcache, vcache, M, C / 4, pos, Lmax);
+  return mage_post_launch();
+}

@@ -1,0 +1,430 @@
+"""Host-side orchestration of the MAGE sampling path on one B200.
+
+Two engines, both driven by the reference's state-dict layout:
+
+* `VQVAEEngine`  -- VectorQuantizedVAE.encode / .decode (vqvae_model.py:233-242) on NHWC tensors:
+  conv stacks as implicit GEMMs, nearest-upsample folded into the consumers' address math,
+  eval-mode BatchNorm folded into the neighbouring conv at load, fused VQ argmin.
+* `SamplerEngine` -- MAGE.autoregressive_generate (mage_model.py:641-693) re-designed as the
+  incremental algorithm of SURVEY.md App. D: per step only the newest temporal position runs
+  through the six axial blocks; the two temporal blocks keep a K/V cache `[B*256, L, 512]`.
+
+Python only sequences kernels of libmage_sm100.so (mage_b200.ops) and owns buffers; the one-time
+weight re-layout at load (permute / BatchNorm folding) uses torch tensor ops and is not on the
+timed path.  A whole `generate` call is captured into a CUDA graph per input signature.
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import Dict, Optional
+
+import torch
+
+from . import ops
+from .ops import ACT_GELU, ACT_NONE, ACT_QUICKGELU, ACT_RELU, ACT_TANH
+
+ACT_POST = 0x100
+RES_RELU = 0x200
+
+
+def _pack_conv(w: torch.Tensor) -> torch.Tensor:
+    """[Cout,Cin,KH,KW] -> [Cout,KH,KW,Cin] (K-contiguous rows for the implicit GEMM)."""
+    return w.permute(0, 2, 3, 1).contiguous()
+
+
+def _bn_fold(sd, name, eps=1e-5):
+    s = sd[name + ".weight"] / torch.sqrt(sd[name + ".running_var"] + eps)
+    return s, sd[name + ".bias"] - sd[name + ".running_mean"] * s
+
+
+class VQVAEEngine:
+    def __init__(self, sd: Dict[str, torch.Tensor]):
+        """sd: VectorQuantizedVAE.state_dict() tensors (fp32, on the CUDA device)."""
+        self.device = sd["codebook.embedding.weight"].device
+        assert self.device.type == "cuda", "VQVAEEngine needs CUDA tensors (no CPU path)"
+        self.down_ratio = 4 if "encoder.1.running_mean" in sd else 8
+        self.codebook = sd["codebook.embedding.weight"].contiguous()
+        self.K, self.D = self.codebook.shape
+        w = {}
+        if self.down_ratio == 8:
+            w["enc0_wt"] = sd["encoder.0.weight"].permute(1, 2, 3, 0).reshape(-1, sd["encoder.0.weight"].shape[0]).contiguous()
+            w["enc0_b"] = sd["encoder.0.bias"].contiguous()
+            self.in_ch = sd["encoder.0.weight"].shape[1]
+            for k, v in sd.items():
+                if k.endswith(".weight") and v.dim() == 4 and k != "encoder.0.weight":
+                    w[k] = _pack_conv(v) if v.shape[-1] > 1 else v.reshape(v.shape[0], v.shape[1]).contiguous()
+                elif k.endswith(".bias"):
+                    w[k] = v.contiguous()
+        else:
+            self.in_ch = sd["encoder.0.weight"].shape[1]
+            s, b = _bn_fold(sd, "encoder.1")
+            w0 = sd["encoder.0.weight"] * s.view(-1, 1, 1, 1)
+            w["enc0_wt"] = w0.permute(1, 2, 3, 0).reshape(-1, w0.shape[0]).contiguous()
+            w["enc0_b"] = (sd["encoder.0.bias"] * s + b).contiguous()
+            w["encoder.3.weight"] = _pack_conv(sd["encoder.3.weight"])
+            w["encoder.3.bias"] = sd["encoder.3.bias"].contiguous()
+            for blk in ("encoder.4", "encoder.5", "decoder.0", "decoder.1"):
+                s1, b1 = _bn_fold(sd, blk + ".block.2")
+                w[blk + ".c3.w"] = _pack_conv(sd[blk + ".block.1.weight"] * s1.view(-1, 1, 1, 1))
+                w[blk + ".c3.b"] = (sd[blk + ".block.1.bias"] * s1 + b1).contiguous()
+                s2, b2 = _bn_fold(sd, blk + ".block.5")
+                w[blk + ".c1.w"] = (sd[blk + ".block.4.weight"][:, :, 0, 0] * s2.view(-1, 1)).contiguous()
+                w[blk + ".c1.b"] = (sd[blk + ".block.4.bias"] * s2 + b2).contiguous()
+            # ConvTranspose2d(4,2,1): out[2y+py] gets taps (input offset, k): py=0 -> (-1,3),(0,1); py=1 -> (0,2),(+1,0)
+            s3, b3 = _bn_fold(sd, "decoder.4")
+            w["decoder.3.b"] = (sd["decoder.3.bias"] * s3 + b3).contiguous()
+            w["decoder.6.b"] = sd["decoder.6.bias"].contiguous()
+            taps = {0: (3, 1), 1: (2, 0)}
+            for name, scale in (("decoder.3", s3), ("decoder.6", None)):
+                wt = sd[name + ".weight"]  # [Cin, Cout, 4, 4]
+                if scale is not None:
+                    wt = wt * scale.view(1, -1, 1, 1)
+                for py in (0, 1):
+                    for px in (0, 1):
+                        sub = wt[:, :, list(taps[py]), :][:, :, :, list(taps[px])]  # [Cin,Cout,2,2]
+                        w[f"{name}.p{py}{px}"] = sub.permute(1, 2, 3, 0).contiguous()  # [Cout,2,2,Cin]
+        self.w = w
+
+    # ------------------------------------------------------------------ encoder
+    def _enc_block(self, name: str, x: torch.Tensor, final_relu: bool = False) -> torch.Tensor:
+        """EncoderBlock (vqvae_model.py:126-145): id(x) + 1x1(relu 3x3(relu 3x3(relu 3x3(relu x))))."""
+        w = self.w
+        n, H, W, C = x.shape
+        x2 = x.view(-1, C)
+        idp = ops.gemm(x2, w[name + ".id_path.weight"], w[name + ".id_path.bias"]) if (name + ".id_path.weight") in w else x2
+        h = ops.conv2d(x, w[name + ".block.1.weight"], w[name + ".block.1.bias"], pad=(1, 1), relu_in=True, act=ACT_RELU)
+        h = ops.conv2d(h, w[name + ".block.3.weight"], w[name + ".block.3.bias"], pad=(1, 1), act=ACT_RELU)
+        h = ops.conv2d(h, w[name + ".block.5.weight"], w[name + ".block.5.bias"], pad=(1, 1), act=ACT_RELU)
+        out = ops.gemm(h.view(-1, h.shape[-1]), w[name + ".block.7.weight"], w[name + ".block.7.bias"], residual=idp,
+                       act=(ACT_RELU | ACT_POST) if final_relu else ACT_NONE)
+        return out.view(n, H, W, -1)
+
+    def _res_block(self, name: str, xr: torch.Tensor, post_relu: bool, res_relu: bool = False) -> torch.Tensor:
+        """ResBlock (vqvae_model.py:111-124) on an input whose in-place ReLU is already applied
+        (or applied on the fly with res_relu): xr + BN(1x1(relu(BN(3x3(xr)))))."""
+        w = self.w
+        n, H, W, C = xr.shape
+        h = ops.conv2d(xr, w[name + ".c3.w"], w[name + ".c3.b"], pad=(1, 1), relu_in=res_relu, act=ACT_RELU)
+        act = (ACT_RELU | ACT_POST) if post_relu else ACT_NONE
+        if res_relu:
+            act |= RES_RELU
+        out = ops.gemm(h.view(-1, C), w[name + ".c1.w"], w[name + ".c1.b"], residual=xr.view(-1, C), act=act)
+        return out.view(n, H, W, C)
+
+    def encode_features(self, x: torch.Tensor) -> torch.Tensor:
+        """x [N,C,H,W] planar fp32 -> z_e NHWC [N,h,w,D] (vqvae_model.py:172-179 / :192-202)."""
+        w = self.w
+        x = x.contiguous()
+        if self.down_ratio == 8:
+            h = ops.conv2d_first(x, w["enc0_wt"], w["enc0_b"], cout=w["enc0_b"].numel(), kh=7, kw=7, stride=1, pad=3)
+            h = ops.maxpool2x2(self._enc_block("encoder.1", h))
+            h = ops.maxpool2x2(self._enc_block("encoder.3", h))
+            h = ops.maxpool2x2(self._enc_block("encoder.5", h))
+            return self._enc_block("encoder.7", h, final_relu=True)
+        h = ops.conv2d_first(x, w["enc0_wt"], w["enc0_b"], cout=w["enc0_b"].numel(), kh=4, kw=4, stride=2, pad=1, act=ACT_RELU)
+        h = ops.conv2d(h, w["encoder.3.weight"], w["encoder.3.bias"], stride=2, pad=(1, 1), act=ACT_RELU)  # relu = ResBlock's in-place one
+        h = self._res_block("encoder.4", h, post_relu=True)
+        return self._res_block("encoder.5", h, post_relu=False)
+
+    def encode(self, x: torch.Tensor) -> torch.Tensor:
+        """VectorQuantizedVAE.encode: [N,C,H,W] -> int64 [N,h,w]."""
+        z = self.encode_features(x)
+        n, h, w_, D = z.shape
+        return ops.vq_argmin(z.view(-1, D), self.codebook).view(n, h, w_)
+
+    # ------------------------------------------------------------------ decoder
+    def _dec_block(self, name: str, x: torch.Tensor, up: bool) -> torch.Tensor:
+        """DecoderBlock (vqvae_model.py:147-166) applied to nearest-x2-upsampled x when `up`.
+        The two 1x1 convs commute with nearest upsampling, so they run at the stored (low)
+        resolution and the 3x3 convs / the skip read them through the upsample."""
+        w = self.w
+        n, H, W, C = x.shape
+        x2 = x.view(-1, C)
+        has_id = (name + ".id_path.weight") in w
+        idp = ops.gemm(x2, w[name + ".id_path.weight"], w[name + ".id_path.bias"]).view(n, H, W, -1) if has_id else x
+        h = ops.gemm(x2, w[name + ".block.1.weight"], w[name + ".block.1.bias"], relu_a=True, act=ACT_RELU).view(n, H, W, -1)
+        h = ops.conv2d(h, w[name + ".block.3.weight"], w[name + ".block.3.bias"], pad=(1, 1), in_up=up, act=ACT_RELU)
+        h = ops.conv2d(h, w[name + ".block.5.weight"], w[name + ".block.5.bias"], pad=(1, 1), act=ACT_RELU)
+        return ops.conv2d(h, w[name + ".block.7.weight"], w[name + ".block.7.bias"], pad=(1, 1), residual=idp,
+                          res_mode=2 if up else 1)
+
+    def decode_into(self, idx: torch.Tensor, out: torch.Tensor, out_img_stride: int) -> None:
+        """VectorQuantizedVAE.decode: idx int64 [N,h,w] -> tanh pixels written planar at
+        out.data_ptr() + n*out_img_stride (elements), each image [C,H,W] contiguous."""
+        w = self.w
+        n = idx.shape[0]
+        z = ops.embedding(idx.reshape(-1), self.codebook).view(n, idx.shape[1], idx.shape[2], self.D)
+        if self.down_ratio == 8:
+            h = self._dec_block("decoder.0", z, up=False)
+            h = self._dec_block("decoder.2", h, up=True)
+            h = self._dec_block("decoder.4", h, up=True)
+            h = self._dec_block("decoder.6", h, up=True)
+            ops.conv1x1_tanh_nchw(h, w["decoder.8.weight"], w["decoder.8.bias"], out, out_img_stride)
+            return
+        h = self._res_block("decoder.0", z, post_relu=True, res_relu=True)
+        h = self._res_block("decoder.1", h, post_relu=True)  # + decoder.2 ReLU
+        _, H, W, C = h.shape
+        up1 = torch.empty(n, 2 * H, 2 * W, C, device=h.device, dtype=torch.float32)
+        for py in (0, 1):
+            for px in (0, 1):
+                ops.conv2d(h, w[f"decoder.3.p{py}{px}"], w["decoder.3.b"], pad=(1 - py, 1 - px), act=ACT_RELU, out=up1,
+                           out_hw=(H, W), scatter=(2, 2, py, px), full_hw=(2 * H, 2 * W))
+        for py in (0, 1):
+            for px in (0, 1):
+                ops.conv2d(up1, w[f"decoder.6.p{py}{px}"], w["decoder.6.b"], pad=(1 - py, 1 - px), act=ACT_TANH, out=out,
+                           out_hw=(2 * H, 2 * W), scatter=(2, 2, py, px), full_hw=(4 * H, 4 * W), out_img_stride=out_img_stride)
+
+    def decode(self, idx: torch.Tensor) -> torch.Tensor:
+        n, h, w_ = idx.shape
+        R = h * self.down_ratio
+        out = torch.empty(n, self.in_ch, R, R, device=idx.device, dtype=torch.float32)
+        self.decode_into(idx.contiguous(), out, self.in_ch * R * R)
+        return out
+
+
+class SamplerEngine:
+    """Incremental greedy sampler for one device.  `sd` is MAGE.state_dict() (CUDA fp32)."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], frames_length: int, randomness: bool, padding_idx: int = 0,
+                 temporal_attn: Optional[str] = None, use_cuda_graph: Optional[bool] = None):
+        self.device = sd["visual_token_embedding.weight"].device
+        assert self.device.type == "cuda", "SamplerEngine needs CUDA tensors (no CPU path)"
+        self.L = frames_length
+        self.randomness = randomness
+        self.padding_idx = padding_idx
+        self.temporal_attn = temporal_attn or os.environ.get("MAGE_TEMPORAL_ATTN", "tma")
+        if use_cuda_graph is None:
+            use_cuda_graph = os.environ.get("MAGE_CUDA_GRAPH", "1") != "0"
+        self.use_cuda_graph = use_cuda_graph
+        self.vq = VQVAEEngine({k[len("first_stage_model."):]: v for k, v in sd.items() if k.startswith("first_stage_model.")})
+        g = lambda k: sd[k].contiguous()
+        self.sd = sd
+        self.E = g("visual_token_embedding.weight")
+        self.C = self.E.shape[1]
+        self.R = sd["H_positional_embedding"].shape[1]
+        self.Wc = _pack_conv(sd["conv.0.weight"])
+        self.posHW = (sd["H_positional_embedding"] + sd["W_positional_embedding"]).reshape(self.R * self.R, self.C).contiguous()
+        p = "generate_model."
+        Tp = sd[p + "T_positional_embedding"].reshape(-1, self.C)
+        assert Tp.shape[0] >= frames_length, "checkpoint has fewer temporal positions than frames_length"
+        self.bias_in_T = (sd[p + "in_linear.bias"].unsqueeze(0) + Tp).contiguous()      # row p: in_linear bias + T_pos[p]
+        self.bias_ctx0 = (sd[p + "context_linear.bias"] + Tp[0]).contiguous()
+        self.n_blocks = 0
+        while (p + f"blocks.{self.n_blocks}.ln_1.weight") in sd:
+            self.n_blocks += 1
+        self.n_text_layers = 0
+        while f"text_encoder.transformer.layers.{self.n_text_layers}.linear1.weight" in sd:
+            self.n_text_layers += 1
+        self.n_ma_layers = 0
+        while f"ma_encoder.blocks.{self.n_ma_layers}.attn.in_proj_weight" in sd:
+            self.n_ma_layers += 1
+        if randomness:
+            self.Wd2 = _pack_conv(sd["conv_d2.weight"])
+            self.adain_w = {f"{br}.{i}": (_pack_conv(sd[f"adain.{br}.{i}.weight"]), g(f"adain.{br}.{i}.bias"))
+                            for br in ("conv_mu", "conv_var") for i in (0, 1)}
+        self.scale = 1.0 / math.sqrt(32.0)
+        self.n_head = self.C // 32
+        self._graphs = {}
+        self.kernels_per_generate = None
+
+    # ------------------------------------------------------------------ prelude
+    def _token_features(self, tok: torch.Tensor, B: int) -> torch.Tensor:
+        """f(tok) = conv3x3(E[tok]) + Hpos + Wpos  -> [B*R*R, C]   (mage_model.py:644-649,674-676)."""
+        emb = ops.embedding(tok.reshape(-1), self.E).view(B, self.R, self.R, self.C)
+        return ops.conv2d(emb, self.Wc, None, pad=(1, 1), residual=self.posHW, res_mode=3).view(-1, self.C)
+
+    def _text_encoder(self, text: torch.Tensor):
+        """TransformerTextEncoder.forward (mage_model.py:223-250) -> ([B*T, C], key_len)."""
+        sd, p = self.sd, "text_encoder."
+        B, T = text.shape
+        x, key_len = ops.text_embed(text, sd[p + "token_embedding.weight"], sd[p + "positions.weight"],
+                                    sd[p + "layer_norm.weight"], sd[p + "layer_norm.bias"], self.padding_idx, 1e-8)
+        x = x.view(B * T, -1)
+        W = x.shape[1]
+        for i in range(self.n_text_layers):
+            lp = p + f"transformer.layers.{i}"
+            qkv = ops.gemm(x, sd[lp + ".self_attn.in_proj_weight"], sd[lp + ".self_attn.in_proj_bias"])
+            a = torch.empty(B * T, W, device=x.device, dtype=torch.float32)
+            ops.mha(qkv, qkv[:, W:], qkv[:, 2 * W:], a, n_outer=B, n_inner=1, n_head=W // 32, Sq=T, Sk=T,
+                    q_strides=(T * 3 * W, 0, 3 * W), k_strides=(T * 3 * W, 0, 3 * W), v_strides=(T * 3 * W, 0, 3 * W),
+                    o_strides=(T * W, 0, W), key_len=key_len, scale=self.scale)
+            y = ops.gemm(a, sd[lp + ".self_attn.out_proj.weight"], sd[lp + ".self_attn.out_proj.bias"], residual=x)
+            x = ops.layernorm(y, sd[lp + ".norm1.weight"], sd[lp + ".norm1.bias"])
+            h = ops.gemm(x, sd[lp + ".linear1.weight"], sd[lp + ".linear1.bias"], act=ACT_GELU)
+            y = ops.gemm(h, sd[lp + ".linear2.weight"], sd[lp + ".linear2.bias"], residual=x)
+            x = ops.layernorm(y, sd[lp + ".norm2.weight"], sd[lp + ".norm2.bias"])
+        x = ops.layernorm(x, sd[p + "ln_text_final.weight"], sd[p + "ln_text_final.bias"])
+        return ops.gemm(x, sd[p + "text_projection.weight"], sd[p + "text_projection.bias"]), key_len
+
+    def _ma_encoder(self, q: torch.Tensor, temb: torch.Tensor, B: int, T: int) -> torch.Tensor:
+        """MAEncoder (mage_model.py:114-117, TransformerBlock line 92: no LN on q/kv, no key mask).
+        q [B*HW, C] batch-major, temb [B*T, C]."""
+        sd, C = self.sd, self.C
+        HW = self.R * self.R
+        x = q
+        for i in range(self.n_ma_layers):
+            p = f"ma_encoder.blocks.{i}"
+            Win, bin_ = sd[p + ".attn.in_proj_weight"], sd[p + ".attn.in_proj_bias"]
+            qp = ops.gemm(x, Win[:C], bin_[:C])
+            kv = ops.gemm(temb, Win[C:], bin_[C:])  # [B*T, 2C]
+            a = torch.empty(B * HW, C, device=x.device, dtype=torch.float32)
+            ops.mha(qp, kv, kv[:, C:], a, n_outer=B, n_inner=1, n_head=self.n_head, Sq=HW, Sk=T,
+                    q_strides=(HW * C, 0, C), k_strides=(T * 2 * C, 0, 2 * C), v_strides=(T * 2 * C, 0, 2 * C),
+                    o_strides=(HW * C, 0, C), key_len=None, scale=self.scale)
+            x = ops.gemm(a, sd[p + ".attn.out_proj.weight"], sd[p + ".attn.out_proj.bias"], residual=x)
+            u = ops.layernorm(x, sd[p + ".ln_2.weight"], sd[p + ".ln_2.bias"])
+            h = ops.gemm(u, sd[p + ".mlp.c_fc.weight"], sd[p + ".mlp.c_fc.bias"], act=ACT_QUICKGELU)
+            x = ops.gemm(h, sd[p + ".mlp.c_proj.weight"], sd[p + ".mlp.c_proj.bias"], residual=x)
+        return x
+
+    def _adain(self, anchor: torch.Tensor, noise_nchw: torch.Tensor, B: int) -> torch.Tensor:
+        """conv_d2 + ADAIN2D (mage_model.py:660-664, 309-314); anchor NHWC [B,R,R,C]."""
+        y = ops.conv2d(ops.nchw_to_nhwc(noise_nchw), self.Wd2, None, pad=(1, 1))
+        mods = []
+        for br in ("conv_mu", "conv_var"):
+            w0, b0 = self.adain_w[br + ".0"]
+            w1, b1 = self.adain_w[br + ".1"]
+            mods.append(ops.conv2d(ops.conv2d(y, w0, b0, pad=(1, 1)), w1, b1, pad=(1, 1)))
+        return ops.adain(anchor, mods[0], mods[1], 1e-5)
+
+    # ------------------------------------------------------------------ decoder step
+    def _block_step(self, i: int, x: torch.Tensor, pos: int, B: int, caches) -> torch.Tensor:
+        """AxialAttentionBlock (mage_model.py:35-53) on one temporal position; x [B*R*R, C] updated in place."""
+        sd, C, R = self.sd, self.C, self.R
+        p = f"generate_model.blocks.{i}"
+        M = x.shape[0]
+        u = ops.layernorm(x, sd[p + ".ln_1.weight"], sd[p + ".ln_1.bias"])
+        qkv = ops.gemm(u, sd[p + ".attn.in_proj_weight"], sd[p + ".attn.in_proj_bias"])
+        a = u  # reuse the LN buffer for the attention output
+        kind = i % 3
+        if kind == 0:
+            kc, vc = caches[i]
+            if self.temporal_attn == "tma":
+                ops.temporal_attn_step(qkv, kc, vc, a, pos, self.scale)
+            else:
+                ops.kv_append(qkv, kc, vc, pos)
+                Lmax = kc.shape[1]
+                ops.mha(qkv, kc, vc, a, n_outer=M, n_inner=1, n_head=self.n_head, Sq=1, Sk=pos + 1,
+                        q_strides=(3 * C, 0, 0), k_strides=(Lmax * C, 0, C), v_strides=(Lmax * C, 0, C),
+                        o_strides=(C, 0, 0), key_len=None, scale=self.scale)
+        else:
+            # rows are (b, h, w); H-block: sequences run over h (stride R rows) for fixed (b, w); W-block over w
+            inner, seq = (1, R) if kind == 1 else (R, 1)
+            ops.mha(qkv, qkv[:, C:], qkv[:, 2 * C:], a, n_outer=B, n_inner=R, n_head=self.n_head, Sq=R, Sk=R,
+                    q_strides=(R * R * 3 * C, inner * 3 * C, seq * 3 * C), k_strides=(R * R * 3 * C, inner * 3 * C, seq * 3 * C),
+                    v_strides=(R * R * 3 * C, inner * 3 * C, seq * 3 * C), o_strides=(R * R * C, inner * C, seq * C),
+                    key_len=None, scale=self.scale)
+        ops.gemm(a, sd[p + ".attn.out_proj.weight"], sd[p + ".attn.out_proj.bias"], residual=x, out=x)
+        ops.layernorm(x, sd[p + ".ln_2.weight"], sd[p + ".ln_2.bias"], out=u)
+        h = ops.gemm(u, sd[p + ".mlp.c_fc.weight"], sd[p + ".mlp.c_fc.bias"], act=ACT_QUICKGELU)
+        ops.gemm(h, sd[p + ".mlp.c_proj.weight"], sd[p + ".mlp.c_proj.bias"], residual=x, out=x)
+        return x
+
+    # ------------------------------------------------------------------ whole path
+    def _generate_impl(self, images0: torch.Tensor, text: torch.Tensor, speed: Optional[torch.Tensor],
+                       noise: Optional[torch.Tensor], video: torch.Tensor, tokens: torch.Tensor, tok0_out: torch.Tensor,
+                       trace: Optional[dict] = None) -> None:
+        """images0 [B,Cimg,Himg,Wimg]; text i64 [B,T]; video [B,L,Cimg,Himg,Wimg] (frames 1.. written);
+        tokens i64 [L-1, B, R*R] (step-major); tok0_out i64 [B, R*R]."""
+        sd, C, R, L = self.sd, self.C, self.R, self.L
+        B, T = text.shape
+        M = B * R * R
+        p = "generate_model."
+        z = self.vq.encode_features(images0)
+        ops.vq_argmin(z.view(M, -1), self.vq.codebook, out=tok0_out.view(-1))
+        f0 = self._token_features(tok0_out, B)
+        temb, _ = self._text_encoder(text)
+        anchor = self._ma_encoder(f0, temb, B, T).view(B, R, R, C)
+        if trace is not None:
+            trace["text_emb"], trace["first_img"], trace["anchor_ma"] = temb.view(B, T, C).clone(), f0.view(B, R * R, C).clone(), anchor.clone()
+        if noise is not None:
+            anchor = self._adain(anchor, noise, B)
+        if speed is not None:
+            ops.add_scaled_vec(anchor, speed, sd["speed_embedding"].view(-1))
+        if trace is not None:
+            trace["anchor"] = anchor.clone()
+
+        caches = {i: (torch.empty(M, L, C, device=self.device, dtype=torch.float32),
+                      torch.empty(M, L, C, device=self.device, dtype=torch.float32))
+                  for i in range(self.n_blocks) if i % 3 == 0}
+        x = ops.gemm(anchor.view(M, C), sd[p + "context_linear.weight"], self.bias_ctx0)
+        for i in range(self.n_blocks):
+            x = self._block_step(i, x, 0, B, caches)
+        tok = tok0_out
+        img_elems = video.shape[2] * video.shape[3] * video.shape[4]
+        logits = torch.empty(M, sd[p + "out.weight"].shape[0], device=self.device, dtype=torch.float32)
+        for j in range(L - 1):
+            f = self._token_features(tok, B)
+            x = ops.gemm(f, sd[p + "in_linear.weight"], self.bias_in_T[j + 1])
+            for i in range(self.n_blocks):
+                x = self._block_step(i, x, j + 1, B, caches)
+            ops.gemm(x, sd[p + "out.weight"], sd[p + "out.bias"], out=logits)
+            tok = ops.argmax_rows(logits, out=tokens[j].view(-1))
+            if trace is not None:
+                trace.setdefault("logits", []).append(logits.clone())
+            # decode this frame for every sample: video[b, j+1]
+            self.vq.decode_into(tok.view(B, R, R), video[:, j + 1], L * img_elems)
+
+    def generate(self, images0: torch.Tensor, text: torch.Tensor, speed: Optional[torch.Tensor] = None,
+                 noise: Optional[torch.Tensor] = None, trace: Optional[dict] = None):
+        """Returns (video [B,L,C,H,W] with frame 0 = images0, tokens i64 [B,L-1,R,R], tok0 i64 [B,R,R])."""
+        assert images0.is_cuda and text.is_cuda and text.dtype == torch.int64
+        if self.randomness:
+            assert noise is not None, "randomness=True needs the N(0,1) noise [B,64,R,R] (drawn by the caller on the CPU, mage_model.py:661)"
+        else:
+            noise = None
+        B, T = text.shape
+        R, L = self.R, self.L
+        images0 = images0.contiguous().float()
+        if not self.use_cuda_graph or trace is not None:
+            video = torch.empty(B, L, *images0.shape[1:], device=self.device, dtype=torch.float32)
+            tokens = torch.empty(L - 1, B, R * R, device=self.device, dtype=torch.int64)
+            tok0 = torch.empty(B, R * R, device=self.device, dtype=torch.int64)
+            n0 = ops.launch_count()
+            self._generate_impl(images0, text, speed, noise, video, tokens, tok0, trace)
+            self.kernels_per_generate = ops.launch_count() - n0
+            video[:, 0].copy_(images0)
+            return video, tokens.permute(1, 0, 2).reshape(B, L - 1, R, R), tok0.view(B, R, R)
+
+        key = (B, T, tuple(images0.shape[1:]), speed is not None, noise is not None)
+        st = self._graphs.get(key)
+        if st is None:
+            st = self._capture(key, images0, text, speed, noise)
+        st["images0"].copy_(images0)
+        st["text"].copy_(text)
+        if speed is not None:
+            st["speed"].copy_(speed)
+        if noise is not None:
+            st["noise"].copy_(noise)
+        st["graph"].replay()
+        video = st["video"]
+        video[:, 0].copy_(st["images0"])
+        return video, st["tokens"].permute(1, 0, 2).reshape(B, L - 1, R, R), st["tok0"].view(B, R, R)
+
+    def _capture(self, key, images0, text, speed, noise):
+        B, T = text.shape
+        R, L = self.R, self.L
+        dev = self.device
+        st = dict(images0=images0.clone(), text=text.clone(),
+                  speed=speed.clone() if speed is not None else None,
+                  noise=noise.clone() if noise is not None else None,
+                  video=torch.empty(B, L, *images0.shape[1:], device=dev, dtype=torch.float32),
+                  tokens=torch.empty(L - 1, B, R * R, device=dev, dtype=torch.int64),
+                  tok0=torch.empty(B, R * R, device=dev, dtype=torch.int64))
+        args = (st["images0"], st["text"], st["speed"], st["noise"], st["video"], st["tokens"], st["tok0"])
+        # warm-up on a side stream (sets kernel attributes, fills the allocator), then capture
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._generate_impl(*args)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        n0 = ops.launch_count()
+        with torch.cuda.graph(g):
+            self._generate_impl(*args)
+        self.kernels_per_generate = ops.launch_count() - n0
+        st["graph"] = g
+        self._graphs[key] = st
+        return st

@@ -1,0 +1,265 @@
+"""Drop-in classes for the reference's config-addressed plugin boundary.
+
+`modules.mage_model.MAGE`, `modules.vqvae_model.VectorQuantizedVAE` and the sub-module classes
+named as `target:` in config/*.yaml resolve (through the thin `modules/` package at the repo
+root) to the classes below.  They keep the constructor kwargs, `state_dict` key names/shapes and
+the two entry points of the sampling path -- `MAGE.autoregressive_generate(batch)` and
+`VectorQuantizedVAE.encode / decode` -- and run them on libmage_sm100.so.  They are parameter
+containers, not torch.nn compute graphs: there is no eager fallback, a CPU-resident model
+refuses to sample.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+from torch import nn
+
+from . import synthetic as syn
+from .config import instantiate_from_config
+
+_TRAIN_ONLY_PREFIXES = ("conv3d.", "conv_mu2.", "conv_var2.")  # mage_model.py:496-503, never run at sampling
+
+
+class ParamTree(nn.Module):
+    """nn.Module whose parameters/buffers are created from (dotted key, shape, kind) specs so
+    that `state_dict()` reproduces the reference's key layout exactly."""
+
+    def __init__(self, spec: Optional[syn.Spec] = None, seed: int = 0):
+        super().__init__()
+        if spec:
+            values = syn.make_state_dict(spec, seed)
+            for name, _, kind in spec:
+                self._add(name.split("."), values[name], buffer=kind in ("bn_mean", "bn_var", "count"))
+
+    def _add(self, parts: List[str], value: torch.Tensor, buffer: bool):
+        if len(parts) == 1:
+            if buffer:
+                self.register_buffer(parts[0], value)
+            else:
+                self.register_parameter(parts[0], nn.Parameter(value, requires_grad=False))
+            return
+        child = self._modules.get(parts[0])
+        if child is None:
+            child = ParamTree()
+            self.add_module(parts[0], child)
+        child._add(parts[1:], value, buffer)
+
+
+def _strip(spec: syn.Spec, prefix: str) -> syn.Spec:
+    return [(n[len(prefix):], s, k) for n, s, k in spec if n.startswith(prefix)]
+
+
+class _EngineOwner(nn.Module):
+    """Invalidates the packed-weight engine whenever tensors move or are reloaded."""
+
+    def __init__(self):
+        super().__init__()
+        self._engine = None
+
+    def _apply(self, fn, *a, **kw):
+        self._engine = None
+        return super()._apply(fn, *a, **kw)
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        self._engine = None
+        return super().load_state_dict(state_dict, strict=strict, **kw)
+
+    def _cuda_state(self) -> Dict[str, torch.Tensor]:
+        sd = {k: v.detach() for k, v in self.state_dict().items()}
+        dev = next(iter(sd.values())).device
+        if dev.type != "cuda":
+            raise RuntimeError("mage_b200 runs only on a CUDA device (sm_100a kernels, no CPU fallback): call .to('cuda') first")
+        return {k: (v.float().contiguous() if v.is_floating_point() else v) for k, v in sd.items()}
+
+
+class VectorQuantizedVAE(_EngineOwner):
+    """modules.vqvae_model.VectorQuantizedVAE (vqvae_model.py:168-248): same ctor, keys, encode/decode."""
+
+    def __init__(self, input_dim, down_ratio, dim, K=512, ckpt_path=None, ignore_keys=[]):
+        super().__init__()
+        spec = syn.vqvae_param_spec(input_dim, dim, down_ratio, K)
+        self.input_dim, self.down_ratio, self.dim, self.K = input_dim, down_ratio, dim, K
+        self.encoder = ParamTree(_strip(spec, "encoder."), seed=7)
+        self.decoder = ParamTree(_strip(spec, "decoder."), seed=8)
+        self.codebook = ParamTree(_strip(spec, "codebook."), seed=9)
+        self.embed_dim = dim if down_ratio == 4 else 4 * dim
+        if ckpt_path is not None:
+            self.init_from_ckpt(ckpt_path, ignore_keys=ignore_keys)
+
+    def init_from_ckpt(self, path, ignore_keys=list()):
+        """vqvae_model.py:222-231 (strict=False, keys starting with an ignore prefix dropped)."""
+        sd = torch.load(path, map_location="cpu")
+        for k in list(sd.keys()):
+            if any(k.startswith(ik) for ik in ignore_keys):
+                print("Deleting key {} from state_dict.".format(k))
+                del sd[k]
+        self.load_state_dict(sd, strict=False)
+        print(f"Restored from {path}")
+
+    def engine(self):
+        if self._engine is None:
+            from .engine import VQVAEEngine
+            self._engine = VQVAEEngine(self._cuda_state())
+        return self._engine
+
+    @torch.no_grad()
+    def encode(self, x):
+        """[N,C,H,W] float -> int64 [N,h,w] code indices (vqvae_model.py:233-237)."""
+        return self.engine().encode(x.float())
+
+    @torch.no_grad()
+    def decode(self, latents=None):
+        """int64 [N,h,w] -> [N,C,H,W] (vqvae_model.py:239-242)."""
+        return self.engine().decode(latents.to(torch.int64))
+
+    def forward(self, x):
+        raise NotImplementedError("stage-1 training (vqvae_model.py:244-248) is outside the sampling path (SURVEY.md §2)")
+
+
+class TransformerTextEncoder(ParamTree):
+    """mage_model.py:180-262 parameter layout; evaluated inside SamplerEngine._text_encoder."""
+
+    def __init__(self, vocab_size, transformer_width, transformer_layers, output_dim, context_length, padding_idx=0, dropout=0.1):
+        cfg = dict(text_encoder_config=dict(params=dict(vocab_size=vocab_size, transformer_width=transformer_width,
+                                                        transformer_layers=transformer_layers, output_dim=output_dim,
+                                                        context_length=context_length)))
+        super().__init__(_strip(_text_spec(cfg), "text_encoder."), seed=21)
+        self.padding_idx = padding_idx
+
+
+class MAEncoder(ParamTree):
+    """mage_model.py:104-117 parameter layout."""
+
+    def __init__(self, layers, d_model, dropout=0.1):
+        super().__init__(_strip(_ma_spec(layers, d_model), "ma_encoder."), seed=22)
+        self.layers, self.d_model = layers, d_model
+
+
+class FlatAxialDecoder(ParamTree):
+    """mage_model.py:317-390 parameter layout (use_cids=True head)."""
+
+    def __init__(self, in_channels, model_channels, out_channels, frames_length, layers, context_channels=None,
+                 use_cids=True, dropout=0.1):
+        if not use_cids:
+            raise NotImplementedError("MAGE+ continuous-latent head (use_cids=False) is not on the VQ sampling path (SURVEY.md F6, N1)")
+        super().__init__(_strip(_decoder_spec(in_channels, model_channels, out_channels, frames_length, layers,
+                                              context_channels or in_channels), "generate_model."), seed=23)
+        self.frames_length, self.layers = frames_length, layers
+
+
+def _full_spec_subset(params_like: dict, prefix: str) -> syn.Spec:
+    return [e for e in syn.mage_param_spec(params_like) if e[0].startswith(prefix)]
+
+
+def _template(**over) -> dict:
+    p = syn.model_params("caterv2")
+    p.update(over)
+    return p
+
+
+def _text_spec(cfg) -> syn.Spec:
+    p = _template()
+    p["text_encoder_config"]["params"].update(cfg["text_encoder_config"]["params"])
+    return _full_spec_subset(p, "text_encoder.")
+
+
+def _ma_spec(layers, d_model) -> syn.Spec:
+    p = _template()
+    p["ma_config"]["params"].update(layers=layers, d_model=d_model)
+    return _full_spec_subset(p, "ma_encoder.")
+
+
+def _decoder_spec(in_channels, model_channels, out_channels, frames_length, layers, context_channels) -> syn.Spec:
+    p = _template()
+    p["ma_config"]["params"].update(d_model=context_channels)
+    p["generate_decoder_config"]["params"].update(in_channels=in_channels, model_channels=model_channels,
+                                                  out_channels=out_channels, frames_length=frames_length, layers=layers)
+    return _full_spec_subset(p, "generate_model.")
+
+
+class MAGE(_EngineOwner):
+    """modules.mage_model.MAGE (mage_model.py:446-693), sampling path only."""
+
+    def __init__(self, first_stage_config, text_encoder_config, ma_config, generate_decoder_config, codebook_size: int,
+                 frames_length: int, image_resolution: int, vision_width: int, dropout: float = 0.1, use_cids=False,
+                 randomness=False, alpha=0., beta=1., v_kl=0., auto_beta=False):
+        super().__init__()
+        if not use_cids:
+            raise NotImplementedError("use_cids=False (MAGE+, AutoencoderKL first stage) is outside this path: parity unpinned (SURVEY.md F6)")
+        self.frames_length, self.image_resolution, self.vision_width = frames_length, image_resolution, vision_width
+        self.dropout, self.use_cids, self.randomness, self.codebook_size = dropout, use_cids, randomness, codebook_size
+        self.first_stage_model = instantiate_from_config(first_stage_config).eval()
+        for prm in self.first_stage_model.parameters():
+            prm.requires_grad = False
+        self.text_encoder = instantiate_from_config(text_encoder_config)
+        self.ma_encoder = instantiate_from_config(ma_config, {"dropout": dropout})
+        self.generate_model = instantiate_from_config(
+            generate_decoder_config, {"use_cids": use_cids, "dropout": dropout, "context_channels": ma_config["params"]["d_model"]})
+        d, R = vision_width, image_resolution
+        top: syn.Spec = [("visual_token_embedding.weight", (codebook_size, d), "normal:0.02"),
+                         ("conv.0.weight", (d, d, 3, 3), "conv"),
+                         ("speed_embedding", (1, d), f"normal:{d ** -0.5}"),
+                         ("H_positional_embedding", (1, R, 1, d), f"normal:{d ** -0.5}"),
+                         ("W_positional_embedding", (1, 1, R, d), f"normal:{d ** -0.5}")]
+        if randomness:
+            top.append(("conv_d2.weight", (d, 64, 3, 3), "conv"))
+            for br in ("conv_mu", "conv_var"):
+                for i in (0, 1):
+                    top.append((f"adain.{br}.{i}.weight", (d, d, 3, 3), "conv"))
+                    top.append((f"adain.{br}.{i}.bias", (d,), "bias"))
+        tree = ParamTree(top, seed=24)
+        for name, child in list(tree._modules.items()):
+            self.add_module(name, child)
+        for name, prm in list(tree._parameters.items()):
+            self.register_parameter(name, prm)
+        self.last_tokens = None
+        self.last_tok0 = None
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        """Accepts released checkpoints: the train-only tensors (3-D conv posterior etc.) are dropped."""
+        sd = {k: v for k, v in state_dict.items() if not k.startswith(_TRAIN_ONLY_PREFIXES)}
+        return super().load_state_dict(sd, strict=strict, **kw)
+
+    def engine(self):
+        if self._engine is None:
+            from .engine import SamplerEngine
+            self._engine = SamplerEngine(self._cuda_state(), self.frames_length, self.randomness,
+                                         padding_idx=getattr(self.text_encoder, "padding_idx", 0))
+        return self._engine
+
+    @torch.no_grad()
+    def first_stage_encode(self, x):
+        """mage_model.py:530-540: [B,T,C,H,W] -> [B,T,h,w] int64."""
+        out = self.first_stage_model.encode(x.reshape(-1, *x.shape[-3:]))
+        return out.view(*x.shape[:-3], *out.shape[1:])
+
+    @torch.no_grad()
+    def first_stage_decode(self, x):
+        """mage_model.py:551-567: [B,T,h,w] -> [B,T,C,H,W]."""
+        out = self.first_stage_model.decode(x.reshape(-1, *x.shape[-2:]))
+        return out.view(*x.shape[:2], *out.shape[1:])
+
+    @torch.no_grad()
+    def autoregressive_generate(self, batch, noise: Optional[torch.Tensor] = None):
+        """mage_model.py:641-693.  batch: 'images' [B,>=1,C,H,W] (frame 0 read), 'text' i64 [B,T], optional
+        'speed' [B].  Returns [B, frames_length, C, H, W]; frame 0 is the input frame.  With
+        randomness=True the N(0,1) noise [B,64,h,w] is drawn like the reference does -- on the CPU
+        default generator -- unless passed explicitly."""
+        eng = self.engine()
+        dev = eng.device
+        images0 = batch["images"][:, 0].to(dev, non_blocking=True)
+        text = batch["text"].to(dev, non_blocking=True)
+        speed = batch["speed"].to(dev, non_blocking=True).float() if "speed" in batch else None
+        if self.randomness:
+            if noise is None:
+                noise = torch.randn([text.shape[0], 64, self.image_resolution, self.image_resolution])
+            noise = noise.to(dev, non_blocking=True).float().contiguous()
+        video, tokens, tok0 = eng.generate(images0, text, speed, noise)
+        self.last_tokens, self.last_tok0 = tokens, tok0
+        # the engine's buffers are reused by the next call (CUDA graph); the reference hands out a fresh
+        # tensor that its caller clamps in place (main_mage.py:242)
+        return video.clone()
+
+    def forward(self, batch, test_flag=False):
+        raise NotImplementedError("stage-2 training objective (mage_model.py:575-639) is outside the sampling path (SURVEY.md §2, N2)")

@@ -1,0 +1,208 @@
+"""Thin Python wrappers over the C ABI (include/mage_b200.h): torch tensors in, raw device
+pointers + the current CUDA stream out.  torch is used only for memory and streams; every
+arithmetic operation on the sampling path is a kernel of libmage_sm100.so."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import check
+
+ACT_NONE, ACT_RELU, ACT_QUICKGELU, ACT_GELU, ACT_TANH = 0, 1, 2, 3, 4
+GEMM_SIMT, GEMM_TCGEN05 = 0, 1
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    assert t.is_cuda, "libmage_sm100 has no CPU path: tensor must live on a CUDA device"
+    return t.data_ptr()
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    assert t.dtype == torch.float32 and t.is_contiguous(), (t.dtype, t.shape, t.stride())
+    return t
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count() -> int:
+    return int(_lib.lib().mage_launch_count())
+
+
+def set_gemm_backend(backend: int) -> None:
+    check(_lib.lib().mage_set_gemm_backend(backend), "mage_set_gemm_backend")
+
+
+def get_gemm_backend() -> int:
+    return int(_lib.lib().mage_get_gemm_backend())
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, out: Optional[torch.Tensor] = None,
+         residual: Optional[torch.Tensor] = None, res_mod: int = 0, act: int = ACT_NONE, relu_a: bool = False) -> torch.Tensor:
+    """out[M,N] = act(a[M,K] @ w[N,K].T + bias) + residual.  `a` may be a row-strided 2-D view."""
+    assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1]
+    assert a.dtype == torch.float32 and a.stride(1) == 1 and w.is_contiguous()
+    M, K = a.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=torch.float32)
+    assert out.shape == (M, N) and out.stride(1) == 1
+    if residual is not None:
+        assert residual.dim() == 2 and residual.shape[1] == N and residual.stride(1) == 1
+    check(_lib.lib().mage_gemm_f32(_p(a), a.stride(0), _p(_f32(w)), w.stride(0), _p(bias), _p(residual),
+                                   residual.stride(0) if residual is not None else 0, res_mod, _p(out), out.stride(0),
+                                   M, N, K, act, int(relu_a), _stream()), "mage_gemm_f32")
+    return out
+
+
+def conv2d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, stride: int = 1, pad=(0, 0),
+           in_up: bool = False, residual: Optional[torch.Tensor] = None, res_mode: int = 0, relu_in: bool = False,
+           act: int = ACT_NONE, out: Optional[torch.Tensor] = None, out_hw=None, scatter=(1, 1, 0, 0),
+           full_hw=None, out_img_stride: Optional[int] = None) -> torch.Tensor:
+    """NHWC implicit-GEMM convolution.  x [N,Hin,Win,Cin], w [Cout,KH,KW,Cin] -> [N,Hout,Wout,Cout]
+    (or a scatter into `out` [N,Hfull,Wfull,Cout] for the sub-pixel phases of a transposed conv)."""
+    n, Hin, Win, Cin = x.shape
+    Cout, KH, KW, Cin2 = w.shape
+    assert Cin == Cin2
+    Hl, Wl = (Hin * 2, Win * 2) if in_up else (Hin, Win)
+    if out_hw is None:
+        out_hw = ((Hl + 2 * pad[0] - KH) // stride + 1, (Wl + 2 * pad[1] - KW) // stride + 1)
+    Hout, Wout = out_hw
+    sy, sx, oy, ox = scatter
+    if full_hw is None:
+        full_hw = (Hout * sy, Wout * sx)
+    Hfull, Wfull = full_hw
+    if out is None:
+        out = torch.empty(n, Hfull, Wfull, Cout, device=x.device, dtype=torch.float32)
+    if out_img_stride is None:
+        out_img_stride = Hfull * Wfull * Cout
+    if residual is not None and res_mode == 0:
+        res_mode = 1
+    check(_lib.lib().mage_conv2d_nhwc_f32(_p(_f32(x)), _p(_f32(w)), _p(bias), _p(residual), _p(out), n, Hin, Win, Cin,
+                                          Hout, Wout, Cout, KH, KW, stride, pad[0], pad[1], int(in_up), res_mode,
+                                          int(relu_in), act, sy, sx, oy, ox, Hfull, Wfull, out_img_stride, _stream()),
+          "mage_conv2d_nhwc_f32")
+    return out
+
+
+def conv2d_first(x_nchw: torch.Tensor, w_t: torch.Tensor, bias: Optional[torch.Tensor], *, cout: int, kh: int, kw: int,
+                 stride: int, pad: int, act: int = ACT_NONE) -> torch.Tensor:
+    n, Cin, H, W = x_nchw.shape
+    Hout = (H + 2 * pad - kh) // stride + 1
+    Wout = (W + 2 * pad - kw) // stride + 1
+    out = torch.empty(n, Hout, Wout, cout, device=x_nchw.device, dtype=torch.float32)
+    check(_lib.lib().mage_conv2d_first_f32(_p(_f32(x_nchw)), _p(_f32(w_t)), _p(bias), _p(out), n, Cin, H, W, Hout, Wout,
+                                           cout, kh, kw, stride, pad, act, _stream()), "mage_conv2d_first_f32")
+    return out
+
+
+def conv1x1_tanh_nchw(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, out: torch.Tensor, out_img_stride: int) -> None:
+    """x NHWC [N,H,W,Cin] -> tanh(conv1x1(relu(x))) written planar into `out` (image stride in elements)."""
+    n, H, W, Cin = x.shape
+    check(_lib.lib().mage_conv1x1_tanh_nchw_f32(_p(_f32(x)), _p(_f32(w)), _p(bias), _p(out), n, H * W, Cin, w.shape[0],
+                                                out_img_stride, _stream()), "mage_conv1x1_tanh_nchw_f32")
+
+
+def maxpool2x2(x: torch.Tensor) -> torch.Tensor:
+    n, H, W, C = x.shape
+    out = torch.empty(n, H // 2, W // 2, C, device=x.device, dtype=torch.float32)
+    check(_lib.lib().mage_maxpool2x2_nhwc_f32(_p(_f32(x)), _p(out), n, H, W, C, _stream()), "mage_maxpool2x2_nhwc_f32")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    C = x.shape[-1]
+    rows = x.numel() // C
+    if out is None:
+        out = torch.empty_like(x)
+    check(_lib.lib().mage_layernorm_f32(_p(_f32(x)), _p(gamma), _p(beta), _p(out), rows, C, eps, _stream()),
+          "mage_layernorm_f32")
+    return out
+
+
+def mha(q, k, v, out, *, n_outer, n_inner, n_head, Sq, Sk, q_strides, k_strides, v_strides, o_strides,
+        key_len: Optional[torch.Tensor] = None, scale: float) -> None:
+    """Strided SDPA core (head_dim 32).  *_strides = (outer, inner, seq) in elements; q/k/v/out may be
+    views into one packed qkv buffer (pass the view: its data_ptr carries the column offset)."""
+    check(_lib.lib().mage_mha_f32(_p(q), _p(k), _p(v), _p(out), n_outer, n_inner, n_head, Sq, Sk, *q_strides, *k_strides,
+                                  *v_strides, *o_strides, _p(key_len), scale, _stream()), "mage_mha_f32")
+
+
+def temporal_attn_step(qkv: torch.Tensor, kcache: torch.Tensor, vcache: torch.Tensor, out: torch.Tensor, pos: int,
+                       scale: float) -> None:
+    M = qkv.shape[0]
+    Lmax = kcache.shape[1]
+    check(_lib.lib().mage_temporal_attn_step_f32(_p(_f32(qkv)), _p(kcache), _p(vcache), _p(out), M, pos, Lmax, scale,
+                                                 _stream()), "mage_temporal_attn_step_f32")
+
+
+def kv_append(qkv: torch.Tensor, kcache: torch.Tensor, vcache: torch.Tensor, pos: int) -> None:
+    M, C3 = qkv.shape
+    check(_lib.lib().mage_kv_append_f32(_p(_f32(qkv)), _p(kcache), _p(vcache), M, C3 // 3, pos, kcache.shape[1], _stream()),
+          "mage_kv_append_f32")
+
+
+def vq_argmin(z: torch.Tensor, codebook: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """z [N,D] fp32, codebook [K,D] -> int64 [N] nearest-code indices (vqvae_model.py:8-25)."""
+    N, D = z.shape
+    K = codebook.shape[0]
+    if out is None:
+        out = torch.empty(N, device=z.device, dtype=torch.int64)
+    scratch = torch.empty(K, device=z.device, dtype=torch.float32)
+    check(_lib.lib().mage_vq_argmin_f32(_p(_f32(z)), _p(_f32(codebook)), _p(scratch), _p(out), N, D, K, _stream()),
+          "mage_vq_argmin_f32")
+    return out
+
+
+def argmax_rows(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    rows, N = x.shape
+    if out is None:
+        out = torch.empty(rows, device=x.device, dtype=torch.int64)
+    check(_lib.lib().mage_argmax_rows_f32(_p(x), x.stride(0), _p(out), rows, N, _stream()), "mage_argmax_rows_f32")
+    return out
+
+
+def embedding(idx: torch.Tensor, table: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    assert idx.dtype == torch.int64 and idx.is_contiguous()
+    rows, C = idx.numel(), table.shape[1]
+    if out is None:
+        out = torch.empty(*idx.shape, C, device=table.device, dtype=torch.float32)
+    check(_lib.lib().mage_embedding_f32(_p(idx), _p(_f32(table)), _p(out), rows, C, _stream()), "mage_embedding_f32")
+    return out
+
+
+def text_embed(text: torch.Tensor, tok_emb, pos_emb, gamma, beta, pad_idx: int, eps: float):
+    B, T = text.shape
+    C = tok_emb.shape[1]
+    x = torch.empty(B, T, C, device=tok_emb.device, dtype=torch.float32)
+    key_len = torch.empty(B, device=tok_emb.device, dtype=torch.int32)
+    check(_lib.lib().mage_text_embed_f32(_p(text), _p(tok_emb), _p(pos_emb), _p(gamma), _p(beta), _p(x), _p(key_len), B, T, C,
+                                         pad_idx, eps, _stream()), "mage_text_embed_f32")
+    return x, key_len
+
+
+def adain(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    n, H, W, C = x.shape
+    out = torch.empty_like(x)
+    check(_lib.lib().mage_adain_nhwc_f32(_p(_f32(x)), _p(_f32(gamma)), _p(_f32(beta)), _p(out), n, H * W, C, eps, _stream()),
+          "mage_adain_nhwc_f32")
+    return out
+
+
+def add_scaled_vec(x: torch.Tensor, s: torch.Tensor, vec: torch.Tensor) -> None:
+    n, C = x.shape[0], x.shape[-1]
+    check(_lib.lib().mage_add_scaled_vec_f32(_p(_f32(x)), _p(s), _p(vec), n, x.numel() // (n * C), C, _stream()),
+          "mage_add_scaled_vec_f32")
+
+
+def nchw_to_nhwc(x: torch.Tensor) -> torch.Tensor:
+    n, C, H, W = x.shape
+    out = torch.empty(n, H, W, C, device=x.device, dtype=torch.float32)
+    check(_lib.lib().mage_nchw_to_nhwc_f32(_p(_f32(x)), _p(out), n, C, H * W, _stream()), "mage_nchw_to_nhwc_f32")
+    return out

@@ -60,31 +60,63 @@ def _install_shims() -> None:
         sys.modules["ldm.models.autoencoder"] = ae
 
 
+_REF_NAMES = ("modules", "modules.vqvae_model", "modules.mage_model", "utils", "utils.util")
+_ref_cache = {}
+
+
+def _exec_reference_modules():
+    """Execute the reference's source files under their own import names (`modules.*`, `utils.*`).
+    This repo has same-named drop-in packages (regular packages beat the reference's namespace
+    packages on sys.path), so the files are loaded explicitly by path and the names are swapped in
+    only while the reference code runs its imports."""
+    import importlib.util
+
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules)
+             if k in ("modules", "utils") or k.startswith("modules.") or k.startswith("utils.")}
+    try:
+        for pkg in ("modules", "utils"):
+            m = types.ModuleType(pkg)
+            m.__path__ = [os.path.join(REFERENCE_ROOT, pkg)]
+            sys.modules[pkg] = m
+        for name in ("utils.util", "modules.vqvae_model", "modules.mage_model"):
+            path = os.path.join(REFERENCE_ROOT, *name.split(".")) + ".py"
+            spec = importlib.util.spec_from_file_location(name, path)
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules[name] = mod
+            spec.loader.exec_module(mod)
+        for k in _REF_NAMES:
+            _ref_cache[k] = sys.modules[k]
+    finally:
+        for k in list(sys.modules):
+            if k in ("modules", "utils") or k.startswith("modules.") or k.startswith("utils."):
+                del sys.modules[k]
+        sys.modules.update(saved)
+
+
+class _reference_names:
+    """Context manager: `modules.*` / `utils.*` resolve to the reference while active
+    (its instantiate_from_config imports targets by dotted path, utils/util.py:58-63)."""
+
+    def __enter__(self):
+        self.saved = {k: sys.modules.get(k) for k in _REF_NAMES}
+        sys.modules.update(_ref_cache)
+
+    def __exit__(self, *exc):
+        for k, v in self.saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
 def load_reference():
     """Returns (mage_model module, vqvae_model module) of the real reference."""
     if not reference_available():
         raise RuntimeError(f"reference not found at {REFERENCE_ROOT}")
     _install_shims()
-    # the reference addresses its packages as top-level `modules.*` / `utils.*`; this repo
-    # has same-named drop-in packages, so temporarily make /root/reference win.
-    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "modules" or k.startswith("modules.")
-             or k == "utils" or k.startswith("utils.")}
-    sys.path.insert(0, REFERENCE_ROOT)
-    try:
-        mm = importlib.import_module("modules.mage_model")
-        vq = importlib.import_module("modules.vqvae_model")
-        ref_mods = {k: sys.modules[k] for k in list(sys.modules) if k == "modules" or k.startswith("modules.")
-                    or k == "utils" or k.startswith("utils.")}
-    finally:
-        sys.path.remove(REFERENCE_ROOT)
-        for k in list(sys.modules):
-            if k == "modules" or k.startswith("modules.") or k == "utils" or k.startswith("utils."):
-                del sys.modules[k]
-        sys.modules.update(saved)
-    # keep the reference modules alive under private names (their functions still work)
-    for k, v in ref_mods.items():
-        sys.modules["_mage_reference." + k] = v
-    return mm, vq
+    if not _ref_cache:
+        _exec_reference_modules()
+    return _ref_cache["modules.mage_model"], _ref_cache["modules.vqvae_model"]
 
 
 def to_dictconfig(obj):
@@ -100,20 +132,9 @@ def build_reference_mage(params: dict, state_dict: dict):
     import torch
 
     mm, _ = load_reference()
-    # instantiate_from_config inside the reference resolves `modules.*` targets by import;
-    # expose the reference modules under those names for the duration of construction.
-    saved = {k: sys.modules.get(k) for k in ("modules", "modules.mage_model", "modules.vqvae_model", "utils", "utils.util")}
-    for k in saved:
-        sys.modules[k] = sys.modules["_mage_reference." + k]
-    try:
+    with _reference_names():
         torch.manual_seed(0)
         model = mm.MAGE(**to_dictconfig(params))
-    finally:
-        for k, v in saved.items():
-            if v is None:
-                sys.modules.pop(k, None)
-            else:
-                sys.modules[k] = v
     missing, unexpected = model.load_state_dict(state_dict, strict=False)
     assert not unexpected, unexpected
     bad = [k for k in missing if not (k.startswith("conv3d.") or k.startswith("conv_mu2") or k.startswith("conv_var2"))]

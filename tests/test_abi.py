@@ -1,0 +1,32 @@
+"""CPU: the C-ABI library builds/loads and exports every symbol include/mage_b200.h declares
+(no compute calls without a GPU)."""
+import os
+import re
+
+from mage_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "mage_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mage_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.isfile(_lib.LIB_PATH):
+        _lib.build()
+    L = _lib.lib()
+    names = _declared()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/mage_b200.h but not exported"
+    assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)
+    assert L.mage_abi_version() == 1
+    assert L.mage_launch_count() >= 0
+
+
+def test_header_cites_reference_lines():
+    text = open(os.path.join(ROOT, "include", "mage_b200.h")).read()
+    assert text.count("mage_model.py:") >= 8 and text.count("vqvae_model.py:") >= 6
