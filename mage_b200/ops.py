@@ -30,6 +30,28 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+# Optional per-launch CUDA-event instrumentation of the GEMM-class kernels (bench.py's roofline leg):
+# when PROFILE is a list, gemm()/conv2d() append (kind, flops, start_event, end_event) around the launch.
+PROFILE = None
+
+
+class _Prof:
+    def __init__(self, kind: str, flops: float):
+        self.kind, self.flops = kind, flops
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record(torch.cuda.current_stream())
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.e1.record(torch.cuda.current_stream())
+            PROFILE.append((self.kind, self.flops, self.e0, self.e1))
+
+
 def launch_count() -> int:
     return int(_lib.lib().mage_launch_count())
 
@@ -54,9 +76,10 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     assert out.shape == (M, N) and out.stride(1) == 1
     if residual is not None:
         assert residual.dim() == 2 and residual.shape[1] == N and residual.stride(1) == 1
-    check(_lib.lib().mage_gemm_f32(_p(a), a.stride(0), _p(_f32(w)), w.stride(0), _p(bias), _p(residual),
-                                   residual.stride(0) if residual is not None else 0, res_mod, _p(out), out.stride(0),
-                                   M, N, K, act, int(relu_a), _stream()), "mage_gemm_f32")
+    with _Prof("gemm", 2.0 * M * N * K):
+        check(_lib.lib().mage_gemm_f32(_p(a), a.stride(0), _p(_f32(w)), w.stride(0), _p(bias), _p(residual),
+                                       residual.stride(0) if residual is not None else 0, res_mod, _p(out), out.stride(0),
+                                       M, N, K, act, int(relu_a), _stream()), "mage_gemm_f32")
     return out
 
 
@@ -83,10 +106,11 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
         out_img_stride = Hfull * Wfull * Cout
     if residual is not None and res_mode == 0:
         res_mode = 1
-    check(_lib.lib().mage_conv2d_nhwc_f32(_p(_f32(x)), _p(_f32(w)), _p(bias), _p(residual), _p(out), n, Hin, Win, Cin,
-                                          Hout, Wout, Cout, KH, KW, stride, pad[0], pad[1], int(in_up), res_mode,
-                                          int(relu_in), act, sy, sx, oy, ox, Hfull, Wfull, out_img_stride, _stream()),
-          "mage_conv2d_nhwc_f32")
+    with _Prof("conv", 2.0 * n * Hout * Wout * Cout * KH * KW * Cin):
+        check(_lib.lib().mage_conv2d_nhwc_f32(_p(_f32(x)), _p(_f32(w)), _p(bias), _p(residual), _p(out), n, Hin, Win, Cin,
+                                              Hout, Wout, Cout, KH, KW, stride, pad[0], pad[1], int(in_up), res_mode,
+                                              int(relu_in), act, sy, sx, oy, ox, Hfull, Wfull, out_img_stride, _stream()),
+              "mage_conv2d_nhwc_f32")
     return out
 
 
