@@ -40,16 +40,10 @@ extern "C" {
 #define MAGE_ACT_POST_RES 0x100 /* apply the activation after the residual add: act(x + bias + residual) */
 #define MAGE_RES_RELU 0x200     /* read the residual through a ReLU (in-place ReLU skip of ResBlock, vqvae_model.py:114-124) */
 
-/* GEMM back ends (mage_set_gemm_backend) */
-#define MAGE_GEMM_SIMT 0     /* fp32 FFMA register-tiled */
-#define MAGE_GEMM_TCGEN05 1  /* tcgen05.mma kind::tf32, 3xTF32 split, TMEM accumulators, TMA operands */
-
 /* Library info / bookkeeping */
-int mage_abi_version(void);
+int mage_abi_version(void); /* 2 */
 /* Number of kernels launched through this library by the calling process so far. */
 int64_t mage_launch_count(void);
-int mage_set_gemm_backend(int backend);
-int mage_get_gemm_backend(void);
 
 /* C[M,N] = act(relu_a?(A)[M,K] . W[N,K]^T + bias[N]) + residual
  * residual row for output row m is (res_mod > 0 ? m % res_mod : m), leading dim ldr; may alias C.
@@ -77,6 +71,46 @@ int mage_conv2d_nhwc_f32(const float* in, const float* w, const float* bias, con
                          int in_up, int res_mode, int relu_in, int act,
                          int out_sy, int out_sx, int out_oy, int out_ox, int Hfull, int Wfull,
                          int64_t out_img_stride, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Tensor-core back end (tcgen05.mma + TMEM accumulators + TMA operand tiles), fp32-grade.
+ *
+ * "split" tensors: an fp32 tensor [rows, C] carried as two fp16 planes (hi at `ptr`, lo at
+ * `ptr + plane` elements): x ~= hi + lo * 2^-11 to ~2^-24 relative for |x| < 65504.  Every product is
+ * three fp16 MMAs with fp32 accumulation (hi*hi, lo*hi, hi*lo), i.e. fp32-grade results at a third
+ * of the fp16 tensor rate.  `flag` (device int, may be NULL) is OR-ed with 1 when a value outside
+ * the fp16 range is split -- callers check it instead of trusting a saturated result.
+ * --------------------------------------------------------------------------------------------- */
+
+/* out(split)[r, :] = split(relu?(x[r, :])); x row stride ldx (elements), C % 4 == 0. */
+int mage_split_f32(const float* x, int64_t ldx, void* out, int64_t plane, int rows, int C, int relu, int* flag,
+                   void* stream);
+
+/* out(split)[r, :] = table(split)[idx[r], :]   (nn.Embedding on a pre-split table: mage_model.py:644,682;
+ * vqvae_model.py:240).  C % 8 == 0. */
+int mage_embedding_split(const int64_t* idx, const void* table, int64_t table_plane, void* out, int64_t out_plane,
+                         int rows, int C, void* stream);
+
+/* C[M,N] = act(A[M,K] . W[N,K]^T + bias[N]) (+ residual), A and W split tensors (row strides lda/ldw in
+ * elements), K % 64 == 0, N % 64 == 0 (else MAGE_ENOTSUP: use mage_gemm_f32).  Any of the three outputs
+ * may be NULL: C fp32 [M,N] (ldc), C_split = split(result), C_split_relu = split(relu(result)) -- the
+ * operand format of the next tensor-core op -- all with row stride ldc and plane stride c_plane.
+ * act / residual semantics as mage_gemm_f32.  Same reference call sites as mage_gemm_f32. */
+int mage_gemm_tc(const void* A, int64_t lda, int64_t a_plane, const void* W, int64_t ldw, int64_t w_plane,
+                 const float* bias, const float* residual, int64_t ldr, int res_mod, float* C, void* C_split,
+                 void* C_split_relu, int64_t ldc, int64_t c_plane, int M, int N, int K, int act, int* flag,
+                 void* stream);
+
+/* Stride-1 NHWC convolution as a tcgen05 implicit GEMM: the A tile of tap (ky,kx) is a TMA box of the
+ * split input [n_img,Hin,Win,Cin] shifted by (ky-pad_y, kx-pad_x); out-of-bounds zero fill is the padding.
+ * w split [Cout][KH][KW][Cin]; Cin % 64 == 0, Cout % 64 == 0, 128 % min(Wout,128) == 0 (else MAGE_ENOTSUP).
+ * Output scatter / residual modes as mage_conv2d_nhwc_f32; outputs as mage_gemm_tc.  Same reference call
+ * sites as mage_conv2d_nhwc_f32. */
+int mage_conv2d_tc(const void* in, int64_t in_plane, const void* w, int64_t w_plane, const float* bias,
+                   const float* residual, float* out, void* out_split, void* out_split_relu, int64_t out_plane,
+                   int n_img, int Hin, int Win, int Cin, int Hout, int Wout, int Cout, int KH, int KW, int pad_y,
+                   int pad_x, int res_mode, int act, int out_sy, int out_sx, int out_oy, int out_ox, int Hfull,
+                   int Wfull, int64_t out_img_stride, int* flag, void* stream);
 
 /* First-layer convolution from a planar NCHW image with a tiny channel count (Cin <= 4):
  * in [N,Cin,H,W], w_t [Cin*KH*KW][Cout] (transposed), out NHWC [N,Hout,Wout,Cout], optional ReLU.

@@ -1,11 +1,11 @@
-// fp32 FFMA register-tiled GEMM / implicit-GEMM convolution (the MAGE_GEMM_SIMT back end).
+// fp32 FFMA register-tiled GEMM / implicit-GEMM convolution (the fp32-exact back end).
 //
 //   C[M,N] = act(A[M,K] . W[N,K]^T + bias) + residual
 //
 // Both operands are K-contiguous ("TN"): nn.Linear weights are [out,in] and conv weights are
 // packed [Cout][KH][KW][Cin], so one kernel serves nn.Linear, 1x1 convs and -- with the A tile
 // gathered on the fly from an NHWC image -- every 3x3 / 4x4 / sub-pixel convolution on the path.
-// The kernel is the fp32-exact fall-back and the in-GPU reference for the tcgen05 back end.
+// It serves every shape the tensor-core back end (gemm_tc.cu) does not take and is its in-GPU reference.
 #include "common.cuh"
 
 namespace {
@@ -245,10 +245,10 @@ int launch(const GemmArgs& a, cudaStream_t st) {
 
 }  // namespace
 
-// Called by the dispatcher in gemm_dispatch.cu
-int mage_gemm_simt(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
-                   const float* residual, int64_t ldr, int res_mod, float* C, int64_t ldc,
-                   int M, int N, int K, int act, int relu_a, cudaStream_t st) {
+extern "C" int mage_gemm_f32(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
+                             const float* residual, int64_t ldr, int res_mod, float* C, int64_t ldc,
+                             int M, int N, int K, int act, int relu_a, void* stream) {
+  cudaStream_t st = as_stream(stream);
   MAGE_CHECK_ARG(M > 0 && N > 0 && K > 0 && (K % 4) == 0 && (lda % 4) == 0 && (ldw % 4) == 0);
   MAGE_CHECK_ARG(aligned16(A) && aligned16(W));
   GemmArgs a{};

@@ -1,8 +1,477 @@
-// tcgen05 GEMM back end -- placeholder until the TMA/TMEM kernel lands (returns ENOTSUP so the
-// dispatcher uses the FFMA kernel).
-#include "common.cuh"
+// Tensor-core back end: fp32-grade GEMM and implicit-GEMM convolution on tcgen05 (sm_100a).
+//
+//   C[M,N] = act(A[M,K] . W[N,K]^T + bias) (+ residual)
+//
+// Operands arrive in the fp16 hi/lo split format (tc_common.cuh): every k-step issues three
+// tcgen05.mma kind::f16 instructions (hi*hi -> main, lo*hi + hi*lo -> corr), both accumulators live
+// in TMEM, the epilogue forms main + corr*2^-11 -- fp32-grade accuracy at a third of the fp16 rate.
+//
+// One persistent CTA per SM, 192 threads, warp-specialised:
+//   warp 0   TMA producer: one 5-D box for the A tile (both planes) + one 3-D box for the W tile per
+//            k-block into a SWIZZLE_128B ring (mbarrier full/empty)
+//   warp 1   TMEM allocator + the single MMA-issuing thread (tcgen05.mma, tcgen05.commit)
+//   warps 2-5 epilogue: tcgen05.ld -> smem transpose -> bias / activation / residual -> coalesced
+//            fp32 and/or split stores (the next consumer's operand format)
+// For a convolution the A tile is an NHWC patch: the box is [64 ch, Wb, Hb, 1 image, 2 planes] at
+// the tap's (dy,dx) offset and TMA's out-of-bounds zero fill is the padding, so im2col never exists.
+#include <cuda.h>
 
-int mage_gemm_tc(const float*, int64_t, const float*, int64_t, const float*, const float*, int64_t, int, float*, int64_t,
-                 int, int, int, int, int, cudaStream_t) {
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace tc;
+
+constexpr int BM = 128;      // rows per tile = TMEM lanes
+constexpr int BK = 64;       // halves per k-block = one 128-byte swizzle row
+constexpr int UK = 16;       // K of one tcgen05.mma kind::f16
+constexpr int NTHREADS = 192;
+constexpr int STG_LD = 36;   // floats per staging row (32 + 4 pad: float4-aligned, conflict-free)
+constexpr int SMEM_BUDGET = 227 * 1024;
+
+struct TcParams {
+  const float* bias;
+  const float* res;
+  float* out;
+  __half* split;
+  __half* split_relu;
+  int* flag;
+  int64_t ldr, ldc, split_plane, split_relu_plane, out_img_stride;
+  int M, N, act, res_mod;
+  int m_tiles, n_tiles, k_iters;
+  // convolution geometry (conv != 0)
+  int conv, Hout, Wout, Wb, Hb, KW, cin_blocks, cin, pad_y, pad_x;
+  int res_mode, out_sy, out_sx, out_oy, out_ox, Hfull, Wfull;
+};
+
+template <int BN>
+struct Cfg {
+  static constexpr int A_BYTES = 2 * BM * BK * 2;   // hi + lo planes
+  static constexpr int W_BYTES = 2 * BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
+  static constexpr int STAGING_BYTES = 4 * 32 * STG_LD * 4;
+  static constexpr int STAGES_RAW = (SMEM_BUDGET - 1024 - STAGING_BYTES - 256) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+  static constexpr int ACC_STAGES = (2 * BN * 2 <= 512) ? 2 : 1;   // main+corr per accumulator stage
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, const TcParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  float* staging = reinterpret_cast<float*>(base_ptr + C::STAGES * C::STAGE_BYTES);
+  const uint32_t bar_base = base + C::STAGES * C::STAGE_BYTES + C::STAGING_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + 2 + a); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + C::STAGES * C::STAGE_BYTES + C::STAGING_BYTES +
+                                                                      8 * (2 * C::STAGES + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapW);
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int itg = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+        int c1 = mt * BM, c2 = 0, c3 = 0;
+        if (p.conv) {
+          const int tiles_x = p.Wout / p.Wb, tiles_y = p.Hout / p.Hb;
+          const int img = mt / (tiles_x * tiles_y), r = mt - img * tiles_x * tiles_y;
+          const int ty = r / tiles_x, tx = r - ty * tiles_x;
+          c1 = tx * p.Wb - p.pad_x;
+          c2 = ty * p.Hb - p.pad_y;
+          c3 = img;
+        }
+        for (int it = 0; it < p.k_iters; ++it, ++itg) {
+          const int s = itg % C::STAGES;
+          const uint32_t ph = (itg / C::STAGES) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          mbar_expect_tx(full_bar(s), C::STAGE_BYTES);
+          const uint32_t sa = base + s * C::STAGE_BYTES;
+          if (p.conv) {
+            const int tap = it / p.cin_blocks, cb = it - tap * p.cin_blocks;
+            const int ky = tap / p.KW, kx = tap - ky * p.KW;
+            tma_load_5d(sa, &mapA, full_bar(s), cb * BK, c1 + kx, c2 + ky, c3, 0);
+          } else {
+            tma_load_5d(sa, &mapA, full_bar(s), it * BK, c1, 0, 0, 0);
+          }
+          tma_load_3d(sa + C::A_BYTES, &mapW, full_bar(s), it * BK, nt * BN, 0);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BN);
+      int itg = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+        const int acc = tcount % C::ACC_STAGES;
+        const uint32_t aph = (tcount / C::ACC_STAGES) & 1;
+        mbar_wait(tempty_bar(acc), aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_main = tmem_base + acc * 2 * BN, d_corr = d_main + BN;
+        for (int it = 0; it < p.k_iters; ++it, ++itg) {
+          const int s = itg % C::STAGES;
+          const uint32_t ph = (itg / C::STAGES) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = base + s * C::STAGE_BYTES;
+          const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + BM * BK * 2);
+          const uint64_t w_hi = umma_desc_sw128(sa + C::A_BYTES), w_lo = umma_desc_sw128(sa + C::A_BYTES + BN * BK * 2);
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k) {
+            const uint64_t adv = (uint64_t)((k * UK * 2) >> 4);  // +32 B per k-step inside the swizzle row
+            const uint32_t accum = (it > 0 || k > 0) ? 1u : 0u;
+            umma_f16(d_corr, a_lo + adv, w_hi + adv, idesc, accum);
+            umma_f16(d_corr, a_hi + adv, w_lo + adv, idesc, 1u);
+            umma_f16(d_main, a_hi + adv, w_hi + adv, idesc, accum);
+          }
+          umma_commit(empty_bar(s));
+        }
+        umma_commit(tfull_bar(acc));
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------ epilogue warps (TMEM lane quadrant = warp % 4)
+    const int quad = warp & 3;
+    float* stg = staging + (warp - 2) * 32 * STG_LD;
+    const int cq = lane & 7, rq = lane >> 3;
+    const int act = p.act & 0xff;
+    const bool post = (p.act & MAGE_ACT_POST_RES) != 0, res_relu = (p.act & MAGE_RES_RELU) != 0;
+    int tcount = 0;
+    bool overflow = false;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+      const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+      const int acc = tcount % C::ACC_STAGES;
+      const uint32_t aph = (tcount / C::ACC_STAGES) & 1;
+      // output / residual row offsets of the 8 rows this lane stores (rows quad*32 + i*4 + rq)
+      int64_t out_off[8], res_off[8];
+      bool row_ok[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = quad * 32 + i * 4 + rq;
+        const int m = mt * BM + r;
+        row_ok[i] = m < p.M;
+        out_off[i] = 0;
+        res_off[i] = -1;
+        if (!row_ok[i]) continue;
+        if (p.conv) {
+          const int tiles_x = p.Wout / p.Wb, tiles_y = p.Hout / p.Hb;
+          const int img = mt / (tiles_x * tiles_y), rr = mt - img * tiles_x * tiles_y;
+          const int ty = rr / tiles_x, tx = rr - ty * tiles_x;
+          const int oy = ty * p.Hb + r / p.Wb, ox = tx * p.Wb + r % p.Wb;
+          out_off[i] = (int64_t)img * p.out_img_stride +
+                       ((int64_t)(oy * p.out_sy + p.out_oy) * p.Wfull + (ox * p.out_sx + p.out_ox)) * p.ldc;
+          if (p.res_mode == 1) res_off[i] = (((int64_t)img * p.Hout + oy) * p.Wout + ox) * p.ldr;
+          else if (p.res_mode == 2) res_off[i] = (((int64_t)img * (p.Hout >> 1) + (oy >> 1)) * (p.Wout >> 1) + (ox >> 1)) * p.ldr;
+          else if (p.res_mode == 3) res_off[i] = ((int64_t)oy * p.Wout + ox) * p.ldr;
+        } else {
+          out_off[i] = (int64_t)m * p.ldc;
+          if (p.res) res_off[i] = (int64_t)(p.res_mod > 0 ? m % p.res_mod : m) * p.ldr;
+        }
+      }
+      mbar_wait(tfull_bar(acc), aph);
+      tc_fence_after();
+      const uint32_t t_main = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 2 * BN, t_corr = t_main + BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t rm[32], rc[32];
+        tmem_ld32(t_main + c * 32, rm);
+        tmem_ld32(t_corr + c * 32, rc);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 v;
+          v.x = fmaf(__uint_as_float(rc[4 * j + 0]), kLoInv, __uint_as_float(rm[4 * j + 0]));
+          v.y = fmaf(__uint_as_float(rc[4 * j + 1]), kLoInv, __uint_as_float(rm[4 * j + 1]));
+          v.z = fmaf(__uint_as_float(rc[4 * j + 2]), kLoInv, __uint_as_float(rm[4 * j + 2]));
+          v.w = fmaf(__uint_as_float(rc[4 * j + 3]), kLoInv, __uint_as_float(rm[4 * j + 3]));
+          *reinterpret_cast<float4*>(stg + lane * STG_LD + 4 * j) = v;
+        }
+        __syncwarp();
+        const int n = nt * BN + c * 32 + cq * 4;
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (!row_ok[i]) continue;
+          float4 v = *reinterpret_cast<const float4*>(stg + (i * 4 + rq) * STG_LD + cq * 4);
+          v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+          if (!post) { v.x = mage_act(v.x, act); v.y = mage_act(v.y, act); v.z = mage_act(v.z, act); v.w = mage_act(v.w, act); }
+          if (res_off[i] >= 0) {
+            float4 rv = __ldg(reinterpret_cast<const float4*>(p.res + res_off[i] + n));
+            if (res_relu) { rv.x = fmaxf(rv.x, 0.f); rv.y = fmaxf(rv.y, 0.f); rv.z = fmaxf(rv.z, 0.f); rv.w = fmaxf(rv.w, 0.f); }
+            v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+          }
+          if (post) { v.x = mage_act(v.x, act); v.y = mage_act(v.y, act); v.z = mage_act(v.z, act); v.w = mage_act(v.w, act); }
+          const int64_t o = out_off[i] + n;
+          if (p.out) *reinterpret_cast<float4*>(p.out + o) = v;
+          if (p.split) {
+            uint2 hi, lo;
+            overflow |= split4(v, hi, lo);
+            *reinterpret_cast<uint2*>(p.split + o) = hi;
+            *reinterpret_cast<uint2*>(p.split + p.split_plane + o) = lo;
+          }
+          if (p.split_relu) {
+            uint2 hi, lo;
+            const float4 rv = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+            overflow |= split4(rv, hi, lo);
+            *reinterpret_cast<uint2*>(p.split_relu + o) = hi;
+            *reinterpret_cast<uint2*>(p.split_relu + p.split_relu_plane + o) = lo;
+          }
+        }
+        __syncwarp();
+      }
+      // accumulator drained: hand the TMEM stage back to the MMA thread
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+    if (overflow && p.flag) atomicOr(p.flag, 1);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ split conversion
+__global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ x, int64_t ldx, __half* __restrict__ out,
+                                                    int64_t plane, int rows, int C4, int relu, int* flag) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)rows * C4) return;
+  const int row = (int)(t / C4), c = (int)(t - (int64_t)row * C4);
+  float4 v = __ldg(reinterpret_cast<const float4*>(x + (int64_t)row * ldx) + c);
+  if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+  uint2 hi, lo;
+  const bool bad = split4(v, hi, lo);
+  const int64_t o = ((int64_t)row * C4 + c) * 4;
+  *reinterpret_cast<uint2*>(out + o) = hi;
+  *reinterpret_cast<uint2*>(out + plane + o) = lo;
+  if (bad && flag) atomicOr(flag, 1);
+}
+
+// out[r, :] (both planes) = table[idx[r], :] (both planes): nn.Embedding on a pre-split table
+__global__ void __launch_bounds__(256) embedding_split_kernel(const int64_t* __restrict__ idx, const __half* __restrict__ table,
+                                                              int64_t table_plane, __half* __restrict__ out, int64_t out_plane,
+                                                              int rows, int C8) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)rows * C8 * 2) return;
+  const int pl = (int)(t / ((int64_t)rows * C8));
+  const int64_t u = t - (int64_t)pl * rows * C8;
+  const int row = (int)(u / C8), c = (int)(u - (int64_t)row * C8);
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(table + pl * table_plane + idx[row] * (int64_t)C8 * 8) + c);
+  reinterpret_cast<uint4*>(out + pl * out_plane)[u] = v;
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+int num_sms() {
+  static int n = [] {
+    int dev = 0, v = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v > 0 ? v : 148;
+  }();
+  return n;
+}
+
+// rank-R fp16 tensor map, SWIZZLE_128B, zero OOB fill.  dims/box innermost first; strides in bytes for dims 1..R-1.
+int make_map(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return MAGE_ENOTSUP;
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : MAGE_EINVAL;
+}
+
+template <int BN>
+int launch_tc(const CUtensorMap& mapA, const CUtensorMap& mapW, const TcParams& p, cudaStream_t st) {
+  using C = Cfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  tc_gemm_kernel<BN><<<grid, NTHREADS, C::SMEM_BYTES, st>>>(mapA, mapW, p);
+  return mage_post_launch();
+}
+
+int pick_bn(int N, int64_t m_tiles) {
+  // widest tile that divides N; prefer a narrower one when the wide tile leaves most SMs idle
+  const int sms = num_sms();
+  for (int bn : {256, 128, 64}) {
+    if (N % bn) continue;
+    if (bn > 64 && m_tiles * (N / bn) < sms && N % (bn / 2) == 0) continue;
+    return bn;
+  }
+  return 0;
+}
+
+int dispatch(int bn, const CUtensorMap& mapA, const CUtensorMap& mapW, const TcParams& p, cudaStream_t st) {
+  switch (bn) {
+    case 256: return launch_tc<256>(mapA, mapW, p, st);
+    case 128: return launch_tc<128>(mapA, mapW, p, st);
+    case 64: return launch_tc<64>(mapA, mapW, p, st);
+  }
   return MAGE_ENOTSUP;
+}
+
+int make_w_map(CUtensorMap* map, const void* W, int64_t ldw, int64_t w_plane, int N, int K, int bn) {
+  const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)N, 2};
+  const cuuint64_t strides[2] = {(cuuint64_t)ldw * 2, (cuuint64_t)w_plane * 2};
+  const cuuint32_t box[3] = {BK, (cuuint32_t)bn, 2};
+  return make_map(map, W, 3, dims, strides, box);
+}
+
+}  // namespace
+
+extern "C" int mage_split_f32(const float* x, int64_t ldx, void* out, int64_t plane, int rows, int C, int relu, int* flag,
+                              void* stream) {
+  MAGE_CHECK_ARG(rows > 0 && C > 0 && C % 4 == 0 && ldx % 4 == 0 && aligned16(x) && (reinterpret_cast<uintptr_t>(out) & 7) == 0 &&
+                 plane % 4 == 0);
+  const int64_t total = (int64_t)rows * (C / 4);
+  split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(x, ldx, reinterpret_cast<__half*>(out), plane, rows,
+                                                                                C / 4, relu, flag);
+  return mage_post_launch();
+}
+
+extern "C" int mage_embedding_split(const int64_t* idx, const void* table, int64_t table_plane, void* out, int64_t out_plane,
+                                    int rows, int C, void* stream) {
+  MAGE_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0 && aligned16(table) && aligned16(out) && table_plane % 8 == 0 && out_plane % 8 == 0);
+  const int64_t total = (int64_t)rows * (C / 8) * 2;
+  embedding_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(
+      idx, reinterpret_cast<const __half*>(table), table_plane, reinterpret_cast<__half*>(out), out_plane, rows, C / 8);
+  return mage_post_launch();
+}
+
+extern "C" int mage_gemm_tc(const void* A, int64_t lda, int64_t a_plane, const void* W, int64_t ldw, int64_t w_plane,
+                            const float* bias, const float* residual, int64_t ldr, int res_mod, float* C, void* C_split,
+                            void* C_split_relu, int64_t ldc, int64_t c_plane, int M, int N, int K, int act, int* flag,
+                            void* stream) {
+  MAGE_CHECK_ARG(M > 0 && N > 0 && K > 0);
+  if (K % BK != 0 || N % 64 != 0) return MAGE_ENOTSUP;
+  MAGE_CHECK_ARG(aligned16(A) && aligned16(W) && lda % 8 == 0 && ldw % 8 == 0 && a_plane % 8 == 0 && w_plane % 8 == 0);
+  MAGE_CHECK_ARG(ldc % 4 == 0 && (!C || aligned16(C)) && (!bias || aligned16(bias)) && (!residual || (aligned16(residual) && ldr % 4 == 0)));
+  MAGE_CHECK_ARG(c_plane % 4 == 0 && (C || C_split || C_split_relu));
+  const int m_tiles = (M + BM - 1) / BM;
+  const int bn = pick_bn(N, m_tiles);
+  if (!bn) return MAGE_ENOTSUP;
+  CUtensorMap mapA, mapW;
+  {
+    const cuuint64_t dims[5] = {(cuuint64_t)K, (cuuint64_t)M, 1, 1, 2};
+    const cuuint64_t strides[4] = {(cuuint64_t)lda * 2, (cuuint64_t)lda * 2 * (cuuint64_t)M, (cuuint64_t)lda * 2 * (cuuint64_t)M,
+                                   (cuuint64_t)a_plane * 2};
+    const cuuint32_t box[5] = {BK, BM, 1, 1, 2};
+    int r = make_map(&mapA, A, 5, dims, strides, box);
+    if (r) return r;
+    r = make_w_map(&mapW, W, ldw, w_plane, N, K, bn);
+    if (r) return r;
+  }
+  TcParams p{};
+  p.bias = bias; p.res = residual; p.out = C;
+  p.split = reinterpret_cast<__half*>(C_split); p.split_relu = reinterpret_cast<__half*>(C_split_relu);
+  p.flag = flag; p.ldr = ldr; p.ldc = ldc; p.split_plane = c_plane; p.split_relu_plane = c_plane;
+  p.M = M; p.N = N; p.act = act; p.res_mod = res_mod;
+  p.m_tiles = m_tiles; p.n_tiles = N / bn; p.k_iters = K / BK;
+  return dispatch(bn, mapA, mapW, p, as_stream(stream));
+}
+
+// Stride-1 NHWC convolution on the tensor cores.  in: split [n_img,Hin,Win,Cin] (Cin % 64 == 0), w: split
+// [Cout][KH][KW][Cin]; output geometry / residual modes / scatter as mage_conv2d_nhwc_f32.
+extern "C" int mage_conv2d_tc(const void* in, int64_t in_plane, const void* w, int64_t w_plane, const float* bias,
+                              const float* residual, float* out, void* out_split, void* out_split_relu, int64_t out_plane,
+                              int n_img, int Hin, int Win, int Cin, int Hout, int Wout, int Cout, int KH, int KW, int pad_y,
+                              int pad_x, int res_mode, int act, int out_sy, int out_sx, int out_oy, int out_ox, int Hfull,
+                              int Wfull, int64_t out_img_stride, int* flag, void* stream) {
+  MAGE_CHECK_ARG(n_img > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && Hout > 0 && Wout > 0);
+  if (Cin % BK != 0 || Cout % 64 != 0) return MAGE_ENOTSUP;
+  const int Wb = Wout < BM ? Wout : BM;
+  if (BM % Wb != 0) return MAGE_ENOTSUP;
+  const int Hb = BM / Wb;
+  if (Wout % Wb != 0 || Hout % Hb != 0) return MAGE_ENOTSUP;
+  MAGE_CHECK_ARG(aligned16(in) && aligned16(w) && in_plane % 8 == 0 && w_plane % 8 == 0 && out_plane % 4 == 0);
+  MAGE_CHECK_ARG(res_mode >= 0 && res_mode <= 3 && (res_mode == 0 || residual != nullptr) && (out || out_split || out_split_relu));
+  MAGE_CHECK_ARG(Cout % 4 == 0 && out_img_stride % 4 == 0 && (!out || aligned16(out)) && (!bias || aligned16(bias)) &&
+                 (!residual || aligned16(residual)));
+  const int64_t m_tiles = (int64_t)n_img * (Hout / Hb) * (Wout / Wb);
+  MAGE_CHECK_ARG(m_tiles < ((int64_t)1 << 24));
+  const int K = KH * KW * Cin;
+  const int bn = pick_bn(Cout, m_tiles);
+  if (!bn) return MAGE_ENOTSUP;
+  CUtensorMap mapA, mapW;
+  {
+    const cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)n_img, 2};
+    const cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)Win * Cin * 2, (cuuint64_t)Hin * Win * Cin * 2,
+                                   (cuuint64_t)in_plane * 2};
+    const cuuint32_t box[5] = {BK, (cuuint32_t)Wb, (cuuint32_t)Hb, 1, 2};
+    int r = make_map(&mapA, in, 5, dims, strides, box);
+    if (r) return r;
+    r = make_w_map(&mapW, w, K, w_plane, Cout, K, bn);
+    if (r) return r;
+  }
+  TcParams p{};
+  p.bias = bias; p.res = residual; p.out = out;
+  p.split = reinterpret_cast<__half*>(out_split); p.split_relu = reinterpret_cast<__half*>(out_split_relu);
+  p.flag = flag; p.ldr = Cout; p.ldc = Cout; p.split_plane = out_plane; p.split_relu_plane = out_plane;
+  p.out_img_stride = out_img_stride;
+  p.M = (int)(m_tiles * BM); p.N = Cout; p.act = act; p.res_mod = 0;
+  p.m_tiles = (int)m_tiles; p.n_tiles = Cout / bn; p.k_iters = KH * KW * (Cin / BK);
+  p.conv = 1; p.Hout = Hout; p.Wout = Wout; p.Wb = Wb; p.Hb = Hb; p.KW = KW; p.cin_blocks = Cin / BK; p.cin = Cin;
+  p.pad_y = pad_y; p.pad_x = pad_x; p.res_mode = res_mode;
+  p.out_sy = out_sy; p.out_sx = out_sx; p.out_oy = out_oy; p.out_ox = out_ox; p.Hfull = Hfull; p.Wfull = Wfull;
+  return dispatch(bn, mapA, mapW, p, as_stream(stream));
 }

@@ -11,7 +11,6 @@ from . import _lib
 from ._lib import check
 
 ACT_NONE, ACT_RELU, ACT_QUICKGELU, ACT_GELU, ACT_TANH = 0, 1, 2, 3, 4
-GEMM_SIMT, GEMM_TCGEN05 = 0, 1
 
 
 def _p(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -56,14 +55,6 @@ def launch_count() -> int:
     return int(_lib.lib().mage_launch_count())
 
 
-def set_gemm_backend(backend: int) -> None:
-    check(_lib.lib().mage_set_gemm_backend(backend), "mage_set_gemm_backend")
-
-
-def get_gemm_backend() -> int:
-    return int(_lib.lib().mage_get_gemm_backend())
-
-
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, out: Optional[torch.Tensor] = None,
          residual: Optional[torch.Tensor] = None, res_mod: int = 0, act: int = ACT_NONE, relu_a: bool = False) -> torch.Tensor:
     """out[M,N] = act(a[M,K] @ w[N,K].T + bias) + residual.  `a` may be a row-strided 2-D view."""
@@ -81,6 +72,123 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
                                        residual.stride(0) if residual is not None else 0, res_mod, _p(out), out.stride(0),
                                        M, N, K, act, int(relu_a), _stream()), "mage_gemm_f32")
     return out
+
+
+# ------------------------------------------------------------------ tensor-core back end (split operands)
+_FLAGS = {}
+
+
+def flag(device) -> torch.Tensor:
+    """Per-device int32 that the tensor-core kernels OR with 1 when a value leaves the fp16 split range."""
+    key = torch.device(device).index or 0
+    f = _FLAGS.get(key)
+    if f is None:
+        f = _FLAGS[key] = torch.zeros(1, device=device, dtype=torch.int32)
+    return f
+
+
+def check_flag(device) -> None:
+    """Raise (loudly, after a sync) if any split conversion since the last check saw |x| > 65504 or NaN."""
+    f = flag(device)
+    if int(f.item()) != 0:
+        f.zero_()
+        raise _lib.MageCudaError("a tensor-core operand left the fp16 hi/lo split range (|x| > 65504 or NaN); "
+                                 "results are invalid -- run with MAGE_BACKEND=simt")
+
+
+def _f16(t: torch.Tensor) -> torch.Tensor:
+    assert t.dtype == torch.float16 and t.is_contiguous() and t.shape[0] == 2, (t.dtype, t.shape, t.stride())
+    return t
+
+
+def split(x: torch.Tensor, relu: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 [..., C] (rows may be strided for a 2-D view) -> split fp16 [2, ..., C] (hi plane, lo plane)."""
+    C = x.shape[-1]
+    if x.dim() == 2:
+        rows, ldx = x.shape[0], x.stride(0)
+        assert x.stride(1) == 1
+    else:
+        assert x.is_contiguous()
+        rows, ldx = x.numel() // C, C
+    if out is None:
+        out = torch.empty(2, *x.shape, device=x.device, dtype=torch.float16)
+    check(_lib.lib().mage_split_f32(_p(x), ldx, _p(_f16(out)), rows * C, rows, C, int(relu), _p(flag(x.device)), _stream()),
+          "mage_split_f32")
+    return out
+
+
+def embedding_split(idx: torch.Tensor, table: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """idx int64 [...], table split [2, K, C] -> split [2, ..., C]."""
+    assert idx.dtype == torch.int64 and idx.is_contiguous()
+    K, C = table.shape[1], table.shape[2]
+    rows = idx.numel()
+    if out is None:
+        out = torch.empty(2, *idx.shape, C, device=table.device, dtype=torch.float16)
+    check(_lib.lib().mage_embedding_split(_p(idx), _p(_f16(table)), K * C, _p(_f16(out)), rows * C, rows, C, _stream()),
+          "mage_embedding_split")
+    return out
+
+
+def gemm_tc(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, out: Optional[torch.Tensor] = None,
+            out_split: Optional[torch.Tensor] = None, out_split_relu: Optional[torch.Tensor] = None, want=("f32",),
+            residual: Optional[torch.Tensor] = None, res_mod: int = 0, act: int = ACT_NONE):
+    """Tensor-core GEMM on split operands: a [2,M,K], w [2,N,K] -> act(a @ w.T + bias) + residual.
+    `want` lists the outputs to allocate when not passed: "f32", "split", "split_relu".
+    Returns (out_f32, out_split, out_split_relu) with None for the ones not produced."""
+    _f16(a), _f16(w)
+    M, K = a.shape[1], a.shape[2]
+    N = w.shape[1]
+    assert w.shape[2] == K
+    dev = a.device
+    if out is None and "f32" in want:
+        out = torch.empty(M, N, device=dev, dtype=torch.float32)
+    if out_split is None and "split" in want:
+        out_split = torch.empty(2, M, N, device=dev, dtype=torch.float16)
+    if out_split_relu is None and "split_relu" in want:
+        out_split_relu = torch.empty(2, M, N, device=dev, dtype=torch.float16)
+    if out is not None:
+        assert out.shape == (M, N) and out.is_contiguous()
+    if residual is not None:
+        assert residual.dim() == 2 and residual.shape[1] == N and residual.stride(1) == 1
+    with _Prof("gemm", 2.0 * M * N * K):
+        check(_lib.lib().mage_gemm_tc(_p(a), K, M * K, _p(w), K, N * K, _p(bias), _p(residual),
+                                      residual.stride(0) if residual is not None else 0, res_mod, _p(out), _p(out_split),
+                                      _p(out_split_relu), N, M * N, M, N, K, act, _p(flag(dev)), _stream()), "mage_gemm_tc")
+    return out, out_split, out_split_relu
+
+
+def conv2d_tc(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, pad=(0, 0),
+              residual: Optional[torch.Tensor] = None, res_mode: int = 0, act: int = ACT_NONE, want=("f32",),
+              out: Optional[torch.Tensor] = None, out_split: Optional[torch.Tensor] = None,
+              out_split_relu: Optional[torch.Tensor] = None, out_hw=None, scatter=(1, 1, 0, 0), full_hw=None):
+    """Tensor-core stride-1 NHWC convolution on split operands: x [2,n,Hin,Win,Cin], w [2,Cout,KH,KW,Cin]."""
+    _f16(x), _f16(w)
+    _, n, Hin, Win, Cin = x.shape
+    _, Cout, KH, KW, Cin2 = w.shape
+    assert Cin == Cin2
+    if out_hw is None:
+        out_hw = (Hin + 2 * pad[0] - KH + 1, Win + 2 * pad[1] - KW + 1)
+    Hout, Wout = out_hw
+    sy, sx, oy, ox = scatter
+    if full_hw is None:
+        full_hw = (Hout * sy, Wout * sx)
+    Hfull, Wfull = full_hw
+    dev = x.device
+    if out is None and "f32" in want:
+        out = torch.empty(n, Hfull, Wfull, Cout, device=dev, dtype=torch.float32)
+    if out_split is None and "split" in want:
+        out_split = torch.empty(2, n, Hfull, Wfull, Cout, device=dev, dtype=torch.float16)
+    if out_split_relu is None and "split_relu" in want:
+        out_split_relu = torch.empty(2, n, Hfull, Wfull, Cout, device=dev, dtype=torch.float16)
+    if residual is not None and res_mode == 0:
+        res_mode = 1
+    img = Hfull * Wfull * Cout
+    with _Prof("conv", 2.0 * n * Hout * Wout * Cout * KH * KW * Cin):
+        check(_lib.lib().mage_conv2d_tc(_p(x), n * Hin * Win * Cin, _p(w), Cout * KH * KW * Cin, _p(bias), _p(residual), _p(out),
+                                        _p(out_split), _p(out_split_relu), n * img, n, Hin, Win, Cin, Hout, Wout, Cout, KH, KW,
+                                        pad[0], pad[1], res_mode, act, sy, sx, oy, ox, Hfull, Wfull, img, _p(flag(dev)),
+                                        _stream()), "mage_conv2d_tc")
+    return out, out_split, out_split_relu
 
 
 def conv2d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, stride: int = 1, pad=(0, 0),

@@ -33,12 +33,10 @@ def _act(x, act):
     return [lambda t: t, F.relu, lambda t: t * torch.sigmoid(1.702 * t), F.gelu, torch.tanh][act](x)
 
 
-@pytest.mark.parametrize("backend", [0])
 @pytest.mark.parametrize("M,N,K", [(300, 512, 512), (4096, 1536, 512), (1000, 2048, 512), (513, 512, 2048),
                                    (77, 3, 256), (1000, 64, 576), (256, 1, 1024), (20000, 128, 64), (40, 1024, 256)])
-def test_gemm_shapes(M, N, K, backend):
+def test_gemm_shapes(M, N, K):
     ops = _ops()
-    ops.set_gemm_backend(backend)
     a, w, b = _rand(M, K, seed=1), _rand(N, K, seed=2, scale=K ** -0.5), _rand(N, seed=3)
     out = ops.gemm(a.to(DEV), w.to(DEV), b.to(DEV))
     _close(out, a.double() @ w.double().t() + b.double())
@@ -47,7 +45,6 @@ def test_gemm_shapes(M, N, K, backend):
 @pytest.mark.parametrize("act", [0, 1, 2, 3, 4])
 def test_gemm_epilogues(act):
     ops = _ops()
-    ops.set_gemm_backend(0)
     M, N, K = 700, 512, 256
     a, w, b, r = _rand(M, K, seed=1), _rand(N, K, seed=2, scale=K ** -0.5), _rand(N, seed=3), _rand(M, N, seed=4)
     want = _act(F.relu(a).double() @ w.double().t() + b.double(), act) + r.double()
@@ -61,7 +58,6 @@ def test_gemm_epilogues(act):
 
 def test_gemm_inplace_residual_resmod_and_strided_a():
     ops = _ops()
-    ops.set_gemm_backend(0)
     M, N, K = 512, 512, 512
     big = _rand(M, 3 * K, seed=5).to(DEV)
     w, x = _rand(N, K, seed=6, scale=K ** -0.5), _rand(M, N, seed=7)

@@ -1,0 +1,185 @@
+"""GPU: the tcgen05 tensor-core back end (fp16 hi/lo split operands, three MMAs per product, fp32
+accumulators in TMEM) against fp64 torch restatements.  The bar is fp32-grade accuracy: the error
+must be of the order of fp32 summation noise, not of fp16/TF32 rounding (which would be ~1e-3)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+RTOL = 4e-6  # (scaled up for K > 2048) relative to max |reference|; single-pass fp16/TF32 would sit near 5e-4
+
+
+def _ops():
+    from mage_b200 import ops
+    return ops
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+def _unsplit(s):
+    s = s.detach().cpu().double()
+    return s[0] + s[1] / 2048.0
+
+
+def _close(got, want, rtol=RTOL):
+    got = got.detach().cpu().double()
+    want = want.double()
+    err = (got - want).abs().max().item()
+    ref = want.abs().max().item()
+    assert err <= rtol * ref, f"max abs err {err:.3e} vs ref magnitude {ref:.3e} (ratio {err / ref:.2e})"
+
+
+def _act(x, act):
+    return [lambda t: t, F.relu, lambda t: t * torch.sigmoid(1.702 * t), F.gelu, torch.tanh][act](x)
+
+
+def test_split_roundtrip_and_flag():
+    ops = _ops()
+    x = torch.cat([_rand(64, 512, seed=1), _rand(64, 512, seed=2, scale=1e-3), _rand(64, 512, seed=3, scale=300.0)])
+    s = ops.split(x.to(DEV))
+    assert s.shape == (2, 192, 512) and s.dtype == torch.float16
+    err = (_unsplit(s) - x.double()).abs()
+    assert (err <= 2.0 ** -23 * x.double().abs() + 1e-10).all(), f"split error {err.max():.3e}"
+    r = ops.split(x.to(DEV), relu=True)
+    assert (_unsplit(r) - F.relu(x).double()).abs().max() <= 2.0 ** -23 * x.abs().max()
+    ops.check_flag(DEV)  # in range: no complaint
+    ops.split(torch.full((4, 8), 1e5, device=DEV))
+    with pytest.raises(RuntimeError):
+        ops.check_flag(DEV)
+    ops.check_flag(DEV)  # flag was cleared
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (300, 512, 512), (4096, 1536, 512), (1000, 2048, 512), (513, 512, 2048),
+                                   (1000, 64, 576), (20000, 128, 64), (40, 1024, 256), (16384, 512, 512), (2560, 256, 1024)])
+def test_gemm_tc_shapes(M, N, K):
+    ops = _ops()
+    a, w, b = _rand(M, K, seed=1), _rand(N, K, seed=2, scale=K ** -0.5), _rand(N, seed=3)
+    out, _, _ = ops.gemm_tc(ops.split(a.to(DEV)), ops.split(w.to(DEV)), b.to(DEV))
+    torch.cuda.synchronize()
+    _close(out, a.double() @ w.double().t() + b.double())
+    ops.check_flag(DEV)
+
+
+@pytest.mark.parametrize("act", [0, 1, 2, 3, 4])
+def test_gemm_tc_epilogues(act):
+    ops = _ops()
+    M, N, K = 700, 512, 256
+    a, w, b, r = _rand(M, K, seed=1), _rand(N, K, seed=2, scale=K ** -0.5), _rand(N, seed=3), _rand(M, N, seed=4)
+    asp, wsp = ops.split(a.to(DEV)), ops.split(w.to(DEV))
+    want = _act(a.double() @ w.double().t() + b.double(), act) + r.double()
+    out, sp, spr = ops.gemm_tc(asp, wsp, b.to(DEV), residual=r.to(DEV), act=act, want=("f32", "split", "split_relu"))
+    _close(out, want)
+    _close(_unsplit(sp), want)
+    _close(_unsplit(spr), F.relu(want))
+    # activation after the residual, residual read through a ReLU; split-only output
+    want2 = _act(a.double() @ w.double().t() + b.double() + F.relu(r).double(), act)
+    out2, sp2, _ = ops.gemm_tc(asp, wsp, b.to(DEV), residual=r.to(DEV), act=act | 0x100 | 0x200, want=("split",))
+    assert out2 is None
+    _close(_unsplit(sp2), want2)
+
+
+def test_gemm_tc_inplace_residual_and_resmod():
+    ops = _ops()
+    M, N, K = 512, 512, 512
+    a, w, x = _rand(M, K, seed=5), _rand(N, K, seed=6, scale=K ** -0.5), _rand(M, N, seed=7)
+    asp, wsp = ops.split(a.to(DEV)), ops.split(w.to(DEV))
+    xd = x.to(DEV).clone()
+    ops.gemm_tc(asp, wsp, None, residual=xd, out=xd)  # x += a @ w.T in place
+    _close(xd, a.double() @ w.double().t() + x.double())
+    tab = _rand(256, N, seed=8)
+    out, _, _ = ops.gemm_tc(asp, wsp, None, residual=tab.to(DEV), res_mod=256)
+    _close(out, a.double() @ w.double().t() + tab.double().repeat(2, 1))
+
+
+def test_gemm_tc_matches_simt_kernel_to_fp32_noise():
+    ops = _ops()
+    M, N, K = 2048, 512, 2048
+    a, w = _rand(M, K, seed=11), _rand(N, K, seed=12, scale=K ** -0.5)
+    want = a.double() @ w.double().t()
+    simt = ops.gemm(a.to(DEV), w.to(DEV))
+    tc, _, _ = ops.gemm_tc(ops.split(a.to(DEV)), ops.split(w.to(DEV)))
+    e_simt = (simt.cpu().double() - want).abs().max().item()
+    e_tc = (tc.cpu().double() - want).abs().max().item()
+    assert e_tc <= 4 * e_simt + 1e-7, f"tensor-core error {e_tc:.3e} vs fp32 FFMA error {e_simt:.3e}"
+
+
+def test_embedding_split():
+    ops = _ops()
+    table = _rand(512, 1024, seed=3)
+    idx = torch.randint(0, 512, (3, 16, 16), generator=torch.Generator().manual_seed(4))
+    tsp = ops.split(table.to(DEV))
+    got = ops.embedding_split(idx.to(DEV), tsp)
+    assert got.shape == (2, 3, 16, 16, 1024)
+    assert torch.equal(got.cpu(), tsp.cpu()[:, idx.reshape(-1)].reshape(2, 3, 16, 16, 1024))
+
+
+def _conv_ref(x, w, b, pad):
+    """x [n,H,W,C] NHWC, w [Cout,KH,KW,Cin] -> NHWC fp64."""
+    y = F.conv2d(x.permute(0, 3, 1, 2).double(), w.permute(0, 3, 1, 2).double(), b.double() if b is not None else None, padding=pad)
+    return y.permute(0, 2, 3, 1)
+
+
+@pytest.mark.parametrize("n,H,Cin,Cout,k", [(3, 16, 64, 64, 3), (2, 16, 128, 512, 3), (2, 32, 64, 256, 3), (1, 64, 64, 64, 3),
+                                            (1, 128, 64, 64, 3), (2, 16, 512, 512, 3), (2, 32, 256, 128, 1)])
+def test_conv2d_tc_plain(n, H, Cin, Cout, k):
+    ops = _ops()
+    x = _rand(n, H, H, Cin, seed=1)
+    w = _rand(Cout, k, k, Cin, seed=2, scale=(k * k * Cin) ** -0.5)
+    b = _rand(Cout, seed=3)
+    out, sp, _ = ops.conv2d_tc(ops.split(x.to(DEV)), ops.split(w.to(DEV)), b.to(DEV), pad=(k // 2, k // 2), act=1,
+                               want=("f32", "split"))
+    want = F.relu(_conv_ref(x, w, b, k // 2))
+    rtol = RTOL * max(1.0, k * k * Cin / 2048)  # the tensor core's fp32 accumulator rounds once per 16-deep MMA: error grows ~K
+    _close(out, want, rtol)
+    _close(_unsplit(sp), want, rtol)
+    ops.check_flag(DEV)
+
+
+def test_conv2d_tc_residual_modes():
+    ops = _ops()
+    n, H, Cin, Cout = 2, 32, 64, 128
+    x, w, b = _rand(n, H, H, Cin, seed=1), _rand(Cout, 3, 3, Cin, seed=2, scale=(9 * Cin) ** -0.5), _rand(Cout, seed=3)
+    xs, ws = ops.split(x.to(DEV)), ops.split(w.to(DEV))
+    base = _conv_ref(x, w, b, 1)
+    r1 = _rand(n, H, H, Cout, seed=4)
+    out, _, _ = ops.conv2d_tc(xs, ws, b.to(DEV), pad=(1, 1), residual=r1.to(DEV), res_mode=1)
+    _close(out, base + r1.double())
+    r2 = _rand(n, H // 2, H // 2, Cout, seed=5)  # stored at half resolution, read through nearest x2
+    out, _, _ = ops.conv2d_tc(xs, ws, b.to(DEV), pad=(1, 1), residual=r2.to(DEV), res_mode=2)
+    up = r2.double().repeat_interleave(2, 1).repeat_interleave(2, 2)
+    _close(out, base + up)
+    r3 = _rand(H * H, Cout, seed=6)  # one map shared by all images (H/W positional embeddings)
+    out, _, _ = ops.conv2d_tc(xs, ws, None, pad=(1, 1), residual=r3.to(DEV), res_mode=3)
+    _close(out, _conv_ref(x, w, None, 1) + r3.double().view(1, H, H, Cout))
+
+
+def test_conv2d_tc_transpose_phases():
+    """ConvTranspose2d(4,2,1) as four 2x2 sub-pixel phase convolutions scattered into the full output."""
+    ops = _ops()
+    n, H, Cin, Cout = 2, 16, 256, 256
+    x = _rand(n, H, H, Cin, seed=1)
+    wt = _rand(Cin, Cout, 4, 4, seed=2, scale=(4 * Cin) ** -0.5)  # ConvTranspose2d layout
+    b = _rand(Cout, seed=3)
+    want = F.conv_transpose2d(x.permute(0, 3, 1, 2).double(), wt.double(), b.double(), stride=2, padding=1).permute(0, 2, 3, 1)
+    xs = ops.split(x.to(DEV))
+    out = torch.empty(n, 2 * H, 2 * H, Cout, device=DEV)
+    taps = {0: (3, 1), 1: (2, 0)}
+    for py in (0, 1):
+        for px in (0, 1):
+            sub = wt[:, :, list(taps[py]), :][:, :, :, list(taps[px])].permute(1, 2, 3, 0).contiguous()  # [Cout,2,2,Cin]
+            ops.conv2d_tc(xs, ops.split(sub.to(DEV)), b.to(DEV), pad=(1 - py, 1 - px), out=out, out_hw=(H, H),
+                          scatter=(2, 2, py, px), full_hw=(2 * H, 2 * H))
+    _close(out, want)
+
+
+def test_tc_rejects_unsupported_shapes():
+    from mage_b200 import _lib
+    ops = _ops()
+    a, w = ops.split(_rand(64, 96, seed=1).to(DEV)), ops.split(_rand(64, 96, seed=2).to(DEV))
+    with pytest.raises(_lib.MageCudaError):
+        ops.gemm_tc(a, w)  # K % 64 != 0 -> MAGE_ENOTSUP, never a silent fallback
