@@ -127,30 +127,31 @@ int mage_conv1x1_tanh_nchw_f32(const float* in, const float* w, const float* bia
 /* 2x2 max pooling, NHWC (vqvae_model.py:195,197,199). */
 int mage_maxpool2x2_nhwc_f32(const float* in, float* out, int n_img, int Hin, int Win, int C, void* stream);
 
-/* Row LayerNorm over the last dim C (C % 128 == 0, C <= 1024); in may alias out.
+/* Row LayerNorm over the last dim C (C % 128 == 0, C <= 1024); in may alias out.  out (fp32) and/or
+ * out_split (split copy for a following tensor-core GEMM, plane stride split_plane) may be NULL.
  * Replaces nn.LayerNorm (mage_model.py:21,27,84,204,206). */
-int mage_layernorm_f32(const float* in, const float* gamma, const float* beta, float* out,
-                       int rows, int C, float eps, void* stream);
+int mage_layernorm_f32(const float* in, const float* gamma, const float* beta, float* out, void* out_split,
+                       int64_t split_plane, int* flag, int rows, int C, float eps, void* stream);
 
 /* Multi-head attention core, head_dim 32: for every (outer, inner, head, query)
  *   out = softmax(scale * q . K^T [keys >= key_len[outer] masked]) . V        (Sk <= 64)
  * Element strides address q/k/v/out as base + outer*X_outer + inner*X_inner + s*X_seq + head*32.
  * Covers the SDPA inside every nn.MultiheadAttention on the path (mage_model.py:33,89,193-199):
  * temporal attention over the K/V cache, H-/W-axial attention, text self-attention (key padding),
- * motion-anchor cross-attention. */
+ * motion-anchor cross-attention.  out (fp32) and/or out_split (split copy, same element offsets) may be NULL. */
 int mage_mha_f32(const float* q, const float* k, const float* v, float* out,
                  int n_outer, int n_inner, int n_head, int Sq, int Sk,
                  int64_t q_outer, int64_t q_inner, int64_t q_seq,
                  int64_t k_outer, int64_t k_inner, int64_t k_seq,
                  int64_t v_outer, int64_t v_inner, int64_t v_seq,
                  int64_t o_outer, int64_t o_inner, int64_t o_seq,
-                 const int32_t* key_len, float scale, void* stream);
+                 const int32_t* key_len, float scale, void* out_split, int64_t split_plane, int* flag, void* stream);
 
 /* Temporal attention for one decode step with a TMA-staged K/V cache (bulk async copies into
  * shared memory).  qkv [M, 3C] holds this position's q|k|v; k,v are appended to the caches
  * [M, Lmax, C] at `pos` and q attends positions 0..pos.  out [M, C].  C = 512, 16 heads x 32. */
-int mage_temporal_attn_step_f32(const float* qkv, float* kcache, float* vcache, float* out,
-                                int M, int pos, int Lmax, float scale, void* stream);
+int mage_temporal_attn_step_f32(const float* qkv, float* kcache, float* vcache, float* out, void* out_split,
+                                int64_t split_plane, int* flag, int M, int pos, int Lmax, float scale, void* stream);
 
 /* Append this step's K and V (columns C..3C of qkv [M,3C]) at position `pos` of caches [M,Lmax,C]. */
 int mage_kv_append_f32(const float* qkv, float* kcache, float* vcache, int M, int C, int pos, int Lmax, void* stream);

@@ -8,6 +8,7 @@
 //    (cp.async.bulk, the TMA engine) that complete on an mbarrier, so the copy engine streams HBM
 //    while other resident CTAs compute.
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace {
 
@@ -18,7 +19,21 @@ struct MhaArgs {
   const int32_t* key_len;
   float scale;
   int64_t total;
+  __half* split;  // optional split (fp16 hi/lo) copy of `out`, same element offsets
+  int64_t split_plane;
+  int* flag;
 };
+
+__device__ __forceinline__ void store_attn(float* out, __half* split, int64_t plane, int* flag, int64_t e, float v) {
+  if (out) out[e] = v;
+  if (split) {
+    __half hi, lo;
+    tc::split_one(v, hi, lo);
+    split[e] = hi;
+    split[plane + e] = lo;
+    if (!(fabsf(v) <= 65504.f) && flag) atomicOr(flag, 1);
+  }
+}
 
 __global__ void __launch_bounds__(256) mha_kernel(const MhaArgs p) {
   const int64_t w = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -66,7 +81,7 @@ __global__ void __launch_bounds__(256) mha_kernel(const MhaArgs p) {
     const float pj = __shfl_sync(0xffffffffu, j < 32 ? p0 : p1, j & 31);
     o = fmaf(pj, __ldg(vb + j * p.v_seq + lane), o);
   }
-  p.out[outer * p.o_outer + inner * p.o_inner + qi * p.o_seq + h * 32 + lane] = o * inv;
+  store_attn(p.out, p.split, p.split_plane, p.flag, outer * p.o_outer + inner * p.o_inner + qi * p.o_seq + h * 32 + lane, o * inv);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -106,6 +121,7 @@ constexpr int TA_C = 512, TA_HALF = 256;
 
 __global__ void __launch_bounds__(256) temporal_attn_kernel(const float* __restrict__ qkv, float* __restrict__ kcache,
                                                             float* __restrict__ vcache, float* __restrict__ out,
+                                                            __half* __restrict__ split, int64_t split_plane, int* flag,
                                                             int pos, int Lmax, float scale) {
   extern __shared__ __align__(128) float smem[];
   float* Ks = smem;                       // [Lmax][256]
@@ -174,7 +190,7 @@ __global__ void __launch_bounds__(256) temporal_attn_kernel(const float* __restr
     const float pj = __shfl_sync(0xffffffffu, j < 32 ? p0 : p1, j & 31);
     o = fmaf(pj, Vs[(size_t)j * TA_HALF + warp * 32 + lane], o);
   }
-  out[(int64_t)m * TA_C + half * TA_HALF + tid] = o * inv;
+  store_attn(out, split, split_plane, flag, (int64_t)m * TA_C + half * TA_HALF + tid, o * inv);
 }
 
 }  // namespace
@@ -182,12 +198,14 @@ __global__ void __launch_bounds__(256) temporal_attn_kernel(const float* __restr
 extern "C" int mage_mha_f32(const float* q, const float* k, const float* v, float* out, int n_outer, int n_inner, int n_head,
                             int Sq, int Sk, int64_t q_outer, int64_t q_inner, int64_t q_seq, int64_t k_outer, int64_t k_inner,
                             int64_t k_seq, int64_t v_outer, int64_t v_inner, int64_t v_seq, int64_t o_outer, int64_t o_inner,
-                            int64_t o_seq, const int32_t* key_len, float scale, void* stream) {
+                            int64_t o_seq, const int32_t* key_len, float scale, void* out_split, int64_t split_plane,
+                            int* flag, void* stream) {
   MAGE_CHECK_ARG(n_outer > 0 && n_inner > 0 && n_head > 0 && Sq > 0 && Sk > 0 && Sk <= 64);
-  MAGE_CHECK_ARG(aligned16(q) && aligned16(k) && aligned16(v));
+  MAGE_CHECK_ARG(aligned16(q) && aligned16(k) && aligned16(v) && (out || out_split));
   MAGE_CHECK_ARG(((q_outer | q_inner | q_seq | k_outer | k_inner | k_seq) & 3) == 0);
   MhaArgs a{q, k, v, out, n_outer, n_inner, n_head, Sq, Sk, q_outer, q_inner, q_seq, k_outer, k_inner, k_seq,
-            v_outer, v_inner, v_seq, o_outer, o_inner, o_seq, key_len, scale, 0};
+            v_outer, v_inner, v_seq, o_outer, o_inner, o_seq, key_len, scale, 0, reinterpret_cast<__half*>(out_split),
+            split_plane, flag};
   a.total = (int64_t)n_outer * n_inner * n_head * Sq;
   const int64_t blocks = (a.total + 7) / 8;
   MAGE_CHECK_ARG(blocks < ((int64_t)1 << 31));
@@ -195,10 +213,11 @@ extern "C" int mage_mha_f32(const float* q, const float* k, const float* v, floa
   return mage_post_launch();
 }
 
-extern "C" int mage_temporal_attn_step_f32(const float* qkv, float* kcache, float* vcache, float* out, int M, int pos,
-                                           int Lmax, float scale, void* stream) {
+extern "C" int mage_temporal_attn_step_f32(const float* qkv, float* kcache, float* vcache, float* out, void* out_split,
+                                           int64_t split_plane, int* flag, int M, int pos, int Lmax, float scale,
+                                           void* stream) {
   MAGE_CHECK_ARG(M > 0 && pos >= 0 && pos < Lmax && Lmax <= 64);
-  MAGE_CHECK_ARG(aligned16(qkv) && aligned16(kcache) && aligned16(vcache) && aligned16(out));
+  MAGE_CHECK_ARG(aligned16(qkv) && aligned16(kcache) && aligned16(vcache) && aligned16(out) && (out || out_split));
   const size_t smem = (size_t)2 * Lmax * TA_HALF * sizeof(float);
   static size_t configured = 0;
   if (smem > 48 * 1024 && smem > configured) {
@@ -206,6 +225,7 @@ extern "C" int mage_temporal_attn_step_f32(const float* qkv, float* kcache, floa
     if (e != cudaSuccess) return (int)e;
     configured = smem;
   }
-  temporal_attn_kernel<<<(unsigned)M * 2, 256, smem, as_stream(stream)>>>(qkv, kcache, vcache, out, pos, Lmax, scale);
+  temporal_attn_kernel<<<(unsigned)M * 2, 256, smem, as_stream(stream)>>>(qkv, kcache, vcache, out, reinterpret_cast<__half*>(out_split),
+                                                                          split_plane, flag, pos, Lmax, scale);
   return mage_post_launch();
 }

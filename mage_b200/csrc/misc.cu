@@ -1,6 +1,7 @@
 // Bandwidth-bound helper kernels of the MAGE sampling path: LayerNorm, greedy argmax, embedding
 // gathers, pooling, AdaIN, first/last VQ-VAE layers.  All fp32, channels-last, float4 accesses.
 #include "common.cuh"
+#include "tc_common.cuh"
 
 int64_t g_mage_launches = 0;
 
@@ -14,6 +15,7 @@ namespace {
 template <int NV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ in, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float* __restrict__ out,
+                                                        __half* __restrict__ split, int64_t plane, int* flag,
                                                         int rows, float eps) {
   constexpr int C = NV * 128;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -36,6 +38,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   }
   const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + eps);
   float4* dst = reinterpret_cast<float4*>(out + (int64_t)row * C);
+  bool bad = false;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
@@ -45,8 +48,16 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     o.y = (v[i].y - mean) * rstd * g.y + b.y;
     o.z = (v[i].z - mean) * rstd * g.z + b.z;
     o.w = (v[i].w - mean) * rstd * g.w + b.w;
-    dst[i * 32 + lane] = o;
+    if (out) dst[i * 32 + lane] = o;
+    if (split) {  // the next tensor-core GEMM's operand format
+      uint2 hi, lo;
+      bad |= tc::split4(o, hi, lo);
+      const int64_t e = (int64_t)row * C + (i * 32 + lane) * 4;
+      *reinterpret_cast<uint2*>(split + e) = hi;
+      *reinterpret_cast<uint2*>(split + plane + e) = lo;
+    }
   }
+  if (bad && flag) atomicOr(flag, 1);
 }
 
 // ------------------------------------------------------------------ argmax over rows
@@ -301,16 +312,18 @@ __global__ void __launch_bounds__(256) kv_append_kernel(const float* __restrict_
 
 }  // namespace
 
-extern "C" int mage_layernorm_f32(const float* in, const float* gamma, const float* beta, float* out, int rows, int C,
-                                  float eps, void* stream) {
+extern "C" int mage_layernorm_f32(const float* in, const float* gamma, const float* beta, float* out, void* out_split,
+                                  int64_t split_plane, int* flag, int rows, int C, float eps, void* stream) {
   MAGE_CHECK_ARG(rows > 0 && C % 128 == 0 && C <= 1024 && aligned16(in) && aligned16(out) && aligned16(gamma) && aligned16(beta));
+  MAGE_CHECK_ARG((out || out_split) && aligned16(out_split) && split_plane % 4 == 0);
   const dim3 g((rows + 7) / 8);
   cudaStream_t st = as_stream(stream);
+  __half* sp = reinterpret_cast<__half*>(out_split);
   switch (C / 128) {
-    case 1: layernorm_kernel<1><<<g, 256, 0, st>>>(in, gamma, beta, out, rows, eps); break;
-    case 2: layernorm_kernel<2><<<g, 256, 0, st>>>(in, gamma, beta, out, rows, eps); break;
-    case 4: layernorm_kernel<4><<<g, 256, 0, st>>>(in, gamma, beta, out, rows, eps); break;
-    case 8: layernorm_kernel<8><<<g, 256, 0, st>>>(in, gamma, beta, out, rows, eps); break;
+    case 1: layernorm_kernel<1><<<g, 256, 0, st>>>(in, gamma, beta, out, sp, split_plane, flag, rows, eps); break;
+    case 2: layernorm_kernel<2><<<g, 256, 0, st>>>(in, gamma, beta, out, sp, split_plane, flag, rows, eps); break;
+    case 4: layernorm_kernel<4><<<g, 256, 0, st>>>(in, gamma, beta, out, sp, split_plane, flag, rows, eps); break;
+    case 8: layernorm_kernel<8><<<g, 256, 0, st>>>(in, gamma, beta, out, sp, split_plane, flag, rows, eps); break;
     default: return MAGE_EINVAL;
   }
   return mage_post_launch();

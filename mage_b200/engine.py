@@ -28,6 +28,31 @@ ACT_POST = 0x100
 RES_RELU = 0x200
 
 
+def default_backend() -> str:
+    """"tc": dense contractions on tcgen05 (fp16 hi/lo split operands, fp32-grade); "simt": fp32 FFMA kernels."""
+    b = os.environ.get("MAGE_BACKEND", "tc")
+    assert b in ("tc", "simt"), b
+    return b
+
+
+def _upsample_phase_weights(w: torch.Tensor):
+    """3x3 conv over a nearest-x2-upsampled map == four 2x2 sub-pixel phase convs over the stored map
+    (vqvae_model.py:205-209 without materialising the upsample).  w [Cout,Cin,3,3] -> {(py,px): [Cout,2,2,Cin]}:
+    output row 2y+py reads stored rows (y-1, y) with weights (w0, w1+w2) for py=0 and rows (y, y+1) with
+    (w0+w1, w2) for py=1 (same along x); sums are formed in fp64 and rounded once to fp32."""
+    wd = w.double()
+    rows = {0: [wd[:, :, 0], wd[:, :, 1] + wd[:, :, 2]], 1: [wd[:, :, 0] + wd[:, :, 1], wd[:, :, 2]]}  # each [Cout,Cin,3(kx)]
+    out = {}
+    for py in (0, 1):
+        for px in (0, 1):
+            taps = []
+            for r in rows[py]:
+                cols = [r[:, :, 0], r[:, :, 1] + r[:, :, 2]] if px == 0 else [r[:, :, 0] + r[:, :, 1], r[:, :, 2]]
+                taps.append(torch.stack(cols, dim=1))  # [Cout,2(kx),Cin]
+            out[(py, px)] = torch.stack(taps, dim=1).float().contiguous()  # [Cout,2(ky),2(kx),Cin]
+    return out
+
+
 def _pack_conv(w: torch.Tensor) -> torch.Tensor:
     """[Cout,Cin,KH,KW] -> [Cout,KH,KW,Cin] (K-contiguous rows for the implicit GEMM)."""
     return w.permute(0, 2, 3, 1).contiguous()
@@ -39,11 +64,15 @@ def _bn_fold(sd, name, eps=1e-5):
 
 
 class VQVAEEngine:
-    def __init__(self, sd: Dict[str, torch.Tensor]):
+    def __init__(self, sd: Dict[str, torch.Tensor], backend: Optional[str] = None):
         """sd: VectorQuantizedVAE.state_dict() tensors (fp32, on the CUDA device)."""
         self.device = sd["codebook.embedding.weight"].device
         assert self.device.type == "cuda", "VQVAEEngine needs CUDA tensors (no CPU path)"
         self.down_ratio = 4 if "encoder.1.running_mean" in sd else 8
+        self.backend = backend or default_backend()
+        if self.down_ratio != 8:
+            self.backend = "simt"  # the f4 (MNIST) stack keeps the fp32 FFMA kernels (stride-2 / Cout=1 layers)
+        ops.flag(self.device)
         self.codebook = sd["codebook.embedding.weight"].contiguous()
         self.K, self.D = self.codebook.shape
         w = {}
@@ -85,6 +114,22 @@ class VQVAEEngine:
                         sub = wt[:, :, list(taps[py]), :][:, :, :, list(taps[px])]  # [Cin,Cout,2,2]
                         w[f"{name}.p{py}{px}"] = sub.permute(1, 2, 3, 0).contiguous()  # [Cout,2,2,Cin]
         self.w = w
+        if self.backend == "tc":
+            self._prepare_tc(sd)
+
+    def _prepare_tc(self, sd):
+        """Split (fp16 hi/lo) copies of every tensor-core operand: conv / 1x1 weights, the codebook (raw and
+        ReLU-ed: DecoderBlock reads both, vqvae_model.py:150-156), phase kernels of the upsample-reading convs."""
+        ws = {}
+        for k, v in self.w.items():
+            if k.endswith(".weight") and not k.startswith("enc0"):
+                ws[k] = ops.split(v)
+        for name in ("decoder.2", "decoder.4", "decoder.6"):
+            for ph, wp in _upsample_phase_weights(sd[name + ".block.3.weight"]).items():
+                ws[f"{name}.block.3.p{ph[0]}{ph[1]}"] = ops.split(wp)
+        self.ws = ws
+        self.cb_split = ops.split(self.codebook)
+        self.cb_relu_split = ops.split(self.codebook, relu=True)
 
     # ------------------------------------------------------------------ encoder
     def _enc_block(self, name: str, x: torch.Tensor, final_relu: bool = False) -> torch.Tensor:
@@ -112,10 +157,32 @@ class VQVAEEngine:
         out = ops.gemm(h.view(-1, C), w[name + ".c1.w"], w[name + ".c1.b"], residual=xr.view(-1, C), act=act)
         return out.view(n, H, W, C)
 
+    def _enc_block_tc(self, name: str, x: torch.Tensor, final_relu: bool = False) -> torch.Tensor:
+        """EncoderBlock on the tensor cores: x fp32 NHWC in, fp32 NHWC out (feeds max-pool / VQ argmin)."""
+        w, ws = self.w, self.ws
+        n, H, W, C = x.shape
+        xr = ops.split(x, relu=True)
+        if (name + ".id_path.weight") in w:
+            idp, _, _ = ops.gemm_tc(ops.split(x).view(2, -1, C), ws[name + ".id_path.weight"], w[name + ".id_path.bias"])
+        else:
+            idp = x.view(-1, C)
+        _, h, _ = ops.conv2d_tc(xr, ws[name + ".block.1.weight"], w[name + ".block.1.bias"], pad=(1, 1), act=ACT_RELU, want=("split",))
+        _, h, _ = ops.conv2d_tc(h, ws[name + ".block.3.weight"], w[name + ".block.3.bias"], pad=(1, 1), act=ACT_RELU, want=("split",))
+        _, h, _ = ops.conv2d_tc(h, ws[name + ".block.5.weight"], w[name + ".block.5.bias"], pad=(1, 1), act=ACT_RELU, want=("split",))
+        out, _, _ = ops.gemm_tc(h.view(2, -1, h.shape[-1]), ws[name + ".block.7.weight"], w[name + ".block.7.bias"], residual=idp,
+                                act=(ACT_RELU | ACT_POST) if final_relu else ACT_NONE)
+        return out.view(n, H, W, -1)
+
     def encode_features(self, x: torch.Tensor) -> torch.Tensor:
         """x [N,C,H,W] planar fp32 -> z_e NHWC [N,h,w,D] (vqvae_model.py:172-179 / :192-202)."""
         w = self.w
         x = x.contiguous()
+        if self.backend == "tc":
+            h = ops.conv2d_first(x, w["enc0_wt"], w["enc0_b"], cout=w["enc0_b"].numel(), kh=7, kw=7, stride=1, pad=3)
+            h = ops.maxpool2x2(self._enc_block_tc("encoder.1", h))
+            h = ops.maxpool2x2(self._enc_block_tc("encoder.3", h))
+            h = ops.maxpool2x2(self._enc_block_tc("encoder.5", h))
+            return self._enc_block_tc("encoder.7", h, final_relu=True)
         if self.down_ratio == 8:
             h = ops.conv2d_first(x, w["enc0_wt"], w["enc0_b"], cout=w["enc0_b"].numel(), kh=7, kw=7, stride=1, pad=3)
             h = ops.maxpool2x2(self._enc_block("encoder.1", h))
@@ -149,9 +216,52 @@ class VQVAEEngine:
         return ops.conv2d(h, w[name + ".block.7.weight"], w[name + ".block.7.bias"], pad=(1, 1), residual=idp,
                           res_mode=2 if up else 1)
 
+    def _decode_into_tc(self, idx: torch.Tensor, out: torch.Tensor, out_img_stride: int) -> None:
+        """f8 decoder on the tensor cores.  Activations travel between layers in the split operand format;
+        a block's output is produced in exactly the forms its consumer reads: split(raw) for an id_path conv,
+        fp32 for an identity skip (read through the nearest x2 upsample), split(relu) for the next 1x1."""
+        w, ws = self.w, self.ws
+        x_split = ops.embedding_split(idx, self.cb_split)        # [2,n,h,w,D]
+        xr_split = ops.embedding_split(idx, self.cb_relu_split)
+        x_f32 = None
+        blocks = [("decoder.0", False), ("decoder.2", True), ("decoder.4", True), ("decoder.6", True)]
+        for bi, (name, up) in enumerate(blocks):
+            _, n, H, W, C = xr_split.shape
+            if (name + ".id_path.weight") in w:
+                idp, _, _ = ops.gemm_tc(x_split.view(2, -1, C), ws[name + ".id_path.weight"], w[name + ".id_path.bias"])
+                idp = idp.view(n, H, W, -1)
+            else:
+                idp = x_f32
+            _, h, _ = ops.gemm_tc(xr_split.view(2, -1, C), ws[name + ".block.1.weight"], w[name + ".block.1.bias"], act=ACT_RELU,
+                                  want=("split",))
+            hid = h.shape[-1]
+            h = h.view(2, n, H, W, hid)
+            if up:
+                h2 = torch.empty(2, n, 2 * H, 2 * W, hid, device=h.device, dtype=torch.float16)
+                for py in (0, 1):
+                    for px in (0, 1):
+                        ops.conv2d_tc(h, ws[f"{name}.block.3.p{py}{px}"], w[name + ".block.3.bias"], pad=(1 - py, 1 - px), act=ACT_RELU,
+                                      want=(), out_split=h2, out_hw=(H, W), scatter=(2, 2, py, px), full_hw=(2 * H, 2 * W))
+            else:
+                _, h2, _ = ops.conv2d_tc(h, ws[name + ".block.3.weight"], w[name + ".block.3.bias"], pad=(1, 1), act=ACT_RELU,
+                                         want=("split",))
+            _, h3, _ = ops.conv2d_tc(h2, ws[name + ".block.5.weight"], w[name + ".block.5.bias"], pad=(1, 1), act=ACT_RELU,
+                                     want=("split",))
+            if bi + 1 == len(blocks):
+                want = ("f32",)
+            elif (blocks[bi + 1][0] + ".id_path.weight") in w:
+                want = ("split", "split_relu")
+            else:
+                want = ("f32", "split_relu")
+            x_f32, x_split, xr_split = ops.conv2d_tc(h3, ws[name + ".block.7.weight"], w[name + ".block.7.bias"], pad=(1, 1),
+                                                     residual=idp, res_mode=2 if up else 1, want=want)
+        ops.conv1x1_tanh_nchw(x_f32, w["decoder.8.weight"], w["decoder.8.bias"], out, out_img_stride)
+
     def decode_into(self, idx: torch.Tensor, out: torch.Tensor, out_img_stride: int) -> None:
         """VectorQuantizedVAE.decode: idx int64 [N,h,w] -> tanh pixels written planar at
         out.data_ptr() + n*out_img_stride (elements), each image [C,H,W] contiguous."""
+        if self.backend == "tc":
+            return self._decode_into_tc(idx, out, out_img_stride)
         w = self.w
         n = idx.shape[0]
         z = ops.embedding(idx.reshape(-1), self.codebook).view(n, idx.shape[1], idx.shape[2], self.D)
@@ -187,9 +297,11 @@ class SamplerEngine:
     """Incremental greedy sampler for one device.  `sd` is MAGE.state_dict() (CUDA fp32)."""
 
     def __init__(self, sd: Dict[str, torch.Tensor], frames_length: int, randomness: bool, padding_idx: int = 0,
-                 temporal_attn: Optional[str] = None, use_cuda_graph: Optional[bool] = None):
+                 temporal_attn: Optional[str] = None, use_cuda_graph: Optional[bool] = None, backend: Optional[str] = None):
         self.device = sd["visual_token_embedding.weight"].device
         assert self.device.type == "cuda", "SamplerEngine needs CUDA tensors (no CPU path)"
+        self.backend = backend or default_backend()
+        ops.flag(self.device)
         self.L = frames_length
         self.randomness = randomness
         self.padding_idx = padding_idx
@@ -197,7 +309,8 @@ class SamplerEngine:
         if use_cuda_graph is None:
             use_cuda_graph = os.environ.get("MAGE_CUDA_GRAPH", "1") != "0"
         self.use_cuda_graph = use_cuda_graph
-        self.vq = VQVAEEngine({k[len("first_stage_model."):]: v for k, v in sd.items() if k.startswith("first_stage_model.")})
+        self.vq = VQVAEEngine({k[len("first_stage_model."):]: v for k, v in sd.items() if k.startswith("first_stage_model.")},
+                              backend=self.backend)
         g = lambda k: sd[k].contiguous()
         self.sd = sd
         self.E = g("visual_token_embedding.weight")
@@ -227,6 +340,16 @@ class SamplerEngine:
         self.n_head = self.C // 32
         self._graphs = {}
         self.kernels_per_generate = None
+        if self.backend == "tc":
+            # split (fp16 hi/lo) copies of the per-step tensor-core operands
+            ws = {"E": ops.split(self.E), "Wc": ops.split(self.Wc)}
+            for k in ("in_linear.weight", "out.weight"):
+                ws[p + k] = ops.split(g(p + k))
+            for i in range(self.n_blocks):
+                bp = p + f"blocks.{i}."
+                for k in ("attn.in_proj_weight", "attn.out_proj.weight", "mlp.c_fc.weight", "mlp.c_proj.weight"):
+                    ws[bp + k] = ops.split(g(bp + k))
+            self.ws = ws
 
     # ------------------------------------------------------------------ prelude
     def _token_features(self, tok: torch.Tensor, B: int) -> torch.Tensor:
@@ -321,6 +444,47 @@ class SamplerEngine:
         ops.gemm(h, sd[p + ".mlp.c_proj.weight"], sd[p + ".mlp.c_proj.bias"], residual=x, out=x)
         return x
 
+    # ------------------------------------------------------------------ decoder step on the tensor cores
+    def _token_features_tc(self, tok: torch.Tensor, B: int) -> torch.Tensor:
+        """split(f(tok)) [2, B*R*R, C]: gather from the pre-split embedding table, 3x3 conv as a tcgen05 implicit
+        GEMM with the H/W positional map added in the epilogue (mage_model.py:674-676, 682)."""
+        emb = ops.embedding_split(tok.view(B, self.R, self.R), self.ws["E"])
+        _, f, _ = ops.conv2d_tc(emb, self.ws["Wc"], None, pad=(1, 1), residual=self.posHW, res_mode=3, want=("split",))
+        return f.view(2, -1, self.C)
+
+    def _block_step_tc(self, i: int, x: torch.Tensor, pos: int, B: int, caches, bufs, last: bool):
+        """AxialAttentionBlock (mage_model.py:35-53) for one temporal position, dense contractions on tcgen05.
+        x [B*R*R, C] fp32 residual stream (updated in place); LayerNorm / attention emit split operands."""
+        sd, ws, C, R = self.sd, self.ws, self.C, self.R
+        p = f"generate_model.blocks.{i}"
+        M = x.shape[0]
+        u, h, qkv = bufs["u"], bufs["h"], bufs["qkv"]
+        ops.layernorm(x, sd[p + ".ln_1.weight"], sd[p + ".ln_1.bias"], out_split=u)
+        ops.gemm_tc(u, ws[p + ".attn.in_proj_weight"], sd[p + ".attn.in_proj_bias"], out=qkv)
+        kind = i % 3
+        if kind == 0:
+            kc, vc = caches[i]
+            if self.temporal_attn == "tma":
+                ops.temporal_attn_step(qkv, kc, vc, None, pos, self.scale, out_split=u)
+            else:
+                ops.kv_append(qkv, kc, vc, pos)
+                Lmax = kc.shape[1]
+                ops.mha(qkv, kc, vc, None, n_outer=M, n_inner=1, n_head=self.n_head, Sq=1, Sk=pos + 1,
+                        q_strides=(3 * C, 0, 0), k_strides=(Lmax * C, 0, C), v_strides=(Lmax * C, 0, C),
+                        o_strides=(C, 0, 0), key_len=None, scale=self.scale, out_split=u)
+        else:
+            inner, seq = (1, R) if kind == 1 else (R, 1)
+            ops.mha(qkv, qkv[:, C:], qkv[:, 2 * C:], None, n_outer=B, n_inner=R, n_head=self.n_head, Sq=R, Sk=R,
+                    q_strides=(R * R * 3 * C, inner * 3 * C, seq * 3 * C), k_strides=(R * R * 3 * C, inner * 3 * C, seq * 3 * C),
+                    v_strides=(R * R * 3 * C, inner * 3 * C, seq * 3 * C), o_strides=(R * R * C, inner * C, seq * C),
+                    key_len=None, scale=self.scale, out_split=u)
+        ops.gemm_tc(u, ws[p + ".attn.out_proj.weight"], sd[p + ".attn.out_proj.bias"], residual=x, out=x)
+        ops.layernorm(x, sd[p + ".ln_2.weight"], sd[p + ".ln_2.bias"], out_split=u)
+        ops.gemm_tc(u, ws[p + ".mlp.c_fc.weight"], sd[p + ".mlp.c_fc.bias"], act=ACT_QUICKGELU, want=(), out_split=h)
+        ops.gemm_tc(h, ws[p + ".mlp.c_proj.weight"], sd[p + ".mlp.c_proj.bias"], residual=x, out=x,
+                    out_split=u if last else None)  # the head reads split(x)
+        return x
+
     # ------------------------------------------------------------------ whole path
     def _generate_impl(self, images0: torch.Tensor, text: torch.Tensor, speed: Optional[torch.Tensor],
                        noise: Optional[torch.Tensor], video: torch.Tensor, tokens: torch.Tensor, tok0_out: torch.Tensor,
@@ -349,17 +513,30 @@ class SamplerEngine:
                       torch.empty(M, L, C, device=self.device, dtype=torch.float32))
                   for i in range(self.n_blocks) if i % 3 == 0}
         x = ops.gemm(anchor.view(M, C), sd[p + "context_linear.weight"], self.bias_ctx0)
+        tc = self.backend == "tc"
+        if tc:
+            ws = self.ws
+            bufs = {"u": torch.empty(2, M, C, device=self.device, dtype=torch.float16),
+                    "h": torch.empty(2, M, 4 * C, device=self.device, dtype=torch.float16),
+                    "qkv": torch.empty(M, 3 * C, device=self.device, dtype=torch.float32)}
         for i in range(self.n_blocks):
-            x = self._block_step(i, x, 0, B, caches)
+            x = self._block_step_tc(i, x, 0, B, caches, bufs, False) if tc else self._block_step(i, x, 0, B, caches)
         tok = tok0_out
         img_elems = video.shape[2] * video.shape[3] * video.shape[4]
         logits = torch.empty(M, sd[p + "out.weight"].shape[0], device=self.device, dtype=torch.float32)
         for j in range(L - 1):
-            f = self._token_features(tok, B)
-            x = ops.gemm(f, sd[p + "in_linear.weight"], self.bias_in_T[j + 1])
-            for i in range(self.n_blocks):
-                x = self._block_step(i, x, j + 1, B, caches)
-            ops.gemm(x, sd[p + "out.weight"], sd[p + "out.bias"], out=logits)
+            if tc:
+                f = self._token_features_tc(tok, B)
+                ops.gemm_tc(f, ws[p + "in_linear.weight"], self.bias_in_T[j + 1], out=x)
+                for i in range(self.n_blocks):
+                    x = self._block_step_tc(i, x, j + 1, B, caches, bufs, i + 1 == self.n_blocks)
+                ops.gemm_tc(bufs["u"], ws[p + "out.weight"], sd[p + "out.bias"], out=logits)
+            else:
+                f = self._token_features(tok, B)
+                x = ops.gemm(f, sd[p + "in_linear.weight"], self.bias_in_T[j + 1])
+                for i in range(self.n_blocks):
+                    x = self._block_step(i, x, j + 1, B, caches)
+                ops.gemm(x, sd[p + "out.weight"], sd[p + "out.bias"], out=logits)
             tok = ops.argmax_rows(logits, out=tokens[j].view(-1))
             if trace is not None:
                 trace.setdefault("logits", []).append(logits.clone())
@@ -385,6 +562,8 @@ class SamplerEngine:
             self._generate_impl(images0, text, speed, noise, video, tokens, tok0, trace)
             self.kernels_per_generate = ops.launch_count() - n0
             video[:, 0].copy_(images0)
+            if self.backend == "tc":
+                ops.check_flag(self.device)
             return video, tokens.permute(1, 0, 2).reshape(B, L - 1, R, R), tok0.view(B, R, R)
 
         key = (B, T, tuple(images0.shape[1:]), speed is not None, noise is not None)
@@ -400,6 +579,8 @@ class SamplerEngine:
         st["graph"].replay()
         video = st["video"]
         video[:, 0].copy_(st["images0"])
+        if self.backend == "tc":
+            ops.check_flag(self.device)  # loud failure if an operand left the fp16 split range (syncs)
         return video, st["tokens"].permute(1, 0, 2).reshape(B, L - 1, R, R), st["tok0"].view(B, R, R)
 
     def _capture(self, key, images0, text, speed, noise):

@@ -248,30 +248,35 @@ def maxpool2x2(x: torch.Tensor) -> torch.Tensor:
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
-              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+              out: Optional[torch.Tensor] = None, out_split: Optional[torch.Tensor] = None):
+    """LayerNorm over the last dim.  With `out_split` (fp16 [2, rows, C]) the result is written in the split
+    operand format of the tensor-core GEMMs (and the fp32 copy only if `out` is given as well)."""
     C = x.shape[-1]
     rows = x.numel() // C
-    if out is None:
+    if out is None and out_split is None:
         out = torch.empty_like(x)
-    check(_lib.lib().mage_layernorm_f32(_p(_f32(x)), _p(gamma), _p(beta), _p(out), rows, C, eps, _stream()),
-          "mage_layernorm_f32")
-    return out
+    check(_lib.lib().mage_layernorm_f32(_p(_f32(x)), _p(gamma), _p(beta), _p(out), _p(out_split), rows * C, _p(flag(x.device)),
+                                        rows, C, eps, _stream()), "mage_layernorm_f32")
+    return out if out_split is None else out_split
 
 
 def mha(q, k, v, out, *, n_outer, n_inner, n_head, Sq, Sk, q_strides, k_strides, v_strides, o_strides,
-        key_len: Optional[torch.Tensor] = None, scale: float) -> None:
+        key_len: Optional[torch.Tensor] = None, scale: float, out_split: Optional[torch.Tensor] = None) -> None:
     """Strided SDPA core (head_dim 32).  *_strides = (outer, inner, seq) in elements; q/k/v/out may be
     views into one packed qkv buffer (pass the view: its data_ptr carries the column offset)."""
     check(_lib.lib().mage_mha_f32(_p(q), _p(k), _p(v), _p(out), n_outer, n_inner, n_head, Sq, Sk, *q_strides, *k_strides,
-                                  *v_strides, *o_strides, _p(key_len), scale, _stream()), "mage_mha_f32")
+                                  *v_strides, *o_strides, _p(key_len), scale, _p(out_split),
+                                  out_split.numel() // 2 if out_split is not None else 0, _p(flag(q.device)), _stream()),
+          "mage_mha_f32")
 
 
-def temporal_attn_step(qkv: torch.Tensor, kcache: torch.Tensor, vcache: torch.Tensor, out: torch.Tensor, pos: int,
-                       scale: float) -> None:
+def temporal_attn_step(qkv: torch.Tensor, kcache: torch.Tensor, vcache: torch.Tensor, out: Optional[torch.Tensor], pos: int,
+                       scale: float, out_split: Optional[torch.Tensor] = None) -> None:
     M = qkv.shape[0]
     Lmax = kcache.shape[1]
-    check(_lib.lib().mage_temporal_attn_step_f32(_p(_f32(qkv)), _p(kcache), _p(vcache), _p(out), M, pos, Lmax, scale,
-                                                 _stream()), "mage_temporal_attn_step_f32")
+    check(_lib.lib().mage_temporal_attn_step_f32(_p(_f32(qkv)), _p(kcache), _p(vcache), _p(out), _p(out_split),
+                                                 out_split.numel() // 2 if out_split is not None else 0, _p(flag(qkv.device)),
+                                                 M, pos, Lmax, scale, _stream()), "mage_temporal_attn_step_f32")
 
 
 def kv_append(qkv: torch.Tensor, kcache: torch.Tensor, vcache: torch.Tensor, pos: int) -> None:

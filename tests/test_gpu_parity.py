@@ -22,6 +22,13 @@ PIX_REL = 1e-3
 PIX_ABS = 5e-3
 
 
+@pytest.fixture(params=["tc", "simt"], autouse=True)
+def backend(request, monkeypatch):
+    """Every parity case runs on both back ends: tcgen05 split-fp16 (default) and fp32 FFMA."""
+    monkeypatch.setenv("MAGE_BACKEND", request.param)
+    return request.param
+
+
 def _build(params, sd):
     from mage_b200.config import instantiate_from_config
     model = instantiate_from_config({"target": "modules.mage_model.MAGE", "params": params})
