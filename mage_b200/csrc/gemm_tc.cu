@@ -6,15 +6,16 @@
 // tcgen05.mma kind::f16 instructions (hi*hi -> main, lo*hi + hi*lo -> corr), both accumulators live
 // in TMEM, the epilogue forms main + corr*2^-11 -- fp32-grade accuracy at a third of the fp16 rate.
 //
-// One persistent CTA per SM, 192 threads, warp-specialised:
+// One persistent CTA per SM, 320 threads, warp-specialised:
 //   warp 0   TMA producer: one 5-D box for the A tile (both planes) + one 3-D box for the W tile per
 //            k-block into a SWIZZLE_128B ring (mbarrier full/empty)
 //   warp 1   TMEM allocator + the single MMA-issuing thread (tcgen05.mma, tcgen05.commit)
-//   warps 2-5 epilogue: tcgen05.ld -> smem transpose -> bias / activation / residual -> coalesced
-//            fp32 and/or split stores (the next consumer's operand format)
+//   warps 2-9 epilogue (two per TMEM lane quadrant): tcgen05.ld -> bias / activation -> smem transpose ->
+//            residual -> coalesced fp32 and/or split stores (the next consumer's operand format)
 // For a convolution the A tile is an NHWC patch: the box is [64 ch, Wb, Hb, 1 image, 2 planes] at
 // the tap's (dy,dx) offset and TMA's out-of-bounds zero fill is the padding, so im2col never exists.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -26,8 +27,7 @@ using namespace tc;
 constexpr int BM = 128;      // rows per tile = TMEM lanes
 constexpr int BK = 64;       // halves per k-block = one 128-byte swizzle row
 constexpr int UK = 16;       // K of one tcgen05.mma kind::f16
-constexpr int NTHREADS = 192;
-constexpr int STG_LD = 36;   // floats per staging row (32 + 4 pad: float4-aligned, conflict-free)
+constexpr int NTHREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 constexpr int SMEM_BUDGET = 227 * 1024;
 
 struct TcParams {
@@ -50,13 +50,138 @@ struct Cfg {
   static constexpr int A_BYTES = 2 * BM * BK * 2;   // hi + lo planes
   static constexpr int W_BYTES = 2 * BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
-  static constexpr int STAGING_BYTES = 4 * 32 * STG_LD * 4;
+  static constexpr int STAGING_BYTES = 8 * 32 * 32 * 4;   // one XOR-swizzled 32x32 fp32 transpose tile per epilogue warp
   static constexpr int STAGES_RAW = (SMEM_BUDGET - 1024 - STAGING_BYTES - 256) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
   static constexpr int ACC_STAGES = (2 * BN * 2 <= 512) ? 2 : 1;   // main+corr per accumulator stage
   static constexpr int TMEM_COLS = 512;
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + 256;
 };
+
+template <int ACT>
+__device__ __forceinline__ float act_fn(float x) {
+  if (ACT == MAGE_ACT_RELU) return fmaxf(x, 0.f);
+  // x * sigmoid(1.702 x) with ex2.approx / rcp.approx (a few ulp, branch-free: the epilogue is latency-bound)
+  if (ACT == MAGE_ACT_QUICKGELU) return __fdividef(x, 1.f + __expf(-1.702f * x));
+  if (ACT == MAGE_ACT_GELU) return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
+  if (ACT == MAGE_ACT_TANH) return tanhf(x);
+  return x;
+}
+
+// Epilogue of one CTA: 8 warps, two per TMEM lane quadrant (warp % 4), the pair splitting the 32-column chunks.
+// Per chunk: tcgen05.ld main + corr -> v = main + corr*2^-11 (row-per-thread layout) -> XOR-swizzled smem
+// transpose -> bias, activation, residual (row-contiguous layout) -> coalesced fp32 and/or split stores.
+template <int BN, int ACT>
+__device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_base, float* staging, uint32_t tfull0, uint32_t tempty0) {
+  using C = Cfg<BN>;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int quad = warp & 3, half = (warp - 2) >> 2;
+  float* stg = staging + (warp - 2) * 32 * 32;
+  const int cq = lane & 7, rq = lane >> 3;
+  const bool res_relu = (p.act & MAGE_RES_RELU) != 0, post = (p.act & MAGE_ACT_POST_RES) != 0;
+  // everything the chunk loop touches lives in registers: `p` is memory the global stores could alias
+  const float* const __restrict__ bias = p.bias;
+  const float* const __restrict__ res = p.res;
+  float* const out = p.out;
+  __half* const split = p.split;
+  __half* const split_relu = p.split_relu;
+  const int64_t split_plane = p.split_plane, split_relu_plane = p.split_relu_plane;
+  const int n_tiles = p.n_tiles, M = p.M;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+  int tcount = 0;
+  bool overflow = false;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+    const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+    const int acc = tcount % C::ACC_STAGES;
+    const uint32_t aph = (tcount / C::ACC_STAGES) & 1;
+    // output / residual row offsets of the 8 rows this lane stores (rows quad*32 + i*4 + rq)
+    int64_t out_off[8], res_off[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = quad * 32 + i * 4 + rq;
+      const int m = mt * BM + r;
+      out_off[i] = -1;
+      res_off[i] = -1;
+      if (m >= M) continue;
+      if (p.conv) {
+        const int tiles_x = p.Wout / p.Wb, tiles_y = p.Hout / p.Hb;
+        const int img = mt / (tiles_x * tiles_y), rr = mt - img * tiles_x * tiles_y;
+        const int ty = rr / tiles_x, tx = rr - ty * tiles_x;
+        const int oy = ty * p.Hb + r / p.Wb, ox = tx * p.Wb + r % p.Wb;
+        out_off[i] = (int64_t)img * p.out_img_stride +
+                     ((int64_t)(oy * p.out_sy + p.out_oy) * p.Wfull + (ox * p.out_sx + p.out_ox)) * p.ldc;
+        if (p.res_mode == 1) res_off[i] = (((int64_t)img * p.Hout + oy) * p.Wout + ox) * p.ldr;
+        else if (p.res_mode == 2) res_off[i] = (((int64_t)img * (p.Hout >> 1) + (oy >> 1)) * (p.Wout >> 1) + (ox >> 1)) * p.ldr;
+        else if (p.res_mode == 3) res_off[i] = ((int64_t)oy * p.Wout + ox) * p.ldr;
+      } else {
+        out_off[i] = (int64_t)m * p.ldc;
+        if (res) res_off[i] = (int64_t)(p.res_mod > 0 ? m % p.res_mod : m) * p.ldr;
+      }
+    }
+    mbar_wait(tfull0 + 8u * acc, aph);
+    tc_fence_after();
+    const uint32_t t_main = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 2 * BN, t_corr = t_main + BN;
+#pragma unroll 1
+    for (int c = half; c < BN / 32; c += 2) {
+      const int n = nt * BN + c * 32 + cq * 4;
+      // bias / residual vectors first: their global latency hides behind the TMEM loads and the transpose
+      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (bias) bv = __ldg(reinterpret_cast<const float4*>(bias + n));
+      float4 rv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (res_off[i] >= 0) rv[i] = __ldg(reinterpret_cast<const float4*>(res + res_off[i] + n));
+      }
+      uint32_t rm[32], rc[32];
+      tmem_ld32(t_main + c * 32, rm);
+      tmem_ld32(t_corr + c * 32, rc);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 v;
+        v.x = fmaf(__uint_as_float(rc[4 * j + 0]), kLoInv, __uint_as_float(rm[4 * j + 0]));
+        v.y = fmaf(__uint_as_float(rc[4 * j + 1]), kLoInv, __uint_as_float(rm[4 * j + 1]));
+        v.z = fmaf(__uint_as_float(rc[4 * j + 2]), kLoInv, __uint_as_float(rm[4 * j + 2]));
+        v.w = fmaf(__uint_as_float(rc[4 * j + 3]), kLoInv, __uint_as_float(rm[4 * j + 3]));
+        *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = v;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (out_off[i] < 0) continue;
+        const int r = i * 4 + rq;
+        float4 v = *reinterpret_cast<const float4*>(stg + r * 32 + ((cq ^ (r & 7)) << 2));
+        v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+        if (ACT != MAGE_ACT_NONE && !post) { v.x = act_fn<ACT>(v.x); v.y = act_fn<ACT>(v.y); v.z = act_fn<ACT>(v.z); v.w = act_fn<ACT>(v.w); }
+        float4 a = rv[i];
+        if (res_relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+        v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+        if (ACT != MAGE_ACT_NONE && post) { v.x = act_fn<ACT>(v.x); v.y = act_fn<ACT>(v.y); v.z = act_fn<ACT>(v.z); v.w = act_fn<ACT>(v.w); }
+        const int64_t o = out_off[i] + n;
+        if (out) *reinterpret_cast<float4*>(out + o) = v;
+        if (split) {
+          uint2 hi, lo;
+          overflow |= split4(v, hi, lo);
+          *reinterpret_cast<uint2*>(split + o) = hi;
+          *reinterpret_cast<uint2*>(split + split_plane + o) = lo;
+        }
+        if (split_relu) {
+          uint2 hi, lo;
+          overflow |= split4(make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f)), hi, lo);
+          *reinterpret_cast<uint2*>(split_relu + o) = hi;
+          *reinterpret_cast<uint2*>(split_relu + split_relu_plane + o) = lo;
+        }
+      }
+      __syncwarp();
+    }
+    // accumulator drained: hand the TMEM stage back to the MMA thread
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
+  }
+  if (overflow && p.flag) atomicOr(p.flag, 1);
+}
 
 template <int BN>
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -86,7 +211,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
+      mbar_init(tempty_bar(a), 8);
     }
     mbar_fence_init();
   }
@@ -163,102 +288,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------ epilogue warps (TMEM lane quadrant = warp % 4)
-    const int quad = warp & 3;
-    float* stg = staging + (warp - 2) * 32 * STG_LD;
-    const int cq = lane & 7, rq = lane >> 3;
-    const int act = p.act & 0xff;
-    const bool post = (p.act & MAGE_ACT_POST_RES) != 0, res_relu = (p.act & MAGE_RES_RELU) != 0;
-    int tcount = 0;
-    bool overflow = false;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
-      const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
-      const int acc = tcount % C::ACC_STAGES;
-      const uint32_t aph = (tcount / C::ACC_STAGES) & 1;
-      // output / residual row offsets of the 8 rows this lane stores (rows quad*32 + i*4 + rq)
-      int64_t out_off[8], res_off[8];
-      bool row_ok[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = quad * 32 + i * 4 + rq;
-        const int m = mt * BM + r;
-        row_ok[i] = m < p.M;
-        out_off[i] = 0;
-        res_off[i] = -1;
-        if (!row_ok[i]) continue;
-        if (p.conv) {
-          const int tiles_x = p.Wout / p.Wb, tiles_y = p.Hout / p.Hb;
-          const int img = mt / (tiles_x * tiles_y), rr = mt - img * tiles_x * tiles_y;
-          const int ty = rr / tiles_x, tx = rr - ty * tiles_x;
-          const int oy = ty * p.Hb + r / p.Wb, ox = tx * p.Wb + r % p.Wb;
-          out_off[i] = (int64_t)img * p.out_img_stride +
-                       ((int64_t)(oy * p.out_sy + p.out_oy) * p.Wfull + (ox * p.out_sx + p.out_ox)) * p.ldc;
-          if (p.res_mode == 1) res_off[i] = (((int64_t)img * p.Hout + oy) * p.Wout + ox) * p.ldr;
-          else if (p.res_mode == 2) res_off[i] = (((int64_t)img * (p.Hout >> 1) + (oy >> 1)) * (p.Wout >> 1) + (ox >> 1)) * p.ldr;
-          else if (p.res_mode == 3) res_off[i] = ((int64_t)oy * p.Wout + ox) * p.ldr;
-        } else {
-          out_off[i] = (int64_t)m * p.ldc;
-          if (p.res) res_off[i] = (int64_t)(p.res_mod > 0 ? m % p.res_mod : m) * p.ldr;
-        }
-      }
-      mbar_wait(tfull_bar(acc), aph);
-      tc_fence_after();
-      const uint32_t t_main = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 2 * BN, t_corr = t_main + BN;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t rm[32], rc[32];
-        tmem_ld32(t_main + c * 32, rm);
-        tmem_ld32(t_corr + c * 32, rc);
-        tmem_wait_ld();
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 v;
-          v.x = fmaf(__uint_as_float(rc[4 * j + 0]), kLoInv, __uint_as_float(rm[4 * j + 0]));
-          v.y = fmaf(__uint_as_float(rc[4 * j + 1]), kLoInv, __uint_as_float(rm[4 * j + 1]));
-          v.z = fmaf(__uint_as_float(rc[4 * j + 2]), kLoInv, __uint_as_float(rm[4 * j + 2]));
-          v.w = fmaf(__uint_as_float(rc[4 * j + 3]), kLoInv, __uint_as_float(rm[4 * j + 3]));
-          *reinterpret_cast<float4*>(stg + lane * STG_LD + 4 * j) = v;
-        }
-        __syncwarp();
-        const int n = nt * BN + c * 32 + cq * 4;
-        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (!row_ok[i]) continue;
-          float4 v = *reinterpret_cast<const float4*>(stg + (i * 4 + rq) * STG_LD + cq * 4);
-          v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-          if (!post) { v.x = mage_act(v.x, act); v.y = mage_act(v.y, act); v.z = mage_act(v.z, act); v.w = mage_act(v.w, act); }
-          if (res_off[i] >= 0) {
-            float4 rv = __ldg(reinterpret_cast<const float4*>(p.res + res_off[i] + n));
-            if (res_relu) { rv.x = fmaxf(rv.x, 0.f); rv.y = fmaxf(rv.y, 0.f); rv.z = fmaxf(rv.z, 0.f); rv.w = fmaxf(rv.w, 0.f); }
-            v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
-          }
-          if (post) { v.x = mage_act(v.x, act); v.y = mage_act(v.y, act); v.z = mage_act(v.z, act); v.w = mage_act(v.w, act); }
-          const int64_t o = out_off[i] + n;
-          if (p.out) *reinterpret_cast<float4*>(p.out + o) = v;
-          if (p.split) {
-            uint2 hi, lo;
-            overflow |= split4(v, hi, lo);
-            *reinterpret_cast<uint2*>(p.split + o) = hi;
-            *reinterpret_cast<uint2*>(p.split + p.split_plane + o) = lo;
-          }
-          if (p.split_relu) {
-            uint2 hi, lo;
-            const float4 rv = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
-            overflow |= split4(rv, hi, lo);
-            *reinterpret_cast<uint2*>(p.split_relu + o) = hi;
-            *reinterpret_cast<uint2*>(p.split_relu + p.split_relu_plane + o) = lo;
-          }
-        }
-        __syncwarp();
-      }
-      // accumulator drained: hand the TMEM stage back to the MMA thread
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    // ------------------------------------------------------------ epilogue warps
+    switch (p.act & 0xff) {
+      case MAGE_ACT_NONE: epilogue_loop<BN, MAGE_ACT_NONE>(p, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
+      case MAGE_ACT_RELU: epilogue_loop<BN, MAGE_ACT_RELU>(p, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
+      case MAGE_ACT_QUICKGELU: epilogue_loop<BN, MAGE_ACT_QUICKGELU>(p, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
+      case MAGE_ACT_GELU: epilogue_loop<BN, MAGE_ACT_GELU>(p, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
+      default: epilogue_loop<BN, MAGE_ACT_TANH>(p, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
     }
-    if (overflow && p.flag) atomicOr(p.flag, 1);
   }
 
   tc_fence_before();
@@ -351,13 +388,14 @@ int launch_tc(const CUtensorMap& mapA, const CUtensorMap& mapW, const TcParams& 
 }
 
 int pick_bn(int N, int64_t m_tiles) {
-  // widest tile that divides N; prefer a narrower one when the wide tile leaves most SMs idle
+  static const int forced = [] { const char* e = getenv("MAGE_TC_BN"); return e ? atoi(e) : 0; }();  // tuning aid
+  if (forced && N % forced == 0) return forced;
+  // BN = 128 keeps two (main + corr) accumulator stages in the 512 TMEM columns, so the epilogue of one tile
+  // overlaps the MMAs of the next; measured faster than BN = 256 (single stage) on every shape of the path.
+  // BN = 64 when N is not a multiple of 128 or the 128-wide tiling would leave most SMs idle.
   const int sms = num_sms();
-  for (int bn : {256, 128, 64}) {
-    if (N % bn) continue;
-    if (bn > 64 && m_tiles * (N / bn) < sms && N % (bn / 2) == 0) continue;
-    return bn;
-  }
+  if (N % 128 == 0 && (m_tiles * (N / 128) >= sms || N % 64 != 0)) return 128;
+  if (N % 64 == 0) return 64;
   return 0;
 }
 

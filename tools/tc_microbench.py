@@ -1,0 +1,96 @@
+#!/usr/bin/env python
+"""Micro-benchmark of the tensor-core GEMM / conv kernel on the shapes of the C5 workload
+(B=64: M = 16384 token rows per decode step; VQ-VAE decoder maps for 64 frames).
+Prints achieved fp32-grade TFLOP/s per shape (CUDA events, L2 flushed between iterations)."""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from mage_b200 import ops  # noqa: E402
+
+DEV = "cuda"
+
+
+def timeit(fn, iters, flush):
+    fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--only", default="")
+    ap.add_argument("--no-flush", action="store_true")
+    args = ap.parse_args()
+    flush = None if args.no_flush else torch.empty(256 << 20, device=DEV, dtype=torch.uint8)
+    M = 16384
+    g = torch.Generator(device="cpu").manual_seed(0)
+    rows = []
+
+    def gemm_case(name, M, N, K, mode):
+        a = ops.split(torch.randn(M, K, generator=g).to(DEV))
+        w = ops.split((torch.randn(N, K, generator=g) * K ** -0.5).to(DEV))
+        b = torch.randn(N, generator=g).to(DEV)
+        x = torch.randn(M, N, generator=g).to(DEV)
+        out = torch.empty(M, N, device=DEV)
+        sp = torch.empty(2, M, N, device=DEV, dtype=torch.float16)
+        if mode == "f32":
+            fn = lambda: ops.gemm_tc(a, w, b, out=out)
+        elif mode == "split":
+            fn = lambda: ops.gemm_tc(a, w, b, want=(), out_split=sp, act=2)
+        elif mode == "res":
+            fn = lambda: ops.gemm_tc(a, w, b, residual=x, out=x)
+        ms = timeit(fn, args.iters, flush)
+        rows.append((name, 2.0 * M * N * K / ms / 1e9, ms))
+
+    def conv_case(name, n, H, Cin, Cout, k, mode="split"):
+        x = ops.split(torch.randn(n, H, H, Cin, generator=g).to(DEV))
+        w = ops.split((torch.randn(Cout, k, k, Cin, generator=g) * (k * k * Cin) ** -0.5).to(DEV))
+        b = torch.randn(Cout, generator=g).to(DEV)
+        sp = torch.empty(2, n, H, H, Cout, device=DEV, dtype=torch.float16)
+        out = torch.empty(n, H, H, Cout, device=DEV) if mode == "f32" else None
+        fn = (lambda: ops.conv2d_tc(x, w, b, pad=(k // 2, k // 2), act=1, want=(), out_split=sp)) if mode == "split" else \
+             (lambda: ops.conv2d_tc(x, w, b, pad=(k // 2, k // 2), act=1, out=out))
+        ms = timeit(fn, args.iters, flush)
+        rows.append((name, 2.0 * n * H * H * Cout * k * k * Cin / ms / 1e9, ms))
+
+    cases = [
+        ("qkv 16384x1536x512 f32", lambda: gemm_case("qkv 16384x1536x512 f32", M, 1536, 512, "f32")),
+        ("outproj 16384x512x512 res", lambda: gemm_case("outproj 16384x512x512 res", M, 512, 512, "res")),
+        ("fc 16384x2048x512 split", lambda: gemm_case("fc 16384x2048x512 split", M, 2048, 512, "split")),
+        ("proj 16384x512x2048 res", lambda: gemm_case("proj 16384x512x2048 res", M, 512, 2048, "res")),
+        ("head 16384x512x512 f32", lambda: gemm_case("head 16384x512x512 f32", M, 512, 512, "f32")),
+        ("conv3x3 tok 64x16x16 512->512", lambda: conv_case("conv3x3 tok 64x16x16 512->512", 64, 16, 512, 512, 3)),
+        ("dec 16x16 128->128", lambda: conv_case("dec 16x16 128->128", 64, 16, 128, 128, 3)),
+        ("dec 16x16 128->512", lambda: conv_case("dec 16x16 128->512", 64, 16, 128, 512, 3, "f32")),
+        ("dec 32x32 64->64", lambda: conv_case("dec 32x32 64->64", 64, 32, 64, 64, 3)),
+        ("dec 64x64 64->64", lambda: conv_case("dec 64x64 64->64", 64, 64, 64, 64, 3)),
+        ("dec 64x64 64->256", lambda: conv_case("dec 64x64 64->256", 64, 64, 64, 256, 3, "f32")),
+        ("dec 128x128 64->64", lambda: conv_case("dec 128x128 64->64", 64, 128, 64, 64, 3)),
+        ("dec 128x128 64->256", lambda: conv_case("dec 128x128 64->256", 64, 128, 64, 256, 3, "f32")),
+    ]
+    for name, fn in cases:
+        if args.only and args.only not in name:
+            continue
+        fn()
+    for name, tf, ms in rows:
+        print(f"{name:36s} {ms:8.3f} ms  {tf:7.1f} TFLOP/s")
+
+
+if __name__ == "__main__":
+    main()
