@@ -235,6 +235,10 @@ def run_cuda(args, rank, world, local_rank):
             d[0] += flops
             d[1] += a.elapsed_time(b)
             d[2] += 1
+        breakdown = {k: {"ms_per_step": round(v[1], 2), "launches": v[2]} for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])}
+        ta = agg.get("temporal_attn")
+        if ta:
+            breakdown["temporal_attn"]["achieved_gbs"] = round(ta[0] / (ta[1] * 1e-3) / 1e9, 1)
         peaks, how = _peaks()
         peak = peaks["bf16_tflops_sustained"]
         g = agg.get("gemm", [0.0, 1.0, 1])
@@ -252,7 +256,10 @@ def run_cuda(args, rank, world, local_rank):
                 "conv_implicit_gemm": {"achieved": round(c[0] / (c[1] * 1e-3) / 1e12, 2), "launches_per_step": c[2], "ms_per_step": round(c[1], 2)},
                 "whole_step_algorithmic": {"achieved": round(value / world * GFLOP_PER_FRAME / 1e3, 2), "unit": "TFLOP/s",
                                            "frac": round(value / world * GFLOP_PER_FRAME / 1e3 / peak, 4)},
-                "how": "sum of algorithmic FLOPs / sum of CUDA-event durations over every launch of the kernel class in one eager step"}
+                "own_ceiling_frac": round(3.0 * ach / peak, 4) if args.backend == "tc" else None,
+                "breakdown_ms_per_step": breakdown,
+                "how": "sum of algorithmic FLOPs / sum of CUDA-event durations over every launch of the kernel class in one eager step; "
+                       "own_ceiling_frac counts the 3 MMAs issued per product"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

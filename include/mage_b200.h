@@ -147,6 +147,13 @@ int mage_mha_f32(const float* q, const float* k, const float* v, float* out,
                  int64_t o_outer, int64_t o_inner, int64_t o_seq,
                  const int32_t* key_len, float scale, void* out_split, int64_t split_plane, int* flag, void* stream);
 
+/* H-/W-axial attention of one temporal position (the non-causal blocks i % 3 == 1, 2 of FlatAxialDecoder,
+ * mage_model.py:35-53,340-345): qkv [B*R*R, 3C] rows ordered (b,h,w), R = 16, head_dim 32, C = 32*n_head.
+ * axis 1 attends along h (fixed b,w), axis 2 along w (fixed b,h).  One warp per (line, head), tiles staged
+ * once in shared memory; out fp32 [B*R*R, C] and/or out_split may be NULL. */
+int mage_axial_attn_f32(const float* qkv, float* out, void* out_split, int64_t split_plane, int* flag, int B, int R,
+                        int n_head, int axis, float scale, void* stream);
+
 /* Temporal attention for one decode step with a TMA-staged K/V cache (bulk async copies into
  * shared memory).  qkv [M, 3C] holds this position's q|k|v; k,v are appended to the caches
  * [M, Lmax, C] at `pos` and q attends positions 0..pos.  out [M, C].  C = 512, 16 heads x 32. */

@@ -85,6 +85,131 @@ __global__ void __launch_bounds__(256) mha_kernel(const MhaArgs p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Axial (H / W) attention of one decode position: 16 queries x 16 keys x 16 heads x 32 dims per line.
+// One warp per (image, line, head): the 16x32 Q, K, V tiles of the line are read ONCE with coalesced
+// 128-byte row segments into shared memory (the generic kernel re-reads K/V per query), scores and
+// P.V run out of shared memory with broadcast reads, the 16x32 output tile goes back through shared
+// memory so every store is a full 128-byte row segment.  HBM-bound: qkv in, attention out, once each.
+//   lane = (qi = lane & 15, half = lane >> 4): scores for keys half*8..+7, output dims half*16..+15.
+// ---------------------------------------------------------------------------------------------
+constexpr int AX_S = 16, AX_D = 32, AX_QLD = 36;  // Q rows padded to 36 floats (2-way instead of 16-way conflicts)
+constexpr int AX_WARPS = 4;  // 4 x 6.3 KB of tiles per block
+
+struct AxialArgs {
+  const float* qkv;  // [rows, 3C]: q | k | v
+  float* out;        // optional fp32 [rows, C]
+  __half* split;     // optional split copy
+  int64_t split_plane;
+  int* flag;
+  int n_lines;       // B * 16 lines
+  int n_head, C;
+  int64_t line_outer, line_inner, seq;  // in rows: row(b, line, s) = b*line_outer + line*line_inner + s*seq
+  int lines_per_img;
+  float scale;
+};
+
+__global__ void __launch_bounds__(AX_WARPS * 32) axial_attn_kernel(const AxialArgs p) {
+  __shared__ __align__(16) float sq[AX_WARPS][AX_S * AX_QLD];
+  __shared__ __align__(16) float sk[AX_WARPS][AX_S * AX_D];
+  __shared__ __align__(16) float sv[AX_WARPS][AX_S * AX_D];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t unit = (int64_t)blockIdx.x * AX_WARPS + warp;  // (line, head)
+  if (unit >= (int64_t)p.n_lines * p.n_head) return;
+  const int head = (int)(unit % p.n_head);
+  const int line = (int)(unit / p.n_head);
+  const int b = line / p.lines_per_img, l = line - b * p.lines_per_img;
+  const int64_t row0 = b * p.line_outer + l * p.line_inner;
+  const int C3 = 3 * p.C;
+
+  // coalesced tile loads: 8 lanes cover one 128-byte row segment, 4 rows per instruction
+  {
+    const int r4 = lane >> 3, c4 = (lane & 7) * 4;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int s = it * 4 + r4;
+      const float* src = p.qkv + (row0 + s * p.seq) * C3 + head * AX_D + c4;
+      const float4 q = __ldg(reinterpret_cast<const float4*>(src));
+      const float4 k = __ldg(reinterpret_cast<const float4*>(src + p.C));
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src + 2 * p.C));
+      *reinterpret_cast<float4*>(&sq[warp][s * AX_QLD + c4]) = q;
+      *reinterpret_cast<float4*>(&sk[warp][s * AX_D + c4]) = k;
+      *reinterpret_cast<float4*>(&sv[warp][s * AX_D + c4]) = v;
+    }
+  }
+  __syncwarp();
+  const int qi = lane & 15, half = lane >> 4;
+  float sc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sc[j] = 0.f;
+#pragma unroll
+  for (int d4 = 0; d4 < AX_D / 4; ++d4) {
+    const float4 q = *reinterpret_cast<const float4*>(&sq[warp][qi * AX_QLD + d4 * 4]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 k = *reinterpret_cast<const float4*>(&sk[warp][(half * 8 + j) * AX_D + d4 * 4]);  // broadcast
+      sc[j] = fmaf(q.x, k.x, sc[j]); sc[j] = fmaf(q.y, k.y, sc[j]);
+      sc[j] = fmaf(q.z, k.z, sc[j]); sc[j] = fmaf(q.w, k.w, sc[j]);
+    }
+  }
+  float m = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] *= p.scale; m = fmaxf(m, sc[j]); }
+  m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = expf(sc[j] - m); sum += sc[j]; }
+  sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+  const float inv = 1.f / sum;
+  // all 16 probabilities of this query: own 8 + the partner lane's 8 (selects keep the arrays in registers)
+  float plo[8], phi[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float other = __shfl_xor_sync(0xffffffffu, sc[j], 16);
+    plo[j] = half ? other : sc[j];
+    phi[j] = half ? sc[j] : other;
+  }
+  float4 o[4];
+#pragma unroll
+  for (int d4 = 0; d4 < 4; ++d4) o[d4] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < AX_S; ++j) {
+    const float pj = (j < 8) ? plo[j & 7] : phi[j & 7];
+#pragma unroll
+    for (int d4 = 0; d4 < 4; ++d4) {
+      const float4 v = *reinterpret_cast<const float4*>(&sv[warp][j * AX_D + half * 16 + d4 * 4]);  // broadcast per half
+      o[d4].x = fmaf(pj, v.x, o[d4].x); o[d4].y = fmaf(pj, v.y, o[d4].y);
+      o[d4].z = fmaf(pj, v.z, o[d4].z); o[d4].w = fmaf(pj, v.w, o[d4].w);
+    }
+  }
+  __syncwarp();  // everyone is done reading sq before it becomes the output staging tile
+#pragma unroll
+  for (int d4 = 0; d4 < 4; ++d4) {
+    float4 v = o[d4];
+    v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
+    *reinterpret_cast<float4*>(&sq[warp][qi * AX_QLD + half * 16 + d4 * 4]) = v;
+  }
+  __syncwarp();
+  {
+    const int r4 = lane >> 3, c4 = (lane & 7) * 4;
+    bool bad = false;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int s = it * 4 + r4;
+      const float4 v = *reinterpret_cast<const float4*>(&sq[warp][s * AX_QLD + c4]);
+      const int64_t e = (row0 + s * p.seq) * p.C + head * AX_D + c4;
+      if (p.out) *reinterpret_cast<float4*>(p.out + e) = v;
+      if (p.split) {
+        uint2 hi, lo;
+        bad |= tc::split4(v, hi, lo);
+        *reinterpret_cast<uint2*>(p.split + e) = hi;
+        *reinterpret_cast<uint2*>(p.split + p.split_plane + e) = lo;
+      }
+    }
+    if (bad && p.flag) atomicOr(p.flag, 1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Temporal attention step with bulk-async (TMA) staging of the K/V cache.
 //   grid  = M locations x 2 head-halves,  block = 256 threads = 8 warps = 8 heads x 32 lanes
 //   smem  = K[Lmax][256] + V[Lmax][256] floats (the 8 heads' 1 KB slice of every cached position)
@@ -210,6 +335,22 @@ extern "C" int mage_mha_f32(const float* q, const float* k, const float* v, floa
   const int64_t blocks = (a.total + 7) / 8;
   MAGE_CHECK_ARG(blocks < ((int64_t)1 << 31));
   mha_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(a);
+  return mage_post_launch();
+}
+
+extern "C" int mage_axial_attn_f32(const float* qkv, float* out, void* out_split, int64_t split_plane, int* flag, int B, int R,
+                                   int n_head, int axis, float scale, void* stream) {
+  // qkv [B*R*R, 3C] rows ordered (b, h, w); axis 1: sequences run over h for fixed (b, w); axis 2: over w for fixed (b, h)
+  MAGE_CHECK_ARG(B > 0 && R == AX_S && n_head > 0 && (axis == 1 || axis == 2) && (out || out_split));
+  MAGE_CHECK_ARG(aligned16(qkv) && aligned16(out) && aligned16(out_split) && split_plane % 4 == 0);
+  AxialArgs a{};
+  a.qkv = qkv; a.out = out; a.split = reinterpret_cast<__half*>(out_split); a.split_plane = split_plane; a.flag = flag;
+  a.n_lines = B * R; a.n_head = n_head; a.C = n_head * AX_D; a.lines_per_img = R; a.scale = scale;
+  a.line_outer = (int64_t)R * R;
+  a.line_inner = axis == 1 ? 1 : R;
+  a.seq = axis == 1 ? R : 1;
+  const int64_t units = (int64_t)a.n_lines * n_head;
+  axial_attn_kernel<<<(unsigned)((units + AX_WARPS - 1) / AX_WARPS), AX_WARPS * 32, 0, as_stream(stream)>>>(a);
   return mage_post_launch();
 }
 

@@ -433,11 +433,14 @@ class SamplerEngine:
                         o_strides=(C, 0, 0), key_len=None, scale=self.scale)
         else:
             # rows are (b, h, w); H-block: sequences run over h (stride R rows) for fixed (b, w); W-block over w
-            inner, seq = (1, R) if kind == 1 else (R, 1)
-            ops.mha(qkv, qkv[:, C:], qkv[:, 2 * C:], a, n_outer=B, n_inner=R, n_head=self.n_head, Sq=R, Sk=R,
-                    q_strides=(R * R * 3 * C, inner * 3 * C, seq * 3 * C), k_strides=(R * R * 3 * C, inner * 3 * C, seq * 3 * C),
-                    v_strides=(R * R * 3 * C, inner * 3 * C, seq * 3 * C), o_strides=(R * R * C, inner * C, seq * C),
-                    key_len=None, scale=self.scale)
+            if R == 16:
+                ops.axial_attn(qkv, a, B=B, R=R, n_head=self.n_head, axis=kind, scale=self.scale)
+            else:
+                inner, seq = (1, R) if kind == 1 else (R, 1)
+                ops.mha(qkv, qkv[:, C:], qkv[:, 2 * C:], a, n_outer=B, n_inner=R, n_head=self.n_head, Sq=R, Sk=R,
+                        q_strides=(R * R * 3 * C, inner * 3 * C, seq * 3 * C), k_strides=(R * R * 3 * C, inner * 3 * C, seq * 3 * C),
+                        v_strides=(R * R * 3 * C, inner * 3 * C, seq * 3 * C), o_strides=(R * R * C, inner * C, seq * C),
+                        key_len=None, scale=self.scale)
         ops.gemm(a, sd[p + ".attn.out_proj.weight"], sd[p + ".attn.out_proj.bias"], residual=x, out=x)
         ops.layernorm(x, sd[p + ".ln_2.weight"], sd[p + ".ln_2.bias"], out=u)
         h = ops.gemm(u, sd[p + ".mlp.c_fc.weight"], sd[p + ".mlp.c_fc.bias"], act=ACT_QUICKGELU)
@@ -473,11 +476,14 @@ class SamplerEngine:
                         q_strides=(3 * C, 0, 0), k_strides=(Lmax * C, 0, C), v_strides=(Lmax * C, 0, C),
                         o_strides=(C, 0, 0), key_len=None, scale=self.scale, out_split=u)
         else:
-            inner, seq = (1, R) if kind == 1 else (R, 1)
-            ops.mha(qkv, qkv[:, C:], qkv[:, 2 * C:], None, n_outer=B, n_inner=R, n_head=self.n_head, Sq=R, Sk=R,
-                    q_strides=(R * R * 3 * C, inner * 3 * C, seq * 3 * C), k_strides=(R * R * 3 * C, inner * 3 * C, seq * 3 * C),
-                    v_strides=(R * R * 3 * C, inner * 3 * C, seq * 3 * C), o_strides=(R * R * C, inner * C, seq * C),
-                    key_len=None, scale=self.scale, out_split=u)
+            if R == 16:
+                ops.axial_attn(qkv, None, B=B, R=R, n_head=self.n_head, axis=kind, scale=self.scale, out_split=u)
+            else:
+                inner, seq = (1, R) if kind == 1 else (R, 1)
+                ops.mha(qkv, qkv[:, C:], qkv[:, 2 * C:], None, n_outer=B, n_inner=R, n_head=self.n_head, Sq=R, Sk=R,
+                        q_strides=(R * R * 3 * C, inner * 3 * C, seq * 3 * C), k_strides=(R * R * 3 * C, inner * 3 * C, seq * 3 * C),
+                        v_strides=(R * R * 3 * C, inner * 3 * C, seq * 3 * C), o_strides=(R * R * C, inner * C, seq * C),
+                        key_len=None, scale=self.scale, out_split=u)
         ops.gemm_tc(u, ws[p + ".attn.out_proj.weight"], sd[p + ".attn.out_proj.bias"], residual=x, out=x)
         ops.layernorm(x, sd[p + ".ln_2.weight"], sd[p + ".ln_2.bias"], out_split=u)
         ops.gemm_tc(u, ws[p + ".mlp.c_fc.weight"], sd[p + ".mlp.c_fc.bias"], act=ACT_QUICKGELU, want=(), out_split=h)

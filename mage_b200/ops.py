@@ -29,8 +29,8 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-# Optional per-launch CUDA-event instrumentation of the GEMM-class kernels (bench.py's roofline leg):
-# when PROFILE is a list, gemm()/conv2d() append (kind, flops, start_event, end_event) around the launch.
+# Optional per-launch CUDA-event instrumentation (bench.py's roofline / breakdown leg): when PROFILE is a
+# list, every wrapper appends (kind, algorithmic flops or bytes, start_event, end_event) around its launch.
 PROFILE = None
 
 
@@ -112,8 +112,9 @@ def split(x: torch.Tensor, relu: bool = False, out: Optional[torch.Tensor] = Non
         rows, ldx = x.numel() // C, C
     if out is None:
         out = torch.empty(2, *x.shape, device=x.device, dtype=torch.float16)
-    check(_lib.lib().mage_split_f32(_p(x), ldx, _p(_f16(out)), rows * C, rows, C, int(relu), _p(flag(x.device)), _stream()),
-          "mage_split_f32")
+    with _Prof("split", 8.0 * rows * C):
+        check(_lib.lib().mage_split_f32(_p(x), ldx, _p(_f16(out)), rows * C, rows, C, int(relu), _p(flag(x.device)), _stream()),
+              "mage_split_f32")
     return out
 
 
@@ -124,8 +125,9 @@ def embedding_split(idx: torch.Tensor, table: torch.Tensor, out: Optional[torch.
     rows = idx.numel()
     if out is None:
         out = torch.empty(2, *idx.shape, C, device=table.device, dtype=torch.float16)
-    check(_lib.lib().mage_embedding_split(_p(idx), _p(_f16(table)), K * C, _p(_f16(out)), rows * C, rows, C, _stream()),
-          "mage_embedding_split")
+    with _Prof("embed", 8.0 * rows * C):
+        check(_lib.lib().mage_embedding_split(_p(idx), _p(_f16(table)), K * C, _p(_f16(out)), rows * C, rows, C, _stream()),
+              "mage_embedding_split")
     return out
 
 
@@ -228,22 +230,25 @@ def conv2d_first(x_nchw: torch.Tensor, w_t: torch.Tensor, bias: Optional[torch.T
     Hout = (H + 2 * pad - kh) // stride + 1
     Wout = (W + 2 * pad - kw) // stride + 1
     out = torch.empty(n, Hout, Wout, cout, device=x_nchw.device, dtype=torch.float32)
-    check(_lib.lib().mage_conv2d_first_f32(_p(_f32(x_nchw)), _p(_f32(w_t)), _p(bias), _p(out), n, Cin, H, W, Hout, Wout,
-                                           cout, kh, kw, stride, pad, act, _stream()), "mage_conv2d_first_f32")
+    with _Prof("conv_first", 4.0 * out.numel()):
+        check(_lib.lib().mage_conv2d_first_f32(_p(_f32(x_nchw)), _p(_f32(w_t)), _p(bias), _p(out), n, Cin, H, W, Hout, Wout,
+                                               cout, kh, kw, stride, pad, act, _stream()), "mage_conv2d_first_f32")
     return out
 
 
 def conv1x1_tanh_nchw(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, out: torch.Tensor, out_img_stride: int) -> None:
     """x NHWC [N,H,W,Cin] -> tanh(conv1x1(relu(x))) written planar into `out` (image stride in elements)."""
     n, H, W, Cin = x.shape
-    check(_lib.lib().mage_conv1x1_tanh_nchw_f32(_p(_f32(x)), _p(_f32(w)), _p(bias), _p(out), n, H * W, Cin, w.shape[0],
-                                                out_img_stride, _stream()), "mage_conv1x1_tanh_nchw_f32")
+    with _Prof("conv1x1_tanh", 4.0 * x.numel()):
+        check(_lib.lib().mage_conv1x1_tanh_nchw_f32(_p(_f32(x)), _p(_f32(w)), _p(bias), _p(out), n, H * W, Cin, w.shape[0],
+                                                    out_img_stride, _stream()), "mage_conv1x1_tanh_nchw_f32")
 
 
 def maxpool2x2(x: torch.Tensor) -> torch.Tensor:
     n, H, W, C = x.shape
     out = torch.empty(n, H // 2, W // 2, C, device=x.device, dtype=torch.float32)
-    check(_lib.lib().mage_maxpool2x2_nhwc_f32(_p(_f32(x)), _p(out), n, H, W, C, _stream()), "mage_maxpool2x2_nhwc_f32")
+    with _Prof("maxpool", 5.0 * x.numel()):
+        check(_lib.lib().mage_maxpool2x2_nhwc_f32(_p(_f32(x)), _p(out), n, H, W, C, _stream()), "mage_maxpool2x2_nhwc_f32")
     return out
 
 
@@ -255,8 +260,9 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     rows = x.numel() // C
     if out is None and out_split is None:
         out = torch.empty_like(x)
-    check(_lib.lib().mage_layernorm_f32(_p(_f32(x)), _p(gamma), _p(beta), _p(out), _p(out_split), rows * C, _p(flag(x.device)),
-                                        rows, C, eps, _stream()), "mage_layernorm_f32")
+    with _Prof("layernorm", 8.0 * x.numel()):
+        check(_lib.lib().mage_layernorm_f32(_p(_f32(x)), _p(gamma), _p(beta), _p(out), _p(out_split), rows * C, _p(flag(x.device)),
+                                            rows, C, eps, _stream()), "mage_layernorm_f32")
     return out if out_split is None else out_split
 
 
@@ -264,25 +270,37 @@ def mha(q, k, v, out, *, n_outer, n_inner, n_head, Sq, Sk, q_strides, k_strides,
         key_len: Optional[torch.Tensor] = None, scale: float, out_split: Optional[torch.Tensor] = None) -> None:
     """Strided SDPA core (head_dim 32).  *_strides = (outer, inner, seq) in elements; q/k/v/out may be
     views into one packed qkv buffer (pass the view: its data_ptr carries the column offset)."""
-    check(_lib.lib().mage_mha_f32(_p(q), _p(k), _p(v), _p(out), n_outer, n_inner, n_head, Sq, Sk, *q_strides, *k_strides,
-                                  *v_strides, *o_strides, _p(key_len), scale, _p(out_split),
-                                  out_split.numel() // 2 if out_split is not None else 0, _p(flag(q.device)), _stream()),
-          "mage_mha_f32")
+    with _Prof("mha", 0.0):
+        check(_lib.lib().mage_mha_f32(_p(q), _p(k), _p(v), _p(out), n_outer, n_inner, n_head, Sq, Sk, *q_strides, *k_strides,
+                                      *v_strides, *o_strides, _p(key_len), scale, _p(out_split),
+                                      out_split.numel() // 2 if out_split is not None else 0, _p(flag(q.device)), _stream()),
+              "mage_mha_f32")
+
+
+def axial_attn(qkv: torch.Tensor, out: Optional[torch.Tensor], *, B: int, R: int, n_head: int, axis: int, scale: float,
+               out_split: Optional[torch.Tensor] = None) -> None:
+    """H (axis=1) / W (axis=2) axial attention of one temporal position: qkv [B*R*R, 3C] -> out [B*R*R, C] and/or split."""
+    with _Prof("axial_attn", 4.0 * qkv.numel() + 4.0 * qkv.numel() / 3):
+        check(_lib.lib().mage_axial_attn_f32(_p(_f32(qkv)), _p(out), _p(out_split),
+                                             out_split.numel() // 2 if out_split is not None else 0, _p(flag(qkv.device)),
+                                             B, R, n_head, axis, scale, _stream()), "mage_axial_attn_f32")
 
 
 def temporal_attn_step(qkv: torch.Tensor, kcache: torch.Tensor, vcache: torch.Tensor, out: Optional[torch.Tensor], pos: int,
                        scale: float, out_split: Optional[torch.Tensor] = None) -> None:
     M = qkv.shape[0]
     Lmax = kcache.shape[1]
-    check(_lib.lib().mage_temporal_attn_step_f32(_p(_f32(qkv)), _p(kcache), _p(vcache), _p(out), _p(out_split),
-                                                 out_split.numel() // 2 if out_split is not None else 0, _p(flag(qkv.device)),
-                                                 M, pos, Lmax, scale, _stream()), "mage_temporal_attn_step_f32")
+    with _Prof("temporal_attn", 8.0 * M * (pos + 1) * kcache.shape[2]):
+        check(_lib.lib().mage_temporal_attn_step_f32(_p(_f32(qkv)), _p(kcache), _p(vcache), _p(out), _p(out_split),
+                                                     out_split.numel() // 2 if out_split is not None else 0, _p(flag(qkv.device)),
+                                                     M, pos, Lmax, scale, _stream()), "mage_temporal_attn_step_f32")
 
 
 def kv_append(qkv: torch.Tensor, kcache: torch.Tensor, vcache: torch.Tensor, pos: int) -> None:
     M, C3 = qkv.shape
-    check(_lib.lib().mage_kv_append_f32(_p(_f32(qkv)), _p(kcache), _p(vcache), M, C3 // 3, pos, kcache.shape[1], _stream()),
-          "mage_kv_append_f32")
+    with _Prof("kv_append", 0.0):
+        check(_lib.lib().mage_kv_append_f32(_p(_f32(qkv)), _p(kcache), _p(vcache), M, C3 // 3, pos, kcache.shape[1], _stream()),
+              "mage_kv_append_f32")
 
 
 def vq_argmin(z: torch.Tensor, codebook: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -292,8 +310,9 @@ def vq_argmin(z: torch.Tensor, codebook: torch.Tensor, out: Optional[torch.Tenso
     if out is None:
         out = torch.empty(N, device=z.device, dtype=torch.int64)
     scratch = torch.empty(K, device=z.device, dtype=torch.float32)
-    check(_lib.lib().mage_vq_argmin_f32(_p(_f32(z)), _p(_f32(codebook)), _p(scratch), _p(out), N, D, K, _stream()),
-          "mage_vq_argmin_f32")
+    with _Prof("vq_argmin", 4.0 * N * D):
+        check(_lib.lib().mage_vq_argmin_f32(_p(_f32(z)), _p(_f32(codebook)), _p(scratch), _p(out), N, D, K, _stream()),
+              "mage_vq_argmin_f32")
     return out
 
 
@@ -301,7 +320,8 @@ def argmax_rows(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Te
     rows, N = x.shape
     if out is None:
         out = torch.empty(rows, device=x.device, dtype=torch.int64)
-    check(_lib.lib().mage_argmax_rows_f32(_p(x), x.stride(0), _p(out), rows, N, _stream()), "mage_argmax_rows_f32")
+    with _Prof("argmax", 4.0 * rows * N):
+        check(_lib.lib().mage_argmax_rows_f32(_p(x), x.stride(0), _p(out), rows, N, _stream()), "mage_argmax_rows_f32")
     return out
 
 
@@ -310,7 +330,8 @@ def embedding(idx: torch.Tensor, table: torch.Tensor, out: Optional[torch.Tensor
     rows, C = idx.numel(), table.shape[1]
     if out is None:
         out = torch.empty(*idx.shape, C, device=table.device, dtype=torch.float32)
-    check(_lib.lib().mage_embedding_f32(_p(idx), _p(_f32(table)), _p(out), rows, C, _stream()), "mage_embedding_f32")
+    with _Prof("embed", 8.0 * rows * C):
+        check(_lib.lib().mage_embedding_f32(_p(idx), _p(_f32(table)), _p(out), rows, C, _stream()), "mage_embedding_f32")
     return out
 
 
@@ -319,27 +340,31 @@ def text_embed(text: torch.Tensor, tok_emb, pos_emb, gamma, beta, pad_idx: int, 
     C = tok_emb.shape[1]
     x = torch.empty(B, T, C, device=tok_emb.device, dtype=torch.float32)
     key_len = torch.empty(B, device=tok_emb.device, dtype=torch.int32)
-    check(_lib.lib().mage_text_embed_f32(_p(text), _p(tok_emb), _p(pos_emb), _p(gamma), _p(beta), _p(x), _p(key_len), B, T, C,
-                                         pad_idx, eps, _stream()), "mage_text_embed_f32")
+    with _Prof("misc", 0.0):
+        check(_lib.lib().mage_text_embed_f32(_p(text), _p(tok_emb), _p(pos_emb), _p(gamma), _p(beta), _p(x), _p(key_len), B, T, C,
+                                             pad_idx, eps, _stream()), "mage_text_embed_f32")
     return x, key_len
 
 
 def adain(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
     n, H, W, C = x.shape
     out = torch.empty_like(x)
-    check(_lib.lib().mage_adain_nhwc_f32(_p(_f32(x)), _p(_f32(gamma)), _p(_f32(beta)), _p(out), n, H * W, C, eps, _stream()),
-          "mage_adain_nhwc_f32")
+    with _Prof("misc", 0.0):
+        check(_lib.lib().mage_adain_nhwc_f32(_p(_f32(x)), _p(_f32(gamma)), _p(_f32(beta)), _p(out), n, H * W, C, eps, _stream()),
+              "mage_adain_nhwc_f32")
     return out
 
 
 def add_scaled_vec(x: torch.Tensor, s: torch.Tensor, vec: torch.Tensor) -> None:
     n, C = x.shape[0], x.shape[-1]
-    check(_lib.lib().mage_add_scaled_vec_f32(_p(_f32(x)), _p(s), _p(vec), n, x.numel() // (n * C), C, _stream()),
-          "mage_add_scaled_vec_f32")
+    with _Prof("misc", 0.0):
+        check(_lib.lib().mage_add_scaled_vec_f32(_p(_f32(x)), _p(s), _p(vec), n, x.numel() // (n * C), C, _stream()),
+              "mage_add_scaled_vec_f32")
 
 
 def nchw_to_nhwc(x: torch.Tensor) -> torch.Tensor:
     n, C, H, W = x.shape
     out = torch.empty(n, H, W, C, device=x.device, dtype=torch.float32)
-    check(_lib.lib().mage_nchw_to_nhwc_f32(_p(_f32(x)), _p(out), n, C, H * W, _stream()), "mage_nchw_to_nhwc_f32")
+    with _Prof("misc", 0.0):
+        check(_lib.lib().mage_nchw_to_nhwc_f32(_p(_f32(x)), _p(out), n, C, H * W, _stream()), "mage_nchw_to_nhwc_f32")
     return out

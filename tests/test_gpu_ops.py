@@ -233,6 +233,28 @@ def test_mha_axial_spatial(kind):
     _close(out, want, 1e-5, 1e-5)
 
 
+@pytest.mark.parametrize("kind", [1, 2])
+def test_axial_attention_tile_kernel(kind):
+    """The specialised one-warp-per-(line, head) axial kernel: fp32 and split outputs, vs torch SDPA in fp64."""
+    ops = _ops()
+    B, R, C, H = 5, 16, 512, 16
+    qkv = _rand(B * R * R, 3 * C, seed=10 + kind)
+    d = qkv.to(DEV)
+    out = torch.empty(B * R * R, C, device=DEV)
+    sp = torch.empty(2, B * R * R, C, device=DEV, dtype=torch.float16)
+    ops.axial_attn(d, out, B=B, R=R, n_head=H, axis=kind, scale=1 / math.sqrt(32), out_split=sp)
+    t = qkv.view(B, R, R, 3, H, 32)
+    ax = 1 if kind == 1 else 2
+    q, k, v = [t[:, :, :, i].movedim(ax, -2) for i in range(3)]
+    want = _sdpa(q, k, v).movedim(-2, ax).reshape(B * R * R, C)
+    _close(out, want, 1e-5, 1e-5)
+    rec = sp.cpu().double()
+    _close(rec[0] + rec[1] / 2048.0, want, 1e-5, 1e-5)
+    only_split = torch.empty_like(sp)
+    ops.axial_attn(d, None, B=B, R=R, n_head=H, axis=kind, scale=1 / math.sqrt(32), out_split=only_split)
+    assert torch.equal(only_split, sp)
+
+
 @pytest.mark.parametrize("impl", ["generic", "tma"])
 def test_temporal_attention_with_kv_cache(impl):
     ops = _ops()
