@@ -1,0 +1,142 @@
+#!/usr/bin/env python
+"""`python main_mage.py --split test --test_model <dir>/model_best.pth` -- the reference's sampling entry
+(/root/reference/main_mage.py:29-56 flags, :201-248 sampling(), :276-297 dispatch) on the B200 path.
+
+Kept from the reference: every flag; the yaml saved next to the checkpoint (`<dir>/config.yaml`) is what gets
+loaded (main_mage.py:203); `instantiate_from_config(configs.model)`; checkpoint `{'state_dict': ...}` with an
+optional DDP `module.` prefix (:218-223); a missing checkpoint file only prints a notice (:227-228);
+`model.eval()`, `torch.no_grad()`, `autoregressive_generate(batch)` then `clamp_(-1, 1)` per sample (:240-242).
+
+Additive flags (the reference hard-wires batch_size=1 and needs the datasets on disk):
+  --batch-size B     prompts per generate call (per GPU)
+  --synthetic N      N seeded synthetic prompts with the reference's batch-dict contract instead of `configs.data`
+  --out DIR          write each clip as <video_id>.npy (the reference's GIF writer is commented out, :244-245)
+  --config           used only when <dir>/config.yaml does not exist
+Under torchrun (WORLD_SIZE > 1) the prompt list is cut into contiguous per-rank slices (mage_b200/shard.py);
+there is no collective on the data path.  `--split train` is the stage-2 training driver, outside this path.
+"""
+import argparse
+import os
+import sys
+import time
+from collections import OrderedDict
+
+import torch
+from torch.utils.data import DataLoader, Subset
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from mage_b200 import shard  # noqa: E402
+from mage_b200.config import load_yaml  # noqa: E402
+from utils.util import instantiate_from_config  # noqa: E402
+
+parser = argparse.ArgumentParser()
+parser.add_argument('--config', type=str, default='config/mage_caterv2_L32.yaml')
+parser.add_argument('--split', type=str, default='test')
+parser.add_argument('--checkpoint-path', type=str, default='../results//')
+parser.add_argument('--device', type=str, default='cuda')
+parser.add_argument("--num-workers", type=int, default=4)
+parser.add_argument('--world-size', default=-1, type=int, help='number of nodes for distributed training')
+parser.add_argument('--rank', default=-1, type=int, help='node rank for distributed training')
+parser.add_argument('--dist-url', default='tcp://127.0.0.1:65532', type=str, help='url used to set up distributed training')
+parser.add_argument('--dist-backend', default='nccl', type=str, help='distributed backend')
+parser.add_argument('--seed', default=None, type=int, help='seed for initializing training. ')
+parser.add_argument('--gpu', default=0, type=int, help='GPU id to use.')
+parser.add_argument('--multiprocessing-distributed', action='store_true')
+parser.add_argument("--n_samples", type=int, default=1, help="how many samples to produce for each instance")
+parser.add_argument("--test_model", type=str, default='./models/MAGE/catergenv2/model_best.pth')
+# additive
+parser.add_argument("--batch-size", type=int, default=1, help="prompts per generate call (reference: 1)")
+parser.add_argument("--synthetic", type=int, default=0, help="use N seeded synthetic prompts instead of configs.data")
+parser.add_argument("--out", type=str, default=None, help="directory for the generated clips (.npy)")
+
+
+def load_configs(opt) -> dict:
+    beside = os.path.join(os.path.dirname(opt.test_model), "config.yaml")
+    return load_yaml(beside if os.path.isfile(beside) else opt.config)
+
+
+def load_checkpoint(model, opt) -> bool:
+    """main_mage.py:210-228."""
+    test_model = opt.test_model
+    if not os.path.isfile(test_model):
+        print("=> no checkpoint found at '{}'".format(test_model))
+        return False
+    loc = None if opt.gpu is None else 'cuda:{}'.format(opt.gpu) if torch.cuda.is_available() else 'cpu'
+    checkpoint = torch.load(test_model, map_location=loc)
+    sd = checkpoint['state_dict']
+    if list(sd.keys())[0].startswith('module.'):
+        sd = OrderedDict((k[7:], v) for k, v in sd.items())
+    model.load_state_dict(sd)
+    print("=> loaded checkpoint '{}'".format(test_model))
+    return True
+
+
+def sampling(opt):
+    configs = load_configs(opt)
+    rank, world, local_rank = shard.env_world()
+    if world > 1:
+        opt.gpu = local_rank
+    if torch.cuda.is_available():
+        torch.cuda.set_device(opt.gpu or 0)
+    device = torch.device(opt.device if opt.device != 'cuda' else 'cuda:{}'.format(opt.gpu or 0))
+    if world > 1:
+        shard.init_distributed(opt.dist_backend, device if device.type == 'cuda' else None)
+
+    if opt.synthetic > 0:
+        from dataload import SyntheticCaptionVideos
+        test_dataset = SyntheticCaptionVideos(configs['model']['params'], opt.synthetic, seed=1234 if opt.seed is None else opt.seed)
+    else:
+        test_dataset = instantiate_from_config(configs['data'], {'split': 'test'})
+    lo, hi = shard.shard_bounds(len(test_dataset), world, rank)
+    from dataload import collate_fn
+    test_dataloader = DataLoader(Subset(test_dataset, range(lo, hi)), batch_size=opt.batch_size, shuffle=False, num_workers=0,
+                                 pin_memory=torch.cuda.is_available(), collate_fn=collate_fn)
+
+    model = instantiate_from_config(configs['model'])
+    model = model.to(device)
+    load_checkpoint(model, opt)
+    model.eval()
+    if opt.out:
+        os.makedirs(opt.out, exist_ok=True)
+    frames = 0
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        idx = 0
+        for batch in test_dataloader:
+            video_ids = batch.pop('video_id', None)
+            for k in batch.keys():
+                batch[k] = batch[k].to(device)
+            for _ in range(opt.n_samples):
+                generated = model.autoregressive_generate(batch)
+                generated.clamp_(min=-1, max=1)
+                frames += generated.shape[0] * (generated.shape[1] - 1)
+            if opt.out:
+                import numpy as np
+                for b in range(generated.shape[0]):
+                    name = video_ids[b] if video_ids else f"r{rank}_{idx}_{b}"
+                    np.save(os.path.join(opt.out, name + ".npy"), generated[b].cpu().numpy())
+            print(idx)
+            idx += 1
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    secs = time.perf_counter() - t0
+    if world > 1:
+        secs = shard.max_over_ranks(secs, device)
+        frames = shard.sum_over_ranks(frames, device)
+    if rank == 0:
+        print(f"generated {int(frames)} frames in {secs:.2f}s on {world} GPU(s)")
+    return frames
+
+
+if __name__ == "__main__":
+    opt = parser.parse_args()
+    if opt.split == 'test':
+        sampling(opt)
+    elif opt.split == 'train':
+        raise SystemExit("--split train (stage-2 training, main_mage.py:58-199) is outside the sampling path this repo implements "
+                         "(SURVEY.md §8f N2)")
+    else:
+        raise SystemExit(f"unknown --split {opt.split!r}")
