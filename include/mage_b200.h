@@ -41,7 +41,7 @@ extern "C" {
 #define MAGE_RES_RELU 0x200     /* read the residual through a ReLU (in-place ReLU skip of ResBlock, vqvae_model.py:114-124) */
 
 /* Library info / bookkeeping */
-int mage_abi_version(void); /* 2 */
+int mage_abi_version(void); /* 3 */
 /* Number of kernels launched through this library by the calling process so far. */
 int64_t mage_launch_count(void);
 
@@ -82,6 +82,12 @@ int mage_conv2d_nhwc_f32(const float* in, const float* w, const float* bias, con
  * the fp16 range is split -- callers check it instead of trusting a saturated result.
  * --------------------------------------------------------------------------------------------- */
 
+/* Tuning / test hook for the tile selection of mage_gemm_tc / mage_conv2d_tc (process-wide, not thread-safe):
+ * bn in {0 = automatic, 64, 128, 256} forces the N tile; pair in {-1 automatic, 0 single-CTA tiles only,
+ * 1 CTA-pair (tcgen05 cta_group::2, 256-row tiles) whenever the row-tile count is even}.  Results do not depend on it
+ * beyond fp32 summation order (identical here: the k order is the same for every tile shape). */
+int mage_tc_tuning(int bn, int pair);
+
 /* out(split)[r, :] = split(relu?(x[r, :])); x row stride ldx (elements), C % 4 == 0. */
 int mage_split_f32(const float* x, int64_t ldx, void* out, int64_t plane, int rows, int C, int relu, int* flag,
                    void* stream);
@@ -111,6 +117,15 @@ int mage_conv2d_tc(const void* in, int64_t in_plane, const void* w, int64_t w_pl
                    int n_img, int Hin, int Win, int Cin, int Hout, int Wout, int Cout, int KH, int KW, int pad_y,
                    int pad_x, int res_mode, int act, int out_sy, int out_sx, int out_oy, int out_ox, int Hfull,
                    int Wfull, int64_t out_img_stride, int* flag, void* stream);
+
+/* mage_conv2d_tc fused with the decoder's pixel head (vqvae_model.py:210-213: DecoderBlock conv -> ReLU -> Conv2d(dim,C,1) ->
+ * Tanh): the conv result x[row, 0..255] (+ bias + residual, never written to memory) is reduced in the epilogue to
+ *   head_out[img, c, y, x] = tanh(head_b[c] + sum_n relu(x[row, n]) * head_w[c, n]),   c < head_cout <= 3,
+ * planar output, image stride head_img_stride elements.  Cout must be 256 (one N tile holds a whole row). */
+int mage_conv2d_tc_pixel_head(const void* in, int64_t in_plane, const void* w, int64_t w_plane, const float* bias,
+                              const float* residual, int n_img, int Hin, int Win, int Cin, int Hout, int Wout, int Cout,
+                              int KH, int KW, int pad_y, int pad_x, int res_mode, const float* head_w, const float* head_b,
+                              int head_cout, float* head_out, int64_t head_img_stride, int* flag, void* stream);
 
 /* First-layer convolution from a planar NCHW image with a tiny channel count (Cin <= 4):
  * in [N,Cin,H,W], w_t [Cin*KH*KW][Cout] (transposed), out NHWC [N,Hout,Wout,Cout], optional ReLU.

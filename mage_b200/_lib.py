@@ -23,11 +23,13 @@ SIGNATURES = {
     "mage_launch_count": [],
     "mage_gemm_f32": [_c_f, _i64, _c_f, _i64, _c_f, _c_f, _i64, _i, _c_f, _i64, _i, _i, _i, _i, _i, _c_f],
     "mage_conv2d_nhwc_f32": [_c_f] * 5 + [_i] * 22 + [_i64, _c_f],
+    "mage_tc_tuning": [_i, _i],
     "mage_split_f32": [_c_f, _i64, _c_f, _i64, _i, _i, _i, _c_f, _c_f],
     "mage_embedding_split": [_c_f, _c_f, _i64, _c_f, _i64, _i, _i, _c_f],
     "mage_gemm_tc": [_c_f, _i64, _i64, _c_f, _i64, _i64, _c_f, _c_f, _i64, _i, _c_f, _c_f, _c_f, _i64, _i64, _i, _i, _i, _i,
                      _c_f, _c_f],
     "mage_conv2d_tc": [_c_f, _i64, _c_f, _i64, _c_f, _c_f, _c_f, _c_f, _c_f, _i64] + [_i] * 19 + [_i64, _c_f, _c_f],
+    "mage_conv2d_tc_pixel_head": [_c_f, _i64, _c_f, _i64, _c_f, _c_f] + [_i] * 12 + [_c_f, _c_f, _i, _c_f, _i64, _c_f, _c_f],
     "mage_conv2d_first_f32": [_c_f] * 4 + [_i] * 12 + [_c_f],
     "mage_conv1x1_tanh_nchw_f32": [_c_f] * 4 + [_i] * 4 + [_i64, _c_f],
     "mage_maxpool2x2_nhwc_f32": [_c_f, _c_f, _i, _i, _i, _i, _c_f],

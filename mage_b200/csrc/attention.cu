@@ -249,8 +249,8 @@ __global__ void __launch_bounds__(256) temporal_attn_kernel(const float* __restr
                                                             __half* __restrict__ split, int64_t split_plane, int* flag,
                                                             int pos, int Lmax, float scale) {
   extern __shared__ __align__(128) float smem[];
-  float* Ks = smem;                       // [Lmax][256]
-  float* Vs = smem + (size_t)Lmax * TA_HALF;
+  float* Ks = smem;                       // [pos+1][256]: sized to the live prefix so early steps fit more CTAs per SM
+  float* Vs = smem + (size_t)(pos + 1) * TA_HALF;
   __shared__ __align__(8) uint64_t bars[2];
   __shared__ __align__(16) float qs[TA_HALF];
 
@@ -359,12 +359,13 @@ extern "C" int mage_temporal_attn_step_f32(const float* qkv, float* kcache, floa
                                            void* stream) {
   MAGE_CHECK_ARG(M > 0 && pos >= 0 && pos < Lmax && Lmax <= 64);
   MAGE_CHECK_ARG(aligned16(qkv) && aligned16(kcache) && aligned16(vcache) && aligned16(out) && (out || out_split));
-  const size_t smem = (size_t)2 * Lmax * TA_HALF * sizeof(float);
+  const size_t smem = (size_t)2 * (pos + 1) * TA_HALF * sizeof(float);
+  const size_t smem_max = (size_t)2 * Lmax * TA_HALF * sizeof(float);
   static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(temporal_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (smem_max > 48 * 1024 && smem_max > configured) {
+    cudaError_t e = cudaFuncSetAttribute(temporal_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
     if (e != cudaSuccess) return (int)e;
-    configured = smem;
+    configured = smem_max;
   }
   temporal_attn_kernel<<<(unsigned)M * 2, 256, smem, as_stream(stream)>>>(qkv, kcache, vcache, out, reinterpret_cast<__half*>(out_split),
                                                                           split_plane, flag, pos, Lmax, scale);

@@ -14,6 +14,12 @@
 //            residual -> coalesced fp32 and/or split stores (the next consumer's operand format)
 // For a convolution the A tile is an NHWC patch: the box is [64 ch, Wb, Hb, 1 image, 2 planes] at
 // the tap's (dy,dx) offset and TMA's out-of-bounds zero fill is the padding, so im2col never exists.
+//
+// CG = 2 (CTA pair, cluster 2x1x1, tcgen05 cta_group::2): the two CTAs of a TPC share one 256 x BN tile.
+// Each loads its own 128 A rows and HALF of the W tile (BN/2 rows); the leader's single thread issues
+// M = 256 MMAs that read B from both CTAs' shared memory and write each CTA's own TMEM.  Operand bytes
+// per MMA drop by 25 % (BN = 128) to 50 % (BN = 256) -- the 1-CTA kernel is bound by L2->SM operand
+// traffic (ncu: ~11 TB/s xbar2sm, tensor pipe < 40 %), not by the tensor pipe.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -43,12 +49,19 @@ struct TcParams {
   // convolution geometry (conv != 0)
   int conv, Hout, Wout, Wb, Hb, KW, cin_blocks, cin, pad_y, pad_x;
   int res_mode, out_sy, out_sx, out_oy, out_ox, Hfull, Wfull;
+  // fused pixel head (last f8 decoder layer): head_out[img, c, pix] = tanh(head_b[c] + sum_n relu(result[row, n]) * head_w[c, n])
+  const float* head_w;
+  const float* head_b;
+  float* head_out;
+  int64_t head_img_stride;
+  int head_cout;
 };
 
-template <int BN>
+template <int BN, int CG>
 struct Cfg {
-  static constexpr int A_BYTES = 2 * BM * BK * 2;   // hi + lo planes
-  static constexpr int W_BYTES = 2 * BN * BK * 2;
+  static constexpr int A_BYTES = 2 * BM * BK * 2;   // hi + lo planes of this CTA's 128 rows
+  static constexpr int W_ROWS = BN / CG;            // W rows this CTA loads (the pair splits the N tile)
+  static constexpr int W_BYTES = 2 * W_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
   static constexpr int STAGING_BYTES = 8 * 32 * 32 * 4;   // one XOR-swizzled 32x32 fp32 transpose tile per epilogue warp
   static constexpr int STAGES_RAW = (SMEM_BUDGET - 1024 - STAGING_BYTES - 256) / STAGE_BYTES;
@@ -71,9 +84,11 @@ __device__ __forceinline__ float act_fn(float x) {
 // Epilogue of one CTA: 8 warps, two per TMEM lane quadrant (warp % 4), the pair splitting the 32-column chunks.
 // Per chunk: tcgen05.ld main + corr -> v = main + corr*2^-11 (row-per-thread layout) -> XOR-swizzled smem
 // transpose -> bias, activation, residual (row-contiguous layout) -> coalesced fp32 and/or split stores.
-template <int BN, int ACT>
+template <int BN, int CG, int ACT, bool HEAD = false>
 __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_base, float* staging, uint32_t tfull0, uint32_t tempty0) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CG>;
+  const int cta_rank = CG == 2 ? (int)cluster_ctarank() : 0;
+  const int unit = blockIdx.x / CG, n_units = gridDim.x / CG;   // a unit = the CTA (pair) that owns a tile
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int quad = warp & 3, half = (warp - 2) >> 2;
   float* stg = staging + (warp - 2) * 32 * 32;
@@ -87,11 +102,11 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
   __half* const split_relu = p.split_relu;
   const int64_t split_plane = p.split_plane, split_relu_plane = p.split_relu_plane;
   const int n_tiles = p.n_tiles, M = p.M;
-  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int num_tiles = (p.m_tiles / CG) * p.n_tiles;
   int tcount = 0;
   bool overflow = false;
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
-    const int mt = tile / n_tiles, nt = tile - mt * n_tiles;
+  for (int tile = unit; tile < num_tiles; tile += n_units, ++tcount) {
+    const int mt = (tile / n_tiles) * CG + cta_rank, nt = tile % n_tiles;
     const int acc = tcount % C::ACC_STAGES;
     const uint32_t aph = (tcount / C::ACC_STAGES) & 1;
     // output / residual row offsets of the 8 rows this lane stores (rows quad*32 + i*4 + rq)
@@ -117,6 +132,11 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
         out_off[i] = (int64_t)m * p.ldc;
         if (res) res_off[i] = (int64_t)(p.res_mod > 0 ? m % p.res_mod : m) * p.ldr;
       }
+    }
+    float hacc[HEAD ? 8 : 1][3];
+    if (HEAD) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) hacc[i][0] = hacc[i][1] = hacc[i][2] = 0.f;
     }
     mbar_wait(tfull0 + 8u * acc, aph);
     tc_fence_after();
@@ -147,6 +167,12 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
         *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = v;
       }
       __syncwarp();
+      float4 hw[3];
+      if (HEAD) {
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch)
+          hw[ch] = ch < p.head_cout ? __ldg(reinterpret_cast<const float4*>(p.head_w + (int64_t)ch * p.N + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         if (out_off[i] < 0) continue;
@@ -158,6 +184,12 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
         if (res_relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
         v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
         if (ACT != MAGE_ACT_NONE && post) { v.x = act_fn<ACT>(v.x); v.y = act_fn<ACT>(v.y); v.z = act_fn<ACT>(v.z); v.w = act_fn<ACT>(v.w); }
+        if (HEAD) {
+          const float4 rl = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch)
+            hacc[i][ch] += (rl.x * hw[ch].x + rl.y * hw[ch].y) + (rl.z * hw[ch].z + rl.w * hw[ch].w);
+        }
         const int64_t o = out_off[i] + n;
         if (out) *reinterpret_cast<float4*>(out + o) = v;
         if (split) {
@@ -178,15 +210,55 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
     // accumulator drained: hand the TMEM stage back to the MMA thread
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(tempty0 + 8u * acc);
+    if (lane == 0) {
+      if (CG == 2) mbar_arrive_cluster(mapa_u32(tempty0 + 8u * acc, 0));   // the leader's MMA thread waits for both CTAs
+      else mbar_arrive(tempty0 + 8u * acc);
+    }
+    if (HEAD) {
+      // per-row sums over this warp's columns: reduce the 8 lanes (cq) that share a row, then add the partner warp's half
+      // of the columns through its staging tile (warps 2+quad and 6+quad pair up on named barrier 1+quad)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+          float x = hacc[i][ch];
+          x += __shfl_xor_sync(0xffffffffu, x, 1);
+          x += __shfl_xor_sync(0xffffffffu, x, 2);
+          x += __shfl_xor_sync(0xffffffffu, x, 4);
+          hacc[i][ch] = x;
+        }
+        if (cq == 0) *reinterpret_cast<float4*>(stg + (i * 4 + rq) * 4) = make_float4(hacc[i][0], hacc[i][1], hacc[i][2], 0.f);
+      }
+      __syncwarp();
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+      if (half == 0) {
+        const float4 a = *reinterpret_cast<const float4*>(stg + lane * 4);
+        const float4 b = *reinterpret_cast<const float4*>(stg + 4 * 32 * 32 + lane * 4);   // warp + 4's tile
+        const int r = quad * 32 + lane, m = mt * BM + r;
+        if (m < M) {
+          const int tiles_x = p.Wout / p.Wb, tiles_y = p.Hout / p.Hb;
+          const int img = mt / (tiles_x * tiles_y), rr = mt - img * tiles_x * tiles_y;
+          const int ty = rr / tiles_x, tx = rr - ty * tiles_x;
+          const int oy = ty * p.Hb + r / p.Wb, ox = tx * p.Wb + r % p.Wb;
+          const int64_t pix = (int64_t)(oy * p.out_sy + p.out_oy) * p.Wfull + (ox * p.out_sx + p.out_ox);
+          const int64_t plane = (int64_t)p.Hfull * p.Wfull;
+          float* dst = p.head_out + (int64_t)img * p.head_img_stride + pix;
+          const float sum[3] = {a.x + b.x, a.y + b.y, a.z + b.z};
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch)
+            if (ch < p.head_cout) dst[ch * plane] = tanhf(sum[ch] + __ldg(p.head_b + ch));
+        }
+      }
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");   // the partner may reuse its staging tile
+    }
   }
   if (overflow && p.flag) atomicOr(p.flag, 1);
 }
 
-template <int BN>
+template <int BN, int CG>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, const TcParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -200,7 +272,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                                                                       8 * (2 * C::STAGES + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int cta_rank = CG == 2 ? (int)cluster_ctarank() : 0;
+  const int unit = blockIdx.x / CG, n_units = gridDim.x / CG;
+  const int num_tiles = (p.m_tiles / CG) * p.n_tiles;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
@@ -211,22 +285,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 8);
+      mbar_init(tempty_bar(a), 8 * CG);
     }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), C::TMEM_COLS);
+  if (warp == 1) {
+    if (CG == 2) tmem_alloc_2sm(smem_u32(const_cast<uint32_t*>(tmem_slot)), C::TMEM_COLS);
+    else tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), C::TMEM_COLS);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();   // the peer's barriers are initialised before anything is signalled remotely
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------ TMA producer (every CTA loads its A rows + its W rows)
     if (lane == 0) {
       int itg = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+      for (int tile = unit; tile < num_tiles; tile += n_units) {
+        const int mt = (tile / p.n_tiles) * CG + cta_rank, nt = tile % p.n_tiles;
         int c1 = mt * BM, c2 = 0, c3 = 0;
         if (p.conv) {
           const int tiles_x = p.Wout / p.Wb, tiles_y = p.Hout / p.Hb;
@@ -236,30 +314,39 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           c2 = ty * p.Hb - p.pad_y;
           c3 = img;
         }
+        const int w_row = nt * BN + cta_rank * C::W_ROWS;
         for (int it = 0; it < p.k_iters; ++it, ++itg) {
           const int s = itg % C::STAGES;
           const uint32_t ph = (itg / C::STAGES) & 1;
           mbar_wait(empty_bar(s), ph ^ 1);
-          mbar_expect_tx(full_bar(s), C::STAGE_BYTES);
           const uint32_t sa = base + s * C::STAGE_BYTES;
+          int a0 = it * BK, a1 = c1, a2 = c2;
           if (p.conv) {
             const int tap = it / p.cin_blocks, cb = it - tap * p.cin_blocks;
             const int ky = tap / p.KW, kx = tap - ky * p.KW;
-            tma_load_5d(sa, &mapA, full_bar(s), cb * BK, c1 + kx, c2 + ky, c3, 0);
-          } else {
-            tma_load_5d(sa, &mapA, full_bar(s), it * BK, c1, 0, 0, 0);
+            a0 = cb * BK; a1 = c1 + kx; a2 = c2 + ky;
           }
-          tma_load_3d(sa + C::A_BYTES, &mapW, full_bar(s), it * BK, nt * BN, 0);
+          if (CG == 2) {
+            // both CTAs' bytes land on the LEADER's full barrier: the MMA thread there consumes both halves
+            const uint32_t fb = mapa_u32(full_bar(s), 0);
+            if (cta_rank == 0) mbar_expect_tx(full_bar(s), 2 * C::STAGE_BYTES);
+            tma_load_5d_2sm(sa, &mapA, fb, a0, a1, a2, c3, 0);
+            tma_load_3d_2sm(sa + C::A_BYTES, &mapW, fb, it * BK, w_row, 0);
+          } else {
+            mbar_expect_tx(full_bar(s), C::STAGE_BYTES);
+            tma_load_5d(sa, &mapA, full_bar(s), a0, a1, a2, c3, 0);
+            tma_load_3d(sa + C::A_BYTES, &mapW, full_bar(s), it * BK, w_row, 0);
+          }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(BN);
+    // ------------------------------------------------------------ MMA issuer (the leader CTA's single thread)
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BN, BM * CG);
       int itg = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+      for (int tile = unit; tile < num_tiles; tile += n_units, ++tcount) {
         const int acc = tcount % C::ACC_STAGES;
         const uint32_t aph = (tcount / C::ACC_STAGES) & 1;
         mbar_wait(tempty_bar(acc), aph ^ 1);
@@ -272,37 +359,50 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           tc_fence_after();
           const uint32_t sa = base + s * C::STAGE_BYTES;
           const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + BM * BK * 2);
-          const uint64_t w_hi = umma_desc_sw128(sa + C::A_BYTES), w_lo = umma_desc_sw128(sa + C::A_BYTES + BN * BK * 2);
+          const uint64_t w_hi = umma_desc_sw128(sa + C::A_BYTES), w_lo = umma_desc_sw128(sa + C::A_BYTES + C::W_ROWS * BK * 2);
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k) {
             const uint64_t adv = (uint64_t)((k * UK * 2) >> 4);  // +32 B per k-step inside the swizzle row
             const uint32_t accum = (it > 0 || k > 0) ? 1u : 0u;
-            umma_f16(d_corr, a_lo + adv, w_hi + adv, idesc, accum);
-            umma_f16(d_corr, a_hi + adv, w_lo + adv, idesc, 1u);
-            umma_f16(d_main, a_hi + adv, w_hi + adv, idesc, accum);
+            if (CG == 2) {
+              umma_f16_2sm(d_corr, a_lo + adv, w_hi + adv, idesc, accum);
+              umma_f16_2sm(d_corr, a_hi + adv, w_lo + adv, idesc, 1u);
+              umma_f16_2sm(d_main, a_hi + adv, w_hi + adv, idesc, accum);
+            } else {
+              umma_f16(d_corr, a_lo + adv, w_hi + adv, idesc, accum);
+              umma_f16(d_corr, a_hi + adv, w_lo + adv, idesc, 1u);
+              umma_f16(d_main, a_hi + adv, w_hi + adv, idesc, accum);
+            }
           }
-          umma_commit(empty_bar(s));
+          if (CG == 2) umma_commit_2sm(empty_bar(s), 3);   // frees the stage in both CTAs
+          else umma_commit(empty_bar(s));
         }
-        umma_commit(tfull_bar(acc));
+        if (CG == 2) umma_commit_2sm(tfull_bar(acc), 3);   // both CTAs' epilogues drain their own TMEM
+        else umma_commit(tfull_bar(acc));
       }
     }
     __syncwarp();
   } else {
     // ------------------------------------------------------------ epilogue warps
+    if (BN == 256 && p.head_w) {
+      if constexpr (BN == 256) epilogue_loop<BN, CG, MAGE_ACT_NONE, true>(p, tmem_base, staging, tfull_bar(0), tempty_bar(0));
+    } else
     switch (p.act & 0xff) {
-      case MAGE_ACT_NONE: epilogue_loop<BN, MAGE_ACT_NONE>(p, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
-      case MAGE_ACT_RELU: epilogue_loop<BN, MAGE_ACT_RELU>(p, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
-      case MAGE_ACT_QUICKGELU: epilogue_loop<BN, MAGE_ACT_QUICKGELU>(p, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
-      case MAGE_ACT_GELU: epilogue_loop<BN, MAGE_ACT_GELU>(p, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
-      default: epilogue_loop<BN, MAGE_ACT_TANH>(p, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
+      case MAGE_ACT_NONE: epilogue_loop<BN, CG, MAGE_ACT_NONE>(p, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
+      case MAGE_ACT_RELU: epilogue_loop<BN, CG, MAGE_ACT_RELU>(p, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
+      case MAGE_ACT_QUICKGELU: epilogue_loop<BN, CG, MAGE_ACT_QUICKGELU>(p, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
+      case MAGE_ACT_GELU: epilogue_loop<BN, CG, MAGE_ACT_GELU>(p, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
+      default: epilogue_loop<BN, CG, MAGE_ACT_TANH>(p, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();   // no CTA of the pair leaves while the other may still signal its barriers / read its smem
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (CG == 2) tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
+    else tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -372,50 +472,106 @@ int make_map(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* dims
   return r == CUDA_SUCCESS ? 0 : MAGE_EINVAL;
 }
 
-template <int BN>
+template <int BN, int CG>
 int launch_tc(const CUtensorMap& mapA, const CUtensorMap& mapW, const TcParams& p, cudaStream_t st) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CG>;
   static bool configured = false;
+  static int max_units = 0;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
+    max_units = num_sms() / CG;
+    if (CG == 2) {
+      // how many CTA pairs can be co-resident (1 CTA per SM): GPCs with an odd SM count leave one SM unpaired
+      cudaLaunchConfig_t q{};
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      q.gridDim = dim3(num_sms() & ~1); q.blockDim = dim3(NTHREADS); q.dynamicSmemBytes = C::SMEM_BYTES; q.attrs = qa; q.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, tc_gemm_kernel<BN, CG>, &q) == cudaSuccess && n > 0) max_units = n < max_units ? n : max_units;
+      else (void)cudaGetLastError();
+    }
     configured = true;
   }
-  const int tiles = p.m_tiles * p.n_tiles;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  tc_gemm_kernel<BN><<<grid, NTHREADS, C::SMEM_BYTES, st>>>(mapA, mapW, p);
+  const int tiles = (p.m_tiles / CG) * p.n_tiles;
+  const int units = tiles < max_units ? tiles : max_units;
+  if (CG == 1) {
+    tc_gemm_kernel<BN, CG><<<units, NTHREADS, C::SMEM_BYTES, st>>>(mapA, mapW, p);
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3(units * 2); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = st;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, CG>, mapA, mapW, p);
+    if (e != cudaSuccess) return (int)e;
+  }
   return mage_post_launch();
 }
 
-int pick_bn(int N, int64_t m_tiles) {
-  static const int forced = [] { const char* e = getenv("MAGE_TC_BN"); return e ? atoi(e) : 0; }();  // tuning aid
-  if (forced && N % forced == 0) return forced;
-  // BN = 128 keeps two (main + corr) accumulator stages in the 512 TMEM columns, so the epilogue of one tile
-  // overlaps the MMAs of the next; measured faster than BN = 256 (single stage) on every shape of the path.
-  // BN = 64 when N is not a multiple of 128 or the 128-wide tiling would leave most SMs idle.
+struct TileCfg { int bn, cg; };
+
+// Tile selection.  The kernel is bound by L2->SM operand traffic, so the widest tile that still fills the machine wins:
+// CTA pair 256x256 (one TMEM accumulator stage), then pair 256x128 (two stages), then the single-CTA tiles.
+// MAGE_TC_BN / MAGE_TC_PAIR (0/1) force a choice (tuning + tests).
+int g_forced_bn = [] { const char* e = getenv("MAGE_TC_BN"); return e ? atoi(e) : 0; }();
+int g_forced_pair = [] { const char* e = getenv("MAGE_TC_PAIR"); return e ? atoi(e) : -1; }();
+
+TileCfg pick_cfg(int N, int64_t m_tiles, int K) {
+  const int forced_bn = g_forced_bn, forced_pair = g_forced_pair;
   const int sms = num_sms();
-  if (N % 128 == 0 && (m_tiles * (N / 128) >= sms || N % 64 != 0)) return 128;
-  if (N % 64 == 0) return 64;
-  return 0;
+  const bool pair_ok = forced_pair != 0 && m_tiles % 2 == 0;
+  if (forced_bn && N % forced_bn == 0) return {forced_bn, (pair_ok && forced_pair == 1) ? 2 : 1};
+  if (pair_ok) {
+    // measured (tools/tc_microbench.py, profiles/): the 256x256 pair tile wins once the k loop is long enough to amortise
+    // its un-overlapped epilogue (single TMEM accumulator stage): K >= 1024.  Shorter k loops stay on the double-buffered
+    // 128-wide single-CTA tile.
+    const int64_t pairs = m_tiles / 2;
+    if (N % 256 == 0 && ((pairs * (N / 256) >= sms / 2 && K >= 1024) || forced_pair == 1)) return {256, 2};
+    if (forced_pair == 1 && N % 128 == 0) return {128, 2};
+    if (forced_pair == 1 && N % 64 == 0) return {64, 2};
+  }
+  // BN = 128 keeps two (main + corr) accumulator stages in the 512 TMEM columns, so the epilogue of one tile
+  // overlaps the MMAs of the next.  BN = 64 when N is not a multiple of 128 or the 128-wide tiling would leave most SMs idle.
+  if (N % 128 == 0 && (m_tiles * (N / 128) >= sms || N % 64 != 0)) return {128, 1};
+  if (N % 64 == 0) return {64, 1};
+  return {0, 0};
 }
 
-int dispatch(int bn, const CUtensorMap& mapA, const CUtensorMap& mapW, const TcParams& p, cudaStream_t st) {
-  switch (bn) {
-    case 256: return launch_tc<256>(mapA, mapW, p, st);
-    case 128: return launch_tc<128>(mapA, mapW, p, st);
-    case 64: return launch_tc<64>(mapA, mapW, p, st);
+int dispatch(TileCfg c, const CUtensorMap& mapA, const CUtensorMap& mapW, const TcParams& p, cudaStream_t st) {
+  if (c.cg == 2) {
+    switch (c.bn) {
+      case 256: return launch_tc<256, 2>(mapA, mapW, p, st);
+      case 128: return launch_tc<128, 2>(mapA, mapW, p, st);
+      case 64: return launch_tc<64, 2>(mapA, mapW, p, st);
+    }
+    return MAGE_ENOTSUP;
+  }
+  switch (c.bn) {
+    case 256: return launch_tc<256, 1>(mapA, mapW, p, st);
+    case 128: return launch_tc<128, 1>(mapA, mapW, p, st);
+    case 64: return launch_tc<64, 1>(mapA, mapW, p, st);
   }
   return MAGE_ENOTSUP;
 }
 
-int make_w_map(CUtensorMap* map, const void* W, int64_t ldw, int64_t w_plane, int N, int K, int bn) {
+int make_w_map(CUtensorMap* map, const void* W, int64_t ldw, int64_t w_plane, int N, int K, int box_rows) {
   const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)N, 2};
   const cuuint64_t strides[2] = {(cuuint64_t)ldw * 2, (cuuint64_t)w_plane * 2};
-  const cuuint32_t box[3] = {BK, (cuuint32_t)bn, 2};
+  const cuuint32_t box[3] = {BK, (cuuint32_t)box_rows, 2};
   return make_map(map, W, 3, dims, strides, box);
 }
 
 }  // namespace
+
+extern "C" int mage_tc_tuning(int bn, int pair) {
+  MAGE_CHECK_ARG((bn == 0 || bn == 64 || bn == 128 || bn == 256) && pair >= -1 && pair <= 1);
+  g_forced_bn = bn;
+  g_forced_pair = pair;
+  return 0;
+}
 
 extern "C" int mage_split_f32(const float* x, int64_t ldx, void* out, int64_t plane, int rows, int C, int relu, int* flag,
                               void* stream) {
@@ -446,8 +602,9 @@ extern "C" int mage_gemm_tc(const void* A, int64_t lda, int64_t a_plane, const v
   MAGE_CHECK_ARG(ldc % 4 == 0 && (!C || aligned16(C)) && (!bias || aligned16(bias)) && (!residual || (aligned16(residual) && ldr % 4 == 0)));
   MAGE_CHECK_ARG(c_plane % 4 == 0 && (C || C_split || C_split_relu));
   const int m_tiles = (M + BM - 1) / BM;
-  const int bn = pick_bn(N, m_tiles);
-  if (!bn) return MAGE_ENOTSUP;
+  const TileCfg tcfg = pick_cfg(N, m_tiles, K);
+  if (!tcfg.bn) return MAGE_ENOTSUP;
+  const int bn = tcfg.bn;
   CUtensorMap mapA, mapW;
   {
     const cuuint64_t dims[5] = {(cuuint64_t)K, (cuuint64_t)M, 1, 1, 2};
@@ -456,7 +613,7 @@ extern "C" int mage_gemm_tc(const void* A, int64_t lda, int64_t a_plane, const v
     const cuuint32_t box[5] = {BK, BM, 1, 1, 2};
     int r = make_map(&mapA, A, 5, dims, strides, box);
     if (r) return r;
-    r = make_w_map(&mapW, W, ldw, w_plane, N, K, bn);
+    r = make_w_map(&mapW, W, ldw, w_plane, N, K, bn / tcfg.cg);
     if (r) return r;
   }
   TcParams p{};
@@ -465,16 +622,19 @@ extern "C" int mage_gemm_tc(const void* A, int64_t lda, int64_t a_plane, const v
   p.flag = flag; p.ldr = ldr; p.ldc = ldc; p.split_plane = c_plane; p.split_relu_plane = c_plane;
   p.M = M; p.N = N; p.act = act; p.res_mod = res_mod;
   p.m_tiles = m_tiles; p.n_tiles = N / bn; p.k_iters = K / BK;
-  return dispatch(bn, mapA, mapW, p, as_stream(stream));
+  return dispatch(tcfg, mapA, mapW, p, as_stream(stream));
 }
 
 // Stride-1 NHWC convolution on the tensor cores.  in: split [n_img,Hin,Win,Cin] (Cin % 64 == 0), w: split
 // [Cout][KH][KW][Cin]; output geometry / residual modes / scatter as mage_conv2d_nhwc_f32.
-extern "C" int mage_conv2d_tc(const void* in, int64_t in_plane, const void* w, int64_t w_plane, const float* bias,
-                              const float* residual, float* out, void* out_split, void* out_split_relu, int64_t out_plane,
-                              int n_img, int Hin, int Win, int Cin, int Hout, int Wout, int Cout, int KH, int KW, int pad_y,
-                              int pad_x, int res_mode, int act, int out_sy, int out_sx, int out_oy, int out_ox, int Hfull,
-                              int Wfull, int64_t out_img_stride, int* flag, void* stream) {
+namespace {
+struct HeadArgs { const float* w; const float* b; float* out; int cout; int64_t img_stride; };
+
+int conv2d_tc_impl(const void* in, int64_t in_plane, const void* w, int64_t w_plane, const float* bias,
+                   const float* residual, float* out, void* out_split, void* out_split_relu, int64_t out_plane,
+                   int n_img, int Hin, int Win, int Cin, int Hout, int Wout, int Cout, int KH, int KW, int pad_y,
+                   int pad_x, int res_mode, int act, int out_sy, int out_sx, int out_oy, int out_ox, int Hfull,
+                   int Wfull, int64_t out_img_stride, int* flag, void* stream, const HeadArgs* head) {
   MAGE_CHECK_ARG(n_img > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && Hout > 0 && Wout > 0);
   if (Cin % BK != 0 || Cout % 64 != 0) return MAGE_ENOTSUP;
   const int Wb = Wout < BM ? Wout : BM;
@@ -482,14 +642,22 @@ extern "C" int mage_conv2d_tc(const void* in, int64_t in_plane, const void* w, i
   const int Hb = BM / Wb;
   if (Wout % Wb != 0 || Hout % Hb != 0) return MAGE_ENOTSUP;
   MAGE_CHECK_ARG(aligned16(in) && aligned16(w) && in_plane % 8 == 0 && w_plane % 8 == 0 && out_plane % 4 == 0);
-  MAGE_CHECK_ARG(res_mode >= 0 && res_mode <= 3 && (res_mode == 0 || residual != nullptr) && (out || out_split || out_split_relu));
+  MAGE_CHECK_ARG(res_mode >= 0 && res_mode <= 3 && (res_mode == 0 || residual != nullptr) && (out || out_split || out_split_relu || head));
   MAGE_CHECK_ARG(Cout % 4 == 0 && out_img_stride % 4 == 0 && (!out || aligned16(out)) && (!bias || aligned16(bias)) &&
                  (!residual || aligned16(residual)));
   const int64_t m_tiles = (int64_t)n_img * (Hout / Hb) * (Wout / Wb);
   MAGE_CHECK_ARG(m_tiles < ((int64_t)1 << 24));
   const int K = KH * KW * Cin;
-  const int bn = pick_bn(Cout, m_tiles);
-  if (!bn) return MAGE_ENOTSUP;
+  TileCfg tcfg = pick_cfg(Cout, m_tiles, K);
+  if (head) {
+    // the pixel head needs every output channel of a row in one CTA: one 256-wide N tile
+    if (Cout != 256 || (act & 0xff) != MAGE_ACT_NONE) return MAGE_ENOTSUP;
+    MAGE_CHECK_ARG(head->w && head->b && head->out && head->cout >= 1 && head->cout <= 3 && aligned16(head->w));
+    tcfg.bn = 256;
+    if (tcfg.cg == 2 && m_tiles % 2 != 0) tcfg.cg = 1;
+  }
+  if (!tcfg.bn) return MAGE_ENOTSUP;
+  const int bn = tcfg.bn;
   CUtensorMap mapA, mapW;
   {
     const cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)n_img, 2};
@@ -498,7 +666,7 @@ extern "C" int mage_conv2d_tc(const void* in, int64_t in_plane, const void* w, i
     const cuuint32_t box[5] = {BK, (cuuint32_t)Wb, (cuuint32_t)Hb, 1, 2};
     int r = make_map(&mapA, in, 5, dims, strides, box);
     if (r) return r;
-    r = make_w_map(&mapW, w, K, w_plane, Cout, K, bn);
+    r = make_w_map(&mapW, w, K, w_plane, Cout, K, bn / tcfg.cg);
     if (r) return r;
   }
   TcParams p{};
@@ -511,5 +679,28 @@ extern "C" int mage_conv2d_tc(const void* in, int64_t in_plane, const void* w, i
   p.conv = 1; p.Hout = Hout; p.Wout = Wout; p.Wb = Wb; p.Hb = Hb; p.KW = KW; p.cin_blocks = Cin / BK; p.cin = Cin;
   p.pad_y = pad_y; p.pad_x = pad_x; p.res_mode = res_mode;
   p.out_sy = out_sy; p.out_sx = out_sx; p.out_oy = out_oy; p.out_ox = out_ox; p.Hfull = Hfull; p.Wfull = Wfull;
-  return dispatch(bn, mapA, mapW, p, as_stream(stream));
+  if (head) { p.head_w = head->w; p.head_b = head->b; p.head_out = head->out; p.head_cout = head->cout; p.head_img_stride = head->img_stride; }
+  return dispatch(tcfg, mapA, mapW, p, as_stream(stream));
+}
+}  // namespace
+
+extern "C" int mage_conv2d_tc(const void* in, int64_t in_plane, const void* w, int64_t w_plane, const float* bias,
+                              const float* residual, float* out, void* out_split, void* out_split_relu, int64_t out_plane,
+                              int n_img, int Hin, int Win, int Cin, int Hout, int Wout, int Cout, int KH, int KW, int pad_y,
+                              int pad_x, int res_mode, int act, int out_sy, int out_sx, int out_oy, int out_ox, int Hfull,
+                              int Wfull, int64_t out_img_stride, int* flag, void* stream) {
+  return conv2d_tc_impl(in, in_plane, w, w_plane, bias, residual, out, out_split, out_split_relu, out_plane, n_img, Hin, Win, Cin,
+                        Hout, Wout, Cout, KH, KW, pad_y, pad_x, res_mode, act, out_sy, out_sx, out_oy, out_ox, Hfull, Wfull,
+                        out_img_stride, flag, stream, nullptr);
+}
+
+extern "C" int mage_conv2d_tc_pixel_head(const void* in, int64_t in_plane, const void* w, int64_t w_plane, const float* bias,
+                                         const float* residual, int n_img, int Hin, int Win, int Cin, int Hout, int Wout,
+                                         int Cout, int KH, int KW, int pad_y, int pad_x, int res_mode, const float* head_w,
+                                         const float* head_b, int head_cout, float* head_out, int64_t head_img_stride,
+                                         int* flag, void* stream) {
+  const HeadArgs h{head_w, head_b, head_out, head_cout, head_img_stride};
+  return conv2d_tc_impl(in, in_plane, w, w_plane, bias, residual, nullptr, nullptr, nullptr, 0, n_img, Hin, Win, Cin, Hout, Wout,
+                        Cout, KH, KW, pad_y, pad_x, res_mode, MAGE_ACT_NONE, 1, 1, 0, 0, Hout, Wout,
+                        (int64_t)Hout * Wout * Cout, flag, stream, &h);
 }

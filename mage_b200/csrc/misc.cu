@@ -5,7 +5,7 @@
 
 int64_t g_mage_launches = 0;
 
-extern "C" int mage_abi_version(void) { return 2; }
+extern "C" int mage_abi_version(void) { return 3; }
 extern "C" int64_t mage_launch_count(void) { return g_mage_launches; }
 
 namespace {

@@ -247,6 +247,13 @@ class VQVAEEngine:
                                          want=("split",))
             _, h3, _ = ops.conv2d_tc(h2, ws[name + ".block.5.weight"], w[name + ".block.5.bias"], pad=(1, 1), act=ACT_RELU,
                                      want=("split",))
+            if bi + 1 == len(blocks) and h3.shape[-1] % 64 == 0 and w[name + ".block.7.weight"].shape[0] == 256 \
+                    and w["decoder.8.bias"].numel() <= 3:
+                # last block: block.7 conv + skip, ReLU, 1x1 conv to pixels and tanh in ONE kernel (the [n,128,128,256] map stays on chip)
+                ops.conv2d_tc_pixel_head(h3, ws[name + ".block.7.weight"], w[name + ".block.7.bias"], pad=(1, 1), residual=idp,
+                                         res_mode=2 if up else 1, head_w=w["decoder.8.weight"], head_b=w["decoder.8.bias"],
+                                         out=out, out_img_stride=out_img_stride)
+                return
             if bi + 1 == len(blocks):
                 want = ("f32",)
             elif (blocks[bi + 1][0] + ".id_path.weight") in w:
@@ -349,6 +356,17 @@ class SamplerEngine:
                 bp = p + f"blocks.{i}."
                 for k in ("attn.in_proj_weight", "attn.out_proj.weight", "mlp.c_fc.weight", "mlp.c_proj.weight"):
                     ws[bp + k] = ops.split(g(bp + k))
+            # prelude operands that see the whole batch (M = B*256 rows): motion-anchor block, context_linear, AdaIN convs
+            ws[p + "context_linear.weight"] = ops.split(g(p + "context_linear.weight"))
+            for i in range(self.n_ma_layers):
+                mp = f"ma_encoder.blocks.{i}."
+                ws[mp + "q_weight"] = ops.split(sd[mp + "attn.in_proj_weight"][:self.C].contiguous())
+                for k in ("attn.out_proj.weight", "mlp.c_fc.weight", "mlp.c_proj.weight"):
+                    ws[mp + k] = ops.split(g(mp + k))
+            if randomness:
+                ws["Wd2"] = ops.split(self.Wd2)
+                for k, (wk, _) in self.adain_w.items():
+                    ws["adain." + k] = ops.split(wk)
             self.ws = ws
 
     # ------------------------------------------------------------------ prelude
@@ -411,6 +429,41 @@ class SamplerEngine:
             mods.append(ops.conv2d(ops.conv2d(y, w0, b0, pad=(1, 1)), w1, b1, pad=(1, 1)))
         return ops.adain(anchor, mods[0], mods[1], 1e-5)
 
+    def _ma_encoder_tc(self, q: torch.Tensor, q_split: torch.Tensor, temb: torch.Tensor, B: int, T: int) -> torch.Tensor:
+        """MAEncoder on the tensor cores (same math as _ma_encoder): q fp32 [B*HW, C] and its split copy."""
+        sd, ws, C = self.sd, self.ws, self.C
+        HW = self.R * self.R
+        M = B * HW
+        x, x_split = q, q_split
+        for i in range(self.n_ma_layers):
+            p = f"ma_encoder.blocks.{i}"
+            Win, bin_ = sd[p + ".attn.in_proj_weight"], sd[p + ".attn.in_proj_bias"]
+            if x_split is None:
+                x_split = ops.split(x)
+            qp, _, _ = ops.gemm_tc(x_split, ws[p + ".q_weight"], bin_[:C].contiguous())
+            kv = ops.gemm(temb, Win[C:], bin_[C:])  # [B*T, 2C]: a few hundred rows, fp32 FFMA kernel
+            a = torch.empty(2, M, C, device=x.device, dtype=torch.float16)
+            ops.mha(qp, kv, kv[:, C:], None, n_outer=B, n_inner=1, n_head=self.n_head, Sq=HW, Sk=T,
+                    q_strides=(HW * C, 0, C), k_strides=(T * 2 * C, 0, 2 * C), v_strides=(T * 2 * C, 0, 2 * C),
+                    o_strides=(HW * C, 0, C), key_len=None, scale=self.scale, out_split=a)
+            x, _, _ = ops.gemm_tc(a, ws[p + ".attn.out_proj.weight"], sd[p + ".attn.out_proj.bias"], residual=x)
+            ops.layernorm(x, sd[p + ".ln_2.weight"], sd[p + ".ln_2.bias"], out_split=a)
+            _, h, _ = ops.gemm_tc(a, ws[p + ".mlp.c_fc.weight"], sd[p + ".mlp.c_fc.bias"], act=ACT_QUICKGELU, want=("split",))
+            ops.gemm_tc(h, ws[p + ".mlp.c_proj.weight"], sd[p + ".mlp.c_proj.bias"], residual=x, out=x)
+            x_split = None
+        return x
+
+    def _adain_tc(self, anchor: torch.Tensor, noise_nchw: torch.Tensor, B: int) -> torch.Tensor:
+        """conv_d2 + ADAIN2D with the five 3x3 convs as tcgen05 implicit GEMMs (same math as _adain)."""
+        ws = self.ws
+        _, y, _ = ops.conv2d_tc(ops.split(ops.nchw_to_nhwc(noise_nchw)), ws["Wd2"], None, pad=(1, 1), want=("split",))
+        mods = []
+        for br in ("conv_mu", "conv_var"):
+            _, h, _ = ops.conv2d_tc(y, ws[f"adain.{br}.0"], self.adain_w[br + ".0"][1], pad=(1, 1), want=("split",))
+            m, _, _ = ops.conv2d_tc(h, ws[f"adain.{br}.1"], self.adain_w[br + ".1"][1], pad=(1, 1))
+            mods.append(m)
+        return ops.adain(anchor, mods[0], mods[1], 1e-5)
+
     # ------------------------------------------------------------------ decoder step
     def _block_step(self, i: int, x: torch.Tensor, pos: int, B: int, caches) -> torch.Tensor:
         """AxialAttentionBlock (mage_model.py:35-53) on one temporal position; x [B*R*R, C] updated in place."""
@@ -448,11 +501,14 @@ class SamplerEngine:
         return x
 
     # ------------------------------------------------------------------ decoder step on the tensor cores
-    def _token_features_tc(self, tok: torch.Tensor, B: int) -> torch.Tensor:
+    def _token_features_tc(self, tok: torch.Tensor, B: int, want_f32: bool = False):
         """split(f(tok)) [2, B*R*R, C]: gather from the pre-split embedding table, 3x3 conv as a tcgen05 implicit
         GEMM with the H/W positional map added in the epilogue (mage_model.py:674-676, 682)."""
         emb = ops.embedding_split(tok.view(B, self.R, self.R), self.ws["E"])
-        _, f, _ = ops.conv2d_tc(emb, self.ws["Wc"], None, pad=(1, 1), residual=self.posHW, res_mode=3, want=("split",))
+        o, f, _ = ops.conv2d_tc(emb, self.ws["Wc"], None, pad=(1, 1), residual=self.posHW, res_mode=3,
+                                want=("f32", "split") if want_f32 else ("split",))
+        if want_f32:
+            return o.view(-1, self.C), f.view(2, -1, self.C)
         return f.view(2, -1, self.C)
 
     def _block_step_tc(self, i: int, x: torch.Tensor, pos: int, B: int, caches, bufs, last: bool):
@@ -503,13 +559,18 @@ class SamplerEngine:
         p = "generate_model."
         z = self.vq.encode_features(images0)
         ops.vq_argmin(z.view(M, -1), self.vq.codebook, out=tok0_out.view(-1))
-        f0 = self._token_features(tok0_out, B)
+        tc = self.backend == "tc"
         temb, _ = self._text_encoder(text)
-        anchor = self._ma_encoder(f0, temb, B, T).view(B, R, R, C)
+        if tc:
+            f0, f0_split = self._token_features_tc(tok0_out, B, want_f32=True)
+            anchor = self._ma_encoder_tc(f0, f0_split, temb, B, T).view(B, R, R, C)
+        else:
+            f0 = self._token_features(tok0_out, B)
+            anchor = self._ma_encoder(f0, temb, B, T).view(B, R, R, C)
         if trace is not None:
             trace["text_emb"], trace["first_img"], trace["anchor_ma"] = temb.view(B, T, C).clone(), f0.view(B, R * R, C).clone(), anchor.clone()
         if noise is not None:
-            anchor = self._adain(anchor, noise, B)
+            anchor = self._adain_tc(anchor, noise, B) if tc else self._adain(anchor, noise, B)
         if speed is not None:
             ops.add_scaled_vec(anchor, speed, sd["speed_embedding"].view(-1))
         if trace is not None:
@@ -518,10 +579,12 @@ class SamplerEngine:
         caches = {i: (torch.empty(M, L, C, device=self.device, dtype=torch.float32),
                       torch.empty(M, L, C, device=self.device, dtype=torch.float32))
                   for i in range(self.n_blocks) if i % 3 == 0}
-        x = ops.gemm(anchor.view(M, C), sd[p + "context_linear.weight"], self.bias_ctx0)
-        tc = self.backend == "tc"
         if tc:
             ws = self.ws
+            x, _, _ = ops.gemm_tc(ops.split(anchor.view(M, C)), ws[p + "context_linear.weight"], self.bias_ctx0)
+        else:
+            x = ops.gemm(anchor.view(M, C), sd[p + "context_linear.weight"], self.bias_ctx0)
+        if tc:
             bufs = {"u": torch.empty(2, M, C, device=self.device, dtype=torch.float16),
                     "h": torch.empty(2, M, 4 * C, device=self.device, dtype=torch.float16),
                     "qkv": torch.empty(M, 3 * C, device=self.device, dtype=torch.float32)}

@@ -96,6 +96,11 @@ def check_flag(device) -> None:
                                  "results are invalid -- run with MAGE_BACKEND=simt")
 
 
+def tc_tuning(bn: int = 0, pair: int = -1) -> None:
+    """Tile-selection override of the tensor-core kernels (tests / tuning): bn 0|64|128|256, pair -1 auto | 0 | 1."""
+    check(_lib.lib().mage_tc_tuning(bn, pair), "mage_tc_tuning")
+
+
 def _f16(t: torch.Tensor) -> torch.Tensor:
     assert t.dtype == torch.float16 and t.is_contiguous() and t.shape[0] == 2, (t.dtype, t.shape, t.stride())
     return t
@@ -191,6 +196,22 @@ def conv2d_tc(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = N
                                         pad[0], pad[1], res_mode, act, sy, sx, oy, ox, Hfull, Wfull, img, _p(flag(dev)),
                                         _stream()), "mage_conv2d_tc")
     return out, out_split, out_split_relu
+
+
+def conv2d_tc_pixel_head(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], *, pad, residual: Optional[torch.Tensor],
+                         res_mode: int, head_w: torch.Tensor, head_b: torch.Tensor, out: torch.Tensor, out_img_stride: int) -> None:
+    """conv2d_tc whose 256-channel result never leaves the SM: tanh(head_b + head_w . relu(conv + bias + residual)) is written
+    planar at out.data_ptr() + img*out_img_stride (vqvae_model.py:210-213)."""
+    _f16(x), _f16(w)
+    _, n, Hin, Win, Cin = x.shape
+    _, Cout, KH, KW, Cin2 = w.shape
+    assert Cin == Cin2 and head_w.shape == (head_b.numel(), Cout) and head_w.is_contiguous()
+    Hout, Wout = Hin + 2 * pad[0] - KH + 1, Win + 2 * pad[1] - KW + 1
+    with _Prof("conv", 2.0 * n * Hout * Wout * Cout * (KH * KW * Cin + head_b.numel())):
+        check(_lib.lib().mage_conv2d_tc_pixel_head(_p(x), n * Hin * Win * Cin, _p(w), Cout * KH * KW * Cin, _p(bias), _p(residual),
+                                                   n, Hin, Win, Cin, Hout, Wout, Cout, KH, KW, pad[0], pad[1], res_mode,
+                                                   _p(head_w), _p(head_b), head_b.numel(), _p(out), out_img_stride,
+                                                   _p(flag(x.device)), _stream()), "mage_conv2d_tc_pixel_head")
 
 
 def conv2d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, stride: int = 1, pad=(0, 0),

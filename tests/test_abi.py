@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/mage_b200.h but not exported"
     assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)
-    assert L.mage_abi_version() == 2
+    assert L.mage_abi_version() == 3
     assert L.mage_launch_count() >= 0
 
 

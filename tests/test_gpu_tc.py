@@ -16,6 +16,17 @@ def _ops():
     return ops
 
 
+@pytest.fixture(params=[("auto", 0, -1), ("pair256", 256, 1), ("pair128", 128, 1), ("pair64", 64, 1), ("single", 0, 0)],
+                ids=lambda p: p[0], autouse=True)
+def tile_cfg(request):
+    """Every test runs under each tile selection: automatic, CTA-pair (cta_group::2) with 256/128/64-wide N tiles where the
+    shape allows it, and single-CTA tiles only."""
+    ops = _ops()
+    ops.tc_tuning(request.param[1], request.param[2])
+    yield request.param[0]
+    ops.tc_tuning(0, -1)
+
+
 def _rand(*shape, seed=0, scale=1.0):
     g = torch.Generator().manual_seed(seed)
     return torch.randn(*shape, generator=g) * scale
@@ -183,3 +194,31 @@ def test_tc_rejects_unsupported_shapes():
     a, w = ops.split(_rand(64, 96, seed=1).to(DEV)), ops.split(_rand(64, 96, seed=2).to(DEV))
     with pytest.raises(_lib.MageCudaError):
         ops.gemm_tc(a, w)  # K % 64 != 0 -> MAGE_ENOTSUP, never a silent fallback
+
+
+@pytest.mark.parametrize("n,H,res_mode", [(2, 128, 2), (3, 16, 1), (2, 32, 2)])
+def test_conv2d_tc_pixel_head_matches_unfused(n, H, res_mode):
+    """The fused last decoder layer (3x3 conv 64->256 + skip -> ReLU -> 1x1 to 3 channels -> tanh, vqvae_model.py:210-213)
+    against the unfused kernels and an fp64 restatement."""
+    ops = _ops()
+    Cin, Cout = 64, 256
+    x, w, b = _rand(n, H, H, Cin, seed=1), _rand(Cout, 3, 3, Cin, seed=2, scale=(9 * Cin) ** -0.5), _rand(Cout, seed=3)
+    Hr = H // 2 if res_mode == 2 else H
+    r = _rand(n, Hr, Hr, Cout, seed=4)
+    hw, hb = _rand(3, Cout, seed=5, scale=Cout ** -0.5), _rand(3, seed=6, scale=0.1)
+    xs, ws_ = ops.split(x.to(DEV)), ops.split(w.to(DEV))
+    out = torch.full((n, 5, 3, H, H), 7.0, device=DEV)           # frame slot 2 of a [n, L=5, 3, H, W] clip
+    ops.conv2d_tc_pixel_head(xs, ws_, b.to(DEV), pad=(1, 1), residual=r.to(DEV), res_mode=res_mode, head_w=hw.to(DEV),
+                             head_b=hb.to(DEV), out=out[:, 2], out_img_stride=5 * 3 * H * H)
+    torch.cuda.synchronize()
+    conv = F.conv2d(x.permute(0, 3, 1, 2).double(), w.permute(0, 3, 1, 2).double(), b.double(), padding=1)
+    res = r.permute(0, 3, 1, 2).double()
+    if res_mode == 2:
+        res = F.interpolate(res, scale_factor=2, mode="nearest")
+    want = torch.tanh(F.conv2d(F.relu(conv + res), hw.double().view(3, Cout, 1, 1), hb.double()))
+    _close(out[:, 2], want, rtol=2e-6)
+    assert (out[:, 1] == 7.0).all() and (out[:, 3] == 7.0).all()   # neighbouring frames untouched
+    full, _, _ = ops.conv2d_tc(xs, ws_, b.to(DEV), pad=(1, 1), residual=r.to(DEV), res_mode=res_mode)
+    ref = torch.empty(n, 3, H, H, device=DEV)
+    ops.conv1x1_tanh_nchw(full, hw.to(DEV), hb.to(DEV), ref, 3 * H * H)
+    _close(out[:, 2], ref.cpu(), rtol=2e-6)

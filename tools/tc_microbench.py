@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--only", default="")
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--cfgs", default="0,-1", help="';'-separated bn,pair tile overrides (ops.tc_tuning) to sweep")
     args = ap.parse_args()
     flush = None if args.no_flush else torch.empty(256 << 20, device=DEV, dtype=torch.uint8)
     M = 16384
@@ -84,12 +85,26 @@ def main():
         ("dec 128x128 64->64", lambda: conv_case("dec 128x128 64->64", 64, 128, 64, 64, 3)),
         ("dec 128x128 64->256", lambda: conv_case("dec 128x128 64->256", 64, 128, 64, 256, 3, "f32")),
     ]
-    for name, fn in cases:
-        if args.only and args.only not in name:
-            continue
-        fn()
-    for name, tf, ms in rows:
-        print(f"{name:36s} {ms:8.3f} ms  {tf:7.1f} TFLOP/s")
+    cases += [
+        ("mainloop 16384x512x8192 f32", lambda: gemm_case("mainloop 16384x512x8192 f32", M, 512, 8192, "f32")),
+        ("mainloop 16384x2048x4096 f32", lambda: gemm_case("mainloop 16384x2048x4096 f32", M, 2048, 4096, "f32")),
+    ]
+    table = {}
+    cfgs = [tuple(int(v) for v in c.split(",")) for c in args.cfgs.split(";")]
+    for bn, pair in cfgs:
+        ops.tc_tuning(bn, pair)
+        rows.clear()
+        g.manual_seed(0)
+        for name, fn in cases:
+            if args.only and args.only not in name:
+                continue
+            fn()
+        for name, tf, ms in rows:
+            table.setdefault(name, []).append((tf, ms))
+    ops.tc_tuning(0, -1)
+    print(f"{'shape':36s} " + " ".join(f"{f'bn{b},pair{p_}':>18s}" for b, p_ in cfgs) + "   (TFLOP/s fp32-grade | ms)")
+    for name, vals in table.items():
+        print(f"{name:36s} " + " ".join(f"{tf:9.1f} |{ms:7.3f}" for tf, ms in vals))
 
 
 if __name__ == "__main__":
