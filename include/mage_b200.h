@@ -87,6 +87,10 @@ int mage_conv2d_nhwc_f32(const float* in, const float* w, const float* bias, con
  * 1 CTA-pair (tcgen05 cta_group::2, 256-row tiles) whenever the row-tile count is even}.  Results do not depend on it
  * beyond fp32 summation order (identical here: the k order is the same for every tile shape). */
 int mage_tc_tuning(int bn, int pair);
+/* enable != 0 (default): KHxKW convolutions whose output is a multiple of 16x8 pixels run in halo mode (the input patch of a
+ * tile is fetched once per 64-channel block and shared by all taps through shifted shared-memory descriptors); 0: every tap
+ * re-fetches its own box.  Same results either way (same k order). */
+int mage_tc_conv_halo(int enable);
 
 /* out(split)[r, :] = split(relu?(x[r, :])); x row stride ldx (elements), C % 4 == 0. */
 int mage_split_f32(const float* x, int64_t ldx, void* out, int64_t plane, int rows, int C, int relu, int* flag,

@@ -49,12 +49,15 @@ struct TcParams {
   // convolution geometry (conv != 0)
   int conv, Hout, Wout, Wb, Hb, KW, cin_blocks, cin, pad_y, pad_x;
   int res_mode, out_sy, out_sx, out_oy, out_ox, Hfull, Wfull;
+  int wb_shift, tiles_x, tiles_img;   // log2(Wb); row tiles per image row / per image (Wb, Hb are powers of two)
   // fused pixel head (last f8 decoder layer): head_out[img, c, pix] = tanh(head_b[c] + sum_n relu(result[row, n]) * head_w[c, n])
   const float* head_w;
   const float* head_b;
   float* head_out;
   int64_t head_img_stride;
   int head_cout;
+  // halo mode (tc_conv_halo_kernel): taps = KH*KW, halo patch pitch in pixels, bytes of one plane / of the whole patch
+  int taps, halo_w, a_plane_bytes, a_tx_bytes;
 };
 
 template <int BN, int CG>
@@ -111,6 +114,18 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
     const uint32_t aph = (tcount / C::ACC_STAGES) & 1;
     // output / residual row offsets of the 8 rows this lane stores (rows quad*32 + i*4 + rq)
     int64_t out_off[8], res_off[8];
+    // tile origin once per tile (two integer divisions); rows inside the tile by shift / mask -- this setup runs on the
+    // epilogue's critical path for every tile, and the k loops of the convolutions are short
+    int img = 0, oy0 = 0, ox0 = 0;
+    int64_t out_base = 0;
+    if (p.conv) {
+      img = mt / p.tiles_img;
+      const int rr = mt - img * p.tiles_img;
+      const int ty = rr / p.tiles_x, tx = rr - ty * p.tiles_x;
+      oy0 = ty * p.Hb;
+      ox0 = tx * p.Wb;
+      out_base = (int64_t)img * p.out_img_stride + ((int64_t)p.out_oy * p.Wfull + p.out_ox) * p.ldc;
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int r = quad * 32 + i * 4 + rq;
@@ -119,12 +134,8 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
       res_off[i] = -1;
       if (m >= M) continue;
       if (p.conv) {
-        const int tiles_x = p.Wout / p.Wb, tiles_y = p.Hout / p.Hb;
-        const int img = mt / (tiles_x * tiles_y), rr = mt - img * tiles_x * tiles_y;
-        const int ty = rr / tiles_x, tx = rr - ty * tiles_x;
-        const int oy = ty * p.Hb + r / p.Wb, ox = tx * p.Wb + r % p.Wb;
-        out_off[i] = (int64_t)img * p.out_img_stride +
-                     ((int64_t)(oy * p.out_sy + p.out_oy) * p.Wfull + (ox * p.out_sx + p.out_ox)) * p.ldc;
+        const int oy = oy0 + (r >> p.wb_shift), ox = ox0 + (r & (p.Wb - 1));
+        out_off[i] = out_base + ((int64_t)(oy * p.out_sy) * p.Wfull + ox * p.out_sx) * p.ldc;
         if (p.res_mode == 1) res_off[i] = (((int64_t)img * p.Hout + oy) * p.Wout + ox) * p.ldr;
         else if (p.res_mode == 2) res_off[i] = (((int64_t)img * (p.Hout >> 1) + (oy >> 1)) * (p.Wout >> 1) + (ox >> 1)) * p.ldr;
         else if (p.res_mode == 3) res_off[i] = ((int64_t)oy * p.Wout + ox) * p.ldr;
@@ -236,10 +247,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_b
         const float4 b = *reinterpret_cast<const float4*>(stg + 4 * 32 * 32 + lane * 4);   // warp + 4's tile
         const int r = quad * 32 + lane, m = mt * BM + r;
         if (m < M) {
-          const int tiles_x = p.Wout / p.Wb, tiles_y = p.Hout / p.Hb;
-          const int img = mt / (tiles_x * tiles_y), rr = mt - img * tiles_x * tiles_y;
-          const int ty = rr / tiles_x, tx = rr - ty * tiles_x;
-          const int oy = ty * p.Hb + r / p.Wb, ox = tx * p.Wb + r % p.Wb;
+          const int oy = oy0 + (r >> p.wb_shift), ox = ox0 + (r & (p.Wb - 1));
           const int64_t pix = (int64_t)(oy * p.out_sy + p.out_oy) * p.Wfull + (ox * p.out_sx + p.out_ox);
           const int64_t plane = (int64_t)p.Hfull * p.Wfull;
           float* dst = p.head_out + (int64_t)img * p.head_img_stride + pix;
@@ -307,9 +315,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int mt = (tile / p.n_tiles) * CG + cta_rank, nt = tile % p.n_tiles;
         int c1 = mt * BM, c2 = 0, c3 = 0;
         if (p.conv) {
-          const int tiles_x = p.Wout / p.Wb, tiles_y = p.Hout / p.Hb;
-          const int img = mt / (tiles_x * tiles_y), r = mt - img * tiles_x * tiles_y;
-          const int ty = r / tiles_x, tx = r - ty * tiles_x;
+          const int img = mt / p.tiles_img, r = mt - img * p.tiles_img;
+          const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
           c1 = tx * p.Wb - p.pad_x;
           c2 = ty * p.Hb - p.pad_y;
           c3 = img;
@@ -403,6 +410,188 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     tc_fence_after();
     if (CG == 2) tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
     else tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------ halo-reusing convolution
+// KHxKW stride-1 convolution on 16x8-pixel output tiles.  Per 64-channel block ONE TMA box brings the (16+KH-1)x(8+KW-1)
+// input patch (both planes); every tap's A operand is that patch read through a shifted descriptor (start + (ky*pitch+kx)
+// rows of 128 B, 8-row groups `pitch` rows apart), so the activations are fetched once instead of KH*KW times.  Weight tiles
+// stream per (tap, channel block) through their own ring.  Same roles / epilogue / CTA-pair scheme as tc_gemm_kernel.
+constexpr int HALO_A_STAGE = 46080;   // 18 x 10 pixels x 128 B x 2 planes (3x3 taps), a multiple of 1024
+constexpr int HALO_SA = 2;
+
+template <int BN, int CG>
+struct HaloCfg {
+  static constexpr int W_ROWS = BN / CG;
+  static constexpr int W_BYTES = 2 * W_ROWS * BK * 2;
+  static constexpr int STAGING_BYTES = 8 * 32 * 32 * 4;
+  static constexpr int SW_RAW = (SMEM_BUDGET - 1024 - 256 - STAGING_BYTES - HALO_SA * HALO_A_STAGE) / W_BYTES;
+  static constexpr int SW = SW_RAW > 8 ? 8 : SW_RAW;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int SMEM_BYTES = 1024 + HALO_SA * HALO_A_STAGE + SW * W_BYTES + STAGING_BYTES + 256;
+  static_assert(SW >= 2, "weight ring too shallow for this tile");
+};
+
+template <int BN, int CG>
+__global__ void __launch_bounds__(NTHREADS, 1)
+tc_conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, const TcParams p) {
+  using H = HaloCfg<BN, CG>;
+  using C = Cfg<BN, CG>;
+  constexpr int SA = HALO_SA, SW = H::SW;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t w_base = base + SA * HALO_A_STAGE;
+  constexpr int STG_OFF = SA * HALO_A_STAGE + SW * H::W_BYTES;
+  float* staging = reinterpret_cast<float*>(base_ptr + STG_OFF);
+  const uint32_t bar_base = base + STG_OFF + H::STAGING_BYTES;
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (SA + s); };
+  auto w_full = [&](int s) { return bar_base + 8u * (2 * SA + s); };
+  auto w_empty = [&](int s) { return bar_base + 8u * (2 * SA + SW + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * SA + 2 * SW + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * SA + 2 * SW + 2 + a); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + STG_OFF + H::STAGING_BYTES + 8 * (2 * SA + 2 * SW + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cta_rank = CG == 2 ? (int)cluster_ctarank() : 0;
+  const int unit = blockIdx.x / CG, n_units = gridDim.x / CG;
+  const int num_tiles = (p.m_tiles / CG) * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapW);
+    for (int s = 0; s < SA; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
+    for (int s = 0; s < SW; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8 * CG); }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    if (CG == 2) tmem_alloc_2sm(smem_u32(const_cast<uint32_t*>(tmem_slot)), H::TMEM_COLS);
+    else tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), H::TMEM_COLS);
+  }
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all();
+  else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int ia = 0, iw = 0;
+      for (int tile = unit; tile < num_tiles; tile += n_units) {
+        const int mt = (tile / p.n_tiles) * CG + cta_rank, nt = tile % p.n_tiles;
+        const int img = mt / p.tiles_img, r = mt - img * p.tiles_img;
+        const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+        const int c1 = tx * p.Wb - p.pad_x, c2 = ty * p.Hb - p.pad_y;
+        const int w_row = nt * BN + cta_rank * H::W_ROWS;
+        for (int cb = 0; cb < p.cin_blocks; ++cb) {
+          {
+            const int s = ia % SA;
+            mbar_wait(a_empty(s), ((ia / SA) & 1) ^ 1);
+            const uint32_t dst = base + s * HALO_A_STAGE;
+            if (CG == 2) {
+              const uint32_t fb = mapa_u32(a_full(s), 0);
+              if (cta_rank == 0) mbar_expect_tx(a_full(s), 2 * p.a_tx_bytes);
+              tma_load_5d_2sm(dst, &mapA, fb, cb * BK, c1, c2, img, 0);
+            } else {
+              mbar_expect_tx(a_full(s), p.a_tx_bytes);
+              tma_load_5d(dst, &mapA, a_full(s), cb * BK, c1, c2, img, 0);
+            }
+            ++ia;
+          }
+          for (int tap = 0; tap < p.taps; ++tap, ++iw) {
+            const int s = iw % SW;
+            mbar_wait(w_empty(s), ((iw / SW) & 1) ^ 1);
+            const uint32_t dst = w_base + s * H::W_BYTES;
+            const int k0 = (tap * p.cin_blocks + cb) * BK;
+            if (CG == 2) {
+              const uint32_t fb = mapa_u32(w_full(s), 0);
+              if (cta_rank == 0) mbar_expect_tx(w_full(s), 2 * H::W_BYTES);
+              tma_load_3d_2sm(dst, &mapW, fb, k0, w_row, 0);
+            } else {
+              mbar_expect_tx(w_full(s), H::W_BYTES);
+              tma_load_3d(dst, &mapW, w_full(s), k0, w_row, 0);
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BN, BM * CG);
+      const uint32_t sbo = (uint32_t)p.halo_w * 128u;
+      int ia = 0, iw = 0, tcount = 0;
+      for (int tile = unit; tile < num_tiles; tile += n_units, ++tcount) {
+        const int acc = tcount % C::ACC_STAGES;
+        const uint32_t aph = (tcount / C::ACC_STAGES) & 1;
+        mbar_wait(tempty_bar(acc), aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_main = tmem_base + acc * 2 * BN, d_corr = d_main + BN;
+        for (int cb = 0; cb < p.cin_blocks; ++cb, ++ia) {
+          const int sa = ia % SA;
+          mbar_wait(a_full(sa), (ia / SA) & 1);
+          tc_fence_after();
+          const uint32_t a_stage = base + sa * HALO_A_STAGE;
+          int ky = 0, kx = 0;
+          for (int tap = 0; tap < p.taps; ++tap, ++iw) {
+            const int sw = iw % SW;
+            mbar_wait(w_full(sw), (iw / SW) & 1);
+            tc_fence_after();
+            const uint32_t a_addr = a_stage + (uint32_t)(ky * p.halo_w + kx) * 128u;
+            const uint64_t a_hi = umma_desc_sw128_sbo(a_addr, sbo), a_lo = umma_desc_sw128_sbo(a_addr + p.a_plane_bytes, sbo);
+            const uint32_t w_addr = w_base + sw * H::W_BYTES;
+            const uint64_t w_hi = umma_desc_sw128(w_addr), w_lo = umma_desc_sw128(w_addr + H::W_ROWS * BK * 2);
+#pragma unroll
+            for (int k = 0; k < BK / UK; ++k) {
+              const uint64_t adv = (uint64_t)((k * UK * 2) >> 4);
+              const uint32_t accum = (cb > 0 || tap > 0 || k > 0) ? 1u : 0u;
+              if (CG == 2) {
+                umma_f16_2sm(d_corr, a_lo + adv, w_hi + adv, idesc, accum);
+                umma_f16_2sm(d_corr, a_hi + adv, w_lo + adv, idesc, 1u);
+                umma_f16_2sm(d_main, a_hi + adv, w_hi + adv, idesc, accum);
+              } else {
+                umma_f16(d_corr, a_lo + adv, w_hi + adv, idesc, accum);
+                umma_f16(d_corr, a_hi + adv, w_lo + adv, idesc, 1u);
+                umma_f16(d_main, a_hi + adv, w_hi + adv, idesc, accum);
+              }
+            }
+            if (CG == 2) umma_commit_2sm(w_empty(sw), 3);
+            else umma_commit(w_empty(sw));
+            if (++kx == p.KW) { kx = 0; ++ky; }
+          }
+          if (CG == 2) umma_commit_2sm(a_empty(sa), 3);
+          else umma_commit(a_empty(sa));
+        }
+        if (CG == 2) umma_commit_2sm(tfull_bar(acc), 3);
+        else umma_commit(tfull_bar(acc));
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------ epilogue warps
+    if (BN == 256 && p.head_w) {
+      if constexpr (BN == 256) epilogue_loop<BN, CG, MAGE_ACT_NONE, true>(p, tmem_base, staging, tfull_bar(0), tempty_bar(0));
+    } else
+    switch (p.act & 0xff) {
+      case MAGE_ACT_NONE: epilogue_loop<BN, CG, MAGE_ACT_NONE>(p, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
+      case MAGE_ACT_RELU: epilogue_loop<BN, CG, MAGE_ACT_RELU>(p, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
+      default: epilogue_loop<BN, CG, MAGE_ACT_TANH>(p, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
+    }
+  }
+
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all();
+  else __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    if (CG == 2) tmem_dealloc_2sm(tmem_base, H::TMEM_COLS);
+    else tmem_dealloc(tmem_base, H::TMEM_COLS);
   }
 }
 
@@ -557,6 +746,78 @@ int dispatch(TileCfg c, const CUtensorMap& mapA, const CUtensorMap& mapW, const 
   return MAGE_ENOTSUP;
 }
 
+
+template <int BN, int CG>
+int launch_halo(const CUtensorMap& mapA, const CUtensorMap& mapW, const TcParams& p, cudaStream_t st) {
+  using H = HaloCfg<BN, CG>;
+  static bool configured = false;
+  static int max_units = 0;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tc_conv_halo_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, H::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    max_units = num_sms() / CG;
+    if (CG == 2) {
+      cudaLaunchConfig_t q{};
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+      q.gridDim = dim3(num_sms() & ~1); q.blockDim = dim3(NTHREADS); q.dynamicSmemBytes = H::SMEM_BYTES; q.attrs = qa; q.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, tc_conv_halo_kernel<BN, CG>, &q) == cudaSuccess && n > 0) max_units = n < max_units ? n : max_units;
+      else (void)cudaGetLastError();
+    }
+    configured = true;
+  }
+  const int tiles = (p.m_tiles / CG) * p.n_tiles;
+  const int units = tiles < max_units ? tiles : max_units;
+  if (CG == 1) {
+    tc_conv_halo_kernel<BN, CG><<<units, NTHREADS, H::SMEM_BYTES, st>>>(mapA, mapW, p);
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3(units * 2); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = H::SMEM_BYTES; cfg.stream = st;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_conv_halo_kernel<BN, CG>, mapA, mapW, p);
+    if (e != cudaSuccess) return (int)e;
+  }
+  return mage_post_launch();
+}
+
+int g_halo = [] { const char* e = getenv("MAGE_TC_HALO"); return e ? atoi(e) : 1; }();
+
+// tile choice of the halo kernel: CTA pairs whenever the row-tile count is even (each CTA then streams only half of every
+// weight tile), the widest N tile the channel count allows; BN = 256 exists only as a pair (weight ring depth).
+TileCfg pick_halo_cfg(int Cout, int64_t m_tiles) {
+  const bool pair_ok = g_forced_pair != 0 && m_tiles % 2 == 0;
+  if (g_forced_bn && Cout % g_forced_bn == 0 && (g_forced_bn != 256 || pair_ok)) return {g_forced_bn, (pair_ok && (g_forced_pair == 1 || g_forced_bn == 256)) ? 2 : 1};
+  if (pair_ok) {
+    if (Cout % 256 == 0) return {256, 2};
+    if (Cout % 128 == 0) return {128, 2};
+    if (Cout % 64 == 0) return {64, 2};
+  }
+  if (Cout % 128 == 0) return {128, 1};
+  if (Cout % 64 == 0) return {64, 1};
+  return {0, 0};
+}
+
+int dispatch_halo(TileCfg c, const CUtensorMap& mapA, const CUtensorMap& mapW, const TcParams& p, cudaStream_t st) {
+  if (c.cg == 2) {
+    switch (c.bn) {
+      case 256: return launch_halo<256, 2>(mapA, mapW, p, st);
+      case 128: return launch_halo<128, 2>(mapA, mapW, p, st);
+      case 64: return launch_halo<64, 2>(mapA, mapW, p, st);
+    }
+    return MAGE_ENOTSUP;
+  }
+  switch (c.bn) {
+    case 128: return launch_halo<128, 1>(mapA, mapW, p, st);
+    case 64: return launch_halo<64, 1>(mapA, mapW, p, st);
+  }
+  return MAGE_ENOTSUP;
+}
+
 int make_w_map(CUtensorMap* map, const void* W, int64_t ldw, int64_t w_plane, int N, int K, int box_rows) {
   const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)N, 2};
   const cuuint64_t strides[2] = {(cuuint64_t)ldw * 2, (cuuint64_t)w_plane * 2};
@@ -570,6 +831,11 @@ extern "C" int mage_tc_tuning(int bn, int pair) {
   MAGE_CHECK_ARG((bn == 0 || bn == 64 || bn == 128 || bn == 256) && pair >= -1 && pair <= 1);
   g_forced_bn = bn;
   g_forced_pair = pair;
+  return 0;
+}
+
+extern "C" int mage_tc_conv_halo(int enable) {
+  g_halo = enable != 0;
   return 0;
 }
 
@@ -637,7 +903,17 @@ int conv2d_tc_impl(const void* in, int64_t in_plane, const void* w, int64_t w_pl
                    int Wfull, int64_t out_img_stride, int* flag, void* stream, const HeadArgs* head) {
   MAGE_CHECK_ARG(n_img > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && Hout > 0 && Wout > 0);
   if (Cin % BK != 0 || Cout % 64 != 0) return MAGE_ENOTSUP;
-  const int Wb = Wout < BM ? Wout : BM;
+  // halo mode: 16x8-pixel tiles, the input patch is fetched once per channel block and shared by all taps
+  const int act_id = act & 0xff;
+  bool halo = g_halo && KH * KW > 1 && Hout % 16 == 0 && Wout % 8 == 0 && (15 + KH) * (7 + KW) * 256 <= HALO_A_STAGE &&
+              (act_id == MAGE_ACT_NONE || act_id == MAGE_ACT_RELU || act_id == MAGE_ACT_TANH);
+  TileCfg hcfg{0, 0};
+  if (halo) {
+    hcfg = pick_halo_cfg(Cout, (int64_t)n_img * (Hout / 16) * (Wout / 8));
+    if (head && !(hcfg.bn == 256 && hcfg.cg == 2)) halo = false;
+    if (!hcfg.bn) halo = false;
+  }
+  const int Wb = halo ? 8 : (Wout < BM ? Wout : BM);
   if (BM % Wb != 0) return MAGE_ENOTSUP;
   const int Hb = BM / Wb;
   if (Wout % Wb != 0 || Hout % Hb != 0) return MAGE_ENOTSUP;
@@ -648,8 +924,8 @@ int conv2d_tc_impl(const void* in, int64_t in_plane, const void* w, int64_t w_pl
   const int64_t m_tiles = (int64_t)n_img * (Hout / Hb) * (Wout / Wb);
   MAGE_CHECK_ARG(m_tiles < ((int64_t)1 << 24));
   const int K = KH * KW * Cin;
-  TileCfg tcfg = pick_cfg(Cout, m_tiles, K);
-  if (head) {
+  TileCfg tcfg = halo ? hcfg : pick_cfg(Cout, m_tiles, K);
+  if (head && !halo) {
     // the pixel head needs every output channel of a row in one CTA: one 256-wide N tile
     if (Cout != 256 || (act & 0xff) != MAGE_ACT_NONE) return MAGE_ENOTSUP;
     MAGE_CHECK_ARG(head->w && head->b && head->out && head->cout >= 1 && head->cout <= 3 && aligned16(head->w));
@@ -663,7 +939,7 @@ int conv2d_tc_impl(const void* in, int64_t in_plane, const void* w, int64_t w_pl
     const cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)n_img, 2};
     const cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)Win * Cin * 2, (cuuint64_t)Hin * Win * Cin * 2,
                                    (cuuint64_t)in_plane * 2};
-    const cuuint32_t box[5] = {BK, (cuuint32_t)Wb, (cuuint32_t)Hb, 1, 2};
+    const cuuint32_t box[5] = {BK, (cuuint32_t)(halo ? Wb + KW - 1 : Wb), (cuuint32_t)(halo ? Hb + KH - 1 : Hb), 1, 2};
     int r = make_map(&mapA, in, 5, dims, strides, box);
     if (r) return r;
     r = make_w_map(&mapW, w, K, w_plane, Cout, K, bn / tcfg.cg);
@@ -677,9 +953,17 @@ int conv2d_tc_impl(const void* in, int64_t in_plane, const void* w, int64_t w_pl
   p.M = (int)(m_tiles * BM); p.N = Cout; p.act = act; p.res_mod = 0;
   p.m_tiles = (int)m_tiles; p.n_tiles = Cout / bn; p.k_iters = KH * KW * (Cin / BK);
   p.conv = 1; p.Hout = Hout; p.Wout = Wout; p.Wb = Wb; p.Hb = Hb; p.KW = KW; p.cin_blocks = Cin / BK; p.cin = Cin;
+  p.wb_shift = 0;
+  while ((1 << p.wb_shift) < Wb) ++p.wb_shift;
+  p.tiles_x = Wout / Wb; p.tiles_img = (Wout / Wb) * (Hout / Hb);
   p.pad_y = pad_y; p.pad_x = pad_x; p.res_mode = res_mode;
   p.out_sy = out_sy; p.out_sx = out_sx; p.out_oy = out_oy; p.out_ox = out_ox; p.Hfull = Hfull; p.Wfull = Wfull;
   if (head) { p.head_w = head->w; p.head_b = head->b; p.head_out = head->out; p.head_cout = head->cout; p.head_img_stride = head->img_stride; }
+  if (halo) {
+    p.taps = KH * KW; p.halo_w = Wb + KW - 1;
+    p.a_plane_bytes = (Hb + KH - 1) * (Wb + KW - 1) * 128; p.a_tx_bytes = 2 * p.a_plane_bytes;
+    return dispatch_halo(tcfg, mapA, mapW, p, as_stream(stream));
+  }
   return dispatch(tcfg, mapA, mapW, p, as_stream(stream));
 }
 }  // namespace

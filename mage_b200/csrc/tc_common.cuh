@@ -120,8 +120,12 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// Default semantics (release at CTA scope), as CUTLASS's ClusterBarrier::arrive(cta_id): a `.release.cluster` arrive compiles
+// to MEMBAR.ALL.GPU + ERRBAR and stalls the epilogue warp until all of its global stores have drained (ncu: 12 % of the
+// kernel's stall samples).  What the remote waiter needs ordered is the TMEM reads, which tcgen05.wait::ld +
+// tcgen05.fence::before_thread_sync already cover.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 
 // ---------------------------------------------------------------- tcgen05
@@ -195,6 +199,19 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset, bits [32,46)
   d |= (uint64_t)1 << 46;                       // version = 1
   d |= (uint64_t)2 << 61;                       // layout = SWIZZLE_128B
+  return d;
+}
+// Same layout with an explicit stride between 8-row groups.  The swizzle XOR is a function of the ABSOLUTE shared-memory
+// address bits (measured: tools/experiments/desc_shift_test.cu), so the start address may sit on any 128-byte row of a
+// TMA-written region (matrix-base-offset field = 0) and the 8-row groups may be any multiple of 128 bytes apart -- a 16x8-pixel
+// tile of a wider halo patch is a valid A operand without copying.
+__device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
   return d;
 }
 // instruction descriptor: fp16 x fp16 -> fp32, both K-major, M = 128, N = n

@@ -101,6 +101,11 @@ def tc_tuning(bn: int = 0, pair: int = -1) -> None:
     check(_lib.lib().mage_tc_tuning(bn, pair), "mage_tc_tuning")
 
 
+def tc_conv_halo(enable: bool = True) -> None:
+    """Halo mode of the tensor-core convolutions on/off (tests / tuning)."""
+    check(_lib.lib().mage_tc_conv_halo(int(enable)), "mage_tc_conv_halo")
+
+
 def _f16(t: torch.Tensor) -> torch.Tensor:
     assert t.dtype == torch.float16 and t.is_contiguous() and t.shape[0] == 2, (t.dtype, t.shape, t.stride())
     return t

@@ -16,15 +16,19 @@ def _ops():
     return ops
 
 
-@pytest.fixture(params=[("auto", 0, -1), ("pair256", 256, 1), ("pair128", 128, 1), ("pair64", 64, 1), ("single", 0, 0)],
+@pytest.fixture(params=[("auto", 0, -1, True), ("pair256", 256, 1, True), ("pair128", 128, 1, True), ("pair64", 64, 1, True),
+                        ("single", 0, 0, True), ("auto-nohalo", 0, -1, False), ("pair256-nohalo", 256, 1, False),
+                        ("single-nohalo", 0, 0, False)],
                 ids=lambda p: p[0], autouse=True)
 def tile_cfg(request):
     """Every test runs under each tile selection: automatic, CTA-pair (cta_group::2) with 256/128/64-wide N tiles where the
-    shape allows it, and single-CTA tiles only."""
+    shape allows it, single-CTA tiles only -- and the convolutions with and without halo reuse."""
     ops = _ops()
     ops.tc_tuning(request.param[1], request.param[2])
+    ops.tc_conv_halo(request.param[3])
     yield request.param[0]
     ops.tc_tuning(0, -1)
+    ops.tc_conv_halo(True)
 
 
 def _rand(*shape, seed=0, scale=1.0):
@@ -222,3 +226,29 @@ def test_conv2d_tc_pixel_head_matches_unfused(n, H, res_mode):
     ref = torch.empty(n, 3, H, H, device=DEV)
     ops.conv1x1_tanh_nchw(full, hw.to(DEV), hb.to(DEV), ref, 3 * H * H)
     _close(out[:, 2], ref.cpu(), rtol=2e-6)
+
+
+@pytest.mark.parametrize("n,H,W,Cin,Cout,k,pad", [(3, 16, 8, 64, 64, 3, (1, 1)), (1, 32, 24, 128, 192, 3, (1, 1)), (2, 16, 16, 64, 256, 2, (1, 0)),
+                                                 (2, 48, 40, 64, 64, 2, (0, 1)), (5, 16, 16, 512, 512, 3, (1, 1))])
+def test_conv2d_tc_halo_geometries(n, H, W, Cin, Cout, k, pad, tile_cfg):
+    """Non-square maps, odd tile counts (no CTA pairing possible), 2x2 phase taps with one-sided padding, many channel blocks."""
+    ops = _ops()
+    if "nohalo" in tile_cfg and 128 % W != 0:
+        from mage_b200 import _lib
+        with pytest.raises(_lib.MageCudaError):   # the per-tap-box kernel tiles rows of 128 / W pixels: loud refusal, no fallback
+            ops.conv2d_tc(ops.split(_rand(n, H, W, Cin).to(DEV)), ops.split(_rand(Cout, k, k, Cin).to(DEV)), None, pad=pad)
+        return
+    x = _rand(n, H, W, Cin, seed=1)
+    w = _rand(Cout, k, k, Cin, seed=2, scale=(k * k * Cin) ** -0.5)
+    b = _rand(Cout, seed=3)
+    Ho, Wo = (H, W)
+    out, _, _ = ops.conv2d_tc(ops.split(x.to(DEV)), ops.split(w.to(DEV)), b.to(DEV), pad=pad, act=1, out_hw=(Ho, Wo))
+    xp = x.permute(0, 3, 1, 2).double()
+    if k == 2:   # out[y,x] = sum in[y - pad_y + ky, x - pad_x + kx] w[ky,kx]: pad before = pad, after = 1 - pad
+        xp = F.pad(xp, (pad[1], 1 - pad[1], pad[0], 1 - pad[0]))
+        want = F.conv2d(xp, w.permute(0, 3, 1, 2).double(), b.double())
+    else:
+        want = F.conv2d(xp, w.permute(0, 3, 1, 2).double(), b.double(), padding=pad)
+    want = F.relu(want).permute(0, 2, 3, 1)
+    _close(out, want, RTOL * max(1.0, k * k * Cin / 2048))
+    ops.check_flag(DEV)
