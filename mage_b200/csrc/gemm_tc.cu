@@ -85,192 +85,214 @@ __device__ __forceinline__ float act_fn(float x) {
 }
 
 // Epilogue of one CTA: 8 warps, two per TMEM lane quadrant (warp % 4), the pair splitting the 32-column chunks.
-// Per chunk: tcgen05.ld main + corr -> v = main + corr*2^-11 (row-per-thread layout) -> XOR-swizzled smem
-// transpose -> bias, activation, residual (row-contiguous layout) -> coalesced fp32 and/or split stores.
+// Row-per-thread: lane l owns output row quad*32 + l (its TMEM lane).  Per 32-column chunk: tcgen05.ld main + corr ->
+// v = main + corr*2^-11 -> bias (uniform loads), activation, residual (the thread's own 128-byte row segment) -> the warp's
+// swizzled 4 KB staging tile -> ONE TMA store per output kind (the fp32 tile, or the hi+lo planes of the split format).
+// No per-row global address arithmetic and no transposes: the k loops on this path are short (K = 512..1152), so the
+// epilogue's instruction count is what paces the kernel (ncu: ~2200 instructions per warp and tile before this form).
+// Rows beyond M are clipped by TMA.
 template <int BN, int CG, int ACT, bool HEAD = false>
-__device__ __forceinline__ void epilogue_loop(const TcParams& p, uint32_t tmem_base, float* staging, uint32_t tfull0, uint32_t tempty0) {
+__device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorMap* mapO, const CUtensorMap* mapS,
+                                              const CUtensorMap* mapR, uint32_t tmem_base, uint8_t* staging, uint32_t tfull0,
+                                              uint32_t tempty0) {
   using C = Cfg<BN, CG>;
   const int cta_rank = CG == 2 ? (int)cluster_ctarank() : 0;
   const int unit = blockIdx.x / CG, n_units = gridDim.x / CG;   // a unit = the CTA (pair) that owns a tile
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int quad = warp & 3, half = (warp - 2) >> 2;
-  float* stg = staging + (warp - 2) * 32 * 32;
-  const int cq = lane & 7, rq = lane >> 3;
+  uint8_t* const stg = staging + (warp - 2) * 4096;
+  const uint32_t stg_s = smem_u32(stg);
   const bool res_relu = (p.act & MAGE_RES_RELU) != 0, post = (p.act & MAGE_ACT_POST_RES) != 0;
-  // everything the chunk loop touches lives in registers: `p` is memory the global stores could alias
   const float* const __restrict__ bias = p.bias;
   const float* const __restrict__ res = p.res;
-  float* const out = p.out;
-  __half* const split = p.split;
-  __half* const split_relu = p.split_relu;
-  const int64_t split_plane = p.split_plane, split_relu_plane = p.split_relu_plane;
+  const bool has_out = p.out != nullptr, has_split = p.split != nullptr, has_relu = p.split_relu != nullptr;
   const int n_tiles = p.n_tiles, M = p.M;
   const int num_tiles = (p.m_tiles / CG) * p.n_tiles;
+  // staging addresses of this lane's row: fp32 tile rows are 128 B (SWIZZLE_128B: 16-byte chunk ^ (row & 7)), split planes
+  // have 64-byte rows (SWIZZLE_64B: chunk ^ ((row >> 1) & 3)), lo plane 2 KB after the hi plane
+  const uint32_t row32 = stg_s + lane * 128, sw32 = lane & 7;
+  const uint32_t row16 = stg_s + lane * 64, sw16 = (lane >> 1) & 3;
   int tcount = 0;
-  bool overflow = false;
+  float amax = 0.f;
+  bool pending = false;   // a TMA store of this warp may still be reading the staging tile
+  auto staging_free = [&]() {
+    if (pending) {
+      if (lane == 0) bulk_wait_read0();
+      __syncwarp();
+      pending = false;
+    }
+  };
   for (int tile = unit; tile < num_tiles; tile += n_units, ++tcount) {
     const int mt = (tile / n_tiles) * CG + cta_rank, nt = tile % n_tiles;
     const int acc = tcount % C::ACC_STAGES;
     const uint32_t aph = (tcount / C::ACC_STAGES) & 1;
-    // output / residual row offsets of the 8 rows this lane stores (rows quad*32 + i*4 + rq)
-    int64_t out_off[8], res_off[8];
-    // tile origin once per tile (two integer divisions); rows inside the tile by shift / mask -- this setup runs on the
-    // epilogue's critical path for every tile, and the k loops of the convolutions are short
-    int img = 0, oy0 = 0, ox0 = 0;
-    int64_t out_base = 0;
+    // the thread's row, the warp's store-box origin and the residual offset: once per tile
+    const int r = quad * 32 + lane, m = mt * BM + r;
+    int sx0 = mt * BM + quad * 32, sy0 = 0, simg = 0, oy = 0, ox = 0;
+    int64_t res_off = -1;
     if (p.conv) {
-      img = mt / p.tiles_img;
-      const int rr = mt - img * p.tiles_img;
+      simg = mt / p.tiles_img;
+      const int rr = mt - simg * p.tiles_img;
       const int ty = rr / p.tiles_x, tx = rr - ty * p.tiles_x;
-      oy0 = ty * p.Hb;
-      ox0 = tx * p.Wb;
-      out_base = (int64_t)img * p.out_img_stride + ((int64_t)p.out_oy * p.Wfull + p.out_ox) * p.ldc;
+      const int r0 = quad * 32;
+      sx0 = tx * p.Wb + (r0 & (p.Wb - 1));
+      sy0 = ty * p.Hb + (r0 >> p.wb_shift);
+      oy = ty * p.Hb + (r >> p.wb_shift);
+      ox = tx * p.Wb + (r & (p.Wb - 1));
+      if (p.res_mode == 1) res_off = (((int64_t)simg * p.Hout + oy) * p.Wout + ox) * p.ldr;
+      else if (p.res_mode == 2) res_off = (((int64_t)simg * (p.Hout >> 1) + (oy >> 1)) * (p.Wout >> 1) + (ox >> 1)) * p.ldr;
+      else if (p.res_mode == 3) res_off = ((int64_t)oy * p.Wout + ox) * p.ldr;
+    } else if (res && m < M) {
+      res_off = (int64_t)(p.res_mod > 0 ? m % p.res_mod : m) * p.ldr;
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = quad * 32 + i * 4 + rq;
-      const int m = mt * BM + r;
-      out_off[i] = -1;
-      res_off[i] = -1;
-      if (m >= M) continue;
-      if (p.conv) {
-        const int oy = oy0 + (r >> p.wb_shift), ox = ox0 + (r & (p.Wb - 1));
-        out_off[i] = out_base + ((int64_t)(oy * p.out_sy) * p.Wfull + ox * p.out_sx) * p.ldc;
-        if (p.res_mode == 1) res_off[i] = (((int64_t)img * p.Hout + oy) * p.Wout + ox) * p.ldr;
-        else if (p.res_mode == 2) res_off[i] = (((int64_t)img * (p.Hout >> 1) + (oy >> 1)) * (p.Wout >> 1) + (ox >> 1)) * p.ldr;
-        else if (p.res_mode == 3) res_off[i] = ((int64_t)oy * p.Wout + ox) * p.ldr;
-      } else {
-        out_off[i] = (int64_t)m * p.ldc;
-        if (res) res_off[i] = (int64_t)(p.res_mod > 0 ? m % p.res_mod : m) * p.ldr;
-      }
-    }
-    float hacc[HEAD ? 8 : 1][3];
-    if (HEAD) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) hacc[i][0] = hacc[i][1] = hacc[i][2] = 0.f;
-    }
+    float hacc[3] = {0.f, 0.f, 0.f};
     mbar_wait(tfull0 + 8u * acc, aph);
     tc_fence_after();
     const uint32_t t_main = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 2 * BN, t_corr = t_main + BN;
 #pragma unroll 1
     for (int c = half; c < BN / 32; c += 2) {
-      const int n = nt * BN + c * 32 + cq * 4;
-      // bias / residual vectors first: their global latency hides behind the TMEM loads and the transpose
-      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (bias) bv = __ldg(reinterpret_cast<const float4*>(bias + n));
-      float4 rv[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (res_off[i] >= 0) rv[i] = __ldg(reinterpret_cast<const float4*>(res + res_off[i] + n));
-      }
+      const int n = nt * BN + c * 32;
       uint32_t rm[32], rc[32];
       tmem_ld32(t_main + c * 32, rm);
       tmem_ld32(t_corr + c * 32, rc);
-      tmem_wait_ld();
+      // the residual row segment travels while the TMEM loads complete
+      float4 rv[8];
+      if (res_off >= 0) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float4 v;
-        v.x = fmaf(__uint_as_float(rc[4 * j + 0]), kLoInv, __uint_as_float(rm[4 * j + 0]));
-        v.y = fmaf(__uint_as_float(rc[4 * j + 1]), kLoInv, __uint_as_float(rm[4 * j + 1]));
-        v.z = fmaf(__uint_as_float(rc[4 * j + 2]), kLoInv, __uint_as_float(rm[4 * j + 2]));
-        v.w = fmaf(__uint_as_float(rc[4 * j + 3]), kLoInv, __uint_as_float(rm[4 * j + 3]));
-        *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = v;
+        for (int j = 0; j < 8; ++j) rv[j] = __ldg(reinterpret_cast<const float4*>(res + res_off + n) + j);
       }
-      __syncwarp();
-      float4 hw[3];
+      tmem_wait_ld();
+      if (c + 2 >= BN / 32) {
+        // this warp's last chunk is in registers: hand the TMEM accumulator stage back before the arithmetic
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cluster(mapa_u32(tempty0 + 8u * acc, 0));   // the leader's MMA thread waits for both CTAs
+          else mbar_arrive(tempty0 + 8u * acc);
+        }
+      }
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(rc[j]), kLoInv, __uint_as_float(rm[j]));
+      if (bias) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n) + j);   // same address in every lane: one broadcast
+          v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+        }
+      }
+      if (ACT != MAGE_ACT_NONE && !post) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = act_fn<ACT>(v[j]);
+      }
+      if (res_off >= 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 a = rv[j];
+          if (res_relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+          v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+        }
+      }
+      if (ACT != MAGE_ACT_NONE && post) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = act_fn<ACT>(v[j]);
+      }
       if (HEAD) {
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch)
-          hw[ch] = ch < p.head_cout ? __ldg(reinterpret_cast<const float4*>(p.head_w + (int64_t)ch * p.N + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+        for (int ch = 0; ch < 3; ++ch) {
+          if (ch < p.head_cout) {
+            float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (out_off[i] < 0) continue;
-        const int r = i * 4 + rq;
-        float4 v = *reinterpret_cast<const float4*>(stg + r * 32 + ((cq ^ (r & 7)) << 2));
-        v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-        if (ACT != MAGE_ACT_NONE && !post) { v.x = act_fn<ACT>(v.x); v.y = act_fn<ACT>(v.y); v.z = act_fn<ACT>(v.z); v.w = act_fn<ACT>(v.w); }
-        float4 a = rv[i];
-        if (res_relu) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
-        v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
-        if (ACT != MAGE_ACT_NONE && post) { v.x = act_fn<ACT>(v.x); v.y = act_fn<ACT>(v.y); v.z = act_fn<ACT>(v.z); v.w = act_fn<ACT>(v.w); }
-        if (HEAD) {
-          const float4 rl = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
-#pragma unroll
-          for (int ch = 0; ch < 3; ++ch)
-            hacc[i][ch] += (rl.x * hw[ch].x + rl.y * hw[ch].y) + (rl.z * hw[ch].z + rl.w * hw[ch].w);
-        }
-        const int64_t o = out_off[i] + n;
-        if (out) *reinterpret_cast<float4*>(out + o) = v;
-        if (split) {
-          uint2 hi, lo;
-          overflow |= split4(v, hi, lo);
-          *reinterpret_cast<uint2*>(split + o) = hi;
-          *reinterpret_cast<uint2*>(split + split_plane + o) = lo;
-        }
-        if (split_relu) {
-          uint2 hi, lo;
-          overflow |= split4(make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f)), hi, lo);
-          *reinterpret_cast<uint2*>(split_relu + o) = hi;
-          *reinterpret_cast<uint2*>(split_relu + split_relu_plane + o) = lo;
+            for (int j = 0; j < 8; ++j) {
+              const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.head_w + (int64_t)ch * p.N + n) + j);
+              s0 = fmaf(fmaxf(v[4 * j], 0.f), w4.x, s0); s1 = fmaf(fmaxf(v[4 * j + 1], 0.f), w4.y, s1);
+              s0 = fmaf(fmaxf(v[4 * j + 2], 0.f), w4.z, s0); s1 = fmaf(fmaxf(v[4 * j + 3], 0.f), w4.w, s1);
+            }
+            hacc[ch] += s0 + s1;
+          }
         }
       }
-      __syncwarp();
-    }
-    // accumulator drained: hand the TMEM stage back to the MMA thread
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) {
-      if (CG == 2) mbar_arrive_cluster(mapa_u32(tempty0 + 8u * acc, 0));   // the leader's MMA thread waits for both CTAs
-      else mbar_arrive(tempty0 + 8u * acc);
+      if (has_out) {
+        staging_free();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          sts128(row32 + ((j ^ sw32) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                 __float_as_uint(v[4 * j + 3]));
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {   // bulk-group bookkeeping is per thread: always the same lane issues and waits
+          tma_store_5d(mapO, stg_s, n, sx0, sy0, simg, 0);
+          bulk_commit();
+        }
+        pending = true;
+      }
+      if (has_split || has_relu) {
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+          if (pass == 0 ? !has_split : !has_relu) continue;
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float a = v[2 * j], b = v[2 * j + 1];
+            if (pass == 1) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+            if (pass == 0 || !has_split) amax = fmaxf(amax, fmaxf(fabsf(a), fabsf(b)));
+            const __half2 h = __floats2half2_rn(a, b);
+            const float2 f = __half22float2(h);
+            const __half2 l = __floats2half2_rn((a - f.x) * kLoScale, (b - f.y) * kLoScale);
+            hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+            lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+          }
+          staging_free();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            sts128(row16 + ((j ^ sw16) << 4), hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+            sts128(row16 + 2048 + ((j ^ sw16) << 4), lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_5d(pass == 0 ? mapS : mapR, stg_s, n, sx0, sy0, simg, 0);
+            bulk_commit();
+          }
+          pending = true;
+        }
+      }
     }
     if (HEAD) {
-      // per-row sums over this warp's columns: reduce the 8 lanes (cq) that share a row, then add the partner warp's half
-      // of the columns through its staging tile (warps 2+quad and 6+quad pair up on named barrier 1+quad)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-#pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-          float x = hacc[i][ch];
-          x += __shfl_xor_sync(0xffffffffu, x, 1);
-          x += __shfl_xor_sync(0xffffffffu, x, 2);
-          x += __shfl_xor_sync(0xffffffffu, x, 4);
-          hacc[i][ch] = x;
-        }
-        if (cq == 0) *reinterpret_cast<float4*>(stg + (i * 4 + rq) * 4) = make_float4(hacc[i][0], hacc[i][1], hacc[i][2], 0.f);
-      }
+      // every thread holds its row's partial sums over this warp's half of the columns; the partner warp (same quadrant,
+      // other half: warp + 4) adds its half through the staging tile, then tanh and the planar pixel stores
+      staging_free();
+      *reinterpret_cast<float4*>(stg + lane * 16) = make_float4(hacc[0], hacc[1], hacc[2], 0.f);
       __syncwarp();
       asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
-      if (half == 0) {
-        const float4 a = *reinterpret_cast<const float4*>(stg + lane * 4);
-        const float4 b = *reinterpret_cast<const float4*>(stg + 4 * 32 * 32 + lane * 4);   // warp + 4's tile
-        const int r = quad * 32 + lane, m = mt * BM + r;
-        if (m < M) {
-          const int oy = oy0 + (r >> p.wb_shift), ox = ox0 + (r & (p.Wb - 1));
-          const int64_t pix = (int64_t)(oy * p.out_sy + p.out_oy) * p.Wfull + (ox * p.out_sx + p.out_ox);
-          const int64_t plane = (int64_t)p.Hfull * p.Wfull;
-          float* dst = p.head_out + (int64_t)img * p.head_img_stride + pix;
-          const float sum[3] = {a.x + b.x, a.y + b.y, a.z + b.z};
+      if (half == 0 && m < M) {
+        const float4 a = *reinterpret_cast<const float4*>(stg + lane * 16);
+        const float4 b = *reinterpret_cast<const float4*>(stg + 4 * 4096 + lane * 16);   // warp + 4's tile
+        const int64_t pix = (int64_t)(oy * p.out_sy + p.out_oy) * p.Wfull + (ox * p.out_sx + p.out_ox);
+        const int64_t plane = (int64_t)p.Hfull * p.Wfull;
+        float* dst = p.head_out + (int64_t)simg * p.head_img_stride + pix;
+        const float sum[3] = {a.x + b.x, a.y + b.y, a.z + b.z};
 #pragma unroll
-          for (int ch = 0; ch < 3; ++ch)
-            if (ch < p.head_cout) dst[ch * plane] = tanhf(sum[ch] + __ldg(p.head_b + ch));
-        }
+        for (int ch = 0; ch < 3; ++ch)
+          if (ch < p.head_cout) dst[ch * plane] = tanhf(sum[ch] + __ldg(p.head_b + ch));
       }
       asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");   // the partner may reuse its staging tile
     }
   }
-  if (overflow && p.flag) atomicOr(p.flag, 1);
+  if (lane == 0) bulk_wait0();   // all of this warp's stores have landed before the CTA may exit
+  if (!(amax <= 65504.f) && p.flag) atomicOr(p.flag, 1);
 }
 
 template <int BN, int CG>
 __global__ void __launch_bounds__(NTHREADS, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, const TcParams p) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
+               const __grid_constant__ CUtensorMap mapO, const __grid_constant__ CUtensorMap mapS,
+               const __grid_constant__ CUtensorMap mapR, const TcParams p) {
   using C = Cfg<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-  float* staging = reinterpret_cast<float*>(base_ptr + C::STAGES * C::STAGE_BYTES);
+  uint8_t* staging = base_ptr + C::STAGES * C::STAGE_BYTES;
   const uint32_t bar_base = base + C::STAGES * C::STAGE_BYTES + C::STAGING_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
@@ -279,7 +301,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + C::STAGES * C::STAGE_BYTES + C::STAGING_BYTES +
                                                                       8 * (2 * C::STAGES + 4));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int cta_rank = CG == 2 ? (int)cluster_ctarank() : 0;
   const int unit = blockIdx.x / CG, n_units = gridDim.x / CG;
   const int num_tiles = (p.m_tiles / CG) * p.n_tiles;
@@ -287,6 +309,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapW);
+    if (p.out) tma_prefetch_desc(&mapO);
+    if (p.split) tma_prefetch_desc(&mapS);
+    if (p.split_relu) tma_prefetch_desc(&mapR);
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -305,11 +330,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (CG == 2) cluster_sync_all();   // the peer's barriers are initialised before anything is signalled remotely
   else __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (every CTA loads its A rows + its W rows)
-    if (lane == 0) {
+    {
       int itg = 0;
       for (int tile = unit; tile < num_tiles; tile += n_units) {
         const int mt = (tile / p.n_tiles) * CG + cta_rank, nt = tile % p.n_tiles;
@@ -336,21 +361,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           if (CG == 2) {
             // both CTAs' bytes land on the LEADER's full barrier: the MMA thread there consumes both halves
             const uint32_t fb = mapa_u32(full_bar(s), 0);
-            if (cta_rank == 0) mbar_expect_tx(full_bar(s), 2 * C::STAGE_BYTES);
-            tma_load_5d_2sm(sa, &mapA, fb, a0, a1, a2, c3, 0);
-            tma_load_3d_2sm(sa + C::A_BYTES, &mapW, fb, it * BK, w_row, 0);
-          } else {
+            if (elect_one()) {
+              if (cta_rank == 0) mbar_expect_tx(full_bar(s), 2 * C::STAGE_BYTES);
+              tma_load_5d_2sm(sa, &mapA, fb, a0, a1, a2, c3, 0);
+              tma_load_3d_2sm(sa + C::A_BYTES, &mapW, fb, it * BK, w_row, 0);
+            }
+          } else if (elect_one()) {
             mbar_expect_tx(full_bar(s), C::STAGE_BYTES);
             tma_load_5d(sa, &mapA, full_bar(s), a0, a1, a2, c3, 0);
             tma_load_3d(sa + C::A_BYTES, &mapW, full_bar(s), it * BK, w_row, 0);
           }
+          __syncwarp();
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (the leader CTA's single thread)
-    if (lane == 0 && cta_rank == 0) {
+    // ------------------------------------------------------------ MMA issuer (the leader CTA; one elected lane issues)
+    if (cta_rank == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(BN, BM * CG);
       int itg = 0, tcount = 0;
       for (int tile = unit; tile < num_tiles; tile += n_units, ++tcount) {
@@ -367,39 +395,44 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           const uint32_t sa = base + s * C::STAGE_BYTES;
           const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + BM * BK * 2);
           const uint64_t w_hi = umma_desc_sw128(sa + C::A_BYTES), w_lo = umma_desc_sw128(sa + C::A_BYTES + C::W_ROWS * BK * 2);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / UK; ++k) {
-            const uint64_t adv = (uint64_t)((k * UK * 2) >> 4);  // +32 B per k-step inside the swizzle row
-            const uint32_t accum = (it > 0 || k > 0) ? 1u : 0u;
-            if (CG == 2) {
-              umma_f16_2sm(d_corr, a_lo + adv, w_hi + adv, idesc, accum);
-              umma_f16_2sm(d_corr, a_hi + adv, w_lo + adv, idesc, 1u);
-              umma_f16_2sm(d_main, a_hi + adv, w_hi + adv, idesc, accum);
-            } else {
-              umma_f16(d_corr, a_lo + adv, w_hi + adv, idesc, accum);
-              umma_f16(d_corr, a_hi + adv, w_lo + adv, idesc, 1u);
-              umma_f16(d_main, a_hi + adv, w_hi + adv, idesc, accum);
+            for (int k = 0; k < BK / UK; ++k) {
+              const uint64_t adv = (uint64_t)((k * UK * 2) >> 4);  // +32 B per k-step inside the swizzle row
+              const uint32_t accum = (it > 0 || k > 0) ? 1u : 0u;
+              if (CG == 2) {
+                umma_f16_2sm(d_corr, a_lo + adv, w_hi + adv, idesc, accum);
+                umma_f16_2sm(d_corr, a_hi + adv, w_lo + adv, idesc, 1u);
+                umma_f16_2sm(d_main, a_hi + adv, w_hi + adv, idesc, accum);
+              } else {
+                umma_f16(d_corr, a_lo + adv, w_hi + adv, idesc, accum);
+                umma_f16(d_corr, a_hi + adv, w_lo + adv, idesc, 1u);
+                umma_f16(d_main, a_hi + adv, w_hi + adv, idesc, accum);
+              }
+            }
+            if (CG == 2) umma_commit_2sm(empty_bar(s), 3);   // frees the stage in both CTAs
+            else umma_commit(empty_bar(s));
+            if (it + 1 == p.k_iters) {
+              if (CG == 2) umma_commit_2sm(tfull_bar(acc), 3);   // both CTAs' epilogues drain their own TMEM
+              else umma_commit(tfull_bar(acc));
             }
           }
-          if (CG == 2) umma_commit_2sm(empty_bar(s), 3);   // frees the stage in both CTAs
-          else umma_commit(empty_bar(s));
+          __syncwarp();
         }
-        if (CG == 2) umma_commit_2sm(tfull_bar(acc), 3);   // both CTAs' epilogues drain their own TMEM
-        else umma_commit(tfull_bar(acc));
       }
     }
     __syncwarp();
   } else {
     // ------------------------------------------------------------ epilogue warps
     if (BN == 256 && p.head_w) {
-      if constexpr (BN == 256) epilogue_loop<BN, CG, MAGE_ACT_NONE, true>(p, tmem_base, staging, tfull_bar(0), tempty_bar(0));
+      if constexpr (BN == 256) epilogue_loop<BN, CG, MAGE_ACT_NONE, true>(p, &mapO, &mapS, &mapR, tmem_base, staging, tfull_bar(0), tempty_bar(0));
     } else
     switch (p.act & 0xff) {
-      case MAGE_ACT_NONE: epilogue_loop<BN, CG, MAGE_ACT_NONE>(p, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
-      case MAGE_ACT_RELU: epilogue_loop<BN, CG, MAGE_ACT_RELU>(p, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
-      case MAGE_ACT_QUICKGELU: epilogue_loop<BN, CG, MAGE_ACT_QUICKGELU>(p, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
-      case MAGE_ACT_GELU: epilogue_loop<BN, CG, MAGE_ACT_GELU>(p, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
-      default: epilogue_loop<BN, CG, MAGE_ACT_TANH>(p, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
+      case MAGE_ACT_NONE: epilogue_loop<BN, CG, MAGE_ACT_NONE>(p, &mapO, &mapS, &mapR, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
+      case MAGE_ACT_RELU: epilogue_loop<BN, CG, MAGE_ACT_RELU>(p, &mapO, &mapS, &mapR, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
+      case MAGE_ACT_QUICKGELU: epilogue_loop<BN, CG, MAGE_ACT_QUICKGELU>(p, &mapO, &mapS, &mapR, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
+      case MAGE_ACT_GELU: epilogue_loop<BN, CG, MAGE_ACT_GELU>(p, &mapO, &mapS, &mapR, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
+      default: epilogue_loop<BN, CG, MAGE_ACT_TANH>(p, &mapO, &mapS, &mapR, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
     }
   }
 
@@ -436,7 +469,9 @@ struct HaloCfg {
 
 template <int BN, int CG>
 __global__ void __launch_bounds__(NTHREADS, 1)
-tc_conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, const TcParams p) {
+tc_conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
+                    const __grid_constant__ CUtensorMap mapO, const __grid_constant__ CUtensorMap mapS,
+                    const __grid_constant__ CUtensorMap mapR, const TcParams p) {
   using H = HaloCfg<BN, CG>;
   using C = Cfg<BN, CG>;
   constexpr int SA = HALO_SA, SW = H::SW;
@@ -445,7 +480,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t w_base = base + SA * HALO_A_STAGE;
   constexpr int STG_OFF = SA * HALO_A_STAGE + SW * H::W_BYTES;
-  float* staging = reinterpret_cast<float*>(base_ptr + STG_OFF);
+  uint8_t* staging = base_ptr + STG_OFF;
   const uint32_t bar_base = base + STG_OFF + H::STAGING_BYTES;
   auto a_full = [&](int s) { return bar_base + 8u * s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (SA + s); };
@@ -455,7 +490,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * SA + 2 * SW + 2 + a); };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + STG_OFF + H::STAGING_BYTES + 8 * (2 * SA + 2 * SW + 4));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int cta_rank = CG == 2 ? (int)cluster_ctarank() : 0;
   const int unit = blockIdx.x / CG, n_units = gridDim.x / CG;
   const int num_tiles = (p.m_tiles / CG) * p.n_tiles;
@@ -463,6 +498,9 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapW);
+    if (p.out) tma_prefetch_desc(&mapO);
+    if (p.split) tma_prefetch_desc(&mapS);
+    if (p.split_relu) tma_prefetch_desc(&mapR);
     for (int s = 0; s < SA; ++s) { mbar_init(a_full(s), 1); mbar_init(a_empty(s), 1); }
     for (int s = 0; s < SW; ++s) { mbar_init(w_full(s), 1); mbar_init(w_empty(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8 * CG); }
@@ -476,11 +514,11 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   if (CG == 2) cluster_sync_all();
   else __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    {
       int ia = 0, iw = 0;
       for (int tile = unit; tile < num_tiles; tile += n_units) {
         const int mt = (tile / p.n_tiles) * CG + cta_rank, nt = tile % p.n_tiles;
@@ -495,12 +533,15 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             const uint32_t dst = base + s * HALO_A_STAGE;
             if (CG == 2) {
               const uint32_t fb = mapa_u32(a_full(s), 0);
-              if (cta_rank == 0) mbar_expect_tx(a_full(s), 2 * p.a_tx_bytes);
-              tma_load_5d_2sm(dst, &mapA, fb, cb * BK, c1, c2, img, 0);
-            } else {
+              if (elect_one()) {
+                if (cta_rank == 0) mbar_expect_tx(a_full(s), 2 * p.a_tx_bytes);
+                tma_load_5d_2sm(dst, &mapA, fb, cb * BK, c1, c2, img, 0);
+              }
+            } else if (elect_one()) {
               mbar_expect_tx(a_full(s), p.a_tx_bytes);
               tma_load_5d(dst, &mapA, a_full(s), cb * BK, c1, c2, img, 0);
             }
+            __syncwarp();
             ++ia;
           }
           for (int tap = 0; tap < p.taps; ++tap, ++iw) {
@@ -510,20 +551,23 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             const int k0 = (tap * p.cin_blocks + cb) * BK;
             if (CG == 2) {
               const uint32_t fb = mapa_u32(w_full(s), 0);
-              if (cta_rank == 0) mbar_expect_tx(w_full(s), 2 * H::W_BYTES);
-              tma_load_3d_2sm(dst, &mapW, fb, k0, w_row, 0);
-            } else {
+              if (elect_one()) {
+                if (cta_rank == 0) mbar_expect_tx(w_full(s), 2 * H::W_BYTES);
+                tma_load_3d_2sm(dst, &mapW, fb, k0, w_row, 0);
+              }
+            } else if (elect_one()) {
               mbar_expect_tx(w_full(s), H::W_BYTES);
               tma_load_3d(dst, &mapW, w_full(s), k0, w_row, 0);
             }
+            __syncwarp();
           }
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0 && cta_rank == 0) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA; one elected lane issues)
+    if (cta_rank == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(BN, BM * CG);
       const uint32_t sbo = (uint32_t)p.halo_w * 128u;
       int ia = 0, iw = 0, tcount = 0;
@@ -547,41 +591,48 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             const uint64_t a_hi = umma_desc_sw128_sbo(a_addr, sbo), a_lo = umma_desc_sw128_sbo(a_addr + p.a_plane_bytes, sbo);
             const uint32_t w_addr = w_base + sw * H::W_BYTES;
             const uint64_t w_hi = umma_desc_sw128(w_addr), w_lo = umma_desc_sw128(w_addr + H::W_ROWS * BK * 2);
+            const bool last_tap = tap + 1 == p.taps, last = last_tap && cb + 1 == p.cin_blocks;
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < BK / UK; ++k) {
-              const uint64_t adv = (uint64_t)((k * UK * 2) >> 4);
-              const uint32_t accum = (cb > 0 || tap > 0 || k > 0) ? 1u : 0u;
+              for (int k = 0; k < BK / UK; ++k) {
+                const uint64_t adv = (uint64_t)((k * UK * 2) >> 4);
+                const uint32_t accum = (cb > 0 || tap > 0 || k > 0) ? 1u : 0u;
+                if (CG == 2) {
+                  umma_f16_2sm(d_corr, a_lo + adv, w_hi + adv, idesc, accum);
+                  umma_f16_2sm(d_corr, a_hi + adv, w_lo + adv, idesc, 1u);
+                  umma_f16_2sm(d_main, a_hi + adv, w_hi + adv, idesc, accum);
+                } else {
+                  umma_f16(d_corr, a_lo + adv, w_hi + adv, idesc, accum);
+                  umma_f16(d_corr, a_hi + adv, w_lo + adv, idesc, 1u);
+                  umma_f16(d_main, a_hi + adv, w_hi + adv, idesc, accum);
+                }
+              }
               if (CG == 2) {
-                umma_f16_2sm(d_corr, a_lo + adv, w_hi + adv, idesc, accum);
-                umma_f16_2sm(d_corr, a_hi + adv, w_lo + adv, idesc, 1u);
-                umma_f16_2sm(d_main, a_hi + adv, w_hi + adv, idesc, accum);
+                umma_commit_2sm(w_empty(sw), 3);
+                if (last_tap) umma_commit_2sm(a_empty(sa), 3);
+                if (last) umma_commit_2sm(tfull_bar(acc), 3);
               } else {
-                umma_f16(d_corr, a_lo + adv, w_hi + adv, idesc, accum);
-                umma_f16(d_corr, a_hi + adv, w_lo + adv, idesc, 1u);
-                umma_f16(d_main, a_hi + adv, w_hi + adv, idesc, accum);
+                umma_commit(w_empty(sw));
+                if (last_tap) umma_commit(a_empty(sa));
+                if (last) umma_commit(tfull_bar(acc));
               }
             }
-            if (CG == 2) umma_commit_2sm(w_empty(sw), 3);
-            else umma_commit(w_empty(sw));
+            __syncwarp();
             if (++kx == p.KW) { kx = 0; ++ky; }
           }
-          if (CG == 2) umma_commit_2sm(a_empty(sa), 3);
-          else umma_commit(a_empty(sa));
         }
-        if (CG == 2) umma_commit_2sm(tfull_bar(acc), 3);
-        else umma_commit(tfull_bar(acc));
       }
     }
     __syncwarp();
   } else {
     // ------------------------------------------------------------ epilogue warps
     if (BN == 256 && p.head_w) {
-      if constexpr (BN == 256) epilogue_loop<BN, CG, MAGE_ACT_NONE, true>(p, tmem_base, staging, tfull_bar(0), tempty_bar(0));
+      if constexpr (BN == 256) epilogue_loop<BN, CG, MAGE_ACT_NONE, true>(p, &mapO, &mapS, &mapR, tmem_base, staging, tfull_bar(0), tempty_bar(0));
     } else
     switch (p.act & 0xff) {
-      case MAGE_ACT_NONE: epilogue_loop<BN, CG, MAGE_ACT_NONE>(p, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
-      case MAGE_ACT_RELU: epilogue_loop<BN, CG, MAGE_ACT_RELU>(p, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
-      default: epilogue_loop<BN, CG, MAGE_ACT_TANH>(p, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
+      case MAGE_ACT_NONE: epilogue_loop<BN, CG, MAGE_ACT_NONE>(p, &mapO, &mapS, &mapR, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
+      case MAGE_ACT_RELU: epilogue_loop<BN, CG, MAGE_ACT_RELU>(p, &mapO, &mapS, &mapR, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
+      default: epilogue_loop<BN, CG, MAGE_ACT_TANH>(p, &mapO, &mapS, &mapR, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
     }
   }
 
@@ -651,18 +702,47 @@ int num_sms() {
 }
 
 // rank-R fp16 tensor map, SWIZZLE_128B, zero OOB fill.  dims/box innermost first; strides in bytes for dims 1..R-1.
-int make_map(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box) {
+int make_map(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box,
+             CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT16, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return MAGE_ENOTSUP;
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(map, dtype, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : MAGE_EINVAL;
 }
 
+// operand maps (A, W) and the epilogue's store maps: O fp32 result, S split(result), R split(relu(result))
+struct Maps { CUtensorMap A, W, O, S, R; };
+
+// Store maps over a (possibly strided / scattered) [n_img, Y, X, Ncols] view: one warp stores a 32-row x 32-column box per
+// call, the 32 rows being bw consecutive x positions of bh consecutive y rows (GEMM: X = rows, bw = 32, Y = n_img = 1).
+// fp32: 128-byte box rows, SWIZZLE_128B.  split: two planes of 64-byte rows, SWIZZLE_64B.  Strides in ELEMENTS.
+int make_store_maps(Maps* mp, float* out, void* split, void* split_relu, int64_t plane, int Ncols, int X, int Y, int n_img,
+                    int64_t sx, int64_t sy, int64_t simg, int bw, int bh) {
+  const cuuint64_t dims[5] = {(cuuint64_t)Ncols, (cuuint64_t)X, (cuuint64_t)Y, (cuuint64_t)n_img, 1};
+  if (out) {
+    const cuuint64_t st[4] = {(cuuint64_t)sx * 4, (cuuint64_t)sy * 4, (cuuint64_t)simg * 4, (cuuint64_t)simg * 4 * (cuuint64_t)n_img};
+    const cuuint32_t box[5] = {32, (cuuint32_t)bw, (cuuint32_t)bh, 1, 1};
+    int r = make_map(&mp->O, out, 5, dims, st, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (r) return r;
+  }
+  const cuuint64_t dims2[5] = {(cuuint64_t)Ncols, (cuuint64_t)X, (cuuint64_t)Y, (cuuint64_t)n_img, 2};
+  const cuuint64_t st2[4] = {(cuuint64_t)sx * 2, (cuuint64_t)sy * 2, (cuuint64_t)simg * 2, (cuuint64_t)plane * 2};
+  const cuuint32_t box2[5] = {32, (cuuint32_t)bw, (cuuint32_t)bh, 1, 2};
+  if (split) {
+    int r = make_map(&mp->S, split, 5, dims2, st2, box2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (r) return r;
+  }
+  if (split_relu) {
+    int r = make_map(&mp->R, split_relu, 5, dims2, st2, box2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (r) return r;
+  }
+  return 0;
+}
+
 template <int BN, int CG>
-int launch_tc(const CUtensorMap& mapA, const CUtensorMap& mapW, const TcParams& p, cudaStream_t st) {
+int launch_tc(const Maps& mp, const TcParams& p, cudaStream_t st) {
   using C = Cfg<BN, CG>;
   static bool configured = false;
   static int max_units = 0;
@@ -686,7 +766,7 @@ int launch_tc(const CUtensorMap& mapA, const CUtensorMap& mapW, const TcParams& 
   const int tiles = (p.m_tiles / CG) * p.n_tiles;
   const int units = tiles < max_units ? tiles : max_units;
   if (CG == 1) {
-    tc_gemm_kernel<BN, CG><<<units, NTHREADS, C::SMEM_BYTES, st>>>(mapA, mapW, p);
+    tc_gemm_kernel<BN, CG><<<units, NTHREADS, C::SMEM_BYTES, st>>>(mp.A, mp.W, mp.O, mp.S, mp.R, p);
   } else {
     cudaLaunchConfig_t cfg{};
     cudaLaunchAttribute attr[1];
@@ -694,7 +774,7 @@ int launch_tc(const CUtensorMap& mapA, const CUtensorMap& mapW, const TcParams& 
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.gridDim = dim3(units * 2); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = st;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, CG>, mapA, mapW, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, CG>, mp.A, mp.W, mp.O, mp.S, mp.R, p);
     if (e != cudaSuccess) return (int)e;
   }
   return mage_post_launch();
@@ -717,9 +797,11 @@ TileCfg pick_cfg(int N, int64_t m_tiles, int K) {
     // measured (tools/tc_microbench.py, profiles/): the 256x256 pair tile wins once the k loop is long enough to amortise
     // its un-overlapped epilogue (single TMEM accumulator stage): K >= 1024.  Shorter k loops stay on the double-buffered
     // 128-wide single-CTA tile.
+    // the 256x128 pair tile (two TMEM accumulator stages, each CTA streams half of the W tile) is the fastest shape on every
+    // GEMM / conv of the path; 256x256 (single accumulator stage) only pays off for very long k loops.
     const int64_t pairs = m_tiles / 2;
-    if (N % 256 == 0 && ((pairs * (N / 256) >= sms / 2 && K >= 1024) || forced_pair == 1)) return {256, 2};
-    if (forced_pair == 1 && N % 128 == 0) return {128, 2};
+    if (N % 256 == 0 && ((pairs * (N / 256) >= sms / 2 && K >= 8192) || (forced_pair == 1 && forced_bn == 0))) return {256, 2};
+    if (N % 128 == 0 && (pairs * (N / 128) >= sms / 2 || forced_pair == 1)) return {128, 2};
     if (forced_pair == 1 && N % 64 == 0) return {64, 2};
   }
   // BN = 128 keeps two (main + corr) accumulator stages in the 512 TMEM columns, so the epilogue of one tile
@@ -729,26 +811,26 @@ TileCfg pick_cfg(int N, int64_t m_tiles, int K) {
   return {0, 0};
 }
 
-int dispatch(TileCfg c, const CUtensorMap& mapA, const CUtensorMap& mapW, const TcParams& p, cudaStream_t st) {
+int dispatch(TileCfg c, const Maps& mp, const TcParams& p, cudaStream_t st) {
   if (c.cg == 2) {
     switch (c.bn) {
-      case 256: return launch_tc<256, 2>(mapA, mapW, p, st);
-      case 128: return launch_tc<128, 2>(mapA, mapW, p, st);
-      case 64: return launch_tc<64, 2>(mapA, mapW, p, st);
+      case 256: return launch_tc<256, 2>(mp, p, st);
+      case 128: return launch_tc<128, 2>(mp, p, st);
+      case 64: return launch_tc<64, 2>(mp, p, st);
     }
     return MAGE_ENOTSUP;
   }
   switch (c.bn) {
-    case 256: return launch_tc<256, 1>(mapA, mapW, p, st);
-    case 128: return launch_tc<128, 1>(mapA, mapW, p, st);
-    case 64: return launch_tc<64, 1>(mapA, mapW, p, st);
+    case 256: return launch_tc<256, 1>(mp, p, st);
+    case 128: return launch_tc<128, 1>(mp, p, st);
+    case 64: return launch_tc<64, 1>(mp, p, st);
   }
   return MAGE_ENOTSUP;
 }
 
 
 template <int BN, int CG>
-int launch_halo(const CUtensorMap& mapA, const CUtensorMap& mapW, const TcParams& p, cudaStream_t st) {
+int launch_halo(const Maps& mp, const TcParams& p, cudaStream_t st) {
   using H = HaloCfg<BN, CG>;
   static bool configured = false;
   static int max_units = 0;
@@ -771,7 +853,7 @@ int launch_halo(const CUtensorMap& mapA, const CUtensorMap& mapW, const TcParams
   const int tiles = (p.m_tiles / CG) * p.n_tiles;
   const int units = tiles < max_units ? tiles : max_units;
   if (CG == 1) {
-    tc_conv_halo_kernel<BN, CG><<<units, NTHREADS, H::SMEM_BYTES, st>>>(mapA, mapW, p);
+    tc_conv_halo_kernel<BN, CG><<<units, NTHREADS, H::SMEM_BYTES, st>>>(mp.A, mp.W, mp.O, mp.S, mp.R, p);
   } else {
     cudaLaunchConfig_t cfg{};
     cudaLaunchAttribute attr[1];
@@ -779,7 +861,7 @@ int launch_halo(const CUtensorMap& mapA, const CUtensorMap& mapW, const TcParams
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.gridDim = dim3(units * 2); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = H::SMEM_BYTES; cfg.stream = st;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_conv_halo_kernel<BN, CG>, mapA, mapW, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_conv_halo_kernel<BN, CG>, mp.A, mp.W, mp.O, mp.S, mp.R, p);
     if (e != cudaSuccess) return (int)e;
   }
   return mage_post_launch();
@@ -793,8 +875,7 @@ TileCfg pick_halo_cfg(int Cout, int64_t m_tiles) {
   const bool pair_ok = g_forced_pair != 0 && m_tiles % 2 == 0;
   if (g_forced_bn && Cout % g_forced_bn == 0 && (g_forced_bn != 256 || pair_ok)) return {g_forced_bn, (pair_ok && (g_forced_pair == 1 || g_forced_bn == 256)) ? 2 : 1};
   if (pair_ok) {
-    if (Cout % 256 == 0) return {256, 2};
-    if (Cout % 128 == 0) return {128, 2};
+    if (Cout % 128 == 0) return {128, 2};   // measured faster than 256-wide pair tiles (two accumulator stages)
     if (Cout % 64 == 0) return {64, 2};
   }
   if (Cout % 128 == 0) return {128, 1};
@@ -802,18 +883,18 @@ TileCfg pick_halo_cfg(int Cout, int64_t m_tiles) {
   return {0, 0};
 }
 
-int dispatch_halo(TileCfg c, const CUtensorMap& mapA, const CUtensorMap& mapW, const TcParams& p, cudaStream_t st) {
+int dispatch_halo(TileCfg c, const Maps& mp, const TcParams& p, cudaStream_t st) {
   if (c.cg == 2) {
     switch (c.bn) {
-      case 256: return launch_halo<256, 2>(mapA, mapW, p, st);
-      case 128: return launch_halo<128, 2>(mapA, mapW, p, st);
-      case 64: return launch_halo<64, 2>(mapA, mapW, p, st);
+      case 256: return launch_halo<256, 2>(mp, p, st);
+      case 128: return launch_halo<128, 2>(mp, p, st);
+      case 64: return launch_halo<64, 2>(mp, p, st);
     }
     return MAGE_ENOTSUP;
   }
   switch (c.bn) {
-    case 128: return launch_halo<128, 1>(mapA, mapW, p, st);
-    case 64: return launch_halo<64, 1>(mapA, mapW, p, st);
+    case 128: return launch_halo<128, 1>(mp, p, st);
+    case 64: return launch_halo<64, 1>(mp, p, st);
   }
   return MAGE_ENOTSUP;
 }
@@ -871,7 +952,9 @@ extern "C" int mage_gemm_tc(const void* A, int64_t lda, int64_t a_plane, const v
   const TileCfg tcfg = pick_cfg(N, m_tiles, K);
   if (!tcfg.bn) return MAGE_ENOTSUP;
   const int bn = tcfg.bn;
-  CUtensorMap mapA, mapW;
+  Maps mp{};
+  CUtensorMap& mapA = mp.A;
+  CUtensorMap& mapW = mp.W;
   {
     const cuuint64_t dims[5] = {(cuuint64_t)K, (cuuint64_t)M, 1, 1, 2};
     const cuuint64_t strides[4] = {(cuuint64_t)lda * 2, (cuuint64_t)lda * 2 * (cuuint64_t)M, (cuuint64_t)lda * 2 * (cuuint64_t)M,
@@ -888,7 +971,12 @@ extern "C" int mage_gemm_tc(const void* A, int64_t lda, int64_t a_plane, const v
   p.flag = flag; p.ldr = ldr; p.ldc = ldc; p.split_plane = c_plane; p.split_relu_plane = c_plane;
   p.M = M; p.N = N; p.act = act; p.res_mod = res_mod;
   p.m_tiles = m_tiles; p.n_tiles = N / bn; p.k_iters = K / BK;
-  return dispatch(tcfg, mapA, mapW, p, as_stream(stream));
+  {
+    MAGE_CHECK_ARG(ldc % 8 == 0 || !(C_split || C_split_relu));   // TMA strides are multiples of 16 bytes
+    int r = make_store_maps(&mp, C, C_split, C_split_relu, c_plane, N, M, 1, 1, ldc, ldc * (int64_t)M, ldc * (int64_t)M, 32, 1);
+    if (r) return r;
+  }
+  return dispatch(tcfg, mp, p, as_stream(stream));
 }
 
 // Stride-1 NHWC convolution on the tensor cores.  in: split [n_img,Hin,Win,Cin] (Cin % 64 == 0), w: split
@@ -909,8 +997,12 @@ int conv2d_tc_impl(const void* in, int64_t in_plane, const void* w, int64_t w_pl
               (act_id == MAGE_ACT_NONE || act_id == MAGE_ACT_RELU || act_id == MAGE_ACT_TANH);
   TileCfg hcfg{0, 0};
   if (halo) {
-    hcfg = pick_halo_cfg(Cout, (int64_t)n_img * (Hout / 16) * (Wout / 8));
-    if (head && !(hcfg.bn == 256 && hcfg.cg == 2)) halo = false;
+    const int64_t hm = (int64_t)n_img * (Hout / 16) * (Wout / 8);
+    hcfg = pick_halo_cfg(Cout, hm);
+    if (head) {   // the pixel head needs all 256 channels of a row in one CTA: the 256-wide pair tile
+      if (hm % 2 == 0 && g_forced_pair != 0 && Cout == 256) hcfg = {256, 2};
+      else halo = false;
+    }
     if (!hcfg.bn) halo = false;
   }
   const int Wb = halo ? 8 : (Wout < BM ? Wout : BM);
@@ -934,7 +1026,9 @@ int conv2d_tc_impl(const void* in, int64_t in_plane, const void* w, int64_t w_pl
   }
   if (!tcfg.bn) return MAGE_ENOTSUP;
   const int bn = tcfg.bn;
-  CUtensorMap mapA, mapW;
+  Maps mp{};
+  CUtensorMap& mapA = mp.A;
+  CUtensorMap& mapW = mp.W;
   {
     const cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)n_img, 2};
     const cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)Win * Cin * 2, (cuuint64_t)Hin * Win * Cin * 2,
@@ -959,12 +1053,22 @@ int conv2d_tc_impl(const void* in, int64_t in_plane, const void* w, int64_t w_pl
   p.pad_y = pad_y; p.pad_x = pad_x; p.res_mode = res_mode;
   p.out_sy = out_sy; p.out_sx = out_sx; p.out_oy = out_oy; p.out_ox = out_ox; p.Hfull = Hfull; p.Wfull = Wfull;
   if (head) { p.head_w = head->w; p.head_b = head->b; p.head_out = head->out; p.head_cout = head->cout; p.head_img_stride = head->img_stride; }
+  {
+    // store maps over the scattered view out[img, oy*sy + out_oy, ox*sx + out_ox, :] (sub-pixel phases of an upsample / ConvTranspose)
+    MAGE_CHECK_ARG(Cout % 8 == 0 && out_img_stride % 8 == 0 && out_plane % 8 == 0);
+    const int64_t o0 = ((int64_t)out_oy * Wfull + out_ox) * Cout;
+    const int bw = Wb < 32 ? Wb : 32;
+    int r = make_store_maps(&mp, out ? out + o0 : nullptr, out_split ? reinterpret_cast<__half*>(out_split) + o0 : nullptr,
+                            out_split_relu ? reinterpret_cast<__half*>(out_split_relu) + o0 : nullptr, out_plane, Cout, Wout, Hout, n_img,
+                            (int64_t)out_sx * Cout, (int64_t)out_sy * Wfull * Cout, out_img_stride, bw, 32 / bw);
+    if (r) return r;
+  }
   if (halo) {
     p.taps = KH * KW; p.halo_w = Wb + KW - 1;
     p.a_plane_bytes = (Hb + KH - 1) * (Wb + KW - 1) * 128; p.a_tx_bytes = 2 * p.a_plane_bytes;
-    return dispatch_halo(tcfg, mapA, mapW, p, as_stream(stream));
+    return dispatch_halo(tcfg, mp, p, as_stream(stream));
   }
-  return dispatch(tcfg, mapA, mapW, p, as_stream(stream));
+  return dispatch(tcfg, mp, p, as_stream(stream));
 }
 }  // namespace
 

@@ -40,6 +40,22 @@ __device__ __forceinline__ bool split4(const float4 v, uint2& hi, uint2& lo) {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a converged warp.  tcgen05.mma / commit / TMA are uniform-datapath instructions (operands in uniform
+// registers): issued under `if (lane == 0)` the compiler cannot prove their operands warp-uniform and wraps EVERY instruction
+// in an ELECT + R2UR.BROADCAST "waterfall" loop (~85 clk per MMA measured -- slower than the MMA itself for N <= 128).
+// The roles therefore run their loops warp-wide in uniform control flow (warp index via shuffle, like CUTLASS's
+// canonical_warp_idx_sync) and only the issue itself is predicated on elect.sync.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -87,6 +103,21 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* map, uint3
           dst),
       "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
+}
+
+// TMA store: one [.. x 32 rows x 32 columns] box from a (swizzled) shared-memory tile to global memory; elements outside the
+// tensor are clipped.  The writing threads fence their generic-proxy shared-memory writes first (fence_proxy_async).
+__device__ __forceinline__ void tma_store_5d(const void* map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
 // 2-CTA variants: the mbarrier may live in the peer CTA of the pair (the leader's "full" barrier counts both CTAs' bytes)

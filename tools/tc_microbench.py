@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--only", default="")
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--scan", action="store_true", help="K / N scans that separate per-tile from per-k-block cost")
     ap.add_argument("--cfgs", default="0,-1", help="';'-separated bn,pair tile overrides (ops.tc_tuning) to sweep")
     args = ap.parse_args()
     flush = None if args.no_flush else torch.empty(256 << 20, device=DEV, dtype=torch.uint8)
@@ -89,6 +90,16 @@ def main():
         ("mainloop 16384x512x8192 f32", lambda: gemm_case("mainloop 16384x512x8192 f32", M, 512, 8192, "f32")),
         ("mainloop 16384x2048x4096 f32", lambda: gemm_case("mainloop 16384x2048x4096 f32", M, 2048, 4096, "f32")),
     ]
+    if args.scan:
+        cases = []
+        for cin in (64, 128, 256):
+            for cout in (64, 128, 256):
+                nm = f"scan 128x128 {cin}->{cout}"
+                cases.append((nm, (lambda nm=nm, cin=cin, cout=cout: conv_case(nm, 64, 128, cin, cout, 3))))
+        for k in (64, 512, 1024, 2048):
+            for n in (64, 128, 512):
+                nm = f"scan gemm 16384x{n}x{k} f32"
+                cases.append((nm, (lambda nm=nm, n=n, k=k: gemm_case(nm, M, n, k, "f32"))))
     table = {}
     cfgs = [tuple(int(v) for v in c.split(",")) for c in args.cfgs.split(";")]
     for bn, pair in cfgs:
