@@ -96,6 +96,13 @@ int mage_tc_conv_halo(int enable);
 int mage_split_f32(const float* x, int64_t ldx, void* out, int64_t plane, int rows, int C, int relu, int* flag,
                    void* stream);
 
+/* First-layer im2row for the tensor cores: in planar [n,C,H,W] fp32 -> out split [n,H,W,64] with
+ *   out[n,y,x, kx*C + c] = in[n,c,y, x+kx-pad]   (zero outside the image; channels >= KW*C are zero),  C*KW <= 64.
+ * A KHxKW convolution of the image (vqvae_model.py:193, 7x7 pad 3) is then mage_conv2d_tc with a KHx1 kernel over these 64
+ * channels and weights w2[co, ky, 0, kx*C + c] = w[co, c, ky, kx]. */
+int mage_patch_rows_split_f32(const float* in, void* out, int64_t plane, int n_img, int C, int H, int W, int KW, int pad,
+                              void* stream);
+
 /* out(split)[r, :] = table(split)[idx[r], :]   (nn.Embedding on a pre-split table: mage_model.py:644,682;
  * vqvae_model.py:240).  C % 8 == 0. */
 int mage_embedding_split(const int64_t* idx, const void* table, int64_t table_plane, void* out, int64_t out_plane,
@@ -174,8 +181,9 @@ int mage_axial_attn_f32(const float* qkv, float* out, void* out_split, int64_t s
                         int n_head, int axis, float scale, void* stream);
 
 /* Temporal attention for one decode step with a TMA-staged K/V cache (bulk async copies into
- * shared memory).  qkv [M, 3C] holds this position's q|k|v; k,v are appended to the caches
- * [M, Lmax, C] at `pos` and q attends positions 0..pos.  out [M, C].  C = 512, 16 heads x 32. */
+ * shared memory).  qkv [M, 3C] holds this position's q|k|v; k,v are appended to the caches at `pos` and q attends
+ * positions 0..pos.  out [M, C].  C = 512, 16 heads x 32.  The caches belong to this entry point and are laid out
+ * [M][2 head-halves][Lmax][256] (each CTA's live prefix is one contiguous block = one bulk copy); they hold M*Lmax*C floats. */
 int mage_temporal_attn_step_f32(const float* qkv, float* kcache, float* vcache, float* out, void* out_split,
                                 int64_t split_plane, int* flag, int M, int pos, int Lmax, float scale, void* stream);
 

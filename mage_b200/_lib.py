@@ -26,6 +26,7 @@ SIGNATURES = {
     "mage_tc_tuning": [_i, _i],
     "mage_tc_conv_halo": [_i],
     "mage_split_f32": [_c_f, _i64, _c_f, _i64, _i, _i, _i, _c_f, _c_f],
+    "mage_patch_rows_split_f32": [_c_f, _c_f, _i64, _i, _i, _i, _i, _i, _i, _c_f],
     "mage_embedding_split": [_c_f, _c_f, _i64, _c_f, _i64, _i, _i, _c_f],
     "mage_gemm_tc": [_c_f, _i64, _i64, _c_f, _i64, _i64, _c_f, _c_f, _i64, _i, _c_f, _c_f, _c_f, _i64, _i64, _i, _i, _i, _i,
                      _c_f, _c_f],

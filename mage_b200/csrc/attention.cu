@@ -257,8 +257,10 @@ __global__ void __launch_bounds__(256) temporal_attn_kernel(const float* __restr
   const int m = blockIdx.x >> 1, half = blockIdx.x & 1;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* row = qkv + (int64_t)m * 3 * TA_C + half * TA_HALF;
-  float* kc = kcache + (int64_t)m * Lmax * TA_C + half * TA_HALF;
-  float* vc = vcache + (int64_t)m * Lmax * TA_C + half * TA_HALF;
+  // cache layout [M][2 head-halves][Lmax][256]: the positions 0..pos-1 of this (row, half) are ONE contiguous block, so each
+  // of K and V arrives with a single bulk copy of pos KB instead of pos copies of 1 KB
+  float* kc = kcache + ((int64_t)m * 2 + half) * Lmax * TA_HALF;
+  float* vc = vcache + ((int64_t)m * 2 + half) * Lmax * TA_HALF;
 
   if (tid == 0) {
     mbar_init(&bars[0], 1);
@@ -266,14 +268,12 @@ __global__ void __launch_bounds__(256) temporal_attn_kernel(const float* __restr
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (warp == 0 && pos > 0) {
-    if (lane == 0) {
-      mbar_expect_tx(&bars[0], (uint32_t)pos * TA_HALF * 4);
-      mbar_expect_tx(&bars[1], (uint32_t)pos * TA_HALF * 4);
-    }
-    __syncwarp();
-    for (int j = lane; j < pos; j += 32) bulk_g2s(Ks + (size_t)j * TA_HALF, kc + (int64_t)j * TA_C, TA_HALF * 4, &bars[0]);
-    for (int j = lane; j < pos; j += 32) bulk_g2s(Vs + (size_t)j * TA_HALF, vc + (int64_t)j * TA_C, TA_HALF * 4, &bars[1]);
+  if (tid == 0 && pos > 0) {
+    const uint32_t bytes = (uint32_t)pos * TA_HALF * 4;
+    mbar_expect_tx(&bars[0], bytes);
+    bulk_g2s(Ks, kc, bytes, &bars[0]);
+    mbar_expect_tx(&bars[1], bytes);
+    bulk_g2s(Vs, vc, bytes, &bars[1]);
   }
   // this position's q, k, v: registers -> shared (math) and -> cache (future steps)
   {
@@ -281,8 +281,8 @@ __global__ void __launch_bounds__(256) temporal_attn_kernel(const float* __restr
     qs[tid] = qv;
     Ks[(size_t)pos * TA_HALF + tid] = kv;
     Vs[(size_t)pos * TA_HALF + tid] = vv;
-    kc[(int64_t)pos * TA_C + tid] = kv;
-    vc[(int64_t)pos * TA_C + tid] = vv;
+    kc[(int64_t)pos * TA_HALF + tid] = kv;
+    vc[(int64_t)pos * TA_HALF + tid] = vv;
   }
   __syncthreads();
   if (pos > 0) mbar_wait(&bars[0], 0);

@@ -56,6 +56,9 @@ struct TcParams {
   float* head_out;
   int64_t head_img_stride;
   int head_cout;
+  // tiles are handed to a CTA (pair) in groups of `group` consecutive tile indices (= all N tiles of one row tile when the
+  // pixel head accumulates across them); 1 = plain round-robin
+  int group;
   // halo mode (tc_conv_halo_kernel): taps = KH*KW, halo patch pitch in pixels, bytes of one plane / of the whole patch
   int taps, halo_w, a_plane_bytes, a_tx_bytes;
 };
@@ -73,6 +76,11 @@ struct Cfg {
   static constexpr int TMEM_COLS = 512;
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + 256;
 };
+
+// i-th tile of unit `unit`: groups of G consecutive tile indices are dealt round-robin to the units
+__device__ __forceinline__ int tile_of(int i, int unit, int n_units, int G) {
+  return G == 1 ? unit + i * n_units : (unit + (i / G) * n_units) * G + i % G;
+}
 
 template <int ACT>
 __device__ __forceinline__ float act_fn(float x) {
@@ -122,7 +130,10 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
       pending = false;
     }
   };
-  for (int tile = unit; tile < num_tiles; tile += n_units, ++tcount) {
+  float hacc[3] = {0.f, 0.f, 0.f};
+  for (;; ++tcount) {
+    const int tile = tile_of(tcount, unit, n_units, p.group);
+    if (tile >= num_tiles) break;
     const int mt = (tile / n_tiles) * CG + cta_rank, nt = tile % n_tiles;
     const int acc = tcount % C::ACC_STAGES;
     const uint32_t aph = (tcount / C::ACC_STAGES) & 1;
@@ -145,7 +156,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
     } else if (res && m < M) {
       res_off = (int64_t)(p.res_mod > 0 ? m % p.res_mod : m) * p.ldr;
     }
-    float hacc[3] = {0.f, 0.f, 0.f};
+    if (HEAD && tcount % p.group == 0) hacc[0] = hacc[1] = hacc[2] = 0.f;
     mbar_wait(tfull0 + 8u * acc, aph);
     tc_fence_after();
     const uint32_t t_main = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 2 * BN, t_corr = t_main + BN;
@@ -258,7 +269,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
         }
       }
     }
-    if (HEAD) {
+    if (HEAD && tcount % p.group == p.group - 1) {
       // every thread holds its row's partial sums over this warp's half of the columns; the partner warp (same quadrant,
       // other half: warp + 4) adds its half through the staging tile, then tanh and the planar pixel stores
       staging_free();
@@ -336,7 +347,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // ------------------------------------------------------------ TMA producer (every CTA loads its A rows + its W rows)
     {
       int itg = 0;
-      for (int tile = unit; tile < num_tiles; tile += n_units) {
+      for (int ti = 0;; ++ti) {
+        const int tile = tile_of(ti, unit, n_units, p.group);
+        if (tile >= num_tiles) break;
         const int mt = (tile / p.n_tiles) * CG + cta_rank, nt = tile % p.n_tiles;
         int c1 = mt * BM, c2 = 0, c3 = 0;
         if (p.conv) {
@@ -381,7 +394,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (cta_rank == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(BN, BM * CG);
       int itg = 0, tcount = 0;
-      for (int tile = unit; tile < num_tiles; tile += n_units, ++tcount) {
+      for (;; ++tcount) {
+        if (tile_of(tcount, unit, n_units, p.group) >= num_tiles) break;
         const int acc = tcount % C::ACC_STAGES;
         const uint32_t aph = (tcount / C::ACC_STAGES) & 1;
         mbar_wait(tempty_bar(acc), aph ^ 1);
@@ -424,8 +438,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     __syncwarp();
   } else {
     // ------------------------------------------------------------ epilogue warps
-    if (BN == 256 && p.head_w) {
-      if constexpr (BN == 256) epilogue_loop<BN, CG, MAGE_ACT_NONE, true>(p, &mapO, &mapS, &mapR, tmem_base, staging, tfull_bar(0), tempty_bar(0));
+    if ((BN == 256 || BN == 128) && p.head_w) {
+      if constexpr (BN == 256 || BN == 128) epilogue_loop<BN, CG, MAGE_ACT_NONE, true>(p, &mapO, &mapS, &mapR, tmem_base, staging, tfull_bar(0), tempty_bar(0));
     } else
     switch (p.act & 0xff) {
       case MAGE_ACT_NONE: epilogue_loop<BN, CG, MAGE_ACT_NONE>(p, &mapO, &mapS, &mapR, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
@@ -520,7 +534,9 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     // ------------------------------------------------------------ TMA producer
     {
       int ia = 0, iw = 0;
-      for (int tile = unit; tile < num_tiles; tile += n_units) {
+      for (int ti = 0;; ++ti) {
+        const int tile = tile_of(ti, unit, n_units, p.group);
+        if (tile >= num_tiles) break;
         const int mt = (tile / p.n_tiles) * CG + cta_rank, nt = tile % p.n_tiles;
         const int img = mt / p.tiles_img, r = mt - img * p.tiles_img;
         const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
@@ -571,7 +587,8 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       constexpr uint32_t idesc = umma_idesc_f16(BN, BM * CG);
       const uint32_t sbo = (uint32_t)p.halo_w * 128u;
       int ia = 0, iw = 0, tcount = 0;
-      for (int tile = unit; tile < num_tiles; tile += n_units, ++tcount) {
+      for (;; ++tcount) {
+        if (tile_of(tcount, unit, n_units, p.group) >= num_tiles) break;
         const int acc = tcount % C::ACC_STAGES;
         const uint32_t aph = (tcount / C::ACC_STAGES) & 1;
         mbar_wait(tempty_bar(acc), aph ^ 1);
@@ -626,8 +643,8 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     __syncwarp();
   } else {
     // ------------------------------------------------------------ epilogue warps
-    if (BN == 256 && p.head_w) {
-      if constexpr (BN == 256) epilogue_loop<BN, CG, MAGE_ACT_NONE, true>(p, &mapO, &mapS, &mapR, tmem_base, staging, tfull_bar(0), tempty_bar(0));
+    if ((BN == 256 || BN == 128) && p.head_w) {
+      if constexpr (BN == 256 || BN == 128) epilogue_loop<BN, CG, MAGE_ACT_NONE, true>(p, &mapO, &mapS, &mapR, tmem_base, staging, tfull_bar(0), tempty_bar(0));
     } else
     switch (p.act & 0xff) {
       case MAGE_ACT_NONE: epilogue_loop<BN, CG, MAGE_ACT_NONE>(p, &mapO, &mapS, &mapR, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
@@ -673,6 +690,32 @@ __global__ void __launch_bounds__(256) embedding_split_kernel(const int64_t* __r
   const int row = (int)(u / C8), c = (int)(u - (int64_t)row * C8);
   const uint4 v = __ldg(reinterpret_cast<const uint4*>(table + pl * table_plane + idx[row] * (int64_t)C8 * 8) + c);
   reinterpret_cast<uint4*>(out + pl * out_plane)[u] = v;
+}
+
+// First-layer im2row: out(split)[n, y, x, kx*C + c] = in[n, c, y, x + kx - pad] (0 outside the image and for the padding
+// channels up to 64), so that a KHxKW convolution of a C<=9-channel planar image becomes a KHx1 convolution with 64 input
+// channels -- a tensor-core (halo) convolution with K = KH*64.  One thread per (pixel, 8-channel chunk).
+__global__ void __launch_bounds__(256) patch_rows_split_kernel(const float* __restrict__ in, __half* __restrict__ out, int64_t plane,
+                                                               int n_img, int C, int H, int W, int KW, int pad) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n_pix = (int64_t)n_img * H * W;
+  if (t >= n_pix * 8) return;
+  const int chunk = (int)(t & 7);
+  const int64_t pix = t >> 3;
+  const int x = (int)(pix % W), y = (int)((pix / W) % H), n = (int)(pix / ((int64_t)W * H));
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int q = chunk * 8 + j, kx = q / C, c = q - kx * C;
+    const int xs = x + kx - pad;
+    v[j] = (kx < KW && xs >= 0 && xs < W) ? __ldg(in + (((int64_t)n * C + c) * H + y) * W + xs) : 0.f;
+  }
+  uint2 h0, l0, h1, l1;
+  split4(make_float4(v[0], v[1], v[2], v[3]), h0, l0);
+  split4(make_float4(v[4], v[5], v[6], v[7]), h1, l1);
+  const int64_t o = pix * 64 + chunk * 8;
+  *reinterpret_cast<uint4*>(out + o) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+  *reinterpret_cast<uint4*>(out + plane + o) = make_uint4(l0.x, l0.y, l1.x, l1.y);
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -930,6 +973,15 @@ extern "C" int mage_split_f32(const float* x, int64_t ldx, void* out, int64_t pl
   return mage_post_launch();
 }
 
+extern "C" int mage_patch_rows_split_f32(const float* in, void* out, int64_t plane, int n_img, int C, int H, int W, int KW, int pad,
+                                         void* stream) {
+  MAGE_CHECK_ARG(n_img > 0 && C > 0 && H > 0 && W > 0 && KW > 0 && C * KW <= 64 && pad >= 0 && aligned16(out) && plane % 8 == 0);
+  const int64_t total = (int64_t)n_img * H * W * 8;
+  patch_rows_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(in, reinterpret_cast<__half*>(out), plane, n_img,
+                                                                                          C, H, W, KW, pad);
+  return mage_post_launch();
+}
+
 extern "C" int mage_embedding_split(const int64_t* idx, const void* table, int64_t table_plane, void* out, int64_t out_plane,
                                     int rows, int C, void* stream) {
   MAGE_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0 && aligned16(table) && aligned16(out) && table_plane % 8 == 0 && out_plane % 8 == 0);
@@ -970,7 +1022,7 @@ extern "C" int mage_gemm_tc(const void* A, int64_t lda, int64_t a_plane, const v
   p.split = reinterpret_cast<__half*>(C_split); p.split_relu = reinterpret_cast<__half*>(C_split_relu);
   p.flag = flag; p.ldr = ldr; p.ldc = ldc; p.split_plane = c_plane; p.split_relu_plane = c_plane;
   p.M = M; p.N = N; p.act = act; p.res_mod = res_mod;
-  p.m_tiles = m_tiles; p.n_tiles = N / bn; p.k_iters = K / BK;
+  p.m_tiles = m_tiles; p.n_tiles = N / bn; p.k_iters = K / BK; p.group = 1;
   {
     MAGE_CHECK_ARG(ldc % 8 == 0 || !(C_split || C_split_relu));   // TMA strides are multiples of 16 bytes
     int r = make_store_maps(&mp, C, C_split, C_split_relu, c_plane, N, M, 1, 1, ldc, ldc * (int64_t)M, ldc * (int64_t)M, 32, 1);
@@ -999,8 +1051,10 @@ int conv2d_tc_impl(const void* in, int64_t in_plane, const void* w, int64_t w_pl
   if (halo) {
     const int64_t hm = (int64_t)n_img * (Hout / 16) * (Wout / 8);
     hcfg = pick_halo_cfg(Cout, hm);
-    if (head) {   // the pixel head needs all 256 channels of a row in one CTA: the 256-wide pair tile
-      if (hm % 2 == 0 && g_forced_pair != 0 && Cout == 256) hcfg = {256, 2};
+    if (head) {
+      // the pixel head needs all 256 channels of a row in one CTA: two consecutive 128-wide tiles of the same rows (the
+      // partial sums stay in registers across the group; TMEM double buffering is kept), or one 256-wide tile when forced
+      if (hm % 2 == 0 && g_forced_pair != 0 && Cout == 256) hcfg = {g_forced_bn == 256 ? 256 : 128, 2};
       else halo = false;
     }
     if (!hcfg.bn) halo = false;
@@ -1052,7 +1106,11 @@ int conv2d_tc_impl(const void* in, int64_t in_plane, const void* w, int64_t w_pl
   p.tiles_x = Wout / Wb; p.tiles_img = (Wout / Wb) * (Hout / Hb);
   p.pad_y = pad_y; p.pad_x = pad_x; p.res_mode = res_mode;
   p.out_sy = out_sy; p.out_sx = out_sx; p.out_oy = out_oy; p.out_ox = out_ox; p.Hfull = Hfull; p.Wfull = Wfull;
-  if (head) { p.head_w = head->w; p.head_b = head->b; p.head_out = head->out; p.head_cout = head->cout; p.head_img_stride = head->img_stride; }
+  p.group = 1;
+  if (head) {
+    p.head_w = head->w; p.head_b = head->b; p.head_out = head->out; p.head_cout = head->cout; p.head_img_stride = head->img_stride;
+    p.group = p.n_tiles;   // all N tiles of a row tile go to the same CTA, back to back
+  }
   {
     // store maps over the scattered view out[img, oy*sy + out_oy, ox*sx + out_ox, :] (sub-pixel phases of an upsample / ConvTranspose)
     MAGE_CHECK_ARG(Cout % 8 == 0 && out_img_stride % 8 == 0 && out_plane % 8 == 0);

@@ -127,6 +127,14 @@ class VQVAEEngine:
         for name in ("decoder.2", "decoder.4", "decoder.6"):
             for ph, wp in _upsample_phase_weights(sd[name + ".block.3.weight"]).items():
                 ws[f"{name}.block.3.p{ph[0]}{ph[1]}"] = ops.split(wp)
+        # encoder.0 (7x7, pad 3, 3 -> dim) as a 7x1 tensor-core convolution over the im2row'ed image: w2[co,ky,0,kx*C+c] = w[co,c,ky,kx]
+        w0 = sd["encoder.0.weight"]
+        co, ci, kh, kw = w0.shape
+        if ci * kw <= 64:
+            w2 = torch.zeros(co, kh, 1, 64, device=w0.device, dtype=torch.float32)
+            w2[:, :, 0, : kw * ci] = w0.permute(0, 2, 3, 1).reshape(co, kh, kw * ci)
+            ws["enc0_rows"] = ops.split(w2)
+            self.enc0_kw, self.enc0_pad = kw, kw // 2
         self.ws = ws
         self.cb_split = ops.split(self.codebook)
         self.cb_relu_split = ops.split(self.codebook, relu=True)
@@ -157,11 +165,13 @@ class VQVAEEngine:
         out = ops.gemm(h.view(-1, C), w[name + ".c1.w"], w[name + ".c1.b"], residual=xr.view(-1, C), act=act)
         return out.view(n, H, W, C)
 
-    def _enc_block_tc(self, name: str, x: torch.Tensor, final_relu: bool = False) -> torch.Tensor:
-        """EncoderBlock on the tensor cores: x fp32 NHWC in, fp32 NHWC out (feeds max-pool / VQ argmin)."""
+    def _enc_block_tc(self, name: str, x: torch.Tensor, final_relu: bool = False, xr: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """EncoderBlock on the tensor cores: x fp32 NHWC in, fp32 NHWC out (feeds max-pool / VQ argmin).
+        xr = split(relu(x)) when the producer already emitted it."""
         w, ws = self.w, self.ws
         n, H, W, C = x.shape
-        xr = ops.split(x, relu=True)
+        if xr is None:
+            xr = ops.split(x, relu=True)
         if (name + ".id_path.weight") in w:
             idp, _, _ = ops.gemm_tc(ops.split(x).view(2, -1, C), ws[name + ".id_path.weight"], w[name + ".id_path.bias"])
         else:
@@ -178,8 +188,13 @@ class VQVAEEngine:
         w = self.w
         x = x.contiguous()
         if self.backend == "tc":
-            h = ops.conv2d_first(x, w["enc0_wt"], w["enc0_b"], cout=w["enc0_b"].numel(), kh=7, kw=7, stride=1, pad=3)
-            h = ops.maxpool2x2(self._enc_block_tc("encoder.1", h))
+            if "enc0_rows" in self.ws and x.shape[2] % 16 == 0 and x.shape[3] % 8 == 0:
+                rows = ops.patch_rows_split(x, self.enc0_kw, self.enc0_pad)
+                h, _, hr = ops.conv2d_tc(rows, self.ws["enc0_rows"], w["enc0_b"], pad=(self.enc0_pad, 0), want=("f32", "split_relu"))
+                h = ops.maxpool2x2(self._enc_block_tc("encoder.1", h, xr=hr))
+            else:
+                h = ops.conv2d_first(x, w["enc0_wt"], w["enc0_b"], cout=w["enc0_b"].numel(), kh=7, kw=7, stride=1, pad=3)
+                h = ops.maxpool2x2(self._enc_block_tc("encoder.1", h))
             h = ops.maxpool2x2(self._enc_block_tc("encoder.3", h))
             h = ops.maxpool2x2(self._enc_block_tc("encoder.5", h))
             return self._enc_block_tc("encoder.7", h, final_relu=True)

@@ -128,6 +128,16 @@ def split(x: torch.Tensor, relu: bool = False, out: Optional[torch.Tensor] = Non
     return out
 
 
+def patch_rows_split(x_nchw: torch.Tensor, kw: int, pad: int) -> torch.Tensor:
+    """planar [n,C,H,W] fp32 -> split [2,n,H,W,64] im2row over the kw horizontal taps (channel kx*C + c), see mage_b200.h."""
+    n, C, H, W = x_nchw.shape
+    out = torch.empty(2, n, H, W, 64, device=x_nchw.device, dtype=torch.float16)
+    with _Prof("conv_first", 16.0 * n * H * W * 64):
+        check(_lib.lib().mage_patch_rows_split_f32(_p(_f32(x_nchw)), _p(out), n * H * W * 64, n, C, H, W, kw, pad, _stream()),
+              "mage_patch_rows_split_f32")
+    return out
+
+
 def embedding_split(idx: torch.Tensor, table: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """idx int64 [...], table split [2, K, C] -> split [2, ..., C]."""
     assert idx.dtype == torch.int64 and idx.is_contiguous()

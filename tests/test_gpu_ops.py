@@ -275,8 +275,13 @@ def test_temporal_attention_with_kv_cache(impl):
         K = torch.stack([s[:, C:2 * C] for s in steps[:p + 1]], 1).view(M, p + 1, H, 32).transpose(1, 2)
         V = torch.stack([s[:, 2 * C:] for s in steps[:p + 1]], 1).view(M, p + 1, H, 32).transpose(1, 2)
         _close(out.view(M, H, 1, 32), _sdpa(q, K, V), 1e-5, 1e-5)
-    assert torch.equal(kc[:, 3].cpu(), steps[3][:, C:2 * C])
-    assert torch.equal(vc[:, L - 1].cpu(), steps[L - 1][:, 2 * C:])
+    if impl == "tma":   # cache layout of the TMA-staged kernel: [M][2 head-halves][L][256]
+        k4, v4 = kc.view(M, 2, L, C // 2).cpu(), vc.view(M, 2, L, C // 2).cpu()
+        assert torch.equal(torch.cat([k4[:, 0, 3], k4[:, 1, 3]], 1), steps[3][:, C:2 * C])
+        assert torch.equal(torch.cat([v4[:, 0, L - 1], v4[:, 1, L - 1]], 1), steps[L - 1][:, 2 * C:])
+    else:
+        assert torch.equal(kc[:, 3].cpu(), steps[3][:, C:2 * C])
+        assert torch.equal(vc[:, L - 1].cpu(), steps[L - 1][:, 2 * C:])
 
 
 def test_mha_cross_attention_long_query():

@@ -252,3 +252,29 @@ def test_conv2d_tc_halo_geometries(n, H, W, Cin, Cout, k, pad, tile_cfg):
     want = F.relu(want).permute(0, 2, 3, 1)
     _close(out, want, RTOL * max(1.0, k * k * Cin / 2048))
     ops.check_flag(DEV)
+
+
+@pytest.mark.parametrize("n,C,H,W,k", [(2, 3, 128, 128, 7), (3, 1, 32, 16, 5), (1, 3, 16, 8, 3)])
+def test_first_conv_as_im2row_plus_column_conv(n, C, H, W, k, tile_cfg):
+    """encoder.0 (vqvae_model.py:193: Conv2d(C, dim, 7, padding=3) on a planar image) as mage_patch_rows_split_f32 followed by a
+    kx1 tensor-core convolution over 64 im2row channels."""
+    ops = _ops()
+    if "nohalo" in tile_cfg and 128 % W != 0:
+        pytest.skip("per-tap-box kernel tiles rows of 128 / W pixels")
+    Cout = 256
+    x = _rand(n, C, H, W, seed=1)
+    w = _rand(Cout, C, k, k, seed=2, scale=(k * k * C) ** -0.5)
+    b = _rand(Cout, seed=3)
+    rows = ops.patch_rows_split(x.to(DEV), k, k // 2)
+    want_rows = torch.zeros(n, H, W, 64, dtype=torch.float64)
+    xp = F.pad(x.double(), (k // 2, k // 2))
+    for kx in range(k):
+        for c in range(C):
+            want_rows[..., kx * C + c] = xp[:, c, :, kx:kx + W]
+    _close(_unsplit(rows), want_rows, rtol=2.0 ** -22)
+    w2 = torch.zeros(Cout, k, 1, 64)
+    w2[:, :, 0, : k * C] = w.permute(0, 2, 3, 1).reshape(Cout, k, k * C)
+    out, _, spr = ops.conv2d_tc(rows, ops.split(w2.to(DEV)), b.to(DEV), pad=(k // 2, 0), want=("f32", "split_relu"))
+    want = F.conv2d(x.double(), w.double(), b.double(), padding=k // 2).permute(0, 2, 3, 1)
+    _close(out, want)
+    _close(_unsplit(spr), F.relu(want))

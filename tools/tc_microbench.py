@@ -71,7 +71,20 @@ def main():
         ms = timeit(fn, args.iters, flush)
         rows.append((name, 2.0 * n * H * H * Cout * k * k * Cin / ms / 1e9, ms))
 
+    def head_case(name, n, H):
+        x = ops.split(torch.randn(n, H, H, 64, generator=g).to(DEV))
+        w = ops.split((torch.randn(256, 3, 3, 64, generator=g) * 576 ** -0.5).to(DEV))
+        b = torch.randn(256, generator=g).to(DEV)
+        r = torch.randn(n, H // 2, H // 2, 256, generator=g).to(DEV)
+        hw, hb = (torch.randn(3, 256, generator=g) / 16).to(DEV), torch.randn(3, generator=g).to(DEV)
+        out = torch.empty(n, 3, H, H, device=DEV)
+        fn = lambda: ops.conv2d_tc_pixel_head(x, w, b, pad=(1, 1), residual=r, res_mode=2, head_w=hw, head_b=hb, out=out,
+                                              out_img_stride=3 * H * H)
+        ms = timeit(fn, args.iters, flush)
+        rows.append((name, 2.0 * n * H * H * 256 * 576 / ms / 1e9, ms))
+
     cases = [
+        ("pixel head 128x128 64->256->3", lambda: head_case("pixel head 128x128 64->256->3", 64, 128)),
         ("qkv 16384x1536x512 f32", lambda: gemm_case("qkv 16384x1536x512 f32", M, 1536, 512, "f32")),
         ("outproj 16384x512x512 res", lambda: gemm_case("outproj 16384x512x512 res", M, 512, 512, "res")),
         ("fc 16384x2048x512 split", lambda: gemm_case("fc 16384x2048x512 split", M, 2048, 512, "split")),
