@@ -149,6 +149,7 @@ def run_cuda(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("MAGE_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     os.environ["MAGE_BACKEND"] = args.backend
     B, L = args.batch, args.frames
@@ -202,9 +203,9 @@ def run_cuda(args, rank, world, local_rank):
     hb = {"images": host["images"], "text": host["text"], "speed": host["speed"]}
 
     def step_e2e():
-        video = model.autoregressive_generate(hb, noise=noise_h)
-        out_host.copy_(video, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        # public API: pinned host inputs -> H2D -> generate -> the clip back on the host (frames stream out as they are decoded)
+        video = model.autoregressive_generate(hb, noise=noise_h, to_host=True)
+        assert not video.is_cuda and tuple(video.shape) == tuple(out_host.shape)
 
     step_e2e()
     barrier()
@@ -224,11 +225,13 @@ def run_cuda(args, rank, world, local_rank):
     roof = None
     if rank == 0:
         eng.use_cuda_graph = False
+        overlap, eng.overlap_decode = eng.overlap_decode, False   # per-kernel durations are taken with the launches serialised
         ops.PROFILE = []
         step_resident()
         torch.cuda.synchronize()
         prof, ops.PROFILE = ops.PROFILE, None
         eng.use_cuda_graph = True
+        eng.overlap_decode = overlap
         agg = {}
         for kind, flops, a, b in prof:
             d = agg.setdefault(kind, [0.0, 0.0, 0])
@@ -273,7 +276,7 @@ def run_cuda(args, rank, world, local_rank):
                 "config": {"workload": f"CATER-GEN-v2 128x128x{L}, batch {B} per GPU (BASELINE.json configs[4])", "family": FAMILY,
                            "frames_length": L, "batch_per_gpu": B, "global_batch": B * world, "text_len": TEXT_LEN,
                            "parallelism": f"prompt-shard x{world}, no data-path collective", "backend": args.backend,
-                           "cuda_graph": True,
+                           "cuda_graph": True, "decode_overlap_stream": bool(eng.overlap_decode),
                            "l2": "working set >> L2 (K/V cache %.1f GB, decoder activations >1 GB per tensor); no explicit flush" %
                                  (2 * 2 * B * 256 * L * 512 * 4 / 1e9)},
                 "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

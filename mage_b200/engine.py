@@ -362,6 +362,11 @@ class SamplerEngine:
         self.n_head = self.C // 32
         self._graphs = {}
         self.kernels_per_generate = None
+        # The VQ-VAE decode of frame j depends only on that frame's tokens and nothing downstream depends on it, so it runs on a
+        # side stream next to transformer step j+1: the tails / launch gaps of one kernel sequence are filled by the other.
+        self.overlap_decode = os.environ.get("MAGE_OVERLAP_DECODE", "0") != "0"   # measured: no gain on B200 (154.2 vs 154.4 ms), off by default
+        self._side = None
+        self._copy = None
         if self.backend == "tc":
             # split (fp16 hi/lo) copies of the per-step tensor-core operands
             ws = {"E": ops.split(self.E), "Wc": ops.split(self.Wc)}
@@ -565,13 +570,17 @@ class SamplerEngine:
     # ------------------------------------------------------------------ whole path
     def _generate_impl(self, images0: torch.Tensor, text: torch.Tensor, speed: Optional[torch.Tensor],
                        noise: Optional[torch.Tensor], video: torch.Tensor, tokens: torch.Tensor, tok0_out: torch.Tensor,
-                       trace: Optional[dict] = None) -> None:
-        """images0 [B,Cimg,Himg,Wimg]; text i64 [B,T]; video [B,L,Cimg,Himg,Wimg] (frames 1.. written);
+                       trace: Optional[dict] = None, host_video: Optional[torch.Tensor] = None) -> None:
+        """images0 [B,Cimg,Himg,Wimg]; text i64 [B,T]; video FRAME-MAJOR [L,B,Cimg,Himg,Wimg] (frame 0 = images0, each generated
+        frame of the whole batch is one contiguous block); host_video: optional pinned host tensor of the same shape that
+        receives every frame over a copy stream as soon as it is decoded (the D2H overlaps the following steps);
         tokens i64 [L-1, B, R*R] (step-major); tok0_out i64 [B, R*R]."""
         sd, C, R, L = self.sd, self.C, self.R, self.L
         B, T = text.shape
         M = B * R * R
         p = "generate_model."
+        video[0].copy_(images0)   # output frame 0 is the raw input frame (mage_model.py:691)
+        self._frame_to_host(video, host_video, 0)
         z = self.vq.encode_features(images0)
         ops.vq_argmin(z.view(M, -1), self.vq.codebook, out=tok0_out.view(-1))
         tc = self.backend == "tc"
@@ -606,7 +615,7 @@ class SamplerEngine:
         for i in range(self.n_blocks):
             x = self._block_step_tc(i, x, 0, B, caches, bufs, False) if tc else self._block_step(i, x, 0, B, caches)
         tok = tok0_out
-        img_elems = video.shape[2] * video.shape[3] * video.shape[4]
+        img_elems = video.shape[2] * video.shape[3] * video.shape[4]   # frame-major video: images of one frame are adjacent
         logits = torch.empty(M, sd[p + "out.weight"].shape[0], device=self.device, dtype=torch.float32)
         for j in range(L - 1):
             if tc:
@@ -625,11 +634,42 @@ class SamplerEngine:
             if trace is not None:
                 trace.setdefault("logits", []).append(logits.clone())
             # decode this frame for every sample: video[b, j+1]
-            self.vq.decode_into(tok.view(B, R, R), video[:, j + 1], L * img_elems)
+            if self.overlap_decode and trace is None:
+                main = torch.cuda.current_stream()
+                if self._side is None:
+                    self._side = torch.cuda.Stream(device=self.device)
+                ready = torch.cuda.Event()
+                ready.record(main)
+                self._side.wait_event(ready)
+                with torch.cuda.stream(self._side):
+                    self.vq.decode_into(tok.view(B, R, R), video[j + 1], img_elems)
+                    self._frame_to_host(video, host_video, j + 1)
+            else:
+                self.vq.decode_into(tok.view(B, R, R), video[j + 1], img_elems)
+                self._frame_to_host(video, host_video, j + 1)
+        if self.overlap_decode and trace is None and self._side is not None:
+            torch.cuda.current_stream().wait_stream(self._side)   # join (also required before a graph capture ends)
+        if host_video is not None:
+            torch.cuda.current_stream().wait_stream(self._copy)
+
+    def _frame_to_host(self, video: torch.Tensor, host_video: Optional[torch.Tensor], f: int) -> None:
+        """Queue the D2H copy of frame f (one contiguous [B,C,H,W] block) on the copy stream, after the work queued so far."""
+        if host_video is None:
+            return
+        cur = torch.cuda.current_stream()
+        if self._copy is None:
+            self._copy = torch.cuda.Stream(device=self.device)
+        done = torch.cuda.Event()
+        done.record(cur)
+        self._copy.wait_event(done)
+        with torch.cuda.stream(self._copy):
+            host_video[f].copy_(video[f], non_blocking=True)
 
     def generate(self, images0: torch.Tensor, text: torch.Tensor, speed: Optional[torch.Tensor] = None,
-                 noise: Optional[torch.Tensor] = None, trace: Optional[dict] = None):
-        """Returns (video [B,L,C,H,W] with frame 0 = images0, tokens i64 [B,L-1,R,R], tok0 i64 [B,R,R])."""
+                 noise: Optional[torch.Tensor] = None, trace: Optional[dict] = None, to_host: bool = False):
+        """Returns (video [B,L,C,H,W] with frame 0 = images0, tokens i64 [B,L-1,R,R], tok0 i64 [B,R,R]).  The video is a view of a
+        frame-major buffer that the next call overwrites.  to_host=True: the video comes back as a pinned HOST tensor, every
+        frame having been copied out while later frames were still being generated (the call returns synchronised)."""
         assert images0.is_cuda and text.is_cuda and text.dtype == torch.int64
         if self.randomness:
             assert noise is not None, "randomness=True needs the N(0,1) noise [B,64,R,R] (drawn by the caller on the CPU, mage_model.py:661)"
@@ -639,21 +679,24 @@ class SamplerEngine:
         R, L = self.R, self.L
         images0 = images0.contiguous().float()
         if not self.use_cuda_graph or trace is not None:
-            video = torch.empty(B, L, *images0.shape[1:], device=self.device, dtype=torch.float32)
+            video = torch.empty(L, B, *images0.shape[1:], device=self.device, dtype=torch.float32)
+            host = torch.empty(L, B, *images0.shape[1:], dtype=torch.float32, pin_memory=True) if to_host else None
             tokens = torch.empty(L - 1, B, R * R, device=self.device, dtype=torch.int64)
             tok0 = torch.empty(B, R * R, device=self.device, dtype=torch.int64)
             n0 = ops.launch_count()
-            self._generate_impl(images0, text, speed, noise, video, tokens, tok0, trace)
+            self._generate_impl(images0, text, speed, noise, video, tokens, tok0, trace, host)
             self.kernels_per_generate = ops.launch_count() - n0
-            video[:, 0].copy_(images0)
             if self.backend == "tc":
                 ops.check_flag(self.device)
-            return video, tokens.permute(1, 0, 2).reshape(B, L - 1, R, R), tok0.view(B, R, R)
+            if to_host:
+                torch.cuda.current_stream().synchronize()
+                video = host
+            return video.permute(1, 0, 2, 3, 4), tokens.permute(1, 0, 2).reshape(B, L - 1, R, R), tok0.view(B, R, R)
 
-        key = (B, T, tuple(images0.shape[1:]), speed is not None, noise is not None)
+        key = (B, T, tuple(images0.shape[1:]), speed is not None, noise is not None, to_host)
         st = self._graphs.get(key)
         if st is None:
-            st = self._capture(key, images0, text, speed, noise)
+            st = self._capture(key, images0, text, speed, noise, to_host)
         st["images0"].copy_(images0)
         st["text"].copy_(text)
         if speed is not None:
@@ -661,23 +704,26 @@ class SamplerEngine:
         if noise is not None:
             st["noise"].copy_(noise)
         st["graph"].replay()
-        video = st["video"]
-        video[:, 0].copy_(st["images0"])
         if self.backend == "tc":
             ops.check_flag(self.device)  # loud failure if an operand left the fp16 split range (syncs)
-        return video, st["tokens"].permute(1, 0, 2).reshape(B, L - 1, R, R), st["tok0"].view(B, R, R)
+        video = st["video"]
+        if to_host:
+            torch.cuda.current_stream().synchronize()
+            video = st["host_video"]
+        return video.permute(1, 0, 2, 3, 4), st["tokens"].permute(1, 0, 2).reshape(B, L - 1, R, R), st["tok0"].view(B, R, R)
 
-    def _capture(self, key, images0, text, speed, noise):
+    def _capture(self, key, images0, text, speed, noise, to_host=False):
         B, T = text.shape
         R, L = self.R, self.L
         dev = self.device
         st = dict(images0=images0.clone(), text=text.clone(),
                   speed=speed.clone() if speed is not None else None,
                   noise=noise.clone() if noise is not None else None,
-                  video=torch.empty(B, L, *images0.shape[1:], device=dev, dtype=torch.float32),
+                  video=torch.empty(L, B, *images0.shape[1:], device=dev, dtype=torch.float32),
+                  host_video=torch.empty(L, B, *images0.shape[1:], dtype=torch.float32, pin_memory=True) if to_host else None,
                   tokens=torch.empty(L - 1, B, R * R, device=dev, dtype=torch.int64),
                   tok0=torch.empty(B, R * R, device=dev, dtype=torch.int64))
-        args = (st["images0"], st["text"], st["speed"], st["noise"], st["video"], st["tokens"], st["tok0"])
+        args = (st["images0"], st["text"], st["speed"], st["noise"], st["video"], st["tokens"], st["tok0"], None, st["host_video"])
         # warm-up on a side stream (sets kernel attributes, fills the allocator), then capture
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())

@@ -241,11 +241,12 @@ class MAGE(_EngineOwner):
         return out.view(*x.shape[:2], *out.shape[1:])
 
     @torch.no_grad()
-    def autoregressive_generate(self, batch, noise: Optional[torch.Tensor] = None):
+    def autoregressive_generate(self, batch, noise: Optional[torch.Tensor] = None, to_host: bool = False):
         """mage_model.py:641-693.  batch: 'images' [B,>=1,C,H,W] (frame 0 read), 'text' i64 [B,T], optional
         'speed' [B].  Returns [B, frames_length, C, H, W]; frame 0 is the input frame.  With
         randomness=True the N(0,1) noise [B,64,h,w] is drawn like the reference does -- on the CPU
-        default generator -- unless passed explicitly."""
+        default generator -- unless passed explicitly.  to_host=True (additive): the clip is returned as a pinned host
+        tensor whose frames were copied out while later frames were still being generated; it is valid until the next call."""
         eng = self.engine()
         dev = eng.device
         images0 = batch["images"][:, 0].to(dev, non_blocking=True)
@@ -255,8 +256,10 @@ class MAGE(_EngineOwner):
             if noise is None:
                 noise = torch.randn([text.shape[0], 64, self.image_resolution, self.image_resolution])
             noise = noise.to(dev, non_blocking=True).float().contiguous()
-        video, tokens, tok0 = eng.generate(images0, text, speed, noise)
+        video, tokens, tok0 = eng.generate(images0, text, speed, noise, to_host=to_host)
         self.last_tokens, self.last_tok0 = tokens, tok0
+        if to_host:
+            return video
         # the engine's buffers are reused by the next call (CUDA graph); the reference hands out a fresh
         # tensor that its caller clamps in place (main_mage.py:242)
         return video.clone()

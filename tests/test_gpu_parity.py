@@ -179,3 +179,20 @@ def test_state_dict_round_trip_and_module_prefix():
     batch = syn.make_batch(params, 1, seed=9, text_len=9)
     cu = {k: v.to("cuda") for k, v in batch.items()}
     assert torch.equal(model.autoregressive_generate(cu), model2.autoregressive_generate(cu))
+
+
+def test_streamed_host_output_equals_device_output():
+    """autoregressive_generate(..., to_host=True) returns the clip in pinned host memory (frames copied out while later frames
+    are generated): same values as the device tensor, frame 0 = the raw input frame (mage_model.py:691), on graph replay too."""
+    params = syn.model_params("caterv2", frames_length=4)
+    sd = syn.make_mage_state_dict(params)
+    model = _build(params, sd)
+    batch = syn.make_batch(params, 3, seed=77, text_len=10)
+    noise = syn.make_noise(3, seed=5)
+    cu = lambda d: {k: v.to("cuda") for k, v in d.items()}
+    dev = model.autoregressive_generate(cu(batch), noise=noise)
+    for _ in range(2):   # capture, then replay
+        host = model.autoregressive_generate(cu(batch), noise=noise, to_host=True)
+        assert not host.is_cuda and host.is_pinned() and tuple(host.shape) == tuple(dev.shape)
+        assert torch.equal(host, dev.cpu())
+    assert torch.equal(host[:, 0], batch["images"][:, 0])
