@@ -264,6 +264,30 @@ def run_cuda(args, rank, world, local_rank):
                 "how": "sum of algorithmic FLOPs / sum of CUDA-event durations over every launch of the kernel class in one eager step; "
                        "own_ceiling_frac counts the 3 MMAs issued per product"}
 
+    eager = None
+    overlap_flag = bool(eng.overlap_decode)
+    if rank == 0 and args.eager_gpu > 0:
+        # context for the >=10x target of BASELINE.json: the reference algorithm (reference evaluation order, no KV cache) as
+        # plain PyTorch eager ops on this same GPU, PyTorch's default precision flags, at a reduced batch (it is O(L^2))
+        from oracle import mage_oracle as orc
+        overlap_flag = bool(eng.overlap_decode)
+        del eng
+        model._engine = None
+        torch.cuda.empty_cache()
+        Be = args.eager_gpu
+        sd_d = {k: v.to(dev) for k, v in sd.items()}
+        eb = {k: v.to(dev) for k, v in syn.make_batch(params, Be, seed=4321, text_len=TEXT_LEN).items()}
+        en = syn.make_noise(Be, seed=7).to(dev)
+        with torch.no_grad():
+            orc.generate(sd_d, {k: v[:1] for k, v in eb.items()}, en[:1])
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            orc.generate(sd_d, eb, en)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        eager = {"value": round(Be * (L - 1) / dt, 2), "unit": UNIT, "batch": Be, "seconds": round(dt, 3),
+                 "kind": "port of the reference algorithm (every step recomputes all L positions), torch eager on the same GPU"}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         v, info = cpu_reference_sample(os.cpu_count() or 1, ar_iters=args.ref_iters)
@@ -276,12 +300,14 @@ def run_cuda(args, rank, world, local_rank):
                 "config": {"workload": f"CATER-GEN-v2 128x128x{L}, batch {B} per GPU (BASELINE.json configs[4])", "family": FAMILY,
                            "frames_length": L, "batch_per_gpu": B, "global_batch": B * world, "text_len": TEXT_LEN,
                            "parallelism": f"prompt-shard x{world}, no data-path collective", "backend": args.backend,
-                           "cuda_graph": True, "decode_overlap_stream": bool(eng.overlap_decode),
+                           "cuda_graph": True, "decode_overlap_stream": overlap_flag,
                            "l2": "working set >> L2 (K/V cache %.1f GB, decoder activations >1 GB per tensor); no explicit flush" %
                                  (2 * 2 * B * 256 * L * 512 * 4 / 1e9)},
                 "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(kernels_per_step * args.steps), "kernels_per_step": int(kernels_per_step),
                 "roofline": roof, "cpu_baseline": cpu, "clocks": clocks}
+        if eager is not None:
+            line["eager_gpu_baseline"] = eager
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -299,6 +325,8 @@ def main():
                     help="tc: tcgen05 tensor cores on split-fp16 operands (fp32-grade); simt: fp32 FFMA kernels")
     ap.add_argument("--ref-iters", type=int, default=3, help="AR iterations timed per CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--eager-gpu", type=int, default=0, metavar="B",
+                    help="also time the reference algorithm as torch eager ops on this GPU at batch B (context only, off by default)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -172,7 +172,7 @@ def text_encoder(sd: SD, text: torch.Tensor, padding_idx: int = 0) -> torch.Tens
     n_head = width // 32
     B, T = text.shape
     text_length = (text != padding_idx).float().sum(-1)
-    pos = torch.arange(T, dtype=text.dtype).unsqueeze(0).expand(B, T)
+    pos = torch.arange(T, dtype=text.dtype, device=text.device).unsqueeze(0).expand(B, T)
     x = F.embedding(text, sd[p + "token_embedding.weight"], padding_idx=padding_idx)
     x = _ln(sd, p + "layer_norm", x + F.embedding(pos, sd[p + "positions.weight"]), eps=1e-8)
     x = x * (text != padding_idx).unsqueeze(-1).type(x.dtype)
@@ -236,7 +236,7 @@ def flat_axial_decoder(sd: SD, motion: torch.Tensor, imgs: torch.Tensor, return_
     Lmax = sd[p + "T_positional_embedding"].shape[0]
     assert x.shape[1] == Lmax, "reference adds the full T_positional_embedding (needs F == frames_length-1)"
     x = x + sd[p + "T_positional_embedding"]
-    mask = torch.full((Lmax, Lmax), float("-inf")).triu_(1)  # mage_model.py:367-372
+    mask = torch.full((Lmax, Lmax), float("-inf")).triu_(1).to(x.device)  # mage_model.py:367-372 (built on the CPU, moved in attention(), :32)
     i = 0
     while (p + f"blocks.{i}.ln_1.weight") in sd:
         x = axial_block(sd, p + f"blocks.{i}", x, i % 3 + 1, mask if i % 3 == 0 else None)
