@@ -252,7 +252,8 @@ def run_cuda(args, rank, world, local_rank):
         if os.path.isfile(tp):
             traffic = json.load(open(tp)).get("gemm_bytes_per_launch")
         roof = {"bound": "tensor", "kernel": "dense GEMM (axial-block linears: QKV, out-proj, MLP, head) -- " +
-                ("tcgen05.mma kind::f16 on fp16 hi/lo split operands, 3 MMAs per product (fp32-grade)" if args.backend == "tc" else "fp32 FFMA"),
+                ("tc_gemm_kernel<128,2>: CTA-pair 256x128 tiles (tcgen05 cta_group::2), kind::f16 MMAs on fp16 hi/lo split operands, "
+                 "3 MMAs per product (fp32-grade), TMA loads + TMA-store epilogue" if args.backend == "tc" else "fp32 FFMA"),
                 "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4), "traffic": traffic,
                 "peak_source": how + ", dense bf16 sustained; token parity needs fp32-grade GEMMs: 3 fp16 MMAs per product, so the kernel's own ceiling is peak/3",
                 "launches_per_step": g[2], "gflop_per_launch_avg": round(g[0] / g[2] / 1e9, 3), "ms_in_kernel_per_step": round(g[1], 2),
