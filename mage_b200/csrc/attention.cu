@@ -109,6 +109,8 @@ struct AxialArgs {
 };
 
 __global__ void __launch_bounds__(AX_WARPS * 32) axial_attn_kernel(const AxialArgs p) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ __align__(16) float sq[AX_WARPS][AX_S * AX_QLD];
   __shared__ __align__(16) float sk[AX_WARPS][AX_S * AX_D];
   __shared__ __align__(16) float sv[AX_WARPS][AX_S * AX_D];
@@ -248,6 +250,7 @@ __global__ void __launch_bounds__(256) temporal_attn_kernel(const float* __restr
                                                             float* __restrict__ vcache, float* __restrict__ out,
                                                             __half* __restrict__ split, int64_t split_plane, int* flag,
                                                             int pos, int Lmax, float scale) {
+  pdl_launch_dependents();
   extern __shared__ __align__(128) float smem[];
   float* Ks = smem;                       // [pos+1][256]: sized to the live prefix so early steps fit more CTAs per SM
   float* Vs = smem + (size_t)(pos + 1) * TA_HALF;
@@ -267,6 +270,7 @@ __global__ void __launch_bounds__(256) temporal_attn_kernel(const float* __restr
     mbar_init(&bars[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  pdl_wait();   // the preceding grid (this step's QKV GEMM) has completed before anything global is touched
   __syncthreads();
   if (tid == 0 && pos > 0) {
     const uint32_t bytes = (uint32_t)pos * TA_HALF * 4;
@@ -350,7 +354,7 @@ extern "C" int mage_axial_attn_f32(const float* qkv, float* out, void* out_split
   a.line_inner = axis == 1 ? 1 : R;
   a.seq = axis == 1 ? R : 1;
   const int64_t units = (int64_t)a.n_lines * n_head;
-  axial_attn_kernel<<<(unsigned)((units + AX_WARPS - 1) / AX_WARPS), AX_WARPS * 32, 0, as_stream(stream)>>>(a);
+  mage_launch_pdl(axial_attn_kernel, (unsigned)((units + AX_WARPS - 1) / AX_WARPS), AX_WARPS * 32, 0, as_stream(stream), 1, a);
   return mage_post_launch();
 }
 
@@ -367,7 +371,7 @@ extern "C" int mage_temporal_attn_step_f32(const float* qkv, float* kcache, floa
     if (e != cudaSuccess) return (int)e;
     configured = smem_max;
   }
-  temporal_attn_kernel<<<(unsigned)M * 2, 256, smem, as_stream(stream)>>>(qkv, kcache, vcache, out, reinterpret_cast<__half*>(out_split),
-                                                                          split_plane, flag, pos, Lmax, scale);
+  mage_launch_pdl(temporal_attn_kernel, (unsigned)M * 2, 256, smem, as_stream(stream), 1, qkv, kcache, vcache, out,
+                  reinterpret_cast<__half*>(out_split), split_plane, flag, pos, Lmax, scale);
   return mage_post_launch();
 }

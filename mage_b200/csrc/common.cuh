@@ -40,5 +40,35 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// Programmatic dependent launch (PDL).  Kernels of the per-step path call pdl_launch_dependents() first thing -- the next
+// kernel's CTAs may then be scheduled as soon as SM resources free up, i.e. its prologue (barrier init, TMEM allocation,
+// descriptor prefetch) and its launch latency overlap this kernel's tail -- and pdl_wait() before their first global-memory
+// access, which blocks until the preceding grid has completed and flushed.  Both are no-ops for a kernel launched without the
+// attribute.  MAGE_PDL=0 launches everything with plain stream order.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+extern int g_mage_pdl;  // defined in misc.cu
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t mage_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x,
+                                          Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (g_mage_pdl) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

@@ -300,6 +300,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                const __grid_constant__ CUtensorMap mapO, const __grid_constant__ CUtensorMap mapS,
                const __grid_constant__ CUtensorMap mapR, const TcParams p) {
   using C = Cfg<BN, CG>;
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -342,6 +343,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  pdl_wait();   // prologue done (barriers, TMEM, descriptor prefetch): now wait for the producer grid of our operands
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (every CTA loads its A rows + its W rows)
@@ -489,6 +491,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   using H = HaloCfg<BN, CG>;
   using C = Cfg<BN, CG>;
   constexpr int SA = HALO_SA, SW = H::SW;
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -529,6 +532,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  pdl_wait();   // prologue done (barriers, TMEM, descriptor prefetch): now wait for the producer grid of our operands
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -683,6 +687,8 @@ __global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ x,
 __global__ void __launch_bounds__(256) embedding_split_kernel(const int64_t* __restrict__ idx, const __half* __restrict__ table,
                                                               int64_t table_plane, __half* __restrict__ out, int64_t out_plane,
                                                               int rows, int C8) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (int64_t)rows * C8 * 2) return;
   const int pl = (int)(t / ((int64_t)rows * C8));
@@ -808,18 +814,9 @@ int launch_tc(const Maps& mp, const TcParams& p, cudaStream_t st) {
   }
   const int tiles = (p.m_tiles / CG) * p.n_tiles;
   const int units = tiles < max_units ? tiles : max_units;
-  if (CG == 1) {
-    tc_gemm_kernel<BN, CG><<<units, NTHREADS, C::SMEM_BYTES, st>>>(mp.A, mp.W, mp.O, mp.S, mp.R, p);
-  } else {
-    cudaLaunchConfig_t cfg{};
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.gridDim = dim3(units * 2); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = st;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, CG>, mp.A, mp.W, mp.O, mp.S, mp.R, p);
-    if (e != cudaSuccess) return (int)e;
-  }
+  cudaError_t e = mage_launch_pdl(tc_gemm_kernel<BN, CG>, dim3(units * CG), dim3(NTHREADS), C::SMEM_BYTES, st, CG, mp.A, mp.W, mp.O, mp.S,
+                                  mp.R, p);
+  if (e != cudaSuccess) return (int)e;
   return mage_post_launch();
 }
 
@@ -895,18 +892,9 @@ int launch_halo(const Maps& mp, const TcParams& p, cudaStream_t st) {
   }
   const int tiles = (p.m_tiles / CG) * p.n_tiles;
   const int units = tiles < max_units ? tiles : max_units;
-  if (CG == 1) {
-    tc_conv_halo_kernel<BN, CG><<<units, NTHREADS, H::SMEM_BYTES, st>>>(mp.A, mp.W, mp.O, mp.S, mp.R, p);
-  } else {
-    cudaLaunchConfig_t cfg{};
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.gridDim = dim3(units * 2); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = H::SMEM_BYTES; cfg.stream = st;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, tc_conv_halo_kernel<BN, CG>, mp.A, mp.W, mp.O, mp.S, mp.R, p);
-    if (e != cudaSuccess) return (int)e;
-  }
+  cudaError_t e = mage_launch_pdl(tc_conv_halo_kernel<BN, CG>, dim3(units * CG), dim3(NTHREADS), H::SMEM_BYTES, st, CG, mp.A, mp.W, mp.O,
+                                  mp.S, mp.R, p);
+  if (e != cudaSuccess) return (int)e;
   return mage_post_launch();
 }
 
@@ -986,8 +974,8 @@ extern "C" int mage_embedding_split(const int64_t* idx, const void* table, int64
                                     int rows, int C, void* stream) {
   MAGE_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0 && aligned16(table) && aligned16(out) && table_plane % 8 == 0 && out_plane % 8 == 0);
   const int64_t total = (int64_t)rows * (C / 8) * 2;
-  embedding_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(
-      idx, reinterpret_cast<const __half*>(table), table_plane, reinterpret_cast<__half*>(out), out_plane, rows, C / 8);
+  mage_launch_pdl(embedding_split_kernel, (unsigned)((total + 255) / 256), 256, 0, as_stream(stream), 1, idx,
+                  reinterpret_cast<const __half*>(table), table_plane, reinterpret_cast<__half*>(out), out_plane, rows, C / 8);
   return mage_post_launch();
 }
 

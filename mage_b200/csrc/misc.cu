@@ -1,8 +1,12 @@
 // Bandwidth-bound helper kernels of the MAGE sampling path: LayerNorm, greedy argmax, embedding
 // gathers, pooling, AdaIN, first/last VQ-VAE layers.  All fp32, channels-last, float4 accesses.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
+// measured on B200: no gain over plain graph launches (157.9 vs 155.9 ms per generate) -> off unless MAGE_PDL=1
+int g_mage_pdl = [] { const char* e = getenv("MAGE_PDL"); return e ? atoi(e) : 0; }();
 int64_t g_mage_launches = 0;
 
 extern "C" int mage_abi_version(void) { return 3; }
@@ -17,6 +21,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ beta, float* __restrict__ out,
                                                         __half* __restrict__ split, int64_t plane, int* flag,
                                                         int rows, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int C = NV * 128;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -63,6 +69,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 // ------------------------------------------------------------------ argmax over rows
 __global__ void __launch_bounds__(256) argmax_rows_kernel(const float* __restrict__ x, int64_t ldx,
                                                           int64_t* __restrict__ idx, int rows, int N) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -320,10 +328,10 @@ extern "C" int mage_layernorm_f32(const float* in, const float* gamma, const flo
   cudaStream_t st = as_stream(stream);
   __half* sp = reinterpret_cast<__half*>(out_split);
   switch (C / 128) {
-    case 1: layernorm_kernel<1><<<g, 256, 0, st>>>(in, gamma, beta, out, sp, split_plane, flag, rows, eps); break;
-    case 2: layernorm_kernel<2><<<g, 256, 0, st>>>(in, gamma, beta, out, sp, split_plane, flag, rows, eps); break;
-    case 4: layernorm_kernel<4><<<g, 256, 0, st>>>(in, gamma, beta, out, sp, split_plane, flag, rows, eps); break;
-    case 8: layernorm_kernel<8><<<g, 256, 0, st>>>(in, gamma, beta, out, sp, split_plane, flag, rows, eps); break;
+    case 1: mage_launch_pdl(layernorm_kernel<1>, g, 256, 0, st, 1, in, gamma, beta, out, sp, split_plane, flag, rows, eps); break;
+    case 2: mage_launch_pdl(layernorm_kernel<2>, g, 256, 0, st, 1, in, gamma, beta, out, sp, split_plane, flag, rows, eps); break;
+    case 4: mage_launch_pdl(layernorm_kernel<4>, g, 256, 0, st, 1, in, gamma, beta, out, sp, split_plane, flag, rows, eps); break;
+    case 8: mage_launch_pdl(layernorm_kernel<8>, g, 256, 0, st, 1, in, gamma, beta, out, sp, split_plane, flag, rows, eps); break;
     default: return MAGE_EINVAL;
   }
   return mage_post_launch();
@@ -331,7 +339,7 @@ extern "C" int mage_layernorm_f32(const float* in, const float* gamma, const flo
 
 extern "C" int mage_argmax_rows_f32(const float* x, int64_t ldx, int64_t* idx, int rows, int N, void* stream) {
   MAGE_CHECK_ARG(rows > 0 && N > 0);
-  argmax_rows_kernel<<<(rows + 7) / 8, 256, 0, as_stream(stream)>>>(x, ldx, idx, rows, N);
+  mage_launch_pdl(argmax_rows_kernel, (rows + 7) / 8, 256, 0, as_stream(stream), 1, x, ldx, idx, rows, N);
   return mage_post_launch();
 }
 

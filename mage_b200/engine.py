@@ -367,6 +367,9 @@ class SamplerEngine:
         self.overlap_decode = os.environ.get("MAGE_OVERLAP_DECODE", "0") != "0"   # measured: no gain on B200 (154.2 vs 154.4 ms), off by default
         self._side = None
         self._copy = None
+        # frames are decoded in groups of `decode_group` steps (one VQ-VAE decoder pass over group*B images): the low-resolution
+        # decoder layers are too small to fill 148 SMs at B images, and a frame's pixels are not needed before the call returns
+        self.decode_group = max(1, int(os.environ.get("MAGE_DECODE_GROUP", "4")))
         if self.backend == "tc":
             # split (fp16 hi/lo) copies of the per-step tensor-core operands
             ws = {"E": ops.split(self.E), "Wc": ops.split(self.Wc)}
@@ -633,20 +636,25 @@ class SamplerEngine:
             tok = ops.argmax_rows(logits, out=tokens[j].view(-1))
             if trace is not None:
                 trace.setdefault("logits", []).append(logits.clone())
-            # decode this frame for every sample: video[b, j+1]
-            if self.overlap_decode and trace is None:
-                main = torch.cuda.current_stream()
-                if self._side is None:
-                    self._side = torch.cuda.Stream(device=self.device)
-                ready = torch.cuda.Event()
-                ready.record(main)
-                self._side.wait_event(ready)
-                with torch.cuda.stream(self._side):
-                    self.vq.decode_into(tok.view(B, R, R), video[j + 1], img_elems)
-                    self._frame_to_host(video, host_video, j + 1)
-            else:
-                self.vq.decode_into(tok.view(B, R, R), video[j + 1], img_elems)
-                self._frame_to_host(video, host_video, j + 1)
+            # decode the finished group of frames for every sample: video[j0+1 .. j+1] (frame-major, contiguous)
+            if (j + 1) % self.decode_group == 0 or j == L - 2:
+                j0 = (j // self.decode_group) * self.decode_group
+                toks = tokens[j0:j + 1].view(-1, R, R)            # [(j-j0+1)*B, R, R], frame-major like the video buffer
+                if self.overlap_decode and trace is None:
+                    main = torch.cuda.current_stream()
+                    if self._side is None:
+                        self._side = torch.cuda.Stream(device=self.device)
+                    ready = torch.cuda.Event()
+                    ready.record(main)
+                    self._side.wait_event(ready)
+                    with torch.cuda.stream(self._side):
+                        self.vq.decode_into(toks, video[j0 + 1], img_elems)
+                        for f in range(j0 + 1, j + 2):
+                            self._frame_to_host(video, host_video, f)
+                else:
+                    self.vq.decode_into(toks, video[j0 + 1], img_elems)
+                    for f in range(j0 + 1, j + 2):
+                        self._frame_to_host(video, host_video, f)
         if self.overlap_decode and trace is None and self._side is not None:
             torch.cuda.current_stream().wait_stream(self._side)   # join (also required before a graph capture ends)
         if host_video is not None:
