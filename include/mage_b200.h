@@ -91,6 +91,9 @@ int mage_tc_tuning(int bn, int pair);
  * tile is fetched once per 64-channel block and shared by all taps through shifted shared-memory descriptors); 0: every tap
  * re-fetches its own box.  Same results either way (same k order). */
 int mage_tc_conv_halo(int enable);
+/* N-split 256-wide CTA-pair tiles of mage_gemm_tc (two 128-column halves with separate TMEM accumulators and barriers):
+ * 0 never, 1 automatic (default), 2 whenever the shape allows (N % 256 == 0, even row-tile count). */
+int mage_tc_nsplit(int mode);
 
 /* out(split)[r, :] = split(relu?(x[r, :])); x row stride ldx (elements), C % 4 == 0. */
 int mage_split_f32(const float* x, int64_t ldx, void* out, int64_t plane, int rows, int C, int relu, int* flag,

@@ -25,6 +25,7 @@ SIGNATURES = {
     "mage_conv2d_nhwc_f32": [_c_f] * 5 + [_i] * 22 + [_i64, _c_f],
     "mage_tc_tuning": [_i, _i],
     "mage_tc_conv_halo": [_i],
+    "mage_tc_nsplit": [_i],
     "mage_split_f32": [_c_f, _i64, _c_f, _i64, _i, _i, _i, _c_f, _c_f],
     "mage_patch_rows_split_f32": [_c_f, _c_f, _i64, _i, _i, _i, _i, _i, _i, _c_f],
     "mage_embedding_split": [_c_f, _c_f, _i64, _c_f, _i64, _i, _i, _c_f],

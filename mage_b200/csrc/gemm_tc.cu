@@ -99,7 +99,10 @@ __device__ __forceinline__ float act_fn(float x) {
 // No per-row global address arithmetic and no transposes: the k loops on this path are short (K = 512..1152), so the
 // epilogue's instruction count is what paces the kernel (ncu: ~2200 instructions per warp and tile before this form).
 // Rows beyond M are clipped by TMA.
-template <int BN, int CG, int ACT, bool HEAD = false>
+// NS ("N-split", BN = 256 pair tiles): the tile's two 128-column halves are separate accumulators [main_h | corr_h] with their
+// own full/empty barriers; epilogue warp (quadrant, hw) drains half hw, so the MMA issuer can start the next tile's half 0
+// while half 1 is still being drained -- a 256-wide tile (A fetched once per 256 output columns) without giving up overlap.
+template <int BN, int CG, int ACT, bool HEAD = false, bool NS = false>
 __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorMap* mapO, const CUtensorMap* mapS,
                                               const CUtensorMap* mapR, uint32_t tmem_base, uint8_t* staging, uint32_t tfull0,
                                               uint32_t tempty0) {
@@ -135,8 +138,8 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
     const int tile = tile_of(tcount, unit, n_units, p.group);
     if (tile >= num_tiles) break;
     const int mt = (tile / n_tiles) * CG + cta_rank, nt = tile % n_tiles;
-    const int acc = tcount % C::ACC_STAGES;
-    const uint32_t aph = (tcount / C::ACC_STAGES) & 1;
+    const int acc = NS ? half : tcount % C::ACC_STAGES;
+    const uint32_t aph = NS ? (tcount & 1) : (tcount / C::ACC_STAGES) & 1;
     // the thread's row, the warp's store-box origin and the residual offset: once per tile
     const int r = quad * 32 + lane, m = mt * BM + r;
     int sx0 = mt * BM + quad * 32, sy0 = 0, simg = 0, oy = 0, ox = 0;
@@ -159,13 +162,15 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
     if (HEAD && tcount % p.group == 0) hacc[0] = hacc[1] = hacc[2] = 0.f;
     mbar_wait(tfull0 + 8u * acc, aph);
     tc_fence_after();
-    const uint32_t t_main = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 2 * BN, t_corr = t_main + BN;
+    const uint32_t t_main = tmem_base + ((uint32_t)(quad * 32) << 16) + (NS ? half * 256 : acc * 2 * BN);
+    const uint32_t t_corr = t_main + (NS ? 128 : BN);
 #pragma unroll 1
-    for (int c = half; c < BN / 32; c += 2) {
+    for (int c = NS ? half * 4 : half; c < (NS ? half * 4 + 4 : BN / 32); c += NS ? 1 : 2) {
       const int n = nt * BN + c * 32;
+      const int tc_col = NS ? (c & 3) * 32 : c * 32;
       uint32_t rm[32], rc[32];
-      tmem_ld32(t_main + c * 32, rm);
-      tmem_ld32(t_corr + c * 32, rc);
+      tmem_ld32(t_main + tc_col, rm);
+      tmem_ld32(t_corr + tc_col, rc);
       // the residual row segment travels while the TMEM loads complete
       float4 rv[8];
       if (res_off >= 0) {
@@ -173,7 +178,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
         for (int j = 0; j < 8; ++j) rv[j] = __ldg(reinterpret_cast<const float4*>(res + res_off + n) + j);
       }
       tmem_wait_ld();
-      if (c + 2 >= BN / 32) {
+      if (NS ? (c & 3) == 3 : c + 2 >= BN / 32) {
         // this warp's last chunk is in registers: hand the TMEM accumulator stage back before the arithmetic
         tc_fence_before();
         __syncwarp();
@@ -294,7 +299,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
   if (!(amax <= 65504.f) && p.flag) atomicOr(p.flag, 1);
 }
 
-template <int BN, int CG>
+template <int BN, int CG, bool NS = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
                const __grid_constant__ CUtensorMap mapO, const __grid_constant__ CUtensorMap mapS,
@@ -330,7 +335,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 8 * CG);
+      mbar_init(tempty_bar(a), (NS ? 4 : 8) * CG);
     }
     mbar_fence_init();
   }
@@ -361,7 +366,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           c2 = ty * p.Hb - p.pad_y;
           c3 = img;
         }
-        const int w_row = nt * BN + cta_rank * C::W_ROWS;
+        const int w_row = NS ? nt * BN + cta_rank * 64 : nt * BN + cta_rank * C::W_ROWS;   // NS: + h*128 per half
         for (int it = 0; it < p.k_iters; ++it, ++itg) {
           const int s = itg % C::STAGES;
           const uint32_t ph = (itg / C::STAGES) & 1;
@@ -379,7 +384,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             if (elect_one()) {
               if (cta_rank == 0) mbar_expect_tx(full_bar(s), 2 * C::STAGE_BYTES);
               tma_load_5d_2sm(sa, &mapA, fb, a0, a1, a2, c3, 0);
-              tma_load_3d_2sm(sa + C::A_BYTES, &mapW, fb, it * BK, w_row, 0);
+              if (NS) {   // two 64-row boxes: this CTA's share of each 128-column half
+                tma_load_3d_2sm(sa + C::A_BYTES, &mapW, fb, it * BK, w_row, 0);
+                tma_load_3d_2sm(sa + C::A_BYTES + C::W_BYTES / 2, &mapW, fb, it * BK, w_row + 128, 0);
+              } else {
+                tma_load_3d_2sm(sa + C::A_BYTES, &mapW, fb, it * BK, w_row, 0);
+              }
             }
           } else if (elect_one()) {
             mbar_expect_tx(full_bar(s), C::STAGE_BYTES);
@@ -393,7 +403,45 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (the leader CTA; one elected lane issues)
-    if (cta_rank == 0) {
+    if (cta_rank == 0 && NS) {
+      constexpr uint32_t idesc = umma_idesc_f16(128, BM * CG);
+      int itg = 0, tcount = 0;
+      for (;; ++tcount) {
+        if (tile_of(tcount, unit, n_units, p.group) >= num_tiles) break;
+        const uint32_t tph = tcount & 1;
+        for (int it = 0; it < p.k_iters; ++it, ++itg) {
+          const int s = itg % C::STAGES;
+          const uint32_t ph = (itg / C::STAGES) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = base + s * C::STAGE_BYTES;
+          const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + BM * BK * 2);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (it == 0) {   // half h of the previous tile has been drained by both CTAs' epilogue warps
+              mbar_wait(tempty_bar(h), tph ^ 1);
+              tc_fence_after();
+            }
+            const uint32_t wb = sa + C::A_BYTES + h * (C::W_BYTES / 2);
+            const uint64_t w_hi = umma_desc_sw128(wb), w_lo = umma_desc_sw128(wb + 64 * BK * 2);
+            const uint32_t d_main = tmem_base + h * 256, d_corr = d_main + 128;
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < BK / UK; ++k) {
+                const uint64_t adv = (uint64_t)((k * UK * 2) >> 4);
+                const uint32_t accum = (it > 0 || k > 0) ? 1u : 0u;
+                umma_f16_2sm(d_corr, a_lo + adv, w_hi + adv, idesc, accum);
+                umma_f16_2sm(d_corr, a_hi + adv, w_lo + adv, idesc, 1u);
+                umma_f16_2sm(d_main, a_hi + adv, w_hi + adv, idesc, accum);
+              }
+              if (h == 1) umma_commit_2sm(empty_bar(s), 3);
+              if (it + 1 == p.k_iters) umma_commit_2sm(tfull_bar(h), 3);
+            }
+            __syncwarp();
+          }
+        }
+      }
+    } else if (cta_rank == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(BN, BM * CG);
       int itg = 0, tcount = 0;
       for (;; ++tcount) {
@@ -444,11 +492,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       if constexpr (BN == 256 || BN == 128) epilogue_loop<BN, CG, MAGE_ACT_NONE, true>(p, &mapO, &mapS, &mapR, tmem_base, staging, tfull_bar(0), tempty_bar(0));
     } else
     switch (p.act & 0xff) {
-      case MAGE_ACT_NONE: epilogue_loop<BN, CG, MAGE_ACT_NONE>(p, &mapO, &mapS, &mapR, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
-      case MAGE_ACT_RELU: epilogue_loop<BN, CG, MAGE_ACT_RELU>(p, &mapO, &mapS, &mapR, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
-      case MAGE_ACT_QUICKGELU: epilogue_loop<BN, CG, MAGE_ACT_QUICKGELU>(p, &mapO, &mapS, &mapR, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
-      case MAGE_ACT_GELU: epilogue_loop<BN, CG, MAGE_ACT_GELU>(p, &mapO, &mapS, &mapR, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
-      default: epilogue_loop<BN, CG, MAGE_ACT_TANH>(p, &mapO, &mapS, &mapR, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
+      case MAGE_ACT_NONE: epilogue_loop<BN, CG, MAGE_ACT_NONE, false, NS>(p, &mapO, &mapS, &mapR, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
+      case MAGE_ACT_RELU: epilogue_loop<BN, CG, MAGE_ACT_RELU, false, NS>(p, &mapO, &mapS, &mapR, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
+      case MAGE_ACT_QUICKGELU: epilogue_loop<BN, CG, MAGE_ACT_QUICKGELU, false, NS>(p, &mapO, &mapS, &mapR, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
+      case MAGE_ACT_GELU: epilogue_loop<BN, CG, MAGE_ACT_GELU, false, NS>(p, &mapO, &mapS, &mapR, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
+      default: epilogue_loop<BN, CG, MAGE_ACT_TANH, false, NS>(p, &mapO, &mapS, &mapR, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
     }
   }
 
@@ -790,13 +838,13 @@ int make_store_maps(Maps* mp, float* out, void* split, void* split_relu, int64_t
   return 0;
 }
 
-template <int BN, int CG>
+template <int BN, int CG, bool NS = false>
 int launch_tc(const Maps& mp, const TcParams& p, cudaStream_t st) {
   using C = Cfg<BN, CG>;
   static bool configured = false;
   static int max_units = 0;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN, CG, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     max_units = num_sms() / CG;
     if (CG == 2) {
@@ -807,32 +855,38 @@ int launch_tc(const Maps& mp, const TcParams& p, cudaStream_t st) {
       qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
       q.gridDim = dim3(num_sms() & ~1); q.blockDim = dim3(NTHREADS); q.dynamicSmemBytes = C::SMEM_BYTES; q.attrs = qa; q.numAttrs = 1;
       int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, tc_gemm_kernel<BN, CG>, &q) == cudaSuccess && n > 0) max_units = n < max_units ? n : max_units;
+      if (cudaOccupancyMaxActiveClusters(&n, tc_gemm_kernel<BN, CG, NS>, &q) == cudaSuccess && n > 0) max_units = n < max_units ? n : max_units;
       else (void)cudaGetLastError();
     }
     configured = true;
   }
   const int tiles = (p.m_tiles / CG) * p.n_tiles;
   const int units = tiles < max_units ? tiles : max_units;
-  cudaError_t e = mage_launch_pdl(tc_gemm_kernel<BN, CG>, dim3(units * CG), dim3(NTHREADS), C::SMEM_BYTES, st, CG, mp.A, mp.W, mp.O, mp.S,
+  cudaError_t e = mage_launch_pdl(tc_gemm_kernel<BN, CG, NS>, dim3(units * CG), dim3(NTHREADS), C::SMEM_BYTES, st, CG, mp.A, mp.W, mp.O, mp.S,
                                   mp.R, p);
   if (e != cudaSuccess) return (int)e;
   return mage_post_launch();
 }
 
-struct TileCfg { int bn, cg; };
+struct TileCfg { int bn, cg, ns; };
 
 // Tile selection.  The kernel is bound by L2->SM operand traffic, so the widest tile that still fills the machine wins:
 // CTA pair 256x256 (one TMEM accumulator stage), then pair 256x128 (two stages), then the single-CTA tiles.
 // MAGE_TC_BN / MAGE_TC_PAIR (0/1) force a choice (tuning + tests).
 int g_forced_bn = [] { const char* e = getenv("MAGE_TC_BN"); return e ? atoi(e) : 0; }();
 int g_forced_pair = [] { const char* e = getenv("MAGE_TC_PAIR"); return e ? atoi(e) : -1; }();
+int g_ns = [] { const char* e = getenv("MAGE_TC_NS"); return e ? atoi(e) : 1; }();   // N-split 256-wide pair tiles for plain GEMMs
 
-TileCfg pick_cfg(int N, int64_t m_tiles, int K) {
+TileCfg pick_cfg(int N, int64_t m_tiles, int K, bool gemm = false) {
   const int forced_bn = g_forced_bn, forced_pair = g_forced_pair;
   const int sms = num_sms();
   const bool pair_ok = forced_pair != 0 && m_tiles % 2 == 0;
-  if (forced_bn && N % forced_bn == 0) return {forced_bn, (pair_ok && forced_pair == 1) ? 2 : 1};
+  // N-split 256-wide pair tiles (plain GEMMs only): A is fetched once per 256 output columns, the two 128-column halves keep
+  // separate accumulators so the epilogue still overlaps the next tile's MMAs.  g_ns: 0 off, 1 automatic, 2 whenever legal.
+  const bool ns_ok = gemm && pair_ok && g_ns != 0 && N % 256 == 0 && (forced_bn == 0 || forced_bn == 256);
+  // measured: wins only for long k loops (16384x2048x4096: 530 vs 508 TFLOP/s); at K = 512 the 256x128 tile is 13-30 % faster
+  if (ns_ok && (g_ns == 2 || (forced_bn == 0 && K >= 4096 && (m_tiles / 2) * (N / 256) >= sms / 2))) return {256, 2, 1};
+  if (forced_bn && N % forced_bn == 0) return {forced_bn, (pair_ok && forced_pair == 1) ? 2 : 1, 0};
   if (pair_ok) {
     // measured (tools/tc_microbench.py, profiles/): the 256x256 pair tile wins once the k loop is long enough to amortise
     // its un-overlapped epilogue (single TMEM accumulator stage): K >= 1024.  Shorter k loops stay on the double-buffered
@@ -840,19 +894,20 @@ TileCfg pick_cfg(int N, int64_t m_tiles, int K) {
     // the 256x128 pair tile (two TMEM accumulator stages, each CTA streams half of the W tile) is the fastest shape on every
     // GEMM / conv of the path; 256x256 (single accumulator stage) only pays off for very long k loops.
     const int64_t pairs = m_tiles / 2;
-    if (N % 256 == 0 && ((pairs * (N / 256) >= sms / 2 && K >= 8192) || (forced_pair == 1 && forced_bn == 0))) return {256, 2};
-    if (N % 128 == 0 && (pairs * (N / 128) >= sms / 2 || forced_pair == 1)) return {128, 2};
-    if (forced_pair == 1 && N % 64 == 0) return {64, 2};
+    if (N % 256 == 0 && ((pairs * (N / 256) >= sms / 2 && K >= 8192) || (forced_pair == 1 && forced_bn == 0))) return {256, 2, 0};
+    if (N % 128 == 0 && (pairs * (N / 128) >= sms / 2 || forced_pair == 1)) return {128, 2, 0};
+    if (forced_pair == 1 && N % 64 == 0) return {64, 2, 0};
   }
   // BN = 128 keeps two (main + corr) accumulator stages in the 512 TMEM columns, so the epilogue of one tile
   // overlaps the MMAs of the next.  BN = 64 when N is not a multiple of 128 or the 128-wide tiling would leave most SMs idle.
-  if (N % 128 == 0 && (m_tiles * (N / 128) >= sms || N % 64 != 0)) return {128, 1};
-  if (N % 64 == 0) return {64, 1};
-  return {0, 0};
+  if (N % 128 == 0 && (m_tiles * (N / 128) >= sms || N % 64 != 0)) return {128, 1, 0};
+  if (N % 64 == 0) return {64, 1, 0};
+  return {0, 0, 0};
 }
 
 int dispatch(TileCfg c, const Maps& mp, const TcParams& p, cudaStream_t st) {
   if (c.cg == 2) {
+    if (c.ns) return c.bn == 256 ? launch_tc<256, 2, true>(mp, p, st) : MAGE_ENOTSUP;
     switch (c.bn) {
       case 256: return launch_tc<256, 2>(mp, p, st);
       case 128: return launch_tc<128, 2>(mp, p, st);
@@ -904,14 +959,14 @@ int g_halo = [] { const char* e = getenv("MAGE_TC_HALO"); return e ? atoi(e) : 1
 // weight tile), the widest N tile the channel count allows; BN = 256 exists only as a pair (weight ring depth).
 TileCfg pick_halo_cfg(int Cout, int64_t m_tiles) {
   const bool pair_ok = g_forced_pair != 0 && m_tiles % 2 == 0;
-  if (g_forced_bn && Cout % g_forced_bn == 0 && (g_forced_bn != 256 || pair_ok)) return {g_forced_bn, (pair_ok && (g_forced_pair == 1 || g_forced_bn == 256)) ? 2 : 1};
+  if (g_forced_bn && Cout % g_forced_bn == 0 && (g_forced_bn != 256 || pair_ok)) return {g_forced_bn, (pair_ok && (g_forced_pair == 1 || g_forced_bn == 256)) ? 2 : 1, 0};
   if (pair_ok) {
-    if (Cout % 128 == 0) return {128, 2};   // measured faster than 256-wide pair tiles (two accumulator stages)
-    if (Cout % 64 == 0) return {64, 2};
+    if (Cout % 128 == 0) return {128, 2, 0};   // measured faster than 256-wide pair tiles (two accumulator stages)
+    if (Cout % 64 == 0) return {64, 2, 0};
   }
-  if (Cout % 128 == 0) return {128, 1};
-  if (Cout % 64 == 0) return {64, 1};
-  return {0, 0};
+  if (Cout % 128 == 0) return {128, 1, 0};
+  if (Cout % 64 == 0) return {64, 1, 0};
+  return {0, 0, 0};
 }
 
 int dispatch_halo(TileCfg c, const Maps& mp, const TcParams& p, cudaStream_t st) {
@@ -943,6 +998,12 @@ extern "C" int mage_tc_tuning(int bn, int pair) {
   MAGE_CHECK_ARG((bn == 0 || bn == 64 || bn == 128 || bn == 256) && pair >= -1 && pair <= 1);
   g_forced_bn = bn;
   g_forced_pair = pair;
+  return 0;
+}
+
+extern "C" int mage_tc_nsplit(int mode) {
+  MAGE_CHECK_ARG(mode >= 0 && mode <= 2);
+  g_ns = mode;
   return 0;
 }
 
@@ -989,7 +1050,7 @@ extern "C" int mage_gemm_tc(const void* A, int64_t lda, int64_t a_plane, const v
   MAGE_CHECK_ARG(ldc % 4 == 0 && (!C || aligned16(C)) && (!bias || aligned16(bias)) && (!residual || (aligned16(residual) && ldr % 4 == 0)));
   MAGE_CHECK_ARG(c_plane % 4 == 0 && (C || C_split || C_split_relu));
   const int m_tiles = (M + BM - 1) / BM;
-  const TileCfg tcfg = pick_cfg(N, m_tiles, K);
+  const TileCfg tcfg = pick_cfg(N, m_tiles, K, true);
   if (!tcfg.bn) return MAGE_ENOTSUP;
   const int bn = tcfg.bn;
   Maps mp{};
@@ -1002,7 +1063,7 @@ extern "C" int mage_gemm_tc(const void* A, int64_t lda, int64_t a_plane, const v
     const cuuint32_t box[5] = {BK, BM, 1, 1, 2};
     int r = make_map(&mapA, A, 5, dims, strides, box);
     if (r) return r;
-    r = make_w_map(&mapW, W, ldw, w_plane, N, K, bn / tcfg.cg);
+    r = make_w_map(&mapW, W, ldw, w_plane, N, K, bn / tcfg.cg / (tcfg.ns ? 2 : 1));
     if (r) return r;
   }
   TcParams p{};
@@ -1035,14 +1096,14 @@ int conv2d_tc_impl(const void* in, int64_t in_plane, const void* w, int64_t w_pl
   const int act_id = act & 0xff;
   bool halo = g_halo && KH * KW > 1 && Hout % 16 == 0 && Wout % 8 == 0 && (15 + KH) * (7 + KW) * 256 <= HALO_A_STAGE &&
               (act_id == MAGE_ACT_NONE || act_id == MAGE_ACT_RELU || act_id == MAGE_ACT_TANH);
-  TileCfg hcfg{0, 0};
+  TileCfg hcfg{0, 0, 0};
   if (halo) {
     const int64_t hm = (int64_t)n_img * (Hout / 16) * (Wout / 8);
     hcfg = pick_halo_cfg(Cout, hm);
     if (head) {
       // the pixel head needs all 256 channels of a row in one CTA: two consecutive 128-wide tiles of the same rows (the
       // partial sums stay in registers across the group; TMEM double buffering is kept), or one 256-wide tile when forced
-      if (hm % 2 == 0 && g_forced_pair != 0 && Cout == 256) hcfg = {g_forced_bn == 256 ? 256 : 128, 2};
+      if (hm % 2 == 0 && g_forced_pair != 0 && Cout == 256) hcfg = {g_forced_bn == 256 ? 256 : 128, 2, 0};
       else halo = false;
     }
     if (!hcfg.bn) halo = false;

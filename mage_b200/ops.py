@@ -101,6 +101,11 @@ def tc_tuning(bn: int = 0, pair: int = -1) -> None:
     check(_lib.lib().mage_tc_tuning(bn, pair), "mage_tc_tuning")
 
 
+def tc_nsplit(mode: int = 1) -> None:
+    """N-split 256-wide pair tiles of gemm_tc: 0 off, 1 automatic, 2 whenever legal (tests / tuning)."""
+    check(_lib.lib().mage_tc_nsplit(mode), "mage_tc_nsplit")
+
+
 def tc_conv_halo(enable: bool = True) -> None:
     """Halo mode of the tensor-core convolutions on/off (tests / tuning)."""
     check(_lib.lib().mage_tc_conv_halo(int(enable)), "mage_tc_conv_halo")

@@ -18,7 +18,7 @@ def _ops():
 
 @pytest.fixture(params=[("auto", 0, -1, True), ("pair256", 256, 1, True), ("pair128", 128, 1, True), ("pair64", 64, 1, True),
                         ("single", 0, 0, True), ("auto-nohalo", 0, -1, False), ("pair256-nohalo", 256, 1, False),
-                        ("single-nohalo", 0, 0, False)],
+                        ("single-nohalo", 0, 0, False), ("nsplit", 0, -1, True), ("auto-no-nsplit", 0, -1, True)],
                 ids=lambda p: p[0], autouse=True)
 def tile_cfg(request):
     """Every test runs under each tile selection: automatic, CTA-pair (cta_group::2) with 256/128/64-wide N tiles where the
@@ -26,9 +26,11 @@ def tile_cfg(request):
     ops = _ops()
     ops.tc_tuning(request.param[1], request.param[2])
     ops.tc_conv_halo(request.param[3])
+    ops.tc_nsplit(2 if request.param[0] == "nsplit" else 0 if request.param[0] == "auto-no-nsplit" else 1)
     yield request.param[0]
     ops.tc_tuning(0, -1)
     ops.tc_conv_halo(True)
+    ops.tc_nsplit(1)
 
 
 def _rand(*shape, seed=0, scale=1.0):

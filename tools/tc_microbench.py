@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--only", default="")
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--nsplit", type=int, default=1, help="ops.tc_nsplit mode (0 off, 1 auto, 2 force)")
     ap.add_argument("--scan", action="store_true", help="K / N scans that separate per-tile from per-k-block cost")
     ap.add_argument("--cfgs", default="0,-1", help="';'-separated bn,pair tile overrides (ops.tc_tuning) to sweep")
     args = ap.parse_args()
@@ -113,6 +114,7 @@ def main():
             for n in (64, 128, 512):
                 nm = f"scan gemm 16384x{n}x{k} f32"
                 cases.append((nm, (lambda nm=nm, n=n, k=k: gemm_case(nm, M, n, k, "f32"))))
+    ops.tc_nsplit(args.nsplit)
     table = {}
     cfgs = [tuple(int(v) for v in c.split(",")) for c in args.cfgs.split(";")]
     for bn, pair in cfgs:
