@@ -196,3 +196,31 @@ def test_streamed_host_output_equals_device_output():
         assert not host.is_cuda and host.is_pinned() and tuple(host.shape) == tuple(dev.shape)
         assert torch.equal(host, dev.cpu())
     assert torch.equal(host[:, 0], batch["images"][:, 0])
+
+
+def test_main_mage_split_test_entry(tmp_path):
+    """`python main_mage.py --split test --test_model <dir>/model_best.pth` (main_mage.py:201-248): the yaml beside the checkpoint
+    is loaded, the checkpoint's `module.`-prefixed state dict is accepted, every prompt is sampled and clamped."""
+    import yaml
+
+    import main_mage
+    params = syn.model_params("caterv2", frames_length=3)
+    sd = syn.make_mage_state_dict(params)
+    (tmp_path / "config.yaml").write_text(yaml.safe_dump({"model": {"target": "modules.mage_model.MAGE", "params": params},
+                                                          "data": {"target": "dataload.CATER", "params": {}}}))
+    torch.save({"epoch": 1, "state_dict": {"module." + k: v for k, v in sd.items()}, "optimizer": {}}, tmp_path / "model_best.pth")
+    out = tmp_path / "clips"
+    opt = main_mage.parser.parse_args(["--split", "test", "--test_model", str(tmp_path / "model_best.pth"), "--synthetic", "3",
+                                       "--batch-size", "2", "--out", str(out)])
+    frames = main_mage.sampling(opt)
+    assert frames == 3 * 2
+    clips = sorted(out.glob("*.npy"))
+    assert len(clips) == 3
+    clip = np.load(clips[0])
+    assert clip.shape == (3, 3, 128, 128) and np.abs(clip).max() <= 1.0
+    # frame 0 is the (clamped) input frame of that prompt (mage_model.py:691, main_mage.py:242); the generated frames depend on
+    # the AdaIN noise drawn from the global CPU generator inside the call, which the DataLoader also advances -- like the reference
+    from dataload import SyntheticCaptionVideos
+    ds = SyntheticCaptionVideos(params, 3, seed=1234)
+    assert np.array_equal(clip[0], ds[0]["images"][0].clamp(-1, 1).numpy())
+    assert np.isfinite(clip).all() and np.abs(clip[1:]).max() > 0.05
