@@ -224,3 +224,31 @@ def test_main_mage_split_test_entry(tmp_path):
     ds = SyntheticCaptionVideos(params, 3, seed=1234)
     assert np.array_equal(clip[0], ds[0]["images"][0].clamp(-1, 1).numpy())
     assert np.isfinite(clip).all() and np.abs(clip[1:]).max() > 0.05
+
+
+@pytest.mark.parametrize("family,L,B,B_check", [("mnist", 16, 1, 1),      # BASELINE configs[1]: single Moving MNIST 64x64x16, batch 1
+                                                 ("mnist", 20, 32, 2),     # configs[2]: double Moving MNIST 64x64x20, batch 32
+                                                 ("caterv1", 16, 16, 2)])  # configs[3]: CATER-GEN-v1 128x128x16, batch 16
+def test_baseline_configs_full_length_vs_incremental_oracle(family, L, B, B_check):
+    """The other BASELINE.json configurations at their full frame counts and batch sizes: the first B_check prompts are held to the
+    CPU oracle (incremental order, proven equal to the reference order in tests/test_oracle_golden.py) -- tokens tie-aware, pixels
+    to 1e-3 -- and, being batch-invariant, stand for the whole batch (test_batch_invariance_and_graph_replay_are_bit_exact)."""
+    from oracle import mage_oracle as orc
+    params = syn.model_params(family, frames_length=L)
+    sd = syn.make_mage_state_dict(params)
+    batch = syn.make_batch(params, B, seed=99, text_len=14, padded=B > 1)
+    noise = syn.make_noise(B, seed=8) if params["randomness"] else None
+    model = _build(params, sd)
+    video = model.autoregressive_generate({k: v.to("cuda") for k, v in batch.items()}, noise=noise)
+    assert tuple(video.shape[:2]) == (B, L)
+    sub = {k: v[:B_check] for k, v in batch.items()}
+    if B > 1:
+        # the motion anchor attends padded caption positions (mage_model.py:92), so a prompt's result depends on the batch's
+        # maximum caption length: keep the full batch's padded width for the oracle's sub-batch
+        assert sub["text"].shape[1] == batch["text"].shape[1]
+    otr = {}
+    want = orc.generate_incremental(sd, sub, noise[:B_check] if noise is not None else None, otr)
+    assert np.array_equal(model.last_tok0[:B_check].cpu().numpy(), otr["tok0"].numpy())
+    _, excused = tie_aware_token_check(model.last_tokens[:B_check].cpu().numpy(), otr["tokens"].numpy(), otr["gap"].numpy(), LOGIT_EPS)
+    if excused == 0:
+        _pix_check(video[:B_check, 1:].cpu().numpy(), want[:, 1:].numpy())
