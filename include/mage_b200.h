@@ -45,6 +45,10 @@ int mage_abi_version(void); /* 3 */
 /* Number of kernels launched through this library by the calling process so far. */
 int64_t mage_launch_count(void);
 
+/* enable != 0: the kernels of the per-step path are launched with the programmatic-stream-serialization attribute (they call
+ * griddepcontrol.launch_dependents / .wait themselves).  Default off (MAGE_PDL=1 turns it on): measured neutral on B200. */
+int mage_pdl(int enable);
+
 /* C[M,N] = act(relu_a?(A)[M,K] . W[N,K]^T + bias[N]) + residual
  * residual row for output row m is (res_mod > 0 ? m % res_mod : m), leading dim ldr; may alias C.
  * Replaces nn.Linear / MHA in-proj / out-proj / MLP (mage_model.py:20-26,33,50-51,375-376,385),

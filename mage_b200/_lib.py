@@ -21,6 +21,7 @@ _f32 = ctypes.c_float
 SIGNATURES = {
     "mage_abi_version": [],
     "mage_launch_count": [],
+    "mage_pdl": [_i],
     "mage_gemm_f32": [_c_f, _i64, _c_f, _i64, _c_f, _c_f, _i64, _i, _c_f, _i64, _i, _i, _i, _i, _i, _c_f],
     "mage_conv2d_nhwc_f32": [_c_f] * 5 + [_i] * 22 + [_i64, _c_f],
     "mage_tc_tuning": [_i, _i],

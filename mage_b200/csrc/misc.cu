@@ -11,6 +11,10 @@ int64_t g_mage_launches = 0;
 
 extern "C" int mage_abi_version(void) { return 3; }
 extern "C" int64_t mage_launch_count(void) { return g_mage_launches; }
+extern "C" int mage_pdl(int enable) {
+  g_mage_pdl = enable != 0;
+  return 0;
+}
 
 namespace {
 

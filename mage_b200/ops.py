@@ -101,6 +101,11 @@ def tc_tuning(bn: int = 0, pair: int = -1) -> None:
     check(_lib.lib().mage_tc_tuning(bn, pair), "mage_tc_tuning")
 
 
+def pdl(enable: bool) -> None:
+    """Programmatic dependent launch for the per-step kernels on/off (see mage_b200.h)."""
+    check(_lib.lib().mage_pdl(int(enable)), "mage_pdl")
+
+
 def tc_nsplit(mode: int = 1) -> None:
     """N-split 256-wide pair tiles of gemm_tc: 0 off, 1 automatic, 2 whenever legal (tests / tuning)."""
     check(_lib.lib().mage_tc_nsplit(mode), "mage_tc_nsplit")

@@ -252,3 +252,28 @@ def test_baseline_configs_full_length_vs_incremental_oracle(family, L, B, B_chec
     _, excused = tie_aware_token_check(model.last_tokens[:B_check].cpu().numpy(), otr["tokens"].numpy(), otr["gap"].numpy(), LOGIT_EPS)
     if excused == 0:
         _pix_check(video[:B_check, 1:].cpu().numpy(), want[:, 1:].numpy())
+
+
+def test_optional_schedules_are_bit_exact():
+    """Scheduling options that are off by default (measured neutral): decoder on a side stream, programmatic dependent launch,
+    per-frame decoding.  None of them may change a single bit."""
+    from mage_b200 import ops
+    params = syn.model_params("caterv2", frames_length=6)
+    sd = syn.make_mage_state_dict(params)
+    batch = {k: v.to("cuda") for k, v in syn.make_batch(params, 4, seed=31, text_len=12).items()}
+    noise = syn.make_noise(4, seed=2)
+    model = _build(params, sd)
+    ref = model.autoregressive_generate(batch, noise=noise)
+    ref_tok = model.last_tokens.clone()
+    eng = model.engine()
+    try:
+        for overlap, group, use_pdl in ((True, 4, False), (False, 1, False), (False, 4, True), (True, 2, True)):
+            eng.overlap_decode, eng.decode_group = overlap, group
+            eng._graphs.clear()
+            ops.pdl(use_pdl)
+            for _ in range(2):   # capture + replay
+                got = model.autoregressive_generate(batch, noise=noise)
+                assert torch.equal(model.last_tokens, ref_tok), (overlap, group, use_pdl)
+                assert torch.equal(got, ref), (overlap, group, use_pdl)
+    finally:
+        ops.pdl(False)
