@@ -277,3 +277,21 @@ def test_optional_schedules_are_bit_exact():
                 assert torch.equal(got, ref), (overlap, group, use_pdl)
     finally:
         ops.pdl(False)
+
+
+def test_c5_full_batch_rows_equal_small_batch_rows():
+    """BASELINE configs[4] at its full size (CATER-v2 128x128x32, 64 prompts): the first two prompts of the 64-prompt call are
+    bit-identical to the same prompts generated alone (which test_full_length_c5_shape_vs_incremental_oracle holds to the oracle),
+    every frame is finite and in tanh range, and the greedy tokens are valid code indices."""
+    params = syn.model_params("caterv2", frames_length=32)
+    sd = syn.make_mage_state_dict(params)
+    batch = syn.make_batch(params, 64, seed=4321, text_len=20)
+    noise = syn.make_noise(64, seed=5)
+    model = _build(params, sd)
+    cu = lambda d: {k: v.to("cuda") for k, v in d.items()}
+    v64 = model.autoregressive_generate(cu(batch), noise=noise)
+    t64 = model.last_tokens.clone()
+    assert tuple(v64.shape) == (64, 32, 3, 128, 128) and torch.isfinite(v64).all() and v64[:, 1:].abs().max() <= 1.0
+    assert t64.min() >= 0 and t64.max() < params["codebook_size"]
+    v2 = model.autoregressive_generate(cu({k: v[:2] for k, v in batch.items()}), noise=noise[:2])
+    assert torch.equal(model.last_tokens, t64[:2]) and torch.equal(v2, v64[:2])
