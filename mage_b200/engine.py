@@ -636,6 +636,10 @@ class SamplerEngine:
             tok = ops.argmax_rows(logits, out=tokens[j].view(-1))
             if trace is not None:
                 trace.setdefault("logits", []).append(logits.clone())
+                if trace.get("force_tokens") is not None:
+                    # teacher forcing (parity diagnostics): this step's prediction is recorded, but the NEXT step is fed the
+                    # given token map -- a near-tie flip then cannot cascade into later frames
+                    tok = trace["force_tokens"][:, j].reshape(-1).contiguous()
             # decode the finished group of frames for every sample: video[j0+1 .. j+1] (frame-major, contiguous)
             if (j + 1) % self.decode_group == 0 or j == L - 2:
                 j0 = (j // self.decode_group) * self.decode_group

@@ -264,5 +264,22 @@ class MAGE(_EngineOwner):
         # tensor that its caller clamps in place (main_mage.py:242)
         return video.clone()
 
+    @torch.no_grad()
+    def teacher_forced_tokens(self, batch, force_tokens: torch.Tensor, noise: Optional[torch.Tensor] = None):
+        """Per-step greedy predictions when every step is fed the GIVEN previous tokens (`force_tokens` int64 [B,L-1,h,w], e.g. the
+        reference's) instead of its own: what `prediction[:, j]` of the reference's last iteration holds (mage_model.py:686-687).
+        Returns (tokens int64 [B,L-1,h,w], logits f32 [B,L-1,h*w,K]).  Runs eagerly (no CUDA graph)."""
+        eng = self.engine()
+        dev = eng.device
+        noise = noise.to(dev).float().contiguous() if (self.randomness and noise is not None) else None
+        if self.randomness and noise is None:
+            noise = torch.randn([batch["text"].shape[0], 64, self.image_resolution, self.image_resolution]).to(dev)
+        trace = {"force_tokens": force_tokens.to(dev, torch.int64)}
+        _, tokens, _ = eng.generate(batch["images"][:, 0].to(dev), batch["text"].to(dev),
+                                    batch["speed"].to(dev).float() if "speed" in batch else None, noise, trace=trace)
+        B = tokens.shape[0]
+        logits = torch.stack([l.view(B, -1, l.shape[-1]) for l in trace["logits"]], 1)
+        return tokens, logits
+
     def forward(self, batch, test_flag=False):
         raise NotImplementedError("stage-2 training objective (mage_model.py:575-639) is outside the sampling path (SURVEY.md §2, N2)")

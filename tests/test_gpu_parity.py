@@ -295,3 +295,23 @@ def test_c5_full_batch_rows_equal_small_batch_rows():
     assert t64.min() >= 0 and t64.max() < params["codebook_size"]
     v2 = model.autoregressive_generate(cu({k: v[:2] for k, v in batch.items()}), noise=noise[:2])
     assert torch.equal(model.last_tokens, t64[:2]) and torch.equal(v2, v64[:2])
+
+
+@pytest.mark.parametrize("name", MAGE_CASES)
+def test_teacher_forced_tokens_vs_reference_golden(name):
+    """with every step fed the REFERENCE's previous tokens, each position's greedy choice must equal the
+    reference's unless the reference's own top1-top2 logit gap is below LOGIT_EPS -- checked at every position of every frame
+    (no cascade, so nothing is skipped after a flip)."""
+    params, sd, batch, noise, g = load_case(name)
+    model = _build(params, sd)
+    ref = torch.from_numpy(g["tokens"].astype(np.int64))
+    tokens, logits = model.teacher_forced_tokens({k: v.to("cuda") for k, v in batch.items()}, ref, noise=noise)
+    neq = tokens.cpu().numpy() != g["tokens"]
+    gap = g["gap"].reshape(neq.shape)
+    assert not (neq & (gap >= LOGIT_EPS)).any(), f"{int((neq & (gap >= LOGIT_EPS)).sum())} teacher-forced mismatches away from ties"
+    # the recorded logits reproduce the recorded choice and match the reference's last-iteration logits (sampled in the golden)
+    assert torch.equal(logits.argmax(-1).view_as(tokens), tokens)
+    B, F = tokens.shape[:2]
+    got = logits.view(B, F, 16, 16, -1)[:, :, ::5, ::5, ::16].cpu().numpy()
+    err = np.abs(got - g["logits_sample"]).max()
+    assert err <= 5e-5 * max(1.0, np.abs(g["logits_sample"]).max()), f"teacher-forced logits differ from the reference by {err:.3e}"
