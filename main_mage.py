@@ -51,6 +51,7 @@ parser.add_argument("--test_model", type=str, default='./models/MAGE/catergenv2/
 parser.add_argument("--batch-size", type=int, default=1, help="prompts per generate call (reference: 1)")
 parser.add_argument("--synthetic", type=int, default=0, help="use N seeded synthetic prompts instead of configs.data")
 parser.add_argument("--out", type=str, default=None, help="directory for the generated clips (.npy)")
+parser.add_argument("--gifs", action="store_true", help="also write <ckpt dir>/videos/<video_id>.gif like the reference's save_gifs")
 
 
 def load_configs(opt) -> dict:
@@ -72,6 +73,22 @@ def load_checkpoint(model, opt) -> bool:
     model.load_state_dict(sd)
     print("=> loaded checkpoint '{}'".format(test_model))
     return True
+
+
+def save_gifs(tgr, video_id, test_model):
+    """main_mage.py:250-257 (commented out at its call site :244-245): frames [L,C,H,W] in [-1,1] -> <ckpt dir>/videos/<id>.gif at
+    3 fps.  The reference uses imageio; PIL writes the same frames here."""
+    import numpy as np
+    from PIL import Image
+    tgr_imgs = (tgr + 1) * 0.5
+    tgr_imgs = (tgr_imgs * 255.).numpy().astype(np.uint8).transpose(0, 2, 3, 1)
+    save_path = os.path.join(os.path.dirname(test_model), 'videos')
+    if not os.path.exists(save_path):
+        os.makedirs(save_path)
+    frames = [Image.fromarray(f[..., 0] if f.shape[-1] == 1 else f) for f in tgr_imgs]
+    path = os.path.join(save_path, video_id + '.gif')
+    frames[0].save(path, save_all=True, append_images=frames[1:], duration=1000 // 3, loop=0)
+    return path
 
 
 def sampling(opt):
@@ -113,11 +130,15 @@ def sampling(opt):
                 generated = model.autoregressive_generate(batch)
                 generated.clamp_(min=-1, max=1)
                 frames += generated.shape[0] * (generated.shape[1] - 1)
-            if opt.out:
+            if opt.out or opt.gifs:
                 import numpy as np
-                for b in range(generated.shape[0]):
+                clips = generated.cpu()
+                for b in range(clips.shape[0]):
                     name = video_ids[b] if video_ids else f"r{rank}_{idx}_{b}"
-                    np.save(os.path.join(opt.out, name + ".npy"), generated[b].cpu().numpy())
+                    if opt.out:
+                        np.save(os.path.join(opt.out, name + ".npy"), clips[b].numpy())
+                    if opt.gifs:
+                        save_gifs(clips[b], name, opt.test_model)
             print(idx)
             idx += 1
     if torch.cuda.is_available():

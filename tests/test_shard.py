@@ -112,3 +112,17 @@ def test_shipped_configs_instantiate():
         assert "generate_model.blocks.5.mlp.c_proj.weight" in keys and "first_stage_model.codebook.embedding.weight" in keys
         with pytest.raises(RuntimeError):
             m.autoregressive_generate({"images": torch.zeros(1, 1, 1, 8, 8), "text": torch.zeros(1, 4, dtype=torch.long)})  # no CPU path
+
+
+def test_save_gifs_writes_the_reference_layout(tmp_path):
+    """main_mage.py:250-257: <ckpt dir>/videos/<video_id>.gif, one GIF frame per video frame."""
+    from PIL import Image
+
+    import main_mage
+    clip = torch.rand(5, 3, 32, 32) * 2 - 1
+    path = main_mage.save_gifs(clip, "vid0", str(tmp_path / "model_best.pth"))
+    assert path == str(tmp_path / "videos" / "vid0.gif")
+    im = Image.open(path)
+    assert im.n_frames == 5 and im.size == (32, 32)
+    gray = main_mage.save_gifs(torch.rand(3, 1, 16, 16) - 0.5, "mnist0", str(tmp_path / "model_best.pth"))
+    assert Image.open(gray).n_frames == 3
