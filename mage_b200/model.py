@@ -249,6 +249,10 @@ class MAGE(_EngineOwner):
         tensor whose frames were copied out while later frames were still being generated; it is valid until the next call."""
         eng = self.engine()
         dev = eng.device
+        if not batch["text"].is_cuda:   # free on the host: token ids must index the vocabulary table (nn.Embedding raises too)
+            vocab = self.text_encoder.state_dict()["token_embedding.weight"].shape[0]
+            if batch["text"].numel() and (int(batch["text"].max()) >= vocab or int(batch["text"].min()) < 0):
+                raise IndexError(f"caption token id outside the vocabulary [0, {vocab})")
         images0 = batch["images"][:, 0].to(dev, non_blocking=True)
         text = batch["text"].to(dev, non_blocking=True)
         speed = batch["speed"].to(dev, non_blocking=True).float() if "speed" in batch else None

@@ -384,6 +384,9 @@ def embedding(idx: torch.Tensor, table: torch.Tensor, out: Optional[torch.Tensor
 def text_embed(text: torch.Tensor, tok_emb, pos_emb, gamma, beta, pad_idx: int, eps: float):
     B, T = text.shape
     C = tok_emb.shape[1]
+    if T > pos_emb.shape[0]:
+        # nn.Embedding would raise on position indices past the table (mage_model.py:228-231); never read out of bounds
+        raise IndexError(f"caption length {T} exceeds the text encoder's context_length {pos_emb.shape[0]}")
     x = torch.empty(B, T, C, device=tok_emb.device, dtype=torch.float32)
     key_len = torch.empty(B, device=tok_emb.device, dtype=torch.int32)
     with _Prof("misc", 0.0):

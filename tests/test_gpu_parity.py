@@ -315,3 +315,36 @@ def test_teacher_forced_tokens_vs_reference_golden(name):
     got = logits.view(B, F, 16, 16, -1)[:, :, ::5, ::5, ::16].cpu().numpy()
     err = np.abs(got - g["logits_sample"]).max()
     assert err <= 5e-5 * max(1.0, np.abs(g["logits_sample"]).max()), f"teacher-forced logits differ from the reference by {err:.3e}"
+
+
+@pytest.mark.parametrize("text_len,with_speed", [(3, True), (38, True), (20, False)])
+def test_caption_length_extremes_and_missing_speed(text_len, with_speed):
+    """Edge inputs of the batch-dict contract (dataload.py:260,370): the shortest caption ([CLS] word [SEP]), the longest the
+    text encoder accepts (context_length 38 for CATER-v2), and a batch without 'speed' (mage_model.py:666 skips the embedding)."""
+    from oracle import mage_oracle as orc
+    params = syn.model_params("caterv2", frames_length=3)
+    sd = syn.make_mage_state_dict(params)
+    batch = syn.make_batch(params, 2, seed=11, text_len=text_len, padded=text_len > 8, with_speed=with_speed)
+    noise = syn.make_noise(2, seed=9)
+    model = _build(params, sd)
+    video = model.autoregressive_generate({k: v.to("cuda") for k, v in batch.items()}, noise=noise)
+    otr = {}
+    want = orc.generate(sd, batch, noise, otr)
+    assert np.array_equal(model.last_tok0.cpu().numpy(), otr["tok0"].numpy())
+    _, excused = tie_aware_token_check(model.last_tokens.cpu().numpy(), otr["tokens"].numpy(), otr["gap"].numpy(), LOGIT_EPS)
+    if excused == 0:
+        _pix_check(video[:, 1:].cpu().numpy(), want[:, 1:].numpy())
+    assert torch.equal(video[:, 0].cpu(), batch["images"][:, 0])
+
+
+def test_too_long_caption_is_refused_like_the_reference():
+    """A caption longer than `context_length` indexes past the learned position table: the reference raises (IndexError from
+    nn.Embedding, mage_model.py:228-231); here the call must fail loudly as well instead of reading out of bounds."""
+    params = syn.model_params("caterv2", frames_length=3)
+    sd = syn.make_mage_state_dict(params)
+    model = _build(params, sd)
+    batch = syn.make_batch(params, 1, seed=3, text_len=20)
+    batch["text"] = torch.cat([batch["text"], torch.full((1, 30), 5, dtype=torch.long)], 1)   # 50 > 38 positions
+    with pytest.raises(Exception):
+        model.autoregressive_generate({k: v.to("cuda") for k, v in batch.items()}, noise=syn.make_noise(1))
+        torch.cuda.synchronize()
