@@ -209,6 +209,14 @@ int mage_argmax_rows_f32(const float* x, int64_t ldx, int64_t* idx, int rows, in
 /* out[r, :] = table[idx[r], :]  (nn.Embedding: mage_model.py:644,682; vqvae_model.py:240). C % 4 == 0. */
 int mage_embedding_f32(const int64_t* idx, const float* table, float* out, int rows, int C, void* stream);
 
+/* Convolution of a codebook-embedded token map followed by a linear layer, as table lookups.  Because the conv input is one of K
+ * embedding rows per pixel, in_linear(conv3x3(E[tok]) + pos) (mage_model.py:674-676,375) is exactly
+ *   out[b,y,x,:] = sum_{ky,kx} table[ky*KW+kx][tok[b, y+ky-KH/2, x+kx-KW/2]][:] + pos_bias[y*R+x][:] + bias[:]
+ * with table[tap][code] = W_in . Wc[:, :, tap] . E[code] precomputed at load ([KH*KW, K, C] fp32), pos_bias = W_in . pos.
+ * tok int64 [n_img, R, R]; zero padding outside the map; C = 512; out fp32 [n_img*R*R, C]. */
+int mage_token_taps_f32(const int64_t* tok, const float* table, const float* pos_bias, const float* bias, float* out,
+                        int n_img, int R, int K, int C, int KH, int KW, void* stream);
+
 /* Text-encoder front end (mage_model.py:224-237): x[b,t,:] = LN_eps(tok_emb[text[b,t]] + pos_emb[t]) * (text[b,t] != pad);
  * key_len[b] = #non-pad tokens.  C = 512. */
 int mage_text_embed_f32(const int64_t* text, const float* tok_emb, const float* pos_emb,

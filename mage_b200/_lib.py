@@ -45,6 +45,7 @@ SIGNATURES = {
     "mage_vq_argmin_f32": [_c_f] * 4 + [_i] * 3 + [_c_f],
     "mage_argmax_rows_f32": [_c_f, _i64, _c_f, _i, _i, _c_f],
     "mage_embedding_f32": [_c_f] * 3 + [_i, _i, _c_f],
+    "mage_token_taps_f32": [_c_f] * 5 + [_i] * 6 + [_c_f],
     "mage_text_embed_f32": [_c_f] * 7 + [_i] * 4 + [_f32, _c_f],
     "mage_adain_nhwc_f32": [_c_f] * 4 + [_i] * 3 + [_f32, _c_f],
     "mage_add_scaled_vec_f32": [_c_f] * 3 + [_i] * 3 + [_c_f],

@@ -103,6 +103,47 @@ __global__ void __launch_bounds__(256) embedding_kernel(const int64_t* __restric
   reinterpret_cast<float4*>(out)[t] = __ldg(reinterpret_cast<const float4*>(table) + idx[row] * C4 + c);
 }
 
+// ------------------------------------------------------------------ convolution of a codebook-embedded token map as table lookups
+// out[b,y,x,:] = sum_{ky,kx} table[ky*KW+kx][tok[b, y+ky-KH/2, x+kx-KW/2]][:] + pos_bias[y*R+x][:] + bias[:]
+// (taps outside the map contribute nothing = zero padding).  One warp per pixel, NV float4 per lane, fixed tap order.
+template <int NV>
+__global__ void __launch_bounds__(256) token_taps_kernel(const int64_t* __restrict__ tok, const float* __restrict__ table,
+                                                         const float* __restrict__ pos_bias, const float* __restrict__ bias,
+                                                         float* __restrict__ out, int n_pix, int R, int K, int KH, int KW) {
+  pdl_launch_dependents();
+  pdl_wait();
+  constexpr int C4 = NV * 32;
+  const int pix = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (pix >= n_pix) return;
+  const int b = pix / (R * R), p = pix - b * R * R, y = p / R, x = p - y * R;
+  float4 acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 pb = __ldg(reinterpret_cast<const float4*>(pos_bias) + (int64_t)p * C4 + i * 32 + lane);
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(bias) + i * 32 + lane);
+    acc[i] = make_float4(pb.x + bb.x, pb.y + bb.y, pb.z + bb.z, pb.w + bb.w);
+  }
+  for (int ky = 0; ky < KH; ++ky) {
+    const int yy = y + ky - KH / 2;
+    if (yy < 0 || yy >= R) continue;
+    for (int kx = 0; kx < KW; ++kx) {
+      const int xx = x + kx - KW / 2;
+      if (xx < 0 || xx >= R) continue;
+      const int64_t code = tok[(int64_t)b * R * R + yy * R + xx];
+      const float4* row = reinterpret_cast<const float4*>(table) + ((int64_t)(ky * KW + kx) * K + code) * C4;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float4 v = __ldg(row + i * 32 + lane);
+        acc[i].x += v.x; acc[i].y += v.y; acc[i].z += v.z; acc[i].w += v.w;
+      }
+    }
+  }
+  float4* dst = reinterpret_cast<float4*>(out) + (int64_t)pix * C4;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) dst[i * 32 + lane] = acc[i];
+}
+
 // ------------------------------------------------------------------ 2x2 max pool NHWC
 __global__ void __launch_bounds__(256) maxpool_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                       int n_img, int Hin, int Win, int C4) {
@@ -351,6 +392,17 @@ extern "C" int mage_embedding_f32(const int64_t* idx, const float* table, float*
   MAGE_CHECK_ARG(rows > 0 && C % 4 == 0 && aligned16(table) && aligned16(out));
   const int64_t total = (int64_t)rows * (C / 4);
   embedding_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(idx, table, out, rows, C / 4);
+  return mage_post_launch();
+}
+
+extern "C" int mage_token_taps_f32(const int64_t* tok, const float* table, const float* pos_bias, const float* bias, float* out,
+                                   int n_img, int R, int K, int C, int KH, int KW, void* stream) {
+  MAGE_CHECK_ARG(n_img > 0 && R > 0 && K > 0 && C == 512 && KH > 0 && KW > 0 && (KH & 1) && (KW & 1));
+  MAGE_CHECK_ARG(aligned16(table) && aligned16(pos_bias) && aligned16(bias) && aligned16(out));
+  const int n_pix = n_img * R * R;
+  cudaError_t e = mage_launch_pdl(token_taps_kernel<4>, dim3((n_pix + 7) / 8), dim3(256), 0, as_stream(stream), 1, tok, table, pos_bias,
+                                  bias, out, n_pix, R, K, KH, KW);
+  if (e != cudaSuccess) return (int)e;
   return mage_post_launch();
 }
 

@@ -361,6 +361,7 @@ class SamplerEngine:
         self.scale = 1.0 / math.sqrt(32.0)
         self.n_head = self.C // 32
         self._graphs = {}
+        self.tok_table = None
         self.kernels_per_generate = None
         # The VQ-VAE decode of frame j depends only on that frame's tokens and nothing downstream depends on it, so it runs on a
         # side stream next to transformer step j+1: the tails / launch gaps of one kernel sequence are filled by the other.
@@ -386,6 +387,18 @@ class SamplerEngine:
                 ws[mp + "q_weight"] = ops.split(sd[mp + "attn.in_proj_weight"][:self.C].contiguous())
                 for k in ("attn.out_proj.weight", "mlp.c_fc.weight", "mlp.c_proj.weight"):
                     ws[mp + k] = ops.split(g(mp + k))
+            # in_linear(conv3x3(E[tok]) + pos) as lookups: the conv input is one of K embedding rows per pixel, so
+            # table[tap][code] = W_in . Wc[:,:,tap] . E[code] (formed in fp64, stored fp32) replaces a 3x3 512->512 convolution and a
+            # 512x512 GEMM per step (86 GFLOP at B=64) by nine 2 KB gathers per pixel; fixed summation order (taps 0..8).
+            if os.environ.get("MAGE_TOKEN_TABLE", "1") != "0":
+                Win = sd[p + "in_linear.weight"].double()
+                Wc = sd["conv.0.weight"].double()                                # [C, C, 3, 3]
+                comp = torch.einsum("oc,cikl->klio", Win, Wc)                      # [3, 3, C_in, C_out]
+                table = torch.einsum("ei,klio->kleo", self.E.double(), comp)       # [3, 3, K, C_out]
+                self.tok_table = table.reshape(9, self.E.shape[0], self.C).float().contiguous()
+                self.tok_posW = (self.posHW.double() @ Win.t()).float().contiguous()  # [R*R, C]
+            else:
+                self.tok_table = None
             if randomness:
                 ws["Wd2"] = ops.split(self.Wd2)
                 for k, (wk, _) in self.adain_w.items():
@@ -622,8 +635,11 @@ class SamplerEngine:
         logits = torch.empty(M, sd[p + "out.weight"].shape[0], device=self.device, dtype=torch.float32)
         for j in range(L - 1):
             if tc:
-                f = self._token_features_tc(tok, B)
-                ops.gemm_tc(f, ws[p + "in_linear.weight"], self.bias_in_T[j + 1], out=x)
+                if self.tok_table is not None:
+                    ops.token_taps(tok.view(B, R, R), self.tok_table, self.tok_posW, self.bias_in_T[j + 1], x)
+                else:
+                    f = self._token_features_tc(tok, B)
+                    ops.gemm_tc(f, ws[p + "in_linear.weight"], self.bias_in_T[j + 1], out=x)
                 for i in range(self.n_blocks):
                     x = self._block_step_tc(i, x, j + 1, B, caches, bufs, i + 1 == self.n_blocks)
                 ops.gemm_tc(bufs["u"], ws[p + "out.weight"], sd[p + "out.bias"], out=logits)

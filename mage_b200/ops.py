@@ -381,6 +381,19 @@ def embedding(idx: torch.Tensor, table: torch.Tensor, out: Optional[torch.Tensor
     return out
 
 
+def token_taps(tok: torch.Tensor, table: torch.Tensor, pos_bias: torch.Tensor, bias: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out[b,y,x,:] = sum_taps table[tap][tok[b, y+dy, x+dx]] + pos_bias[y*R+x] + bias (see mage_b200.h).
+    tok int64 [n,R,R]; table [KH*KW, K, C]; out fp32 [n*R*R, C]."""
+    n, R, _ = tok.shape
+    taps, K, C = table.shape
+    kh = int(round(taps ** 0.5))
+    assert kh * kh == taps and tok.dtype == torch.int64 and tok.is_contiguous() and out.is_contiguous()
+    with _Prof("embed", 4.0 * n * R * R * C * (taps + 2)):
+        check(_lib.lib().mage_token_taps_f32(_p(tok), _p(_f32(table)), _p(_f32(pos_bias)), _p(_f32(bias)), _p(out), n, R, K, C, kh, kh,
+                                             _stream()), "mage_token_taps_f32")
+    return out
+
+
 def text_embed(text: torch.Tensor, tok_emb, pos_emb, gamma, beta, pad_idx: int, eps: float):
     B, T = text.shape
     C = tok_emb.shape[1]

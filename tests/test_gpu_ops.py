@@ -330,3 +330,26 @@ def test_bad_arguments_are_rejected_not_run():
         ops.layernorm(torch.zeros(4, 100, device=DEV), torch.zeros(100, device=DEV), torch.zeros(100, device=DEV))
     with pytest.raises(AssertionError):
         ops.gemm(torch.zeros(4, 8), torch.zeros(8, 8))  # CPU tensors: no fallback
+
+
+def test_token_taps_equals_conv_plus_linear():
+    """in_linear(conv3x3(E[tok]) + pos) (mage_model.py:674-676,375) as nine table lookups per pixel."""
+    ops = _ops()
+    import torch.nn.functional as F
+    B, R, K, C = 3, 16, 512, 512
+    g = torch.Generator().manual_seed(5)
+    E = torch.randn(K, C, generator=g) * 0.02
+    Wc = torch.randn(C, C, 3, 3, generator=g) * (9 * C) ** -0.5
+    Win = torch.randn(C, C, generator=g) * C ** -0.5
+    b_in = torch.randn(C, generator=g) * 0.1
+    pos = torch.randn(R * R, C, generator=g) * C ** -0.5
+    tok = torch.randint(0, K, (B, R, R), generator=g)
+    emb = E[tok].permute(0, 3, 1, 2).double()                                  # [B,C,R,R]
+    f = F.conv2d(emb, Wc.double(), padding=1).permute(0, 2, 3, 1) + pos.double().view(1, R, R, C)
+    want = f @ Win.double().t() + b_in.double()
+    comp = torch.einsum("oc,cikl->klio", Win.double(), Wc.double())
+    table = torch.einsum("ei,klio->kleo", E.double(), comp).reshape(9, K, C).float().contiguous()
+    posW = (pos.double() @ Win.double().t()).float()
+    out = torch.empty(B * R * R, C, device=DEV)
+    ops.token_taps(tok.to(DEV), table.to(DEV), posW.to(DEV), b_in.to(DEV), out)
+    _close(out.view(B, R, R, C), want, 2e-6, 2e-6)
