@@ -138,6 +138,15 @@ class VQVAEEngine:
         self.ws = ws
         self.cb_split = ops.split(self.codebook)
         self.cb_relu_split = ops.split(self.codebook, relu=True)
+        # decoder.0 reads codebook rows, so its two 1x1 convolutions (id_path 4dim->2dim, block.1 4dim->hid) are functions of the
+        # code index alone: evaluate them once per code with the same kernels (rows of a GEMM are independent, so the per-pixel
+        # results are bit-identical) and gather at decode time
+        self.dec0_tables = None
+        if ("decoder.0.id_path.weight") in self.w:
+            idp_tab, _, _ = ops.gemm_tc(self.cb_split, ws["decoder.0.id_path.weight"], self.w["decoder.0.id_path.bias"])
+            _, h_tab, _ = ops.gemm_tc(self.cb_relu_split, ws["decoder.0.block.1.weight"], self.w["decoder.0.block.1.bias"], act=ACT_RELU,
+                                      want=("split",))
+            self.dec0_tables = (idp_tab.contiguous(), h_tab.contiguous())
 
     # ------------------------------------------------------------------ encoder
     def _enc_block(self, name: str, x: torch.Tensor, final_relu: bool = False) -> torch.Tensor:
@@ -236,19 +245,25 @@ class VQVAEEngine:
         a block's output is produced in exactly the forms its consumer reads: split(raw) for an id_path conv,
         fp32 for an identity skip (read through the nearest x2 upsample), split(relu) for the next 1x1."""
         w, ws = self.w, self.ws
-        x_split = ops.embedding_split(idx, self.cb_split)        # [2,n,h,w,D]
-        xr_split = ops.embedding_split(idx, self.cb_relu_split)
-        x_f32 = None
+        x_f32 = x_split = xr_split = None
+        if self.dec0_tables is None:
+            x_split = ops.embedding_split(idx, self.cb_split)        # [2,n,h,w,D]
+            xr_split = ops.embedding_split(idx, self.cb_relu_split)
         blocks = [("decoder.0", False), ("decoder.2", True), ("decoder.4", True), ("decoder.6", True)]
         for bi, (name, up) in enumerate(blocks):
-            _, n, H, W, C = xr_split.shape
-            if (name + ".id_path.weight") in w:
-                idp, _, _ = ops.gemm_tc(x_split.view(2, -1, C), ws[name + ".id_path.weight"], w[name + ".id_path.bias"])
-                idp = idp.view(n, H, W, -1)
+            if bi == 0 and self.dec0_tables is not None:
+                n, H, W = idx.shape
+                idp = ops.embedding(idx.reshape(-1), self.dec0_tables[0]).view(n, H, W, -1)
+                h = ops.embedding_split(idx, self.dec0_tables[1])          # [2,n,h,w,hid]
             else:
-                idp = x_f32
-            _, h, _ = ops.gemm_tc(xr_split.view(2, -1, C), ws[name + ".block.1.weight"], w[name + ".block.1.bias"], act=ACT_RELU,
-                                  want=("split",))
+                _, n, H, W, C = xr_split.shape
+                if (name + ".id_path.weight") in w:
+                    idp, _, _ = ops.gemm_tc(x_split.view(2, -1, C), ws[name + ".id_path.weight"], w[name + ".id_path.bias"])
+                    idp = idp.view(n, H, W, -1)
+                else:
+                    idp = x_f32
+                _, h, _ = ops.gemm_tc(xr_split.view(2, -1, C), ws[name + ".block.1.weight"], w[name + ".block.1.bias"], act=ACT_RELU,
+                                      want=("split",))
             hid = h.shape[-1]
             h = h.view(2, n, H, W, hid)
             if up:
