@@ -10,7 +10,7 @@ import os
 import subprocess
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
-LIB_PATH = os.path.join(CSRC, "libmage_sm100.so")
+LIB_PATH = os.environ.get("MAGE_LIB") or os.path.join(CSRC, "libmage_sm100.so")   # MAGE_LIB: experiment builds (tools/experiments)
 
 _c_f = ctypes.c_void_p  # device pointers travel as integers
 _i = ctypes.c_int

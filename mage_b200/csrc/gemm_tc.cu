@@ -35,6 +35,15 @@ constexpr int BK = 64;       // halves per k-block = one 128-byte swizzle row
 constexpr int UK = 16;       // K of one tcgen05.mma kind::f16
 constexpr int NTHREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 constexpr int SMEM_BUDGET = 227 * 1024;
+// TIMING EXPERIMENT ONLY (tools/experiments/build_oneacc.sh builds a separate library with -DMAGE_EXPERIMENT_ONEACC): all three
+// MMAs of a product accumulate into ONE TMEM accumulator, which frees the columns for double-buffered 256-wide tiles.  With the
+// 2^11-scaled lo plane of the shipped split format the RESULTS ARE WRONG; the build exists to measure what a single-accumulator
+// format (unscaled lo plane, power-of-two pre-scaled tensors) would buy before committing to it.  Never part of libmage_sm100.so.
+#ifdef MAGE_EXPERIMENT_ONEACC
+constexpr bool kOneAcc = true;
+#else
+constexpr bool kOneAcc = false;
+#endif
 
 struct TcParams {
   const float* bias;
@@ -72,7 +81,8 @@ struct Cfg {
   static constexpr int STAGING_BYTES = 8 * 32 * 32 * 4;   // one XOR-swizzled 32x32 fp32 transpose tile per epilogue warp
   static constexpr int STAGES_RAW = (SMEM_BUDGET - 1024 - STAGING_BYTES - 256) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
-  static constexpr int ACC_STAGES = (2 * BN * 2 <= 512) ? 2 : 1;   // main+corr per accumulator stage
+  static constexpr int ACC_COLS = kOneAcc ? BN : 2 * BN;           // main+corr per accumulator stage
+  static constexpr int ACC_STAGES = (ACC_COLS * 2 <= 512) ? 2 : 1;
   static constexpr int TMEM_COLS = 512;
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STAGING_BYTES + 256;
 };
@@ -162,15 +172,15 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
     if (HEAD && tcount % p.group == 0) hacc[0] = hacc[1] = hacc[2] = 0.f;
     mbar_wait(tfull0 + 8u * acc, aph);
     tc_fence_after();
-    const uint32_t t_main = tmem_base + ((uint32_t)(quad * 32) << 16) + (NS ? half * 256 : acc * 2 * BN);
-    const uint32_t t_corr = t_main + (NS ? 128 : BN);
+    const uint32_t t_main = tmem_base + ((uint32_t)(quad * 32) << 16) + (NS ? half * 256 : acc * C::ACC_COLS);
+    const uint32_t t_corr = t_main + (NS ? 128 : kOneAcc ? 0 : BN);
 #pragma unroll 1
     for (int c = NS ? half * 4 : half; c < (NS ? half * 4 + 4 : BN / 32); c += NS ? 1 : 2) {
       const int n = nt * BN + c * 32;
       const int tc_col = NS ? (c & 3) * 32 : c * 32;
       uint32_t rm[32], rc[32];
       tmem_ld32(t_main + tc_col, rm);
-      tmem_ld32(t_corr + tc_col, rc);
+      if (!kOneAcc) tmem_ld32(t_corr + tc_col, rc);
       // the residual row segment travels while the TMEM loads complete
       float4 rv[8];
       if (res_off >= 0) {
@@ -189,7 +199,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
       }
       float v[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(rc[j]), kLoInv, __uint_as_float(rm[j]));
+      for (int j = 0; j < 32; ++j) v[j] = kOneAcc ? __uint_as_float(rm[j]) : fmaf(__uint_as_float(rc[j]), kLoInv, __uint_as_float(rm[j]));
       if (bias) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -450,7 +460,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const uint32_t aph = (tcount / C::ACC_STAGES) & 1;
         mbar_wait(tempty_bar(acc), aph ^ 1);
         tc_fence_after();
-        const uint32_t d_main = tmem_base + acc * 2 * BN, d_corr = d_main + BN;
+        const uint32_t d_main = tmem_base + acc * C::ACC_COLS, d_corr = kOneAcc ? d_main : d_main + BN;
         for (int it = 0; it < p.k_iters; ++it, ++itg) {
           const int s = itg % C::STAGES;
           const uint32_t ph = (itg / C::STAGES) & 1;
@@ -467,11 +477,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               if (CG == 2) {
                 umma_f16_2sm(d_corr, a_lo + adv, w_hi + adv, idesc, accum);
                 umma_f16_2sm(d_corr, a_hi + adv, w_lo + adv, idesc, 1u);
-                umma_f16_2sm(d_main, a_hi + adv, w_hi + adv, idesc, accum);
+                umma_f16_2sm(d_main, a_hi + adv, w_hi + adv, idesc, kOneAcc ? 1u : accum);
               } else {
                 umma_f16(d_corr, a_lo + adv, w_hi + adv, idesc, accum);
                 umma_f16(d_corr, a_hi + adv, w_lo + adv, idesc, 1u);
-                umma_f16(d_main, a_hi + adv, w_hi + adv, idesc, accum);
+                umma_f16(d_main, a_hi + adv, w_hi + adv, idesc, kOneAcc ? 1u : accum);
               }
             }
             if (CG == 2) umma_commit_2sm(empty_bar(s), 3);   // frees the stage in both CTAs
@@ -645,7 +655,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         const uint32_t aph = (tcount / C::ACC_STAGES) & 1;
         mbar_wait(tempty_bar(acc), aph ^ 1);
         tc_fence_after();
-        const uint32_t d_main = tmem_base + acc * 2 * BN, d_corr = d_main + BN;
+        const uint32_t d_main = tmem_base + acc * C::ACC_COLS, d_corr = kOneAcc ? d_main : d_main + BN;
         for (int cb = 0; cb < p.cin_blocks; ++cb, ++ia) {
           const int sa = ia % SA;
           mbar_wait(a_full(sa), (ia / SA) & 1);
@@ -669,11 +679,11 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                 if (CG == 2) {
                   umma_f16_2sm(d_corr, a_lo + adv, w_hi + adv, idesc, accum);
                   umma_f16_2sm(d_corr, a_hi + adv, w_lo + adv, idesc, 1u);
-                  umma_f16_2sm(d_main, a_hi + adv, w_hi + adv, idesc, accum);
+                  umma_f16_2sm(d_main, a_hi + adv, w_hi + adv, idesc, kOneAcc ? 1u : accum);
                 } else {
                   umma_f16(d_corr, a_lo + adv, w_hi + adv, idesc, accum);
                   umma_f16(d_corr, a_hi + adv, w_lo + adv, idesc, 1u);
-                  umma_f16(d_main, a_hi + adv, w_hi + adv, idesc, accum);
+                  umma_f16(d_main, a_hi + adv, w_hi + adv, idesc, kOneAcc ? 1u : accum);
                 }
               }
               if (CG == 2) {
