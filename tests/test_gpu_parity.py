@@ -348,3 +348,22 @@ def test_too_long_caption_is_refused_like_the_reference():
     with pytest.raises(Exception):
         model.autoregressive_generate({k: v.to("cuda") for k, v in batch.items()}, noise=syn.make_noise(1))
         torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("family,L,B", [("caterv2", 2, 1), ("mnist", 2, 3), ("caterv1", 5, 5)])
+def test_small_and_odd_shapes_vs_oracle(family, L, B):
+    """Shortest clip (one generated frame), odd batch sizes (odd row-tile counts: no CTA pairing on some layers)."""
+    from oracle import mage_oracle as orc
+    params = syn.model_params(family, frames_length=L)
+    sd = syn.make_mage_state_dict(params)
+    batch = syn.make_batch(params, B, seed=17, text_len=9)
+    noise = syn.make_noise(B, seed=4) if params["randomness"] else None
+    model = _build(params, sd)
+    video = model.autoregressive_generate({k: v.to("cuda") for k, v in batch.items()}, noise=noise)
+    otr = {}
+    want = orc.generate(sd, batch, noise, otr)
+    assert tuple(video.shape) == tuple(want.shape)
+    assert np.array_equal(model.last_tok0.cpu().numpy(), otr["tok0"].numpy())
+    _, excused = tie_aware_token_check(model.last_tokens.cpu().numpy(), otr["tokens"].numpy(), otr["gap"].numpy(), LOGIT_EPS)
+    if excused == 0:
+        _pix_check(video[:, 1:].cpu().numpy(), want[:, 1:].numpy())
