@@ -6,20 +6,21 @@
 // tcgen05.mma kind::f16 instructions (hi*hi -> main, lo*hi + hi*lo -> corr), both accumulators live
 // in TMEM, the epilogue forms main + corr*2^-11 -- fp32-grade accuracy at a third of the fp16 rate.
 //
-// One persistent CTA per SM, 320 threads, warp-specialised:
-//   warp 0   TMA producer: one 5-D box for the A tile (both planes) + one 3-D box for the W tile per
-//            k-block into a SWIZZLE_128B ring (mbarrier full/empty)
-//   warp 1   TMEM allocator + the single MMA-issuing thread (tcgen05.mma, tcgen05.commit)
-//   warps 2-9 epilogue (two per TMEM lane quadrant): tcgen05.ld -> bias / activation -> smem transpose ->
-//            residual -> coalesced fp32 and/or split stores (the next consumer's operand format)
-// For a convolution the A tile is an NHWC patch: the box is [64 ch, Wb, Hb, 1 image, 2 planes] at
-// the tap's (dy,dx) offset and TMA's out-of-bounds zero fill is the padding, so im2col never exists.
+// One persistent CTA per SM (or CTA pair per TPC), 320 threads, warp-specialised; every role loop runs warp-wide in uniform
+// control flow and only the issue is predicated on elect.sync (tc_common.cuh: elect_one):
+//   warp 0   TMA producer: one 5-D box for the A tile (both planes) + one 3-D box for the W tile per k-block into a
+//            SWIZZLE_128B ring (mbarrier full/empty)
+//   warp 1   TMEM allocator + MMA issuer (tcgen05.mma on uniform-register descriptors, tcgen05.commit)
+//   warps 2-9 epilogue, row per thread (two warps per TMEM lane quadrant): tcgen05.ld -> main + corr*2^-11 -> bias /
+//            activation / residual -> swizzled 4 KB staging tile -> one TMA store per output kind (fp32 tile, or the hi+lo
+//            planes of the split format = the next consumer's operand)
+// Kernels: tc_gemm_kernel (GEMM; convolution with one TMA box per tap), tc_conv_halo_kernel (convolution with one input patch
+// per channel block and shifted descriptors per tap, optional fused pixel head).  For a convolution the A tile is an NHWC
+// patch and TMA's out-of-bounds zero fill is the padding, so im2col never exists.
 //
-// CG = 2 (CTA pair, cluster 2x1x1, tcgen05 cta_group::2): the two CTAs of a TPC share one 256 x BN tile.
-// Each loads its own 128 A rows and HALF of the W tile (BN/2 rows); the leader's single thread issues
-// M = 256 MMAs that read B from both CTAs' shared memory and write each CTA's own TMEM.  Operand bytes
-// per MMA drop by 25 % (BN = 128) to 50 % (BN = 256) -- the 1-CTA kernel is bound by L2->SM operand
-// traffic (ncu: ~11 TB/s xbar2sm, tensor pipe < 40 %), not by the tensor pipe.
+// CG = 2 (CTA pair, cluster 2x1x1, tcgen05 cta_group::2): the two CTAs of a TPC share one 256 x BN tile.  Each loads its own
+// 128 A rows and HALF of the W tile (BN/2 rows); the leader issues M = 256 MMAs that read B from both CTAs' shared memory and
+// write each CTA's own TMEM.  256 x 128 with two accumulator stages is the default shape of the path.
 #include <cuda.h>
 #include <stdlib.h>
 
