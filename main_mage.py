@@ -51,6 +51,11 @@ parser.add_argument("--test_model", type=str, default='./models/MAGE/catergenv2/
 parser.add_argument("--batch-size", type=int, default=1, help="prompts per generate call (reference: 1)")
 parser.add_argument("--synthetic", type=int, default=0, help="use N seeded synthetic prompts instead of configs.data")
 parser.add_argument("--out", type=str, default=None, help="directory for the generated clips (.npy)")
+parser.add_argument("--caption", type=str, default=None, help="sample ONE clip from this caption (needs --image); word-level vocabulary of --dataset")
+parser.add_argument("--image", type=str, default=None, help="first frame for --caption (any PIL-readable file)")
+parser.add_argument("--speed", type=float, default=0.5, help="speed in [0,1) for --caption")
+parser.add_argument("--dataset", type=str, default=None, choices=["mnist", "caterv1", "caterv2"],
+                    help="vocabulary for --caption (default: configs.data.params.dataset, else by vocab size)")
 parser.add_argument("--gifs", action="store_true", help="also write <ckpt dir>/videos/<video_id>.gif like the reference's save_gifs")
 
 
@@ -102,7 +107,19 @@ def sampling(opt):
     if world > 1:
         shard.init_distributed(opt.dist_backend, device if device.type == 'cuda' else None)
 
-    if opt.synthetic > 0:
+    if opt.caption is not None:
+        from dataload import VOCABS, encode_caption, load_first_frame
+        mp = configs['model']['params']
+        fs = mp['first_stage_config']['params']
+        ds = opt.dataset or (configs.get('data', {}).get('params', {}) or {}).get('dataset')
+        if ds not in VOCABS:
+            sizes = {len(v): k for k, v in VOCABS.items() if k != 'caterv1'}
+            ds = sizes.get(mp['text_encoder_config']['params']['vocab_size'], 'mnist' if fs['down_ratio'] == 4 else 'caterv2')
+        assert opt.image, "--caption needs --image (the clip's first frame)"
+        item = {'images': load_first_frame(opt.image, fs['input_dim'], mp['image_resolution'] * fs['down_ratio']),
+                'text': encode_caption(opt.caption, ds), 'speed': torch.tensor(opt.speed, dtype=torch.float32), 'video_id': 'caption_0'}
+        test_dataset = [item]
+    elif opt.synthetic > 0:
         from dataload import SyntheticCaptionVideos
         test_dataset = SyntheticCaptionVideos(configs['model']['params'], opt.synthetic, seed=1234 if opt.seed is None else opt.seed)
     else:

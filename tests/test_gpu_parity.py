@@ -367,3 +367,24 @@ def test_small_and_odd_shapes_vs_oracle(family, L, B):
     _, excused = tie_aware_token_check(model.last_tokens.cpu().numpy(), otr["tokens"].numpy(), otr["gap"].numpy(), LOGIT_EPS)
     if excused == 0:
         _pix_check(video[:, 1:].cpu().numpy(), want[:, 1:].numpy())
+
+
+def test_main_mage_caption_and_image_prompt(tmp_path):
+    """Additive entry: one clip from a caption (the dataset's word-level vocabulary) and a first-frame image file."""
+    import yaml
+    from PIL import Image
+
+    import main_mage
+    params = syn.model_params("caterv2", frames_length=3)
+    (tmp_path / "config.yaml").write_text(yaml.safe_dump({"model": {"target": "modules.mage_model.MAGE", "params": params},
+                                                          "data": {"target": "dataload.CATER", "params": {"dataset": "caterv2"}}}))
+    torch.save({"state_dict": syn.make_mage_state_dict(params)}, tmp_path / "model_best.pth")
+    img = (syn.structured_images(1, 3, 128, seed=3)[0].permute(1, 2, 0).numpy() * 0.5 + 0.5) * 255
+    Image.fromarray(img.astype(np.uint8)).save(tmp_path / "first.png")
+    opt = main_mage.parser.parse_args(["--split", "test", "--test_model", str(tmp_path / "model_best.pth"), "--caption",
+                                       "the small blue rubber sphere is picked up and placed to (2, -3).", "--image",
+                                       str(tmp_path / "first.png"), "--out", str(tmp_path / "o"), "--gifs"])
+    assert main_mage.sampling(opt) == 2
+    clip = np.load(tmp_path / "o" / "caption_0.npy")
+    assert clip.shape == (3, 3, 128, 128) and np.isfinite(clip).all()
+    assert (tmp_path / "videos" / "caption_0.gif").exists()

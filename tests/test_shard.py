@@ -126,3 +126,32 @@ def test_save_gifs_writes_the_reference_layout(tmp_path):
     assert im.n_frames == 5 and im.size == (32, 32)
     gray = main_mage.save_gifs(torch.rand(3, 1, 16, 16) - 0.5, "mnist0", str(tmp_path / "model_best.pth"))
     assert Image.open(gray).n_frames == 3
+
+
+def test_caption_vocabularies_and_tokeniser():
+    """Token ids are part of the checkpoint contract (they index text_encoder.token_embedding): dataload.py:199-203, 299-312."""
+    import dataload
+    v = dataload.VOCABS
+    assert len(v["mnist"]) == 30 and len(v["caterv1"]) == 30 and len(v["caterv2"]) == 50      # = vocab_size of the configs
+    assert (v["mnist"]["0"], v["mnist"]["9"], v["mnist"]["the"], v["mnist"]["."]) == (3, 12, 13, 29)
+    assert (v["caterv1"]["rotating"], v["caterv1"]["-3"], v["caterv1"]["quadrant"]) == (11, 22, 29)
+    assert (v["caterv2"]["sphere"], v["caterv2"]["yellow"], v["caterv2"]["-1"], v["caterv2"]["quadrant"]) == (14, 30, 36, 49)
+    t = dataload.encode_caption("the digit 3 is moving up and down .", "mnist")
+    assert t.tolist() == [1, 13, 14, 6, 16, 19, 24, 15, 25, 29, 2]
+    c = dataload.encode_caption("the large red metal cone is sliding to (-1, 2).", "caterv2")
+    assert c.tolist() == [1, 3, 19, 24, 20, 4, 6, 7, 12, 31, 36, 39, 34, 32, 40, 2]
+    assert dataload.decode_caption(c[1:-1], "caterv2") == "the large red metal cone is sliding to ( -1 , 2 ) ."
+    with pytest.raises(KeyError):
+        dataload.encode_caption("the elephant is sliding .", "caterv2")
+
+
+def test_first_frame_loader_ranges(tmp_path):
+    import numpy as np
+    from PIL import Image
+
+    import dataload
+    Image.fromarray((np.random.rand(40, 60, 3) * 255).astype(np.uint8)).save(tmp_path / "f.png")
+    x = dataload.load_first_frame(str(tmp_path / "f.png"), 3, 128)
+    assert tuple(x.shape) == (1, 3, 128, 128) and -1.0 <= float(x.min()) and float(x.max()) <= 1.0
+    g = dataload.load_first_frame(str(tmp_path / "f.png"), 1, 64)
+    assert tuple(g.shape) == (1, 1, 64, 64) and -0.5 <= float(g.min()) and float(g.max()) <= 0.5
