@@ -1,17 +1,20 @@
 #!/usr/bin/env python
-"""Benchmark of the MAGE sampling path (BASELINE.json metric: generated frames/sec,
-CATER-v2 128x128x32, batch 64 per GPU).
+"""Benchmark of the MAGE sampling path (BASELINE.json metric: generated frames/sec, CATER-v2 128x128x32, batch 64,
+on 1/2/4/8 B200 next to the reference's CPU path).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own implementation on the host CPU
 
-A "step" is one `autoregressive_generate` call over one synthetic batch: VQ-VAE encode of frame 0,
-text / motion-anchor prelude, L-1 greedy decode steps through the 6 axial blocks, VQ-VAE decode of
-every generated frame.  One process per GPU (torchrun for N > 1); prompts are independent, so the
-batch shards with no collective on the data path (NCCL only for the barrier / max-over-ranks of the
-timings) -- weak scaling, 64 prompts per GPU.
+A "step" is one `autoregressive_generate` call over one synthetic batch: VQ-VAE encode of frame 0, text / motion-anchor
+prelude, L-1 greedy decode steps through the 6 axial blocks, VQ-VAE decode of every generated frame.
 
-Printed by rank 0: ONE JSON line (see README of the contract in DESIGN.md §Measurement).
+Multi-GPU: one process per GPU (torchrun); the GLOBAL prompt batch of the workload (64 for C5) is drawn once
+and cut into contiguous per-rank slices -- STRONG scaling, 64/N prompts per GPU, which is the split BASELINE.json quotes
+("b64, 1/2/4/8 B200", configs[4] "batch 64, 8xB200 batch-shard").  Prompts are independent, so there is no collective on the
+data path; NCCL carries the barrier and the max-over-ranks of the timings only.  `--scaling weak` keeps 64 prompts per GPU;
+at N > 1 the strong line also carries a short weak-scaling measurement under "weak_scaling".
+
+Printed by rank 0: ONE JSON line on stdout (NCCL's INFO log goes to stderr).
 """
 import argparse
 import json
@@ -26,10 +29,19 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-METRIC = "generated frames/sec, CATER-v2 128x128x32 b64"
 UNIT = "frames/s"
-FAMILY, FRAMES, BATCH, TEXT_LEN = "caterv2", 32, 64, 20
-GFLOP_PER_FRAME = 23.58  # algorithmic (incremental) FLOPs per generated frame at C5, SURVEY.md §8(d)
+TEXT_LEN = 20
+# BASELINE.json configs[1..4]; gflop = algorithmic (incremental) FLOPs per generated frame, SURVEY.md §8(d) / BASELINE.md §2
+WORKLOADS = {
+    "c5": dict(family="caterv2", frames=32, batch=64, gflop=23.58, name="CATER-GEN-v2 128x128x32", cfg="BASELINE.json configs[4]",
+               metric="generated frames/sec, CATER-v2 128x128x32 b64"),
+    "c4": dict(family="caterv1", frames=16, batch=16, gflop=24.67, name="CATER-GEN-v1 128x128x16", cfg="BASELINE.json configs[3]",
+               metric="generated frames/sec, CATER-v1 128x128x16 b16"),
+    "c3": dict(family="mnist", frames=20, batch=32, gflop=13.41, name="Double Moving MNIST 64x64x20", cfg="BASELINE.json configs[2]",
+               metric="generated frames/sec, Moving-MNIST 64x64x20 b32"),
+    "c2": dict(family="mnist", frames=16, batch=1, gflop=13.67, name="Single Moving MNIST 64x64x16", cfg="BASELINE.json configs[1]",
+               metric="generated frames/sec, Moving-MNIST 64x64x16 b1"),
+}
 
 
 def _peaks():
@@ -75,30 +87,77 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_sample(threads: int, ar_iters: int = 3):
-    """Time the reference algorithm (oracle/mage_oracle.py, reference evaluation order -- every step
-    re-runs the conv and the 6 blocks over all L positions, mage_model.py:673-684) on the host CPU
-    for ONE prompt of the C5 workload.  Bounded sample: prelude + `ar_iters` of the L-1 (identical-cost)
-    autoregressive iterations + the full VQ-VAE decode; frames/s = (L-1) / (prelude + (L-1)*mean_iter + decode)."""
+def _workload_inputs(wl, batch, seed=1234, noise_seed=99):
+    """Seeded synthetic checkpoint + GLOBAL prompt batch of a workload (every rank builds the same tensors and slices its rows)."""
+    from mage_b200 import synthetic as syn
+    params = syn.model_params(wl["family"], frames_length=wl["frames"])
+    fs = params["first_stage_config"]["params"]
+    cb = os.path.join(syn.GOLDEN_DIR, "codebook_f%d.npy" % fs["down_ratio"])
+    sd = syn.make_mage_state_dict(params, conditioned=os.path.isfile(cb))
+    b = syn.make_batch(params, batch, seed=seed, text_len=TEXT_LEN)
+    noise = syn.make_noise(batch, seed=noise_seed) if params["randomness"] else None
+    return params, sd, b, noise
+
+
+# ---------------------------------------------------------------------------------------------- reference arms (CPU / eager GPU)
+def _reference_model(params, sd, device="cpu"):
+    """The UNMODIFIED reference (oracle/_ref: a git-ignored copy of /root/reference/{modules,utils} made by oracle/build_ref.py,
+    or /root/reference itself) behind three import shims, or None when neither is present."""
+    from oracle import ref_shims
+    if not ref_shims.reference_available():
+        return None
+    m = ref_shims.build_reference_mage(params, sd)
+    return m.to(device)
+
+
+def cpu_reference_sample(wl, threads: int, ar_iters: int = 0, budget_s: float = 60.0):
+    """Time the reference's own CPU implementation of the path on ONE prompt of the workload (CPU throughput is flat in batch,
+    BASELINE.md §2): `MAGE.autoregressive_generate` of the unmodified reference when a copy is present (kind "reference"),
+    else the oracle's restatement in the reference's evaluation order (kind "port").  The whole call is timed -- prelude, all
+    L-1 autoregressive iterations (each re-runs the conv and the 6 blocks over all L positions, mage_model.py:673-684), VQ-VAE
+    decode -- unless one iteration of the port predicts more than `budget_s` (slow host) or `ar_iters` > 0 is forced: then
+    prelude + `ar_iters` identical-cost iterations + decode are timed through the port and extrapolated."""
     from mage_b200 import synthetic as syn
     from oracle import mage_oracle as orc
 
     torch.set_num_threads(threads)
-    params = syn.model_params(FAMILY, frames_length=FRAMES)
-    sd = syn.make_mage_state_dict(params, conditioned=os.path.isfile(os.path.join(syn.GOLDEN_DIR, "codebook_f8.npy")))
-    batch = syn.make_batch(params, 1, seed=1234, text_len=TEXT_LEN)
-    noise = syn.make_noise(1)
+    L = wl["frames"]
+    params, sd, batch, noise = _workload_inputs(wl, 1)
     fsd = {k[len("first_stage_model."):]: v for k, v in sd.items() if k.startswith("first_stage_model.")}
-    L = FRAMES
     with torch.no_grad():
+        # one warm iteration of the port: predicts the cost of the full call
+        tok0 = orc.vqvae_encode(fsd, batch["images"][:, 0])
+        anchor = orc.motion_anchor(sd, tok0, batch["text"], batch.get("speed"), noise)
+        inp = orc.embed_tokens(sd, tok0).unsqueeze(1).repeat(1, L - 1, 1, 1, 1)
+        orc.flat_axial_decoder(sd, anchor, orc.token_features(sd, inp))
+        t0 = time.perf_counter()
+        orc.flat_axial_decoder(sd, anchor, orc.token_features(sd, inp))
+        t_iter_est = time.perf_counter() - t0
+        if ar_iters <= 0 and t_iter_est * (L - 1) <= budget_s:
+            ref = _reference_model(params, sd)
+            t0 = time.perf_counter()
+            if ref is not None:
+                if noise is not None:
+                    torch.manual_seed(0)
+                ref.autoregressive_generate(batch)
+                kind = "reference"
+            else:
+                orc.generate(sd, batch, noise)
+                kind = "port"
+            total = time.perf_counter() - t0
+            what = ("the unmodified reference's MAGE.autoregressive_generate" if kind == "reference" else
+                    "the oracle's restatement of MAGE.autoregressive_generate (reference evaluation order)")
+            return (L - 1) / total, {"kind": kind, "measured_s": total,
+                                     "sample": f"1 prompt of {wl['name']}: one full call of {what} -- prelude, all {L - 1} O(L) "
+                                               f"autoregressive iterations, VQ-VAE decode -- {total:.1f}s on {threads} threads"}
+        k = max(ar_iters, 3)
         t0 = time.perf_counter()
         tok0 = orc.vqvae_encode(fsd, batch["images"][:, 0])
         anchor = orc.motion_anchor(sd, tok0, batch["text"], batch.get("speed"), noise)
         inp = orc.embed_tokens(sd, tok0).unsqueeze(1).repeat(1, L - 1, 1, 1, 1)
         t_pre = time.perf_counter() - t0
-        iters = []
-        pred = None
-        for i in range(ar_iters):
+        iters, pred = [], None
+        for i in range(k):
             t0 = time.perf_counter()
             pred = orc.flat_axial_decoder(sd, anchor, orc.token_features(sd, inp))
             ids = torch.max(pred, -1)[1]
@@ -111,101 +170,172 @@ def cpu_reference_sample(threads: int, ar_iters: int = 3):
     t_iter = sum(iters) / len(iters)
     total = t_pre + (L - 1) * t_iter + t_dec
     return (L - 1) / total, {
-        "sample": f"1 prompt of the C5 workload (CATER-v2 128x128x32), reference evaluation order: prelude {t_pre:.2f}s + "
-                  f"{ar_iters} of {L - 1} identical-cost AR iterations (mean {t_iter:.2f}s) + full 31-frame VQ-VAE decode {t_dec:.2f}s; "
-                  f"extrapolated to {total:.1f}s per prompt (CPU throughput is flat in batch, BASELINE.md)",
-        "measured_s": t_pre + sum(iters) + t_dec}
+        "kind": "port", "measured_s": t_pre + sum(iters) + t_dec,
+        "sample": f"1 prompt of {wl['name']}, oracle restatement in the reference's evaluation order: prelude {t_pre:.2f}s + {k} of "
+                  f"{L - 1} identical-cost AR iterations (mean {t_iter:.2f}s) + full VQ-VAE decode {t_dec:.2f}s, extrapolated to "
+                  f"{total:.1f}s per prompt on {threads} threads (a full call would exceed the bench's time budget on this host)"}
 
 
-def run_reference(args, rank):
+def run_reference(args, wl, rank):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    vals, secs = [], []
+    vals, secs, info = [], [], None
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        v, info = cpu_reference_sample(threads, ar_iters=args.ref_iters)
+        v, info = cpu_reference_sample(wl, threads, ar_iters=args.ref_iters)
         if i >= args.warmup:
             vals.append(v)
             secs.append(time.perf_counter() - t0)
     value = sum(vals) / len(vals)
-    line = {"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": round(1e3 * sum(secs) / len(secs), 1), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"CATER-GEN-v2 128x128x{FRAMES}, batch {BATCH} per GPU (timed on 1 prompt, see cpu_baseline.sample)",
-                       "family": FAMILY, "frames_length": FRAMES, "batch_per_gpu": BATCH, "text_len": TEXT_LEN},
-            "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": threads, "kind": "port", "sample": info["sample"]},
+    line = {"impl": "reference", "metric": wl["metric"], "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(1e3 * sum(secs) / len(secs), 1), "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{wl['name']}, global batch {wl['batch']} ({wl['cfg']}); timed on 1 prompt, see cpu_baseline.sample",
+                       "family": wl["family"], "frames_length": wl["frames"], "global_batch": wl["batch"], "text_len": TEXT_LEN},
+            "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": threads, "kind": info["kind"], "sample": info["sample"]},
             "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def run_cuda(args, rank, world, local_rank):
+def eager_gpu_baseline(wl, dev, batch_n):
+    """The >= 10x target's denominator (BASELINE.json north_star): the reference's eager-PyTorch path on THIS GPU with PyTorch's
+    default precision flags (TF32 cuDNN convs, fp32 GEMMs), at a reduced batch (the reference algorithm is O(L^2) per prompt).
+    Unmodified reference when a copy is present, else the oracle's restatement of the same algorithm (torch eager ops)."""
+    from oracle import mage_oracle as orc
+    L = wl["frames"]
+    params, sd, batch, noise = _workload_inputs(wl, batch_n, seed=4321, noise_seed=7)
+    eb = {k: v.to(dev) for k, v in batch.items()}
+    ref = _reference_model(params, sd, dev)
+    with torch.no_grad():
+        if ref is not None:
+            one = {k: v[:1] for k, v in eb.items()}
+            ref.autoregressive_generate(one)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ref.autoregressive_generate(eb)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            kind = "the unmodified reference (MAGE.autoregressive_generate, torch eager, PyTorch default precision flags) on the same GPU"
+        else:
+            sd_d = {k: v.to(dev) for k, v in sd.items()}
+            en = noise.to(dev) if noise is not None else None
+            orc.generate(sd_d, {k: v[:1] for k, v in eb.items()}, en[:1] if en is not None else None)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            orc.generate(sd_d, eb, en)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            kind = "port of the reference algorithm (every step recomputes all L positions), torch eager on the same GPU"
+    del ref
+    torch.cuda.empty_cache()
+    return {"value": round(batch_n * (L - 1) / dt, 2), "unit": UNIT, "batch": batch_n, "seconds": round(dt, 3), "kind": kind}
+
+
+# ---------------------------------------------------------------------------------------------- this repo's CUDA path
+def _time_resident(eng, dev_in, steps, barrier):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(steps):
+        eng.generate(*dev_in)
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1)
+
+
+def run_cuda(args, wl, rank, world, local_rank):
     import torch.distributed as dist
 
-    from mage_b200 import ops, synthetic as syn
+    from mage_b200 import ops, shard
     from mage_b200.config import instantiate_from_config
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("MAGE_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+        # NCCL's INFO log (ranks, transports) on stderr; stdout carries the one JSON line
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     os.environ["MAGE_BACKEND"] = args.backend
-    B, L = args.batch, args.frames
-    params = syn.model_params(FAMILY, frames_length=L)
-    sd = syn.make_mage_state_dict(params, conditioned=os.path.isfile(os.path.join(syn.GOLDEN_DIR, "codebook_f8.npy")))
+    L = wl["frames"]
+    G = args.batch if args.batch > 0 else wl["batch"]                      # global batch
+    weak = args.scaling == "weak"
+    params, sd, gbatch, gnoise = _workload_inputs(wl, G * world if weak else G)
+    lo, hi = shard.shard_bounds(G * world if weak else G, world, rank)
+    B = hi - lo
+    assert B > 0, f"rank {rank} has no prompts (global batch {G} over {world} GPUs)"
     model = instantiate_from_config({"target": "modules.mage_model.MAGE", "params": params})
     model.load_state_dict(sd)
     model = model.to(dev).eval()
     eng = model.engine()
-    # every rank gets its own shard of the global prompt batch (seeded by rank): no data-path collective
-    batch = syn.make_batch(params, B, seed=1234 + rank, text_len=TEXT_LEN)
-    noise = syn.make_noise(B, seed=99 + rank)
-    host = {k: v.pin_memory() for k, v in batch.items()}
+    batch = {k: v[lo:hi] for k, v in gbatch.items()}
+    noise = gnoise[lo:hi] if gnoise is not None else None
+    host = {k: v.contiguous().pin_memory() for k, v in batch.items()}
     host["images"] = batch["images"][:, 0:1].contiguous().pin_memory()
-    noise_h = noise.pin_memory()
-    d_img, d_txt, d_spd, d_noise = host["images"][:, 0].to(dev), host["text"].to(dev), host["speed"].to(dev), noise_h.to(dev)
-
-    def step_resident():
-        return eng.generate(d_img, d_txt, d_spd, d_noise)
+    noise_h = noise.contiguous().pin_memory() if noise is not None else None
+    dev_in = (host["images"][:, 0].to(dev), host["text"].to(dev), host["speed"].to(dev), noise_h.to(dev) if noise_h is not None else None)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_ranks(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_ranks(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
     for _ in range(max(args.warmup, 3)):
-        step_resident()
+        eng.generate(*dev_in)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        step_resident()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms_max = max_ranks(_time_resident(eng, dev_in, args.steps, barrier))
     clocks = sampler.stop() if rank == 0 else None
     kernels_per_step = eng.kernels_per_generate
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    frames_total = world * B * (L - 1) * args.steps
-    value = frames_total / (ms_max / 1e3)
+    frames_step = sum_ranks(B * (L - 1))                   # generated frames of one step, all ranks
+    value = frames_step * args.steps / (ms_max / 1e3)
+    plan = eng._plan(B)
+
+    # ---- parity evidence for the timed configuration: rows 0-1 of this rank's shard against the CPU oracle
+    parity = None
+    if rank == 0 and not args.no_parity:
+        from oracle import mage_oracle as orc
+        n = min(2, B)
+        _, tokens, tok0 = eng.generate(*dev_in)
+        tokens, tok0 = tokens[:n].cpu(), tok0[:n].cpu()
+        otr = {}
+        t0 = time.perf_counter()
+        torch.set_num_threads(os.cpu_count() or 1)
+        orc.generate_incremental(sd, {k: v[:n] for k, v in batch.items()}, noise[:n] if noise is not None else None, otr)
+        neq = tokens != otr["tokens"]
+        gap = otr["gap"].reshape(neq.shape)
+        first_bad = [int(torch.nonzero(neq[b].flatten(1).any(1))[0]) if neq[b].any() else None for b in range(n)]
+        parity = {"rows": n, "positions": int(neq.numel()), "token_mismatches": int(neq.sum()),
+                  "mismatches_at_reference_gap_ge_5e-5": int((neq & (gap >= 5e-5)).sum()),
+                  "first_frame_vq_index_mismatches": int((tok0 != otr["tok0"].reshape(tok0.shape)).sum()),
+                  "first_diverging_frame_per_row": first_bad, "oracle_seconds": round(time.perf_counter() - t0, 1),
+                  "what": "free-running greedy tokens of rows 0..%d of the timed batch vs oracle.generate_incremental (CPU fp32); a flip at a "
+                          "reference near-tie cascades into the later frames of that row (tests/ re-check those teacher-forced)" % (n - 1)}
 
     # ---- end to end through the public API: pinned host inputs -> H2D -> generate -> D2H of the video
-    out_host = torch.empty(B, L, *host["images"].shape[2:], dtype=torch.float32).pin_memory()
     hb = {"images": host["images"], "text": host["text"], "speed": host["speed"]}
+    out_shape = (B, L, *host["images"].shape[2:])
 
     def step_e2e():
         # public API: pinned host inputs -> H2D -> generate -> the clip back on the host (frames stream out as they are decoded)
         video = model.autoregressive_generate(hb, noise=noise_h, to_host=True)
-        assert not video.is_cuda and tuple(video.shape) == tuple(out_host.shape)
+        assert not video.is_cuda and tuple(video.shape) == out_shape
 
     step_e2e()
     barrier()
@@ -213,25 +343,35 @@ def run_cuda(args, rank, world, local_rank):
     for _ in range(args.steps):
         step_e2e()
     barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = frames_total / float(e2e_s.item())
-    h2d = sum(v.numel() * v.element_size() for v in hb.values()) + noise_h.numel() * 4
-    d2h = out_host.numel() * 4
+    e2e_value = frames_step * args.steps / max_ranks(time.perf_counter() - t0)
+    h2d = sum(v.numel() * v.element_size() for v in hb.values()) + (noise_h.numel() * 4 if noise_h is not None else 0)
+    d2h = 4
+    for d in out_shape:
+        d2h *= d
+
+    # ---- at N > 1 on the strong split: the weak-scaling figure (global batch per GPU) as an extra key
+    weak_extra = None
+    if world > 1 and not weak and not args.no_weak:
+        wparams, _, wb, wn = _workload_inputs(wl, G, seed=1234 + rank, noise_seed=99 + rank)
+        w_in = (wb["images"][:, 0].to(dev), wb["text"].to(dev), wb["speed"].to(dev), wn.to(dev) if wn is not None else None)
+        for _ in range(2):
+            eng.generate(*w_in)
+        wms = max_ranks(_time_resident(eng, w_in, 3, barrier))
+        weak_extra = {"value": round(world * G * (L - 1) * 3 / (wms / 1e3), 2), "unit": UNIT, "batch_per_gpu": G, "steps": 3}
 
     # ---- roofline of the dominant kernel class (dense GEMM of the axial blocks), CUDA events around
     #      every launch of one extra eager step on the launching stream
     roof = None
     if rank == 0:
         eng.use_cuda_graph = False
-        overlap, eng.overlap_decode = eng.overlap_decode, False   # per-kernel durations are taken with the launches serialised
+        saved = (eng.overlap_decode, eng.n_streams)
+        eng.overlap_decode, eng.n_streams = False, 1   # per-kernel durations are taken with the launches serialised on one stream
         ops.PROFILE = []
-        step_resident()
+        eng.generate(*dev_in)
         torch.cuda.synchronize()
         prof, ops.PROFILE = ops.PROFILE, None
         eng.use_cuda_graph = True
-        eng.overlap_decode = overlap
+        eng.overlap_decode, eng.n_streams = saved
         agg = {}
         for kind, flops, a, b in prof:
             d = agg.setdefault(kind, [0.0, 0.0, 0])
@@ -251,62 +391,56 @@ def run_cuda(args, rank, world, local_rank):
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.isfile(tp):
             traffic = json.load(open(tp)).get("gemm_bytes_per_launch")
+        per_gpu_fps = value / world
         roof = {"bound": "tensor", "kernel": "dense GEMM (axial-block linears: QKV, out-proj, MLP, head) -- " +
-                ("tc_gemm_kernel<128,2>: CTA-pair 256x128 tiles (tcgen05 cta_group::2), kind::f16 MMAs on fp16 hi/lo split operands, "
+                ("tc_gemm_kernel: CTA-pair tiles (tcgen05 cta_group::2), kind::f16 MMAs on fp16 hi/lo split operands, "
                  "3 MMAs per product (fp32-grade), TMA loads + TMA-store epilogue" if args.backend == "tc" else "fp32 FFMA"),
                 "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4), "traffic": traffic,
                 "peak_source": how + ", dense bf16 sustained; token parity needs fp32-grade GEMMs: 3 fp16 MMAs per product, so the kernel's own ceiling is peak/3",
                 "launches_per_step": g[2], "gflop_per_launch_avg": round(g[0] / g[2] / 1e9, 3), "ms_in_kernel_per_step": round(g[1], 2),
                 "conv_implicit_gemm": {"achieved": round(c[0] / (c[1] * 1e-3) / 1e12, 2), "launches_per_step": c[2], "ms_per_step": round(c[1], 2)},
-                "whole_step_algorithmic": {"achieved": round(value / world * GFLOP_PER_FRAME / 1e3, 2), "unit": "TFLOP/s",
-                                           "frac": round(value / world * GFLOP_PER_FRAME / 1e3 / peak, 4)},
+                "whole_step_algorithmic": {"achieved": round(per_gpu_fps * wl["gflop"] / 1e3, 2), "unit": "TFLOP/s",
+                                           "frac": round(per_gpu_fps * wl["gflop"] / 1e3 / peak, 4),
+                                           "note": "SURVEY.md §8(d) FLOPs per generated frame; the token 3x3 conv + in_linear (1.34 GFLOP "
+                                                   "per frame, 5.7 %) are counted although they run as per-code table lookups here"},
                 "own_ceiling_frac": round(3.0 * ach / peak, 4) if args.backend == "tc" else None,
                 "breakdown_ms_per_step": breakdown,
-                "how": "sum of algorithmic FLOPs / sum of CUDA-event durations over every launch of the kernel class in one eager step; "
-                       "own_ceiling_frac counts the 3 MMAs issued per product"}
+                "how": "sum of algorithmic FLOPs / sum of CUDA-event durations over every launch of the kernel class in one eager "
+                       "single-stream step of rank 0; own_ceiling_frac counts the 3 MMAs issued per product"}
 
     eager = None
-    overlap_flag = bool(eng.overlap_decode)
     if rank == 0 and args.eager_gpu > 0:
-        # context for the >=10x target of BASELINE.json: the reference algorithm (reference evaluation order, no KV cache) as
-        # plain PyTorch eager ops on this same GPU, PyTorch's default precision flags, at a reduced batch (it is O(L^2))
-        from oracle import mage_oracle as orc
-        overlap_flag = bool(eng.overlap_decode)
         del eng
-        model._engine = None
+        model.invalidate()
         torch.cuda.empty_cache()
-        Be = args.eager_gpu
-        sd_d = {k: v.to(dev) for k, v in sd.items()}
-        eb = {k: v.to(dev) for k, v in syn.make_batch(params, Be, seed=4321, text_len=TEXT_LEN).items()}
-        en = syn.make_noise(Be, seed=7).to(dev)
-        with torch.no_grad():
-            orc.generate(sd_d, {k: v[:1] for k, v in eb.items()}, en[:1])
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            orc.generate(sd_d, eb, en)
-            torch.cuda.synchronize()
-            dt = time.perf_counter() - t0
-        eager = {"value": round(Be * (L - 1) / dt, 2), "unit": UNIT, "batch": Be, "seconds": round(dt, 3),
-                 "kind": "port of the reference algorithm (every step recomputes all L positions), torch eager on the same GPU"}
+        try:
+            eager = eager_gpu_baseline(wl, dev, args.eager_gpu)
+            eager["ratio_resident_per_gpu"] = round(value / world / eager["value"], 1)
+            eager["ratio_e2e_per_gpu"] = round(e2e_value / world / eager["value"], 1)
+        except Exception as e:   # context only: never lose the bench line over it
+            eager = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        v, info = cpu_reference_sample(os.cpu_count() or 1, ar_iters=args.ref_iters)
-        cpu = {"value": round(v, 4), "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": info["sample"]}
+        v, info = cpu_reference_sample(wl, os.cpu_count() or 1, ar_iters=args.ref_iters)
+        cpu = {"value": round(v, 4), "unit": UNIT, "cores": os.cpu_count() or 1, "kind": info["kind"], "sample": info["sample"]}
 
     if rank == 0:
-        line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": round(ms_max / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"CATER-GEN-v2 128x128x{L}, batch {B} per GPU (BASELINE.json configs[4])", "family": FAMILY,
-                           "frames_length": L, "batch_per_gpu": B, "global_batch": B * world, "text_len": TEXT_LEN,
+        S, Gd = plan
+        line = {"metric": wl["metric"], "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": round(ms_max / args.steps, 3), "higher_is_better": True,
+                "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"{wl['name']}, global batch {G * world if weak else G} ({wl['cfg']})", "family": wl["family"],
+                           "frames_length": L, "global_batch": G * world if weak else G, "batch_per_gpu": B, "text_len": TEXT_LEN,
                            "parallelism": f"prompt-shard x{world}, no data-path collective", "backend": args.backend,
-                           "cuda_graph": True, "decode_overlap_stream": overlap_flag,
-                           "l2": "working set >> L2 (K/V cache %.1f GB, decoder activations >1 GB per tensor); no explicit flush" %
+                           "cuda_graph": True, "chunk_streams": S, "decode_group_frames": Gd,
+                           "l2": "working set >> L2 (K/V cache %.1f GB, decoder activations > 126 MB per layer); no explicit flush" %
                                  (2 * 2 * B * 256 * L * 512 * 4 / 1e9)},
                 "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(kernels_per_step * args.steps), "kernels_per_step": int(kernels_per_step),
-                "roofline": roof, "cpu_baseline": cpu, "clocks": clocks}
+                "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "parity": parity}
+        if weak_extra is not None:
+            line["weak_scaling"] = weak_extra
         if eager is not None:
             line["eager_gpu_baseline"] = eager
         print(json.dumps(line), flush=True)
@@ -320,27 +454,32 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH, help="prompts per GPU")
-    ap.add_argument("--frames", type=int, default=FRAMES)
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS), help="BASELINE.json configs[1..4] (default c5 = the metric's)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: the workload's global batch is sharded over the GPUs (BASELINE's split); weak: that batch per GPU")
+    ap.add_argument("--batch", type=int, default=0, help="override the workload's global batch (strong) / per-GPU batch (weak)")
     ap.add_argument("--backend", default=os.environ.get("MAGE_BACKEND", "tc"), choices=["tc", "simt"],
                     help="tc: tcgen05 tensor cores on split-fp16 operands (fp32-grade); simt: fp32 FFMA kernels")
-    ap.add_argument("--ref-iters", type=int, default=3, help="AR iterations timed per CPU sample")
+    ap.add_argument("--ref-iters", type=int, default=0, help="force the extrapolated CPU sample with this many AR iterations (0 = full call)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--eager-gpu", type=int, default=0, metavar="B",
-                    help="also time the reference algorithm as torch eager ops on this GPU at batch B (context only, off by default)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle token check of the timed batch's first rows")
+    ap.add_argument("--no-weak", action="store_true", help="skip the extra weak-scaling measurement at N > 1")
+    ap.add_argument("--eager-gpu", type=int, default=8, metavar="B",
+                    help="time the reference's eager-PyTorch path on this GPU at batch B (the >=10x target's denominator; 0 = skip)")
     args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, wl, rank)
         return
     if world == 1 and args.gpus > 1:
         # convenience: re-launch under torchrun
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
-    run_cuda(args, rank, world, local_rank)
+    run_cuda(args, wl, rank, world, local_rank)
 
 
 if __name__ == "__main__":

@@ -41,7 +41,7 @@ extern "C" {
 #define MAGE_RES_RELU 0x200     /* read the residual through a ReLU (in-place ReLU skip of ResBlock, vqvae_model.py:114-124) */
 
 /* Library info / bookkeeping */
-int mage_abi_version(void); /* 3 */
+int mage_abi_version(void); /* 4 */
 /* Number of kernels launched through this library by the calling process so far. */
 int64_t mage_launch_count(void);
 
@@ -129,12 +129,17 @@ int mage_gemm_tc(const void* A, int64_t lda, int64_t a_plane, const void* W, int
  * split input [n_img,Hin,Win,Cin] shifted by (ky-pad_y, kx-pad_x); out-of-bounds zero fill is the padding.
  * w split [Cout][KH][KW][Cin]; Cin % 64 == 0, Cout % 64 == 0, 128 % min(Wout,128) == 0 (else MAGE_ENOTSUP).
  * Output scatter / residual modes as mage_conv2d_nhwc_f32; outputs as mage_gemm_tc.  Same reference call
- * sites as mage_conv2d_nhwc_f32. */
+ * sites as mage_conv2d_nhwc_f32, plus the f4 stack's stride-2 / transposed convolutions (vqvae_model.py:175,184) once the
+ * caller has rewritten them as stride-1 convolutions (mage_s2d_pad_split_f32; 2x2 sub-pixel phases).
+ * passes: 3 = fp32-grade products (hi*hi + lo*hi + hi*lo); 1 = hi*hi only (plain fp16 operands, fp32 accumulation; only the
+ * hi planes are fetched) -- allowed ONLY where the result feeds no token: the last block of the VQ-VAE decoder, whose pixel
+ * error stays inside the 1e-3 bar (tests/test_gpu_parity.py::test_decoder_precision_budget).  A shape the single-pass kernel
+ * does not cover silently runs with 3 passes. */
 int mage_conv2d_tc(const void* in, int64_t in_plane, const void* w, int64_t w_plane, const float* bias,
                    const float* residual, float* out, void* out_split, void* out_split_relu, int64_t out_plane,
                    int n_img, int Hin, int Win, int Cin, int Hout, int Wout, int Cout, int KH, int KW, int pad_y,
                    int pad_x, int res_mode, int act, int out_sy, int out_sx, int out_oy, int out_ox, int Hfull,
-                   int Wfull, int64_t out_img_stride, int* flag, void* stream);
+                   int Wfull, int64_t out_img_stride, int passes, int* flag, void* stream);
 
 /* mage_conv2d_tc fused with the decoder's pixel head (vqvae_model.py:210-213: DecoderBlock conv -> ReLU -> Conv2d(dim,C,1) ->
  * Tanh): the conv result x[row, 0..255] (+ bias + residual, never written to memory) is reduced in the epilogue to
@@ -143,7 +148,7 @@ int mage_conv2d_tc(const void* in, int64_t in_plane, const void* w, int64_t w_pl
 int mage_conv2d_tc_pixel_head(const void* in, int64_t in_plane, const void* w, int64_t w_plane, const float* bias,
                               const float* residual, int n_img, int Hin, int Win, int Cin, int Hout, int Wout, int Cout,
                               int KH, int KW, int pad_y, int pad_x, int res_mode, const float* head_w, const float* head_b,
-                              int head_cout, float* head_out, int64_t head_img_stride, int* flag, void* stream);
+                              int head_cout, float* head_out, int64_t head_img_stride, int passes, int* flag, void* stream);
 
 /* First-layer convolution from a planar NCHW image with a tiny channel count (Cin <= 4):
  * in [N,Cin,H,W], w_t [Cin*KH*KW][Cout] (transposed), out NHWC [N,Hout,Wout,Cout], optional ReLU.
@@ -218,10 +223,11 @@ int mage_token_taps_f32(const int64_t* tok, const float* table, const float* pos
                         int n_img, int R, int K, int C, int KH, int KW, void* stream);
 
 /* Text-encoder front end (mage_model.py:224-237): x[b,t,:] = LN_eps(tok_emb[text[b,t]] + pos_emb[t]) * (text[b,t] != pad);
- * key_len[b] = #non-pad tokens.  C = 512. */
+ * key_len[b] = #non-pad tokens.  C = 512.  tok_emb has `vocab` rows: an id outside [0, vocab) -- on which the reference's
+ * nn.Embedding raises (mage_model.py:228) -- is never dereferenced; bit 1 of *flag is set instead (the host raises after the call). */
 int mage_text_embed_f32(const int64_t* text, const float* tok_emb, const float* pos_emb,
                         const float* gamma, const float* beta, float* x, int32_t* key_len,
-                        int B, int T, int C, int pad_idx, float eps, void* stream);
+                        int B, int T, int C, int pad_idx, float eps, int vocab, int* flag, void* stream);
 
 /* AdaIN (mage_model.py:309-314): out = gamma * InstanceNorm(x) + beta over the HW positions of each
  * (image, channel); x/gamma/beta/out NHWC [N,HW,C]; out may alias x. */

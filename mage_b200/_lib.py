@@ -12,6 +12,8 @@ import subprocess
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB_PATH = os.environ.get("MAGE_LIB") or os.path.join(CSRC, "libmage_sm100.so")   # MAGE_LIB: experiment builds (tools/experiments)
 
+ABI_VERSION = 4   # include/mage_b200.h: mage_abi_version()
+
 _c_f = ctypes.c_void_p  # device pointers travel as integers
 _i = ctypes.c_int
 _i64 = ctypes.c_int64
@@ -32,8 +34,8 @@ SIGNATURES = {
     "mage_embedding_split": [_c_f, _c_f, _i64, _c_f, _i64, _i, _i, _c_f],
     "mage_gemm_tc": [_c_f, _i64, _i64, _c_f, _i64, _i64, _c_f, _c_f, _i64, _i, _c_f, _c_f, _c_f, _i64, _i64, _i, _i, _i, _i,
                      _c_f, _c_f],
-    "mage_conv2d_tc": [_c_f, _i64, _c_f, _i64, _c_f, _c_f, _c_f, _c_f, _c_f, _i64] + [_i] * 19 + [_i64, _c_f, _c_f],
-    "mage_conv2d_tc_pixel_head": [_c_f, _i64, _c_f, _i64, _c_f, _c_f] + [_i] * 12 + [_c_f, _c_f, _i, _c_f, _i64, _c_f, _c_f],
+    "mage_conv2d_tc": [_c_f, _i64, _c_f, _i64, _c_f, _c_f, _c_f, _c_f, _c_f, _i64] + [_i] * 19 + [_i64, _i, _c_f, _c_f],
+    "mage_conv2d_tc_pixel_head": [_c_f, _i64, _c_f, _i64, _c_f, _c_f] + [_i] * 12 + [_c_f, _c_f, _i, _c_f, _i64, _i, _c_f, _c_f],
     "mage_conv2d_first_f32": [_c_f] * 4 + [_i] * 12 + [_c_f],
     "mage_conv1x1_tanh_nchw_f32": [_c_f] * 4 + [_i] * 4 + [_i64, _c_f],
     "mage_maxpool2x2_nhwc_f32": [_c_f, _c_f, _i, _i, _i, _i, _c_f],
@@ -46,7 +48,7 @@ SIGNATURES = {
     "mage_argmax_rows_f32": [_c_f, _i64, _c_f, _i, _i, _c_f],
     "mage_embedding_f32": [_c_f] * 3 + [_i, _i, _c_f],
     "mage_token_taps_f32": [_c_f] * 5 + [_i] * 6 + [_c_f],
-    "mage_text_embed_f32": [_c_f] * 7 + [_i] * 4 + [_f32, _c_f],
+    "mage_text_embed_f32": [_c_f] * 7 + [_i] * 4 + [_f32, _i, _c_f, _c_f],
     "mage_adain_nhwc_f32": [_c_f] * 4 + [_i] * 3 + [_f32, _c_f],
     "mage_add_scaled_vec_f32": [_c_f] * 3 + [_i] * 3 + [_c_f],
     "mage_nchw_to_nhwc_f32": [_c_f, _c_f, _i, _i, _i, _c_f],

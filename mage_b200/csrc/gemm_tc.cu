@@ -71,6 +71,10 @@ struct TcParams {
   int group;
   // halo mode (tc_conv_halo_kernel): taps = KH*KW, halo patch pitch in pixels, bytes of one plane / of the whole patch
   int taps, halo_w, a_plane_bytes, a_tx_bytes;
+  // passes = 3: fp32-grade product (hi*hi + lo*hi + hi*lo).  passes = 1 (halo kernel only): hi*hi alone -- plain fp16 operands
+  // with fp32 accumulation, for layers whose result feeds no token (the last VQ-VAE decoder block: DESIGN.md "decoder
+  // precision budget"); only the hi planes are fetched (w_tx_bytes / a_tx_bytes halve) and the corr accumulator is never read.
+  int passes, w_tx_bytes;
 };
 
 template <int BN, int CG>
@@ -125,6 +129,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
   uint8_t* const stg = staging + (warp - 2) * 4096;
   const uint32_t stg_s = smem_u32(stg);
   const bool res_relu = (p.act & MAGE_RES_RELU) != 0, post = (p.act & MAGE_ACT_POST_RES) != 0;
+  const bool single = kOneAcc || p.passes == 1;   // no corr accumulator to fold in
   const float* const __restrict__ bias = p.bias;
   const float* const __restrict__ res = p.res;
   const bool has_out = p.out != nullptr, has_split = p.split != nullptr, has_relu = p.split_relu != nullptr;
@@ -181,7 +186,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
       const int tc_col = NS ? (c & 3) * 32 : c * 32;
       uint32_t rm[32], rc[32];
       tmem_ld32(t_main + tc_col, rm);
-      if (!kOneAcc) tmem_ld32(t_corr + tc_col, rc);
+      if (!single) tmem_ld32(t_corr + tc_col, rc);
       // the residual row segment travels while the TMEM loads complete
       float4 rv[8];
       if (res_off >= 0) {
@@ -200,7 +205,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
       }
       float v[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = kOneAcc ? __uint_as_float(rm[j]) : fmaf(__uint_as_float(rc[j]), kLoInv, __uint_as_float(rm[j]));
+      for (int j = 0; j < 32; ++j) v[j] = single ? __uint_as_float(rm[j]) : fmaf(__uint_as_float(rc[j]), kLoInv, __uint_as_float(rm[j]));
       if (bias) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -631,11 +636,11 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             if (CG == 2) {
               const uint32_t fb = mapa_u32(w_full(s), 0);
               if (elect_one()) {
-                if (cta_rank == 0) mbar_expect_tx(w_full(s), 2 * H::W_BYTES);
+                if (cta_rank == 0) mbar_expect_tx(w_full(s), 2 * p.w_tx_bytes);
                 tma_load_3d_2sm(dst, &mapW, fb, k0, w_row, 0);
               }
             } else if (elect_one()) {
-              mbar_expect_tx(w_full(s), H::W_BYTES);
+              mbar_expect_tx(w_full(s), p.w_tx_bytes);
               tma_load_3d(dst, &mapW, w_full(s), k0, w_row, 0);
             }
             __syncwarp();
@@ -673,6 +678,15 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             const uint64_t w_hi = umma_desc_sw128(w_addr), w_lo = umma_desc_sw128(w_addr + H::W_ROWS * BK * 2);
             const bool last_tap = tap + 1 == p.taps, last = last_tap && cb + 1 == p.cin_blocks;
             if (elect_one()) {
+              if (p.passes == 1) {
+#pragma unroll
+                for (int k = 0; k < BK / UK; ++k) {
+                  const uint64_t adv = (uint64_t)((k * UK * 2) >> 4);
+                  const uint32_t accum = (cb > 0 || tap > 0 || k > 0) ? 1u : 0u;
+                  if (CG == 2) umma_f16_2sm(d_main, a_hi + adv, w_hi + adv, idesc, accum);
+                  else umma_f16(d_main, a_hi + adv, w_hi + adv, idesc, accum);
+                }
+              } else {
 #pragma unroll
               for (int k = 0; k < BK / UK; ++k) {
                 const uint64_t adv = (uint64_t)((k * UK * 2) >> 4);
@@ -686,6 +700,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                   umma_f16(d_corr, a_hi + adv, w_lo + adv, idesc, 1u);
                   umma_f16(d_main, a_hi + adv, w_hi + adv, idesc, kOneAcc ? 1u : accum);
                 }
+              }
               }
               if (CG == 2) {
                 umma_commit_2sm(w_empty(sw), 3);
@@ -996,10 +1011,10 @@ int dispatch_halo(TileCfg c, const Maps& mp, const TcParams& p, cudaStream_t st)
   return MAGE_ENOTSUP;
 }
 
-int make_w_map(CUtensorMap* map, const void* W, int64_t ldw, int64_t w_plane, int N, int K, int box_rows) {
+int make_w_map(CUtensorMap* map, const void* W, int64_t ldw, int64_t w_plane, int N, int K, int box_rows, int planes = 2) {
   const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)N, 2};
   const cuuint64_t strides[2] = {(cuuint64_t)ldw * 2, (cuuint64_t)w_plane * 2};
-  const cuuint32_t box[3] = {BK, (cuuint32_t)box_rows, 2};
+  const cuuint32_t box[3] = {BK, (cuuint32_t)box_rows, (cuuint32_t)planes};
   return make_map(map, W, 3, dims, strides, box);
 }
 
@@ -1100,8 +1115,8 @@ int conv2d_tc_impl(const void* in, int64_t in_plane, const void* w, int64_t w_pl
                    const float* residual, float* out, void* out_split, void* out_split_relu, int64_t out_plane,
                    int n_img, int Hin, int Win, int Cin, int Hout, int Wout, int Cout, int KH, int KW, int pad_y,
                    int pad_x, int res_mode, int act, int out_sy, int out_sx, int out_oy, int out_ox, int Hfull,
-                   int Wfull, int64_t out_img_stride, int* flag, void* stream, const HeadArgs* head) {
-  MAGE_CHECK_ARG(n_img > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && Hout > 0 && Wout > 0);
+                   int Wfull, int64_t out_img_stride, int* flag, void* stream, const HeadArgs* head, int passes) {
+  MAGE_CHECK_ARG(n_img > 0 && Cin > 0 && Cout > 0 && KH > 0 && KW > 0 && Hout > 0 && Wout > 0 && (passes == 1 || passes == 3));
   if (Cin % BK != 0 || Cout % 64 != 0) return MAGE_ENOTSUP;
   // halo mode: 16x8-pixel tiles, the input patch is fetched once per channel block and shared by all taps
   const int act_id = act & 0xff;
@@ -1147,10 +1162,12 @@ int conv2d_tc_impl(const void* in, int64_t in_plane, const void* w, int64_t w_pl
     const cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)n_img, 2};
     const cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)Win * Cin * 2, (cuuint64_t)Hin * Win * Cin * 2,
                                    (cuuint64_t)in_plane * 2};
-    const cuuint32_t box[5] = {BK, (cuuint32_t)(halo ? Wb + KW - 1 : Wb), (cuuint32_t)(halo ? Hb + KH - 1 : Hb), 1, 2};
+    // single-pass (hi*hi only) exists in the halo kernel; elsewhere the request falls back to the fp32-grade product
+    const int planes = (halo && passes == 1) ? 1 : 2;
+    const cuuint32_t box[5] = {BK, (cuuint32_t)(halo ? Wb + KW - 1 : Wb), (cuuint32_t)(halo ? Hb + KH - 1 : Hb), 1, (cuuint32_t)planes};
     int r = make_map(&mapA, in, 5, dims, strides, box);
     if (r) return r;
-    r = make_w_map(&mapW, w, K, w_plane, Cout, K, bn / tcfg.cg);
+    r = make_w_map(&mapW, w, K, w_plane, Cout, K, bn / tcfg.cg, planes);
     if (r) return r;
   }
   TcParams p{};
@@ -1183,7 +1200,9 @@ int conv2d_tc_impl(const void* in, int64_t in_plane, const void* w, int64_t w_pl
   }
   if (halo) {
     p.taps = KH * KW; p.halo_w = Wb + KW - 1;
-    p.a_plane_bytes = (Hb + KH - 1) * (Wb + KW - 1) * 128; p.a_tx_bytes = 2 * p.a_plane_bytes;
+    p.passes = passes;
+    p.a_plane_bytes = (Hb + KH - 1) * (Wb + KW - 1) * 128; p.a_tx_bytes = (passes == 1 ? 1 : 2) * p.a_plane_bytes;
+    p.w_tx_bytes = (passes == 1 ? 1 : 2) * (bn / tcfg.cg) * BK * 2;
     return dispatch_halo(tcfg, mp, p, as_stream(stream));
   }
   return dispatch(tcfg, mp, p, as_stream(stream));
@@ -1194,19 +1213,19 @@ extern "C" int mage_conv2d_tc(const void* in, int64_t in_plane, const void* w, i
                               const float* residual, float* out, void* out_split, void* out_split_relu, int64_t out_plane,
                               int n_img, int Hin, int Win, int Cin, int Hout, int Wout, int Cout, int KH, int KW, int pad_y,
                               int pad_x, int res_mode, int act, int out_sy, int out_sx, int out_oy, int out_ox, int Hfull,
-                              int Wfull, int64_t out_img_stride, int* flag, void* stream) {
+                              int Wfull, int64_t out_img_stride, int passes, int* flag, void* stream) {
   return conv2d_tc_impl(in, in_plane, w, w_plane, bias, residual, out, out_split, out_split_relu, out_plane, n_img, Hin, Win, Cin,
                         Hout, Wout, Cout, KH, KW, pad_y, pad_x, res_mode, act, out_sy, out_sx, out_oy, out_ox, Hfull, Wfull,
-                        out_img_stride, flag, stream, nullptr);
+                        out_img_stride, flag, stream, nullptr, passes);
 }
 
 extern "C" int mage_conv2d_tc_pixel_head(const void* in, int64_t in_plane, const void* w, int64_t w_plane, const float* bias,
                                          const float* residual, int n_img, int Hin, int Win, int Cin, int Hout, int Wout,
                                          int Cout, int KH, int KW, int pad_y, int pad_x, int res_mode, const float* head_w,
                                          const float* head_b, int head_cout, float* head_out, int64_t head_img_stride,
-                                         int* flag, void* stream) {
+                                         int passes, int* flag, void* stream) {
   const HeadArgs h{head_w, head_b, head_out, head_cout, head_img_stride};
   return conv2d_tc_impl(in, in_plane, w, w_plane, bias, residual, nullptr, nullptr, nullptr, 0, n_img, Hin, Win, Cin, Hout, Wout,
                         Cout, KH, KW, pad_y, pad_x, res_mode, MAGE_ACT_NONE, 1, 1, 0, 0, Hout, Wout,
-                        (int64_t)Hout * Wout * Cout, flag, stream, &h);
+                        (int64_t)Hout * Wout * Cout, flag, stream, &h, passes);
 }

@@ -9,7 +9,7 @@
 int g_mage_pdl = [] { const char* e = getenv("MAGE_PDL"); return e ? atoi(e) : 0; }();
 int64_t g_mage_launches = 0;
 
-extern "C" int mage_abi_version(void) { return 3; }
+extern "C" int mage_abi_version(void) { return 4; }
 extern "C" int64_t mage_launch_count(void) { return g_mage_launches; }
 extern "C" int mage_pdl(int enable) {
   g_mage_pdl = enable != 0;
@@ -170,13 +170,20 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const float* __restrict__ 
 __global__ void __launch_bounds__(256) text_embed_kernel(const int64_t* __restrict__ text, const float* __restrict__ tok_emb,
                                                          const float* __restrict__ pos_emb, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, float* __restrict__ x,
-                                                         int32_t* __restrict__ key_len, int B, int T, int pad_idx, float eps) {
+                                                         int32_t* __restrict__ key_len, int B, int T, int pad_idx, float eps,
+                                                         int vocab, int* flag) {
   constexpr int NV = 4, C = 512;
   const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (w >= B * T) return;
   const int b = w / T, t = w - b * T;
-  const int64_t tok = text[w];
+  int64_t tok = text[w];
+  if (tok < 0 || tok >= vocab) {
+    // nn.Embedding raises on an id outside the table (mage_model.py:228); never read out of bounds: flag it (the host raises
+    // IndexError after the call) and embed the padding row instead
+    if (lane == 0 && flag) atomicOr(flag, 2);
+    tok = pad_idx;
+  }
   if (t == 0) {
     int cnt = 0;
     for (int i = lane; i < T; i += 32) cnt += (text[b * T + i] != pad_idx) ? 1 : 0;
@@ -415,10 +422,11 @@ extern "C" int mage_maxpool2x2_nhwc_f32(const float* in, float* out, int n_img, 
 
 extern "C" int mage_text_embed_f32(const int64_t* text, const float* tok_emb, const float* pos_emb, const float* gamma,
                                    const float* beta, float* x, int32_t* key_len, int B, int T, int C, int pad_idx,
-                                   float eps, void* stream) {
+                                   float eps, int vocab, int* flag, void* stream) {
   MAGE_CHECK_ARG(B > 0 && T > 0 && C == 512 && aligned16(tok_emb) && aligned16(pos_emb) && aligned16(x));
+  MAGE_CHECK_ARG(vocab > 0 && pad_idx >= 0 && pad_idx < vocab);
   text_embed_kernel<<<(B * T + 7) / 8, 256, 0, as_stream(stream)>>>(text, tok_emb, pos_emb, gamma, beta, x, key_len, B, T,
-                                                                   pad_idx, eps);
+                                                                   pad_idx, eps, vocab, flag);
   return mage_post_launch();
 }
 

@@ -73,6 +73,13 @@ class VQVAEEngine:
         if self.down_ratio != 8:
             self.backend = "simt"  # the f4 (MNIST) stack keeps the fp32 FFMA kernels (stride-2 / Cout=1 layers)
         ops.flag(self.device)
+        # Decoder precision budget: the decoder feeds no token and its bar is 1e-3 relative on pixels (north_star),
+        # so the two convolutions that hold 63 % of its FLOPs -- block.5 and block.7 (+ fused pixel head) of the last, 128x128
+        # block -- run single-pass (fp16 operands, fp32 accumulation) instead of the 3-MMA fp32-grade product: measured pixel
+        # rel-L2 3.6e-4 .. 5.8e-4 against fp32 (tools/experiments/decoder_precision_emulation.py, tests::test_decoder_precision_budget).
+        # "fp32" keeps every layer fp32-grade (pixels ~1e-6).  The encoder and everything that feeds a token is always fp32-grade.
+        self.decoder_precision = os.environ.get("MAGE_DECODER_PRECISION", "budget")
+        assert self.decoder_precision in ("budget", "fp32"), self.decoder_precision
         self.codebook = sd["codebook.embedding.weight"].contiguous()
         self.K, self.D = self.codebook.shape
         w = {}
@@ -275,14 +282,15 @@ class VQVAEEngine:
             else:
                 _, h2, _ = ops.conv2d_tc(h, ws[name + ".block.3.weight"], w[name + ".block.3.bias"], pad=(1, 1), act=ACT_RELU,
                                          want=("split",))
+            last_passes = 1 if (bi + 1 == len(blocks) and self.decoder_precision == "budget") else 3
             _, h3, _ = ops.conv2d_tc(h2, ws[name + ".block.5.weight"], w[name + ".block.5.bias"], pad=(1, 1), act=ACT_RELU,
-                                     want=("split",))
+                                     want=("split",), passes=last_passes)
             if bi + 1 == len(blocks) and h3.shape[-1] % 64 == 0 and w[name + ".block.7.weight"].shape[0] == 256 \
                     and w["decoder.8.bias"].numel() <= 3:
                 # last block: block.7 conv + skip, ReLU, 1x1 conv to pixels and tanh in ONE kernel (the [n,128,128,256] map stays on chip)
                 ops.conv2d_tc_pixel_head(h3, ws[name + ".block.7.weight"], w[name + ".block.7.bias"], pad=(1, 1), residual=idp,
                                          res_mode=2 if up else 1, head_w=w["decoder.8.weight"], head_b=w["decoder.8.bias"],
-                                         out=out, out_img_stride=out_img_stride)
+                                         out=out, out_img_stride=out_img_stride, passes=last_passes)
                 return
             if bi + 1 == len(blocks):
                 want = ("f32",)
@@ -291,7 +299,7 @@ class VQVAEEngine:
             else:
                 want = ("f32", "split_relu")
             x_f32, x_split, xr_split = ops.conv2d_tc(h3, ws[name + ".block.7.weight"], w[name + ".block.7.bias"], pad=(1, 1),
-                                                     residual=idp, res_mode=2 if up else 1, want=want)
+                                                     residual=idp, res_mode=2 if up else 1, want=want, passes=last_passes)
         ops.conv1x1_tanh_nchw(x_f32, w["decoder.8.weight"], w["decoder.8.bias"], out, out_img_stride)
 
     def decode_into(self, idx: torch.Tensor, out: torch.Tensor, out_img_stride: int) -> None:
@@ -380,12 +388,17 @@ class SamplerEngine:
         self.kernels_per_generate = None
         # The VQ-VAE decode of frame j depends only on that frame's tokens and nothing downstream depends on it, so it runs on a
         # side stream next to transformer step j+1: the tails / launch gaps of one kernel sequence are filled by the other.
-        self.overlap_decode = os.environ.get("MAGE_OVERLAP_DECODE", "0") != "0"   # measured: no gain on B200 (154.2 vs 154.4 ms), off by default
+        self.overlap_decode = os.environ.get("MAGE_OVERLAP_DECODE", "0") != "0"   # measured at B=64: no gain (154.2 vs 154.4 ms), off there
         self._side = None
         self._copy = None
+        self._chunk_streams = []
+        self._pool = None
+        self.max_graphs = max(1, int(os.environ.get("MAGE_MAX_GRAPHS", "8")))
         # frames are decoded in groups of `decode_group` steps (one VQ-VAE decoder pass over group*B images): the low-resolution
-        # decoder layers are too small to fill 148 SMs at B images, and a frame's pixels are not needed before the call returns
-        self.decode_group = max(1, int(os.environ.get("MAGE_DECODE_GROUP", "4")))
+        # decoder layers are too small to fill 148 SMs at B images, and a frame's pixels are not needed before the call returns.
+        # 0 = chosen from the batch size (`_plan`); likewise the number of chunk streams.
+        self.decode_group = max(0, int(os.environ.get("MAGE_DECODE_GROUP", "0")))
+        self.n_streams = max(0, int(os.environ.get("MAGE_STREAMS", "0")))
         if self.backend == "tc":
             # split (fp16 hi/lo) copies of the per-step tensor-core operands
             ws = {"E": ops.split(self.E), "Wc": ops.split(self.Wc)}
@@ -599,19 +612,15 @@ class SamplerEngine:
         return x
 
     # ------------------------------------------------------------------ whole path
-    def _generate_impl(self, images0: torch.Tensor, text: torch.Tensor, speed: Optional[torch.Tensor],
-                       noise: Optional[torch.Tensor], video: torch.Tensor, tokens: torch.Tensor, tok0_out: torch.Tensor,
-                       trace: Optional[dict] = None, host_video: Optional[torch.Tensor] = None) -> None:
-        """images0 [B,Cimg,Himg,Wimg]; text i64 [B,T]; video FRAME-MAJOR [L,B,Cimg,Himg,Wimg] (frame 0 = images0, each generated
-        frame of the whole batch is one contiguous block); host_video: optional pinned host tensor of the same shape that
-        receives every frame over a copy stream as soon as it is decoded (the D2H overlaps the following steps);
-        tokens i64 [L-1, B, R*R] (step-major); tok0_out i64 [B, R*R]."""
+    def _prelude(self, images0: torch.Tensor, text: torch.Tensor, speed: Optional[torch.Tensor], noise: Optional[torch.Tensor],
+                 tok0_out: torch.Tensor, trace: Optional[dict]) -> dict:
+        """Everything that runs once per prompt (SURVEY.md App. D `prelude`) for one chunk of the batch, up to and including the
+        motion anchor's pass through the six blocks as temporal position 0 (fills the K/V caches).  Returns the chunk's decode
+        state: residual stream x, K/V caches, scratch buffers."""
         sd, C, R, L = self.sd, self.C, self.R, self.L
         B, T = text.shape
         M = B * R * R
         p = "generate_model."
-        video[0].copy_(images0)   # output frame 0 is the raw input frame (mage_model.py:691)
-        self._frame_to_host(video, host_video, 0)
         z = self.vq.encode_features(images0)
         ops.vq_argmin(z.view(M, -1), self.vq.codebook, out=tok0_out.view(-1))
         tc = self.backend == "tc"
@@ -630,70 +639,124 @@ class SamplerEngine:
             ops.add_scaled_vec(anchor, speed, sd["speed_embedding"].view(-1))
         if trace is not None:
             trace["anchor"] = anchor.clone()
-
         caches = {i: (torch.empty(M, L, C, device=self.device, dtype=torch.float32),
                       torch.empty(M, L, C, device=self.device, dtype=torch.float32))
                   for i in range(self.n_blocks) if i % 3 == 0}
+        bufs = None
         if tc:
-            ws = self.ws
-            x, _, _ = ops.gemm_tc(ops.split(anchor.view(M, C)), ws[p + "context_linear.weight"], self.bias_ctx0)
-        else:
-            x = ops.gemm(anchor.view(M, C), sd[p + "context_linear.weight"], self.bias_ctx0)
-        if tc:
+            x, _, _ = ops.gemm_tc(ops.split(anchor.view(M, C)), self.ws[p + "context_linear.weight"], self.bias_ctx0)
             bufs = {"u": torch.empty(2, M, C, device=self.device, dtype=torch.float16),
                     "h": torch.empty(2, M, 4 * C, device=self.device, dtype=torch.float16),
                     "qkv": torch.empty(M, 3 * C, device=self.device, dtype=torch.float32)}
+        else:
+            x = ops.gemm(anchor.view(M, C), sd[p + "context_linear.weight"], self.bias_ctx0)
         for i in range(self.n_blocks):
             x = self._block_step_tc(i, x, 0, B, caches, bufs, False) if tc else self._block_step(i, x, 0, B, caches)
-        tok = tok0_out
-        img_elems = video.shape[2] * video.shape[3] * video.shape[4]   # frame-major video: images of one frame are adjacent
         logits = torch.empty(M, sd[p + "out.weight"].shape[0], device=self.device, dtype=torch.float32)
-        for j in range(L - 1):
-            if tc:
-                if self.tok_table is not None:
-                    ops.token_taps(tok.view(B, R, R), self.tok_table, self.tok_posW, self.bias_in_T[j + 1], x)
-                else:
-                    f = self._token_features_tc(tok, B)
-                    ops.gemm_tc(f, ws[p + "in_linear.weight"], self.bias_in_T[j + 1], out=x)
-                for i in range(self.n_blocks):
-                    x = self._block_step_tc(i, x, j + 1, B, caches, bufs, i + 1 == self.n_blocks)
-                ops.gemm_tc(bufs["u"], ws[p + "out.weight"], sd[p + "out.bias"], out=logits)
+        return dict(B=B, x=x, caches=caches, bufs=bufs, logits=logits, tok=tok0_out)
+
+    def _decode_step(self, st: dict, j: int, tok_out: torch.Tensor, trace: Optional[dict]) -> None:
+        """Temporal position j+1 of one chunk: features of the previous frame's tokens -> six blocks -> head -> greedy tokens of
+        frame j+1 into `tok_out` (int64 [B*R*R], a slice of the step-major token buffer)."""
+        sd, R = self.sd, self.R
+        p = "generate_model."
+        B, x, caches, bufs, logits, tok = st["B"], st["x"], st["caches"], st["bufs"], st["logits"], st["tok"]
+        if self.backend == "tc":
+            ws = self.ws
+            if self.tok_table is not None:
+                ops.token_taps(tok.view(B, R, R), self.tok_table, self.tok_posW, self.bias_in_T[j + 1], x)
             else:
-                f = self._token_features(tok, B)
-                x = ops.gemm(f, sd[p + "in_linear.weight"], self.bias_in_T[j + 1])
-                for i in range(self.n_blocks):
-                    x = self._block_step(i, x, j + 1, B, caches)
-                ops.gemm(x, sd[p + "out.weight"], sd[p + "out.bias"], out=logits)
-            tok = ops.argmax_rows(logits, out=tokens[j].view(-1))
-            if trace is not None:
-                trace.setdefault("logits", []).append(logits.clone())
-                if trace.get("force_tokens") is not None:
-                    # teacher forcing (parity diagnostics): this step's prediction is recorded, but the NEXT step is fed the
-                    # given token map -- a near-tie flip then cannot cascade into later frames
-                    tok = trace["force_tokens"][:, j].reshape(-1).contiguous()
-            # decode the finished group of frames for every sample: video[j0+1 .. j+1] (frame-major, contiguous)
-            if (j + 1) % self.decode_group == 0 or j == L - 2:
-                j0 = (j // self.decode_group) * self.decode_group
-                toks = tokens[j0:j + 1].view(-1, R, R)            # [(j-j0+1)*B, R, R], frame-major like the video buffer
-                if self.overlap_decode and trace is None:
-                    main = torch.cuda.current_stream()
-                    if self._side is None:
-                        self._side = torch.cuda.Stream(device=self.device)
-                    ready = torch.cuda.Event()
-                    ready.record(main)
-                    self._side.wait_event(ready)
-                    with torch.cuda.stream(self._side):
-                        self.vq.decode_into(toks, video[j0 + 1], img_elems)
-                        for f in range(j0 + 1, j + 2):
-                            self._frame_to_host(video, host_video, f)
-                else:
-                    self.vq.decode_into(toks, video[j0 + 1], img_elems)
-                    for f in range(j0 + 1, j + 2):
-                        self._frame_to_host(video, host_video, f)
-        if self.overlap_decode and trace is None and self._side is not None:
-            torch.cuda.current_stream().wait_stream(self._side)   # join (also required before a graph capture ends)
+                f = self._token_features_tc(tok, B)
+                ops.gemm_tc(f, ws[p + "in_linear.weight"], self.bias_in_T[j + 1], out=x)
+            for i in range(self.n_blocks):
+                x = self._block_step_tc(i, x, j + 1, B, caches, bufs, i + 1 == self.n_blocks)
+            ops.gemm_tc(bufs["u"], ws[p + "out.weight"], sd[p + "out.bias"], out=logits)
+        else:
+            f = self._token_features(tok, B)
+            x = ops.gemm(f, sd[p + "in_linear.weight"], self.bias_in_T[j + 1])
+            for i in range(self.n_blocks):
+                x = self._block_step(i, x, j + 1, B, caches)
+            ops.gemm(x, sd[p + "out.weight"], sd[p + "out.bias"], out=logits)
+        st["x"] = x
+        st["tok"] = ops.argmax_rows(logits, out=tok_out)
+        if trace is not None:
+            trace.setdefault("logits", []).append(logits.clone())
+            if trace.get("force_tokens") is not None:
+                # teacher forcing (parity diagnostics): this step's prediction is recorded, but the NEXT step is fed the
+                # given token map -- a near-tie flip then cannot cascade into later frames
+                st["tok"] = trace["force_tokens"][:, j].reshape(-1).contiguous()
+
+    def _plan(self, B: int):
+        """(number of chunk streams, decode group) for a batch of B prompts.  Small batches are latency-bound (a decode step is
+        45 launches of a few microseconds each): the batch is cut into chunks whose launch sequences run concurrently on their
+        own streams, and the VQ-VAE decoder -- which nothing downstream depends on -- runs over larger groups of frames on a
+        side stream next to them.  Large batches fill the machine on their own: one stream, groups of 4 frames."""
+        S = self.n_streams
+        if S <= 0:
+            S = 1 if B >= 32 else (2 if B >= 4 else 1)
+        S = max(1, min(S, B))
+        G = self.decode_group
+        if G <= 0:
+            G = 4 if B >= 32 else max(4, min(self.L - 1, 128 // max(B, 1)))
+        return S, G
+
+    def _generate_impl(self, images0: torch.Tensor, text: torch.Tensor, speed: Optional[torch.Tensor],
+                       noise: Optional[torch.Tensor], video: torch.Tensor, tokens: torch.Tensor, tok0_out: torch.Tensor,
+                       trace: Optional[dict] = None, host_video: Optional[torch.Tensor] = None) -> None:
+        """images0 [B,Cimg,Himg,Wimg]; text i64 [B,T]; video FRAME-MAJOR [L,B,Cimg,Himg,Wimg] (frame 0 = images0, each generated
+        frame of the whole batch is one contiguous block); host_video: optional pinned host tensor of the same shape that
+        receives every frame over a copy stream as soon as it is decoded (the D2H overlaps the following steps);
+        tokens i64 [L-1, B, R*R] (step-major); tok0_out i64 [B, R*R].
+
+        Schedule: the batch is cut into S contiguous chunks (`_plan`); chunk c runs its prelude and its L-1 decode steps on its
+        own stream, the VQ-VAE decoder runs over groups of G finished frames of the WHOLE batch on a decode stream, frames leave
+        for the host on a copy stream.  Rows are independent and every kernel is deterministic, so the schedule cannot change a
+        bit of the result (tests/test_gpu_parity.py::test_optional_schedules_are_bit_exact)."""
+        R, L = self.R, self.L
+        B = text.shape[0]
+        main = torch.cuda.current_stream()
+        S, G = self._plan(B) if trace is None else (1, self.decode_group if self.decode_group > 0 else 4)
+        side_decode = trace is None and (S > 1 or self.overlap_decode)
+        while len(self._chunk_streams) < (S if S > 1 else 0):
+            self._chunk_streams.append(torch.cuda.Stream(device=self.device))
+        if side_decode and self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        streams = self._chunk_streams[:S] if S > 1 else [main]
+        dec_stream = self._side if side_decode else main
+        from .shard import shard_bounds
+        bounds = [shard_bounds(B, S, c) for c in range(S)]
+
+        video[0].copy_(images0)   # output frame 0 is the raw input frame (mage_model.py:691)
+        self._frame_to_host(video, host_video, 0)
+        states = []
+        for c, (lo, hi) in enumerate(bounds):
+            if streams[c] is not main:
+                streams[c].wait_stream(main)
+            with torch.cuda.stream(streams[c]):
+                states.append(self._prelude(images0[lo:hi], text[lo:hi], speed[lo:hi] if speed is not None else None,
+                                            noise[lo:hi] if noise is not None else None, tok0_out[lo:hi], trace))
+        img_elems = video.shape[2] * video.shape[3] * video.shape[4]   # frame-major video: images of one frame are adjacent
+        for j0 in range(0, L - 1, G):
+            j1 = min(j0 + G, L - 1)           # this group generates frames j0+1 .. j1 (steps j0 .. j1-1)
+            for c, (lo, hi) in enumerate(bounds):
+                with torch.cuda.stream(streams[c]):
+                    for j in range(j0, j1):
+                        self._decode_step(states[c], j, tokens[j, lo:hi].reshape(-1), trace)
+                if dec_stream is not streams[c]:
+                    dec_stream.wait_stream(streams[c])
+            # decode the finished group of frames for every sample: video[j0+1 .. j1] (frame-major, contiguous)
+            toks = tokens[j0:j1].view(-1, R, R)            # [(j1-j0)*B, R, R], frame-major like the video buffer
+            with torch.cuda.stream(dec_stream):
+                self.vq.decode_into(toks, video[j0 + 1], img_elems)
+                for f in range(j0 + 1, j1 + 1):
+                    self._frame_to_host(video, host_video, f)
+        for s_ in streams:
+            if s_ is not main:
+                main.wait_stream(s_)
+        if dec_stream is not main:
+            main.wait_stream(dec_stream)   # join (also required before a graph capture ends)
         if host_video is not None:
-            torch.cuda.current_stream().wait_stream(self._copy)
+            main.wait_stream(self._copy)
 
     def _frame_to_host(self, video: torch.Tensor, host_video: Optional[torch.Tensor], f: int) -> None:
         """Queue the D2H copy of frame f (one contiguous [B,C,H,W] block) on the copy stream, after the work queued so far."""
@@ -702,9 +765,7 @@ class SamplerEngine:
         cur = torch.cuda.current_stream()
         if self._copy is None:
             self._copy = torch.cuda.Stream(device=self.device)
-        done = torch.cuda.Event()
-        done.record(cur)
-        self._copy.wait_event(done)
+        self._copy.wait_stream(cur)
         with torch.cuda.stream(self._copy):
             host_video[f].copy_(video[f], non_blocking=True)
 
@@ -729,17 +790,17 @@ class SamplerEngine:
             n0 = ops.launch_count()
             self._generate_impl(images0, text, speed, noise, video, tokens, tok0, trace, host)
             self.kernels_per_generate = ops.launch_count() - n0
-            if self.backend == "tc":
-                ops.check_flag(self.device)
+            ops.check_flag(self.device)
             if to_host:
                 torch.cuda.current_stream().synchronize()
                 video = host
-            return video.permute(1, 0, 2, 3, 4), tokens.permute(1, 0, 2).reshape(B, L - 1, R, R), tok0.view(B, R, R)
+            return video.permute(1, 0, 2, 3, 4), tokens.permute(1, 0, 2).reshape(B, L - 1, R, R), tok0.view(B, R, R).clone()
 
-        key = (B, T, tuple(images0.shape[1:]), speed is not None, noise is not None, to_host)
-        st = self._graphs.get(key)
+        key = (B, T, tuple(images0.shape[1:]), speed is not None, noise is not None, to_host, self._plan(B), self.overlap_decode)
+        st = self._graphs.pop(key, None)
         if st is None:
             st = self._capture(key, images0, text, speed, noise, to_host)
+        self._graphs[key] = st     # most recently used last (dicts keep insertion order)
         st["images0"].copy_(images0)
         st["text"].copy_(text)
         if speed is not None:
@@ -747,18 +808,25 @@ class SamplerEngine:
         if noise is not None:
             st["noise"].copy_(noise)
         st["graph"].replay()
-        if self.backend == "tc":
-            ops.check_flag(self.device)  # loud failure if an operand left the fp16 split range (syncs)
+        ops.check_flag(self.device)  # loud failure if an operand left the fp16 split range / a caption id left the vocabulary (syncs)
         video = st["video"]
         if to_host:
             torch.cuda.current_stream().synchronize()
             video = st["host_video"]
-        return video.permute(1, 0, 2, 3, 4), st["tokens"].permute(1, 0, 2).reshape(B, L - 1, R, R), st["tok0"].view(B, R, R)
+        return video.permute(1, 0, 2, 3, 4), st["tokens"].permute(1, 0, 2).reshape(B, L - 1, R, R), st["tok0"].view(B, R, R).clone()
 
     def _capture(self, key, images0, text, speed, noise, to_host=False):
+        """Capture one whole generate call for this input signature.  All graphs of an engine replay serially, so they are captured
+        into ONE shared memory pool (the K/V caches, activations and decoder maps of different signatures alias each other: the
+        pool holds the largest signature, not the sum), and the cache keeps at most `max_graphs` signatures (LRU) -- captions
+        cannot be padded to a common length because the motion anchor attends padded positions (mage_model.py:92), so real
+        data produces one signature per caption length."""
         B, T = text.shape
         R, L = self.R, self.L
         dev = self.device
+        while len(self._graphs) >= self.max_graphs:
+            old = next(iter(self._graphs))
+            self._graphs.pop(old)["graph"].reset()
         st = dict(images0=images0.clone(), text=text.clone(),
                   speed=speed.clone() if speed is not None else None,
                   noise=noise.clone() if noise is not None else None,
@@ -774,11 +842,13 @@ class SamplerEngine:
             self._generate_impl(*args)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        ops.check_flag(dev)
+        if self._pool is None:
+            self._pool = torch.cuda.graph_pool_handle()
         g = torch.cuda.CUDAGraph()
         n0 = ops.launch_count()
-        with torch.cuda.graph(g):
+        with torch.cuda.graph(g, pool=self._pool):
             self._generate_impl(*args)
         self.kernels_per_generate = ops.launch_count() - n0
         st["graph"] = g
-        self._graphs[key] = st
         return st

@@ -51,18 +51,33 @@ def _strip(spec: syn.Spec, prefix: str) -> syn.Spec:
 
 
 class _EngineOwner(nn.Module):
-    """Invalidates the packed-weight engine whenever tensors move or are reloaded."""
+    """Owns the packed-weight engine (split fp16 copies, per-code tables, folded BatchNorm) and rebuilds it whenever the
+    parameters it was packed from have changed: the engine is keyed on every parameter's / buffer's storage address and
+    in-place version counter, so `.to()`, `load_state_dict` on this module OR on any child (e.g. `first_stage_model.
+    init_from_ckpt`), and in-place edits all invalidate it -- never a silent sample from stale weights."""
 
     def __init__(self):
         super().__init__()
         self._engine = None
+        self._engine_sig = None
+
+    def _signature(self):
+        return tuple((t.data_ptr(), t._version, t.device.index) for t in list(self.parameters()) + list(self.buffers()))
+
+    def _engine_valid(self) -> bool:
+        return self._engine is not None and self._engine_sig == self._signature()
+
+    def invalidate(self) -> None:
+        """Drop the packed-weight engine explicitly (it is rebuilt on the next call)."""
+        self._engine = None
+        self._engine_sig = None
 
     def _apply(self, fn, *a, **kw):
-        self._engine = None
+        self.invalidate()
         return super()._apply(fn, *a, **kw)
 
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
-        self._engine = None
+        self.invalidate()
         return super().load_state_dict(state_dict, strict=strict, **kw)
 
     def _cuda_state(self) -> Dict[str, torch.Tensor]:
@@ -98,9 +113,10 @@ class VectorQuantizedVAE(_EngineOwner):
         print(f"Restored from {path}")
 
     def engine(self):
-        if self._engine is None:
+        if not self._engine_valid():
             from .engine import VQVAEEngine
             self._engine = VQVAEEngine(self._cuda_state())
+            self._engine_sig = self._signature()
         return self._engine
 
     @torch.no_grad()
@@ -222,10 +238,11 @@ class MAGE(_EngineOwner):
         return super().load_state_dict(sd, strict=strict, **kw)
 
     def engine(self):
-        if self._engine is None:
+        if not self._engine_valid():
             from .engine import SamplerEngine
             self._engine = SamplerEngine(self._cuda_state(), self.frames_length, self.randomness,
                                          padding_idx=getattr(self.text_encoder, "padding_idx", 0))
+            self._engine_sig = self._signature()
         return self._engine
 
     @torch.no_grad()
@@ -249,7 +266,9 @@ class MAGE(_EngineOwner):
         tensor whose frames were copied out while later frames were still being generated; it is valid until the next call."""
         eng = self.engine()
         dev = eng.device
-        if not batch["text"].is_cuda:   # free on the host: token ids must index the vocabulary table (nn.Embedding raises too)
+        # token ids must index the vocabulary table (nn.Embedding raises, mage_model.py:228): checked for free on a host tensor
+        # here, and for a device tensor inside text_embed_kernel (flagged, never dereferenced; raised after the call)
+        if not batch["text"].is_cuda:
             vocab = self.text_encoder.state_dict()["token_embedding.weight"].shape[0]
             if batch["text"].numel() and (int(batch["text"].max()) >= vocab or int(batch["text"].min()) < 0):
                 raise IndexError(f"caption token id outside the vocabulary [0, {vocab})")
@@ -264,9 +283,9 @@ class MAGE(_EngineOwner):
         self.last_tokens, self.last_tok0 = tokens, tok0
         if to_host:
             return video
-        # the engine's buffers are reused by the next call (CUDA graph); the reference hands out a fresh
-        # tensor that its caller clamps in place (main_mage.py:242)
-        return video.clone()
+        # the engine's buffers are reused by the next call (CUDA graph); the reference hands out a fresh CONTIGUOUS
+        # [B,L,C,H,W] tensor (torch.cat, mage_model.py:691) that its caller clamps in place and views (main_mage.py:242)
+        return video.clone(memory_format=torch.contiguous_format)
 
     @torch.no_grad()
     def teacher_forced_tokens(self, batch, force_tokens: torch.Tensor, noise: Optional[torch.Tensor] = None):

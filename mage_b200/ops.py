@@ -88,10 +88,15 @@ def flag(device) -> torch.Tensor:
 
 
 def check_flag(device) -> None:
-    """Raise (loudly, after a sync) if any split conversion since the last check saw |x| > 65504 or NaN."""
+    """Raise (loudly, after a sync) if a kernel since the last check reported a condition on which the reference would have
+    raised or which invalidates the results: bit 0 = a split conversion saw |x| > 65504 or NaN, bit 1 = a caption token id
+    outside the vocabulary table (nn.Embedding raises IndexError, mage_model.py:228)."""
     f = flag(device)
-    if int(f.item()) != 0:
+    v = int(f.item())
+    if v != 0:
         f.zero_()
+        if v & 2:
+            raise IndexError("caption token id outside the text encoder's vocabulary (index out of range in self)")
         raise _lib.MageCudaError("a tensor-core operand left the fp16 hi/lo split range (|x| > 65504 or NaN); "
                                  "results are invalid -- run with MAGE_BACKEND=simt")
 
@@ -192,8 +197,9 @@ def gemm_tc(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = Non
 def conv2d_tc(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, pad=(0, 0),
               residual: Optional[torch.Tensor] = None, res_mode: int = 0, act: int = ACT_NONE, want=("f32",),
               out: Optional[torch.Tensor] = None, out_split: Optional[torch.Tensor] = None,
-              out_split_relu: Optional[torch.Tensor] = None, out_hw=None, scatter=(1, 1, 0, 0), full_hw=None):
-    """Tensor-core stride-1 NHWC convolution on split operands: x [2,n,Hin,Win,Cin], w [2,Cout,KH,KW,Cin]."""
+              out_split_relu: Optional[torch.Tensor] = None, out_hw=None, scatter=(1, 1, 0, 0), full_hw=None, passes: int = 3):
+    """Tensor-core stride-1 NHWC convolution on split operands: x [2,n,Hin,Win,Cin], w [2,Cout,KH,KW,Cin].
+    passes=1: hi*hi products only (see mage_b200.h) -- decoder layers that feed no token."""
     _f16(x), _f16(w)
     _, n, Hin, Win, Cin = x.shape
     _, Cout, KH, KW, Cin2 = w.shape
@@ -218,13 +224,14 @@ def conv2d_tc(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = N
     with _Prof("conv", 2.0 * n * Hout * Wout * Cout * KH * KW * Cin):
         check(_lib.lib().mage_conv2d_tc(_p(x), n * Hin * Win * Cin, _p(w), Cout * KH * KW * Cin, _p(bias), _p(residual), _p(out),
                                         _p(out_split), _p(out_split_relu), n * img, n, Hin, Win, Cin, Hout, Wout, Cout, KH, KW,
-                                        pad[0], pad[1], res_mode, act, sy, sx, oy, ox, Hfull, Wfull, img, _p(flag(dev)),
+                                        pad[0], pad[1], res_mode, act, sy, sx, oy, ox, Hfull, Wfull, img, passes, _p(flag(dev)),
                                         _stream()), "mage_conv2d_tc")
     return out, out_split, out_split_relu
 
 
 def conv2d_tc_pixel_head(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], *, pad, residual: Optional[torch.Tensor],
-                         res_mode: int, head_w: torch.Tensor, head_b: torch.Tensor, out: torch.Tensor, out_img_stride: int) -> None:
+                         res_mode: int, head_w: torch.Tensor, head_b: torch.Tensor, out: torch.Tensor, out_img_stride: int,
+                         passes: int = 3) -> None:
     """conv2d_tc whose 256-channel result never leaves the SM: tanh(head_b + head_w . relu(conv + bias + residual)) is written
     planar at out.data_ptr() + img*out_img_stride (vqvae_model.py:210-213)."""
     _f16(x), _f16(w)
@@ -235,7 +242,7 @@ def conv2d_tc_pixel_head(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.
     with _Prof("conv", 2.0 * n * Hout * Wout * Cout * (KH * KW * Cin + head_b.numel())):
         check(_lib.lib().mage_conv2d_tc_pixel_head(_p(x), n * Hin * Win * Cin, _p(w), Cout * KH * KW * Cin, _p(bias), _p(residual),
                                                    n, Hin, Win, Cin, Hout, Wout, Cout, KH, KW, pad[0], pad[1], res_mode,
-                                                   _p(head_w), _p(head_b), head_b.numel(), _p(out), out_img_stride,
+                                                   _p(head_w), _p(head_b), head_b.numel(), _p(out), out_img_stride, passes,
                                                    _p(flag(x.device)), _stream()), "mage_conv2d_tc_pixel_head")
 
 
@@ -404,7 +411,7 @@ def text_embed(text: torch.Tensor, tok_emb, pos_emb, gamma, beta, pad_idx: int, 
     key_len = torch.empty(B, device=tok_emb.device, dtype=torch.int32)
     with _Prof("misc", 0.0):
         check(_lib.lib().mage_text_embed_f32(_p(text), _p(tok_emb), _p(pos_emb), _p(gamma), _p(beta), _p(x), _p(key_len), B, T, C,
-                                             pad_idx, eps, _stream()), "mage_text_embed_f32")
+                                             pad_idx, eps, tok_emb.shape[0], _p(flag(tok_emb.device)), _stream()), "mage_text_embed_f32")
     return x, key_len
 
 

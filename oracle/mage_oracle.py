@@ -377,9 +377,13 @@ def generate_incremental(sd: SD, batch: Dict[str, torch.Tensor], noise: Optional
         tok = torch.max(logits, -1)[1]
         toks.append(tok)
         gaps.append(_top2_gap(logits))
+        if trace is not None and trace.get("want_logits"):
+            trace.setdefault("logits", []).append(logits.reshape(logits.shape[0], -1, logits.shape[-1]))
     tokens = torch.stack(toks, 1)
     if trace is not None:
         trace["tok0"], trace["tokens"], trace["gap"] = tok0, tokens, torch.stack(gaps, 1)
+        if trace.get("want_logits"):
+            trace["logits"] = torch.stack(trace["logits"], 1)   # [B, L-1, h*w, K]
     B = tokens.shape[0]
     pix = vqvae_decode(fsd, tokens.view(-1, *tokens.shape[-2:]))
     pix = pix.view(B, L - 1, *pix.shape[1:])

@@ -4,8 +4,13 @@ container so the oracle can be pinned against it and golden vectors can be gener
 The reference's `modules/mage_model.py` imports three packages that are not installed
 here (`pytorch_transformers`, `omegaconf`, `ldm`).  None of them is touched
 on the VQ sampling path, so three empty shims in `sys.modules` are enough to run
-`MAGE.autoregressive_generate` as shipped.  /root/reference does not exist on the GPU box:
-nothing outside oracle/make_golden.py and the `needs_reference` CPU tests may call this.
+`MAGE.autoregressive_generate` as shipped.
+
+/root/reference does not exist on the GPU box.  `oracle/build_ref.py` (run by `__graft_entry__.build()` in the authoring
+container) copies the three reference source files of this path (modules/mage_model.py, modules/vqvae_model.py, utils/util.py), unmodified, into the git-ignored `oracle/_ref/`, which travels
+to the GPU box with the repo snapshot: there it serves ONLY bench.py's reference arms (`--impl reference`, `cpu_baseline`,
+`eager_gpu_baseline`) -- the thing being compared against, never the thing measured or shipped.  Callers: oracle/make_golden.py,
+the `needs_reference` CPU tests, bench.py's reference arms.
 """
 from __future__ import annotations
 
@@ -14,7 +19,20 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("MAGE_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root() -> str:
+    env = os.environ.get("MAGE_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", os.path.join(_HERE, "_ref")):
+        if os.path.isfile(os.path.join(cand, "modules", "mage_model.py")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def reference_available() -> bool:

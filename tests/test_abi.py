@@ -23,10 +23,24 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/mage_b200.h but not exported"
     assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)
-    assert L.mage_abi_version() == 3
+    assert L.mage_abi_version() == _lib.ABI_VERSION
     assert L.mage_launch_count() >= 0
 
 
 def test_header_cites_reference_lines():
     text = open(os.path.join(ROOT, "include", "mage_b200.h")).read()
     assert text.count("mage_model.py:") >= 8 and text.count("vqvae_model.py:") >= 6
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ (and the oracle/_ref copy of the reference) is test / bench infrastructure: no product module may import it."""
+    bad = []
+    files = [os.path.join(ROOT, f) for f in ("main_mage.py", "dataload.py")]
+    for d in ("mage_b200", "modules", "utils"):
+        for dp, _, fs in os.walk(os.path.join(ROOT, d)):
+            files += [os.path.join(dp, f) for f in fs if f.endswith(".py")]
+    for f in files:
+        for ln in open(f):
+            if re.match(r"\s*(from|import)\s+oracle\b", ln) or "oracle/_ref" in ln or "ref_shims" in ln:
+                bad.append((f, ln.strip()))
+    assert not bad, bad

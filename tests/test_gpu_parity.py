@@ -12,14 +12,11 @@ import pytest
 import torch
 
 from mage_b200 import synthetic as syn
-from tests.helpers import GOLDEN_DIR, MAGE_CASES, load_case, tie_aware_token_check
+from tests.helpers import GOLDEN_DIR, LOGIT_EPS, MAGE_CASES, load_case, parity_check, pix_check
 
 pytestmark = pytest.mark.gpu
 
-LOGIT_EPS = 2e-4   # logit std is ~1.5; fp32 GEMM-order noise on a logit is ~1e-5
 VQ_EPS = 1e-3      # VQ distances are O(10..100)
-PIX_REL = 1e-3
-PIX_ABS = 5e-3
 
 
 @pytest.fixture(params=["tc", "simt"], autouse=True)
@@ -37,10 +34,7 @@ def _build(params, sd):
 
 
 def _pix_check(got, want):
-    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
-    rel = np.linalg.norm(got - want) / np.linalg.norm(want)
-    assert rel <= PIX_REL, f"pixel rel-L2 error {rel:.3e} > {PIX_REL}"
-    assert np.abs(got - want).max() <= PIX_ABS, f"pixel max-abs error {np.abs(got - want).max():.3e}"
+    pix_check(got, want)
 
 
 @pytest.mark.parametrize("ratio", [4, 8])
@@ -89,10 +83,42 @@ def test_generate_vs_reference_golden(name):
     assert tuple(video.shape[:2]) == (B, L)
     assert torch.equal(video[:, 0].cpu(), batch["images"][:, 0]), "frame 0 must be the raw input frame (mage_model.py:691)"
     assert np.array_equal(model.last_tok0.cpu().numpy(), g["tok0"]), "first-frame VQ indices differ from the reference"
-    _, excused = tie_aware_token_check(model.last_tokens.cpu().numpy(), g["tokens"], g["gap"], LOGIT_EPS)
-    if excused == 0:
-        s = int(g["pixel_stride"])
-        _pix_check(video[:, 1:][..., ::s, ::s].cpu().numpy(), g["pixels"])
+    parity_check(model, batch, noise, video, g["tokens"], g["gap"], g["pixels"], label=f"golden {name}",
+                 pixel_stride=int(g["pixel_stride"]), ref_logits=g["logits_sample"])
+
+
+def test_decoder_precision_budget(backend, monkeypatch):
+    """DESIGN.md "decoder precision budget": the last decoder block's block.5 / block.7 (+ pixel head) convolutions -- 63 % of the
+    decoder's FLOPs, feeding no token -- run single-pass fp16 by default.  Held here to the north_star bar (decoded pixels within
+    1e-3 relative) against the fp32 CPU oracle on the tokens of all five reference goldens' family plus three seeds of random
+    token maps and random-weight decoders, next to the all-fp32-grade mode (MAGE_DECODER_PRECISION=fp32: ~1e-6)."""
+    if backend != "tc":
+        pytest.skip("the FFMA back end has no reduced-precision mode")
+    from mage_b200.engine import VQVAEEngine
+    from oracle import mage_oracle as orc
+    fs = syn.model_params("caterv2")["first_stage_config"]["params"]
+    worst = 0.0
+    for seed in (7, 8, 9):
+        sd = syn.make_vqvae_state_dict(fs, seed=seed)
+        g = torch.Generator().manual_seed(seed)
+        idx = torch.randint(0, 512, (8, 16, 16), generator=g)
+        if seed == 7:   # the goldens' checkpoint: decode the reference's own greedy tokens of the L=10 golden as well
+            gold = np.load(os.path.join(GOLDEN_DIR, "mage_cater_L10_b1.npz"))
+            idx = torch.cat([idx, torch.from_numpy(gold["tokens"].astype(np.int64)).view(-1, 16, 16)])
+        with torch.no_grad():
+            want = orc.vqvae_decode(sd, idx).numpy().astype(np.float64)
+        errs = {}
+        for mode in ("budget", "fp32"):
+            monkeypatch.setenv("MAGE_DECODER_PRECISION", mode)
+            eng = VQVAEEngine({k: v.to("cuda") for k, v in sd.items()})
+            got = eng.decode(idx.to("cuda")).cpu().numpy().astype(np.float64)
+            errs[mode] = (np.linalg.norm(got - want) / np.linalg.norm(want), np.abs(got - want).max())
+        print(f"[parity] decoder precision, seed {seed}, {idx.shape[0]} frames: budget rel-L2 {errs['budget'][0]:.2e} max-abs "
+              f"{errs['budget'][1]:.2e}; fp32-grade rel-L2 {errs['fp32'][0]:.2e} max-abs {errs['fp32'][1]:.2e}")
+        assert errs["fp32"][0] <= 2e-5
+        assert errs["budget"][0] <= 8e-4 and errs["budget"][1] <= 8e-3, errs   # bar 1e-3 with margin
+        worst = max(worst, errs["budget"][0])
+    assert worst > 1e-5, "the budget mode did not engage (results equal the fp32-grade path)"
 
 
 def test_prelude_intermediates_vs_oracle():
@@ -131,12 +157,12 @@ def test_full_length_c5_shape_vs_incremental_oracle():
     noise = syn.make_noise(2, seed=5)
     model = _build(params, sd)
     video = model.autoregressive_generate({k: v.to("cuda") for k, v in batch.items()}, noise=noise)
-    otr = {}
+    otr = {"want_logits": True}
     want = orc.generate_incremental(sd, batch, noise, otr)
     assert np.array_equal(model.last_tok0.cpu().numpy(), otr["tok0"].numpy())
-    _, excused = tie_aware_token_check(model.last_tokens.cpu().numpy(), otr["tokens"].numpy(), otr["gap"].numpy(), LOGIT_EPS)
-    if excused == 0:
-        _pix_check(video[:, 1:].cpu().numpy(), want[:, 1:].numpy())
+    # free-running AND teacher-forced (all 31 x 256 x B positions, logits to 5e-5, every frame's pixels): no cascade can hide anything
+    parity_check(model, batch, noise, video, otr["tokens"].numpy(), otr["gap"].numpy(), want[:, 1:].numpy(),
+                 label="C5 shape (CATER-v2 128x128x32) B=2", ref_logits=otr["logits"].numpy(), always_teacher_forced=True)
 
 
 def test_batch_invariance_and_graph_replay_are_bit_exact():
@@ -246,37 +272,122 @@ def test_baseline_configs_full_length_vs_incremental_oracle(family, L, B, B_chec
         # the motion anchor attends padded caption positions (mage_model.py:92), so a prompt's result depends on the batch's
         # maximum caption length: keep the full batch's padded width for the oracle's sub-batch
         assert sub["text"].shape[1] == batch["text"].shape[1]
-    otr = {}
+    otr = {"want_logits": True}
     want = orc.generate_incremental(sd, sub, noise[:B_check] if noise is not None else None, otr)
     assert np.array_equal(model.last_tok0[:B_check].cpu().numpy(), otr["tok0"].numpy())
-    _, excused = tie_aware_token_check(model.last_tokens[:B_check].cpu().numpy(), otr["tokens"].numpy(), otr["gap"].numpy(), LOGIT_EPS)
-    if excused == 0:
-        _pix_check(video[:B_check, 1:].cpu().numpy(), want[:, 1:].numpy())
+    # teacher-forced as well (L = 16 / 20 at full length): every position and every frame is compared, no cascade
+    parity_check(model, sub, noise, video, otr["tokens"].numpy(), otr["gap"].numpy(), want[:, 1:].numpy(),
+                 label=f"{family} L={L} B={B} (first {B_check} prompts)", ref_logits=otr["logits"].numpy(),
+                 always_teacher_forced=True, rows=B_check)
 
 
 def test_optional_schedules_are_bit_exact():
-    """Scheduling options that are off by default (measured neutral): decoder on a side stream, programmatic dependent launch,
-    per-frame decoding.  None of them may change a single bit."""
+    """Schedules: chunk streams (the batch cut into S chunks whose launch sequences run concurrently), decoder on a side stream,
+    decode group size, programmatic dependent launch.  Rows are independent and every kernel is deterministic, so none of them
+    may change a single bit -- of the tokens, of the device clip, or of the streamed host clip."""
     from mage_b200 import ops
     params = syn.model_params("caterv2", frames_length=6)
     sd = syn.make_mage_state_dict(params)
-    batch = {k: v.to("cuda") for k, v in syn.make_batch(params, 4, seed=31, text_len=12).items()}
-    noise = syn.make_noise(4, seed=2)
+    batch = {k: v.to("cuda") for k, v in syn.make_batch(params, 5, seed=31, text_len=12).items()}
+    noise = syn.make_noise(5, seed=2)
     model = _build(params, sd)
+    eng = model.engine()
+    eng.n_streams, eng.decode_group, eng.overlap_decode = 1, 4, False
     ref = model.autoregressive_generate(batch, noise=noise)
     ref_tok = model.last_tokens.clone()
-    eng = model.engine()
     try:
-        for overlap, group, use_pdl in ((True, 4, False), (False, 1, False), (False, 4, True), (True, 2, True)):
-            eng.overlap_decode, eng.decode_group = overlap, group
+        for streams, overlap, group, use_pdl in ((1, True, 4, False), (1, False, 1, False), (1, False, 4, True), (1, True, 2, True),
+                                                 (2, False, 4, False), (3, False, 2, True), (5, False, 5, False), (0, False, 0, False)):
+            eng.n_streams, eng.overlap_decode, eng.decode_group = streams, overlap, group
             eng._graphs.clear()
             ops.pdl(use_pdl)
-            for _ in range(2):   # capture + replay
-                got = model.autoregressive_generate(batch, noise=noise)
-                assert torch.equal(model.last_tokens, ref_tok), (overlap, group, use_pdl)
-                assert torch.equal(got, ref), (overlap, group, use_pdl)
+            for it in range(2):   # capture + replay
+                got = model.autoregressive_generate(batch, noise=noise, to_host=it == 1 and streams != 1)
+                assert torch.equal(model.last_tokens, ref_tok), (streams, overlap, group, use_pdl)
+                assert torch.equal(got.cuda(), ref), (streams, overlap, group, use_pdl)
+        eng.use_cuda_graph = False   # the same multi-stream schedule launched eagerly
+        eng.n_streams, eng.decode_group = 2, 2
+        got = model.autoregressive_generate(batch, noise=noise)
+        assert torch.equal(model.last_tokens, ref_tok) and torch.equal(got, ref)
     finally:
         ops.pdl(False)
+
+
+def test_graph_cache_is_bounded_and_shares_one_pool():
+    """Captions cannot be padded to a common length (the motion anchor attends padded positions, mage_model.py:92), so real data
+    yields one CUDA graph per caption length: the cache keeps at most `max_graphs` signatures (LRU) and all graphs live in ONE
+    memory pool -- device memory must not grow with the number of signatures seen."""
+    params = syn.model_params("caterv2", frames_length=4)
+    sd = syn.make_mage_state_dict(params)
+    model = _build(params, sd)
+    eng = model.engine()
+    eng.max_graphs = 3
+    noise = syn.make_noise(2, seed=2)
+    outs, mem = {}, []
+    for T in (8, 9, 10, 11, 12, 8, 12):
+        batch = {k: v.to("cuda") for k, v in syn.make_batch(params, 2, seed=31, text_len=T).items()}
+        v = model.autoregressive_generate(batch, noise=noise)
+        if T in outs:
+            assert torch.equal(outs[T], v), "a re-captured signature must reproduce the earlier result"
+        outs[T] = v
+        assert len(eng._graphs) <= 3
+        torch.cuda.synchronize()
+        mem.append(torch.cuda.memory_reserved())
+    assert mem[-1] <= mem[1] * 1.25 + (64 << 20), f"reserved memory grew with the number of caption lengths: {mem}"
+
+
+def test_out_of_vocabulary_caption_on_the_device_is_refused():
+    """main_mage.py moves the batch to the device before the call, so the host-side range check never ran there and
+    text_embed_kernel would have read past the vocabulary table.  The kernel now flags the id (never dereferences it) and the
+    call raises IndexError like nn.Embedding (mage_model.py:228)."""
+    params = syn.model_params("caterv1", frames_length=3)   # vocabulary of 30 ids
+    sd = syn.make_mage_state_dict(params)
+    model = _build(params, sd)
+    batch = syn.make_batch(params, 2, seed=3, text_len=10)
+    batch["text"][1, 4] = 45                                  # a CATER-v2 id (vocab 50) fed to a CATER-v1 checkpoint
+    with pytest.raises(IndexError):
+        model.autoregressive_generate({k: v.to("cuda") for k, v in batch.items()}, noise=syn.make_noise(2))
+    batch["text"][1, 4] = 5
+    out = model.autoregressive_generate({k: v.to("cuda") for k, v in batch.items()}, noise=syn.make_noise(2))
+    assert torch.isfinite(out).all() and out.is_contiguous()
+
+
+def test_engine_follows_child_and_in_place_weight_updates(tmp_path):
+    """loading into a submodule (`first_stage_model.init_from_ckpt`, the way every shipped yaml loads the VQ-VAE,
+    vqvae_model.py:222-231) or editing a parameter in place must not leave the sampler on stale packed weights."""
+    from modules.vqvae_model import VectorQuantizedVAE
+    params = syn.model_params("caterv2", frames_length=3)
+    sd = syn.make_mage_state_dict(params)
+    fs = params["first_stage_config"]["params"]
+    fs_sd = {k[len("first_stage_model."):]: v for k, v in sd.items() if k.startswith("first_stage_model.")}
+    torch.save(fs_sd, tmp_path / "vqvae.pt")
+    # (a) the first stage restores itself from ckpt_path inside the MAGE constructor
+    p2 = {**params, "first_stage_config": {"target": params["first_stage_config"]["target"],
+                                            "params": {**fs, "ckpt_path": str(tmp_path / "vqvae.pt")}}}
+    from mage_b200.config import instantiate_from_config
+    m2 = instantiate_from_config({"target": "modules.mage_model.MAGE", "params": p2})
+    m2.load_state_dict({k: v for k, v in sd.items() if not k.startswith("first_stage_model.")}, strict=False)
+    m2 = m2.to("cuda").eval()
+    m1 = _build(params, sd)
+    batch = {k: v.to("cuda") for k, v in syn.make_batch(params, 2, seed=5, text_len=9).items()}
+    noise = syn.make_noise(2, seed=1)
+    want = m1.autoregressive_generate(batch, noise=noise)
+    assert torch.equal(m2.autoregressive_generate(batch, noise=noise), want), "first stage loaded through ckpt_path differs"
+    # (b) a child reload after the first generate: start from a different VQ-VAE, then restore the right one through the child
+    other = syn.make_vqvae_state_dict(fs, seed=123)
+    m3 = _build(params, {**sd, **{"first_stage_model." + k: v for k, v in other.items()}})
+    assert not torch.equal(m3.autoregressive_generate(batch, noise=noise), want)
+    m3.first_stage_model.init_from_ckpt(str(tmp_path / "vqvae.pt"))
+    assert torch.equal(m3.autoregressive_generate(batch, noise=noise), want), "engine kept the stale first-stage weights"
+    # (c) an in-place edit of a parameter is picked up as well
+    with torch.no_grad():
+        m3.generate_model.out.bias.add_(1.0)    # uniform shift of every logit: same argmax, new version counter
+    assert not m3._engine_valid()
+    assert torch.equal(m3.autoregressive_generate(batch, noise=noise), want)
+    # standalone first stage through its own ckpt_path
+    vq = VectorQuantizedVAE(**{**fs, "ckpt_path": str(tmp_path / "vqvae.pt")}).to("cuda")
+    x = syn.structured_images(2, fs["input_dim"], 128, seed=4)
+    assert torch.equal(vq.encode(x.to("cuda")), m1.first_stage_model.encode(x.to("cuda")))
 
 
 def test_c5_full_batch_rows_equal_small_batch_rows():
@@ -314,6 +425,8 @@ def test_teacher_forced_tokens_vs_reference_golden(name):
     B, F = tokens.shape[:2]
     got = logits.view(B, F, 16, 16, -1)[:, :, ::5, ::5, ::16].cpu().numpy()
     err = np.abs(got - g["logits_sample"]).max()
+    print(f"[parity] teacher-forced golden {name}: {neq.size} positions, {int(neq.sum())} excused, {int((gap < LOGIT_EPS).sum())} reference "
+          f"near-ties, logit err {err:.2e} at |logit| <= {np.abs(g['logits_sample']).max():.2f}")
     assert err <= 5e-5 * max(1.0, np.abs(g["logits_sample"]).max()), f"teacher-forced logits differ from the reference by {err:.3e}"
 
 
@@ -331,9 +444,8 @@ def test_caption_length_extremes_and_missing_speed(text_len, with_speed):
     otr = {}
     want = orc.generate(sd, batch, noise, otr)
     assert np.array_equal(model.last_tok0.cpu().numpy(), otr["tok0"].numpy())
-    _, excused = tie_aware_token_check(model.last_tokens.cpu().numpy(), otr["tokens"].numpy(), otr["gap"].numpy(), LOGIT_EPS)
-    if excused == 0:
-        _pix_check(video[:, 1:].cpu().numpy(), want[:, 1:].numpy())
+    parity_check(model, batch, noise, video, otr["tokens"].numpy(), otr["gap"].numpy(), want[:, 1:].numpy(),
+                 label=f"caption T={text_len} speed={with_speed}")
     assert torch.equal(video[:, 0].cpu(), batch["images"][:, 0])
 
 
@@ -364,9 +476,8 @@ def test_small_and_odd_shapes_vs_oracle(family, L, B):
     want = orc.generate(sd, batch, noise, otr)
     assert tuple(video.shape) == tuple(want.shape)
     assert np.array_equal(model.last_tok0.cpu().numpy(), otr["tok0"].numpy())
-    _, excused = tie_aware_token_check(model.last_tokens.cpu().numpy(), otr["tokens"].numpy(), otr["gap"].numpy(), LOGIT_EPS)
-    if excused == 0:
-        _pix_check(video[:, 1:].cpu().numpy(), want[:, 1:].numpy())
+    parity_check(model, batch, noise, video, otr["tokens"].numpy(), otr["gap"].numpy(), want[:, 1:].numpy(),
+                 label=f"{family} L={L} B={B}")
 
 
 def test_main_mage_caption_and_image_prompt(tmp_path):

@@ -10,7 +10,7 @@ import torch
 from mage_b200 import synthetic as syn
 from oracle import mage_oracle as orc
 from oracle import ref_shims
-from tests.helpers import GOLDEN_DIR, MAGE_CASES, load_case, tie_aware_token_check
+from tests.helpers import GOLDEN_DIR, MAGE_CASES, free_running_token_report, load_case
 
 
 @pytest.mark.parametrize("ratio", [4, 8])
@@ -37,12 +37,12 @@ def test_generate_matches_reference_golden(name):
     tr = {}
     video = orc.generate(sd, batch, noise, tr)
     assert np.array_equal(tr["tok0"].numpy(), g["tok0"]), "first-frame VQ indices differ from the reference"
-    _, excused = tie_aware_token_check(tr["tokens"].numpy(), g["tokens"], g["gap"], eps=1e-5)
-    if excused == 0:
-        s = int(g["pixel_stride"])
-        pix = video[:, 1:][..., ::s, ::s].numpy()
-        np.testing.assert_allclose(pix, g["pixels"], rtol=0, atol=2e-6)
-        np.testing.assert_allclose(tr["gap"].numpy(), g["gap"], rtol=0, atol=2e-5)
+    rep = free_running_token_report(tr["tokens"].numpy(), g["tokens"], g["gap"], eps=1e-5)
+    assert rep["excused"] == 0 and rep["compared"] == rep["positions"], "the oracle must reproduce the reference's tokens exactly"
+    s = int(g["pixel_stride"])
+    pix = video[:, 1:][..., ::s, ::s].numpy()
+    np.testing.assert_allclose(pix, g["pixels"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(tr["gap"].numpy(), g["gap"], rtol=0, atol=2e-5)
 
 
 @pytest.mark.parametrize("name", ["cater_L4_b2_pad", "mnist_L5_b2", "cater_L10_b1"])
@@ -50,10 +50,10 @@ def test_incremental_order_equals_reference_order(name):
     params, sd, batch, noise, g = load_case(name)
     tr = {}
     video = orc.generate_incremental(sd, batch, noise, tr)
-    _, excused = tie_aware_token_check(tr["tokens"].numpy(), g["tokens"], g["gap"], eps=1e-5)
-    if excused == 0:
-        s = int(g["pixel_stride"])
-        np.testing.assert_allclose(video[:, 1:][..., ::s, ::s].numpy(), g["pixels"], rtol=0, atol=2e-6)
+    rep = free_running_token_report(tr["tokens"].numpy(), g["tokens"], g["gap"], eps=1e-5)
+    assert rep["excused"] == 0 and rep["compared"] == rep["positions"], "incremental and reference order must give the same tokens"
+    s = int(g["pixel_stride"])
+    np.testing.assert_allclose(video[:, 1:][..., ::s, ::s].numpy(), g["pixels"], rtol=0, atol=2e-6)
 
 
 def test_incremental_can_run_longer_than_checkpoint_positions_is_rejected():
