@@ -110,6 +110,13 @@ int mage_split_f32(const float* x, int64_t ldx, void* out, int64_t plane, int ro
 int mage_patch_rows_split_f32(const float* in, void* out, int64_t plane, int n_img, int C, int H, int W, int KW, int pad,
                               void* stream);
 
+/* Space-to-depth with a one-pixel top/left pad, in the split format: in fp32 NHWC [n,H,W,C] (H, W even, C % 8 == 0) -> out split
+ * [n, H/2+1, W/2+1, 4C] with out[n, Y, X, (py*2+px)*C + c] = relu?(in[n, 2Y+py-1, 2X+px-1, c]) (zero outside the image).
+ * A 4x4 stride-2 pad-1 convolution (vqvae_model.py:175) over `in` is then the 2x2 stride-1 VALID mage_conv2d_tc over `out`
+ * with w2[co, ty, tx, (py*2+px)*C + c] = w[co, c, 2ty+py, 2tx+px]: same products, every weight used once. */
+int mage_s2d_pad_split_f32(const float* in, void* out, int64_t plane, int n_img, int H, int W, int C, int relu, int* flag,
+                           void* stream);
+
 /* out(split)[r, :] = table(split)[idx[r], :]   (nn.Embedding on a pre-split table: mage_model.py:644,682;
  * vqvae_model.py:240).  C % 8 == 0. */
 int mage_embedding_split(const int64_t* idx, const void* table, int64_t table_plane, void* out, int64_t out_plane,
@@ -239,6 +246,17 @@ int mage_add_scaled_vec_f32(float* x, const float* s, const float* vec, int n_im
 
 /* out[n,h,w,c] = in[n,c,h,w]  (noise [B,64,16,16] -> NHWC). */
 int mage_nchw_to_nhwc_f32(const float* in, float* out, int n_img, int C, int HW, void* stream);
+
+/* MAGE+ continuous head (use_cids=False), mage_model.py:349-354 + :386-388: GroupNorm(groups) over (C/groups channels x all
+ * temporal slots x H x W) of a sample -> SiLU -> 1x1x1 Conv3d to `cout` latent channels.
+ * mage_gn_partial_f32: x fp32 [n_slots, B, HW, C] -> part double [n_slots, B, groups, 2] = (sum, sum of squares) of each
+ *   (slot, sample, group); a slot is re-reduced only when its hidden state changes.
+ * mage_gn_silu_head_f32: rows of x [rows = k*B*HW, C] (row -> sample (row / HW) % B), statistics combined over the n_slots
+ *   slots of `part`; out fp32 [rows, cout] = bias + w[cout, C] . silu(GN(x)).  C = 512, groups = 32, cout <= 8. */
+int mage_gn_partial_f32(const float* x, double* part, int n_slots, int B, int HW, int C, int groups, void* stream);
+int mage_gn_silu_head_f32(const float* x, const double* part, const float* gamma, const float* beta, const float* w,
+                          const float* bias, float* out, int rows, int B, int HW, int n_slots, int C, int groups, int cout,
+                          float eps, void* stream);
 
 #ifdef __cplusplus
 }

@@ -31,6 +31,7 @@ SIGNATURES = {
     "mage_tc_nsplit": [_i],
     "mage_split_f32": [_c_f, _i64, _c_f, _i64, _i, _i, _i, _c_f, _c_f],
     "mage_patch_rows_split_f32": [_c_f, _c_f, _i64, _i, _i, _i, _i, _i, _i, _c_f],
+    "mage_s2d_pad_split_f32": [_c_f, _c_f, _i64, _i, _i, _i, _i, _i, _c_f, _c_f],
     "mage_embedding_split": [_c_f, _c_f, _i64, _c_f, _i64, _i, _i, _c_f],
     "mage_gemm_tc": [_c_f, _i64, _i64, _c_f, _i64, _i64, _c_f, _c_f, _i64, _i, _c_f, _c_f, _c_f, _i64, _i64, _i, _i, _i, _i,
                      _c_f, _c_f],
@@ -52,6 +53,8 @@ SIGNATURES = {
     "mage_adain_nhwc_f32": [_c_f] * 4 + [_i] * 3 + [_f32, _c_f],
     "mage_add_scaled_vec_f32": [_c_f] * 3 + [_i] * 3 + [_c_f],
     "mage_nchw_to_nhwc_f32": [_c_f, _c_f, _i, _i, _i, _c_f],
+    "mage_gn_partial_f32": [_c_f, _c_f, _i, _i, _i, _i, _i, _c_f],
+    "mage_gn_silu_head_f32": [_c_f] * 7 + [_i] * 7 + [_f32, _c_f],
 }
 
 

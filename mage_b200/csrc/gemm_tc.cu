@@ -798,6 +798,41 @@ __global__ void __launch_bounds__(256) patch_rows_split_kernel(const float* __re
   *reinterpret_cast<uint4*>(out + plane + o) = make_uint4(l0.x, l0.y, l1.x, l1.y);
 }
 
+// Space-to-depth with a one-pixel top/left pad, emitted in the split format: the input operand of a 4x4 stride-2 pad-1
+// convolution rewritten as a 2x2 stride-1 VALID convolution (vqvae_model.py:175).  Output pixel (Y, X), channel block
+// q = py*2+px holds input pixel (2Y+py-1, 2X+px-1) (zero outside the image), so output row oy of the strided convolution
+// reads rows 2oy-1 .. 2oy+2 = s2d rows oy, oy+1 with both parities -- every weight is used, K = 4 taps x 4C.
+//   in fp32 NHWC [n, H, W, C] -> out split [n, H/2+1, W/2+1, 4C].  One thread per (output pixel, parity, 8-channel chunk).
+__global__ void __launch_bounds__(256) s2d_pad_split_kernel(const float* __restrict__ in, __half* __restrict__ out, int64_t plane,
+                                                            int n_img, int H, int W, int C8, int relu, int* flag) {
+  const int Ho = H / 2 + 1, Wo = W / 2 + 1;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)n_img * Ho * Wo * 4 * C8;
+  if (t >= total) return;
+  const int c = (int)(t % C8);
+  int64_t r = t / C8;
+  const int q = (int)(r & 3); r >>= 2;
+  const int X = (int)(r % Wo); r /= Wo;
+  const int Y = (int)(r % Ho);
+  const int n = (int)(r / Ho);
+  const int y = 2 * Y + (q >> 1) - 1, x = 2 * X + (q & 1) - 1;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+  if (y >= 0 && y < H && x >= 0 && x < W) {
+    const float4* src = reinterpret_cast<const float4*>(in + (((int64_t)n * H + y) * W + x) * (int64_t)C8 * 8) + 2 * c;
+    a = __ldg(src); b = __ldg(src + 1);
+    if (relu) {
+      a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+      b.x = fmaxf(b.x, 0.f); b.y = fmaxf(b.y, 0.f); b.z = fmaxf(b.z, 0.f); b.w = fmaxf(b.w, 0.f);
+    }
+  }
+  uint2 h0, l0, h1, l1;
+  const bool bad = split4(a, h0, l0) | split4(b, h1, l1);
+  const int64_t o = ((((int64_t)n * Ho + Y) * Wo + X) * 4 + q) * (int64_t)C8 * 8 + c * 8;
+  *reinterpret_cast<uint4*>(out + o) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+  *reinterpret_cast<uint4*>(out + plane + o) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+  if (bad && flag) atomicOr(flag, 1);
+}
+
 // ------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -902,6 +937,35 @@ struct TileCfg { int bn, cg, ns; };
 int g_forced_bn = [] { const char* e = getenv("MAGE_TC_BN"); return e ? atoi(e) : 0; }();
 int g_forced_pair = [] { const char* e = getenv("MAGE_TC_PAIR"); return e ? atoi(e) : -1; }();
 int g_ns = [] { const char* e = getenv("MAGE_TC_NS"); return e ? atoi(e) : 1; }();   // N-split 256-wide pair tiles for plain GEMMs
+int g_small = [] { const char* e = getenv("MAGE_TC_SMALL"); return e ? atoi(e) : 1; }();   // one-tile cost model for sub-2-wave GEMMs
+
+// Small problems (a decode step of a few prompts: M = 2048 rows at 8 prompts) run one or two waves of tiles, so neither the
+// double-buffered accumulator nor wave-averaging helps: what counts is the number of waves and what ONE tile costs -- per
+// k-block the larger of its MMA time and the time to pull its operand bytes into the SM (measured: ~110 GB/s per SM; the
+// 128x64 tiles of the K = 2048 GEMM are ingest-bound at B = 8, profiles/r02a_*).  Pick the tile that minimises
+// waves x (fixed + k_iters x t_k).  Candidates: CTA pairs 256 x {64,128,192,256} (even row-tile count), single 128 x {64,128}.
+TileCfg pick_small(int N, int64_t m_tiles, int K, int sms, bool pair_ok) {
+  const double ingest = 110e9, clk = 1.9e9, flop_clk = 8192.0;
+  TileCfg best{0, 0, 0};
+  double best_t = 1e30;
+  const int k_iters = K / BK;
+  for (int cg = 2; cg >= 1; --cg) {
+    if (cg == 2 && !pair_ok) continue;
+    const int units = sms / cg;
+    for (int bn : {256, 192, 128, 64}) {
+      if (N % bn != 0 || (cg == 1 && bn > 128)) continue;
+      const int64_t tiles = (m_tiles / cg) * (N / bn);
+      const int64_t waves = (tiles + units - 1) / units;
+      const double bytes = 2.0 * BM * BK * 2 + 2.0 * (bn / cg) * BK * 2;        // per CTA per k-block: A hi+lo, its W share hi+lo
+      const double t_mma = 3.0 * (BK / UK) * (2.0 * BM * bn * UK) / flop_clk / clk;
+      const double t_k = bytes / ingest > t_mma ? bytes / ingest : t_mma;
+      const double t_epi = 0.35e-6 * (bn / 32);                                // epilogue of the last tile: not overlapped
+      const double t = waves * (k_iters * t_k + 0.6e-6) + t_epi;
+      if (t < best_t) { best_t = t; best = {bn, cg, 0}; }
+    }
+  }
+  return best;
+}
 
 TileCfg pick_cfg(int N, int64_t m_tiles, int K, bool gemm = false) {
   const int forced_bn = g_forced_bn, forced_pair = g_forced_pair;
@@ -912,13 +976,15 @@ TileCfg pick_cfg(int N, int64_t m_tiles, int K, bool gemm = false) {
   const bool ns_ok = gemm && pair_ok && g_ns != 0 && N % 256 == 0 && (forced_bn == 0 || forced_bn == 256);
   // measured: wins only for long k loops (16384x2048x4096: 530 vs 508 TFLOP/s); at K = 512 the 256x128 tile is 13-30 % faster
   if (ns_ok && (g_ns == 2 || (forced_bn == 0 && K >= 4096 && (m_tiles / 2) * (N / 256) >= sms / 2))) return {256, 2, 1};
-  if (forced_bn && N % forced_bn == 0) return {forced_bn, (pair_ok && forced_pair == 1) ? 2 : 1, 0};
+  if (forced_bn && N % forced_bn == 0 && (forced_bn != 192 || (pair_ok && forced_pair == 1))) return {forced_bn, (pair_ok && forced_pair == 1) ? 2 : 1, 0};
+  // fewer than two waves of the default 256x128 / 128x128 tiling: choose by the one-tile cost model
+  if (gemm && forced_pair == -1 && g_small && N % 64 == 0 && m_tiles * ((N + 127) / 128) < 2 * sms) {
+    const TileCfg c = pick_small(N, m_tiles, K, sms, pair_ok);
+    if (c.bn) return c;
+  }
   if (pair_ok) {
-    // measured (tools/tc_microbench.py, profiles/): the 256x256 pair tile wins once the k loop is long enough to amortise
-    // its un-overlapped epilogue (single TMEM accumulator stage): K >= 1024.  Shorter k loops stay on the double-buffered
-    // 128-wide single-CTA tile.
     // the 256x128 pair tile (two TMEM accumulator stages, each CTA streams half of the W tile) is the fastest shape on every
-    // GEMM / conv of the path; 256x256 (single accumulator stage) only pays off for very long k loops.
+    // large GEMM / conv of the path; 256x256 (single accumulator stage) only pays off for very long k loops.
     const int64_t pairs = m_tiles / 2;
     if (N % 256 == 0 && ((pairs * (N / 256) >= sms / 2 && K >= 8192) || (forced_pair == 1 && forced_bn == 0))) return {256, 2, 0};
     if (N % 128 == 0 && (pairs * (N / 128) >= sms / 2 || forced_pair == 1)) return {128, 2, 0};
@@ -936,6 +1002,7 @@ int dispatch(TileCfg c, const Maps& mp, const TcParams& p, cudaStream_t st) {
     if (c.ns) return c.bn == 256 ? launch_tc<256, 2, true>(mp, p, st) : MAGE_ENOTSUP;
     switch (c.bn) {
       case 256: return launch_tc<256, 2>(mp, p, st);
+      case 192: return launch_tc<192, 2>(mp, p, st);
       case 128: return launch_tc<128, 2>(mp, p, st);
       case 64: return launch_tc<64, 2>(mp, p, st);
     }
@@ -985,7 +1052,7 @@ int g_halo = [] { const char* e = getenv("MAGE_TC_HALO"); return e ? atoi(e) : 1
 // weight tile), the widest N tile the channel count allows; BN = 256 exists only as a pair (weight ring depth).
 TileCfg pick_halo_cfg(int Cout, int64_t m_tiles) {
   const bool pair_ok = g_forced_pair != 0 && m_tiles % 2 == 0;
-  if (g_forced_bn && Cout % g_forced_bn == 0 && (g_forced_bn != 256 || pair_ok)) return {g_forced_bn, (pair_ok && (g_forced_pair == 1 || g_forced_bn == 256)) ? 2 : 1, 0};
+  if (g_forced_bn && g_forced_bn != 192 && Cout % g_forced_bn == 0 && (g_forced_bn != 256 || pair_ok)) return {g_forced_bn, (pair_ok && (g_forced_pair == 1 || g_forced_bn == 256)) ? 2 : 1, 0};
   if (pair_ok) {
     if (Cout % 128 == 0) return {128, 2, 0};   // measured faster than 256-wide pair tiles (two accumulator stages)
     if (Cout % 64 == 0) return {64, 2, 0};
@@ -1021,7 +1088,7 @@ int make_w_map(CUtensorMap* map, const void* W, int64_t ldw, int64_t w_plane, in
 }  // namespace
 
 extern "C" int mage_tc_tuning(int bn, int pair) {
-  MAGE_CHECK_ARG((bn == 0 || bn == 64 || bn == 128 || bn == 256) && pair >= -1 && pair <= 1);
+  MAGE_CHECK_ARG((bn == 0 || bn == 64 || bn == 128 || bn == 192 || bn == 256) && pair >= -1 && pair <= 1);
   g_forced_bn = bn;
   g_forced_pair = pair;
   return 0;
@@ -1054,6 +1121,16 @@ extern "C" int mage_patch_rows_split_f32(const float* in, void* out, int64_t pla
   const int64_t total = (int64_t)n_img * H * W * 8;
   patch_rows_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(in, reinterpret_cast<__half*>(out), plane, n_img,
                                                                                           C, H, W, KW, pad);
+  return mage_post_launch();
+}
+
+extern "C" int mage_s2d_pad_split_f32(const float* in, void* out, int64_t plane, int n_img, int H, int W, int C, int relu, int* flag,
+                                      void* stream) {
+  MAGE_CHECK_ARG(n_img > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && C > 0 && C % 8 == 0 && aligned16(in) && aligned16(out) &&
+                 plane % 8 == 0);
+  const int64_t total = (int64_t)n_img * (H / 2 + 1) * (W / 2 + 1) * 4 * (C / 8);
+  s2d_pad_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(in, reinterpret_cast<__half*>(out), plane, n_img,
+                                                                                       H, W, C / 8, relu, flag);
   return mage_post_launch();
 }
 

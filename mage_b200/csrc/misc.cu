@@ -282,6 +282,88 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
   out[t] = in[(n * C + c) * HW + p];
 }
 
+
+// ------------------------------------------------------------------ MAGE+ continuous head: GroupNorm(32) -> SiLU -> 1x1x1 conv
+// (mage_model.py:349-354, :386-388).  The GroupNorm statistics of a sample span its 16 channels x ALL temporal slots x H x W,
+// so they are kept as per-(slot, sample, group) partial sums in double (a slot's partials are recomputed only when its hidden
+// state changes) and combined over the slots by the consumer.
+// gn_partial: one block per (slot, sample, group): 256 threads = the HW positions (strided if HW != 256), 16 channels each.
+__global__ void __launch_bounds__(256) gn_partial_kernel(const float* __restrict__ x, double* __restrict__ part, int B, int HW,
+                                                         int C, int cpg) {
+  __shared__ double red[2][256];
+  const int g = blockIdx.x % (C / cpg);
+  const int sb = blockIdx.x / (C / cpg);               // slot * B + sample
+  const float* base = x + (int64_t)sb * HW * C + g * cpg;
+  double s = 0.0, q = 0.0;
+  for (int p = threadIdx.x; p < HW; p += 256) {
+    const float* r = base + (int64_t)p * C;
+    for (int c = 0; c < cpg; c += 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(r + c));
+      s += (double)v.x + (double)v.y + (double)v.z + (double)v.w;
+      q += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+    }
+  }
+  red[0][threadIdx.x] = s;
+  red[1][threadIdx.x] = q;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {   // fixed-order tree: deterministic
+    if (threadIdx.x < o) {
+      red[0][threadIdx.x] += red[0][threadIdx.x + o];
+      red[1][threadIdx.x] += red[1][threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    part[(int64_t)blockIdx.x * 2] = red[0][0];
+    part[(int64_t)blockIdx.x * 2 + 1] = red[1][0];
+  }
+}
+
+// gn_head: one warp per row (slot, sample, position) of `x` [rows, 512]; lane = group (32 groups of 16 channels).
+//   out[row, co] = bias[co] + sum_c w[co, c] * silu((x[row, c] - mean_g) * rstd_g * gamma[c] + beta[c]),   co < cout <= 8
+// mean/rstd of (sample, group) from the partial sums of ALL n_slots slots (part [n_slots, B, 32, 2]).
+__global__ void __launch_bounds__(256) gn_head_kernel(const float* __restrict__ x, const double* __restrict__ part,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      const float* __restrict__ w, const float* __restrict__ bias,
+                                                      float* __restrict__ out, int rows, int B, int HW, int n_slots, int cout,
+                                                      float eps) {
+  constexpr int C = 512, CPG = 16;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int b = (row / HW) % B;
+  double s = 0.0, q = 0.0;
+  for (int sl = 0; sl < n_slots; ++sl) {
+    const double* pp = part + (((int64_t)sl * B + b) * 32 + lane) * 2;
+    s += pp[0];
+    q += pp[1];
+  }
+  const double n = (double)n_slots * HW * CPG;
+  const double mean_d = s / n;
+  const float mean = (float)mean_d;
+  const float rstd = rsqrtf((float)(q / n - mean_d * mean_d) + eps);
+  float y[CPG];
+  const float* xr = x + (int64_t)row * C + lane * CPG;
+#pragma unroll
+  for (int c = 0; c < CPG; c += 4) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(xr + c));
+    const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + lane * CPG + c));
+    const float4 bt = __ldg(reinterpret_cast<const float4*>(beta + lane * CPG + c));
+    const float t0 = (v.x - mean) * rstd * gm.x + bt.x, t1 = (v.y - mean) * rstd * gm.y + bt.y;
+    const float t2 = (v.z - mean) * rstd * gm.z + bt.z, t3 = (v.w - mean) * rstd * gm.w + bt.w;
+    y[c] = t0 / (1.f + expf(-t0)); y[c + 1] = t1 / (1.f + expf(-t1));
+    y[c + 2] = t2 / (1.f + expf(-t2)); y[c + 3] = t3 / (1.f + expf(-t3));
+  }
+  for (int co = 0; co < cout; ++co) {
+    const float* wr = w + (int64_t)co * C + lane * CPG;
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < CPG; ++c) acc = fmaf(y[c], __ldg(wr + c), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) out[(int64_t)row * cout + co] = acc + __ldg(bias + co);
+  }
+}
+
 // ------------------------------------------------------------------ first conv layer (tiny Cin, planar input)
 // block: one output row segment of PX pixels x all Cout channels; the input patch sits in shared memory,
 // each thread owns one output channel and PX accumulators; weights stream through L1 (transposed [K][Cout]).
@@ -481,5 +563,21 @@ extern "C" int mage_kv_append_f32(const float* qkv, float* kcache, float* vcache
   MAGE_CHECK_ARG(M > 0 && C % 4 == 0 && pos >= 0 && pos < Lmax && aligned16(qkv) && aligned16(kcache) && aligned16(vcache));
   const int64_t total = (int64_t)M * (C / 4);
   kv_append_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(qkv, kcache, vcache, M, C / 4, pos, Lmax);
+  return mage_post_launch();
+}
+
+extern "C" int mage_gn_partial_f32(const float* x, double* part, int n_slots, int B, int HW, int C, int groups, void* stream) {
+  MAGE_CHECK_ARG(n_slots > 0 && B > 0 && HW > 0 && groups > 0 && C % groups == 0 && (C / groups) % 4 == 0 && aligned16(x));
+  gn_partial_kernel<<<(unsigned)((int64_t)n_slots * B * groups), 256, 0, as_stream(stream)>>>(x, part, B, HW, C, C / groups);
+  return mage_post_launch();
+}
+
+extern "C" int mage_gn_silu_head_f32(const float* x, const double* part, const float* gamma, const float* beta, const float* w,
+                                     const float* bias, float* out, int rows, int B, int HW, int n_slots, int C, int groups,
+                                     int cout, float eps, void* stream) {
+  MAGE_CHECK_ARG(rows > 0 && B > 0 && HW > 0 && n_slots > 0 && C == 512 && groups == 32 && cout >= 1 && cout <= 8);
+  MAGE_CHECK_ARG(aligned16(x) && aligned16(gamma) && aligned16(beta));
+  gn_head_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, as_stream(stream)>>>(x, part, gamma, beta, w, bias, out, rows, B, HW, n_slots,
+                                                                            cout, eps);
   return mage_post_launch();
 }

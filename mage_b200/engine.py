@@ -70,8 +70,6 @@ class VQVAEEngine:
         assert self.device.type == "cuda", "VQVAEEngine needs CUDA tensors (no CPU path)"
         self.down_ratio = 4 if "encoder.1.running_mean" in sd else 8
         self.backend = backend or default_backend()
-        if self.down_ratio != 8:
-            self.backend = "simt"  # the f4 (MNIST) stack keeps the fp32 FFMA kernels (stride-2 / Cout=1 layers)
         ops.flag(self.device)
         # Decoder precision budget: the decoder feeds no token and its bar is 1e-3 relative on pixels (north_star),
         # so the two convolutions that hold 63 % of its FLOPs -- block.5 and block.7 (+ fused pixel head) of the last, 128x128
@@ -122,7 +120,30 @@ class VQVAEEngine:
                         w[f"{name}.p{py}{px}"] = sub.permute(1, 2, 3, 0).contiguous()  # [Cout,2,2,Cin]
         self.w = w
         if self.backend == "tc":
-            self._prepare_tc(sd)
+            if self.down_ratio == 8:
+                self._prepare_tc(sd)
+            else:
+                self._prepare_tc_f4(sd)
+
+    def _prepare_tc_f4(self, sd):
+        """Split copies of the f4 (MNIST) stack's tensor-core operands (vqvae_model.py:172-189): the 4x4 stride-2 convolution
+        encoder.3 as a 2x2 valid convolution over the padded space-to-depth map (mage_s2d_pad_split_f32), the ResBlocks' BN-folded
+        3x3 / 1x1 weights, the four 2x2 sub-pixel phases of ConvTranspose decoder.3, the (ReLU-ed) codebook.  The two single-channel
+        ends -- encoder.0 (1 -> 256, K = 16) and decoder.6 (256 -> 1) -- are 8 MFLOP per image each and stay on the FFMA kernels."""
+        w, ws = self.w, {}
+        w3 = sd["encoder.3.weight"]                                   # [Cout, Cin, 4, 4], ky = 2*ty + py, kx = 2*tx + px
+        co, ci = w3.shape[:2]
+        w2 = w3.view(co, ci, 2, 2, 2, 2).permute(0, 2, 4, 3, 5, 1).reshape(co, 2, 2, 4 * ci).contiguous()   # [co, ty, tx, (py,px,c)]
+        ws["encoder.3.s2d"] = ops.split(w2)
+        for blk in ("encoder.4", "encoder.5", "decoder.0", "decoder.1"):
+            ws[blk + ".c3.w"] = ops.split(w[blk + ".c3.w"])
+            ws[blk + ".c1.w"] = ops.split(w[blk + ".c1.w"])
+        for py in (0, 1):
+            for px in (0, 1):
+                ws[f"decoder.3.p{py}{px}"] = ops.split(w[f"decoder.3.p{py}{px}"])
+        self.ws = ws
+        self.cb_relu = torch.relu(self.codebook).contiguous()
+        self.cb_relu_split = ops.split(self.codebook, relu=True)
 
     def _prepare_tc(self, sd):
         """Split (fp16 hi/lo) copies of every tensor-core operand: conv / 1x1 weights, the codebook (raw and
@@ -199,10 +220,28 @@ class VQVAEEngine:
                                 act=(ACT_RELU | ACT_POST) if final_relu else ACT_NONE)
         return out.view(n, H, W, -1)
 
+    def _res_block_tc(self, name: str, xr: torch.Tensor, xr_split: torch.Tensor, post_relu: bool, want):
+        """ResBlock (vqvae_model.py:111-124) on the tensor cores; xr / xr_split = relu(x) as fp32 (the skip: the block's leading
+        ReLU is in place) and as split operand.  Returns (fp32, split) of xr + BN(1x1(relu(BN(3x3(xr))))), ReLU-ed when the next
+        consumer's in-place ReLU is folded in (`post_relu`)."""
+        w, ws = self.w, self.ws
+        n, H, W, C = xr.shape
+        _, h, _ = ops.conv2d_tc(xr_split, ws[name + ".c3.w"], w[name + ".c3.b"], pad=(1, 1), act=ACT_RELU, want=("split",))
+        out, out_split, _ = ops.gemm_tc(h.view(2, -1, C), ws[name + ".c1.w"], w[name + ".c1.b"], residual=xr.view(-1, C),
+                                        act=(ACT_RELU | ACT_POST) if post_relu else ACT_NONE, want=want)
+        return (out.view(n, H, W, C) if out is not None else None,
+                out_split.view(2, n, H, W, C) if out_split is not None else None)
+
     def encode_features(self, x: torch.Tensor) -> torch.Tensor:
         """x [N,C,H,W] planar fp32 -> z_e NHWC [N,h,w,D] (vqvae_model.py:172-179 / :192-202)."""
         w = self.w
         x = x.contiguous()
+        if self.backend == "tc" and self.down_ratio == 4:
+            h = ops.conv2d_first(x, w["enc0_wt"], w["enc0_b"], cout=w["enc0_b"].numel(), kh=4, kw=4, stride=2, pad=1, act=ACT_RELU)
+            xr, xr_split, _ = ops.conv2d_tc(ops.s2d_pad_split(h), self.ws["encoder.3.s2d"], w["encoder.3.bias"], pad=(0, 0),
+                                            act=ACT_RELU, want=("f32", "split"))          # relu = encoder.4's in-place one
+            xr, xr_split = self._res_block_tc("encoder.4", xr, xr_split, post_relu=True, want=("f32", "split"))
+            return self._res_block_tc("encoder.5", xr, xr_split, post_relu=False, want=("f32",))[0]
         if self.backend == "tc":
             if "enc0_rows" in self.ws and x.shape[2] % 16 == 0 and x.shape[3] % 8 == 0:
                 rows = ops.patch_rows_split(x, self.enc0_kw, self.enc0_pad)
@@ -305,10 +344,28 @@ class VQVAEEngine:
     def decode_into(self, idx: torch.Tensor, out: torch.Tensor, out_img_stride: int) -> None:
         """VectorQuantizedVAE.decode: idx int64 [N,h,w] -> tanh pixels written planar at
         out.data_ptr() + n*out_img_stride (elements), each image [C,H,W] contiguous."""
-        if self.backend == "tc":
+        if self.backend == "tc" and self.down_ratio == 8:
             return self._decode_into_tc(idx, out, out_img_stride)
         w = self.w
         n = idx.shape[0]
+        if self.backend == "tc":
+            # f4 decoder (vqvae_model.py:180-189): ResBlocks and ConvTranspose 256 -> 256 (four 2x2 sub-pixel phases) on tcgen05
+            H, W = idx.shape[1], idx.shape[2]
+            zr = ops.embedding(idx.reshape(-1), self.cb_relu).view(n, H, W, self.D)       # relu(z): decoder.0's in-place ReLU
+            zr_split = ops.embedding_split(idx, self.cb_relu_split)
+            h, h_split = self._res_block_tc("decoder.0", zr, zr_split, post_relu=True, want=("f32", "split"))
+            _, h_split = self._res_block_tc("decoder.1", h, h_split, post_relu=True, want=("split",))   # + decoder.2 ReLU
+            C = self.D
+            up1 = torch.empty(n, 2 * H, 2 * W, C, device=idx.device, dtype=torch.float32)
+            for py in (0, 1):
+                for px in (0, 1):
+                    ops.conv2d_tc(h_split, self.ws[f"decoder.3.p{py}{px}"], w["decoder.3.b"], pad=(1 - py, 1 - px), act=ACT_RELU,
+                                  want=(), out=up1, out_hw=(H, W), scatter=(2, 2, py, px), full_hw=(2 * H, 2 * W))
+            for py in (0, 1):
+                for px in (0, 1):
+                    ops.conv2d(up1, w[f"decoder.6.p{py}{px}"], w["decoder.6.b"], pad=(1 - py, 1 - px), act=ACT_TANH, out=out,
+                               out_hw=(2 * H, 2 * W), scatter=(2, 2, py, px), full_hw=(4 * H, 4 * W), out_img_stride=out_img_stride)
+            return
         z = ops.embedding(idx.reshape(-1), self.codebook).view(n, idx.shape[1], idx.shape[2], self.D)
         if self.down_ratio == 8:
             h = self._dec_block("decoder.0", z, up=False)

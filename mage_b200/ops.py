@@ -153,6 +153,17 @@ def patch_rows_split(x_nchw: torch.Tensor, kw: int, pad: int) -> torch.Tensor:
     return out
 
 
+def s2d_pad_split(x: torch.Tensor, relu: bool = False) -> torch.Tensor:
+    """fp32 NHWC [n,H,W,C] -> split [2, n, H/2+1, W/2+1, 4C]: padded space-to-depth (operand of a 4x4 stride-2 pad-1 convolution
+    rewritten as a 2x2 stride-1 valid convolution, see mage_b200.h)."""
+    n, H, W, C = x.shape
+    out = torch.empty(2, n, H // 2 + 1, W // 2 + 1, 4 * C, device=x.device, dtype=torch.float16)
+    with _Prof("split", 8.0 * out.numel()):
+        check(_lib.lib().mage_s2d_pad_split_f32(_p(_f32(x)), _p(out), out.numel() // 2, n, H, W, C, int(relu), _p(flag(x.device)),
+                                                _stream()), "mage_s2d_pad_split_f32")
+    return out
+
+
 def embedding_split(idx: torch.Tensor, table: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """idx int64 [...], table split [2, K, C] -> split [2, ..., C]."""
     assert idx.dtype == torch.int64 and idx.is_contiguous()
@@ -343,9 +354,11 @@ def temporal_attn_step(qkv: torch.Tensor, kcache: torch.Tensor, vcache: torch.Te
                        scale: float, out_split: Optional[torch.Tensor] = None) -> None:
     M = qkv.shape[0]
     Lmax = kcache.shape[1]
+    if out_split is not None:   # may be a row range of a larger split tensor: the lo plane sits stride(0) elements after the hi plane
+        assert out_split.dtype == torch.float16 and out_split.shape[0] == 2 and out_split[0].is_contiguous()
     with _Prof("temporal_attn", 8.0 * M * (pos + 1) * kcache.shape[2]):
         check(_lib.lib().mage_temporal_attn_step_f32(_p(_f32(qkv)), _p(kcache), _p(vcache), _p(out), _p(out_split),
-                                                     out_split.numel() // 2 if out_split is not None else 0, _p(flag(qkv.device)),
+                                                     out_split.stride(0) if out_split is not None else 0, _p(flag(qkv.device)),
                                                      M, pos, Lmax, scale, _stream()), "mage_temporal_attn_step_f32")
 
 
@@ -436,4 +449,25 @@ def nchw_to_nhwc(x: torch.Tensor) -> torch.Tensor:
     out = torch.empty(n, H, W, C, device=x.device, dtype=torch.float32)
     with _Prof("misc", 0.0):
         check(_lib.lib().mage_nchw_to_nhwc_f32(_p(_f32(x)), _p(out), n, C, H * W, _stream()), "mage_nchw_to_nhwc_f32")
+    return out
+
+
+def gn_partial(x: torch.Tensor, part: torch.Tensor, B: int, HW: int, groups: int = 32) -> None:
+    """x fp32 [n_slots*B*HW, C] -> part f64 [n_slots, B, groups, 2] (sum, sum of squares per slot / sample / group)."""
+    C = x.shape[-1]
+    n_slots = x.numel() // (B * HW * C)
+    assert part.dtype == torch.float64 and part.is_contiguous() and part.numel() == n_slots * B * groups * 2
+    with _Prof("misc", 0.0):
+        check(_lib.lib().mage_gn_partial_f32(_p(_f32(x)), _p(part), n_slots, B, HW, C, groups, _stream()), "mage_gn_partial_f32")
+
+
+def gn_silu_head(x: torch.Tensor, part: torch.Tensor, gamma, beta, w: torch.Tensor, bias: torch.Tensor, B: int, HW: int,
+                 eps: float = 1e-5) -> torch.Tensor:
+    """GroupNorm(32) (statistics over all slots of `part` [n_slots,B,32,2]) -> SiLU -> linear to w.shape[0] channels, rows of x."""
+    rows, C = x.shape
+    cout = w.shape[0]
+    out = torch.empty(rows, cout, device=x.device, dtype=torch.float32)
+    with _Prof("misc", 0.0):
+        check(_lib.lib().mage_gn_silu_head_f32(_p(_f32(x)), _p(part), _p(_f32(gamma)), _p(_f32(beta)), _p(_f32(w)), _p(_f32(bias)),
+                                               _p(out), rows, B, HW, part.shape[0], C, 32, cout, eps, _stream()), "mage_gn_silu_head_f32")
     return out

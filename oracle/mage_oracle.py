@@ -388,3 +388,87 @@ def generate_incremental(sd: SD, batch: Dict[str, torch.Tensor], noise: Optional
     pix = vqvae_decode(fsd, tokens.view(-1, *tokens.shape[-2:]))
     pix = pix.view(B, L - 1, *pix.shape[1:])
     return torch.cat([batch["images"][:, 0:1], pix], 1)
+
+
+# --------------------------------------------------------------------------------------
+# MAGE+ branch: use_cids=False (continuous latents, no codebook / argmax)
+#   mage_model.py:482-483 (Linear embed), :349-354 + :386-388 (GroupNorm -> SiLU -> 1x1x1 Conv3d head),
+#   :646,:684,:689 (continuous autoregression), :93 (ln_q / ln_kv motion anchor -- the documented manual edit).
+# The first stage (AutoencoderKL of un-vendored latent-diffusion@main in the shipped yaml) is a pluggable module whose
+# encode()/decode() are taken as given: PARITY UNPINNED for that module, pinned for everything below it.
+# --------------------------------------------------------------------------------------
+def embed_latents(sd: SD, z: torch.Tensor) -> torch.Tensor:
+    """visual_token_embedding = Linear(embed_dim, C) on channels-last latents (mage_model.py:482-483, :646).
+    z [..., c, H, W] -> [..., C, H, W]."""
+    nd = z.dim()
+    zl = z.permute(*range(nd - 3), nd - 2, nd - 1, nd - 3)
+    e = F.linear(zl, sd["visual_token_embedding.weight"], sd["visual_token_embedding.bias"])
+    return e.permute(*range(nd - 3), nd - 1, nd - 3, nd - 2).contiguous()
+
+
+def ma_encoder_ln(sd: SD, q: torch.Tensor, kv: torch.Tensor) -> torch.Tensor:
+    """MAEncoder with TransformerBlock line 93 (the MAGE+ edit): x = q + attn(ln_q(q), ln_kv(kv), ln_kv(kv), key_mask=None)."""
+    i = 0
+    x = q
+    while f"ma_encoder.blocks.{i}.attn.in_proj_weight" in sd:
+        p = f"ma_encoder.blocks.{i}"
+        k = _ln(sd, p + ".ln_kv", kv)
+        x = x + _mha(sd, p + ".attn", _ln(sd, p + ".ln_q", x), k, k, x.shape[-1] // 32)
+        x = x + _mlp(sd, p + ".mlp", _ln(sd, p + ".ln_2", x))
+        i += 1
+    return x
+
+
+def continuous_head(sd: SD, hidden: torch.Tensor) -> torch.Tensor:
+    """FlatAxialDecoder.out for use_cids=False (mage_model.py:349-354, :386-388): hidden [B,F,H,W,C] -> GroupNorm(32) over
+    (C/32 channels x F x H x W) per sample -> SiLU -> 1x1x1 Conv3d -> [B,F,H,W,c_out].  The statistics span ALL F slots."""
+    p = "generate_model.out."
+    x = hidden.permute(0, 4, 1, 2, 3).contiguous()
+    x = F.group_norm(x, 32, sd[p + "0.weight"], sd[p + "0.bias"], eps=1e-5)
+    x = F.conv3d(F.silu(x), sd[p + "2.weight"], sd[p + "2.bias"])
+    return x.permute(0, 2, 3, 4, 1).contiguous()
+
+
+def flat_axial_decoder_continuous(sd: SD, motion: torch.Tensor, imgs: torch.Tensor) -> torch.Tensor:
+    """FlatAxialDecoder.forward, use_cids=False: same blocks as `flat_axial_decoder`, continuous head."""
+    p = "generate_model."
+    x = torch.cat([F.linear(motion, sd[p + "context_linear.weight"], sd[p + "context_linear.bias"]).unsqueeze(1),
+                   F.linear(imgs, sd[p + "in_linear.weight"], sd[p + "in_linear.bias"])], 1)
+    Lmax = sd[p + "T_positional_embedding"].shape[0]
+    assert x.shape[1] == Lmax
+    x = x + sd[p + "T_positional_embedding"]
+    mask = torch.full((Lmax, Lmax), float("-inf")).triu_(1).to(x.device)
+    i = 0
+    while (p + f"blocks.{i}.ln_1.weight") in sd:
+        x = axial_block(sd, p + f"blocks.{i}", x, i % 3 + 1, mask if i % 3 == 0 else None)
+        i += 1
+    return continuous_head(sd, x[:, 1:])
+
+
+@torch.no_grad()
+def generate_continuous(sd: SD, z0: torch.Tensor, text: torch.Tensor, speed: Optional[torch.Tensor],
+                        noise: Optional[torch.Tensor] = None, ma_ln: bool = False, trace: Optional[dict] = None) -> torch.Tensor:
+    """MAGE.autoregressive_generate for use_cids=False between the two first-stage calls (mage_model.py:642-689), reference
+    evaluation order.  z0 [B,c,H,W] = first_stage_encode(images[:, 0:1])[:, 0]; returns the predicted latents [B,L-1,c,H,W]
+    (what the reference hands to first_stage_decode, :689-690)."""
+    L = sd["generate_model.T_positional_embedding"].shape[0]
+    B, c, H, W = z0.shape
+    x_emb = embed_latents(sd, z0.unsqueeze(1))                                   # [B,1,C,H,W]
+    C = x_emb.shape[2]
+    first = token_features(sd, x_emb)[:, 0].reshape(B, -1, C).permute(1, 0, 2).contiguous()
+    t = text_encoder(sd, text).permute(1, 0, 2).contiguous()
+    a = (ma_encoder_ln if ma_ln else ma_encoder)(sd, first, t).permute(1, 0, 2).contiguous().view(B, H, W, C)
+    if noise is not None:
+        y = F.conv2d(noise, sd["conv_d2.weight"], None, padding=1)
+        a = adain(sd, a.permute(0, 3, 1, 2).contiguous(), y).permute(0, 2, 3, 1).contiguous()
+    if speed is not None:
+        a = a + (speed.view(B, 1) @ sd["speed_embedding"]).unsqueeze(1).unsqueeze(1)
+    if trace is not None:
+        trace["anchor"] = a
+    inp = x_emb.repeat(1, L - 1, 1, 1, 1)
+    pred = None
+    for i in range(L - 1):
+        pred = flat_axial_decoder_continuous(sd, a, token_features(sd, inp))        # [B,L-1,H,W,c]
+        if i != L - 2:
+            inp[:, i + 1] = embed_latents(sd, pred.permute(0, 1, 4, 2, 3))[:, i]
+    return pred.permute(0, 1, 4, 2, 3).contiguous()

@@ -16,7 +16,7 @@ def _ops():
     return ops
 
 
-@pytest.fixture(params=[("auto", 0, -1, True), ("pair256", 256, 1, True), ("pair128", 128, 1, True), ("pair64", 64, 1, True),
+@pytest.fixture(params=[("auto", 0, -1, True), ("pair256", 256, 1, True), ("pair192", 192, 1, True), ("pair128", 128, 1, True), ("pair64", 64, 1, True),
                         ("single", 0, 0, True), ("auto-nohalo", 0, -1, False), ("pair256-nohalo", 256, 1, False),
                         ("single-nohalo", 0, 0, False), ("nsplit", 0, -1, True), ("auto-no-nsplit", 0, -1, True)],
                 ids=lambda p: p[0], autouse=True)
@@ -71,7 +71,8 @@ def test_split_roundtrip_and_flag():
     ops.check_flag(DEV)  # flag was cleared
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (300, 512, 512), (4096, 1536, 512), (1000, 2048, 512), (513, 512, 2048),
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (300, 512, 512), (4096, 1536, 512), (2048, 1536, 512), (2048, 2048, 512), (2048, 512, 2048),
+                                   (1024, 1536, 512), (1000, 2048, 512), (513, 512, 2048),
                                    (1000, 64, 576), (20000, 128, 64), (40, 1024, 256), (16384, 512, 512), (2560, 256, 1024)])
 def test_gemm_tc_shapes(M, N, K):
     ops = _ops()
@@ -280,3 +281,51 @@ def test_first_conv_as_im2row_plus_column_conv(n, C, H, W, k, tile_cfg):
     want = F.conv2d(x.double(), w.double(), b.double(), padding=k // 2).permute(0, 2, 3, 1)
     _close(out, want)
     _close(_unsplit(spr), F.relu(want))
+
+
+@pytest.mark.parametrize("n,H,C,Cout", [(2, 32, 256, 256), (3, 32, 64, 128)])
+def test_strided_conv_as_s2d_valid_conv(n, H, C, Cout, tile_cfg):
+    """vqvae_model.py:175 (Conv2d 4x4, stride 2, pad 1) on the tensor cores: padded space-to-depth (mage_s2d_pad_split_f32) followed
+    by a 2x2 stride-1 VALID convolution with the re-indexed weights -- the same products, each weight used once."""
+    ops = _ops()
+    x = F.relu(_rand(n, C, H, H, seed=1))
+    w = _rand(Cout, C, 4, 4, seed=2, scale=(16 * C) ** -0.5)
+    b = _rand(Cout, seed=3)
+    want = F.conv2d(x.double(), w.double(), b.double(), stride=2, padding=1).permute(0, 2, 3, 1)
+    s = ops.s2d_pad_split(x.permute(0, 2, 3, 1).contiguous().to(DEV))
+    assert tuple(s.shape) == (2, n, H // 2 + 1, H // 2 + 1, 4 * C)
+    # s2d[n, Y, X, (py*2+px)*C + c] == x[n, c, 2Y+py-1, 2X+px-1]
+    xp = F.pad(x, (1, 1, 1, 1)).double()
+    sd = _unsplit(s).view(n, H // 2 + 1, H // 2 + 1, 2, 2, C)
+    for py in (0, 1):
+        for px in (0, 1):
+            ref = xp[:, :, py::2, px::2][:, :, : H // 2 + 1, : H // 2 + 1].permute(0, 2, 3, 1)
+            assert (sd[:, :, :, py, px] - ref).abs().max() <= 2.0 ** -22 * x.abs().max()
+    w2 = w.view(Cout, C, 2, 2, 2, 2).permute(0, 2, 4, 3, 5, 1).reshape(Cout, 2, 2, 4 * C).contiguous()
+    out, _, _ = ops.conv2d_tc(s, ops.split(w2.to(DEV)), b.to(DEV), pad=(0, 0))
+    torch.cuda.synchronize()
+    ops.check_flag(DEV)
+    assert tuple(out.shape) == (n, H // 2, H // 2, Cout)
+    _close(out, want)
+
+
+@pytest.mark.parametrize("n,H,Cin,Cout", [(4, 32, 64, 64), (2, 64, 64, 256)])
+def test_conv2d_tc_single_pass_is_fp16_grade_not_fp32_grade(n, H, Cin, Cout, tile_cfg):
+    """passes=1 (decoder precision budget): hi*hi products only.  The result must equal the convolution of the fp16-ROUNDED
+    operands to fp32-accumulation noise (i.e. the mode really drops the two correction MMAs and nothing else), and sit at fp16
+    distance (~1e-3 .. 1e-4) from the exact product -- while passes=3 stays fp32-grade."""
+    ops = _ops()
+    x, w, b = _rand(n, H, H, Cin, seed=1), _rand(Cout, 3, 3, Cin, seed=2, scale=(9 * Cin) ** -0.5), _rand(Cout, seed=3)
+    xs, ws = ops.split(x.to(DEV)), ops.split(w.to(DEV))
+    exact = F.conv2d(x.permute(0, 3, 1, 2).double(), w.permute(0, 3, 1, 2).double(), b.double(), padding=1).permute(0, 2, 3, 1)
+    rounded = F.conv2d(x.half().double().permute(0, 3, 1, 2), w.half().double().permute(0, 3, 1, 2), b.double(), padding=1).permute(0, 2, 3, 1)
+    o3, _, _ = ops.conv2d_tc(xs, ws, b.to(DEV), pad=(1, 1))
+    o1, _, _ = ops.conv2d_tc(xs, ws, b.to(DEV), pad=(1, 1), passes=1)
+    torch.cuda.synchronize()
+    _close(o3, exact)
+    if "nohalo" in tile_cfg:
+        _close(o1, exact)            # outside the halo kernel the request falls back to the fp32-grade product
+        return
+    _close(o1, rounded)
+    err = (o1.cpu().double() - exact).abs().max().item() / exact.abs().max().item()
+    assert 2e-5 < err < 3e-3, err
