@@ -8,8 +8,10 @@
  * of the reference would add.
  *
  * Conventions
+ *   - the first argument of every call is the opaque handle made by mage_ctx_create (one per GPU / process); the library has
+ *     no other mutable state;
  *   - every pointer is a DEVICE pointer owned by the caller (PyTorch allocator); nothing is
- *     allocated, freed or cached by the library, so it is re-entrant;
+ *     allocated, freed or cached by the library, so it is re-entrant per handle;
  *   - activations are channels-last fp32 (`[rows, C]`, images `[N,H,W,C]`); token / code
  *     indices are int64 (what the reference's `torch.max`/`torch.min` return);
  *   - kernels are enqueued on `stream` (a cudaStream_t passed as void*) and return at once;
@@ -40,20 +42,31 @@ extern "C" {
 #define MAGE_ACT_POST_RES 0x100 /* apply the activation after the residual add: act(x + bias + residual) */
 #define MAGE_RES_RELU 0x200     /* read the residual through a ReLU (in-place ReLU skip of ResBlock, vqvae_model.py:114-124) */
 
-/* Library info / bookkeeping */
-int mage_abi_version(void); /* 4 */
-/* Number of kernels launched through this library by the calling process so far. */
-int64_t mage_launch_count(void);
+/* Library info */
+int mage_abi_version(void); /* 5 */
+
+/* The opaque handle.  Everything the library remembers between calls lives in it: the device it was
+ * created for, that device's SM count and per-kernel launch configuration (opt-in shared-memory size, number of co-resident
+ * CTA pairs), the tile-selection / launch switches below, the launch counter.  There is no other mutable state, so the library
+ * is re-entrant per handle: one handle per (process, GPU) -- or per thread -- and two handles never see each other.  Every entry
+ * point takes the handle first; the caller keeps that device current (cudaSetDevice) and passes its own stream.
+ * mage_ctx_create fails with MAGE_ENOTSUP on anything but an sm_100 device (no other code path exists). */
+typedef struct mage_ctx mage_ctx;
+int mage_ctx_create(int device, mage_ctx** out);
+int mage_ctx_destroy(mage_ctx* ctx);
+int mage_ctx_device(mage_ctx* ctx);
+/* Number of kernels launched through this handle so far. */
+int64_t mage_launch_count(mage_ctx* ctx);
 
 /* enable != 0: the kernels of the per-step path are launched with the programmatic-stream-serialization attribute (they call
  * griddepcontrol.launch_dependents / .wait themselves).  Default off (MAGE_PDL=1 turns it on): measured neutral on B200. */
-int mage_pdl(int enable);
+int mage_pdl(mage_ctx* ctx, int enable);
 
 /* C[M,N] = act(relu_a?(A)[M,K] . W[N,K]^T + bias[N]) + residual
  * residual row for output row m is (res_mod > 0 ? m % res_mod : m), leading dim ldr; may alias C.
  * Replaces nn.Linear / MHA in-proj / out-proj / MLP (mage_model.py:20-26,33,50-51,375-376,385),
  * and 1x1 convolutions on NHWC data (vqvae_model.py:131,142,150,153).  K % 4 == 0, lda/ldw % 4 == 0. */
-int mage_gemm_f32(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
+int mage_gemm_f32(mage_ctx* ctx, const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
                   const float* residual, int64_t ldr, int res_mod, float* C, int64_t ldc,
                   int M, int N, int K, int act, int relu_a, void* stream);
 
@@ -69,7 +82,7 @@ int mage_gemm_f32(const float* A, int64_t lda, const float* W, int64_t ldw, cons
  *   (vqvae_model.py:184,187) into the full [Hfull,Wfull] output; out_img_stride is in elements.
  * Replaces nn.Conv2d / nn.ConvTranspose2d calls of vqvae_model.py:111-166,172-214 and
  * mage_model.py:485-488,304-305,504. */
-int mage_conv2d_nhwc_f32(const float* in, const float* w, const float* bias, const float* residual, float* out,
+int mage_conv2d_nhwc_f32(mage_ctx* ctx, const float* in, const float* w, const float* bias, const float* residual, float* out,
                          int n_img, int Hin, int Win, int Cin, int Hout, int Wout, int Cout,
                          int KH, int KW, int stride, int pad_y, int pad_x,
                          int in_up, int res_mode, int relu_in, int act,
@@ -86,40 +99,40 @@ int mage_conv2d_nhwc_f32(const float* in, const float* w, const float* bias, con
  * the fp16 range is split -- callers check it instead of trusting a saturated result.
  * --------------------------------------------------------------------------------------------- */
 
-/* Tuning / test hook for the tile selection of mage_gemm_tc / mage_conv2d_tc (process-wide, not thread-safe):
+/* Tuning / test hook for the tile selection of mage_gemm_tc / mage_conv2d_tc (per handle):
  * bn in {0 = automatic, 64, 128, 256} forces the N tile; pair in {-1 automatic, 0 single-CTA tiles only,
  * 1 CTA-pair (tcgen05 cta_group::2, 256-row tiles) whenever the row-tile count is even}.  Results do not depend on it
  * beyond fp32 summation order (identical here: the k order is the same for every tile shape). */
-int mage_tc_tuning(int bn, int pair);
+int mage_tc_tuning(mage_ctx* ctx, int bn, int pair);
 /* enable != 0 (default): KHxKW convolutions whose output is a multiple of 16x8 pixels run in halo mode (the input patch of a
  * tile is fetched once per 64-channel block and shared by all taps through shifted shared-memory descriptors); 0: every tap
  * re-fetches its own box.  Same results either way (same k order). */
-int mage_tc_conv_halo(int enable);
+int mage_tc_conv_halo(mage_ctx* ctx, int enable);
 /* N-split 256-wide CTA-pair tiles of mage_gemm_tc (two 128-column halves with separate TMEM accumulators and barriers):
  * 0 never, 1 automatic (default), 2 whenever the shape allows (N % 256 == 0, even row-tile count). */
-int mage_tc_nsplit(int mode);
+int mage_tc_nsplit(mage_ctx* ctx, int mode);
 
 /* out(split)[r, :] = split(relu?(x[r, :])); x row stride ldx (elements), C % 4 == 0. */
-int mage_split_f32(const float* x, int64_t ldx, void* out, int64_t plane, int rows, int C, int relu, int* flag,
+int mage_split_f32(mage_ctx* ctx, const float* x, int64_t ldx, void* out, int64_t plane, int rows, int C, int relu, int* flag,
                    void* stream);
 
 /* First-layer im2row for the tensor cores: in planar [n,C,H,W] fp32 -> out split [n,H,W,64] with
  *   out[n,y,x, kx*C + c] = in[n,c,y, x+kx-pad]   (zero outside the image; channels >= KW*C are zero),  C*KW <= 64.
  * A KHxKW convolution of the image (vqvae_model.py:193, 7x7 pad 3) is then mage_conv2d_tc with a KHx1 kernel over these 64
  * channels and weights w2[co, ky, 0, kx*C + c] = w[co, c, ky, kx]. */
-int mage_patch_rows_split_f32(const float* in, void* out, int64_t plane, int n_img, int C, int H, int W, int KW, int pad,
+int mage_patch_rows_split_f32(mage_ctx* ctx, const float* in, void* out, int64_t plane, int n_img, int C, int H, int W, int KW, int pad,
                               void* stream);
 
 /* Space-to-depth with a one-pixel top/left pad, in the split format: in fp32 NHWC [n,H,W,C] (H, W even, C % 8 == 0) -> out split
  * [n, H/2+1, W/2+1, 4C] with out[n, Y, X, (py*2+px)*C + c] = relu?(in[n, 2Y+py-1, 2X+px-1, c]) (zero outside the image).
  * A 4x4 stride-2 pad-1 convolution (vqvae_model.py:175) over `in` is then the 2x2 stride-1 VALID mage_conv2d_tc over `out`
  * with w2[co, ty, tx, (py*2+px)*C + c] = w[co, c, 2ty+py, 2tx+px]: same products, every weight used once. */
-int mage_s2d_pad_split_f32(const float* in, void* out, int64_t plane, int n_img, int H, int W, int C, int relu, int* flag,
+int mage_s2d_pad_split_f32(mage_ctx* ctx, const float* in, void* out, int64_t plane, int n_img, int H, int W, int C, int relu, int* flag,
                            void* stream);
 
 /* out(split)[r, :] = table(split)[idx[r], :]   (nn.Embedding on a pre-split table: mage_model.py:644,682;
  * vqvae_model.py:240).  C % 8 == 0. */
-int mage_embedding_split(const int64_t* idx, const void* table, int64_t table_plane, void* out, int64_t out_plane,
+int mage_embedding_split(mage_ctx* ctx, const int64_t* idx, const void* table, int64_t table_plane, void* out, int64_t out_plane,
                          int rows, int C, void* stream);
 
 /* C[M,N] = act(A[M,K] . W[N,K]^T + bias[N]) (+ residual), A and W split tensors (row strides lda/ldw in
@@ -127,7 +140,7 @@ int mage_embedding_split(const int64_t* idx, const void* table, int64_t table_pl
  * may be NULL: C fp32 [M,N] (ldc), C_split = split(result), C_split_relu = split(relu(result)) -- the
  * operand format of the next tensor-core op -- all with row stride ldc and plane stride c_plane.
  * act / residual semantics as mage_gemm_f32.  Same reference call sites as mage_gemm_f32. */
-int mage_gemm_tc(const void* A, int64_t lda, int64_t a_plane, const void* W, int64_t ldw, int64_t w_plane,
+int mage_gemm_tc(mage_ctx* ctx, const void* A, int64_t lda, int64_t a_plane, const void* W, int64_t ldw, int64_t w_plane,
                  const float* bias, const float* residual, int64_t ldr, int res_mod, float* C, void* C_split,
                  void* C_split_relu, int64_t ldc, int64_t c_plane, int M, int N, int K, int act, int* flag,
                  void* stream);
@@ -142,7 +155,7 @@ int mage_gemm_tc(const void* A, int64_t lda, int64_t a_plane, const void* W, int
  * hi planes are fetched) -- allowed ONLY where the result feeds no token: the last block of the VQ-VAE decoder, whose pixel
  * error stays inside the 1e-3 bar (tests/test_gpu_parity.py::test_decoder_precision_budget).  A shape the single-pass kernel
  * does not cover silently runs with 3 passes. */
-int mage_conv2d_tc(const void* in, int64_t in_plane, const void* w, int64_t w_plane, const float* bias,
+int mage_conv2d_tc(mage_ctx* ctx, const void* in, int64_t in_plane, const void* w, int64_t w_plane, const float* bias,
                    const float* residual, float* out, void* out_split, void* out_split_relu, int64_t out_plane,
                    int n_img, int Hin, int Win, int Cin, int Hout, int Wout, int Cout, int KH, int KW, int pad_y,
                    int pad_x, int res_mode, int act, int out_sy, int out_sx, int out_oy, int out_ox, int Hfull,
@@ -152,7 +165,7 @@ int mage_conv2d_tc(const void* in, int64_t in_plane, const void* w, int64_t w_pl
  * Tanh): the conv result x[row, 0..255] (+ bias + residual, never written to memory) is reduced in the epilogue to
  *   head_out[img, c, y, x] = tanh(head_b[c] + sum_n relu(x[row, n]) * head_w[c, n]),   c < head_cout <= 3,
  * planar output, image stride head_img_stride elements.  Cout must be 256 (one N tile holds a whole row). */
-int mage_conv2d_tc_pixel_head(const void* in, int64_t in_plane, const void* w, int64_t w_plane, const float* bias,
+int mage_conv2d_tc_pixel_head(mage_ctx* ctx, const void* in, int64_t in_plane, const void* w, int64_t w_plane, const float* bias,
                               const float* residual, int n_img, int Hin, int Win, int Cin, int Hout, int Wout, int Cout,
                               int KH, int KW, int pad_y, int pad_x, int res_mode, const float* head_w, const float* head_b,
                               int head_cout, float* head_out, int64_t head_img_stride, int passes, int* flag, void* stream);
@@ -160,22 +173,22 @@ int mage_conv2d_tc_pixel_head(const void* in, int64_t in_plane, const void* w, i
 /* First-layer convolution from a planar NCHW image with a tiny channel count (Cin <= 4):
  * in [N,Cin,H,W], w_t [Cin*KH*KW][Cout] (transposed), out NHWC [N,Hout,Wout,Cout], optional ReLU.
  * Replaces vqvae_model.py:172-173 (4x4 s2, BN folded by the caller) and :193 (7x7 pad 3). */
-int mage_conv2d_first_f32(const float* in, const float* w_t, const float* bias, float* out,
+int mage_conv2d_first_f32(mage_ctx* ctx, const float* in, const float* w_t, const float* bias, float* out,
                           int n_img, int Cin, int H, int W, int Hout, int Wout, int Cout,
                           int KH, int KW, int stride, int pad, int act, void* stream);
 
 /* Last f8 decoder layer: out[n,c,y,x] = tanh(sum_k relu(in[n,y,x,k]) * w[c,k] + bias[c]), planar
  * output with image stride out_img_stride elements (vqvae_model.py:211-213). Cin % 128 == 0, Cout <= 4. */
-int mage_conv1x1_tanh_nchw_f32(const float* in, const float* w, const float* bias, float* out,
+int mage_conv1x1_tanh_nchw_f32(mage_ctx* ctx, const float* in, const float* w, const float* bias, float* out,
                                int n_img, int HW, int Cin, int Cout, int64_t out_img_stride, void* stream);
 
 /* 2x2 max pooling, NHWC (vqvae_model.py:195,197,199). */
-int mage_maxpool2x2_nhwc_f32(const float* in, float* out, int n_img, int Hin, int Win, int C, void* stream);
+int mage_maxpool2x2_nhwc_f32(mage_ctx* ctx, const float* in, float* out, int n_img, int Hin, int Win, int C, void* stream);
 
 /* Row LayerNorm over the last dim C (C % 128 == 0, C <= 1024); in may alias out.  out (fp32) and/or
  * out_split (split copy for a following tensor-core GEMM, plane stride split_plane) may be NULL.
  * Replaces nn.LayerNorm (mage_model.py:21,27,84,204,206). */
-int mage_layernorm_f32(const float* in, const float* gamma, const float* beta, float* out, void* out_split,
+int mage_layernorm_f32(mage_ctx* ctx, const float* in, const float* gamma, const float* beta, float* out, void* out_split,
                        int64_t split_plane, int* flag, int rows, int C, float eps, void* stream);
 
 /* Multi-head attention core, head_dim 32: for every (outer, inner, head, query)
@@ -184,7 +197,7 @@ int mage_layernorm_f32(const float* in, const float* gamma, const float* beta, f
  * Covers the SDPA inside every nn.MultiheadAttention on the path (mage_model.py:33,89,193-199):
  * temporal attention over the K/V cache, H-/W-axial attention, text self-attention (key padding),
  * motion-anchor cross-attention.  out (fp32) and/or out_split (split copy, same element offsets) may be NULL. */
-int mage_mha_f32(const float* q, const float* k, const float* v, float* out,
+int mage_mha_f32(mage_ctx* ctx, const float* q, const float* k, const float* v, float* out,
                  int n_outer, int n_inner, int n_head, int Sq, int Sk,
                  int64_t q_outer, int64_t q_inner, int64_t q_seq,
                  int64_t k_outer, int64_t k_inner, int64_t k_seq,
@@ -196,56 +209,56 @@ int mage_mha_f32(const float* q, const float* k, const float* v, float* out,
  * mage_model.py:35-53,340-345): qkv [B*R*R, 3C] rows ordered (b,h,w), R = 16, head_dim 32, C = 32*n_head.
  * axis 1 attends along h (fixed b,w), axis 2 along w (fixed b,h).  One warp per (line, head), tiles staged
  * once in shared memory; out fp32 [B*R*R, C] and/or out_split may be NULL. */
-int mage_axial_attn_f32(const float* qkv, float* out, void* out_split, int64_t split_plane, int* flag, int B, int R,
+int mage_axial_attn_f32(mage_ctx* ctx, const float* qkv, float* out, void* out_split, int64_t split_plane, int* flag, int B, int R,
                         int n_head, int axis, float scale, void* stream);
 
 /* Temporal attention for one decode step with a TMA-staged K/V cache (bulk async copies into
  * shared memory).  qkv [M, 3C] holds this position's q|k|v; k,v are appended to the caches at `pos` and q attends
  * positions 0..pos.  out [M, C].  C = 512, 16 heads x 32.  The caches belong to this entry point and are laid out
  * [M][2 head-halves][Lmax][256] (each CTA's live prefix is one contiguous block = one bulk copy); they hold M*Lmax*C floats. */
-int mage_temporal_attn_step_f32(const float* qkv, float* kcache, float* vcache, float* out, void* out_split,
+int mage_temporal_attn_step_f32(mage_ctx* ctx, const float* qkv, float* kcache, float* vcache, float* out, void* out_split,
                                 int64_t split_plane, int* flag, int M, int pos, int Lmax, float scale, void* stream);
 
 /* Append this step's K and V (columns C..3C of qkv [M,3C]) at position `pos` of caches [M,Lmax,C]. */
-int mage_kv_append_f32(const float* qkv, float* kcache, float* vcache, int M, int C, int pos, int Lmax, void* stream);
+int mage_kv_append_f32(mage_ctx* ctx, const float* qkv, float* kcache, float* vcache, int M, int C, int pos, int Lmax, void* stream);
 
 /* L2 nearest-code search of the VectorQuantizer (vqvae_model.py:8-25):
  *   idx[n] = argmin_k ( (|c_k|^2 + |z_n|^2) - 2 z_n.c_k ),   z [N,D], codebook [K,D], D % 16 == 0, K % 128 == 0.
  * csq_scratch: K floats of scratch.  Ties resolve to the lowest index. */
-int mage_vq_argmin_f32(const float* z, const float* codebook, float* csq_scratch, int64_t* idx,
+int mage_vq_argmin_f32(mage_ctx* ctx, const float* z, const float* codebook, float* csq_scratch, int64_t* idx,
                        int N, int D, int K, void* stream);
 
 /* idx[r] = argmax_n x[r, n] (lowest index on ties); greedy decode, mage_model.py:681,687. */
-int mage_argmax_rows_f32(const float* x, int64_t ldx, int64_t* idx, int rows, int N, void* stream);
+int mage_argmax_rows_f32(mage_ctx* ctx, const float* x, int64_t ldx, int64_t* idx, int rows, int N, void* stream);
 
 /* out[r, :] = table[idx[r], :]  (nn.Embedding: mage_model.py:644,682; vqvae_model.py:240). C % 4 == 0. */
-int mage_embedding_f32(const int64_t* idx, const float* table, float* out, int rows, int C, void* stream);
+int mage_embedding_f32(mage_ctx* ctx, const int64_t* idx, const float* table, float* out, int rows, int C, void* stream);
 
 /* Convolution of a codebook-embedded token map followed by a linear layer, as table lookups.  Because the conv input is one of K
  * embedding rows per pixel, in_linear(conv3x3(E[tok]) + pos) (mage_model.py:674-676,375) is exactly
  *   out[b,y,x,:] = sum_{ky,kx} table[ky*KW+kx][tok[b, y+ky-KH/2, x+kx-KW/2]][:] + pos_bias[y*R+x][:] + bias[:]
  * with table[tap][code] = W_in . Wc[:, :, tap] . E[code] precomputed at load ([KH*KW, K, C] fp32), pos_bias = W_in . pos.
  * tok int64 [n_img, R, R]; zero padding outside the map; C = 512; out fp32 [n_img*R*R, C]. */
-int mage_token_taps_f32(const int64_t* tok, const float* table, const float* pos_bias, const float* bias, float* out,
+int mage_token_taps_f32(mage_ctx* ctx, const int64_t* tok, const float* table, const float* pos_bias, const float* bias, float* out,
                         int n_img, int R, int K, int C, int KH, int KW, void* stream);
 
 /* Text-encoder front end (mage_model.py:224-237): x[b,t,:] = LN_eps(tok_emb[text[b,t]] + pos_emb[t]) * (text[b,t] != pad);
  * key_len[b] = #non-pad tokens.  C = 512.  tok_emb has `vocab` rows: an id outside [0, vocab) -- on which the reference's
  * nn.Embedding raises (mage_model.py:228) -- is never dereferenced; bit 1 of *flag is set instead (the host raises after the call). */
-int mage_text_embed_f32(const int64_t* text, const float* tok_emb, const float* pos_emb,
+int mage_text_embed_f32(mage_ctx* ctx, const int64_t* text, const float* tok_emb, const float* pos_emb,
                         const float* gamma, const float* beta, float* x, int32_t* key_len,
                         int B, int T, int C, int pad_idx, float eps, int vocab, int* flag, void* stream);
 
 /* AdaIN (mage_model.py:309-314): out = gamma * InstanceNorm(x) + beta over the HW positions of each
  * (image, channel); x/gamma/beta/out NHWC [N,HW,C]; out may alias x. */
-int mage_adain_nhwc_f32(const float* x, const float* gamma, const float* beta, float* out,
+int mage_adain_nhwc_f32(mage_ctx* ctx, const float* x, const float* gamma, const float* beta, float* out,
                         int n_img, int HW, int C, float eps, void* stream);
 
 /* x[n, p, :] += s[n] * vec[:]  (speed embedding, mage_model.py:666-668). */
-int mage_add_scaled_vec_f32(float* x, const float* s, const float* vec, int n_img, int HW, int C, void* stream);
+int mage_add_scaled_vec_f32(mage_ctx* ctx, float* x, const float* s, const float* vec, int n_img, int HW, int C, void* stream);
 
 /* out[n,h,w,c] = in[n,c,h,w]  (noise [B,64,16,16] -> NHWC). */
-int mage_nchw_to_nhwc_f32(const float* in, float* out, int n_img, int C, int HW, void* stream);
+int mage_nchw_to_nhwc_f32(mage_ctx* ctx, const float* in, float* out, int n_img, int C, int HW, void* stream);
 
 /* MAGE+ continuous head (use_cids=False), mage_model.py:349-354 + :386-388: GroupNorm(groups) over (C/groups channels x all
  * temporal slots x H x W) of a sample -> SiLU -> 1x1x1 Conv3d to `cout` latent channels.
@@ -253,8 +266,8 @@ int mage_nchw_to_nhwc_f32(const float* in, float* out, int n_img, int C, int HW,
  *   (slot, sample, group); a slot is re-reduced only when its hidden state changes.
  * mage_gn_silu_head_f32: rows of x [rows = k*B*HW, C] (row -> sample (row / HW) % B), statistics combined over the n_slots
  *   slots of `part`; out fp32 [rows, cout] = bias + w[cout, C] . silu(GN(x)).  C = 512, groups = 32, cout <= 8. */
-int mage_gn_partial_f32(const float* x, double* part, int n_slots, int B, int HW, int C, int groups, void* stream);
-int mage_gn_silu_head_f32(const float* x, const double* part, const float* gamma, const float* beta, const float* w,
+int mage_gn_partial_f32(mage_ctx* ctx, const float* x, double* part, int n_slots, int B, int HW, int C, int groups, void* stream);
+int mage_gn_silu_head_f32(mage_ctx* ctx, const float* x, const double* part, const float* gamma, const float* beta, const float* w,
                           const float* bias, float* out, int rows, int B, int HW, int n_slots, int C, int groups, int cout,
                           float eps, void* stream);
 

@@ -12,7 +12,7 @@ import subprocess
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB_PATH = os.environ.get("MAGE_LIB") or os.path.join(CSRC, "libmage_sm100.so")   # MAGE_LIB: experiment builds (tools/experiments)
 
-ABI_VERSION = 4   # include/mage_b200.h: mage_abi_version()
+ABI_VERSION = 5   # include/mage_b200.h: mage_abi_version()
 
 _c_f = ctypes.c_void_p  # device pointers travel as integers
 _i = ctypes.c_int
@@ -22,39 +22,42 @@ _f32 = ctypes.c_float
 # name -> argtypes (restype is int for all but the two bookkeeping calls)
 SIGNATURES = {
     "mage_abi_version": [],
-    "mage_launch_count": [],
-    "mage_pdl": [_i],
-    "mage_gemm_f32": [_c_f, _i64, _c_f, _i64, _c_f, _c_f, _i64, _i, _c_f, _i64, _i, _i, _i, _i, _i, _c_f],
-    "mage_conv2d_nhwc_f32": [_c_f] * 5 + [_i] * 22 + [_i64, _c_f],
-    "mage_tc_tuning": [_i, _i],
-    "mage_tc_conv_halo": [_i],
-    "mage_tc_nsplit": [_i],
-    "mage_split_f32": [_c_f, _i64, _c_f, _i64, _i, _i, _i, _c_f, _c_f],
-    "mage_patch_rows_split_f32": [_c_f, _c_f, _i64, _i, _i, _i, _i, _i, _i, _c_f],
-    "mage_s2d_pad_split_f32": [_c_f, _c_f, _i64, _i, _i, _i, _i, _i, _c_f, _c_f],
-    "mage_embedding_split": [_c_f, _c_f, _i64, _c_f, _i64, _i, _i, _c_f],
-    "mage_gemm_tc": [_c_f, _i64, _i64, _c_f, _i64, _i64, _c_f, _c_f, _i64, _i, _c_f, _c_f, _c_f, _i64, _i64, _i, _i, _i, _i,
+    "mage_ctx_create": [_i, ctypes.POINTER(ctypes.c_void_p)],   # no ctx argument (special-cased below)
+    "mage_ctx_destroy": [_c_f],
+    "mage_ctx_device": [_c_f],
+    "mage_launch_count": [_c_f],
+    "mage_pdl": [_c_f] + [_i],
+    "mage_gemm_f32": [_c_f, _c_f, _i64, _c_f, _i64, _c_f, _c_f, _i64, _i, _c_f, _i64, _i, _i, _i, _i, _i, _c_f],
+    "mage_conv2d_nhwc_f32": [_c_f] + [_c_f] * 5 + [_i] * 22 + [_i64, _c_f],
+    "mage_tc_tuning": [_c_f] + [_i, _i],
+    "mage_tc_conv_halo": [_c_f] + [_i],
+    "mage_tc_nsplit": [_c_f] + [_i],
+    "mage_split_f32": [_c_f, _c_f, _i64, _c_f, _i64, _i, _i, _i, _c_f, _c_f],
+    "mage_patch_rows_split_f32": [_c_f, _c_f, _c_f, _i64, _i, _i, _i, _i, _i, _i, _c_f],
+    "mage_s2d_pad_split_f32": [_c_f, _c_f, _c_f, _i64, _i, _i, _i, _i, _i, _c_f, _c_f],
+    "mage_embedding_split": [_c_f, _c_f, _c_f, _i64, _c_f, _i64, _i, _i, _c_f],
+    "mage_gemm_tc": [_c_f, _c_f, _i64, _i64, _c_f, _i64, _i64, _c_f, _c_f, _i64, _i, _c_f, _c_f, _c_f, _i64, _i64, _i, _i, _i, _i,
                      _c_f, _c_f],
-    "mage_conv2d_tc": [_c_f, _i64, _c_f, _i64, _c_f, _c_f, _c_f, _c_f, _c_f, _i64] + [_i] * 19 + [_i64, _i, _c_f, _c_f],
-    "mage_conv2d_tc_pixel_head": [_c_f, _i64, _c_f, _i64, _c_f, _c_f] + [_i] * 12 + [_c_f, _c_f, _i, _c_f, _i64, _i, _c_f, _c_f],
-    "mage_conv2d_first_f32": [_c_f] * 4 + [_i] * 12 + [_c_f],
-    "mage_conv1x1_tanh_nchw_f32": [_c_f] * 4 + [_i] * 4 + [_i64, _c_f],
-    "mage_maxpool2x2_nhwc_f32": [_c_f, _c_f, _i, _i, _i, _i, _c_f],
-    "mage_layernorm_f32": [_c_f] * 5 + [_i64, _c_f, _i, _i, _f32, _c_f],
-    "mage_mha_f32": [_c_f] * 4 + [_i] * 5 + [_i64] * 12 + [_c_f, _f32, _c_f, _i64, _c_f, _c_f],
-    "mage_axial_attn_f32": [_c_f, _c_f, _c_f, _i64, _c_f, _i, _i, _i, _i, _f32, _c_f],
-    "mage_temporal_attn_step_f32": [_c_f] * 5 + [_i64, _c_f, _i, _i, _i, _f32, _c_f],
-    "mage_kv_append_f32": [_c_f] * 3 + [_i] * 4 + [_c_f],
-    "mage_vq_argmin_f32": [_c_f] * 4 + [_i] * 3 + [_c_f],
-    "mage_argmax_rows_f32": [_c_f, _i64, _c_f, _i, _i, _c_f],
-    "mage_embedding_f32": [_c_f] * 3 + [_i, _i, _c_f],
-    "mage_token_taps_f32": [_c_f] * 5 + [_i] * 6 + [_c_f],
-    "mage_text_embed_f32": [_c_f] * 7 + [_i] * 4 + [_f32, _i, _c_f, _c_f],
-    "mage_adain_nhwc_f32": [_c_f] * 4 + [_i] * 3 + [_f32, _c_f],
-    "mage_add_scaled_vec_f32": [_c_f] * 3 + [_i] * 3 + [_c_f],
-    "mage_nchw_to_nhwc_f32": [_c_f, _c_f, _i, _i, _i, _c_f],
-    "mage_gn_partial_f32": [_c_f, _c_f, _i, _i, _i, _i, _i, _c_f],
-    "mage_gn_silu_head_f32": [_c_f] * 7 + [_i] * 7 + [_f32, _c_f],
+    "mage_conv2d_tc": [_c_f, _c_f, _i64, _c_f, _i64, _c_f, _c_f, _c_f, _c_f, _c_f, _i64] + [_i] * 19 + [_i64, _i, _c_f, _c_f],
+    "mage_conv2d_tc_pixel_head": [_c_f, _c_f, _i64, _c_f, _i64, _c_f, _c_f] + [_i] * 12 + [_c_f, _c_f, _i, _c_f, _i64, _i, _c_f, _c_f],
+    "mage_conv2d_first_f32": [_c_f] + [_c_f] * 4 + [_i] * 12 + [_c_f],
+    "mage_conv1x1_tanh_nchw_f32": [_c_f] + [_c_f] * 4 + [_i] * 4 + [_i64, _c_f],
+    "mage_maxpool2x2_nhwc_f32": [_c_f, _c_f, _c_f, _i, _i, _i, _i, _c_f],
+    "mage_layernorm_f32": [_c_f] + [_c_f] * 5 + [_i64, _c_f, _i, _i, _f32, _c_f],
+    "mage_mha_f32": [_c_f] + [_c_f] * 4 + [_i] * 5 + [_i64] * 12 + [_c_f, _f32, _c_f, _i64, _c_f, _c_f],
+    "mage_axial_attn_f32": [_c_f, _c_f, _c_f, _c_f, _i64, _c_f, _i, _i, _i, _i, _f32, _c_f],
+    "mage_temporal_attn_step_f32": [_c_f] + [_c_f] * 5 + [_i64, _c_f, _i, _i, _i, _f32, _c_f],
+    "mage_kv_append_f32": [_c_f] + [_c_f] * 3 + [_i] * 4 + [_c_f],
+    "mage_vq_argmin_f32": [_c_f] + [_c_f] * 4 + [_i] * 3 + [_c_f],
+    "mage_argmax_rows_f32": [_c_f, _c_f, _i64, _c_f, _i, _i, _c_f],
+    "mage_embedding_f32": [_c_f] + [_c_f] * 3 + [_i, _i, _c_f],
+    "mage_token_taps_f32": [_c_f] + [_c_f] * 5 + [_i] * 6 + [_c_f],
+    "mage_text_embed_f32": [_c_f] + [_c_f] * 7 + [_i] * 4 + [_f32, _i, _c_f, _c_f],
+    "mage_adain_nhwc_f32": [_c_f] + [_c_f] * 4 + [_i] * 3 + [_f32, _c_f],
+    "mage_add_scaled_vec_f32": [_c_f] + [_c_f] * 3 + [_i] * 3 + [_c_f],
+    "mage_nchw_to_nhwc_f32": [_c_f, _c_f, _c_f, _i, _i, _i, _c_f],
+    "mage_gn_partial_f32": [_c_f, _c_f, _c_f, _i, _i, _i, _i, _i, _c_f],
+    "mage_gn_silu_head_f32": [_c_f] + [_c_f] * 7 + [_i] * 7 + [_f32, _c_f],
 }
 
 
@@ -90,6 +93,20 @@ def lib() -> ctypes.CDLL:
 
 class MageCudaError(RuntimeError):
     pass
+
+
+_ctx = {}
+
+
+def ctx(device_index: int) -> int:
+    """The library handle (`mage_ctx*`, include/mage_b200.h) of a CUDA device: created on first use, one per (process, device).
+    All state the library keeps between calls -- per-device kernel configuration, tuning switches, launch counter -- lives in it."""
+    h = _ctx.get(device_index)
+    if h is None:
+        out = ctypes.c_void_p()
+        check(lib().mage_ctx_create(int(device_index), ctypes.byref(out)), f"mage_ctx_create(device {device_index})")
+        h = _ctx[device_index] = out.value
+    return h
 
 
 def check(code: int, what: str) -> None:

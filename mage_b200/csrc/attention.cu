@@ -324,11 +324,12 @@ __global__ void __launch_bounds__(256) temporal_attn_kernel(const float* __restr
 
 }  // namespace
 
-extern "C" int mage_mha_f32(const float* q, const float* k, const float* v, float* out, int n_outer, int n_inner, int n_head,
+extern "C" int mage_mha_f32(mage_ctx* ctx, const float* q, const float* k, const float* v, float* out, int n_outer, int n_inner, int n_head,
                             int Sq, int Sk, int64_t q_outer, int64_t q_inner, int64_t q_seq, int64_t k_outer, int64_t k_inner,
                             int64_t k_seq, int64_t v_outer, int64_t v_inner, int64_t v_seq, int64_t o_outer, int64_t o_inner,
                             int64_t o_seq, const int32_t* key_len, float scale, void* out_split, int64_t split_plane,
                             int* flag, void* stream) {
+  MAGE_CHECK_CTX(ctx);
   MAGE_CHECK_ARG(n_outer > 0 && n_inner > 0 && n_head > 0 && Sq > 0 && Sk > 0 && Sk <= 64);
   MAGE_CHECK_ARG(aligned16(q) && aligned16(k) && aligned16(v) && (out || out_split));
   MAGE_CHECK_ARG(((q_outer | q_inner | q_seq | k_outer | k_inner | k_seq) & 3) == 0);
@@ -339,11 +340,12 @@ extern "C" int mage_mha_f32(const float* q, const float* k, const float* v, floa
   const int64_t blocks = (a.total + 7) / 8;
   MAGE_CHECK_ARG(blocks < ((int64_t)1 << 31));
   mha_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(a);
-  return mage_post_launch();
+  return mage_post_launch(ctx);
 }
 
-extern "C" int mage_axial_attn_f32(const float* qkv, float* out, void* out_split, int64_t split_plane, int* flag, int B, int R,
+extern "C" int mage_axial_attn_f32(mage_ctx* ctx, const float* qkv, float* out, void* out_split, int64_t split_plane, int* flag, int B, int R,
                                    int n_head, int axis, float scale, void* stream) {
+  MAGE_CHECK_CTX(ctx);
   // qkv [B*R*R, 3C] rows ordered (b, h, w); axis 1: sequences run over h for fixed (b, w); axis 2: over w for fixed (b, h)
   MAGE_CHECK_ARG(B > 0 && R == AX_S && n_head > 0 && (axis == 1 || axis == 2) && (out || out_split));
   MAGE_CHECK_ARG(aligned16(qkv) && aligned16(out) && aligned16(out_split) && split_plane % 4 == 0);
@@ -354,24 +356,29 @@ extern "C" int mage_axial_attn_f32(const float* qkv, float* out, void* out_split
   a.line_inner = axis == 1 ? 1 : R;
   a.seq = axis == 1 ? R : 1;
   const int64_t units = (int64_t)a.n_lines * n_head;
-  mage_launch_pdl(axial_attn_kernel, (unsigned)((units + AX_WARPS - 1) / AX_WARPS), AX_WARPS * 32, 0, as_stream(stream), 1, a);
-  return mage_post_launch();
+  mage_launch_pdl(ctx, axial_attn_kernel, (unsigned)((units + AX_WARPS - 1) / AX_WARPS), AX_WARPS * 32, 0, as_stream(stream), 1, a);
+  return mage_post_launch(ctx);
 }
 
-extern "C" int mage_temporal_attn_step_f32(const float* qkv, float* kcache, float* vcache, float* out, void* out_split,
+extern "C" int mage_temporal_attn_step_f32(mage_ctx* ctx, const float* qkv, float* kcache, float* vcache, float* out, void* out_split,
                                            int64_t split_plane, int* flag, int M, int pos, int Lmax, float scale,
                                            void* stream) {
+  MAGE_CHECK_CTX(ctx);
   MAGE_CHECK_ARG(M > 0 && pos >= 0 && pos < Lmax && Lmax <= 64);
   MAGE_CHECK_ARG(aligned16(qkv) && aligned16(kcache) && aligned16(vcache) && aligned16(out) && (out || out_split));
   const size_t smem = (size_t)2 * (pos + 1) * TA_HALF * sizeof(float);
   const size_t smem_max = (size_t)2 * Lmax * TA_HALF * sizeof(float);
-  static size_t configured = 0;
-  if (smem_max > 48 * 1024 && smem_max > configured) {
-    cudaError_t e = cudaFuncSetAttribute(temporal_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
-    if (e != cudaSuccess) return (int)e;
-    configured = smem_max;
+  if (smem_max > 48 * 1024) {   // the opt-in shared-memory size is a per-device attribute: remembered in the handle, not in a static
+    const void* fn = reinterpret_cast<const void*>(&temporal_attn_kernel);
+    int k = ctx->find(fn);
+    if (k < 0 || ctx->cfg_smem[k] < smem_max) {
+      cudaError_t e = cudaFuncSetAttribute(temporal_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+      if (e != cudaSuccess) return (int)e;
+      if (k < 0) k = ctx->add(fn, 0, smem_max);
+      if (k >= 0) ctx->cfg_smem[k] = smem_max;
+    }
   }
-  mage_launch_pdl(temporal_attn_kernel, (unsigned)M * 2, 256, smem, as_stream(stream), 1, qkv, kcache, vcache, out,
+  mage_launch_pdl(ctx, temporal_attn_kernel, (unsigned)M * 2, 256, smem, as_stream(stream), 1, qkv, kcache, vcache, out,
                   reinterpret_cast<__half*>(out_split), split_plane, flag, pos, Lmax, scale);
-  return mage_post_launch();
+  return mage_post_launch(ctx);
 }

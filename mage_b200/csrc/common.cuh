@@ -5,16 +5,49 @@
 
 #include "../../include/mage_b200.h"
 
-extern int64_t g_mage_launches;  // defined in misc.cu
+// The opaque handle of the C ABI (include/mage_b200.h: mage_ctx_create / mage_ctx_destroy): everything the library remembers
+// between calls lives here -- the device it was created for, that device's SM count and per-kernel launch configuration
+// (opt-in shared-memory size, co-resident CTA-pair count), the tile-selection / launch tuning switches, the launch counter.
+// No process-global mutable state: two handles (two devices, two threads) never see each other.
+struct mage_ctx {
+  int device = 0;
+  int sms = 148;
+  int forced_bn = 0, forced_pair = -1;   // mage_tc_tuning
+  int ns = 1;                            // mage_tc_nsplit
+  int halo = 1;                          // mage_tc_conv_halo
+  int small = 1;                         // one-tile cost model for sub-2-wave GEMMs (MAGE_TC_SMALL)
+  int resident = 1;                      // resident weight slots in the halo convolution when they fit (MAGE_TC_RESIDENT)
+  int pdl = 0;                           // mage_pdl
+  int64_t launches = 0;
+  static constexpr int kMaxKernels = 64;
+  const void* cfg_fn[kMaxKernels] = {};  // kernels whose attributes have been set on `device`
+  int cfg_units[kMaxKernels] = {};       // ... and how many CTAs / CTA pairs of each can be co-resident
+  size_t cfg_smem[kMaxKernels] = {};
+  int n_cfg = 0;
+  int find(const void* fn) const {
+    for (int i = 0; i < n_cfg; ++i)
+      if (cfg_fn[i] == fn) return i;
+    return -1;
+  }
+  int add(const void* fn, int units, size_t smem) {
+    if (n_cfg >= kMaxKernels) return -1;
+    cfg_fn[n_cfg] = fn; cfg_units[n_cfg] = units; cfg_smem[n_cfg] = smem;
+    return n_cfg++;
+  }
+};
 
 #define MAGE_CHECK_ARG(cond) \
   do {                       \
     if (!(cond)) return MAGE_EINVAL; \
   } while (0)
+#define MAGE_CHECK_CTX(ctx) \
+  do {                      \
+    if ((ctx) == nullptr) return MAGE_EINVAL; \
+  } while (0)
 
 // Count the launch and surface launch-time errors (never sync here: callers own the stream).
-static inline int mage_post_launch() {
-  ++g_mage_launches;
+static inline int mage_post_launch(mage_ctx* ctx) {
+  ++ctx->launches;
   cudaError_t e = cudaGetLastError();
   return (int)e;
 }
@@ -48,11 +81,9 @@ __device__ __forceinline__ float warp_max(float v) {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-extern int g_mage_pdl;  // defined in misc.cu
-
 template <typename... KArgs, typename... Args>
-static inline cudaError_t mage_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x,
-                                          Args&&... args) {
+static inline cudaError_t mage_launch_pdl(const mage_ctx* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                          int cluster_x, Args&&... args) {
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[2];
   int n = 0;
@@ -61,7 +92,7 @@ static inline cudaError_t mage_launch_pdl(void (*kernel)(KArgs...), dim3 grid, d
     attr[n].val.clusterDim.x = cluster_x; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
     ++n;
   }
-  if (g_mage_pdl) {
+  if (ctx->pdl) {
     attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[n].val.programmaticStreamSerializationAllowed = 1;
     ++n;

@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(256, 2) sgemm_kernel(const GemmArgs p) {
 }
 
 template <bool CONV>
-int launch(const GemmArgs& a, cudaStream_t st) {
+int launch(mage_ctx* ctx, const GemmArgs& a, cudaStream_t st) {
   const long t128 = (long)((a.M + 127) / 128) * ((a.N + 127) / 128);
   if (a.N <= 64 || (a.N % 128 != 0 && a.N % 128 <= 64 && a.N < 256)) {
     if ((long)((a.M + 127) / 128) * ((a.N + 63) / 64) >= 148) {
@@ -240,14 +240,15 @@ int launch(const GemmArgs& a, cudaStream_t st) {
     dim3 g((a.M + 63) / 64, (a.N + 63) / 64);
     sgemm_kernel<64, 64, 4, 4, CONV><<<g, 256, 0, st>>>(a);
   }
-  return mage_post_launch();
+  return mage_post_launch(ctx);
 }
 
 }  // namespace
 
-extern "C" int mage_gemm_f32(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
+extern "C" int mage_gemm_f32(mage_ctx* ctx, const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias,
                              const float* residual, int64_t ldr, int res_mod, float* C, int64_t ldc,
                              int M, int N, int K, int act, int relu_a, void* stream) {
+  MAGE_CHECK_CTX(ctx);
   cudaStream_t st = as_stream(stream);
   MAGE_CHECK_ARG(M > 0 && N > 0 && K > 0 && (K % 4) == 0 && (lda % 4) == 0 && (ldw % 4) == 0);
   MAGE_CHECK_ARG(aligned16(A) && aligned16(W));
@@ -257,14 +258,15 @@ extern "C" int mage_gemm_f32(const float* A, int64_t lda, const float* W, int64_
   a.res_mod = res_mod; a.act = act; a.relu_a = relu_a;
   a.vec_ok = (N % 4 == 0) && (ldc % 4 == 0) && aligned16(C) && (!bias || aligned16(bias)) &&
              (!residual || (aligned16(residual) && ldr % 4 == 0));
-  return launch<false>(a, st);
+  return launch<false>(ctx, a, st);
 }
 
-extern "C" int mage_conv2d_nhwc_f32(const float* in, const float* w, const float* bias, const float* residual,
+extern "C" int mage_conv2d_nhwc_f32(mage_ctx* ctx, const float* in, const float* w, const float* bias, const float* residual,
                                     float* out, int n_img, int Hin, int Win, int Cin, int Hout, int Wout, int Cout,
                                     int KH, int KW, int stride, int pad_y, int pad_x, int in_up, int res_mode,
                                     int relu_in, int act, int out_sy, int out_sx, int out_oy, int out_ox,
                                     int Hfull, int Wfull, int64_t out_img_stride, void* stream) {
+  MAGE_CHECK_CTX(ctx);
   MAGE_CHECK_ARG(n_img > 0 && Cin > 0 && (Cin % 4) == 0 && Cout > 0 && KH > 0 && KW > 0 && stride > 0);
   MAGE_CHECK_ARG(aligned16(in) && aligned16(w) && (in_up == 0 || in_up == 1));
   MAGE_CHECK_ARG(res_mode >= 0 && res_mode <= 3 && (res_mode == 0 || residual != nullptr));
@@ -280,5 +282,5 @@ extern "C" int mage_conv2d_nhwc_f32(const float* in, const float* w, const float
   a.Hfull = Hfull; a.Wfull = Wfull; a.out_img_stride = out_img_stride;
   a.vec_ok = (Cout % 4 == 0) && aligned16(out) && (out_img_stride % 4 == 0) && (!bias || aligned16(bias)) &&
              (!residual || aligned16(residual));
-  return launch<true>(a, as_stream(stream));
+  return launch<true>(ctx, a, as_stream(stream));
 }

@@ -75,6 +75,8 @@ struct TcParams {
   // with fp32 accumulation, for layers whose result feeds no token (the last VQ-VAE decoder block: DESIGN.md "decoder
   // precision budget"); only the hi planes are fetched (w_tx_bytes / a_tx_bytes halve) and the corr accumulator is never read.
   int passes, w_tx_bytes;
+  // halo kernel shared-memory plan of this launch (HaloCfg): A ring depth / stage bytes, W slots / slot bytes, resident weights
+  int sa, sw, a_stage_bytes, w_slot_bytes, w_resident, smem_bytes;
 };
 
 template <int BN, int CG>
@@ -189,7 +191,11 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
       if (!single) tmem_ld32(t_corr + tc_col, rc);
       // the residual row segment travels while the TMEM loads complete
       float4 rv[8];
+#ifdef MAGE_EXP_NO_RES
+      if (false) {
+#else
       if (res_off >= 0) {
+#endif
 #pragma unroll
         for (int j = 0; j < 8; ++j) rv[j] = __ldg(reinterpret_cast<const float4*>(res + res_off + n) + j);
       }
@@ -206,7 +212,11 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = single ? __uint_as_float(rm[j]) : fmaf(__uint_as_float(rc[j]), kLoInv, __uint_as_float(rm[j]));
+#ifdef MAGE_EXP_NO_BIAS
+      if (false) {
+#else
       if (bias) {
+#endif
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n) + j);   // same address in every lane: one broadcast
@@ -217,7 +227,11 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = act_fn<ACT>(v[j]);
       }
+#ifdef MAGE_EXP_NO_RES
+      if (false) {
+#else
       if (res_off >= 0) {
+#endif
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float4 a = rv[j];
@@ -244,7 +258,11 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
           }
         }
       }
+#ifdef MAGE_EXP_NO_STORE
+      if (has_out && v[0] == 123456.789f) {
+#else
       if (has_out) {
+#endif
         staging_free();
 #pragma unroll
         for (int j = 0; j < 8; ++j)
@@ -258,7 +276,11 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
         }
         pending = true;
       }
+#ifdef MAGE_EXP_NO_STORE
+      if ((has_split || has_relu) && v[0] == 123456.789f) {
+#else
       if (has_split || has_relu) {
+#endif
 #pragma unroll
         for (int pass = 0; pass < 2; ++pass) {
           if (pass == 0 ? !has_split : !has_relu) continue;
@@ -532,19 +554,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 // input patch (both planes); every tap's A operand is that patch read through a shifted descriptor (start + (ky*pitch+kx)
 // rows of 128 B, 8-row groups `pitch` rows apart), so the activations are fetched once instead of KH*KW times.  Weight tiles
 // stream per (tap, channel block) through their own ring.  Same roles / epilogue / CTA-pair scheme as tc_gemm_kernel.
-constexpr int HALO_A_STAGE = 46080;   // 18 x 10 pixels x 128 B x 2 planes (3x3 taps), a multiple of 1024
-constexpr int HALO_SA = 2;
+constexpr int HALO_A_STAGE = 46080;   // 18 x 10 pixels x 128 B x 2 planes (3x3 taps), a multiple of 1024: the largest A stage
+constexpr int HALO_SA_MAX = 4, HALO_SW_MAX = 24;   // barrier slots; the ring depths themselves are chosen per launch (TcParams)
+constexpr int HALO_BAR_BYTES = 1024;               // 2*4 + 2*24 + 4 mbarriers + the TMEM slot
 
+// Shared memory of the halo kernel, laid out per launch:  [ sa A stages | sw W slots | 32 KB epilogue staging | barriers ]
+//   A stage = the halo patch of one 64-channel block (both planes, or the hi plane alone in single-pass mode), 1 KB aligned;
+//   W slot  = one (tap, channel block) weight tile: this CTA's W_ROWS rows x 128 B per plane.
+// Weight slots work in one of two ways (TcParams::w_resident):
+//   ring      sw slots cycle through the (tap, block) tiles of every output tile -- weights are re-fetched per tile;
+//   resident  every weight tile this CTA will ever need (taps x channel blocks x the N tiles of its group) has its own slot, is
+//             fetched ONCE and stays: a 3x3 64->64 layer re-uses the same nine tiles for each of its ~55 output tiles per CTA,
+//             and with a ring shallower than one tile's worth of taps the TMA latency of the refetch was exposed on every tile
+//             (ncu, profiles/r02d_*: the MMA warp waiting on w_full, 2.6 us per tile for 0.6 us of MMAs).
 template <int BN, int CG>
 struct HaloCfg {
   static constexpr int W_ROWS = BN / CG;
-  static constexpr int W_BYTES = 2 * W_ROWS * BK * 2;
+  static constexpr int W_PLANE_BYTES = W_ROWS * BK * 2;
   static constexpr int STAGING_BYTES = 8 * 32 * 32 * 4;
-  static constexpr int SW_RAW = (SMEM_BUDGET - 1024 - 256 - STAGING_BYTES - HALO_SA * HALO_A_STAGE) / W_BYTES;
-  static constexpr int SW = SW_RAW > 8 ? 8 : SW_RAW;
   static constexpr int TMEM_COLS = 512;
-  static constexpr int SMEM_BYTES = 1024 + HALO_SA * HALO_A_STAGE + SW * W_BYTES + STAGING_BYTES + 256;
-  static_assert(SW >= 2, "weight ring too shallow for this tile");
+  static constexpr int SMEM_MAX = SMEM_BUDGET;
+  static constexpr int FIXED_BYTES = 1024 + STAGING_BYTES + HALO_BAR_BYTES;   // alignment slack + staging + barriers
 };
 
 template <int BN, int CG>
@@ -554,22 +584,25 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                     const __grid_constant__ CUtensorMap mapR, const TcParams p) {
   using H = HaloCfg<BN, CG>;
   using C = Cfg<BN, CG>;
-  constexpr int SA = HALO_SA, SW = H::SW;
+  const int SA = p.sa, SW = p.sw;                 // ring depths of this launch
+  const uint32_t a_stage_bytes = (uint32_t)p.a_stage_bytes, w_slot_bytes = (uint32_t)p.w_slot_bytes;
+  const uint32_t w_plane_off = (uint32_t)H::W_PLANE_BYTES;   // lo plane of a weight slot (3-pass mode)
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t w_base = base + SA * HALO_A_STAGE;
-  constexpr int STG_OFF = SA * HALO_A_STAGE + SW * H::W_BYTES;
+  const uint32_t w_base = base + SA * a_stage_bytes;
+  const uint32_t STG_OFF = SA * a_stage_bytes + SW * w_slot_bytes;
   uint8_t* staging = base_ptr + STG_OFF;
   const uint32_t bar_base = base + STG_OFF + H::STAGING_BYTES;
   auto a_full = [&](int s) { return bar_base + 8u * s; };
-  auto a_empty = [&](int s) { return bar_base + 8u * (SA + s); };
-  auto w_full = [&](int s) { return bar_base + 8u * (2 * SA + s); };
-  auto w_empty = [&](int s) { return bar_base + 8u * (2 * SA + SW + s); };
-  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * SA + 2 * SW + a); };
-  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * SA + 2 * SW + 2 + a); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + STG_OFF + H::STAGING_BYTES + 8 * (2 * SA + 2 * SW + 4));
+  auto a_empty = [&](int s) { return bar_base + 8u * (HALO_SA_MAX + s); };
+  auto w_full = [&](int s) { return bar_base + 8u * (2 * HALO_SA_MAX + s); };
+  auto w_empty = [&](int s) { return bar_base + 8u * (2 * HALO_SA_MAX + HALO_SW_MAX + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * HALO_SA_MAX + 2 * HALO_SW_MAX + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * HALO_SA_MAX + 2 * HALO_SW_MAX + 2 + a); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + STG_OFF + H::STAGING_BYTES +
+                                                                      8 * (2 * HALO_SA_MAX + 2 * HALO_SW_MAX + 4));
 
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int cta_rank = CG == 2 ? (int)cluster_ctarank() : 0;
@@ -614,7 +647,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           {
             const int s = ia % SA;
             mbar_wait(a_empty(s), ((ia / SA) & 1) ^ 1);
-            const uint32_t dst = base + s * HALO_A_STAGE;
+            const uint32_t dst = base + s * a_stage_bytes;
             if (CG == 2) {
               const uint32_t fb = mapa_u32(a_full(s), 0);
               if (elect_one()) {
@@ -629,9 +662,16 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             ++ia;
           }
           for (int tap = 0; tap < p.taps; ++tap, ++iw) {
-            const int s = iw % SW;
-            mbar_wait(w_empty(s), ((iw / SW) & 1) ^ 1);
-            const uint32_t dst = w_base + s * H::W_BYTES;
+            int s;
+            if (p.w_resident) {
+              // every weight tile of this CTA has its own slot and is fetched once: during the first group of tiles
+              if (ti >= p.group) continue;
+              s = ((ti % p.group) * p.cin_blocks + cb) * p.taps + tap;
+            } else {
+              s = iw % SW;
+              mbar_wait(w_empty(s), ((iw / SW) & 1) ^ 1);
+            }
+            const uint32_t dst = w_base + s * w_slot_bytes;
             const int k0 = (tap * p.cin_blocks + cb) * BK;
             if (CG == 2) {
               const uint32_t fb = mapa_u32(w_full(s), 0);
@@ -666,16 +706,16 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           const int sa = ia % SA;
           mbar_wait(a_full(sa), (ia / SA) & 1);
           tc_fence_after();
-          const uint32_t a_stage = base + sa * HALO_A_STAGE;
+          const uint32_t a_stage = base + sa * a_stage_bytes;
           int ky = 0, kx = 0;
           for (int tap = 0; tap < p.taps; ++tap, ++iw) {
-            const int sw = iw % SW;
-            mbar_wait(w_full(sw), (iw / SW) & 1);
+            const int sw = p.w_resident ? ((tcount % p.group) * p.cin_blocks + cb) * p.taps + tap : iw % SW;
+            mbar_wait(w_full(sw), p.w_resident ? 0u : (uint32_t)((iw / SW) & 1));   // resident: completes once, stays complete
             tc_fence_after();
             const uint32_t a_addr = a_stage + (uint32_t)(ky * p.halo_w + kx) * 128u;
             const uint64_t a_hi = umma_desc_sw128_sbo(a_addr, sbo), a_lo = umma_desc_sw128_sbo(a_addr + p.a_plane_bytes, sbo);
-            const uint32_t w_addr = w_base + sw * H::W_BYTES;
-            const uint64_t w_hi = umma_desc_sw128(w_addr), w_lo = umma_desc_sw128(w_addr + H::W_ROWS * BK * 2);
+            const uint32_t w_addr = w_base + sw * w_slot_bytes;
+            const uint64_t w_hi = umma_desc_sw128(w_addr), w_lo = umma_desc_sw128(w_addr + w_plane_off);
             const bool last_tap = tap + 1 == p.taps, last = last_tap && cb + 1 == p.cin_blocks;
             if (elect_one()) {
               if (p.passes == 1) {
@@ -703,11 +743,11 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
               }
               }
               if (CG == 2) {
-                umma_commit_2sm(w_empty(sw), 3);
+                if (!p.w_resident) umma_commit_2sm(w_empty(sw), 3);
                 if (last_tap) umma_commit_2sm(a_empty(sa), 3);
                 if (last) umma_commit_2sm(tfull_bar(acc), 3);
               } else {
-                umma_commit(w_empty(sw));
+                if (!p.w_resident) umma_commit(w_empty(sw));
                 if (last_tap) umma_commit(a_empty(sa));
                 if (last) umma_commit(tfull_bar(acc));
               }
@@ -849,16 +889,6 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-int num_sms() {
-  static int n = [] {
-    int dev = 0, v = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-    return v > 0 ? v : 148;
-  }();
-  return n;
-}
-
 // rank-R fp16 tensor map, SWIZZLE_128B, zero OOB fill.  dims/box innermost first; strides in bytes for dims 1..R-1.
 int make_map(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box,
              CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT16, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
@@ -899,46 +929,51 @@ int make_store_maps(Maps* mp, float* out, void* split, void* split_relu, int64_t
   return 0;
 }
 
-template <int BN, int CG, bool NS = false>
-int launch_tc(const Maps& mp, const TcParams& p, cudaStream_t st) {
-  using C = Cfg<BN, CG>;
-  static bool configured = false;
-  static int max_units = 0;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN, CG, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+// Per-device launch configuration of a kernel: opt-in shared-memory size set once per handle (= per device), and how many CTAs /
+// CTA pairs can be co-resident (1 CTA per SM; GPCs with an odd SM count leave one SM unpaired).
+template <typename K>
+int configure_kernel(mage_ctx* ctx, K kernel, int cg, int smem_bytes, int* max_units) {
+  const void* fn = reinterpret_cast<const void*>(kernel);
+  int k = ctx->find(fn);
+  if (k < 0) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return (int)e;
-    max_units = num_sms() / CG;
-    if (CG == 2) {
-      // how many CTA pairs can be co-resident (1 CTA per SM): GPCs with an odd SM count leave one SM unpaired
+    int units = ctx->sms / cg;
+    if (cg == 2) {
       cudaLaunchConfig_t q{};
       cudaLaunchAttribute qa[1];
       qa[0].id = cudaLaunchAttributeClusterDimension;
       qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
-      q.gridDim = dim3(num_sms() & ~1); q.blockDim = dim3(NTHREADS); q.dynamicSmemBytes = C::SMEM_BYTES; q.attrs = qa; q.numAttrs = 1;
+      q.gridDim = dim3(ctx->sms & ~1); q.blockDim = dim3(NTHREADS); q.dynamicSmemBytes = smem_bytes; q.attrs = qa; q.numAttrs = 1;
       int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, tc_gemm_kernel<BN, CG, NS>, &q) == cudaSuccess && n > 0) max_units = n < max_units ? n : max_units;
+      if (cudaOccupancyMaxActiveClusters(&n, kernel, &q) == cudaSuccess && n > 0) units = n < units ? n : units;
       else (void)cudaGetLastError();
     }
-    configured = true;
+    k = ctx->add(fn, units, (size_t)smem_bytes);
+    if (k < 0) return MAGE_EINVAL;
   }
+  *max_units = ctx->cfg_units[k];
+  return 0;
+}
+
+template <int BN, int CG, bool NS = false>
+int launch_tc(mage_ctx* ctx, const Maps& mp, const TcParams& p, cudaStream_t st) {
+  using C = Cfg<BN, CG>;
+  int max_units = 0;
+  if (int r = configure_kernel(ctx, tc_gemm_kernel<BN, CG, NS>, CG, C::SMEM_BYTES, &max_units)) return r;
   const int tiles = (p.m_tiles / CG) * p.n_tiles;
   const int units = tiles < max_units ? tiles : max_units;
-  cudaError_t e = mage_launch_pdl(tc_gemm_kernel<BN, CG, NS>, dim3(units * CG), dim3(NTHREADS), C::SMEM_BYTES, st, CG, mp.A, mp.W, mp.O, mp.S,
+  cudaError_t e = mage_launch_pdl(ctx, tc_gemm_kernel<BN, CG, NS>, dim3(units * CG), dim3(NTHREADS), C::SMEM_BYTES, st, CG, mp.A, mp.W, mp.O, mp.S,
                                   mp.R, p);
   if (e != cudaSuccess) return (int)e;
-  return mage_post_launch();
+  return mage_post_launch(ctx);
 }
 
 struct TileCfg { int bn, cg, ns; };
 
 // Tile selection.  The kernel is bound by L2->SM operand traffic, so the widest tile that still fills the machine wins:
 // CTA pair 256x256 (one TMEM accumulator stage), then pair 256x128 (two stages), then the single-CTA tiles.
-// MAGE_TC_BN / MAGE_TC_PAIR (0/1) force a choice (tuning + tests).
-int g_forced_bn = [] { const char* e = getenv("MAGE_TC_BN"); return e ? atoi(e) : 0; }();
-int g_forced_pair = [] { const char* e = getenv("MAGE_TC_PAIR"); return e ? atoi(e) : -1; }();
-int g_ns = [] { const char* e = getenv("MAGE_TC_NS"); return e ? atoi(e) : 1; }();   // N-split 256-wide pair tiles for plain GEMMs
-int g_small = [] { const char* e = getenv("MAGE_TC_SMALL"); return e ? atoi(e) : 1; }();   // one-tile cost model for sub-2-wave GEMMs
-
+// The handle's forced_bn / forced_pair (mage_tc_tuning; seeded from MAGE_TC_BN / MAGE_TC_PAIR) force a choice (tuning + tests).
 // Small problems (a decode step of a few prompts: M = 2048 rows at 8 prompts) run one or two waves of tiles, so neither the
 // double-buffered accumulator nor wave-averaging helps: what counts is the number of waves and what ONE tile costs -- per
 // k-block the larger of its MMA time and the time to pull its operand bytes into the SM (measured: ~110 GB/s per SM; the
@@ -967,9 +1002,9 @@ TileCfg pick_small(int N, int64_t m_tiles, int K, int sms, bool pair_ok) {
   return best;
 }
 
-TileCfg pick_cfg(int N, int64_t m_tiles, int K, bool gemm = false) {
-  const int forced_bn = g_forced_bn, forced_pair = g_forced_pair;
-  const int sms = num_sms();
+TileCfg pick_cfg(const mage_ctx* ctx, int N, int64_t m_tiles, int K, bool gemm = false) {
+  const int forced_bn = ctx->forced_bn, forced_pair = ctx->forced_pair, g_ns = ctx->ns, g_small = ctx->small;
+  const int sms = ctx->sms;
   const bool pair_ok = forced_pair != 0 && m_tiles % 2 == 0;
   // N-split 256-wide pair tiles (plain GEMMs only): A is fetched once per 256 output columns, the two 128-column halves keep
   // separate accumulators so the epilogue still overlaps the next tile's MMAs.  g_ns: 0 off, 1 automatic, 2 whenever legal.
@@ -997,60 +1032,64 @@ TileCfg pick_cfg(int N, int64_t m_tiles, int K, bool gemm = false) {
   return {0, 0, 0};
 }
 
-int dispatch(TileCfg c, const Maps& mp, const TcParams& p, cudaStream_t st) {
+int dispatch(mage_ctx* ctx, TileCfg c, const Maps& mp, const TcParams& p, cudaStream_t st) {
   if (c.cg == 2) {
-    if (c.ns) return c.bn == 256 ? launch_tc<256, 2, true>(mp, p, st) : MAGE_ENOTSUP;
+    if (c.ns) return c.bn == 256 ? launch_tc<256, 2, true>(ctx, mp, p, st) : MAGE_ENOTSUP;
     switch (c.bn) {
-      case 256: return launch_tc<256, 2>(mp, p, st);
-      case 192: return launch_tc<192, 2>(mp, p, st);
-      case 128: return launch_tc<128, 2>(mp, p, st);
-      case 64: return launch_tc<64, 2>(mp, p, st);
+      case 256: return launch_tc<256, 2>(ctx, mp, p, st);
+      case 192: return launch_tc<192, 2>(ctx, mp, p, st);
+      case 128: return launch_tc<128, 2>(ctx, mp, p, st);
+      case 64: return launch_tc<64, 2>(ctx, mp, p, st);
     }
     return MAGE_ENOTSUP;
   }
   switch (c.bn) {
-    case 256: return launch_tc<256, 1>(mp, p, st);
-    case 128: return launch_tc<128, 1>(mp, p, st);
-    case 64: return launch_tc<64, 1>(mp, p, st);
+    case 256: return launch_tc<256, 1>(ctx, mp, p, st);
+    case 128: return launch_tc<128, 1>(ctx, mp, p, st);
+    case 64: return launch_tc<64, 1>(ctx, mp, p, st);
   }
   return MAGE_ENOTSUP;
 }
 
 
 template <int BN, int CG>
-int launch_halo(const Maps& mp, const TcParams& p, cudaStream_t st) {
+int launch_halo(mage_ctx* ctx, const Maps& mp, const TcParams& p, cudaStream_t st) {
   using H = HaloCfg<BN, CG>;
-  static bool configured = false;
-  static int max_units = 0;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_conv_halo_kernel<BN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, H::SMEM_BYTES);
-    if (e != cudaSuccess) return (int)e;
-    max_units = num_sms() / CG;
-    if (CG == 2) {
-      cudaLaunchConfig_t q{};
-      cudaLaunchAttribute qa[1];
-      qa[0].id = cudaLaunchAttributeClusterDimension;
-      qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
-      q.gridDim = dim3(num_sms() & ~1); q.blockDim = dim3(NTHREADS); q.dynamicSmemBytes = H::SMEM_BYTES; q.attrs = qa; q.numAttrs = 1;
-      int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, tc_conv_halo_kernel<BN, CG>, &q) == cudaSuccess && n > 0) max_units = n < max_units ? n : max_units;
-      else (void)cudaGetLastError();
-    }
-    configured = true;
-  }
+  int max_units = 0;
+  if (int r = configure_kernel(ctx, tc_conv_halo_kernel<BN, CG>, CG, H::SMEM_MAX, &max_units)) return r;
   const int tiles = (p.m_tiles / CG) * p.n_tiles;
   const int units = tiles < max_units ? tiles : max_units;
-  cudaError_t e = mage_launch_pdl(tc_conv_halo_kernel<BN, CG>, dim3(units * CG), dim3(NTHREADS), H::SMEM_BYTES, st, CG, mp.A, mp.W, mp.O,
-                                  mp.S, mp.R, p);
+  // shared-memory plan (see HaloCfg): resident weights when every weight tile a CTA needs fits next to two A stages and the CTA
+  // always works on the same N tile(s); otherwise a weight ring as deep as the budget allows.  Spare room deepens the A ring.
+  TcParams q = p;
+  const int planes = p.passes == 1 ? 1 : 2;
+  q.a_stage_bytes = (planes * p.a_plane_bytes + 1023) & ~1023;
+  q.w_slot_bytes = planes * H::W_PLANE_BYTES;
+  const int budget = H::SMEM_MAX - H::FIXED_BYTES;
+  const bool fixed_nt = p.n_tiles == 1 || p.group == p.n_tiles || (p.group == 1 && units % p.n_tiles == 0);
+  const int need = p.taps * p.cin_blocks * p.group;
+  if (ctx->resident && fixed_nt && need <= HALO_SW_MAX && 2 * q.a_stage_bytes + need * q.w_slot_bytes <= budget) {
+    q.w_resident = 1;
+    q.sw = need;
+  } else {
+    q.w_resident = 0;
+    q.sw = (budget - 2 * q.a_stage_bytes) / q.w_slot_bytes;
+    if (q.sw > 12) q.sw = 12;
+    if (q.sw < 2) return MAGE_ENOTSUP;
+  }
+  q.sa = 2 + (budget - 2 * q.a_stage_bytes - q.sw * q.w_slot_bytes) / q.a_stage_bytes;
+  if (q.sa > HALO_SA_MAX) q.sa = HALO_SA_MAX;
+  q.smem_bytes = 1024 + q.sa * q.a_stage_bytes + q.sw * q.w_slot_bytes + H::STAGING_BYTES + HALO_BAR_BYTES;
+  cudaError_t e = mage_launch_pdl(ctx, tc_conv_halo_kernel<BN, CG>, dim3(units * CG), dim3(NTHREADS), (size_t)q.smem_bytes, st, CG, mp.A, mp.W,
+                                  mp.O, mp.S, mp.R, q);
   if (e != cudaSuccess) return (int)e;
-  return mage_post_launch();
+  return mage_post_launch(ctx);
 }
-
-int g_halo = [] { const char* e = getenv("MAGE_TC_HALO"); return e ? atoi(e) : 1; }();
 
 // tile choice of the halo kernel: CTA pairs whenever the row-tile count is even (each CTA then streams only half of every
 // weight tile), the widest N tile the channel count allows; BN = 256 exists only as a pair (weight ring depth).
-TileCfg pick_halo_cfg(int Cout, int64_t m_tiles) {
+TileCfg pick_halo_cfg(const mage_ctx* ctx, int Cout, int64_t m_tiles) {
+  const int g_forced_bn = ctx->forced_bn, g_forced_pair = ctx->forced_pair;
   const bool pair_ok = g_forced_pair != 0 && m_tiles % 2 == 0;
   if (g_forced_bn && g_forced_bn != 192 && Cout % g_forced_bn == 0 && (g_forced_bn != 256 || pair_ok)) return {g_forced_bn, (pair_ok && (g_forced_pair == 1 || g_forced_bn == 256)) ? 2 : 1, 0};
   if (pair_ok) {
@@ -1062,18 +1101,18 @@ TileCfg pick_halo_cfg(int Cout, int64_t m_tiles) {
   return {0, 0, 0};
 }
 
-int dispatch_halo(TileCfg c, const Maps& mp, const TcParams& p, cudaStream_t st) {
+int dispatch_halo(mage_ctx* ctx, TileCfg c, const Maps& mp, const TcParams& p, cudaStream_t st) {
   if (c.cg == 2) {
     switch (c.bn) {
-      case 256: return launch_halo<256, 2>(mp, p, st);
-      case 128: return launch_halo<128, 2>(mp, p, st);
-      case 64: return launch_halo<64, 2>(mp, p, st);
+      case 256: return launch_halo<256, 2>(ctx, mp, p, st);
+      case 128: return launch_halo<128, 2>(ctx, mp, p, st);
+      case 64: return launch_halo<64, 2>(ctx, mp, p, st);
     }
     return MAGE_ENOTSUP;
   }
   switch (c.bn) {
-    case 128: return launch_halo<128, 1>(mp, p, st);
-    case 64: return launch_halo<64, 1>(mp, p, st);
+    case 128: return launch_halo<128, 1>(ctx, mp, p, st);
+    case 64: return launch_halo<64, 1>(ctx, mp, p, st);
   }
   return MAGE_ENOTSUP;
 }
@@ -1087,73 +1126,81 @@ int make_w_map(CUtensorMap* map, const void* W, int64_t ldw, int64_t w_plane, in
 
 }  // namespace
 
-extern "C" int mage_tc_tuning(int bn, int pair) {
+extern "C" int mage_tc_tuning(mage_ctx* ctx, int bn, int pair) {
+  MAGE_CHECK_CTX(ctx);
   MAGE_CHECK_ARG((bn == 0 || bn == 64 || bn == 128 || bn == 192 || bn == 256) && pair >= -1 && pair <= 1);
-  g_forced_bn = bn;
-  g_forced_pair = pair;
+  ctx->forced_bn = bn;
+  ctx->forced_pair = pair;
   return 0;
 }
 
-extern "C" int mage_tc_nsplit(int mode) {
+extern "C" int mage_tc_nsplit(mage_ctx* ctx, int mode) {
+  MAGE_CHECK_CTX(ctx);
   MAGE_CHECK_ARG(mode >= 0 && mode <= 2);
-  g_ns = mode;
+  ctx->ns = mode;
   return 0;
 }
 
-extern "C" int mage_tc_conv_halo(int enable) {
-  g_halo = enable != 0;
+extern "C" int mage_tc_conv_halo(mage_ctx* ctx, int enable) {
+  MAGE_CHECK_CTX(ctx);
+  ctx->halo = enable != 0;
   return 0;
 }
 
-extern "C" int mage_split_f32(const float* x, int64_t ldx, void* out, int64_t plane, int rows, int C, int relu, int* flag,
+extern "C" int mage_split_f32(mage_ctx* ctx, const float* x, int64_t ldx, void* out, int64_t plane, int rows, int C, int relu, int* flag,
                               void* stream) {
+  MAGE_CHECK_CTX(ctx);
   MAGE_CHECK_ARG(rows > 0 && C > 0 && C % 4 == 0 && ldx % 4 == 0 && aligned16(x) && (reinterpret_cast<uintptr_t>(out) & 7) == 0 &&
                  plane % 4 == 0);
   const int64_t total = (int64_t)rows * (C / 4);
   split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(x, ldx, reinterpret_cast<__half*>(out), plane, rows,
                                                                                 C / 4, relu, flag);
-  return mage_post_launch();
+  return mage_post_launch(ctx);
 }
 
-extern "C" int mage_patch_rows_split_f32(const float* in, void* out, int64_t plane, int n_img, int C, int H, int W, int KW, int pad,
+extern "C" int mage_patch_rows_split_f32(mage_ctx* ctx, const float* in, void* out, int64_t plane, int n_img, int C, int H, int W, int KW, int pad,
                                          void* stream) {
+  MAGE_CHECK_CTX(ctx);
   MAGE_CHECK_ARG(n_img > 0 && C > 0 && H > 0 && W > 0 && KW > 0 && C * KW <= 64 && pad >= 0 && aligned16(out) && plane % 8 == 0);
   const int64_t total = (int64_t)n_img * H * W * 8;
   patch_rows_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(in, reinterpret_cast<__half*>(out), plane, n_img,
                                                                                           C, H, W, KW, pad);
-  return mage_post_launch();
+  return mage_post_launch(ctx);
 }
 
-extern "C" int mage_s2d_pad_split_f32(const float* in, void* out, int64_t plane, int n_img, int H, int W, int C, int relu, int* flag,
+extern "C" int mage_s2d_pad_split_f32(mage_ctx* ctx, const float* in, void* out, int64_t plane, int n_img, int H, int W, int C, int relu, int* flag,
                                       void* stream) {
+  MAGE_CHECK_CTX(ctx);
   MAGE_CHECK_ARG(n_img > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && C > 0 && C % 8 == 0 && aligned16(in) && aligned16(out) &&
                  plane % 8 == 0);
   const int64_t total = (int64_t)n_img * (H / 2 + 1) * (W / 2 + 1) * 4 * (C / 8);
   s2d_pad_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(in, reinterpret_cast<__half*>(out), plane, n_img,
                                                                                        H, W, C / 8, relu, flag);
-  return mage_post_launch();
+  return mage_post_launch(ctx);
 }
 
-extern "C" int mage_embedding_split(const int64_t* idx, const void* table, int64_t table_plane, void* out, int64_t out_plane,
+extern "C" int mage_embedding_split(mage_ctx* ctx, const int64_t* idx, const void* table, int64_t table_plane, void* out, int64_t out_plane,
                                     int rows, int C, void* stream) {
+  MAGE_CHECK_CTX(ctx);
   MAGE_CHECK_ARG(rows > 0 && C > 0 && C % 8 == 0 && aligned16(table) && aligned16(out) && table_plane % 8 == 0 && out_plane % 8 == 0);
   const int64_t total = (int64_t)rows * (C / 8) * 2;
-  mage_launch_pdl(embedding_split_kernel, (unsigned)((total + 255) / 256), 256, 0, as_stream(stream), 1, idx,
+  mage_launch_pdl(ctx, embedding_split_kernel, (unsigned)((total + 255) / 256), 256, 0, as_stream(stream), 1, idx,
                   reinterpret_cast<const __half*>(table), table_plane, reinterpret_cast<__half*>(out), out_plane, rows, C / 8);
-  return mage_post_launch();
+  return mage_post_launch(ctx);
 }
 
-extern "C" int mage_gemm_tc(const void* A, int64_t lda, int64_t a_plane, const void* W, int64_t ldw, int64_t w_plane,
+extern "C" int mage_gemm_tc(mage_ctx* ctx, const void* A, int64_t lda, int64_t a_plane, const void* W, int64_t ldw, int64_t w_plane,
                             const float* bias, const float* residual, int64_t ldr, int res_mod, float* C, void* C_split,
                             void* C_split_relu, int64_t ldc, int64_t c_plane, int M, int N, int K, int act, int* flag,
                             void* stream) {
+  MAGE_CHECK_CTX(ctx);
   MAGE_CHECK_ARG(M > 0 && N > 0 && K > 0);
   if (K % BK != 0 || N % 64 != 0) return MAGE_ENOTSUP;
   MAGE_CHECK_ARG(aligned16(A) && aligned16(W) && lda % 8 == 0 && ldw % 8 == 0 && a_plane % 8 == 0 && w_plane % 8 == 0);
   MAGE_CHECK_ARG(ldc % 4 == 0 && (!C || aligned16(C)) && (!bias || aligned16(bias)) && (!residual || (aligned16(residual) && ldr % 4 == 0)));
   MAGE_CHECK_ARG(c_plane % 4 == 0 && (C || C_split || C_split_relu));
   const int m_tiles = (M + BM - 1) / BM;
-  const TileCfg tcfg = pick_cfg(N, m_tiles, K, true);
+  const TileCfg tcfg = pick_cfg(ctx, N, m_tiles, K, true);
   if (!tcfg.bn) return MAGE_ENOTSUP;
   const int bn = tcfg.bn;
   Maps mp{};
@@ -1180,7 +1227,7 @@ extern "C" int mage_gemm_tc(const void* A, int64_t lda, int64_t a_plane, const v
     int r = make_store_maps(&mp, C, C_split, C_split_relu, c_plane, N, M, 1, 1, ldc, ldc * (int64_t)M, ldc * (int64_t)M, 32, 1);
     if (r) return r;
   }
-  return dispatch(tcfg, mp, p, as_stream(stream));
+  return dispatch(ctx, tcfg, mp, p, as_stream(stream));
 }
 
 // Stride-1 NHWC convolution on the tensor cores.  in: split [n_img,Hin,Win,Cin] (Cin % 64 == 0), w: split
@@ -1188,7 +1235,7 @@ extern "C" int mage_gemm_tc(const void* A, int64_t lda, int64_t a_plane, const v
 namespace {
 struct HeadArgs { const float* w; const float* b; float* out; int cout; int64_t img_stride; };
 
-int conv2d_tc_impl(const void* in, int64_t in_plane, const void* w, int64_t w_plane, const float* bias,
+int conv2d_tc_impl(mage_ctx* ctx, const void* in, int64_t in_plane, const void* w, int64_t w_plane, const float* bias,
                    const float* residual, float* out, void* out_split, void* out_split_relu, int64_t out_plane,
                    int n_img, int Hin, int Win, int Cin, int Hout, int Wout, int Cout, int KH, int KW, int pad_y,
                    int pad_x, int res_mode, int act, int out_sy, int out_sx, int out_oy, int out_ox, int Hfull,
@@ -1197,12 +1244,13 @@ int conv2d_tc_impl(const void* in, int64_t in_plane, const void* w, int64_t w_pl
   if (Cin % BK != 0 || Cout % 64 != 0) return MAGE_ENOTSUP;
   // halo mode: 16x8-pixel tiles, the input patch is fetched once per channel block and shared by all taps
   const int act_id = act & 0xff;
-  bool halo = g_halo && KH * KW > 1 && Hout % 16 == 0 && Wout % 8 == 0 && (15 + KH) * (7 + KW) * 256 <= HALO_A_STAGE &&
+  const int g_forced_bn = ctx->forced_bn, g_forced_pair = ctx->forced_pair;
+  bool halo = ctx->halo && KH * KW > 1 && Hout % 16 == 0 && Wout % 8 == 0 && (15 + KH) * (7 + KW) * 256 <= HALO_A_STAGE &&
               (act_id == MAGE_ACT_NONE || act_id == MAGE_ACT_RELU || act_id == MAGE_ACT_TANH);
   TileCfg hcfg{0, 0, 0};
   if (halo) {
     const int64_t hm = (int64_t)n_img * (Hout / 16) * (Wout / 8);
-    hcfg = pick_halo_cfg(Cout, hm);
+    hcfg = pick_halo_cfg(ctx, Cout, hm);
     if (head) {
       // the pixel head needs all 256 channels of a row in one CTA: two consecutive 128-wide tiles of the same rows (the
       // partial sums stay in registers across the group; TMEM double buffering is kept), or one 256-wide tile when forced
@@ -1222,7 +1270,7 @@ int conv2d_tc_impl(const void* in, int64_t in_plane, const void* w, int64_t w_pl
   const int64_t m_tiles = (int64_t)n_img * (Hout / Hb) * (Wout / Wb);
   MAGE_CHECK_ARG(m_tiles < ((int64_t)1 << 24));
   const int K = KH * KW * Cin;
-  TileCfg tcfg = halo ? hcfg : pick_cfg(Cout, m_tiles, K);
+  TileCfg tcfg = halo ? hcfg : pick_cfg(ctx, Cout, m_tiles, K);
   if (head && !halo) {
     // the pixel head needs every output channel of a row in one CTA: one 256-wide N tile
     if (Cout != 256 || (act & 0xff) != MAGE_ACT_NONE) return MAGE_ENOTSUP;
@@ -1280,29 +1328,31 @@ int conv2d_tc_impl(const void* in, int64_t in_plane, const void* w, int64_t w_pl
     p.passes = passes;
     p.a_plane_bytes = (Hb + KH - 1) * (Wb + KW - 1) * 128; p.a_tx_bytes = (passes == 1 ? 1 : 2) * p.a_plane_bytes;
     p.w_tx_bytes = (passes == 1 ? 1 : 2) * (bn / tcfg.cg) * BK * 2;
-    return dispatch_halo(tcfg, mp, p, as_stream(stream));
+    return dispatch_halo(ctx, tcfg, mp, p, as_stream(stream));
   }
-  return dispatch(tcfg, mp, p, as_stream(stream));
+  return dispatch(ctx, tcfg, mp, p, as_stream(stream));
 }
 }  // namespace
 
-extern "C" int mage_conv2d_tc(const void* in, int64_t in_plane, const void* w, int64_t w_plane, const float* bias,
+extern "C" int mage_conv2d_tc(mage_ctx* ctx, const void* in, int64_t in_plane, const void* w, int64_t w_plane, const float* bias,
                               const float* residual, float* out, void* out_split, void* out_split_relu, int64_t out_plane,
                               int n_img, int Hin, int Win, int Cin, int Hout, int Wout, int Cout, int KH, int KW, int pad_y,
                               int pad_x, int res_mode, int act, int out_sy, int out_sx, int out_oy, int out_ox, int Hfull,
                               int Wfull, int64_t out_img_stride, int passes, int* flag, void* stream) {
-  return conv2d_tc_impl(in, in_plane, w, w_plane, bias, residual, out, out_split, out_split_relu, out_plane, n_img, Hin, Win, Cin,
+  MAGE_CHECK_CTX(ctx);
+  return conv2d_tc_impl(ctx, in, in_plane, w, w_plane, bias, residual, out, out_split, out_split_relu, out_plane, n_img, Hin, Win, Cin,
                         Hout, Wout, Cout, KH, KW, pad_y, pad_x, res_mode, act, out_sy, out_sx, out_oy, out_ox, Hfull, Wfull,
                         out_img_stride, flag, stream, nullptr, passes);
 }
 
-extern "C" int mage_conv2d_tc_pixel_head(const void* in, int64_t in_plane, const void* w, int64_t w_plane, const float* bias,
+extern "C" int mage_conv2d_tc_pixel_head(mage_ctx* ctx, const void* in, int64_t in_plane, const void* w, int64_t w_plane, const float* bias,
                                          const float* residual, int n_img, int Hin, int Win, int Cin, int Hout, int Wout,
                                          int Cout, int KH, int KW, int pad_y, int pad_x, int res_mode, const float* head_w,
                                          const float* head_b, int head_cout, float* head_out, int64_t head_img_stride,
                                          int passes, int* flag, void* stream) {
+  MAGE_CHECK_CTX(ctx);
   const HeadArgs h{head_w, head_b, head_out, head_cout, head_img_stride};
-  return conv2d_tc_impl(in, in_plane, w, w_plane, bias, residual, nullptr, nullptr, nullptr, 0, n_img, Hin, Win, Cin, Hout, Wout,
+  return conv2d_tc_impl(ctx, in, in_plane, w, w_plane, bias, residual, nullptr, nullptr, nullptr, 0, n_img, Hin, Win, Cin, Hout, Wout,
                         Cout, KH, KW, pad_y, pad_x, res_mode, MAGE_ACT_NONE, 1, 1, 0, 0, Hout, Wout,
                         (int64_t)Hout * Wout * Cout, flag, stream, &h, passes);
 }

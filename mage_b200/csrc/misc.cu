@@ -5,14 +5,45 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 
-// measured on B200: no gain over plain graph launches (157.9 vs 155.9 ms per generate) -> off unless MAGE_PDL=1
-int g_mage_pdl = [] { const char* e = getenv("MAGE_PDL"); return e ? atoi(e) : 0; }();
-int64_t g_mage_launches = 0;
+extern "C" int mage_abi_version(void) { return 5; }
 
-extern "C" int mage_abi_version(void) { return 4; }
-extern "C" int64_t mage_launch_count(void) { return g_mage_launches; }
-extern "C" int mage_pdl(int enable) {
-  g_mage_pdl = enable != 0;
+// One handle per (process, device).  Environment variables only seed a new handle's switches: MAGE_PDL (measured on B200: no
+// gain over plain graph launches, 157.9 vs 155.9 ms per generate -> off), MAGE_TC_BN / MAGE_TC_PAIR / MAGE_TC_NS / MAGE_TC_HALO /
+// MAGE_TC_SMALL (tile selection, see gemm_tc.cu).
+extern "C" int mage_ctx_create(int device, mage_ctx** out) {
+  if (!out) return MAGE_EINVAL;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) return (int)e;
+  if (device < 0 || device >= n) return MAGE_EINVAL;
+  int major = 0, sms = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  if (major != 10) return MAGE_ENOTSUP;   // sm_100a code only: no fallback for other architectures
+  mage_ctx* c = new mage_ctx();
+  c->device = device;
+  c->sms = sms > 0 ? sms : 148;
+  auto env = [](const char* k, int d) { const char* v = getenv(k); return v ? atoi(v) : d; };
+  c->pdl = env("MAGE_PDL", 0);
+  c->forced_bn = env("MAGE_TC_BN", 0);
+  c->forced_pair = env("MAGE_TC_PAIR", -1);
+  c->ns = env("MAGE_TC_NS", 1);
+  c->halo = env("MAGE_TC_HALO", 1);
+  c->small = env("MAGE_TC_SMALL", 1);
+  c->resident = env("MAGE_TC_RESIDENT", 1);
+  *out = c;
+  return 0;
+}
+extern "C" int mage_ctx_destroy(mage_ctx* ctx) {
+  delete ctx;
+  return 0;
+}
+extern "C" int mage_ctx_device(mage_ctx* ctx) { return ctx ? ctx->device : MAGE_EINVAL; }
+extern "C" int64_t mage_launch_count(mage_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int mage_pdl(mage_ctx* ctx, int enable) {
+  MAGE_CHECK_CTX(ctx);
+  ctx->pdl = enable != 0;
   return 0;
 }
 
@@ -454,88 +485,98 @@ __global__ void __launch_bounds__(256) kv_append_kernel(const float* __restrict_
 
 }  // namespace
 
-extern "C" int mage_layernorm_f32(const float* in, const float* gamma, const float* beta, float* out, void* out_split,
+extern "C" int mage_layernorm_f32(mage_ctx* ctx, const float* in, const float* gamma, const float* beta, float* out, void* out_split,
                                   int64_t split_plane, int* flag, int rows, int C, float eps, void* stream) {
+  MAGE_CHECK_CTX(ctx);
   MAGE_CHECK_ARG(rows > 0 && C % 128 == 0 && C <= 1024 && aligned16(in) && aligned16(out) && aligned16(gamma) && aligned16(beta));
   MAGE_CHECK_ARG((out || out_split) && aligned16(out_split) && split_plane % 4 == 0);
   const dim3 g((rows + 7) / 8);
   cudaStream_t st = as_stream(stream);
   __half* sp = reinterpret_cast<__half*>(out_split);
   switch (C / 128) {
-    case 1: mage_launch_pdl(layernorm_kernel<1>, g, 256, 0, st, 1, in, gamma, beta, out, sp, split_plane, flag, rows, eps); break;
-    case 2: mage_launch_pdl(layernorm_kernel<2>, g, 256, 0, st, 1, in, gamma, beta, out, sp, split_plane, flag, rows, eps); break;
-    case 4: mage_launch_pdl(layernorm_kernel<4>, g, 256, 0, st, 1, in, gamma, beta, out, sp, split_plane, flag, rows, eps); break;
-    case 8: mage_launch_pdl(layernorm_kernel<8>, g, 256, 0, st, 1, in, gamma, beta, out, sp, split_plane, flag, rows, eps); break;
+    case 1: mage_launch_pdl(ctx, layernorm_kernel<1>, g, 256, 0, st, 1, in, gamma, beta, out, sp, split_plane, flag, rows, eps); break;
+    case 2: mage_launch_pdl(ctx, layernorm_kernel<2>, g, 256, 0, st, 1, in, gamma, beta, out, sp, split_plane, flag, rows, eps); break;
+    case 4: mage_launch_pdl(ctx, layernorm_kernel<4>, g, 256, 0, st, 1, in, gamma, beta, out, sp, split_plane, flag, rows, eps); break;
+    case 8: mage_launch_pdl(ctx, layernorm_kernel<8>, g, 256, 0, st, 1, in, gamma, beta, out, sp, split_plane, flag, rows, eps); break;
     default: return MAGE_EINVAL;
   }
-  return mage_post_launch();
+  return mage_post_launch(ctx);
 }
 
-extern "C" int mage_argmax_rows_f32(const float* x, int64_t ldx, int64_t* idx, int rows, int N, void* stream) {
+extern "C" int mage_argmax_rows_f32(mage_ctx* ctx, const float* x, int64_t ldx, int64_t* idx, int rows, int N, void* stream) {
+  MAGE_CHECK_CTX(ctx);
   MAGE_CHECK_ARG(rows > 0 && N > 0);
-  mage_launch_pdl(argmax_rows_kernel, (rows + 7) / 8, 256, 0, as_stream(stream), 1, x, ldx, idx, rows, N);
-  return mage_post_launch();
+  mage_launch_pdl(ctx, argmax_rows_kernel, (rows + 7) / 8, 256, 0, as_stream(stream), 1, x, ldx, idx, rows, N);
+  return mage_post_launch(ctx);
 }
 
-extern "C" int mage_embedding_f32(const int64_t* idx, const float* table, float* out, int rows, int C, void* stream) {
+extern "C" int mage_embedding_f32(mage_ctx* ctx, const int64_t* idx, const float* table, float* out, int rows, int C, void* stream) {
+  MAGE_CHECK_CTX(ctx);
   MAGE_CHECK_ARG(rows > 0 && C % 4 == 0 && aligned16(table) && aligned16(out));
   const int64_t total = (int64_t)rows * (C / 4);
   embedding_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(idx, table, out, rows, C / 4);
-  return mage_post_launch();
+  return mage_post_launch(ctx);
 }
 
-extern "C" int mage_token_taps_f32(const int64_t* tok, const float* table, const float* pos_bias, const float* bias, float* out,
+extern "C" int mage_token_taps_f32(mage_ctx* ctx, const int64_t* tok, const float* table, const float* pos_bias, const float* bias, float* out,
                                    int n_img, int R, int K, int C, int KH, int KW, void* stream) {
+  MAGE_CHECK_CTX(ctx);
   MAGE_CHECK_ARG(n_img > 0 && R > 0 && K > 0 && C == 512 && KH > 0 && KW > 0 && (KH & 1) && (KW & 1));
   MAGE_CHECK_ARG(aligned16(table) && aligned16(pos_bias) && aligned16(bias) && aligned16(out));
   const int n_pix = n_img * R * R;
-  cudaError_t e = mage_launch_pdl(token_taps_kernel<4>, dim3((n_pix + 7) / 8), dim3(256), 0, as_stream(stream), 1, tok, table, pos_bias,
+  cudaError_t e = mage_launch_pdl(ctx, token_taps_kernel<4>, dim3((n_pix + 7) / 8), dim3(256), 0, as_stream(stream), 1, tok, table, pos_bias,
                                   bias, out, n_pix, R, K, KH, KW);
   if (e != cudaSuccess) return (int)e;
-  return mage_post_launch();
+  return mage_post_launch(ctx);
 }
 
-extern "C" int mage_maxpool2x2_nhwc_f32(const float* in, float* out, int n_img, int Hin, int Win, int C, void* stream) {
+extern "C" int mage_maxpool2x2_nhwc_f32(mage_ctx* ctx, const float* in, float* out, int n_img, int Hin, int Win, int C, void* stream) {
+  MAGE_CHECK_CTX(ctx);
   MAGE_CHECK_ARG(n_img > 0 && Hin % 2 == 0 && Win % 2 == 0 && C % 4 == 0 && aligned16(in) && aligned16(out));
   const int64_t total = (int64_t)n_img * (Hin / 2) * (Win / 2) * (C / 4);
   maxpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(in, out, n_img, Hin, Win, C / 4);
-  return mage_post_launch();
+  return mage_post_launch(ctx);
 }
 
-extern "C" int mage_text_embed_f32(const int64_t* text, const float* tok_emb, const float* pos_emb, const float* gamma,
+extern "C" int mage_text_embed_f32(mage_ctx* ctx, const int64_t* text, const float* tok_emb, const float* pos_emb, const float* gamma,
                                    const float* beta, float* x, int32_t* key_len, int B, int T, int C, int pad_idx,
                                    float eps, int vocab, int* flag, void* stream) {
+  MAGE_CHECK_CTX(ctx);
   MAGE_CHECK_ARG(B > 0 && T > 0 && C == 512 && aligned16(tok_emb) && aligned16(pos_emb) && aligned16(x));
   MAGE_CHECK_ARG(vocab > 0 && pad_idx >= 0 && pad_idx < vocab);
   text_embed_kernel<<<(B * T + 7) / 8, 256, 0, as_stream(stream)>>>(text, tok_emb, pos_emb, gamma, beta, x, key_len, B, T,
                                                                    pad_idx, eps, vocab, flag);
-  return mage_post_launch();
+  return mage_post_launch(ctx);
 }
 
-extern "C" int mage_adain_nhwc_f32(const float* x, const float* gamma, const float* beta, float* out, int n_img, int HW,
+extern "C" int mage_adain_nhwc_f32(mage_ctx* ctx, const float* x, const float* gamma, const float* beta, float* out, int n_img, int HW,
                                    int C, float eps, void* stream) {
+  MAGE_CHECK_CTX(ctx);
   MAGE_CHECK_ARG(n_img > 0 && HW > 0 && C % 32 == 0);
   adain_kernel<<<dim3(C / 32, n_img), 256, 0, as_stream(stream)>>>(x, gamma, beta, out, HW, C, eps);
-  return mage_post_launch();
+  return mage_post_launch(ctx);
 }
 
-extern "C" int mage_add_scaled_vec_f32(float* x, const float* s, const float* vec, int n_img, int HW, int C, void* stream) {
+extern "C" int mage_add_scaled_vec_f32(mage_ctx* ctx, float* x, const float* s, const float* vec, int n_img, int HW, int C, void* stream) {
+  MAGE_CHECK_CTX(ctx);
   MAGE_CHECK_ARG(n_img > 0 && HW > 0 && C > 0);
   const int64_t total = (int64_t)n_img * HW * C;
   add_scaled_vec_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(x, s, vec, HW, C, total);
-  return mage_post_launch();
+  return mage_post_launch(ctx);
 }
 
-extern "C" int mage_nchw_to_nhwc_f32(const float* in, float* out, int n_img, int C, int HW, void* stream) {
+extern "C" int mage_nchw_to_nhwc_f32(mage_ctx* ctx, const float* in, float* out, int n_img, int C, int HW, void* stream) {
+  MAGE_CHECK_CTX(ctx);
   MAGE_CHECK_ARG(n_img > 0 && C > 0 && HW > 0);
   const int64_t total = (int64_t)n_img * HW * C;
   nchw_to_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(in, out, C, HW, total);
-  return mage_post_launch();
+  return mage_post_launch(ctx);
 }
 
-extern "C" int mage_conv2d_first_f32(const float* in, const float* w_t, const float* bias, float* out, int n_img, int Cin,
+extern "C" int mage_conv2d_first_f32(mage_ctx* ctx, const float* in, const float* w_t, const float* bias, float* out, int n_img, int Cin,
                                      int H, int W, int Hout, int Wout, int Cout, int KH, int KW, int stride, int pad,
                                      int act, void* stream) {
+  MAGE_CHECK_CTX(ctx);
   MAGE_CHECK_ARG(n_img > 0 && Cin > 0 && Cin <= 4 && Cout > 0 && KH > 0 && KW > 0 && stride > 0);
   constexpr int PX = 16;
   const int PW = (PX - 1) * stride + KW;
@@ -546,38 +587,42 @@ extern "C" int mage_conv2d_first_f32(const float* in, const float* w_t, const fl
   MAGE_CHECK_ARG(blocks < ((int64_t)1 << 31));
   conv_first_kernel<PX><<<(unsigned)blocks, 256, smem, as_stream(stream)>>>(in, w_t, bias, out, Cin, H, W, Hout, Wout, Cout,
                                                                            KH, KW, stride, pad, act);
-  return mage_post_launch();
+  return mage_post_launch(ctx);
 }
 
-extern "C" int mage_conv1x1_tanh_nchw_f32(const float* in, const float* w, const float* bias, float* out, int n_img, int HW,
+extern "C" int mage_conv1x1_tanh_nchw_f32(mage_ctx* ctx, const float* in, const float* w, const float* bias, float* out, int n_img, int HW,
                                           int Cin, int Cout, int64_t out_img_stride, void* stream) {
+  MAGE_CHECK_CTX(ctx);
   MAGE_CHECK_ARG(n_img > 0 && HW > 0 && Cin % 4 == 0 && Cout >= 1 && Cout <= 4 && aligned16(in) && aligned16(w) && bias);
   const int64_t n_pix = (int64_t)n_img * HW;
   conv1x1_tanh_kernel<<<(unsigned)((n_pix + 7) / 8), 256, 0, as_stream(stream)>>>(in, w, bias, out, n_pix, HW, Cin, Cout,
                                                                                  out_img_stride);
-  return mage_post_launch();
+  return mage_post_launch(ctx);
 }
 
-extern "C" int mage_kv_append_f32(const float* qkv, float* kcache, float* vcache, int M, int C, int pos, int Lmax,
+extern "C" int mage_kv_append_f32(mage_ctx* ctx, const float* qkv, float* kcache, float* vcache, int M, int C, int pos, int Lmax,
                                   void* stream) {
+  MAGE_CHECK_CTX(ctx);
   MAGE_CHECK_ARG(M > 0 && C % 4 == 0 && pos >= 0 && pos < Lmax && aligned16(qkv) && aligned16(kcache) && aligned16(vcache));
   const int64_t total = (int64_t)M * (C / 4);
   kv_append_kernel<<<(unsigned)((total + 255) / 256), 256, 0, as_stream(stream)>>>(qkv, kcache, vcache, M, C / 4, pos, Lmax);
-  return mage_post_launch();
+  return mage_post_launch(ctx);
 }
 
-extern "C" int mage_gn_partial_f32(const float* x, double* part, int n_slots, int B, int HW, int C, int groups, void* stream) {
+extern "C" int mage_gn_partial_f32(mage_ctx* ctx, const float* x, double* part, int n_slots, int B, int HW, int C, int groups, void* stream) {
+  MAGE_CHECK_CTX(ctx);
   MAGE_CHECK_ARG(n_slots > 0 && B > 0 && HW > 0 && groups > 0 && C % groups == 0 && (C / groups) % 4 == 0 && aligned16(x));
   gn_partial_kernel<<<(unsigned)((int64_t)n_slots * B * groups), 256, 0, as_stream(stream)>>>(x, part, B, HW, C, C / groups);
-  return mage_post_launch();
+  return mage_post_launch(ctx);
 }
 
-extern "C" int mage_gn_silu_head_f32(const float* x, const double* part, const float* gamma, const float* beta, const float* w,
+extern "C" int mage_gn_silu_head_f32(mage_ctx* ctx, const float* x, const double* part, const float* gamma, const float* beta, const float* w,
                                      const float* bias, float* out, int rows, int B, int HW, int n_slots, int C, int groups,
                                      int cout, float eps, void* stream) {
+  MAGE_CHECK_CTX(ctx);
   MAGE_CHECK_ARG(rows > 0 && B > 0 && HW > 0 && n_slots > 0 && C == 512 && groups == 32 && cout >= 1 && cout <= 8);
   MAGE_CHECK_ARG(aligned16(x) && aligned16(gamma) && aligned16(beta));
   gn_head_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, as_stream(stream)>>>(x, part, gamma, beta, w, bias, out, rows, B, HW, n_slots,
                                                                             cout, eps);
-  return mage_post_launch();
+  return mage_post_launch(ctx);
 }

@@ -125,13 +125,14 @@ __global__ void __launch_bounds__(256) vq_argmin_kernel(const float* __restrict_
 
 }  // namespace
 
-extern "C" int mage_vq_argmin_f32(const float* z, const float* codebook, float* csq_scratch, int64_t* idx, int N, int D, int K,
+extern "C" int mage_vq_argmin_f32(mage_ctx* ctx, const float* z, const float* codebook, float* csq_scratch, int64_t* idx, int N, int D, int K,
                                   void* stream) {
+  MAGE_CHECK_CTX(ctx);
   MAGE_CHECK_ARG(N > 0 && D > 0 && D % VBK == 0 && K > 0 && K % VBN == 0 && aligned16(z) && aligned16(codebook) && csq_scratch);
   cudaStream_t st = as_stream(stream);
   row_sqnorm_kernel<<<(K + 7) / 8, 256, 0, st>>>(codebook, csq_scratch, K, D);
-  int e = mage_post_launch();
+  int e = mage_post_launch(ctx);
   if (e) return e;
   vq_argmin_kernel<<<(N + VBM - 1) / VBM, 256, 0, st>>>(z, codebook, csq_scratch, idx, N, D, K);
-  return mage_post_launch();
+  return mage_post_launch(ctx);
 }

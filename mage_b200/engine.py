@@ -399,7 +399,8 @@ class SamplerEngine:
     """Incremental greedy sampler for one device.  `sd` is MAGE.state_dict() (CUDA fp32)."""
 
     def __init__(self, sd: Dict[str, torch.Tensor], frames_length: int, randomness: bool, padding_idx: int = 0,
-                 temporal_attn: Optional[str] = None, use_cuda_graph: Optional[bool] = None, backend: Optional[str] = None):
+                 temporal_attn: Optional[str] = None, use_cuda_graph: Optional[bool] = None, backend: Optional[str] = None,
+                 use_cids: bool = True, ma_ln: bool = False):
         self.device = sd["visual_token_embedding.weight"].device
         assert self.device.type == "cuda", "SamplerEngine needs CUDA tensors (no CPU path)"
         self.backend = backend or default_backend()
@@ -407,16 +408,18 @@ class SamplerEngine:
         self.L = frames_length
         self.randomness = randomness
         self.padding_idx = padding_idx
+        self.use_cids = use_cids      # False: MAGE+ continuous-latent branch (generate_continuous)
+        self.ma_ln = ma_ln            # TransformerBlock line 93 (ln_q / ln_kv) instead of the shipped line 92
         self.temporal_attn = temporal_attn or os.environ.get("MAGE_TEMPORAL_ATTN", "tma")
         if use_cuda_graph is None:
             use_cuda_graph = os.environ.get("MAGE_CUDA_GRAPH", "1") != "0"
         self.use_cuda_graph = use_cuda_graph
         self.vq = VQVAEEngine({k[len("first_stage_model."):]: v for k, v in sd.items() if k.startswith("first_stage_model.")},
-                              backend=self.backend)
+                              backend=self.backend) if use_cids else None
         g = lambda k: sd[k].contiguous()
         self.sd = sd
-        self.E = g("visual_token_embedding.weight")
-        self.C = self.E.shape[1]
+        self.E = g("visual_token_embedding.weight")      # [K, C] table (use_cids) or Linear weight [C, embed_dim] (MAGE+)
+        self.C = sd["conv.0.weight"].shape[0]
         self.R = sd["H_positional_embedding"].shape[1]
         self.Wc = _pack_conv(sd["conv.0.weight"])
         self.posHW = (sd["H_positional_embedding"] + sd["W_positional_embedding"]).reshape(self.R * self.R, self.C).contiguous()
@@ -458,8 +461,10 @@ class SamplerEngine:
         self.n_streams = max(0, int(os.environ.get("MAGE_STREAMS", "0")))
         if self.backend == "tc":
             # split (fp16 hi/lo) copies of the per-step tensor-core operands
-            ws = {"E": ops.split(self.E), "Wc": ops.split(self.Wc)}
-            for k in ("in_linear.weight", "out.weight"):
+            ws = {"Wc": ops.split(self.Wc)}
+            if use_cids:
+                ws["E"] = ops.split(self.E)
+            for k in ("in_linear.weight", "out.weight") if use_cids else ("in_linear.weight",):
                 ws[p + k] = ops.split(g(p + k))
             for i in range(self.n_blocks):
                 bp = p + f"blocks.{i}."
@@ -475,7 +480,7 @@ class SamplerEngine:
             # in_linear(conv3x3(E[tok]) + pos) as lookups: the conv input is one of K embedding rows per pixel, so
             # table[tap][code] = W_in . Wc[:,:,tap] . E[code] (formed in fp64, stored fp32) replaces a 3x3 512->512 convolution and a
             # 512x512 GEMM per step (86 GFLOP at B=64) by nine 2 KB gathers per pixel; fixed summation order (taps 0..8).
-            if os.environ.get("MAGE_TOKEN_TABLE", "1") != "0":
+            if use_cids and os.environ.get("MAGE_TOKEN_TABLE", "1") != "0":
                 Win = sd[p + "in_linear.weight"].double()
                 Wc = sd["conv.0.weight"].double()                                # [C, C, 3, 3]
                 comp = torch.einsum("oc,cikl->klio", Win, Wc)                      # [3, 3, C_in, C_out]
@@ -559,10 +564,16 @@ class SamplerEngine:
         for i in range(self.n_ma_layers):
             p = f"ma_encoder.blocks.{i}"
             Win, bin_ = sd[p + ".attn.in_proj_weight"], sd[p + ".attn.in_proj_bias"]
-            if x_split is None:
-                x_split = ops.split(x)
+            if self.ma_ln:   # TransformerBlock line 93 (MAGE+): attention reads ln_q(q), ln_kv(kv); the residual stays q
+                x_split = ops.layernorm(x, sd[p + ".ln_q.weight"], sd[p + ".ln_q.bias"],
+                                        out_split=torch.empty(2, M, C, device=x.device, dtype=torch.float16))
+                temb_i = ops.layernorm(temb, sd[p + ".ln_kv.weight"], sd[p + ".ln_kv.bias"])
+            else:
+                temb_i = temb
+                if x_split is None:
+                    x_split = ops.split(x)
             qp, _, _ = ops.gemm_tc(x_split, ws[p + ".q_weight"], bin_[:C].contiguous())
-            kv = ops.gemm(temb, Win[C:], bin_[C:])  # [B*T, 2C]: a few hundred rows, fp32 FFMA kernel
+            kv = ops.gemm(temb_i, Win[C:], bin_[C:])  # [B*T, 2C]: a few hundred rows, fp32 FFMA kernel
             a = torch.empty(2, M, C, device=x.device, dtype=torch.float16)
             ops.mha(qp, kv, kv[:, C:], None, n_outer=B, n_inner=1, n_head=self.n_head, Sq=HW, Sk=T,
                     q_strides=(HW * C, 0, C), k_strides=(T * 2 * C, 0, 2 * C), v_strides=(T * 2 * C, 0, 2 * C),
@@ -814,6 +825,110 @@ class SamplerEngine:
             main.wait_stream(dec_stream)   # join (also required before a graph capture ends)
         if host_video is not None:
             main.wait_stream(self._copy)
+
+    # ------------------------------------------------------------------ MAGE+ branch (use_cids=False): continuous latents
+    def _block_seq_tc(self, i: int, x: torch.Tensor, pos0: int, n_pos: int, B: int, caches, u, h, qkv) -> None:
+        """AxialAttentionBlock (mage_model.py:35-53) over `n_pos` CONSECUTIVE temporal positions pos0 .. pos0+n_pos-1 at once (the
+        reference-order / full-sequence form): x [n_pos*B*R*R, C] rows ordered (position, b, h, w), updated in place.  GEMMs,
+        LayerNorms and the H/W attention see all positions as one batch of images; the temporal block appends and attends
+        position by position (causal: position p reads cache entries 0..p, all of which are final by then)."""
+        sd, ws, C, R = self.sd, self.ws, self.C, self.R
+        p = f"generate_model.blocks.{i}"
+        M = B * R * R
+        ops.layernorm(x, sd[p + ".ln_1.weight"], sd[p + ".ln_1.bias"], out_split=u)
+        ops.gemm_tc(u, ws[p + ".attn.in_proj_weight"], sd[p + ".attn.in_proj_bias"], out=qkv)
+        kind = i % 3
+        if kind == 0:
+            kc, vc = caches[i]
+            for s_ in range(n_pos):
+                ops.temporal_attn_step(qkv[s_ * M:(s_ + 1) * M], kc, vc, None, pos0 + s_, self.scale, out_split=u[:, s_ * M:(s_ + 1) * M])
+        else:
+            assert R == 16, "the full-sequence path uses the 16x16 axial kernel"
+            ops.axial_attn(qkv, None, B=n_pos * B, R=R, n_head=self.n_head, axis=kind, scale=self.scale, out_split=u)
+        ops.gemm_tc(u, ws[p + ".attn.out_proj.weight"], sd[p + ".attn.out_proj.bias"], residual=x, out=x)
+        ops.layernorm(x, sd[p + ".ln_2.weight"], sd[p + ".ln_2.bias"], out_split=u)
+        ops.gemm_tc(u, ws[p + ".mlp.c_fc.weight"], sd[p + ".mlp.c_fc.bias"], act=ACT_QUICKGELU, want=(), out_split=h)
+        ops.gemm_tc(h, ws[p + ".mlp.c_proj.weight"], sd[p + ".mlp.c_proj.bias"], residual=x, out=x)
+
+    def generate_continuous(self, z0: torch.Tensor, text: torch.Tensor, speed: Optional[torch.Tensor] = None,
+                            noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """MAGE+ sampling between the two first-stage calls (mage_model.py:642-689 with use_cids=False): z0 [B,c,R,R] latents of
+        frame 0 -> predicted latents [B, L-1, c, R, R].
+
+        The continuous head normalises over ALL L-1 temporal slots (GroupNorm over [C/32, L-1, H, W], :349-354,386-388), including
+        the not-yet-generated slots that the reference pre-fills with frame 0's embedding (:670): slot j's hidden state still
+        depends only on slots <= j (causal), but the prediction of slot i at iteration i needs every slot's hidden state.  So the
+        one-position-per-step KV-cache form of the VQ path is NOT equivalent here; what is: at iteration i only slots >= i
+        changed since iteration i-1 (slot i's input became the real prediction), so the SUFFIX i..L-2 is re-evaluated through the
+        six blocks in full-sequence form against the K/V cache of the unchanged prefix, per-slot GroupNorm partial sums of the
+        prefix are kept, and the head is evaluated for slot i only (all slots at the last iteration).  (L-1)L/2 position passes
+        instead of the reference's (L-1)L, each on a batch of (suffix x B) images -- bit-for-bit the same dataflow otherwise."""
+        assert not self.use_cids and self.backend == "tc", "the MAGE+ branch runs on the tensor-core back end"
+        assert z0.is_cuda and text.is_cuda
+        sd, ws, C, R, L = self.sd, self.ws, self.C, self.R, self.L
+        p = "generate_model."
+        B, c = z0.shape[0], z0.shape[1]
+        T = text.shape[1]
+        M = B * R * R
+        F_ = L - 1                                                   # slots (frames to predict); slot f sits at temporal position f+1
+        dev = self.device
+        We, be = self.E, sd["visual_token_embedding.bias"]
+        Wo = sd[p + "out.2.weight"].reshape(sd[p + "out.2.weight"].shape[0], C).contiguous()
+        bo = sd[p + "out.2.bias"]
+        gnw, gnb = sd[p + "out.0.weight"], sd[p + "out.0.bias"]
+
+        def features(lat_rows: torch.Tensor):
+            """latents [M, c] (rows (b,h,w)) -> Linear embed -> 3x3 conv + H/W pos: (fp32 [M,C], split [2,M,C])."""
+            emb = ops.gemm(lat_rows, We, be)                          # K = c = 4: FFMA kernel
+            o, f, _ = ops.conv2d_tc(ops.split(emb).view(2, B, R, R, C), ws["Wc"], None, pad=(1, 1), residual=self.posHW, res_mode=3,
+                                    want=("f32", "split"))
+            return o.view(M, C), f.view(2, M, C)
+
+        if noise is None and self.randomness:
+            raise AssertionError("randomness=True needs the N(0,1) noise [B,64,R,R]")
+        z_rows = z0.permute(0, 2, 3, 1).reshape(M, c).contiguous().float()
+        f0, f0_split = features(z_rows)
+        temb, _ = self._text_encoder(text)
+        anchor = self._ma_encoder_tc(f0, f0_split, temb, B, T).view(B, R, R, C)
+        if noise is not None and self.randomness:
+            anchor = self._adain_tc(anchor, noise, B)
+        if speed is not None:
+            ops.add_scaled_vec(anchor, speed, sd["speed_embedding"].view(-1))
+        caches = {i: (torch.empty(M, L, C, device=dev, dtype=torch.float32), torch.empty(M, L, C, device=dev, dtype=torch.float32))
+                  for i in range(self.n_blocks) if i % 3 == 0}
+        # temporal position 0 = the motion anchor: one pass, fills cache entry 0
+        x0, _, _ = ops.gemm_tc(ops.split(anchor.view(M, C)), ws[p + "context_linear.weight"], self.bias_ctx0)
+        u1 = torch.empty(2, M, C, device=dev, dtype=torch.float16)
+        h1 = torch.empty(2, M, 4 * C, device=dev, dtype=torch.float16)
+        q1 = torch.empty(M, 3 * C, device=dev, dtype=torch.float32)
+        for i in range(self.n_blocks):
+            self._block_seq_tc(i, x0, 0, 1, B, caches, u1, h1, q1)
+        del x0, u1, h1, q1
+        hidden = torch.empty(F_, M, C, device=dev, dtype=torch.float32)           # final hidden state of every slot
+        part = torch.empty(F_, B, 32, 2, device=dev, dtype=torch.float64)         # GroupNorm partial sums per slot
+        f_real_split = f0_split                                                   # features of the slot that just became real
+        pred = None
+        for i in range(F_):
+            n_s = F_ - i
+            x = hidden[i:].view(n_s * M, C)
+            # in_linear (+ T_pos of the slot): slot i reads the newest real features, the later slots frame 0's (mage_model.py:670)
+            for s_ in range(n_s):
+                ops.gemm_tc(f_real_split if s_ == 0 else f0_split, ws[p + "in_linear.weight"], self.bias_in_T[i + s_ + 1],
+                            out=x[s_ * M:(s_ + 1) * M])
+            u = torch.empty(2, n_s * M, C, device=dev, dtype=torch.float16)
+            h = torch.empty(2, n_s * M, 4 * C, device=dev, dtype=torch.float16)
+            qkv = torch.empty(n_s * M, 3 * C, device=dev, dtype=torch.float32)
+            for blk in range(self.n_blocks):
+                self._block_seq_tc(blk, x, i + 1, n_s, B, caches, u, h, qkv)
+            del u, h, qkv
+            ops.gn_partial(x, part[i:], B, R * R)
+            if i + 1 < F_:
+                pred_i = ops.gn_silu_head(hidden[i], part, gnw, gnb, Wo, bo, B, R * R)      # [M, c]: slot i only
+                _, f_real_split = features(pred_i)
+            else:
+                pred = ops.gn_silu_head(hidden.view(F_ * M, C), part, gnw, gnb, Wo, bo, B, R * R)   # every slot (mage_model.py:689)
+        ops.check_flag(dev)
+        return pred.view(F_, B, R, R, -1).permute(1, 0, 4, 2, 3).contiguous()
 
     def _frame_to_host(self, video: torch.Tensor, host_video: Optional[torch.Tensor], f: int) -> None:
         """Queue the D2H copy of frame f (one contiguous [B,C,H,W] block) on the copy stream, after the work queued so far."""

@@ -145,23 +145,24 @@ class TransformerTextEncoder(ParamTree):
 
 
 class MAEncoder(ParamTree):
-    """mage_model.py:104-117 parameter layout."""
+    """mage_model.py:104-117 parameter layout.  `ln_qkv` (additive, default False = the shipped line 92) selects TransformerBlock
+    line 93 -- `x = q + attn(ln_q(q), ln_kv(k), ln_kv(v))` -- which the reference asks MAGE+ users to enable by editing the
+    source (mage_model.py:92-93); here it is a config switch (`ma_config.params.ln_qkv: true` in config/mage+_*.yaml)."""
 
-    def __init__(self, layers, d_model, dropout=0.1):
+    def __init__(self, layers, d_model, dropout=0.1, ln_qkv=False):
         super().__init__(_strip(_ma_spec(layers, d_model), "ma_encoder."), seed=22)
-        self.layers, self.d_model = layers, d_model
+        self.layers, self.d_model, self.ln_qkv = layers, d_model, bool(ln_qkv)
 
 
 class FlatAxialDecoder(ParamTree):
-    """mage_model.py:317-390 parameter layout (use_cids=True head)."""
+    """mage_model.py:317-390 parameter layout: `out` = Linear(model_channels, K) for use_cids=True, GroupNorm(32) -> SiLU ->
+    1x1x1 Conv3d(model_channels, out_channels) (keys out.0.*, out.2.*) for the MAGE+ continuous head (:349-354)."""
 
     def __init__(self, in_channels, model_channels, out_channels, frames_length, layers, context_channels=None,
                  use_cids=True, dropout=0.1):
-        if not use_cids:
-            raise NotImplementedError("MAGE+ continuous-latent head (use_cids=False) is not on the VQ sampling path (SURVEY.md F6, N1)")
         super().__init__(_strip(_decoder_spec(in_channels, model_channels, out_channels, frames_length, layers,
-                                              context_channels or in_channels), "generate_model."), seed=23)
-        self.frames_length, self.layers = frames_length, layers
+                                              context_channels or in_channels, use_cids), "generate_model."), seed=23)
+        self.frames_length, self.layers, self.use_cids = frames_length, layers, use_cids
 
 
 def _full_spec_subset(params_like: dict, prefix: str) -> syn.Spec:
@@ -186,8 +187,8 @@ def _ma_spec(layers, d_model) -> syn.Spec:
     return _full_spec_subset(p, "ma_encoder.")
 
 
-def _decoder_spec(in_channels, model_channels, out_channels, frames_length, layers, context_channels) -> syn.Spec:
-    p = _template()
+def _decoder_spec(in_channels, model_channels, out_channels, frames_length, layers, context_channels, use_cids=True) -> syn.Spec:
+    p = _template() if use_cids else syn.model_params("caterv2plus")
     p["ma_config"]["params"].update(d_model=context_channels)
     p["generate_decoder_config"]["params"].update(in_channels=in_channels, model_channels=model_channels,
                                                   out_channels=out_channels, frames_length=frames_length, layers=layers)
@@ -201,11 +202,15 @@ class MAGE(_EngineOwner):
                  frames_length: int, image_resolution: int, vision_width: int, dropout: float = 0.1, use_cids=False,
                  randomness=False, alpha=0., beta=1., v_kl=0., auto_beta=False):
         super().__init__()
-        if not use_cids:
-            raise NotImplementedError("use_cids=False (MAGE+, AutoencoderKL first stage) is outside this path: parity unpinned (SURVEY.md F6)")
         self.frames_length, self.image_resolution, self.vision_width = frames_length, image_resolution, vision_width
         self.dropout, self.use_cids, self.randomness, self.codebook_size = dropout, use_cids, randomness, codebook_size
-        self.first_stage_model = instantiate_from_config(first_stage_config).eval()
+        try:
+            self.first_stage_model = instantiate_from_config(first_stage_config).eval()
+        except ImportError as e:
+            # MAGE+ yamls name latent-diffusion's AutoencoderKL (requirements.txt:22, un-vendored): the first stage is a pluggable
+            # torch module taken as given -- any class with .embed_dim, .encode(x) -> Tensor | object with .sample(), .decode(z)
+            raise ImportError(f"cannot import the first stage {first_stage_config.get('target')!r} ({e}); for use_cids=False install "
+                              "it or point first_stage_config.target at a module with encode()/decode()/embed_dim") from e
         for prm in self.first_stage_model.parameters():
             prm.requires_grad = False
         self.text_encoder = instantiate_from_config(text_encoder_config)
@@ -213,8 +218,12 @@ class MAGE(_EngineOwner):
         self.generate_model = instantiate_from_config(
             generate_decoder_config, {"use_cids": use_cids, "dropout": dropout, "context_channels": ma_config["params"]["d_model"]})
         d, R = vision_width, image_resolution
-        top: syn.Spec = [("visual_token_embedding.weight", (codebook_size, d), "normal:0.02"),
-                         ("conv.0.weight", (d, d, 3, 3), "conv"),
+        if use_cids:
+            emb: syn.Spec = [("visual_token_embedding.weight", (codebook_size, d), "normal:0.02")]
+        else:   # nn.Linear(first_stage_model.embed_dim, vision_width), mage_model.py:482-483
+            emb = [("visual_token_embedding.weight", (d, self.first_stage_model.embed_dim), "normal:0.02"),
+                   ("visual_token_embedding.bias", (d,), "bias")]
+        top: syn.Spec = emb + [("conv.0.weight", (d, d, 3, 3), "conv"),
                          ("speed_embedding", (1, d), f"normal:{d ** -0.5}"),
                          ("H_positional_embedding", (1, R, 1, d), f"normal:{d ** -0.5}"),
                          ("W_positional_embedding", (1, 1, R, d), f"normal:{d ** -0.5}")]
@@ -241,21 +250,30 @@ class MAGE(_EngineOwner):
         if not self._engine_valid():
             from .engine import SamplerEngine
             self._engine = SamplerEngine(self._cuda_state(), self.frames_length, self.randomness,
-                                         padding_idx=getattr(self.text_encoder, "padding_idx", 0))
+                                         padding_idx=getattr(self.text_encoder, "padding_idx", 0), use_cids=self.use_cids,
+                                         ma_ln=getattr(self.ma_encoder, "ln_qkv", False))
             self._engine_sig = self._signature()
         return self._engine
 
+    def get_first_stage_encoding(self, encoder_posterior):
+        """mage_model.py:542-549: a posterior object is sampled, a tensor is taken as is."""
+        if isinstance(encoder_posterior, torch.Tensor):
+            return encoder_posterior
+        if hasattr(encoder_posterior, "sample"):
+            return encoder_posterior.sample()
+        raise NotImplementedError(f"encoder_posterior of type '{type(encoder_posterior)}' not yet implemented")
+
     @torch.no_grad()
     def first_stage_encode(self, x):
-        """mage_model.py:530-540: [B,T,C,H,W] -> [B,T,h,w] int64."""
-        out = self.first_stage_model.encode(x.reshape(-1, *x.shape[-3:]))
-        return out.view(*x.shape[:-3], *out.shape[1:])
+        """mage_model.py:530-540: [B,T,C,H,W] -> [B,T,h,w] int64 (use_cids) / [B,T,c,h,w] latents."""
+        out = self.get_first_stage_encoding(self.first_stage_model.encode(x.reshape(-1, *x.shape[-3:])))
+        return out.view(*x.shape[:-3], *out.shape[1:]).contiguous().detach()
 
     @torch.no_grad()
     def first_stage_decode(self, x):
-        """mage_model.py:551-567: [B,T,h,w] -> [B,T,C,H,W]."""
-        out = self.first_stage_model.decode(x.reshape(-1, *x.shape[-2:]))
-        return out.view(*x.shape[:2], *out.shape[1:])
+        """mage_model.py:551-567: [B,T,h,w] (use_cids) / [B,T,c,h,w] -> [B,T,C,H,W]."""
+        out = self.first_stage_model.decode(x.reshape(-1, *x.shape[(-2 if self.use_cids else -3):]))
+        return out.view(*x.shape[:2], *out.shape[1:]).contiguous().detach()
 
     @torch.no_grad()
     def autoregressive_generate(self, batch, noise: Optional[torch.Tensor] = None, to_host: bool = False):
@@ -275,10 +293,24 @@ class MAGE(_EngineOwner):
         images0 = batch["images"][:, 0].to(dev, non_blocking=True)
         text = batch["text"].to(dev, non_blocking=True)
         speed = batch["speed"].to(dev, non_blocking=True).float() if "speed" in batch else None
+        z0 = None
+        if not self.use_cids:
+            # the posterior is sampled BEFORE the AdaIN noise is drawn, like the reference (mage_model.py:642 then :661)
+            z0 = self.first_stage_encode(images0.unsqueeze(1))[:, 0].float().contiguous()
         if self.randomness:
             if noise is None:
                 noise = torch.randn([text.shape[0], 64, self.image_resolution, self.image_resolution])
             noise = noise.to(dev, non_blocking=True).float().contiguous()
+        if not self.use_cids:
+            # MAGE+ (mage_model.py:646,684,689): continuous latents between the two first-stage calls; no tokens, no argmax
+            latents = eng.generate_continuous(z0, text, speed, noise)
+            self.last_latents, self.last_tokens, self.last_tok0 = latents, None, None
+            video = torch.cat([images0.unsqueeze(1).float(), self.first_stage_decode(latents).float()], 1)
+            if to_host:
+                host = torch.empty(video.shape, dtype=torch.float32, pin_memory=True)
+                host.copy_(video)
+                return host
+            return video
         video, tokens, tok0 = eng.generate(images0, text, speed, noise, to_host=to_host)
         self.last_tokens, self.last_tok0 = tokens, tok0
         if to_host:

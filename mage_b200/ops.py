@@ -29,6 +29,11 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def _ctx() -> int:
+    """Library handle of the CURRENT CUDA device (one mage_ctx per device, created on first use)."""
+    return _lib.ctx(torch.cuda.current_device())
+
+
 # Optional per-launch CUDA-event instrumentation (bench.py's roofline / breakdown leg): when PROFILE is a
 # list, every wrapper appends (kind, algorithmic flops or bytes, start_event, end_event) around its launch.
 PROFILE = None
@@ -52,7 +57,7 @@ class _Prof:
 
 
 def launch_count() -> int:
-    return int(_lib.lib().mage_launch_count())
+    return int(_lib.lib().mage_launch_count(_ctx()))
 
 
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, out: Optional[torch.Tensor] = None,
@@ -68,7 +73,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     if residual is not None:
         assert residual.dim() == 2 and residual.shape[1] == N and residual.stride(1) == 1
     with _Prof("gemm", 2.0 * M * N * K):
-        check(_lib.lib().mage_gemm_f32(_p(a), a.stride(0), _p(_f32(w)), w.stride(0), _p(bias), _p(residual),
+        check(_lib.lib().mage_gemm_f32(_ctx(), _p(a), a.stride(0), _p(_f32(w)), w.stride(0), _p(bias), _p(residual),
                                        residual.stride(0) if residual is not None else 0, res_mod, _p(out), out.stride(0),
                                        M, N, K, act, int(relu_a), _stream()), "mage_gemm_f32")
     return out
@@ -103,22 +108,22 @@ def check_flag(device) -> None:
 
 def tc_tuning(bn: int = 0, pair: int = -1) -> None:
     """Tile-selection override of the tensor-core kernels (tests / tuning): bn 0|64|128|256, pair -1 auto | 0 | 1."""
-    check(_lib.lib().mage_tc_tuning(bn, pair), "mage_tc_tuning")
+    check(_lib.lib().mage_tc_tuning(_ctx(), bn, pair), "mage_tc_tuning")
 
 
 def pdl(enable: bool) -> None:
     """Programmatic dependent launch for the per-step kernels on/off (see mage_b200.h)."""
-    check(_lib.lib().mage_pdl(int(enable)), "mage_pdl")
+    check(_lib.lib().mage_pdl(_ctx(), int(enable)), "mage_pdl")
 
 
 def tc_nsplit(mode: int = 1) -> None:
     """N-split 256-wide pair tiles of gemm_tc: 0 off, 1 automatic, 2 whenever legal (tests / tuning)."""
-    check(_lib.lib().mage_tc_nsplit(mode), "mage_tc_nsplit")
+    check(_lib.lib().mage_tc_nsplit(_ctx(), mode), "mage_tc_nsplit")
 
 
 def tc_conv_halo(enable: bool = True) -> None:
     """Halo mode of the tensor-core convolutions on/off (tests / tuning)."""
-    check(_lib.lib().mage_tc_conv_halo(int(enable)), "mage_tc_conv_halo")
+    check(_lib.lib().mage_tc_conv_halo(_ctx(), int(enable)), "mage_tc_conv_halo")
 
 
 def _f16(t: torch.Tensor) -> torch.Tensor:
@@ -138,7 +143,7 @@ def split(x: torch.Tensor, relu: bool = False, out: Optional[torch.Tensor] = Non
     if out is None:
         out = torch.empty(2, *x.shape, device=x.device, dtype=torch.float16)
     with _Prof("split", 8.0 * rows * C):
-        check(_lib.lib().mage_split_f32(_p(x), ldx, _p(_f16(out)), rows * C, rows, C, int(relu), _p(flag(x.device)), _stream()),
+        check(_lib.lib().mage_split_f32(_ctx(), _p(x), ldx, _p(_f16(out)), rows * C, rows, C, int(relu), _p(flag(x.device)), _stream()),
               "mage_split_f32")
     return out
 
@@ -148,7 +153,7 @@ def patch_rows_split(x_nchw: torch.Tensor, kw: int, pad: int) -> torch.Tensor:
     n, C, H, W = x_nchw.shape
     out = torch.empty(2, n, H, W, 64, device=x_nchw.device, dtype=torch.float16)
     with _Prof("conv_first", 16.0 * n * H * W * 64):
-        check(_lib.lib().mage_patch_rows_split_f32(_p(_f32(x_nchw)), _p(out), n * H * W * 64, n, C, H, W, kw, pad, _stream()),
+        check(_lib.lib().mage_patch_rows_split_f32(_ctx(), _p(_f32(x_nchw)), _p(out), n * H * W * 64, n, C, H, W, kw, pad, _stream()),
               "mage_patch_rows_split_f32")
     return out
 
@@ -159,7 +164,7 @@ def s2d_pad_split(x: torch.Tensor, relu: bool = False) -> torch.Tensor:
     n, H, W, C = x.shape
     out = torch.empty(2, n, H // 2 + 1, W // 2 + 1, 4 * C, device=x.device, dtype=torch.float16)
     with _Prof("split", 8.0 * out.numel()):
-        check(_lib.lib().mage_s2d_pad_split_f32(_p(_f32(x)), _p(out), out.numel() // 2, n, H, W, C, int(relu), _p(flag(x.device)),
+        check(_lib.lib().mage_s2d_pad_split_f32(_ctx(), _p(_f32(x)), _p(out), out.numel() // 2, n, H, W, C, int(relu), _p(flag(x.device)),
                                                 _stream()), "mage_s2d_pad_split_f32")
     return out
 
@@ -172,7 +177,7 @@ def embedding_split(idx: torch.Tensor, table: torch.Tensor, out: Optional[torch.
     if out is None:
         out = torch.empty(2, *idx.shape, C, device=table.device, dtype=torch.float16)
     with _Prof("embed", 8.0 * rows * C):
-        check(_lib.lib().mage_embedding_split(_p(idx), _p(_f16(table)), K * C, _p(_f16(out)), rows * C, rows, C, _stream()),
+        check(_lib.lib().mage_embedding_split(_ctx(), _p(idx), _p(_f16(table)), K * C, _p(_f16(out)), rows * C, rows, C, _stream()),
               "mage_embedding_split")
     return out
 
@@ -199,7 +204,7 @@ def gemm_tc(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = Non
     if residual is not None:
         assert residual.dim() == 2 and residual.shape[1] == N and residual.stride(1) == 1
     with _Prof("gemm", 2.0 * M * N * K):
-        check(_lib.lib().mage_gemm_tc(_p(a), K, M * K, _p(w), K, N * K, _p(bias), _p(residual),
+        check(_lib.lib().mage_gemm_tc(_ctx(), _p(a), K, M * K, _p(w), K, N * K, _p(bias), _p(residual),
                                       residual.stride(0) if residual is not None else 0, res_mod, _p(out), _p(out_split),
                                       _p(out_split_relu), N, M * N, M, N, K, act, _p(flag(dev)), _stream()), "mage_gemm_tc")
     return out, out_split, out_split_relu
@@ -233,7 +238,7 @@ def conv2d_tc(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = N
         res_mode = 1
     img = Hfull * Wfull * Cout
     with _Prof("conv", 2.0 * n * Hout * Wout * Cout * KH * KW * Cin):
-        check(_lib.lib().mage_conv2d_tc(_p(x), n * Hin * Win * Cin, _p(w), Cout * KH * KW * Cin, _p(bias), _p(residual), _p(out),
+        check(_lib.lib().mage_conv2d_tc(_ctx(), _p(x), n * Hin * Win * Cin, _p(w), Cout * KH * KW * Cin, _p(bias), _p(residual), _p(out),
                                         _p(out_split), _p(out_split_relu), n * img, n, Hin, Win, Cin, Hout, Wout, Cout, KH, KW,
                                         pad[0], pad[1], res_mode, act, sy, sx, oy, ox, Hfull, Wfull, img, passes, _p(flag(dev)),
                                         _stream()), "mage_conv2d_tc")
@@ -251,7 +256,7 @@ def conv2d_tc_pixel_head(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.
     assert Cin == Cin2 and head_w.shape == (head_b.numel(), Cout) and head_w.is_contiguous()
     Hout, Wout = Hin + 2 * pad[0] - KH + 1, Win + 2 * pad[1] - KW + 1
     with _Prof("conv", 2.0 * n * Hout * Wout * Cout * (KH * KW * Cin + head_b.numel())):
-        check(_lib.lib().mage_conv2d_tc_pixel_head(_p(x), n * Hin * Win * Cin, _p(w), Cout * KH * KW * Cin, _p(bias), _p(residual),
+        check(_lib.lib().mage_conv2d_tc_pixel_head(_ctx(), _p(x), n * Hin * Win * Cin, _p(w), Cout * KH * KW * Cin, _p(bias), _p(residual),
                                                    n, Hin, Win, Cin, Hout, Wout, Cout, KH, KW, pad[0], pad[1], res_mode,
                                                    _p(head_w), _p(head_b), head_b.numel(), _p(out), out_img_stride, passes,
                                                    _p(flag(x.device)), _stream()), "mage_conv2d_tc_pixel_head")
@@ -281,7 +286,7 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     if residual is not None and res_mode == 0:
         res_mode = 1
     with _Prof("conv", 2.0 * n * Hout * Wout * Cout * KH * KW * Cin):
-        check(_lib.lib().mage_conv2d_nhwc_f32(_p(_f32(x)), _p(_f32(w)), _p(bias), _p(residual), _p(out), n, Hin, Win, Cin,
+        check(_lib.lib().mage_conv2d_nhwc_f32(_ctx(), _p(_f32(x)), _p(_f32(w)), _p(bias), _p(residual), _p(out), n, Hin, Win, Cin,
                                               Hout, Wout, Cout, KH, KW, stride, pad[0], pad[1], int(in_up), res_mode,
                                               int(relu_in), act, sy, sx, oy, ox, Hfull, Wfull, out_img_stride, _stream()),
               "mage_conv2d_nhwc_f32")
@@ -295,7 +300,7 @@ def conv2d_first(x_nchw: torch.Tensor, w_t: torch.Tensor, bias: Optional[torch.T
     Wout = (W + 2 * pad - kw) // stride + 1
     out = torch.empty(n, Hout, Wout, cout, device=x_nchw.device, dtype=torch.float32)
     with _Prof("conv_first", 4.0 * out.numel()):
-        check(_lib.lib().mage_conv2d_first_f32(_p(_f32(x_nchw)), _p(_f32(w_t)), _p(bias), _p(out), n, Cin, H, W, Hout, Wout,
+        check(_lib.lib().mage_conv2d_first_f32(_ctx(), _p(_f32(x_nchw)), _p(_f32(w_t)), _p(bias), _p(out), n, Cin, H, W, Hout, Wout,
                                                cout, kh, kw, stride, pad, act, _stream()), "mage_conv2d_first_f32")
     return out
 
@@ -304,7 +309,7 @@ def conv1x1_tanh_nchw(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, out:
     """x NHWC [N,H,W,Cin] -> tanh(conv1x1(relu(x))) written planar into `out` (image stride in elements)."""
     n, H, W, Cin = x.shape
     with _Prof("conv1x1_tanh", 4.0 * x.numel()):
-        check(_lib.lib().mage_conv1x1_tanh_nchw_f32(_p(_f32(x)), _p(_f32(w)), _p(bias), _p(out), n, H * W, Cin, w.shape[0],
+        check(_lib.lib().mage_conv1x1_tanh_nchw_f32(_ctx(), _p(_f32(x)), _p(_f32(w)), _p(bias), _p(out), n, H * W, Cin, w.shape[0],
                                                     out_img_stride, _stream()), "mage_conv1x1_tanh_nchw_f32")
 
 
@@ -312,7 +317,7 @@ def maxpool2x2(x: torch.Tensor) -> torch.Tensor:
     n, H, W, C = x.shape
     out = torch.empty(n, H // 2, W // 2, C, device=x.device, dtype=torch.float32)
     with _Prof("maxpool", 5.0 * x.numel()):
-        check(_lib.lib().mage_maxpool2x2_nhwc_f32(_p(_f32(x)), _p(out), n, H, W, C, _stream()), "mage_maxpool2x2_nhwc_f32")
+        check(_lib.lib().mage_maxpool2x2_nhwc_f32(_ctx(), _p(_f32(x)), _p(out), n, H, W, C, _stream()), "mage_maxpool2x2_nhwc_f32")
     return out
 
 
@@ -325,7 +330,7 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     if out is None and out_split is None:
         out = torch.empty_like(x)
     with _Prof("layernorm", 8.0 * x.numel()):
-        check(_lib.lib().mage_layernorm_f32(_p(_f32(x)), _p(gamma), _p(beta), _p(out), _p(out_split), rows * C, _p(flag(x.device)),
+        check(_lib.lib().mage_layernorm_f32(_ctx(), _p(_f32(x)), _p(gamma), _p(beta), _p(out), _p(out_split), rows * C, _p(flag(x.device)),
                                             rows, C, eps, _stream()), "mage_layernorm_f32")
     return out if out_split is None else out_split
 
@@ -335,7 +340,7 @@ def mha(q, k, v, out, *, n_outer, n_inner, n_head, Sq, Sk, q_strides, k_strides,
     """Strided SDPA core (head_dim 32).  *_strides = (outer, inner, seq) in elements; q/k/v/out may be
     views into one packed qkv buffer (pass the view: its data_ptr carries the column offset)."""
     with _Prof("mha", 0.0):
-        check(_lib.lib().mage_mha_f32(_p(q), _p(k), _p(v), _p(out), n_outer, n_inner, n_head, Sq, Sk, *q_strides, *k_strides,
+        check(_lib.lib().mage_mha_f32(_ctx(), _p(q), _p(k), _p(v), _p(out), n_outer, n_inner, n_head, Sq, Sk, *q_strides, *k_strides,
                                       *v_strides, *o_strides, _p(key_len), scale, _p(out_split),
                                       out_split.numel() // 2 if out_split is not None else 0, _p(flag(q.device)), _stream()),
               "mage_mha_f32")
@@ -345,7 +350,7 @@ def axial_attn(qkv: torch.Tensor, out: Optional[torch.Tensor], *, B: int, R: int
                out_split: Optional[torch.Tensor] = None) -> None:
     """H (axis=1) / W (axis=2) axial attention of one temporal position: qkv [B*R*R, 3C] -> out [B*R*R, C] and/or split."""
     with _Prof("axial_attn", 4.0 * qkv.numel() + 4.0 * qkv.numel() / 3):
-        check(_lib.lib().mage_axial_attn_f32(_p(_f32(qkv)), _p(out), _p(out_split),
+        check(_lib.lib().mage_axial_attn_f32(_ctx(), _p(_f32(qkv)), _p(out), _p(out_split),
                                              out_split.numel() // 2 if out_split is not None else 0, _p(flag(qkv.device)),
                                              B, R, n_head, axis, scale, _stream()), "mage_axial_attn_f32")
 
@@ -357,7 +362,7 @@ def temporal_attn_step(qkv: torch.Tensor, kcache: torch.Tensor, vcache: torch.Te
     if out_split is not None:   # may be a row range of a larger split tensor: the lo plane sits stride(0) elements after the hi plane
         assert out_split.dtype == torch.float16 and out_split.shape[0] == 2 and out_split[0].is_contiguous()
     with _Prof("temporal_attn", 8.0 * M * (pos + 1) * kcache.shape[2]):
-        check(_lib.lib().mage_temporal_attn_step_f32(_p(_f32(qkv)), _p(kcache), _p(vcache), _p(out), _p(out_split),
+        check(_lib.lib().mage_temporal_attn_step_f32(_ctx(), _p(_f32(qkv)), _p(kcache), _p(vcache), _p(out), _p(out_split),
                                                      out_split.stride(0) if out_split is not None else 0, _p(flag(qkv.device)),
                                                      M, pos, Lmax, scale, _stream()), "mage_temporal_attn_step_f32")
 
@@ -365,7 +370,7 @@ def temporal_attn_step(qkv: torch.Tensor, kcache: torch.Tensor, vcache: torch.Te
 def kv_append(qkv: torch.Tensor, kcache: torch.Tensor, vcache: torch.Tensor, pos: int) -> None:
     M, C3 = qkv.shape
     with _Prof("kv_append", 0.0):
-        check(_lib.lib().mage_kv_append_f32(_p(_f32(qkv)), _p(kcache), _p(vcache), M, C3 // 3, pos, kcache.shape[1], _stream()),
+        check(_lib.lib().mage_kv_append_f32(_ctx(), _p(_f32(qkv)), _p(kcache), _p(vcache), M, C3 // 3, pos, kcache.shape[1], _stream()),
               "mage_kv_append_f32")
 
 
@@ -377,7 +382,7 @@ def vq_argmin(z: torch.Tensor, codebook: torch.Tensor, out: Optional[torch.Tenso
         out = torch.empty(N, device=z.device, dtype=torch.int64)
     scratch = torch.empty(K, device=z.device, dtype=torch.float32)
     with _Prof("vq_argmin", 4.0 * N * D):
-        check(_lib.lib().mage_vq_argmin_f32(_p(_f32(z)), _p(_f32(codebook)), _p(scratch), _p(out), N, D, K, _stream()),
+        check(_lib.lib().mage_vq_argmin_f32(_ctx(), _p(_f32(z)), _p(_f32(codebook)), _p(scratch), _p(out), N, D, K, _stream()),
               "mage_vq_argmin_f32")
     return out
 
@@ -387,7 +392,7 @@ def argmax_rows(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Te
     if out is None:
         out = torch.empty(rows, device=x.device, dtype=torch.int64)
     with _Prof("argmax", 4.0 * rows * N):
-        check(_lib.lib().mage_argmax_rows_f32(_p(x), x.stride(0), _p(out), rows, N, _stream()), "mage_argmax_rows_f32")
+        check(_lib.lib().mage_argmax_rows_f32(_ctx(), _p(x), x.stride(0), _p(out), rows, N, _stream()), "mage_argmax_rows_f32")
     return out
 
 
@@ -397,7 +402,7 @@ def embedding(idx: torch.Tensor, table: torch.Tensor, out: Optional[torch.Tensor
     if out is None:
         out = torch.empty(*idx.shape, C, device=table.device, dtype=torch.float32)
     with _Prof("embed", 8.0 * rows * C):
-        check(_lib.lib().mage_embedding_f32(_p(idx), _p(_f32(table)), _p(out), rows, C, _stream()), "mage_embedding_f32")
+        check(_lib.lib().mage_embedding_f32(_ctx(), _p(idx), _p(_f32(table)), _p(out), rows, C, _stream()), "mage_embedding_f32")
     return out
 
 
@@ -409,7 +414,7 @@ def token_taps(tok: torch.Tensor, table: torch.Tensor, pos_bias: torch.Tensor, b
     kh = int(round(taps ** 0.5))
     assert kh * kh == taps and tok.dtype == torch.int64 and tok.is_contiguous() and out.is_contiguous()
     with _Prof("embed", 4.0 * n * R * R * C * (taps + 2)):
-        check(_lib.lib().mage_token_taps_f32(_p(tok), _p(_f32(table)), _p(_f32(pos_bias)), _p(_f32(bias)), _p(out), n, R, K, C, kh, kh,
+        check(_lib.lib().mage_token_taps_f32(_ctx(), _p(tok), _p(_f32(table)), _p(_f32(pos_bias)), _p(_f32(bias)), _p(out), n, R, K, C, kh, kh,
                                              _stream()), "mage_token_taps_f32")
     return out
 
@@ -423,7 +428,7 @@ def text_embed(text: torch.Tensor, tok_emb, pos_emb, gamma, beta, pad_idx: int, 
     x = torch.empty(B, T, C, device=tok_emb.device, dtype=torch.float32)
     key_len = torch.empty(B, device=tok_emb.device, dtype=torch.int32)
     with _Prof("misc", 0.0):
-        check(_lib.lib().mage_text_embed_f32(_p(text), _p(tok_emb), _p(pos_emb), _p(gamma), _p(beta), _p(x), _p(key_len), B, T, C,
+        check(_lib.lib().mage_text_embed_f32(_ctx(), _p(text), _p(tok_emb), _p(pos_emb), _p(gamma), _p(beta), _p(x), _p(key_len), B, T, C,
                                              pad_idx, eps, tok_emb.shape[0], _p(flag(tok_emb.device)), _stream()), "mage_text_embed_f32")
     return x, key_len
 
@@ -432,7 +437,7 @@ def adain(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float =
     n, H, W, C = x.shape
     out = torch.empty_like(x)
     with _Prof("misc", 0.0):
-        check(_lib.lib().mage_adain_nhwc_f32(_p(_f32(x)), _p(_f32(gamma)), _p(_f32(beta)), _p(out), n, H * W, C, eps, _stream()),
+        check(_lib.lib().mage_adain_nhwc_f32(_ctx(), _p(_f32(x)), _p(_f32(gamma)), _p(_f32(beta)), _p(out), n, H * W, C, eps, _stream()),
               "mage_adain_nhwc_f32")
     return out
 
@@ -440,7 +445,7 @@ def adain(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float =
 def add_scaled_vec(x: torch.Tensor, s: torch.Tensor, vec: torch.Tensor) -> None:
     n, C = x.shape[0], x.shape[-1]
     with _Prof("misc", 0.0):
-        check(_lib.lib().mage_add_scaled_vec_f32(_p(_f32(x)), _p(s), _p(vec), n, x.numel() // (n * C), C, _stream()),
+        check(_lib.lib().mage_add_scaled_vec_f32(_ctx(), _p(_f32(x)), _p(s), _p(vec), n, x.numel() // (n * C), C, _stream()),
               "mage_add_scaled_vec_f32")
 
 
@@ -448,7 +453,7 @@ def nchw_to_nhwc(x: torch.Tensor) -> torch.Tensor:
     n, C, H, W = x.shape
     out = torch.empty(n, H, W, C, device=x.device, dtype=torch.float32)
     with _Prof("misc", 0.0):
-        check(_lib.lib().mage_nchw_to_nhwc_f32(_p(_f32(x)), _p(out), n, C, H * W, _stream()), "mage_nchw_to_nhwc_f32")
+        check(_lib.lib().mage_nchw_to_nhwc_f32(_ctx(), _p(_f32(x)), _p(out), n, C, H * W, _stream()), "mage_nchw_to_nhwc_f32")
     return out
 
 
@@ -458,7 +463,7 @@ def gn_partial(x: torch.Tensor, part: torch.Tensor, B: int, HW: int, groups: int
     n_slots = x.numel() // (B * HW * C)
     assert part.dtype == torch.float64 and part.is_contiguous() and part.numel() == n_slots * B * groups * 2
     with _Prof("misc", 0.0):
-        check(_lib.lib().mage_gn_partial_f32(_p(_f32(x)), _p(part), n_slots, B, HW, C, groups, _stream()), "mage_gn_partial_f32")
+        check(_lib.lib().mage_gn_partial_f32(_ctx(), _p(_f32(x)), _p(part), n_slots, B, HW, C, groups, _stream()), "mage_gn_partial_f32")
 
 
 def gn_silu_head(x: torch.Tensor, part: torch.Tensor, gamma, beta, w: torch.Tensor, bias: torch.Tensor, B: int, HW: int,
@@ -468,6 +473,6 @@ def gn_silu_head(x: torch.Tensor, part: torch.Tensor, gamma, beta, w: torch.Tens
     cout = w.shape[0]
     out = torch.empty(rows, cout, device=x.device, dtype=torch.float32)
     with _Prof("misc", 0.0):
-        check(_lib.lib().mage_gn_silu_head_f32(_p(_f32(x)), _p(part), _p(_f32(gamma)), _p(_f32(beta)), _p(_f32(w)), _p(_f32(bias)),
+        check(_lib.lib().mage_gn_silu_head_f32(_ctx(), _p(_f32(x)), _p(part), _p(_f32(gamma)), _p(_f32(beta)), _p(_f32(w)), _p(_f32(bias)),
                                                _p(out), rows, B, HW, part.shape[0], C, 32, cout, eps, _stream()), "mage_gn_silu_head_f32")
     return out

@@ -42,22 +42,54 @@ def model_params(family: str = "caterv2", frames_length: int = 10, randomness: O
     elif family == "mnist":
         fs = dict(input_dim=1, dim=256, down_ratio=4, K=512)
         vocab, ctx, rnd = 30, 32, False
+    elif family == "caterv2plus":
+        # MAGE+ (config/mage+_caterv2.yaml): use_cids=False, 4-channel continuous latents.  The shipped first stage is
+        # latent-diffusion's AutoencoderKL (not vendored); PatchLatentAE below stands in for it in tests / goldens.
+        fs = dict(in_channels=3, embed_dim=4, down_ratio=8, seed=5)
+        vocab, ctx, rnd = 50, 38, True
     else:
         raise KeyError(family)
     if randomness is not None:
         rnd = randomness
+    plus = family == "caterv2plus"
     return dict(
         codebook_size=512, frames_length=frames_length, image_resolution=16, vision_width=512,
-        dropout=0.1, use_cids=True, randomness=rnd, alpha=0.0001, beta=0.0005,
-        first_stage_config=dict(target="modules.vqvae_model.VectorQuantizedVAE", params=dict(ckpt_path=None, **fs)),
+        dropout=0.1, use_cids=not plus, randomness=rnd, alpha=0.0001, beta=0.0005,
+        first_stage_config=(dict(target="mage_b200.synthetic.PatchLatentAE", params=dict(**fs)) if plus else
+                            dict(target="modules.vqvae_model.VectorQuantizedVAE", params=dict(ckpt_path=None, **fs))),
         text_encoder_config=dict(target="modules.mage_model.TransformerTextEncoder",
                                  params=dict(vocab_size=vocab, context_length=ctx, transformer_width=512,
                                              transformer_layers=2, output_dim=512, padding_idx=0, dropout=0.1)),
         ma_config=dict(target="modules.mage_model.MAEncoder", params=dict(layers=1, d_model=512)),
         generate_decoder_config=dict(target="modules.mage_model.FlatAxialDecoder",
-                                     params=dict(in_channels=512, out_channels=512, model_channels=512,
+                                     params=dict(in_channels=512, out_channels=4 if plus else 512, model_channels=512,
                                                  frames_length=frames_length, layers=6)),
     )
+
+
+class PatchLatentAE(torch.nn.Module):
+    """Stand-in first stage for the MAGE+ branch in tests and goldens: a seeded linear patch autoencoder with the interface the
+    reference expects of `first_stage_model` when use_cids=False (mage_model.py:530-567): `.embed_dim`, `.encode(x[N,C,H,W]) ->
+    Tensor [N,embed_dim,H/r,W/r]` (the reference also accepts an object with `.sample()`), `.decode(z) -> [N,C,H,W]`.
+    Plain PyTorch on purpose: the real first stage (latent-diffusion's AutoencoderKL) is an external module that this repo
+    treats as given -- parity unpinned for it, pinned for everything between the two calls."""
+
+    def __init__(self, in_channels: int = 3, embed_dim: int = 4, down_ratio: int = 8, seed: int = 5):
+        super().__init__()
+        g = torch.Generator(device="cpu")
+        g.manual_seed(seed)
+        k = down_ratio
+        self.embed_dim, self.down_ratio = embed_dim, down_ratio
+        self.register_buffer("enc_w", torch.randn(embed_dim, in_channels, k, k, generator=g) * (2.0 / (k * math.sqrt(in_channels))))
+        self.register_buffer("dec_w", torch.randn(embed_dim, in_channels, k, k, generator=g) * 0.5)
+
+    @torch.no_grad()
+    def encode(self, x):
+        return torch.nn.functional.conv2d(x.float(), self.enc_w, stride=self.down_ratio)
+
+    @torch.no_grad()
+    def decode(self, z):
+        return torch.tanh(torch.nn.functional.conv_transpose2d(z.float(), self.dec_w, stride=self.down_ratio))
 
 
 # --------------------------------------------------------------------------------------
@@ -153,8 +185,9 @@ def mage_param_spec(params: dict) -> Spec:
     R = params["image_resolution"]
     s: Spec = []
     fs = params["first_stage_config"]["params"]
-    for n, shp, kind in vqvae_param_spec(**{k: v for k, v in fs.items() if k != "ckpt_path"}):
-        s.append(("first_stage_model." + n, shp, kind))
+    if params["use_cids"]:
+        for n, shp, kind in vqvae_param_spec(**{k: v for k, v in fs.items() if k != "ckpt_path"}):
+            s.append(("first_stage_model." + n, shp, kind))
 
     te = params["text_encoder_config"]["params"]
     w = te["transformer_width"]
@@ -204,12 +237,19 @@ def mage_param_spec(params: dict) -> Spec:
         s.append((p + ".mlp.c_proj.weight", (mc, 4 * mc), f"normal:{proj_std}"))
         s.append((p + ".mlp.c_proj.bias", (mc,), "bias"))
         _ln(s, p + ".ln_2", mc)
-    if not params["use_cids"]:
-        raise NotImplementedError("MAGE+ (use_cids=False) head is outside the VQ hot path (SURVEY.md F6)")
-    s.append(("generate_model.out.weight", (gd["out_channels"], mc), f"normal:{mc ** -0.5}"))
-    s.append(("generate_model.out.bias", (gd["out_channels"],), "bias"))
+    if params["use_cids"]:
+        s.append(("generate_model.out.weight", (gd["out_channels"], mc), f"normal:{mc ** -0.5}"))
+        s.append(("generate_model.out.bias", (gd["out_channels"],), "bias"))
+        s.append(("visual_token_embedding.weight", (K, d), "normal:1.0"))
+    else:
+        # MAGE+ head: GroupNorm(32, mc) -> SiLU -> Conv3d(mc, out, 1) (mage_model.py:349-354; zero-initialised in the reference,
+        # random here so that the autoregression is exercised); Linear embed of the latents (:482-483)
+        _ln(s, "generate_model.out.0", mc)
+        s.append(("generate_model.out.2.weight", (gd["out_channels"], mc, 1, 1, 1), f"normal:{mc ** -0.5}"))
+        s.append(("generate_model.out.2.bias", (gd["out_channels"],), "bias"))
+        s.append(("visual_token_embedding.weight", (d, fs["embed_dim"]), "normal:0.5"))
+        s.append(("visual_token_embedding.bias", (d,), "bias"))
 
-    s.append(("visual_token_embedding.weight", (K, d), "normal:1.0"))
     s.append(("conv.0.weight", (d, d, 3, 3), "conv"))
     s.append(("speed_embedding", (1, d), f"normal:{d ** -0.5}"))
     s.append(("H_positional_embedding", (1, R, 1, d), f"normal:{d ** -0.5}"))
@@ -279,6 +319,10 @@ def make_vqvae_state_dict(fs_params: dict, seed: int = 7, conditioned: bool = Tr
 def make_mage_state_dict(params: dict, seed: int = 11, vq_seed: int = 7, conditioned: bool = True) -> Dict[str, torch.Tensor]:
     """Synthetic MAGE checkpoint `state_dict` (sampling subset) for `params`."""
     sd = make_state_dict(mage_param_spec(params), seed)
+    if not params["use_cids"]:
+        for k, v in PatchLatentAE(**params["first_stage_config"]["params"]).state_dict().items():
+            sd["first_stage_model." + k] = v
+        return sd
     fs = make_vqvae_state_dict(params["first_stage_config"]["params"], vq_seed, conditioned)
     for k, v in fs.items():
         sd["first_stage_model." + k] = v
@@ -313,7 +357,7 @@ def make_batch(params: dict, batch: int, seed: int = 1234, text_len: int = 20, p
     'images' f32 [B,frames,C,R,R], 'text' i64 [B,T] = [CLS]=1 ... [SEP]=2 (pad 0), 'speed' f32 [B].
     Only images[:,0] is read by sampling (mage_model.py:642,691)."""
     fs = params["first_stage_config"]["params"]
-    C, res = fs["input_dim"], params["image_resolution"] * fs["down_ratio"]
+    C, res = fs.get("input_dim", fs.get("in_channels")), params["image_resolution"] * fs["down_ratio"]
     lo, hi = ((-0.5, 0.5) if fs["down_ratio"] == 4 else (-1.0, 1.0))
     imgs = structured_images(batch * frames, C, res, seed, lo, hi).view(batch, frames, C, res, res)
     g = torch.Generator(device="cpu")

@@ -128,6 +128,41 @@ def make_goldens():
               f"min logit gap {float(rec['gap'].min()):.3g}, logit std {float(pred.std()):.3f}")
 
 
+# MAGE+ branch (use_cids=False): (name, frames_length, batch, text_len, padded, noise_seed, the reference's line-93 edit)
+PLUS_CASES = [
+    ("plus_L4_b2", 4, 2, 12, False, 91, False),        # reference exactly as shipped (TransformerBlock line 92)
+    ("plus_L5_b2_ln_pad", 5, 2, 14, True, 92, True),   # with the edit the reference documents for MAGE+ (line 93: ln_q / ln_kv)
+    ("plus_L10_b1_ln", 10, 1, 20, False, 93, True),    # frames_length of the shipped mage+_cater*.yaml
+]
+
+
+def make_plus_goldens():
+    """Reference outputs of the MAGE+ branch: the unmodified reference (and the reference with its own documented line 92->93
+    edit, applied in memory) with use_cids=False and the stand-in first stage `mage_b200.synthetic.PatchLatentAE` (the shipped
+    first stage, latent-diffusion's AutoencoderKL, is not vendored).  Stored: the latents the reference hands to
+    first_stage_decode (captured at the module boundary by a forward hook on `generate_model`) and the pixels."""
+    assert ref_shims.reference_available(), "needs /root/reference"
+    for name, L, B, T, padded, noise_seed, edit in PLUS_CASES:
+        params = syn.model_params("caterv2plus", frames_length=L)
+        sd = syn.make_mage_state_dict(params)
+        batch = syn.make_batch(params, B, seed=1234, text_len=T, padded=padded)
+        model = ref_shims.build_reference_mage(params, sd, mage_plus_edit=edit)
+        captured = {}
+        h = model.generate_model.register_forward_hook(lambda m, i, o: captured.__setitem__("pred", o.detach()))
+        t0 = time.time()
+        with torch.no_grad():
+            torch.manual_seed(noise_seed)
+            video = model.autoregressive_generate({k: v.clone() for k, v in batch.items()})
+            z0 = model.first_stage_encode(batch["images"][:, 0:1])[:, 0]
+        h.remove()
+        lat = captured["pred"].permute(0, 1, 4, 2, 3).contiguous()            # [B, L-1, c, h, w] (mage_model.py:689)
+        rec = dict(frames_length=L, batch=B, text_len=T, padded=padded, noise_seed=noise_seed, ma_ln=edit,
+                   z0=_np(z0).astype(np.float32), latents=_np(lat).astype(np.float32),
+                   pixels=_np(video[:, 1:, :, ::4, ::4]).astype(np.float32), pixel_stride=4)
+        np.savez_compressed(os.path.join(GOLDEN_DIR, f"mage_{name}.npz"), **rec)
+        print(f"mage+ {name}: {time.time() - t0:.1f}s, latents {tuple(lat.shape)} std {float(lat.std()):.3f} max {float(lat.abs().max()):.3f}")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
@@ -135,3 +170,5 @@ if __name__ == "__main__":
         make_codebooks()
     if what in ("goldens", "all"):
         make_goldens()
+    if what in ("plus", "all"):
+        make_plus_goldens()

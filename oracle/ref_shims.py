@@ -80,9 +80,22 @@ def _install_shims() -> None:
 
 _REF_NAMES = ("modules", "modules.vqvae_model", "modules.mage_model", "utils", "utils.util")
 _ref_cache = {}
+_ref_cache_ln = {}   # the reference with its documented MAGE+ edit applied in memory (mage_model.py:92-93)
+
+_LINE92 = "x = q + self.dropout(self.attention(q, k, v)) #NOTE"
+_LINE93 = "# x = q + self.dropout(self.attention(self.ln_q(q), self.ln_kv(k), self.ln_kv(v), key_mask)) #NOTE"
 
 
-def _exec_reference_modules():
+def _mage_plus_edit(src: str) -> str:
+    """The manual edit the reference's own comments prescribe for MAGE+ ("Kindly comment out this line when employing MAGE+" /
+    "Please uncomment this line when employing MAGE+", mage_model.py:92-93), applied to the source text IN MEMORY: line 92 is
+    commented out, line 93 is uncommented.  Nothing is written anywhere."""
+    assert src.count(_LINE92) == 1 and src.count(_LINE93) == 1, "reference source differs from the surveyed revision"
+    src = src.replace(_LINE93, _LINE93[2:])
+    return src.replace("        " + _LINE92, "        # " + _LINE92)
+
+
+def _exec_reference_modules(cache=None, mage_plus_edit: bool = False):
     """Execute the reference's source files under their own import names (`modules.*`, `utils.*`).
     This repo has same-named drop-in packages (regular packages beat the reference's namespace
     packages on sys.path), so the files are loaded explicitly by path and the names are swapped in
@@ -96,14 +109,18 @@ def _exec_reference_modules():
             m = types.ModuleType(pkg)
             m.__path__ = [os.path.join(REFERENCE_ROOT, pkg)]
             sys.modules[pkg] = m
+        cache = _ref_cache if cache is None else cache
         for name in ("utils.util", "modules.vqvae_model", "modules.mage_model"):
             path = os.path.join(REFERENCE_ROOT, *name.split(".")) + ".py"
             spec = importlib.util.spec_from_file_location(name, path)
             mod = importlib.util.module_from_spec(spec)
             sys.modules[name] = mod
-            spec.loader.exec_module(mod)
+            if mage_plus_edit and name == "modules.mage_model":
+                exec(compile(_mage_plus_edit(open(path).read()), path, "exec"), mod.__dict__)
+            else:
+                spec.loader.exec_module(mod)
         for k in _REF_NAMES:
-            _ref_cache[k] = sys.modules[k]
+            cache[k] = sys.modules[k]
     finally:
         for k in list(sys.modules):
             if k in ("modules", "utils") or k.startswith("modules.") or k.startswith("utils."):
@@ -115,9 +132,12 @@ class _reference_names:
     """Context manager: `modules.*` / `utils.*` resolve to the reference while active
     (its instantiate_from_config imports targets by dotted path, utils/util.py:58-63)."""
 
+    def __init__(self, cache=None):
+        self.cache = _ref_cache if cache is None else cache
+
     def __enter__(self):
         self.saved = {k: sys.modules.get(k) for k in _REF_NAMES}
-        sys.modules.update(_ref_cache)
+        sys.modules.update(self.cache)
 
     def __exit__(self, *exc):
         for k, v in self.saved.items():
@@ -127,14 +147,16 @@ class _reference_names:
                 sys.modules[k] = v
 
 
-def load_reference():
-    """Returns (mage_model module, vqvae_model module) of the real reference."""
+def load_reference(mage_plus_edit: bool = False):
+    """Returns (mage_model module, vqvae_model module) of the real reference; `mage_plus_edit` applies the MAGE+ source edit the
+    reference documents at mage_model.py:92-93 (in memory)."""
     if not reference_available():
         raise RuntimeError(f"reference not found at {REFERENCE_ROOT}")
     _install_shims()
-    if not _ref_cache:
-        _exec_reference_modules()
-    return _ref_cache["modules.mage_model"], _ref_cache["modules.vqvae_model"]
+    cache = _ref_cache_ln if mage_plus_edit else _ref_cache
+    if not cache:
+        _exec_reference_modules(cache, mage_plus_edit)
+    return cache["modules.mage_model"], cache["modules.vqvae_model"]
 
 
 def to_dictconfig(obj):
@@ -144,13 +166,13 @@ def to_dictconfig(obj):
     return obj
 
 
-def build_reference_mage(params: dict, state_dict: dict):
+def build_reference_mage(params: dict, state_dict: dict, mage_plus_edit: bool = False):
     """Instantiate the reference's MAGE with `params`, load the synthetic sampling subset
     (strict=False: the train-only conv3d/conv_mu2/conv_var2 keep their default init)."""
     import torch
 
-    mm, _ = load_reference()
-    with _reference_names():
+    mm, _ = load_reference(mage_plus_edit)
+    with _reference_names(_ref_cache_ln if mage_plus_edit else _ref_cache):
         torch.manual_seed(0)
         model = mm.MAGE(**to_dictconfig(params))
     missing, unexpected = model.load_state_dict(state_dict, strict=False)

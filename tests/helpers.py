@@ -36,6 +36,21 @@ def load_case(name):
     return params, sd, batch, noise, g
 
 
+PLUS_CASES = ["plus_L4_b2", "plus_L5_b2_ln_pad", "plus_L10_b1_ln"]
+
+
+def load_plus_case(name):
+    """MAGE+ golden (use_cids=False, stand-in first stage): params (with the additive `ln_qkv` switch set like the golden's
+    reference edit), checkpoint, batch, AdaIN noise as the reference drew it, golden arrays."""
+    g = dict(np.load(os.path.join(GOLDEN_DIR, f"mage_{name}.npz")))
+    params = syn.model_params("caterv2plus", frames_length=int(g["frames_length"]))
+    sd = syn.make_mage_state_dict(params)
+    batch = syn.make_batch(params, int(g["batch"]), seed=1234, text_len=int(g["text_len"]), padded=bool(g["padded"]))
+    torch.manual_seed(int(g["noise_seed"]))
+    noise = torch.randn(int(g["batch"]), 64, 16, 16)
+    return params, sd, batch, noise, g
+
+
 def pix_check(got, want, what="pixels"):
     got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
     rel = np.linalg.norm(got - want) / max(np.linalg.norm(want), 1e-30)

@@ -24,7 +24,13 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(L, n), f"{n} declared in include/mage_b200.h but not exported"
     assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)
     assert L.mage_abi_version() == _lib.ABI_VERSION
-    assert L.mage_launch_count() >= 0
+    assert L.mage_launch_count(None) == 0          # no handle, nothing launched
+    import ctypes
+    import torch
+    if not torch.cuda.is_available():
+        # the handle is the only way in, and it only exists on an sm_100 device: no CPU path to fall back to
+        h = ctypes.c_void_p()
+        assert L.mage_ctx_create(0, ctypes.byref(h)) != 0 and not h.value
 
 
 def test_header_cites_reference_lines():

@@ -353,3 +353,30 @@ def test_token_taps_equals_conv_plus_linear():
     out = torch.empty(B * R * R, C, device=DEV)
     ops.token_taps(tok.to(DEV), table.to(DEV), posW.to(DEV), b_in.to(DEV), out)
     _close(out.view(B, R, R, C), want, 2e-6, 2e-6)
+
+
+def test_handles_are_independent():
+    """all library state lives in the opaque handle.  A second handle on the same device has its own launch
+    counter and tuning switches; using it does not disturb the handle the package works through."""
+    import ctypes
+
+    from mage_b200 import _lib, ops
+    L = _lib.lib()
+    h = ctypes.c_void_p()
+    assert L.mage_ctx_create(0, ctypes.byref(h)) == 0 and h.value
+    assert L.mage_ctx_device(h) == 0 and L.mage_launch_count(h) == 0
+    n0 = ops.launch_count()
+    x = torch.randn(64, 512, device="cuda")
+    g, b = torch.ones(512, device="cuda"), torch.zeros(512, device="cuda")
+    want = ops.layernorm(x, g, b)
+    assert ops.launch_count() == n0 + 1 and L.mage_launch_count(h) == 0
+    assert L.mage_tc_tuning(h, 64, 0) == 0 and L.mage_pdl(h, 1) == 0     # switches of the second handle only
+    out = torch.empty_like(x)
+    assert L.mage_layernorm_f32(h, x.data_ptr(), g.data_ptr(), b.data_ptr(), out.data_ptr(), None, 0, None, 64, 512, 1e-5,
+                                torch.cuda.current_stream().cuda_stream) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(out, want) and L.mage_launch_count(h) == 1 and ops.launch_count() == n0 + 1
+    assert L.mage_layernorm_f32(None, x.data_ptr(), g.data_ptr(), b.data_ptr(), out.data_ptr(), None, 0, None, 64, 512, 1e-5, None) == -1
+    assert L.mage_ctx_destroy(h) == 0
+    h2 = ctypes.c_void_p()
+    assert L.mage_ctx_create(99, ctypes.byref(h2)) != 0 and not h2.value   # no such device

@@ -10,7 +10,7 @@ import torch
 from mage_b200 import synthetic as syn
 from oracle import mage_oracle as orc
 from oracle import ref_shims
-from tests.helpers import GOLDEN_DIR, MAGE_CASES, free_running_token_report, load_case
+from tests.helpers import GOLDEN_DIR, MAGE_CASES, PLUS_CASES, free_running_token_report, load_case, load_plus_case
 
 
 @pytest.mark.parametrize("ratio", [4, 8])
@@ -54,6 +54,21 @@ def test_incremental_order_equals_reference_order(name):
     assert rep["excused"] == 0 and rep["compared"] == rep["positions"], "incremental and reference order must give the same tokens"
     s = int(g["pixel_stride"])
     np.testing.assert_allclose(video[:, 1:][..., ::s, ::s].numpy(), g["pixels"], rtol=0, atol=2e-6)
+
+
+@pytest.mark.parametrize("name", PLUS_CASES)
+def test_mage_plus_branch_matches_reference_golden(name):
+    """MAGE+ (use_cids=False): the oracle's continuous-latent restatement against the reference's own latents -- as shipped
+    (TransformerBlock line 92) and with the reference's documented line-93 edit (ln_q / ln_kv)."""
+    params, sd, batch, noise, g = load_plus_case(name)
+    ae = syn.PatchLatentAE(**params["first_stage_config"]["params"])
+    z0 = ae.encode(batch["images"][:, 0])
+    np.testing.assert_allclose(z0.numpy(), g["z0"], rtol=0, atol=1e-6)
+    lat = orc.generate_continuous(sd, z0, batch["text"], batch.get("speed"), noise, ma_ln=bool(g["ma_ln"]))
+    np.testing.assert_allclose(lat.numpy(), g["latents"], rtol=0, atol=2e-5)
+    B, Fr = lat.shape[:2]
+    pix = ae.decode(lat.reshape(-1, *lat.shape[2:])).view(B, Fr, 3, 128, 128)[..., ::4, ::4]
+    np.testing.assert_allclose(pix.numpy(), g["pixels"], rtol=0, atol=2e-5)
 
 
 def test_incremental_can_run_longer_than_checkpoint_positions_is_rejected():

@@ -87,8 +87,8 @@ def test_entry_flags_and_config_resolution(tmp_path):
     got = main_mage.load_configs(opt)
     assert got["model"]["params"]["frames_length"] == 3
     from utils.util import instantiate_from_config
-    with pytest.raises(NotImplementedError):
-        instantiate_from_config(got["data"], {"split": "test"})     # real readers: out of scope, loud
+    with pytest.raises(TypeError):
+        instantiate_from_config(got["data"], {"split": "test"})     # the real reader needs its data_root etc., like the reference's
     with pytest.raises(KeyError):
         instantiate_from_config({"params": {}})                     # utils/util.py:51
 
@@ -105,11 +105,22 @@ def test_shipped_configs_instantiate():
     for p in paths:
         cfg = load_yaml(p)
         params = dict(cfg["model"]["params"])
-        params["first_stage_config"] = {"target": params["first_stage_config"]["target"],
-                                        "params": {**params["first_stage_config"]["params"], "ckpt_path": None}}
+        plus = not params["use_cids"]
+        if plus:
+            # MAGE+ yamls keep the reference's external first stage (latent-diffusion's AutoencoderKL, not vendored): swap in the
+            # stand-in torch module to check the transformer-side key layout (Linear embed, GroupNorm/Conv3d head, ln_qkv switch)
+            params["first_stage_config"] = {"target": "mage_b200.synthetic.PatchLatentAE", "params": {"embed_dim": 4}}
+        else:
+            params["first_stage_config"] = {"target": params["first_stage_config"]["target"],
+                                            "params": {**params["first_stage_config"]["params"], "ckpt_path": None}}
         m = instantiate_from_config({"target": cfg["model"]["target"], "params": params})
         keys = set(m.state_dict().keys())
-        assert "generate_model.blocks.5.mlp.c_proj.weight" in keys and "first_stage_model.codebook.embedding.weight" in keys
+        assert "generate_model.blocks.5.mlp.c_proj.weight" in keys
+        if plus:
+            assert {"generate_model.out.0.weight", "generate_model.out.2.weight", "visual_token_embedding.bias"} <= keys
+            assert tuple(m.state_dict()["visual_token_embedding.weight"].shape) == (512, 4) and m.ma_encoder.ln_qkv
+        else:
+            assert "first_stage_model.codebook.embedding.weight" in keys
         with pytest.raises(RuntimeError):
             m.autoregressive_generate({"images": torch.zeros(1, 1, 1, 8, 8), "text": torch.zeros(1, 4, dtype=torch.long)})  # no CPU path
 
@@ -155,3 +166,85 @@ def test_first_frame_loader_ranges(tmp_path):
     assert tuple(x.shape) == (1, 3, 128, 128) and -1.0 <= float(x.min()) and float(x.max()) <= 1.0
     g = dataload.load_first_frame(str(tmp_path / "f.png"), 1, 64)
     assert tuple(g.shape) == (1, 1, 64, 64) and -0.5 <= float(g.min()) and float(g.max()) <= 0.5
+
+
+def test_speed_based_frame_subsampling_matches_the_reference_formula():
+    """dataload.py:244-248 (Moving MNIST, interval >= 1) and :346-349 (CATER, interval >= 3)."""
+    import numpy as np
+    from dataload import speed_subsample_indices
+    for n, speed, ss, lo in [(300, 0.0, [3.0, 6.0], 3.0), (300, 0.999, [3.0, 6.0], 3.0), (301, 0.37, [3.0, 6.0], 3.0),
+                             (40, 0.5, [1.0, 2.0], 1.0), (40, 0.1, [0.5, 1.5], 1.0), (20, 0.9, [2.0, 5.0], 3.0)]:
+        interval = max(lo, speed * (ss[-1] - ss[0]) + ss[0])
+        want = np.floor(np.linspace(0, n - 1, round(n / interval), endpoint=True)).astype(np.int32)
+        got = speed_subsample_indices(n, speed, ss, lo)
+        assert np.array_equal(got, want) and got[0] == 0 and got[-1] == n - 1 and (np.diff(got) >= 1).all()
+
+
+def test_cater_reader_items_and_collate(tmp_path):
+    """dataload.CATER (dataload.py:273-381) on a tiny on-disk dataset: anno json, one .npy clip, one frame directory; item dict,
+    [-1,1] range, NEAREST shorter-side resize to 128, last-frame padding, word-level token ids, text padded with 0 by collate."""
+    import json
+    import random
+
+    import numpy as np
+    from PIL import Image
+
+    from dataload import CATER, VOCABS
+    rng = np.random.RandomState(0)
+    clip = rng.randint(0, 256, size=(60, 64, 64, 3), dtype=np.uint8)
+    np.save(tmp_path / "a.npy", clip)
+    (tmp_path / "b").mkdir()
+    short = rng.randint(0, 256, size=(12, 128, 160, 3), dtype=np.uint8)       # 12 frames, 160x128 (w x h): shorter side already 128
+    for i, f in enumerate(short):
+        Image.fromarray(f).save(tmp_path / "b" / f"{i:03d}.png")
+    anno = {"0": {"video": "a.npy", "caption": "the small blue rubber sphere is sliding to (2, -3)."},
+            "1": {"video": "b", "caption": "the cone is picked up and placed to (1, 1)."}}
+    (tmp_path / "test_explicit.json").write_text(json.dumps(anno))
+    ds = CATER("caterv2", str(tmp_path), "test", frames_length=10, sample_speed=[3.0, 6.0])
+    assert len(ds) == 2
+    random.seed(3)
+    speed = random.random()
+    random.seed(3)
+    it = ds[0]
+    assert it["video_id"] == "a.npy" and abs(float(it["speed"]) - speed) < 1e-7
+    assert tuple(it["images"].shape) == (10, 3, 128, 128) and it["images"].min() >= -1 and it["images"].max() <= 1
+    from dataload import speed_subsample_indices
+    idx = speed_subsample_indices(60, speed, [3.0, 6.0], 3.0)[:10]
+    want0 = np.asarray(Image.fromarray(clip[idx[3]]).resize((128, 128), Image.NEAREST), dtype=np.float32) / 255.0
+    assert np.allclose(it["images"][3].permute(1, 2, 0).numpy(), (want0 - 0.5) / 0.5)
+    v = VOCABS["caterv2"]
+    assert it["text"].tolist() == [1] + [v[w] for w in "the small blue rubber sphere is sliding to ( 2 , -3 ) .".split()] + [2]
+    it1 = ds[1]
+    assert tuple(it1["images"].shape) == (10, 3, 128, 160)                     # aspect kept, like the reference's Resize(128)
+    n_real = len(speed_subsample_indices(12, float(it1["speed"]), [3.0, 6.0], 3.0))
+    assert n_real < 10 and torch.equal(it1["images"][n_real - 1], it1["images"][-1])   # padded with the last frame
+    sq = CATER("caterv2", str(tmp_path), "test", frames_length=4, sample_speed=[3.0, 6.0])
+    batch = sq.collate_fn([sq[0], sq[0]])
+    assert tuple(batch["images"].shape) == (2, 4, 3, 128, 128) and batch["text"].dtype == torch.long and len(batch["video_id"]) == 2
+    with pytest.raises(KeyError):
+        ds.encode("the unknownword is sliding")
+
+
+def test_moving_mnist_reader(tmp_path):
+    """dataload.MovingMnistLMDB (dataload.py:183-271) from the dependency-free pickle form: [-0.5, 0.5] range, interval >= 1."""
+    import pickle
+    import random
+
+    import numpy as np
+
+    from dataload import MovingMnistLMDB, VOCABS, collate_fn
+    rng = np.random.RandomState(1)
+    items = [(rng.randint(0, 256, size=(30, 1, 64, 64), dtype=np.uint8), "the digit 3 is moving left then right ."),
+             (rng.randint(0, 256, size=(8, 1, 64, 64), dtype=np.uint8), "the digit 0 and the digit 9 are bouncing around .")]
+    with open(str(tmp_path) + "/test.pkl", "wb") as fp:
+        pickle.dump(items, fp)
+    ds = MovingMnistLMDB(str(tmp_path) + "/", "test", frames_length=16, sample_speed=[1.0, 2.0])
+    random.seed(5)
+    a, b = ds[0], ds[1]
+    assert tuple(a["images"].shape) == (16, 1, 64, 64) and a["images"].min() >= -0.5 and a["images"].max() <= 0.5
+    assert tuple(b["images"].shape) == (16, 1, 64, 64) and torch.equal(b["images"][-1], b["images"][7])   # 8 frames, padded
+    v = VOCABS["mnist"]
+    assert a["text"].tolist() == [1] + [v[w] for w in items[0][1].split()] + [2]
+    batch = collate_fn([a, b])
+    assert tuple(batch["text"].shape) == (2, max(len(a["text"]), len(b["text"]))) and "video_id" not in batch
+    assert " the digit 3" in ds.decode(a["text"][1:4])

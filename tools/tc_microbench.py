@@ -39,9 +39,11 @@ def main():
     ap.add_argument("--nsplit", type=int, default=1, help="ops.tc_nsplit mode (0 off, 1 auto, 2 force)")
     ap.add_argument("--scan", action="store_true", help="K / N scans that separate per-tile from per-k-block cost")
     ap.add_argument("--cfgs", default="0,-1", help="';'-separated bn,pair tile overrides (ops.tc_tuning) to sweep")
+    ap.add_argument("--passes", type=int, default=3, help="convolutions: 3 = fp32-grade products, 1 = single-pass fp16 (decoder budget)")
+    ap.add_argument("--rows", type=int, default=16384, help="M of the GEMM cases (16384 = 64 prompts, 2048 = 8 prompts)")
     args = ap.parse_args()
     flush = None if args.no_flush else torch.empty(256 << 20, device=DEV, dtype=torch.uint8)
-    M = 16384
+    M = args.rows
     g = torch.Generator(device="cpu").manual_seed(0)
     rows = []
 
@@ -67,8 +69,8 @@ def main():
         b = torch.randn(Cout, generator=g).to(DEV)
         sp = torch.empty(2, n, H, H, Cout, device=DEV, dtype=torch.float16)
         out = torch.empty(n, H, H, Cout, device=DEV) if mode == "f32" else None
-        fn = (lambda: ops.conv2d_tc(x, w, b, pad=(k // 2, k // 2), act=1, want=(), out_split=sp)) if mode == "split" else \
-             (lambda: ops.conv2d_tc(x, w, b, pad=(k // 2, k // 2), act=1, out=out))
+        fn = (lambda: ops.conv2d_tc(x, w, b, pad=(k // 2, k // 2), act=1, want=(), out_split=sp, passes=args.passes)) if mode == "split" else \
+             (lambda: ops.conv2d_tc(x, w, b, pad=(k // 2, k // 2), act=1, out=out, passes=args.passes))
         ms = timeit(fn, args.iters, flush)
         rows.append((name, 2.0 * n * H * H * Cout * k * k * Cin / ms / 1e9, ms))
 
@@ -80,17 +82,17 @@ def main():
         hw, hb = (torch.randn(3, 256, generator=g) / 16).to(DEV), torch.randn(3, generator=g).to(DEV)
         out = torch.empty(n, 3, H, H, device=DEV)
         fn = lambda: ops.conv2d_tc_pixel_head(x, w, b, pad=(1, 1), residual=r, res_mode=2, head_w=hw, head_b=hb, out=out,
-                                              out_img_stride=3 * H * H)
+                                              out_img_stride=3 * H * H, passes=args.passes)
         ms = timeit(fn, args.iters, flush)
         rows.append((name, 2.0 * n * H * H * 256 * 576 / ms / 1e9, ms))
 
     cases = [
         ("pixel head 128x128 64->256->3", lambda: head_case("pixel head 128x128 64->256->3", 64, 128)),
-        ("qkv 16384x1536x512 f32", lambda: gemm_case("qkv 16384x1536x512 f32", M, 1536, 512, "f32")),
-        ("outproj 16384x512x512 res", lambda: gemm_case("outproj 16384x512x512 res", M, 512, 512, "res")),
-        ("fc 16384x2048x512 split", lambda: gemm_case("fc 16384x2048x512 split", M, 2048, 512, "split")),
-        ("proj 16384x512x2048 res", lambda: gemm_case("proj 16384x512x2048 res", M, 512, 2048, "res")),
-        ("head 16384x512x512 f32", lambda: gemm_case("head 16384x512x512 f32", M, 512, 512, "f32")),
+        (f"qkv {M}x1536x512 f32", lambda: gemm_case(f"qkv {M}x1536x512 f32", M, 1536, 512, "f32")),
+        (f"outproj {M}x512x512 res", lambda: gemm_case(f"outproj {M}x512x512 res", M, 512, 512, "res")),
+        (f"fc {M}x2048x512 split", lambda: gemm_case(f"fc {M}x2048x512 split", M, 2048, 512, "split")),
+        (f"proj {M}x512x2048 res", lambda: gemm_case(f"proj {M}x512x2048 res", M, 512, 2048, "res")),
+        (f"head {M}x512x512 f32", lambda: gemm_case(f"head {M}x512x512 f32", M, 512, 512, "f32")),
         ("conv3x3 tok 64x16x16 512->512", lambda: conv_case("conv3x3 tok 64x16x16 512->512", 64, 16, 512, 512, 3)),
         ("dec 16x16 128->128", lambda: conv_case("dec 16x16 128->128", 64, 16, 128, 128, 3)),
         ("dec 16x16 128->512", lambda: conv_case("dec 16x16 128->512", 64, 16, 128, 512, 3, "f32")),
