@@ -254,9 +254,11 @@ def run_cuda(args, wl, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # NCCL's INFO log (ranks, transports) on stderr; stdout carries the one JSON line
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # NCCL's INFO log (ranks, transports) goes to stderr; stdout carries the one JSON line and nothing else (NCCL prints to
+        # stdout unless a debug file is named, and the image presets NCCL_DEBUG=VERSION)
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = os.environ.get("MAGE_NCCL_DEBUG", "INFO")
+        os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         dist.init_process_group("nccl", device_id=dev)
     os.environ["MAGE_BACKEND"] = args.backend
     L = wl["frames"]

@@ -145,6 +145,18 @@ int mage_gemm_tc(mage_ctx* ctx, const void* A, int64_t lda, int64_t a_plane, con
                  void* C_split_relu, int64_t ldc, int64_t c_plane, int M, int N, int K, int act, int* flag,
                  void* stream);
 
+/* Fused QKV projection + axial attention of the H / W blocks (AxialAttentionBlock.attention, mage_model.py:31-33, with the
+ * permutes of :36-47 expressed in tensor maps): for rows ordered (img, h, w) of A = split(ln_1(x)) [n_img*R*R, K],
+ *   out = softmax(q k^T * scale) v   per (img, line, head) over the R = 16 positions of the attended axis
+ *         (axis 1: along h for fixed w;  axis 2: along w for fixed h),   [q|k|v] = A . W_in^T + b_in,
+ * written as split(out) [n_img*R*R, n_head*32] -- the operand of the out-projection.  One tcgen05 GEMM whose epilogue does the
+ * attention: the [rows, 3C] QKV tensor never reaches memory.  Wp / bias_p are W_in / b_in with rows PERMUTED so that every
+ * 192-row tile holds [q|k|v] x 32 of two heads: new row t*192 + s*96 + part*32 + d  <-  old row part*C + (2t+s)*32 + d.
+ * R = 16, head_dim 32, n_head even, K % 64 == 0. */
+int mage_qkv_axial_attn_tc(mage_ctx* ctx, const void* A, int64_t a_plane, const void* Wp, int64_t w_plane, const float* bias_p,
+                           void* out_split, int64_t out_plane, int n_img, int R, int n_head, int K, int axis, float scale,
+                           int* flag, void* stream);
+
 /* Stride-1 NHWC convolution as a tcgen05 implicit GEMM: the A tile of tap (ky,kx) is a TMA box of the
  * split input [n_img,Hin,Win,Cin] shifted by (ky-pad_y, kx-pad_x); out-of-bounds zero fill is the padding.
  * w split [Cout][KH][KW][Cin]; Cin % 64 == 0, Cout % 64 == 0, 128 % min(Wout,128) == 0 (else MAGE_ENOTSUP).

@@ -75,6 +75,10 @@ struct TcParams {
   // with fp32 accumulation, for layers whose result feeds no token (the last VQ-VAE decoder block: DESIGN.md "decoder
   // precision budget"); only the hi planes are fetched (w_tx_bytes / a_tx_bytes halve) and the corr accumulator is never read.
   int passes, w_tx_bytes;
+  // fused QKV projection + axial attention (mage_qkv_axial_attn_tc): the N tile holds [q|k|v] x 32 columns of two heads, the
+  // epilogue runs softmax(q k^T * attn_scale) v over the 16 positions of each line and stores only the attention output
+  int attn;
+  float attn_scale;
   // halo kernel shared-memory plan of this launch (HaloCfg): A ring depth / stage bytes, W slots / slot bytes, resident weights
   int sa, sw, a_stage_bytes, w_slot_bytes, w_resident, smem_bytes;
 };
@@ -337,6 +341,159 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
   if (!(amax <= 65504.f) && p.flag) atomicOr(p.flag, 1);
 }
 
+// Epilogue of the fused QKV-projection + axial-attention kernel (AxialAttentionBlock.attention for the H / W blocks,
+// mage_model.py:31-33 with the permutes of :36-47 expressed in the tensor maps).  The A tile is 128 rows = 8 lines x 16
+// positions of the attended axis (gathered in that order by the A map), the N tile (192 columns) is [q|k|v] x 32 of two heads
+// (weights permuted at load).  Warp (quad, half) owns rows quad*32 .. +31 (two whole lines) and head `half` of the tile:
+//   tcgen05.ld q, k, v (main + corr*2^-11 + bias) -> the TMEM stage is handed back at once (the MMAs of the next tile overlap
+//   the attention math) -> k through the warp's 4 KB staging tile: s[j] = q . k_j over the 16 rows of the thread's own line
+//   (the two lines of a warp read two addresses per instruction: broadcasts, no conflicts) -> softmax -> v through the same
+//   tile: o = sum_j p[j] v_j -> split (hi/lo) -> one TMA store of the 32x32 output block.  The [rows, 1536] QKV tensor never
+//   exists in memory.
+template <int BN, int CG>
+__device__ __forceinline__ void attn_epilogue_loop(const TcParams& p, const CUtensorMap* mapS, uint32_t tmem_base, uint8_t* staging,
+                                                   uint32_t tfull0, uint32_t tempty0) {
+  static_assert(BN == 192, "two heads x (q,k,v) x 32 columns");
+  using C = Cfg<BN, CG>;
+  const int cta_rank = CG == 2 ? (int)cluster_ctarank() : 0;
+  const int unit = blockIdx.x / CG, n_units = gridDim.x / CG;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  const int quad = warp & 3, half = (warp - 2) >> 2;
+  uint8_t* const stg = staging + (warp - 2) * 4096;
+  const uint32_t stg_s = smem_u32(stg);
+  float* const stg_f = reinterpret_cast<float*>(stg);
+  const float* const __restrict__ bias = p.bias;
+  const int n_tiles = p.n_tiles;
+  const int num_tiles = (p.m_tiles / CG) * p.n_tiles;
+  const uint32_t row16 = stg_s + lane * 64, sw16 = (lane >> 1) & 3;
+  const int line0 = lane & 16;   // first lane of this thread's line
+  float amax = 0.f;
+  bool pending = false;
+  for (int tcount = 0;; ++tcount) {
+    const int tile = tile_of(tcount, unit, n_units, 1);
+    if (tile >= num_tiles) break;
+    const int mt = (tile / n_tiles) * CG + cta_rank, nt = tile % n_tiles;
+    const int acc = tcount % C::ACC_STAGES;
+    const uint32_t aph = (tcount / C::ACC_STAGES) & 1;
+    const int simg = mt / p.tiles_img;
+    const int rr = mt - simg * p.tiles_img;
+    const int ty = rr / p.tiles_x, tx = rr - ty * p.tiles_x;
+    const int r0 = quad * 32;
+    const int sx0 = tx * p.Wb + (r0 & (p.Wb - 1)), sy0 = ty * p.Hb + (r0 >> p.wb_shift);
+    mbar_wait(tfull0 + 8u * acc, aph);
+    tc_fence_after();
+    const uint32_t t_main = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * C::ACC_COLS + half * 96;
+    const uint32_t t_corr = t_main + BN;
+    if (pending) {   // the previous tile's TMA store may still be reading the staging tile
+      if (lane == 0) bulk_wait_read0();
+      __syncwarp();
+      pending = false;
+    }
+    // staging tile as a [32 rows][32 floats] exchange buffer: row = lane, 16-byte chunk c of a row sits at chunk c ^ (row & 7)
+    // (conflict-free 128-bit stores; a line's 16 lanes read one row per instruction = a broadcast)
+    auto load_part = [&](int part, float (&dst)[32]) {
+      uint32_t rm[32], rc[32];
+      tmem_ld32(t_main + part * 32, rm);
+      tmem_ld32(t_corr + part * 32, rc);
+      tmem_wait_ld();
+      const float* b = bias + nt * BN + half * 96 + part * 32;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(b) + j);
+        dst[4 * j] = fmaf(__uint_as_float(rc[4 * j]), kLoInv, __uint_as_float(rm[4 * j])) + bb.x;
+        dst[4 * j + 1] = fmaf(__uint_as_float(rc[4 * j + 1]), kLoInv, __uint_as_float(rm[4 * j + 1])) + bb.y;
+        dst[4 * j + 2] = fmaf(__uint_as_float(rc[4 * j + 2]), kLoInv, __uint_as_float(rm[4 * j + 2])) + bb.z;
+        dst[4 * j + 3] = fmaf(__uint_as_float(rc[4 * j + 3]), kLoInv, __uint_as_float(rm[4 * j + 3])) + bb.w;
+      }
+    };
+    auto to_smem = [&](const float (&src)[32]) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(stg_f + lane * 32 + 4 * (j ^ (lane & 7))) = make_float4(src[4 * j], src[4 * j + 1], src[4 * j + 2], src[4 * j + 3]);
+    };
+    float q[32], v[32];
+    {
+      float k[32];
+      load_part(1, k);
+      to_smem(k);
+    }
+    load_part(0, q);
+    load_part(2, v);
+    // q, k, v have left TMEM: hand the stage back before the attention math (the next tile's MMAs overlap it)
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      if (CG == 2) mbar_arrive_cluster(mapa_u32(tempty0 + 8u * acc, 0));
+      else mbar_arrive(tempty0 + 8u * acc);
+    }
+    // ---- scores over the thread's line (the k rows of the warp's two lines are in the exchange buffer)
+    float s[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float4* kr = reinterpret_cast<const float4*>(stg_f + (line0 + j) * 32);
+      float d = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 kv = kr[i ^ (j & 7)];
+        d = fmaf(q[4 * i], kv.x, d); d = fmaf(q[4 * i + 1], kv.y, d);
+        d = fmaf(q[4 * i + 2], kv.z, d); d = fmaf(q[4 * i + 3], kv.w, d);
+      }
+      s[j] = d * p.attn_scale;
+    }
+    float mx = s[0];
+#pragma unroll
+    for (int j = 1; j < 16; ++j) mx = fmaxf(mx, s[j]);
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { s[j] = expf(s[j] - mx); sum += s[j]; }
+    const float inv = 1.f / sum;
+    __syncwarp();   // everyone is done with k
+    to_smem(v);
+    __syncwarp();
+    float o[32];
+#pragma unroll
+    for (int d = 0; d < 32; ++d) o[d] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float4* vr = reinterpret_cast<const float4*>(stg_f + (line0 + j) * 32);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 vv = vr[i ^ (j & 7)];
+        o[4 * i] = fmaf(s[j], vv.x, o[4 * i]); o[4 * i + 1] = fmaf(s[j], vv.y, o[4 * i + 1]);
+        o[4 * i + 2] = fmaf(s[j], vv.z, o[4 * i + 2]); o[4 * i + 3] = fmaf(s[j], vv.w, o[4 * i + 3]);
+      }
+    }
+    __syncwarp();   // everyone is done with v: the tile becomes the output staging (hi plane 2 KB | lo plane 2 KB, SWIZZLE_64B)
+    {
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float a = o[2 * j] * inv, b = o[2 * j + 1] * inv;
+        amax = fmaxf(amax, fmaxf(fabsf(a), fabsf(b)));
+        const __half2 h = __floats2half2_rn(a, b);
+        const float2 f = __half22float2(h);
+        const __half2 l = __floats2half2_rn((a - f.x) * kLoScale, (b - f.y) * kLoScale);
+        hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+        lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        sts128(row16 + ((j ^ sw16) << 4), hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+        sts128(row16 + 2048 + ((j ^ sw16) << 4), lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_5d(mapS, stg_s, (nt * 2 + half) * 32, sx0, sy0, simg, 0);   // output column = head * 32
+        bulk_commit();
+      }
+      pending = true;
+    }
+  }
+  if (lane == 0) bulk_wait0();
+  if (!(amax <= 65504.f) && p.flag) atomicOr(p.flag, 1);
+}
+
 template <int BN, int CG, bool NS = false>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW,
@@ -526,7 +683,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     __syncwarp();
   } else {
     // ------------------------------------------------------------ epilogue warps
-    if ((BN == 256 || BN == 128) && p.head_w) {
+    if (BN == 192 && p.attn) {
+      if constexpr (BN == 192) attn_epilogue_loop<BN, CG>(p, &mapS, tmem_base, staging, tfull_bar(0), tempty_bar(0));
+    } else if ((BN == 256 || BN == 128) && p.head_w) {
       if constexpr (BN == 256 || BN == 128) epilogue_loop<BN, CG, MAGE_ACT_NONE, true>(p, &mapO, &mapS, &mapR, tmem_base, staging, tfull_bar(0), tempty_bar(0));
     } else
     switch (p.act & 0xff) {
@@ -1228,6 +1387,41 @@ extern "C" int mage_gemm_tc(mage_ctx* ctx, const void* A, int64_t lda, int64_t a
     if (r) return r;
   }
   return dispatch(ctx, tcfg, mp, p, as_stream(stream));
+}
+
+// Fused QKV projection + axial (H / W) attention of one temporal position (or of a batch of positions): mage_b200.h.
+extern "C" int mage_qkv_axial_attn_tc(mage_ctx* ctx, const void* A, int64_t a_plane, const void* Wp, int64_t w_plane,
+                                      const float* bias_p, void* out_split, int64_t out_plane, int n_img, int R, int n_head,
+                                      int K, int axis, float scale, int* flag, void* stream) {
+  MAGE_CHECK_CTX(ctx);
+  MAGE_CHECK_ARG(n_img > 0 && R == 16 && n_head > 0 && n_head % 2 == 0 && K % BK == 0 && (axis == 1 || axis == 2));
+  MAGE_CHECK_ARG(aligned16(A) && aligned16(Wp) && aligned16(bias_p) && aligned16(out_split) && a_plane % 8 == 0 && w_plane % 8 == 0 &&
+                 out_plane % 8 == 0);
+  const int C = n_head * 32, N = 3 * C;
+  const int cg = (ctx->forced_pair != 0) ? 2 : 1;   // an image is two 128-row tiles: always pairable
+  Maps mp{};
+  // rows of A / of the output are (img, h, w); a tile is 8 lines x 16 positions ALONG the attended axis, so the map's "x"
+  // dimension is that axis: w (stride 1 row) for axis 2, h (stride R rows) for axis 1
+  const int64_t sx = axis == 2 ? 1 : R, sy = axis == 2 ? R : 1;
+  {
+    const cuuint64_t dims[5] = {(cuuint64_t)K, (cuuint64_t)R, (cuuint64_t)R, (cuuint64_t)n_img, 2};
+    const cuuint64_t strides[4] = {(cuuint64_t)(sx * K * 2), (cuuint64_t)(sy * K * 2), (cuuint64_t)((int64_t)R * R * K * 2), (cuuint64_t)a_plane * 2};
+    const cuuint32_t box[5] = {BK, 16, 8, 1, 2};
+    int r = make_map(&mp.A, A, 5, dims, strides, box);
+    if (r) return r;
+    r = make_w_map(&mp.W, Wp, K, w_plane, N, K, 192 / cg);
+    if (r) return r;
+    r = make_store_maps(&mp, nullptr, out_split, nullptr, out_plane, C, R, R, n_img, sx * C, sy * C, (int64_t)R * R * C, 16, 2);
+    if (r) return r;
+  }
+  TcParams p{};
+  p.bias = bias_p; p.split = reinterpret_cast<__half*>(out_split); p.flag = flag;
+  p.split_plane = out_plane; p.M = n_img * R * R; p.N = N;
+  p.m_tiles = n_img * 2; p.n_tiles = N / 192; p.k_iters = K / BK; p.group = 1;
+  p.conv = 1; p.Hout = R; p.Wout = R; p.Wb = 16; p.Hb = 8; p.KW = 1; p.cin_blocks = K / BK; p.cin = K;
+  p.wb_shift = 4; p.tiles_x = 1; p.tiles_img = 2;
+  p.attn = 1; p.attn_scale = scale;
+  return cg == 2 ? launch_tc<192, 2>(ctx, mp, p, as_stream(stream)) : launch_tc<192, 1>(ctx, mp, p, as_stream(stream));
 }
 
 // Stride-1 NHWC convolution on the tensor cores.  in: split [n_img,Hin,Win,Cin] (Cin % 64 == 0), w: split

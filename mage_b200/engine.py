@@ -466,10 +466,18 @@ class SamplerEngine:
                 ws["E"] = ops.split(self.E)
             for k in ("in_linear.weight", "out.weight") if use_cids else ("in_linear.weight",):
                 ws[p + k] = ops.split(g(p + k))
+            # H / W blocks: QKV projection and the 16x16 axial attention run as ONE kernel (mage_qkv_axial_attn_tc) on a
+            # head-permuted copy of the packed in-projection; MAGE_FUSED_AXIAL=0 keeps the two-kernel form (tests compare them)
+            self.fused_axial = os.environ.get("MAGE_FUSED_AXIAL", "1") != "0" and self.R == 16 and (self.C // 32) % 2 == 0
+            self.axial_bias = {}
             for i in range(self.n_blocks):
                 bp = p + f"blocks.{i}."
                 for k in ("attn.in_proj_weight", "attn.out_proj.weight", "mlp.c_fc.weight", "mlp.c_proj.weight"):
                     ws[bp + k] = ops.split(g(bp + k))
+                if i % 3 != 0 and self.R == 16 and (self.C // 32) % 2 == 0:
+                    wp, bp_ = ops.permute_qkv_for_axial(g(bp + "attn.in_proj_weight"), g(bp + "attn.in_proj_bias"), self.C // 32)
+                    ws[bp + "attn.in_proj_weight.axial"] = ops.split(wp)
+                    self.axial_bias[i] = bp_
             # prelude operands that see the whole batch (M = B*256 rows): motion-anchor block, context_linear, AdaIN convs
             ws[p + "context_linear.weight"] = ops.split(g(p + "context_linear.weight"))
             for i in range(self.n_ma_layers):
@@ -651,8 +659,18 @@ class SamplerEngine:
         M = x.shape[0]
         u, h, qkv = bufs["u"], bufs["h"], bufs["qkv"]
         ops.layernorm(x, sd[p + ".ln_1.weight"], sd[p + ".ln_1.bias"], out_split=u)
-        ops.gemm_tc(u, ws[p + ".attn.in_proj_weight"], sd[p + ".attn.in_proj_bias"], out=qkv)
         kind = i % 3
+        if kind != 0 and self.fused_axial:
+            a = bufs["a"]
+            ops.qkv_axial_attn_tc(u, ws[p + ".attn.in_proj_weight.axial"], self.axial_bias[i], a, n_img=B, R=R, n_head=self.n_head,
+                                  axis=kind, scale=self.scale)
+            ops.gemm_tc(a, ws[p + ".attn.out_proj.weight"], sd[p + ".attn.out_proj.bias"], residual=x, out=x)
+            ops.layernorm(x, sd[p + ".ln_2.weight"], sd[p + ".ln_2.bias"], out_split=u)
+            ops.gemm_tc(u, ws[p + ".mlp.c_fc.weight"], sd[p + ".mlp.c_fc.bias"], act=ACT_QUICKGELU, want=(), out_split=h)
+            ops.gemm_tc(h, ws[p + ".mlp.c_proj.weight"], sd[p + ".mlp.c_proj.bias"], residual=x, out=x,
+                        out_split=u if last else None)
+            return x
+        ops.gemm_tc(u, ws[p + ".attn.in_proj_weight"], sd[p + ".attn.in_proj_bias"], out=qkv)
         if kind == 0:
             kc, vc = caches[i]
             if self.temporal_attn == "tma":
@@ -714,6 +732,7 @@ class SamplerEngine:
         if tc:
             x, _, _ = ops.gemm_tc(ops.split(anchor.view(M, C)), self.ws[p + "context_linear.weight"], self.bias_ctx0)
             bufs = {"u": torch.empty(2, M, C, device=self.device, dtype=torch.float16),
+                    "a": torch.empty(2, M, C, device=self.device, dtype=torch.float16),
                     "h": torch.empty(2, M, 4 * C, device=self.device, dtype=torch.float16),
                     "qkv": torch.empty(M, 3 * C, device=self.device, dtype=torch.float32)}
         else:
@@ -755,13 +774,13 @@ class SamplerEngine:
                 st["tok"] = trace["force_tokens"][:, j].reshape(-1).contiguous()
 
     def _plan(self, B: int):
-        """(number of chunk streams, decode group) for a batch of B prompts.  Small batches are latency-bound (a decode step is
-        45 launches of a few microseconds each): the batch is cut into chunks whose launch sequences run concurrently on their
-        own streams, and the VQ-VAE decoder -- which nothing downstream depends on -- runs over larger groups of frames on a
-        side stream next to them.  Large batches fill the machine on their own: one stream, groups of 4 frames."""
-        S = self.n_streams
-        if S <= 0:
-            S = 1 if B >= 32 else (2 if B >= 4 else 1)
+        """(number of chunk streams, decode group) for a batch of B prompts.  The VQ-VAE decoder -- which nothing downstream depends
+        on -- runs over groups of finished frames: 4 frames at large batches, more at small ones so that a decoder pass still
+        covers >= 128 images (its low-resolution layers cannot fill 148 SMs otherwise).  Chunk streams (the batch cut into S
+        chunks whose launch sequences run concurrently, `MAGE_STREAMS`) are OFF by default: measured slower at every batch size
+        (profiles/r02b_small_batch_schedule_sweep.txt -- a decode step's kernels are persistent and each takes the whole machine,
+        so two chains only interleave and every chunk pays the per-kernel latency again)."""
+        S = self.n_streams if self.n_streams > 0 else 1
         S = max(1, min(S, B))
         G = self.decode_group
         if G <= 0:
@@ -836,16 +855,24 @@ class SamplerEngine:
         p = f"generate_model.blocks.{i}"
         M = B * R * R
         ops.layernorm(x, sd[p + ".ln_1.weight"], sd[p + ".ln_1.bias"], out_split=u)
-        ops.gemm_tc(u, ws[p + ".attn.in_proj_weight"], sd[p + ".attn.in_proj_bias"], out=qkv)
         kind = i % 3
         if kind == 0:
+            ops.gemm_tc(u, ws[p + ".attn.in_proj_weight"], sd[p + ".attn.in_proj_bias"], out=qkv)
             kc, vc = caches[i]
             for s_ in range(n_pos):
                 ops.temporal_attn_step(qkv[s_ * M:(s_ + 1) * M], kc, vc, None, pos0 + s_, self.scale, out_split=u[:, s_ * M:(s_ + 1) * M])
+            a = u
         else:
-            assert R == 16, "the full-sequence path uses the 16x16 axial kernel"
-            ops.axial_attn(qkv, None, B=n_pos * B, R=R, n_head=self.n_head, axis=kind, scale=self.scale, out_split=u)
-        ops.gemm_tc(u, ws[p + ".attn.out_proj.weight"], sd[p + ".attn.out_proj.bias"], residual=x, out=x)
+            assert R == 16, "the full-sequence path uses the 16x16 axial kernels"
+            if self.fused_axial:
+                a = torch.empty_like(u)
+                ops.qkv_axial_attn_tc(u, ws[p + ".attn.in_proj_weight.axial"], self.axial_bias[i], a, n_img=n_pos * B, R=R,
+                                      n_head=self.n_head, axis=kind, scale=self.scale)
+            else:
+                ops.gemm_tc(u, ws[p + ".attn.in_proj_weight"], sd[p + ".attn.in_proj_bias"], out=qkv)
+                ops.axial_attn(qkv, None, B=n_pos * B, R=R, n_head=self.n_head, axis=kind, scale=self.scale, out_split=u)
+                a = u
+        ops.gemm_tc(a, ws[p + ".attn.out_proj.weight"], sd[p + ".attn.out_proj.bias"], residual=x, out=x)
         ops.layernorm(x, sd[p + ".ln_2.weight"], sd[p + ".ln_2.bias"], out_split=u)
         ops.gemm_tc(u, ws[p + ".mlp.c_fc.weight"], sd[p + ".mlp.c_fc.bias"], act=ACT_QUICKGELU, want=(), out_split=h)
         ops.gemm_tc(h, ws[p + ".mlp.c_proj.weight"], sd[p + ".mlp.c_proj.bias"], residual=x, out=x)

@@ -210,6 +210,31 @@ def gemm_tc(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = Non
     return out, out_split, out_split_relu
 
 
+def permute_qkv_for_axial(w_in: torch.Tensor, b_in: torch.Tensor, n_head: int):
+    """nn.MultiheadAttention's packed in-projection (rows [q(C) | k(C) | v(C)], mage_model.py:20) re-ordered for
+    mage_qkv_axial_attn_tc: every 192-row tile = [q|k|v] x 32 of two heads.  Returns (weight [3C, K], bias [3C])."""
+    C = w_in.shape[0] // 3
+    idx = torch.arange(3 * C, device=w_in.device).view(3, n_head, 32)          # [part, head, d] -> old row
+    perm = idx.permute(1, 0, 2).reshape(-1)                                     # new order: head, part, d
+    return w_in[perm].contiguous(), b_in[perm].contiguous()
+
+
+def qkv_axial_attn_tc(a: torch.Tensor, w_perm: torch.Tensor, bias_perm: torch.Tensor, out_split: torch.Tensor, *, n_img: int, R: int,
+                      n_head: int, axis: int, scale: float) -> torch.Tensor:
+    """Fused QKV projection + H (axis=1) / W (axis=2) axial attention: a split [2, n_img*R*R, K] -> out_split [2, n_img*R*R, C]
+    (see mage_b200.h).  `out_split` must not alias `a`."""
+    _f16(a), _f16(w_perm), _f16(out_split)
+    M, K = a.shape[1], a.shape[2]
+    C = n_head * 32
+    assert M == n_img * R * R and tuple(w_perm.shape[1:]) == (3 * C, K) and tuple(out_split.shape[1:]) == (M, C)
+    assert out_split.data_ptr() != a.data_ptr()
+    with _Prof("gemm", 2.0 * M * 3 * C * K):
+        check(_lib.lib().mage_qkv_axial_attn_tc(_ctx(), _p(a), M * K, _p(w_perm), 3 * C * K, _p(_f32(bias_perm)), _p(out_split), M * C,
+                                                n_img, R, n_head, K, axis, scale, _p(flag(a.device)), _stream()),
+              "mage_qkv_axial_attn_tc")
+    return out_split
+
+
 def conv2d_tc(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, pad=(0, 0),
               residual: Optional[torch.Tensor] = None, res_mode: int = 0, act: int = ACT_NONE, want=("f32",),
               out: Optional[torch.Tensor] = None, out_split: Optional[torch.Tensor] = None,

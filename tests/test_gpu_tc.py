@@ -329,3 +329,35 @@ def test_conv2d_tc_single_pass_is_fp16_grade_not_fp32_grade(n, H, Cin, Cout, til
     _close(o1, rounded)
     err = (o1.cpu().double() - exact).abs().max().item() / exact.abs().max().item()
     assert 2e-5 < err < 3e-3, err
+
+
+@pytest.mark.parametrize("n_img,axis", [(2, 1), (2, 2), (5, 1), (9, 2), (64, 2)])
+def test_fused_qkv_axial_attention(n_img, axis, tile_cfg):
+    """mage_qkv_axial_attn_tc (AxialAttentionBlock.attention of the H / W blocks, mage_model.py:31-33,36-47): one tcgen05 GEMM over
+    the head-permuted packed in-projection whose epilogue runs softmax(q k^T / sqrt(32)) v over the 16 positions of every line.
+    Against an fp64 restatement (nn.MultiheadAttention semantics on the permuted axis) and against the two-kernel form."""
+    ops = _ops()
+    R, H, C = 16, 16, 512
+    M = n_img * R * R
+    u = _rand(M, C, seed=1)
+    w_in = _rand(3 * C, C, seed=2, scale=C ** -0.5)
+    b_in = _rand(3 * C, seed=3, scale=0.1)
+    scale = 32 ** -0.5
+    qkv = (u.double() @ w_in.double().t() + b_in.double()).view(n_img, R, R, 3, H, 32)      # [img, h, w, part, head, d]
+    q, k, v = qkv[:, :, :, 0], qkv[:, :, :, 1], qkv[:, :, :, 2]                             # [img, h, w, head, d]
+    ax = 1 if axis == 1 else 2                                                                  # attended spatial dim
+    mv = lambda t: t.movedim(ax, -2)                                                            # [img, other, head, S, d]
+    att = torch.softmax(mv(q) @ mv(k).transpose(-1, -2) * scale, -1) @ mv(v)
+    want = att.movedim(-2, ax).reshape(M, C)
+    us = ops.split(u.to(DEV))
+    wp, bp = ops.permute_qkv_for_axial(w_in.to(DEV), b_in.to(DEV), H)
+    out = torch.empty(2, M, C, device=DEV, dtype=torch.float16)
+    ops.qkv_axial_attn_tc(us, ops.split(wp), bp, out, n_img=n_img, R=R, n_head=H, axis=axis, scale=scale)
+    torch.cuda.synchronize()
+    ops.check_flag(DEV)
+    _close(_unsplit(out), want, rtol=6e-6)
+    # the two-kernel form (QKV GEMM -> fp32 [M, 3C] -> axial_attn_kernel) agrees to fp32 noise
+    qkv2, _, _ = ops.gemm_tc(us, ops.split(w_in.to(DEV)), b_in.to(DEV))
+    out2 = torch.empty(2, M, C, device=DEV, dtype=torch.float16)
+    ops.axial_attn(qkv2, None, B=n_img, R=R, n_head=H, axis=axis, scale=scale, out_split=out2)
+    assert (_unsplit(out) - _unsplit(out2)).abs().max() <= 4e-6 * want.abs().max()
