@@ -148,6 +148,22 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
   int tcount = 0;
   float amax = 0.f;
   bool pending = false;   // a TMA store of this warp may still be reading the staging tile
+  // HEAD (fused pixel head): nothing is staged for a store, so the staging region holds (a) the eight warps' 512-byte slots of
+  // the final two-warp combine and (b) a [256][4] table (head_w[0][n], head_w[1][n], head_w[2][n], bias[n]): per column ONE
+  // broadcast 16-byte shared-memory read replaces the bias load and three global weight loads, whose latency sat on the
+  // epilogue's dependent chain (ncu, profiles/r02j_*: ~15 % of the stall samples on the first FFMA of each output channel).
+  uint8_t* const hslot = staging + (warp - 2) * 512;
+  const float4* const htab = reinterpret_cast<const float4*>(staging + 4096);
+  if (HEAD) {
+    const int n = (warp - 2) * 32 + lane;   // 256 epilogue threads = the 256 conv channels
+    float4 t;
+    t.x = p.head_cout > 0 ? __ldg(p.head_w + n) : 0.f;
+    t.y = p.head_cout > 1 ? __ldg(p.head_w + p.N + n) : 0.f;
+    t.z = p.head_cout > 2 ? __ldg(p.head_w + 2 * p.N + n) : 0.f;
+    t.w = bias ? __ldg(bias + n) : 0.f;
+    reinterpret_cast<float4*>(staging + 4096)[n] = t;
+    asm volatile("bar.sync 5, 256;" ::: "memory");
+  }
   auto staging_free = [&]() {
     if (pending) {
       if (lane == 0) bulk_wait_read0();
@@ -182,27 +198,33 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
       res_off = (int64_t)(p.res_mod > 0 ? m % p.res_mod : m) * p.ldr;
     }
     if (HEAD && tcount % p.group == 0) hacc[0] = hacc[1] = hacc[2] = 0.f;
+    // Residual row segments are requested EARLY -- the first chunk's before the wait for the MMAs, the following ones at the end of
+    // the previous chunk -- so that their L2 latency is off the epilogue's critical path (ncu, profiles/r02j_*: 20-25 % of the
+    // kernel's stall samples sat on the first use of the residual when it was loaded inside its own chunk).
+    constexpr int c_first = 0, c_step = NS ? 1 : 2;
+    const int c_begin = NS ? half * 4 : half, c_end = NS ? half * 4 + 4 : BN / 32;
+    (void)c_first;
+    float4 rv[8];
+    auto load_res = [&](int c, float4 (&dst)[8]) {
+#ifndef MAGE_EXP_NO_RES
+      if (res_off >= 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[j] = __ldg(reinterpret_cast<const float4*>(res + res_off + nt * BN + c * 32) + j);
+      }
+#endif
+    };
+    load_res(c_begin, rv);
     mbar_wait(tfull0 + 8u * acc, aph);
     tc_fence_after();
     const uint32_t t_main = tmem_base + ((uint32_t)(quad * 32) << 16) + (NS ? half * 256 : acc * C::ACC_COLS);
     const uint32_t t_corr = t_main + (NS ? 128 : kOneAcc ? 0 : BN);
 #pragma unroll 1
-    for (int c = NS ? half * 4 : half; c < (NS ? half * 4 + 4 : BN / 32); c += NS ? 1 : 2) {
+    for (int c = c_begin; c < c_end; c += c_step) {
       const int n = nt * BN + c * 32;
       const int tc_col = NS ? (c & 3) * 32 : c * 32;
       uint32_t rm[32], rc[32];
       tmem_ld32(t_main + tc_col, rm);
       if (!single) tmem_ld32(t_corr + tc_col, rc);
-      // the residual row segment travels while the TMEM loads complete
-      float4 rv[8];
-#ifdef MAGE_EXP_NO_RES
-      if (false) {
-#else
-      if (res_off >= 0) {
-#endif
-#pragma unroll
-        for (int j = 0; j < 8; ++j) rv[j] = __ldg(reinterpret_cast<const float4*>(res + res_off + n) + j);
-      }
       tmem_wait_ld();
       if (NS ? (c & 3) == 3 : c + 2 >= BN / 32) {
         // this warp's last chunk is in registers: hand the TMEM accumulator stage back before the arithmetic
@@ -219,7 +241,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
 #ifdef MAGE_EXP_NO_BIAS
       if (false) {
 #else
-      if (bias) {
+      if (bias && !HEAD) {   // HEAD: the bias comes out of the shared-memory table together with the head weights
 #endif
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -248,19 +270,16 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
         for (int j = 0; j < 32; ++j) v[j] = act_fn<ACT>(v[j]);
       }
       if (HEAD) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, u0 = 0.f, u1 = 0.f, u2 = 0.f;   // two chains per output channel
+        const float4* tab = htab + n;
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-          if (ch < p.head_cout) {
-            float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.head_w + (int64_t)ch * p.N + n) + j);
-              s0 = fmaf(fmaxf(v[4 * j], 0.f), w4.x, s0); s1 = fmaf(fmaxf(v[4 * j + 1], 0.f), w4.y, s1);
-              s0 = fmaf(fmaxf(v[4 * j + 2], 0.f), w4.z, s0); s1 = fmaf(fmaxf(v[4 * j + 3], 0.f), w4.w, s1);
-            }
-            hacc[ch] += s0 + s1;
-          }
+        for (int j = 0; j < 32; j += 2) {
+          const float4 ta = tab[j], tb = tab[j + 1];   // same address in every lane: broadcast
+          const float ra = fmaxf(v[j] + ta.w, 0.f), rb = fmaxf(v[j + 1] + tb.w, 0.f);
+          s0 = fmaf(ra, ta.x, s0); s1 = fmaf(ra, ta.y, s1); s2 = fmaf(ra, ta.z, s2);
+          u0 = fmaf(rb, tb.x, u0); u1 = fmaf(rb, tb.y, u1); u2 = fmaf(rb, tb.z, u2);
         }
+        hacc[0] += s0 + u0; hacc[1] += s1 + u1; hacc[2] += s2 + u2;
       }
 #ifdef MAGE_EXP_NO_STORE
       if (has_out && v[0] == 123456.789f) {
@@ -315,17 +334,20 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
           pending = true;
         }
       }
+      // next chunk's residual: issued as soon as this chunk's values have left the registers, in flight during the staging
+      // hand-off and the next chunk's TMEM loads.  (A register double buffer -- loading it at the TOP of this chunk -- spills at
+      // the 168-register cap of a 320-thread CTA and measured slower: profiles/r02k_residual_prefetch_ab.txt.)
+      if (c + c_step < c_end) load_res(c + c_step, rv);
     }
     if (HEAD && tcount % p.group == p.group - 1) {
       // every thread holds its row's partial sums over this warp's half of the columns; the partner warp (same quadrant,
       // other half: warp + 4) adds its half through the staging tile, then tanh and the planar pixel stores
-      staging_free();
-      *reinterpret_cast<float4*>(stg + lane * 16) = make_float4(hacc[0], hacc[1], hacc[2], 0.f);
+      *reinterpret_cast<float4*>(hslot + lane * 16) = make_float4(hacc[0], hacc[1], hacc[2], 0.f);
       __syncwarp();
       asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
       if (half == 0 && m < M) {
-        const float4 a = *reinterpret_cast<const float4*>(stg + lane * 16);
-        const float4 b = *reinterpret_cast<const float4*>(stg + 4 * 4096 + lane * 16);   // warp + 4's tile
+        const float4 a = *reinterpret_cast<const float4*>(hslot + lane * 16);
+        const float4 b = *reinterpret_cast<const float4*>(hslot + 4 * 512 + lane * 16);   // warp + 4's slot
         const int64_t pix = (int64_t)(oy * p.out_sy + p.out_oy) * p.Wfull + (ox * p.out_sx + p.out_ox);
         const int64_t plane = (int64_t)p.Hfull * p.Wfull;
         float* dst = p.head_out + (int64_t)simg * p.head_img_stride + pix;
@@ -334,7 +356,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
         for (int ch = 0; ch < 3; ++ch)
           if (ch < p.head_cout) dst[ch * plane] = tanhf(sum[ch] + __ldg(p.head_b + ch));
       }
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");   // the partner may reuse its staging tile
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");   // the partner may reuse its slot
     }
   }
   if (lane == 0) bulk_wait0();   // all of this warp's stores have landed before the CTA may exit
