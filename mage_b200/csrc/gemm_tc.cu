@@ -359,7 +359,11 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
       asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");   // the partner may reuse its slot
     }
   }
+#ifdef MAGE_EXP_WAIT_READ   // experiment: only wait until the TMA engine has READ the staging tile (global visibility at grid end)
+  if (lane == 0) bulk_wait_read0();
+#else
   if (lane == 0) bulk_wait0();   // all of this warp's stores have landed before the CTA may exit
+#endif
   if (!(amax <= 65504.f) && p.flag) atomicOr(p.flag, 1);
 }
 
@@ -512,7 +516,11 @@ __device__ __forceinline__ void attn_epilogue_loop(const TcParams& p, const CUte
       pending = true;
     }
   }
+#ifdef MAGE_EXP_WAIT_READ
+  if (lane == 0) bulk_wait_read0();
+#else
   if (lane == 0) bulk_wait0();
+#endif
   if (!(amax <= 65504.f) && p.flag) atomicOr(p.flag, 1);
 }
 
