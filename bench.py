@@ -27,6 +27,11 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# torchrun exports OMP_NUM_THREADS=1 for every rank; the only CPU-heavy work here is rank 0's checker / reference legs (the oracle),
+# which should use the host's cores (measured: 49 s instead of 3 s for the parity leg with one thread)
+if os.environ.get("OMP_NUM_THREADS") == "1" and os.environ.get("RANK", "0") == "0":
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+
 import torch  # noqa: E402
 
 UNIT = "frames/s"
@@ -308,27 +313,10 @@ def run_cuda(args, wl, rank, world, local_rank):
     frames_step = sum_ranks(B * (L - 1))                   # generated frames of one step, all ranks
     value = frames_step * args.steps / (ms_max / 1e3)
     plan = eng._plan(B)
-
-    # ---- parity evidence for the timed configuration: rows 0-1 of this rank's shard against the CPU oracle
-    parity = None
+    parity_tokens = None
     if rank == 0 and not args.no_parity:
-        from oracle import mage_oracle as orc
-        n = min(2, B)
-        _, tokens, tok0 = eng.generate(*dev_in)
-        tokens, tok0 = tokens[:n].cpu(), tok0[:n].cpu()
-        otr = {}
-        t0 = time.perf_counter()
-        torch.set_num_threads(os.cpu_count() or 1)
-        orc.generate_incremental(sd, {k: v[:n] for k, v in batch.items()}, noise[:n] if noise is not None else None, otr)
-        neq = tokens != otr["tokens"]
-        gap = otr["gap"].reshape(neq.shape)
-        first_bad = [int(torch.nonzero(neq[b].flatten(1).any(1))[0]) if neq[b].any() else None for b in range(n)]
-        parity = {"rows": n, "positions": int(neq.numel()), "token_mismatches": int(neq.sum()),
-                  "mismatches_at_reference_gap_ge_5e-5": int((neq & (gap >= 5e-5)).sum()),
-                  "first_frame_vq_index_mismatches": int((tok0 != otr["tok0"].reshape(tok0.shape)).sum()),
-                  "first_diverging_frame_per_row": first_bad, "oracle_seconds": round(time.perf_counter() - t0, 1),
-                  "what": "free-running greedy tokens of rows 0..%d of the timed batch vs oracle.generate_incremental (CPU fp32); a flip at a "
-                          "reference near-tie cascades into the later frames of that row (tests/ re-check those teacher-forced)" % (n - 1)}
+        _, ptok, ptok0 = eng.generate(*dev_in)
+        parity_tokens = (ptok[:min(2, B)].cpu(), ptok0[:min(2, B)].cpu())
 
     # ---- end to end through the public API: pinned host inputs -> H2D -> generate -> D2H of the video
     hb = {"images": host["images"], "text": host["text"], "speed": host["speed"]}
@@ -421,6 +409,27 @@ def run_cuda(args, wl, rank, world, local_rank):
             eager["ratio_e2e_per_gpu"] = round(e2e_value / world / eager["value"], 1)
         except Exception as e:   # context only: never lose the bench line over it
             eager = {"error": f"{type(e).__name__}: {e}"[:300]}
+
+    # ---- parity evidence for the timed configuration: rows 0-1 of this rank's shard against the CPU oracle
+    # (runs after every timed region: the other ranks are past their last barrier, so they do not spin next to the oracle's threads)
+    parity = None
+    if rank == 0 and not args.no_parity:
+        from oracle import mage_oracle as orc
+        n = min(2, B)
+        tokens, tok0 = parity_tokens
+        otr = {}
+        t0 = time.perf_counter()
+        torch.set_num_threads(max(1, (os.cpu_count() or 1) - (world - 1)))
+        orc.generate_incremental(sd, {k: v[:n] for k, v in batch.items()}, noise[:n] if noise is not None else None, otr)
+        neq = tokens != otr["tokens"]
+        gap = otr["gap"].reshape(neq.shape)
+        first_bad = [int(torch.nonzero(neq[b].flatten(1).any(1))[0]) if neq[b].any() else None for b in range(n)]
+        parity = {"rows": n, "positions": int(neq.numel()), "token_mismatches": int(neq.sum()),
+                  "mismatches_at_reference_gap_ge_5e-5": int((neq & (gap >= 5e-5)).sum()),
+                  "first_frame_vq_index_mismatches": int((tok0 != otr["tok0"].reshape(tok0.shape)).sum()),
+                  "first_diverging_frame_per_row": first_bad, "oracle_seconds": round(time.perf_counter() - t0, 1),
+                  "what": "free-running greedy tokens of rows 0..%d of the timed batch vs oracle.generate_incremental (CPU fp32); a flip at a "
+                          "reference near-tie cascades into the later frames of that row (tests/ re-check those teacher-forced)" % (n - 1)}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
