@@ -46,6 +46,10 @@ WORKLOADS = {
                metric="generated frames/sec, Moving-MNIST 64x64x20 b32"),
     "c2": dict(family="mnist", frames=16, batch=1, gflop=13.67, name="Single Moving MNIST 64x64x16", cfg="BASELINE.json configs[1]",
                metric="generated frames/sec, Moving-MNIST 64x64x16 b1"),
+    # BASELINE.json configs[4] names the MAGE+ yaml: the same shape through the use_cids=False branch (continuous 4-channel latents,
+    # GroupNorm head over all slots => suffix re-evaluation, (L-1)L/2 position passes; stand-in first stage)
+    "c5plus": dict(family="caterv2plus", frames=32, batch=64, gflop=None, name="CATER-GEN-v2 MAGE+ 128x128x32 (use_cids=False)",
+                   cfg="BASELINE.json configs[4], mage+_caterv2.yaml branch", metric="generated frames/sec, CATER-v2 MAGE+ 128x128x32 b64"),
 }
 
 
@@ -128,6 +132,23 @@ def cpu_reference_sample(wl, threads: int, ar_iters: int = 0, budget_s: float = 
     torch.set_num_threads(threads)
     L = wl["frames"]
     params, sd, batch, noise = _workload_inputs(wl, 1)
+    if not params["use_cids"]:
+        ref = _reference_model(params, sd)
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            if ref is not None:
+                torch.manual_seed(0)
+                ref.autoregressive_generate(batch)
+                kind = "reference"
+            else:
+                ae = syn.PatchLatentAE(**params["first_stage_config"]["params"])
+                ae.decode(orc.generate_continuous(sd, ae.encode(batch["images"][:, 0]), batch["text"], batch.get("speed"), noise)[0])
+                kind = "port"
+            total = time.perf_counter() - t0
+        return (L - 1) / total, {"kind": kind, "measured_s": total,
+                                 "sample": f"1 prompt of {wl['name']}: one full MAGE.autoregressive_generate call of the "
+                                           f"{'unmodified reference' if kind == 'reference' else 'oracle restatement'} (use_cids=False, "
+                                           f"stand-in first stage), {total:.1f}s on {threads} threads"}
     fsd = {k[len("first_stage_model."):]: v for k, v in sd.items() if k.startswith("first_stage_model.")}
     with torch.no_grad():
         # one warm iteration of the port: predicts the cost of the full call
@@ -223,6 +244,8 @@ def eager_gpu_baseline(wl, dev, batch_n):
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             kind = "the unmodified reference (MAGE.autoregressive_generate, torch eager, PyTorch default precision flags) on the same GPU"
+        elif not params["use_cids"]:
+            raise RuntimeError("no reference copy (oracle/_ref) for the MAGE+ eager-GPU leg")
         else:
             sd_d = {k: v.to(dev) for k, v in sd.items()}
             en = noise.to(dev) if noise is not None else None
@@ -459,6 +482,139 @@ def run_cuda(args, wl, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_cuda_plus(args, wl, rank, world, local_rank):
+    """MAGE+ branch (use_cids=False): the public call is the step -- first-stage encode (plain torch module), the CUDA path between
+    the two first-stage calls (`SamplerEngine.generate_continuous`), first-stage decode.  Same line format as run_cuda."""
+    import torch.distributed as dist
+
+    from mage_b200 import ops, shard
+    from mage_b200.config import instantiate_from_config
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = os.environ.get("MAGE_NCCL_DEBUG", "INFO")
+        os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
+        dist.init_process_group("nccl", device_id=dev)
+    L = wl["frames"]
+    G = args.batch if args.batch > 0 else wl["batch"]
+    params, sd, gbatch, gnoise = _workload_inputs(wl, G)
+    lo, hi = shard.shard_bounds(G, world, rank)
+    B = hi - lo
+    model = instantiate_from_config({"target": "modules.mage_model.MAGE", "params": params})
+    model.load_state_dict(sd)
+    model = model.to(dev).eval()
+    batch = {k: v[lo:hi] for k, v in gbatch.items()}
+    batch["images"] = batch["images"][:, 0:1].contiguous()
+    noise = gnoise[lo:hi].contiguous()
+    host = {k: v.contiguous().pin_memory() for k, v in batch.items()}
+    noise_h = noise.pin_memory()
+    dbatch = {k: v.to(dev) for k, v in host.items()}
+    dnoise = noise_h.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allred(x, op):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    for _ in range(max(args.warmup, 3)):
+        model.autoregressive_generate(dbatch, noise=dnoise)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    n0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        video = model.autoregressive_generate(dbatch, noise=dnoise)
+    e1.record()
+    barrier()
+    ms_max = allred(e0.elapsed_time(e1), dist.ReduceOp.MAX if world > 1 else None)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ops.launch_count() - n0
+    frames_step = allred(B * (L - 1), dist.ReduceOp.SUM if world > 1 else None)
+    value = frames_step * args.steps / (ms_max / 1e3)
+    lat = model.last_latents[:1].cpu()
+    # end to end: pinned host inputs -> H2D -> generate -> the clip in pinned host memory
+    model.autoregressive_generate(host, noise=noise_h, to_host=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = model.autoregressive_generate(host, noise=noise_h, to_host=True)
+        assert not out.is_cuda
+    barrier()
+    e2e_value = frames_step * args.steps / allred(time.perf_counter() - t0, dist.ReduceOp.MAX if world > 1 else None)
+    h2d = sum(v.numel() * v.element_size() for v in host.values()) + noise_h.numel() * 4
+    d2h = out.numel() * 4
+    roof = eager = cpu = parity = None
+    if rank == 0:
+        ops.PROFILE = []
+        model.autoregressive_generate(dbatch, noise=dnoise)
+        torch.cuda.synchronize()
+        prof, ops.PROFILE = ops.PROFILE, None
+        agg = {}
+        for kind, flops, a, b in prof:
+            d = agg.setdefault(kind, [0.0, 0.0, 0])
+            d[0] += flops; d[1] += a.elapsed_time(b); d[2] += 1
+        peaks, how = _peaks()
+        peak = peaks["bf16_tflops_sustained"]
+        g = agg.get("gemm", [0.0, 1.0, 1])
+        ach = g[0] / (g[1] * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "dense GEMM class of the full-sequence block path (tc_gemm_kernel, fused QKV + axial attention)",
+                "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4), "traffic": None,
+                "peak_source": how + ", dense bf16 sustained; 3 fp16 MMAs per product (fp32-grade)", "own_ceiling_frac": round(3 * ach / peak, 4),
+                "launches_per_step": g[2], "breakdown_ms_per_step": {k: {"ms_per_step": round(v[1], 2), "launches": v[2]}
+                                                                      for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])},
+                "how": "sum of algorithmic FLOPs / sum of CUDA-event durations over every launch of the class in one step of rank 0"}
+        if not args.no_parity:
+            from oracle import mage_oracle as orc
+            from mage_b200 import synthetic as syn
+            torch.set_num_threads(max(1, (os.cpu_count() or 1) - (world - 1)))
+            t0 = time.perf_counter()
+            ae = syn.PatchLatentAE(**params["first_stage_config"]["params"])
+            want = orc.generate_continuous(sd, ae.encode(batch["images"][:1, 0]), batch["text"][:1], batch["speed"][:1], noise[:1])
+            err = float((lat - want).abs().max())
+            parity = {"rows": 1, "latent_max_abs_err": err, "latent_max_abs": float(want.abs().max()), "slots": L - 1,
+                      "oracle_seconds": round(time.perf_counter() - t0, 1),
+                      "what": "predicted latents of row 0 of the timed batch vs oracle.generate_continuous (CPU fp32, reference evaluation order)"}
+        if args.eager_gpu > 0:
+            model.invalidate()
+            torch.cuda.empty_cache()
+            try:
+                eager = eager_gpu_baseline(wl, dev, args.eager_gpu)
+                eager["ratio_resident_per_gpu"] = round(value / world / eager["value"], 1)
+            except Exception as e:
+                eager = {"error": f"{type(e).__name__}: {e}"[:300]}
+        if world == 1 and not args.no_cpu:
+            v, info = cpu_reference_sample(wl, os.cpu_count() or 1)
+            cpu = {"value": round(v, 4), "unit": UNIT, "cores": os.cpu_count() or 1, "kind": info["kind"], "sample": info["sample"]}
+        line = {"metric": wl["metric"], "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": round(ms_max / args.steps, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": f"{wl['name']}, global batch {G} ({wl['cfg']})", "family": wl["family"], "frames_length": L,
+                           "global_batch": G, "batch_per_gpu": B, "text_len": TEXT_LEN, "parallelism": f"prompt-shard x{world}, no data-path collective",
+                           "first_stage": "mage_b200.synthetic.PatchLatentAE (stand-in torch module; the shipped AutoencoderKL is not vendored)",
+                           "position_passes": (L - 1) * L // 2, "cuda_graph": False,
+                           "l2": "working set >> L2 (suffix activations up to %.1f GB per tensor); no explicit flush" % ((L - 1) * B * 256 * 2048 * 4 / 1e9)},
+                "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": int(launches), "kernels_per_step": int(launches // args.steps), "roofline": roof, "cpu_baseline": cpu,
+                "clocks": clocks, "parity": parity}
+        if eager is not None:
+            line["eager_gpu_baseline"] = eager
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -490,7 +646,10 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
-    run_cuda(args, wl, rank, world, local_rank)
+    if wl["family"] == "caterv2plus":
+        run_cuda_plus(args, wl, rank, world, local_rank)
+    else:
+        run_cuda(args, wl, rank, world, local_rank)
 
 
 if __name__ == "__main__":

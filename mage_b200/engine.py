@@ -878,7 +878,7 @@ class SamplerEngine:
         ops.gemm_tc(h, ws[p + ".mlp.c_proj.weight"], sd[p + ".mlp.c_proj.bias"], residual=x, out=x)
 
     def generate_continuous(self, z0: torch.Tensor, text: torch.Tensor, speed: Optional[torch.Tensor] = None,
-                            noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+                            noise: Optional[torch.Tensor] = None, trace: Optional[dict] = None) -> torch.Tensor:
         """MAGE+ sampling between the two first-stage calls (mage_model.py:642-689 with use_cids=False): z0 [B,c,R,R] latents of
         frame 0 -> predicted latents [B, L-1, c, R, R].
 
@@ -951,10 +951,18 @@ class SamplerEngine:
             ops.gn_partial(x, part[i:], B, R * R)
             if i + 1 < F_:
                 pred_i = ops.gn_silu_head(hidden[i], part, gnw, gnb, Wo, bo, B, R * R)      # [M, c]: slot i only
+                if trace is not None:
+                    # parity diagnostics: record what this iteration would feed forward and, if asked, feed the GIVEN latents
+                    # instead (teacher forcing: every iteration is then compared under identical inputs, no accumulation)
+                    trace.setdefault("step_pred", []).append(pred_i.view(B, R, R, -1).permute(0, 3, 1, 2).clone())
+                    if trace.get("force_step_pred") is not None:
+                        pred_i = trace["force_step_pred"][:, i].permute(0, 2, 3, 1).reshape(M, -1).contiguous().float()
                 _, f_real_split = features(pred_i)
             else:
                 pred = ops.gn_silu_head(hidden.view(F_ * M, C), part, gnw, gnb, Wo, bo, B, R * R)   # every slot (mage_model.py:689)
         ops.check_flag(dev)
+        if trace is not None and "step_pred" in trace:
+            trace["step_pred"] = torch.stack(trace["step_pred"], 1)   # [B, L-2, c, R, R]
         return pred.view(F_, B, R, R, -1).permute(1, 0, 4, 2, 3).contiguous()
 
     def _frame_to_host(self, video: torch.Tensor, host_video: Optional[torch.Tensor], f: int) -> None:

@@ -83,13 +83,24 @@ class PatchLatentAE(torch.nn.Module):
         self.register_buffer("enc_w", torch.randn(embed_dim, in_channels, k, k, generator=g) * (2.0 / (k * math.sqrt(in_channels))))
         self.register_buffer("dec_w", torch.randn(embed_dim, in_channels, k, k, generator=g) * 0.5)
 
+    # Patchify + plain fp32 matmul instead of conv2d / conv_transpose2d: on CUDA PyTorch's default lets cuDNN run convolutions in
+    # TF32, which at batch 64 moved the latents by ~1e-3 -- the stand-in must be the same function on every device.
     @torch.no_grad()
     def encode(self, x):
-        return torch.nn.functional.conv2d(x.float(), self.enc_w, stride=self.down_ratio)
+        n, c, h, w = x.shape
+        k = self.down_ratio
+        p = x.float().reshape(n, c, h // k, k, w // k, k).permute(0, 2, 4, 1, 3, 5).reshape(n, h // k, w // k, c * k * k)
+        z = p @ self.enc_w.reshape(self.embed_dim, -1).t()
+        return z.permute(0, 3, 1, 2).contiguous()
 
     @torch.no_grad()
     def decode(self, z):
-        return torch.tanh(torch.nn.functional.conv_transpose2d(z.float(), self.dec_w, stride=self.down_ratio))
+        n, e, h, w = z.shape
+        k = self.down_ratio
+        c = self.dec_w.shape[1]
+        y = z.float().permute(0, 2, 3, 1) @ self.dec_w.reshape(e, -1)                 # [n, h, w, c*k*k]
+        y = y.reshape(n, h, w, c, k, k).permute(0, 3, 1, 4, 2, 5).reshape(n, c, h * k, w * k)
+        return torch.tanh(y)
 
 
 # --------------------------------------------------------------------------------------

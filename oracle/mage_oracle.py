@@ -470,5 +470,9 @@ def generate_continuous(sd: SD, z0: torch.Tensor, text: torch.Tensor, speed: Opt
     for i in range(L - 1):
         pred = flat_axial_decoder_continuous(sd, a, token_features(sd, inp))        # [B,L-1,H,W,c]
         if i != L - 2:
+            if trace is not None:   # what iteration i feeds into slot i+1 (differs from the FINAL prediction of slot i: the head's
+                trace.setdefault("step_pred", []).append(pred[:, i].permute(0, 3, 1, 2).clone())   # GroupNorm spans all slots)
             inp[:, i + 1] = embed_latents(sd, pred.permute(0, 1, 4, 2, 3))[:, i]
+    if trace is not None and "step_pred" in trace:
+        trace["step_pred"] = torch.stack(trace["step_pred"], 1)                     # [B, L-2, c, H, W]
     return pred.permute(0, 1, 4, 2, 3).contiguous()
