@@ -272,6 +272,14 @@ int mage_add_scaled_vec_f32(mage_ctx* ctx, float* x, const float* s, const float
 /* out[n,h,w,c] = in[n,c,h,w]  (noise [B,64,16,16] -> NHWC). */
 int mage_nchw_to_nhwc_f32(mage_ctx* ctx, const float* in, float* out, int n_img, int C, int HW, void* stream);
 
+/* Temporal attention of n_pos CONSECUTIVE positions pos0 .. pos0+n_pos-1 in one launch (full-sequence form, used by the MAGE+
+ * suffix re-evaluation; causal mask of mage_model.py:367-372 = "query at position p reads keys 0..p"): qkv rows of position s,
+ * location m at row s*M + m ([n_pos*M, 3*512] fp32); the new k,v rows are appended to the caches ([M][2][Lmax][256], as
+ * mage_temporal_attn_step_f32); out_split = split(attention) with the same row order.  Equivalent to n_pos calls of
+ * mage_temporal_attn_step_f32 (same math order), with the K/V prefix of a location staged once. */
+int mage_temporal_attn_seq_f32(mage_ctx* ctx, const float* qkv, float* kcache, float* vcache, void* out_split, int64_t split_plane,
+                               int* flag, int M, int pos0, int n_pos, int Lmax, float scale, void* stream);
+
 /* MAGE+ continuous head (use_cids=False), mage_model.py:349-354 + :386-388: GroupNorm(groups) over (C/groups channels x all
  * temporal slots x H x W) of a sample -> SiLU -> 1x1x1 Conv3d to `cout` latent channels.
  * mage_gn_partial_f32: x fp32 [n_slots, B, HW, C] -> part double [n_slots, B, groups, 2] = (sum, sum of squares) of each

@@ -48,6 +48,7 @@ SIGNATURES = {
     "mage_mha_f32": [_c_f] + [_c_f] * 4 + [_i] * 5 + [_i64] * 12 + [_c_f, _f32, _c_f, _i64, _c_f, _c_f],
     "mage_axial_attn_f32": [_c_f, _c_f, _c_f, _c_f, _i64, _c_f, _i, _i, _i, _i, _f32, _c_f],
     "mage_temporal_attn_step_f32": [_c_f] + [_c_f] * 5 + [_i64, _c_f, _i, _i, _i, _f32, _c_f],
+    "mage_temporal_attn_seq_f32": [_c_f] + [_c_f] * 4 + [_i64, _c_f, _i, _i, _i, _i, _f32, _c_f],
     "mage_kv_append_f32": [_c_f] + [_c_f] * 3 + [_i] * 4 + [_c_f],
     "mage_vq_argmin_f32": [_c_f] + [_c_f] * 4 + [_i] * 3 + [_c_f],
     "mage_argmax_rows_f32": [_c_f, _c_f, _i64, _c_f, _i, _i, _c_f],

@@ -321,6 +321,89 @@ __global__ void __launch_bounds__(256) temporal_attn_kernel(const float* __restr
   store_attn(out, split, split_plane, flag, (int64_t)m * TA_C + half * TA_HALF + tid, o * inv);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Temporal attention over SEVERAL consecutive positions at once (the full-sequence form of the MAGE+ suffix re-evaluation):
+// the queries of positions pos0 .. pos0+n_pos-1 of one (location, head-half) share one K/V prefix, so it is staged ONCE --
+// cached positions 0..pos0-1 by bulk copy, the n_pos new k,v rows from qkv (also appended to the cache) -- and every query
+// attends keys 0..its own position (causal).  Same grid / warp roles / math order as temporal_attn_kernel, looped over queries.
+//   qkv rows: position s of location m at row s*M + m.
+// ---------------------------------------------------------------------------------------------
+constexpr int TAS_GROUPS = 1;   // query groups: warp = (head, group); group g takes queries g, g+G, ... (measured: 4 groups = 1024-thread
+                                // CTAs are SLOWER, 305 vs 250 ms per MAGE+ generate: the kernel is instruction-bound, not latency-bound)
+__global__ void __launch_bounds__(256 * TAS_GROUPS) temporal_attn_seq_kernel(const float* __restrict__ qkv, float* __restrict__ kcache,
+                                                                float* __restrict__ vcache, __half* __restrict__ split,
+                                                                int64_t split_plane, int* flag, int M, int pos0, int n_pos,
+                                                                int Lmax, float scale) {
+  extern __shared__ __align__(128) float smem[];
+  const int S_all = pos0 + n_pos;
+  float* Ks = smem;
+  float* Vs = smem + (size_t)S_all * TA_HALF;
+  float* Qs = Vs + (size_t)S_all * TA_HALF;      // [n_pos][256]: every query of this (location, half), staged up front so that the
+  __shared__ __align__(8) uint64_t bars[2];      // eight head-warps run through their queries without block-wide barriers
+  const int m = blockIdx.x >> 1, half = blockIdx.x & 1;
+  const int tid = threadIdx.x & 255, grp = threadIdx.x >> 8, warp = tid >> 5, lane = tid & 31;
+  float* kc = kcache + ((int64_t)m * 2 + half) * Lmax * TA_HALF;
+  float* vc = vcache + ((int64_t)m * 2 + half) * Lmax * TA_HALF;
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && pos0 > 0) {
+    const uint32_t bytes = (uint32_t)pos0 * TA_HALF * 4;
+    mbar_expect_tx(&bars[0], bytes);
+    bulk_g2s(Ks, kc, bytes, &bars[0]);
+    mbar_expect_tx(&bars[1], bytes);
+    bulk_g2s(Vs, vc, bytes, &bars[1]);
+  }
+  for (int s = grp; s < n_pos; s += TAS_GROUPS) {   // staging is shared out over the groups too
+    const float* row = qkv + ((int64_t)s * M + m) * 3 * TA_C + half * TA_HALF;
+    const float kv = row[TA_C + tid], vv = row[2 * TA_C + tid];
+    Qs[(size_t)s * TA_HALF + tid] = row[tid];
+    Ks[(size_t)(pos0 + s) * TA_HALF + tid] = kv;
+    Vs[(size_t)(pos0 + s) * TA_HALF + tid] = vv;
+    kc[(int64_t)(pos0 + s) * TA_HALF + tid] = kv;
+    vc[(int64_t)(pos0 + s) * TA_HALF + tid] = vv;
+  }
+  __syncthreads();
+  if (pos0 > 0) {
+    mbar_wait(&bars[0], 0);
+    mbar_wait(&bars[1], 0);
+  }
+  for (int s = grp; s < n_pos; s += TAS_GROUPS) {
+    const int S = pos0 + s + 1;
+    const float* qh = Qs + (size_t)s * TA_HALF + warp * 32;
+    float sc[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int j = lane + t * 32;
+      sc[t] = -INFINITY;
+      if (j < S) {
+        const float* kr = Ks + (size_t)j * TA_HALF + warp * 32;
+        float d = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int dd = (i + lane) & 31;
+          d = fmaf(qh[dd], kr[dd], d);
+        }
+        sc[t] = d * scale;
+      }
+    }
+    const float mx = warp_max(fmaxf(sc[0], sc[1]));
+    const float p0 = (lane < S) ? expf(sc[0] - mx) : 0.f;
+    const float p1 = (lane + 32 < S) ? expf(sc[1] - mx) : 0.f;
+    const float inv = 1.f / warp_sum(p0 + p1);
+    float o = 0.f;
+    for (int j = 0; j < S; ++j) {
+      const float pj = __shfl_sync(0xffffffffu, j < 32 ? p0 : p1, j & 31);
+      o = fmaf(pj, Vs[(size_t)j * TA_HALF + warp * 32 + lane], o);
+    }
+    store_attn(nullptr, split, split_plane, flag, ((int64_t)s * M + m) * TA_C + half * TA_HALF + tid, o * inv);
+  }
+}
+
 }  // namespace
 
 extern "C" int mage_mha_f32(mage_ctx* ctx, const float* q, const float* k, const float* v, float* out, int n_outer, int n_inner, int n_head,
@@ -379,5 +462,28 @@ extern "C" int mage_temporal_attn_step_f32(mage_ctx* ctx, const float* qkv, floa
   }
   mage_launch_pdl(ctx, temporal_attn_kernel, (unsigned)M * 2, 256, smem, as_stream(stream), 1, qkv, kcache, vcache, out,
                   reinterpret_cast<__half*>(out_split), split_plane, flag, pos, Lmax, scale);
+  return mage_post_launch(ctx);
+}
+
+extern "C" int mage_temporal_attn_seq_f32(mage_ctx* ctx, const float* qkv, float* kcache, float* vcache, void* out_split,
+                                          int64_t split_plane, int* flag, int M, int pos0, int n_pos, int Lmax, float scale,
+                                          void* stream) {
+  MAGE_CHECK_CTX(ctx);
+  MAGE_CHECK_ARG(M > 0 && pos0 >= 0 && n_pos > 0 && pos0 + n_pos <= Lmax && Lmax <= 64 && out_split != nullptr);
+  MAGE_CHECK_ARG(aligned16(qkv) && aligned16(kcache) && aligned16(vcache));
+  const size_t smem = (size_t)(2 * (pos0 + n_pos) + n_pos) * TA_HALF * sizeof(float);
+  const size_t smem_max = (size_t)3 * Lmax * TA_HALF * sizeof(float);
+  if (smem_max > 48 * 1024) {
+    const void* fn = reinterpret_cast<const void*>(&temporal_attn_seq_kernel);
+    int k = ctx->find(fn);
+    if (k < 0 || ctx->cfg_smem[k] < smem_max) {
+      cudaError_t e = cudaFuncSetAttribute(temporal_attn_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+      if (e != cudaSuccess) return (int)e;
+      if (k < 0) k = ctx->add(fn, 0, smem_max);
+      if (k >= 0) ctx->cfg_smem[k] = smem_max;
+    }
+  }
+  temporal_attn_seq_kernel<<<(unsigned)M * 2, 256 * TAS_GROUPS, smem, as_stream(stream)>>>(qkv, kcache, vcache, reinterpret_cast<__half*>(out_split),
+                                                                           split_plane, flag, M, pos0, n_pos, Lmax, scale);
   return mage_post_launch(ctx);
 }

@@ -859,8 +859,10 @@ class SamplerEngine:
         if kind == 0:
             ops.gemm_tc(u, ws[p + ".attn.in_proj_weight"], sd[p + ".attn.in_proj_bias"], out=qkv)
             kc, vc = caches[i]
-            for s_ in range(n_pos):
-                ops.temporal_attn_step(qkv[s_ * M:(s_ + 1) * M], kc, vc, None, pos0 + s_, self.scale, out_split=u[:, s_ * M:(s_ + 1) * M])
+            if n_pos == 1:
+                ops.temporal_attn_step(qkv, kc, vc, None, pos0, self.scale, out_split=u)
+            else:   # the K/V prefix of a location is staged once for all n_pos queries
+                ops.temporal_attn_seq(qkv, kc, vc, pos0, n_pos, self.scale, out_split=u)
             a = u
         else:
             assert R == 16, "the full-sequence path uses the 16x16 axial kernels"

@@ -392,6 +392,17 @@ def temporal_attn_step(qkv: torch.Tensor, kcache: torch.Tensor, vcache: torch.Te
                                                      M, pos, Lmax, scale, _stream()), "mage_temporal_attn_step_f32")
 
 
+def temporal_attn_seq(qkv: torch.Tensor, kcache: torch.Tensor, vcache: torch.Tensor, pos0: int, n_pos: int, scale: float,
+                      out_split: torch.Tensor) -> None:
+    """n_pos consecutive temporal positions in one launch: qkv [n_pos*M, 3C] (position-major), out_split [2, n_pos*M, C]."""
+    M = kcache.shape[0]
+    assert qkv.shape[0] == n_pos * M and _f16(out_split).shape[1] == n_pos * M
+    with _Prof("temporal_attn", 8.0 * M * kcache.shape[2] * sum(pos0 + s + 1 for s in range(n_pos)) / max(n_pos, 1) * 1.0):
+        check(_lib.lib().mage_temporal_attn_seq_f32(_ctx(), _p(_f32(qkv)), _p(kcache), _p(vcache), _p(out_split), out_split.stride(0),
+                                                    _p(flag(qkv.device)), M, pos0, n_pos, kcache.shape[1], scale, _stream()),
+              "mage_temporal_attn_seq_f32")
+
+
 def kv_append(qkv: torch.Tensor, kcache: torch.Tensor, vcache: torch.Tensor, pos: int) -> None:
     M, C3 = qkv.shape
     with _Prof("kv_append", 0.0):

@@ -380,3 +380,25 @@ def test_handles_are_independent():
     assert L.mage_ctx_destroy(h) == 0
     h2 = ctypes.c_void_p()
     assert L.mage_ctx_create(99, ctypes.byref(h2)) != 0 and not h2.value   # no such device
+
+
+@pytest.mark.parametrize("M,pos0,n_pos,Lmax", [(64, 0, 5, 8), (33, 3, 4, 10), (16, 9, 23, 32), (8, 31, 1, 32)])
+def test_temporal_attn_seq_equals_position_by_position(M, pos0, n_pos, Lmax):
+    """mage_temporal_attn_seq_f32 (n_pos consecutive positions in one launch, the K/V prefix staged once) against n_pos calls of
+    mage_temporal_attn_step_f32: same math order -> bit-identical attention output and cache contents."""
+    from mage_b200 import ops
+    C = 512
+    g = torch.Generator().manual_seed(5)
+    qkv = torch.randn(n_pos * M, 3 * C, generator=g).cuda()
+    pre = torch.randn(2, M, Lmax, C, generator=g).cuda()
+    k1, v1 = pre[0].clone(), pre[1].clone()
+    k2, v2 = pre[0].clone(), pre[1].clone()
+    scale = 32 ** -0.5
+    u1 = torch.zeros(2, n_pos * M, C, device="cuda", dtype=torch.float16)
+    u2 = torch.zeros_like(u1)
+    for s in range(n_pos):
+        ops.temporal_attn_step(qkv[s * M:(s + 1) * M], k1, v1, None, pos0 + s, scale, out_split=u1[:, s * M:(s + 1) * M])
+    ops.temporal_attn_seq(qkv, k2, v2, pos0, n_pos, scale, out_split=u2)
+    torch.cuda.synchronize()
+    assert torch.equal(u1, u2)
+    assert torch.equal(k1, k2) and torch.equal(v1, v2)
