@@ -59,7 +59,8 @@ int mage_ctx_device(mage_ctx* ctx);
 int64_t mage_launch_count(mage_ctx* ctx);
 
 /* enable != 0: the kernels of the per-step path are launched with the programmatic-stream-serialization attribute (they call
- * griddepcontrol.launch_dependents / .wait themselves).  Default off (MAGE_PDL=1 turns it on): measured neutral on B200. */
+ * griddepcontrol.launch_dependents / .wait themselves).  Default on (MAGE_PDL=0 turns it off): the next kernel's launch latency and
+ * prologue overlap the previous kernel's tail -- 3 % per generate at 8 prompts per GPU, neutral at 64; results are bit-identical. */
 int mage_pdl(mage_ctx* ctx, int enable);
 
 /* C[M,N] = act(relu_a?(A)[M,K] . W[N,K]^T + bias[N]) + residual

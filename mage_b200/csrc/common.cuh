@@ -17,7 +17,7 @@ struct mage_ctx {
   int halo = 1;                          // mage_tc_conv_halo
   int small = 1;                         // one-tile cost model for sub-2-wave GEMMs (MAGE_TC_SMALL)
   int resident = 1;                      // resident weight slots in the halo convolution when they fit (MAGE_TC_RESIDENT)
-  int pdl = 0;                           // mage_pdl
+  int pdl = 1;                           // mage_pdl
   int64_t launches = 0;
   static constexpr int kMaxKernels = 64;
   const void* cfg_fn[kMaxKernels] = {};  // kernels whose attributes have been set on `device`
@@ -77,7 +77,7 @@ __device__ __forceinline__ float warp_max(float v) {
 // kernel's CTAs may then be scheduled as soon as SM resources free up, i.e. its prologue (barrier init, TMEM allocation,
 // descriptor prefetch) and its launch latency overlap this kernel's tail -- and pdl_wait() before their first global-memory
 // access, which blocks until the preceding grid has completed and flushed.  Both are no-ops for a kernel launched without the
-// attribute.  MAGE_PDL=0 launches everything with plain stream order.
+// attribute.  On by default (mage_ctx::pdl); MAGE_PDL=0 launches everything with plain stream order.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 

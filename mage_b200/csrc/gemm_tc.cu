@@ -573,10 +573,35 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
-  pdl_wait();   // prologue done (barriers, TMEM, descriptor prefetch): now wait for the producer grid of our operands
+  // Programmatic dependent launch: this grid may have started while its predecessor is still running.  Everything that does not
+  // depend on the predecessor -- barriers, TMEM, descriptor prefetch above, and the WEIGHT tiles of the first pipeline stages
+  // below -- happens before griddepcontrol.wait; activations (A tiles, residuals) only after it.
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (every CTA loads its A rows + its W rows)
+    int pre = 0;   // stages of the first tile whose W tile (and expect_tx) were issued ahead of the dependency wait
+    if (!NS) {
+      const int tile0 = tile_of(0, unit, n_units, p.group);
+      if (tile0 < num_tiles) {
+        pre = p.k_iters < C::STAGES ? p.k_iters : C::STAGES;
+        const int w_row0 = (tile0 % p.n_tiles) * BN + cta_rank * C::W_ROWS;
+        for (int it = 0; it < pre; ++it) {
+          const uint32_t sa = base + it * C::STAGE_BYTES;
+          if (CG == 2) {
+            const uint32_t fb = mapa_u32(full_bar(it), 0);
+            if (elect_one()) {
+              if (cta_rank == 0) mbar_expect_tx(full_bar(it), 2 * C::STAGE_BYTES);
+              tma_load_3d_2sm(sa + C::A_BYTES, &mapW, fb, it * BK, w_row0, 0);
+            }
+          } else if (elect_one()) {
+            mbar_expect_tx(full_bar(it), C::STAGE_BYTES);
+            tma_load_3d(sa + C::A_BYTES, &mapW, full_bar(it), it * BK, w_row0, 0);
+          }
+          __syncwarp();
+        }
+      }
+    }
+    pdl_wait();
     {
       int itg = 0;
       for (int ti = 0;; ++ti) {
@@ -603,23 +628,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const int ky = tap / p.KW, kx = tap - ky * p.KW;
             a0 = cb * BK; a1 = c1 + kx; a2 = c2 + ky;
           }
+          const bool w_done = ti == 0 && it < pre;   // expect_tx + W tile of this stage went out before the dependency wait
           if (CG == 2) {
             // both CTAs' bytes land on the LEADER's full barrier: the MMA thread there consumes both halves
             const uint32_t fb = mapa_u32(full_bar(s), 0);
             if (elect_one()) {
-              if (cta_rank == 0) mbar_expect_tx(full_bar(s), 2 * C::STAGE_BYTES);
+              if (cta_rank == 0 && !w_done) mbar_expect_tx(full_bar(s), 2 * C::STAGE_BYTES);
               tma_load_5d_2sm(sa, &mapA, fb, a0, a1, a2, c3, 0);
               if (NS) {   // two 64-row boxes: this CTA's share of each 128-column half
                 tma_load_3d_2sm(sa + C::A_BYTES, &mapW, fb, it * BK, w_row, 0);
                 tma_load_3d_2sm(sa + C::A_BYTES + C::W_BYTES / 2, &mapW, fb, it * BK, w_row + 128, 0);
-              } else {
+              } else if (!w_done) {
                 tma_load_3d_2sm(sa + C::A_BYTES, &mapW, fb, it * BK, w_row, 0);
               }
             }
           } else if (elect_one()) {
-            mbar_expect_tx(full_bar(s), C::STAGE_BYTES);
+            if (!w_done) mbar_expect_tx(full_bar(s), C::STAGE_BYTES);
             tma_load_5d(sa, &mapA, full_bar(s), a0, a1, a2, c3, 0);
-            tma_load_3d(sa + C::A_BYTES, &mapW, full_bar(s), it * BK, w_row, 0);
+            if (!w_done) tma_load_3d(sa + C::A_BYTES, &mapW, full_bar(s), it * BK, w_row, 0);
           }
           __syncwarp();
         }
@@ -628,6 +654,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (the leader CTA; one elected lane issues)
+    pdl_wait();
     if (cta_rank == 0 && NS) {
       constexpr uint32_t idesc = umma_idesc_f16(128, BM * CG);
       int itg = 0, tcount = 0;
@@ -713,6 +740,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     __syncwarp();
   } else {
     // ------------------------------------------------------------ epilogue warps
+    pdl_wait();   // residuals are the predecessor's output
     if (BN == 192 && p.attn) {
       if constexpr (BN == 192) attn_epilogue_loop<BN, CG>(p, &mapS, tmem_base, staging, tfull_bar(0), tempty_bar(0));
     } else if ((BN == 256 || BN == 128) && p.head_w) {
@@ -818,10 +846,38 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
-  pdl_wait();   // prologue done (barriers, TMEM, descriptor prefetch): now wait for the producer grid of our operands
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
+    // resident weights do not depend on the predecessor grid: all of them go out BEFORE griddepcontrol.wait (PDL), so the weight
+    // fetch of this layer overlaps the tail of the previous one; activations only after the wait
+    bool w_pre = false;
+    if (p.w_resident) {
+      for (int g = 0; g < p.group; ++g) {
+        const int tile = tile_of(g, unit, n_units, p.group);
+        if (tile >= num_tiles) break;
+        const int w_row = (tile % p.n_tiles) * BN + cta_rank * H::W_ROWS;
+        for (int cb = 0; cb < p.cin_blocks; ++cb)
+          for (int tap = 0; tap < p.taps; ++tap) {
+            const int s = (g * p.cin_blocks + cb) * p.taps + tap;
+            const uint32_t dst = w_base + s * w_slot_bytes;
+            const int k0 = (tap * p.cin_blocks + cb) * BK;
+            if (CG == 2) {
+              const uint32_t fb = mapa_u32(w_full(s), 0);
+              if (elect_one()) {
+                if (cta_rank == 0) mbar_expect_tx(w_full(s), 2 * p.w_tx_bytes);
+                tma_load_3d_2sm(dst, &mapW, fb, k0, w_row, 0);
+              }
+            } else if (elect_one()) {
+              mbar_expect_tx(w_full(s), p.w_tx_bytes);
+              tma_load_3d(dst, &mapW, w_full(s), k0, w_row, 0);
+            }
+            __syncwarp();
+          }
+      }
+      w_pre = true;
+    }
+    pdl_wait();
     {
       int ia = 0, iw = 0;
       for (int ti = 0;; ++ti) {
@@ -853,8 +909,8 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           for (int tap = 0; tap < p.taps; ++tap, ++iw) {
             int s;
             if (p.w_resident) {
-              // every weight tile of this CTA has its own slot and is fetched once: during the first group of tiles
-              if (ti >= p.group) continue;
+              // every weight tile of this CTA has its own slot and was fetched once, ahead of the dependency wait
+              if (w_pre || ti >= p.group) continue;
               s = ((ti % p.group) * p.cin_blocks + cb) * p.taps + tap;
             } else {
               s = iw % SW;
@@ -880,6 +936,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (leader CTA; one elected lane issues)
+    pdl_wait();
     if (cta_rank == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(BN, BM * CG);
       const uint32_t sbo = (uint32_t)p.halo_w * 128u;
@@ -950,6 +1007,7 @@ tc_conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     __syncwarp();
   } else {
     // ------------------------------------------------------------ epilogue warps
+    pdl_wait();   // residuals are the predecessor's output
     if ((BN == 256 || BN == 128) && p.head_w) {
       if constexpr (BN == 256 || BN == 128) epilogue_loop<BN, CG, MAGE_ACT_NONE, true>(p, &mapO, &mapS, &mapR, tmem_base, staging, tfull_bar(0), tempty_bar(0));
     } else

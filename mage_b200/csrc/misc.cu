@@ -7,9 +7,10 @@
 
 extern "C" int mage_abi_version(void) { return 5; }
 
-// One handle per (process, device).  Environment variables only seed a new handle's switches: MAGE_PDL (measured on B200: no
-// gain over plain graph launches, 157.9 vs 155.9 ms per generate -> off), MAGE_TC_BN / MAGE_TC_PAIR / MAGE_TC_NS / MAGE_TC_HALO /
-// MAGE_TC_SMALL (tile selection, see gemm_tc.cu).
+// One handle per (process, device).  Environment variables only seed a new handle's switches: MAGE_PDL (programmatic dependent
+// launch of the per-step kernels: ON -- same-box A/B, profiles/r02z_pdl_ab.txt: 22.29 -> 21.56 ms per generate at 8 prompts, 36.3 ->
+// 35.6 at 16, neutral at 64), MAGE_TC_BN / MAGE_TC_PAIR / MAGE_TC_NS / MAGE_TC_HALO / MAGE_TC_SMALL / MAGE_TC_RESIDENT (tile
+// selection, see gemm_tc.cu).
 extern "C" int mage_ctx_create(int device, mage_ctx** out) {
   if (!out) return MAGE_EINVAL;
   *out = nullptr;
@@ -25,7 +26,7 @@ extern "C" int mage_ctx_create(int device, mage_ctx** out) {
   c->device = device;
   c->sms = sms > 0 ? sms : 148;
   auto env = [](const char* k, int d) { const char* v = getenv(k); return v ? atoi(v) : d; };
-  c->pdl = env("MAGE_PDL", 0);
+  c->pdl = env("MAGE_PDL", 1);
   c->forced_bn = env("MAGE_TC_BN", 0);
   c->forced_pair = env("MAGE_TC_PAIR", -1);
   c->ns = env("MAGE_TC_NS", 1);

@@ -317,7 +317,7 @@ def test_optional_schedules_are_bit_exact():
             assert torch.equal(model.last_tokens, ref_tok) and (got2 - ref).abs().max() < 2e-4
             eng.fused_axial = True
     finally:
-        ops.pdl(False)
+        ops.pdl(True)   # the default
 
 
 def test_graph_cache_is_bounded_and_shares_one_pool():
