@@ -44,6 +44,18 @@ def global_noise(batch: int, res: int = 16, seed: Optional[int] = None) -> torch
     return torch.randn(batch, 64, res, res, generator=g)
 
 
+def noise_for_prompts(seed: int, indices, res: int = 16) -> torch.Tensor:
+    """N(0,1) [len(indices), 64, res, res] where row i depends only on (seed, indices[i]) -- the GLOBAL index of the prompt in the
+    dataset.  With a seed, a prompt's AdaIN noise (mage_model.py:661) -- and therefore its clip -- is the same whichever rank,
+    batch or world size it is generated in (results must not depend on the number of GPUs)."""
+    out = torch.empty(len(indices), 64, res, res)
+    g = torch.Generator(device="cpu")
+    for j, idx in enumerate(indices):
+        g.manual_seed((int(seed) * 1000003 + int(idx)) & 0x7FFFFFFFFFFFFFFF)
+        out[j] = torch.randn(64, res, res, generator=g)
+    return out
+
+
 def env_world() -> Tuple[int, int, int]:
     """(rank, world, local_rank) as torchrun exports them; (0, 1, 0) for a plain launch."""
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))

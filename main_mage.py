@@ -139,12 +139,20 @@ def sampling(opt):
     t0 = time.perf_counter()
     with torch.no_grad():
         idx = 0
+        seen = 0
         for batch in test_dataloader:
             video_ids = batch.pop('video_id', None)
             for k in batch.keys():
                 batch[k] = batch[k].to(device)
-            for _ in range(opt.n_samples):
-                generated = model.autoregressive_generate(batch)
+            n_here = batch['text'].shape[0]
+            for rep in range(opt.n_samples):
+                noise = None
+                if opt.seed is not None and getattr(model, 'randomness', False):
+                    # additive: with --seed a prompt's AdaIN noise depends only on (seed, sample repetition, GLOBAL prompt index), so
+                    # the clips do not depend on the batch size or on how many GPUs share the prompt list; without --seed the noise
+                    # comes from the process's default CPU generator inside the call, exactly like the reference (mage_model.py:661)
+                    noise = shard.noise_for_prompts(opt.seed + 7919 * rep, range(lo + seen, lo + seen + n_here), model.image_resolution)
+                generated = model.autoregressive_generate(batch) if noise is None else model.autoregressive_generate(batch, noise=noise)
                 generated.clamp_(min=-1, max=1)
                 frames += generated.shape[0] * (generated.shape[1] - 1)
             if opt.out or opt.gifs:
@@ -158,6 +166,7 @@ def sampling(opt):
                         save_gifs(clips[b], name, opt.test_model)
             print(idx)
             idx += 1
+            seen += n_here
     if torch.cuda.is_available():
         torch.cuda.synchronize()
     secs = time.perf_counter() - t0

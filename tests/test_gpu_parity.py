@@ -487,6 +487,28 @@ def test_small_and_odd_shapes_vs_oracle(family, L, B):
                  label=f"{family} L={L} B={B}")
 
 
+def test_main_mage_seeded_clips_do_not_depend_on_batch_size(tmp_path):
+    """`--seed`: a prompt's AdaIN noise is a function of (seed, global prompt index), so the clips written by the entry are the same
+    for --batch-size 1 and 3 (and therefore for any prompt-shard over GPUs)."""
+    import yaml
+
+    import main_mage
+    params = syn.model_params("caterv2", frames_length=3)
+    (tmp_path / "config.yaml").write_text(yaml.safe_dump({"model": {"target": "modules.mage_model.MAGE", "params": params},
+                                                          "data": {"target": "dataload.CATER", "params": {}}}))
+    torch.save({"state_dict": syn.make_mage_state_dict(params)}, tmp_path / "model_best.pth")
+    clips = {}
+    for bs in (1, 3):
+        out = tmp_path / f"clips{bs}"
+        opt = main_mage.parser.parse_args(["--split", "test", "--test_model", str(tmp_path / "model_best.pth"), "--synthetic", "4",
+                                           "--batch-size", str(bs), "--seed", "5", "--out", str(out)])
+        assert main_mage.sampling(opt) == 4 * 2
+        clips[bs] = {p.name: np.load(p) for p in sorted(out.glob("*.npy"))}
+    assert len(clips[1]) == 4 and clips[1].keys() == clips[3].keys()
+    for k in clips[1]:
+        assert np.array_equal(clips[1][k], clips[3][k]), k
+
+
 def test_main_mage_caption_and_image_prompt(tmp_path):
     """Additive entry: one clip from a caption (the dataset's word-level vocabulary) and a first-frame image file."""
     import yaml

@@ -248,3 +248,19 @@ def test_moving_mnist_reader(tmp_path):
     batch = collate_fn([a, b])
     assert tuple(batch["text"].shape) == (2, max(len(a["text"]), len(b["text"]))) and "video_id" not in batch
     assert " the digit 3" in ds.decode(a["text"][1:4])
+
+
+def test_seeded_noise_depends_only_on_the_global_prompt_index():
+    """main_mage.py --seed: a prompt's AdaIN noise is a function of (seed, global index) -- independent of batch size and of the
+    rank / world size that generates it."""
+    from mage_b200 import shard
+    full = shard.noise_for_prompts(11, range(0, 12))
+    assert tuple(full.shape) == (12, 64, 16, 16) and abs(float(full.mean())) < 0.02 and abs(float(full.std()) - 1) < 0.02
+    for world in (1, 2, 3, 5):
+        parts = []
+        for rank in range(world):
+            lo, hi = shard.shard_bounds(12, world, rank)
+            for b0 in range(lo, hi, 4):                       # batches of <= 4 inside the rank's slice
+                parts.append(shard.noise_for_prompts(11, range(b0, min(b0 + 4, hi))))
+        assert torch.equal(torch.cat(parts), full)
+    assert not torch.equal(shard.noise_for_prompts(12, range(0, 2)), full[:2])
