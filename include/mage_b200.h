@@ -146,6 +146,17 @@ int mage_gemm_tc(mage_ctx* ctx, const void* A, int64_t lda, int64_t a_plane, con
                  void* C_split_relu, int64_t ldc, int64_t c_plane, int M, int N, int K, int act, int* flag,
                  void* stream);
 
+/* mage_gemm_tc for the two GEMMs that write the residual stream (attention out-projection and c_proj, N = 512, fp32 result with
+ * residual, no activation: mage_model.py:50-51) with the FOLLOWING LayerNorm (ln_2 of the block / ln_1 of the next, :49-51) fused:
+ *   C[M,512] = A . W^T + bias + residual        and        ln_split = split(LayerNorm_{gamma,beta,eps}(C))   (the next GEMM's operand)
+ * A LayerNorm needs whole rows while the GEMM is tiled over N, so every CTA, once the stores of a tile are complete and visible
+ * device-wide, bumps ln_count[128-row block]; the CTA that brings it to N / tile_width normalises those 128 rows (read back with
+ * ld.global.cg) -- same arithmetic as mage_layernorm_f32, row by row, so the result does not depend on which CTA does it.
+ * ln_count: int32 [ceil(M / 128)], zero before the first call; the kernel leaves it zero.  residual may alias C. */
+int mage_gemm_tc_ln(mage_ctx* ctx, const void* A, int64_t lda, int64_t a_plane, const void* W, int64_t ldw, int64_t w_plane,
+                    const float* bias, const float* residual, int64_t ldr, float* C, int M, int K, const float* ln_gamma,
+                    const float* ln_beta, float ln_eps, void* ln_split, int64_t ln_plane, int* ln_count, int* flag, void* stream);
+
 /* Fused QKV projection + axial attention of the H / W blocks (AxialAttentionBlock.attention, mage_model.py:31-33, with the
  * permutes of :36-47 expressed in tensor maps): for rows ordered (img, h, w) of A = split(ln_1(x)) [n_img*R*R, K],
  *   out = softmax(q k^T * scale) v   per (img, line, head) over the R = 16 positions of the attended axis
@@ -254,6 +265,12 @@ int mage_embedding_f32(mage_ctx* ctx, const int64_t* idx, const float* table, fl
  * tok int64 [n_img, R, R]; zero padding outside the map; C = 512; out fp32 [n_img*R*R, C]. */
 int mage_token_taps_f32(mage_ctx* ctx, const int64_t* tok, const float* table, const float* pos_bias, const float* bias, float* out,
                         int n_img, int R, int K, int C, int KH, int KW, void* stream);
+
+/* mage_token_taps_f32 that also applies the FIRST block's ln_1 (mage_model.py:49, eps 1e-5) to each finished row and writes it as
+ * the split operand of that block's QKV projection: ln_split = split(LayerNorm(out)), plane stride ln_plane elements. */
+int mage_token_taps_ln_f32(mage_ctx* ctx, const int64_t* tok, const float* table, const float* pos_bias, const float* bias, float* out,
+                           int n_img, int R, int K, int C, int KH, int KW, const float* ln_gamma, const float* ln_beta, float ln_eps,
+                           void* ln_split, int64_t ln_plane, int* flag, void* stream);
 
 /* Text-encoder front end (mage_model.py:224-237): x[b,t,:] = LN_eps(tok_emb[text[b,t]] + pos_emb[t]) * (text[b,t] != pad);
  * key_len[b] = #non-pad tokens.  C = 512.  tok_emb has `vocab` rows: an id outside [0, vocab) -- on which the reference's

@@ -38,6 +38,8 @@ SIGNATURES = {
     "mage_embedding_split": [_c_f, _c_f, _c_f, _i64, _c_f, _i64, _i, _i, _c_f],
     "mage_gemm_tc": [_c_f, _c_f, _i64, _i64, _c_f, _i64, _i64, _c_f, _c_f, _i64, _i, _c_f, _c_f, _c_f, _i64, _i64, _i, _i, _i, _i,
                      _c_f, _c_f],
+    "mage_gemm_tc_ln": [_c_f, _c_f, _i64, _i64, _c_f, _i64, _i64, _c_f, _c_f, _i64, _c_f, _i, _i, _c_f, _c_f, _f32, _c_f, _i64, _c_f, _c_f, _c_f],
+    "mage_token_taps_ln_f32": [_c_f] + [_c_f] * 5 + [_i] * 6 + [_c_f, _c_f, _f32, _c_f, _i64, _c_f, _c_f],
     "mage_qkv_axial_attn_tc": [_c_f, _c_f, _i64, _c_f, _i64, _c_f, _c_f, _i64, _i, _i, _i, _i, _i, _f32, _c_f, _c_f],
     "mage_conv2d_tc": [_c_f, _c_f, _i64, _c_f, _i64, _c_f, _c_f, _c_f, _c_f, _c_f, _i64] + [_i] * 19 + [_i64, _i, _c_f, _c_f],
     "mage_conv2d_tc_pixel_head": [_c_f, _c_f, _i64, _c_f, _i64, _c_f, _c_f] + [_i] * 12 + [_c_f, _c_f, _i, _c_f, _i64, _i, _c_f, _c_f],

@@ -75,6 +75,14 @@ struct TcParams {
   // with fp32 accumulation, for layers whose result feeds no token (the last VQ-VAE decoder block: DESIGN.md "decoder
   // precision budget"); only the hi planes are fetched (w_tx_bytes / a_tx_bytes halve) and the corr accumulator is never read.
   int passes, w_tx_bytes;
+  // fused LayerNorm of the rows this GEMM completes (mage_gemm_tc_ln): the CTA whose tile is the LAST of a 128-row block to become
+  // globally visible (ln_count[row block] reaches n_tiles) normalises those rows of `out` into ln_split (the next GEMM's operand)
+  const float* ln_gamma;
+  const float* ln_beta;
+  __half* ln_split;
+  int64_t ln_plane;
+  int* ln_count;
+  float ln_eps;
   // fused QKV projection + axial attention (mage_qkv_axial_attn_tc): the N tile holds [q|k|v] x 32 columns of two heads, the
   // epilogue runs softmax(q k^T * attn_scale) v over the 16 positions of each line and stores only the attention output
   int attn;
@@ -123,10 +131,65 @@ __device__ __forceinline__ float act_fn(float x) {
 // NS ("N-split", BN = 256 pair tiles): the tile's two 128-column halves are separate accumulators [main_h | corr_h] with their
 // own full/empty barriers; epilogue warp (quadrant, hw) drains half hw, so the MMA issuer can start the next tile's half 0
 // while half 1 is still being drained -- a 256-wide tile (A fetched once per 256 output columns) without giving up overlap.
+// LayerNorm of NR rows (C = 512) by one warp, the math of layernorm_kernel<4> (misc.cu) -- two-pass statistics in registers, same
+// element-to-lane layout and summation order, so the result is bit-identical to the separate kernel's.  The rows were written by
+// OTHER CTAs' TMA stores, which this SM's L1 may not have seen: ld.global.cg.  NR rows are loaded before any is reduced, so the
+// L2 round trips overlap (one row at a time would put 16 dependent round trips on the tail of the GEMM).
+template <int NR>
+__device__ __forceinline__ bool ln_rows_512(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                            __half* __restrict__ split, int64_t plane, int64_t row0, int M, float eps, int lane) {
+  constexpr int C = 512, NV = 4;
+  float4 v[NR][NV];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    const int64_t row = row0 + r < M ? row0 + r : M - 1;
+    const float4* src = reinterpret_cast<const float4*>(x + row * C);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[r][i] = __ldcg(src + i * 32 + lane);
+  }
+  bool bad = false;
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float a = v[r][i].x - mean, b = v[r][i].y - mean, c = v[r][i].z - mean, d = v[r][i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * (1.f / C) + eps);
+    if (row0 + r < M) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + i * 32 + lane);
+        float4 o;
+        o.x = (v[r][i].x - mean) * rstd * g.x + b.x;
+        o.y = (v[r][i].y - mean) * rstd * g.y + b.y;
+        o.z = (v[r][i].z - mean) * rstd * g.z + b.z;
+        o.w = (v[r][i].w - mean) * rstd * g.w + b.w;
+        uint2 hi, lo;
+        bad |= split4(o, hi, lo);
+        const int64_t e = (row0 + r) * C + (i * 32 + lane) * 4;
+        *reinterpret_cast<uint2*>(split + e) = hi;
+        *reinterpret_cast<uint2*>(split + plane + e) = lo;
+      }
+    }
+  }
+  return bad;
+}
+
 template <int BN, int CG, int ACT, bool HEAD = false, bool NS = false>
 __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorMap* mapO, const CUtensorMap* mapS,
                                               const CUtensorMap* mapR, uint32_t tmem_base, uint8_t* staging, uint32_t tfull0,
-                                              uint32_t tempty0) {
+                                              uint32_t tempty0, volatile int* s_flag = nullptr) {
   using C = Cfg<BN, CG>;
   const int cta_rank = CG == 2 ? (int)cluster_ctarank() : 0;
   const int unit = blockIdx.x / CG, n_units = gridDim.x / CG;   // a unit = the CTA (pair) that owns a tile
@@ -148,6 +211,35 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
   int tcount = 0;
   float amax = 0.f;
   bool pending = false;   // a TMA store of this warp may still be reading the staging tile
+  // Fused LayerNorm (p.ln_count): called one tile LATE (at the top of the next tile, and once after the loop), when the stores of
+  // row block `mt_done` issued by this CTA have long been in flight: wait for their completion, make them visible device-wide,
+  // bump the row block's counter; whichever CTA brings it to n_tiles has every column of those 128 rows visible and normalises
+  // them (8 warps x 16 rows).  Which CTA that is does not matter for the result: LayerNorm is per row, the order inside a row fixed.
+  bool ln_bad = false;
+  auto ln_finish = [&](int mt_done) {
+    if (mt_done * BM >= p.M) return;   // CTA-uniform (the padding row tile of an odd pair)
+    if (lane == 0) bulk_wait0();
+    __syncwarp();
+    pending = false;
+    fence_proxy_async();
+    __threadfence();
+    asm volatile("bar.sync 6, 256;" ::: "memory");
+    if (warp == 2 && lane == 0) {
+      const int old = atomicAdd(p.ln_count + mt_done, 1);
+      const int last = old == p.n_tiles - 1;
+      if (last) p.ln_count[mt_done] = 0;   // self-resetting: every contribution of this launch has been counted
+      *s_flag = last;
+    }
+    asm volatile("bar.sync 6, 256;" ::: "memory");
+    if (*s_flag) {
+      __threadfence();
+      const int r0 = mt_done * BM + (warp - 2) * 16;
+#pragma unroll 1
+      for (int r = r0; r < r0 + 16 && r < p.M; r += 4)
+        ln_bad |= ln_rows_512<4>(p.out, p.ln_gamma, p.ln_beta, p.ln_split, p.ln_plane, r, p.M, p.ln_eps, lane);
+    }
+  };
+  int mt_prev = -1;
   // HEAD (fused pixel head): nothing is staged for a store, so the staging region holds (a) the eight warps' 512-byte slots of
   // the final two-warp combine and (b) a [256][4] table (head_w[0][n], head_w[1][n], head_w[2][n], bias[n]): per column ONE
   // broadcast 16-byte shared-memory read replaces the bias load and three global weight loads, whose latency sat on the
@@ -178,6 +270,8 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
     const int mt = (tile / n_tiles) * CG + cta_rank, nt = tile % n_tiles;
     const int acc = NS ? half : tcount % C::ACC_STAGES;
     const uint32_t aph = NS ? (tcount & 1) : (tcount / C::ACC_STAGES) & 1;
+    if (!HEAD && p.ln_count && mt_prev >= 0) ln_finish(mt_prev);
+    mt_prev = mt;
     // the thread's row, the warp's store-box origin and the residual offset: once per tile
     const int r = quad * 32 + lane, m = mt * BM + r;
     int sx0 = mt * BM + quad * 32, sy0 = 0, simg = 0, oy = 0, ox = 0;
@@ -359,6 +453,8 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& p, const CUtensorM
       asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");   // the partner may reuse its slot
     }
   }
+  if (!HEAD && p.ln_count && mt_prev >= 0) ln_finish(mt_prev);
+  if (ln_bad && p.flag) atomicOr(p.flag, 1);
 #ifdef MAGE_EXP_WAIT_READ   // experiment: only wait until the TMA engine has READ the staging tile (global visibility at grid end)
   if (lane == 0) bulk_wait_read0();
 #else
@@ -747,7 +843,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       if constexpr (BN == 256 || BN == 128) epilogue_loop<BN, CG, MAGE_ACT_NONE, true>(p, &mapO, &mapS, &mapR, tmem_base, staging, tfull_bar(0), tempty_bar(0));
     } else
     switch (p.act & 0xff) {
-      case MAGE_ACT_NONE: epilogue_loop<BN, CG, MAGE_ACT_NONE, false, NS>(p, &mapO, &mapS, &mapR, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
+      case MAGE_ACT_NONE: epilogue_loop<BN, CG, MAGE_ACT_NONE, false, NS>(p, &mapO, &mapS, &mapR, tmem_base, staging, tfull_bar(0), tempty_bar(0),
+                                                                          reinterpret_cast<volatile int*>(tmem_slot + 1)); break;
       case MAGE_ACT_RELU: epilogue_loop<BN, CG, MAGE_ACT_RELU, false, NS>(p, &mapO, &mapS, &mapR, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
       case MAGE_ACT_QUICKGELU: epilogue_loop<BN, CG, MAGE_ACT_QUICKGELU, false, NS>(p, &mapO, &mapS, &mapR, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
       case MAGE_ACT_GELU: epilogue_loop<BN, CG, MAGE_ACT_GELU, false, NS>(p, &mapO, &mapS, &mapR, tmem_base, staging, tfull_bar(0), tempty_bar(0)); break;
@@ -1436,10 +1533,13 @@ extern "C" int mage_embedding_split(mage_ctx* ctx, const int64_t* idx, const voi
   return mage_post_launch(ctx);
 }
 
-extern "C" int mage_gemm_tc(mage_ctx* ctx, const void* A, int64_t lda, int64_t a_plane, const void* W, int64_t ldw, int64_t w_plane,
-                            const float* bias, const float* residual, int64_t ldr, int res_mod, float* C, void* C_split,
-                            void* C_split_relu, int64_t ldc, int64_t c_plane, int M, int N, int K, int act, int* flag,
-                            void* stream) {
+namespace {
+struct LnArgs { const float* gamma; const float* beta; float eps; void* split; int64_t plane; int* count; };
+
+int gemm_tc_impl(mage_ctx* ctx, const void* A, int64_t lda, int64_t a_plane, const void* W, int64_t ldw, int64_t w_plane,
+                 const float* bias, const float* residual, int64_t ldr, int res_mod, float* C, void* C_split,
+                 void* C_split_relu, int64_t ldc, int64_t c_plane, int M, int N, int K, int act, int* flag,
+                 void* stream, const LnArgs* ln) {
   MAGE_CHECK_CTX(ctx);
   MAGE_CHECK_ARG(M > 0 && N > 0 && K > 0);
   if (K % BK != 0 || N % 64 != 0) return MAGE_ENOTSUP;
@@ -1447,8 +1547,9 @@ extern "C" int mage_gemm_tc(mage_ctx* ctx, const void* A, int64_t lda, int64_t a
   MAGE_CHECK_ARG(ldc % 4 == 0 && (!C || aligned16(C)) && (!bias || aligned16(bias)) && (!residual || (aligned16(residual) && ldr % 4 == 0)));
   MAGE_CHECK_ARG(c_plane % 4 == 0 && (C || C_split || C_split_relu));
   const int m_tiles = (M + BM - 1) / BM;
-  const TileCfg tcfg = pick_cfg(ctx, N, m_tiles, K, true);
+  TileCfg tcfg = pick_cfg(ctx, N, m_tiles, K, true);
   if (!tcfg.bn) return MAGE_ENOTSUP;
+  if (ln && tcfg.ns) tcfg.ns = 0;   // the N-split epilogue (two half-tile drains) has no fused LayerNorm: plain 256x256 pair tile
   const int bn = tcfg.bn;
   Maps mp{};
   CUtensorMap& mapA = mp.A;
@@ -1474,7 +1575,32 @@ extern "C" int mage_gemm_tc(mage_ctx* ctx, const void* A, int64_t lda, int64_t a
     int r = make_store_maps(&mp, C, C_split, C_split_relu, c_plane, N, M, 1, 1, ldc, ldc * (int64_t)M, ldc * (int64_t)M, 32, 1);
     if (r) return r;
   }
+  if (ln) {
+    // the fused LayerNorm reads whole rows of the fp32 result: N = row width = 512, dense rows, no activation in between
+    MAGE_CHECK_ARG(C != nullptr && N == 512 && ldc == 512 && (act & 0xff) == MAGE_ACT_NONE && ln->gamma && ln->beta && ln->split && ln->count &&
+                   aligned16(ln->gamma) && aligned16(ln->beta) && (reinterpret_cast<uintptr_t>(ln->split) & 7) == 0 && ln->plane % 4 == 0);
+    p.ln_gamma = ln->gamma; p.ln_beta = ln->beta; p.ln_eps = ln->eps; p.ln_split = reinterpret_cast<__half*>(ln->split);
+    p.ln_plane = ln->plane; p.ln_count = ln->count;
+  }
   return dispatch(ctx, tcfg, mp, p, as_stream(stream));
+}
+}  // namespace
+
+extern "C" int mage_gemm_tc(mage_ctx* ctx, const void* A, int64_t lda, int64_t a_plane, const void* W, int64_t ldw, int64_t w_plane,
+                            const float* bias, const float* residual, int64_t ldr, int res_mod, float* C, void* C_split,
+                            void* C_split_relu, int64_t ldc, int64_t c_plane, int M, int N, int K, int act, int* flag,
+                            void* stream) {
+  return gemm_tc_impl(ctx, A, lda, a_plane, W, ldw, w_plane, bias, residual, ldr, res_mod, C, C_split, C_split_relu, ldc, c_plane, M, N, K,
+                      act, flag, stream, nullptr);
+}
+
+extern "C" int mage_gemm_tc_ln(mage_ctx* ctx, const void* A, int64_t lda, int64_t a_plane, const void* W, int64_t ldw, int64_t w_plane,
+                               const float* bias, const float* residual, int64_t ldr, float* C, int M, int K, const float* ln_gamma,
+                               const float* ln_beta, float ln_eps, void* ln_split, int64_t ln_plane, int* ln_count, int* flag,
+                               void* stream) {
+  const LnArgs ln{ln_gamma, ln_beta, ln_eps, ln_split, ln_plane, ln_count};
+  return gemm_tc_impl(ctx, A, lda, a_plane, W, ldw, w_plane, bias, residual, ldr, 0, C, nullptr, nullptr, 512, (int64_t)M * 512, M, 512, K,
+                      MAGE_ACT_NONE, flag, stream, &ln);
 }
 
 // Fused QKV projection + axial (H / W) attention of one temporal position (or of a batch of positions): mage_b200.h.

@@ -141,7 +141,9 @@ __global__ void __launch_bounds__(256) embedding_kernel(const int64_t* __restric
 template <int NV>
 __global__ void __launch_bounds__(256) token_taps_kernel(const int64_t* __restrict__ tok, const float* __restrict__ table,
                                                          const float* __restrict__ pos_bias, const float* __restrict__ bias,
-                                                         float* __restrict__ out, int n_pix, int R, int K, int KH, int KW) {
+                                                         float* __restrict__ out, int n_pix, int R, int K, int KH, int KW,
+                                                         const float* __restrict__ ln_gamma, const float* __restrict__ ln_beta,
+                                                         float ln_eps, __half* __restrict__ ln_split, int64_t ln_plane, int* flag) {
   pdl_launch_dependents();
   pdl_wait();
   constexpr int C4 = NV * 32;
@@ -174,6 +176,39 @@ __global__ void __launch_bounds__(256) token_taps_kernel(const int64_t* __restri
   float4* dst = reinterpret_cast<float4*>(out) + (int64_t)pix * C4;
 #pragma unroll
   for (int i = 0; i < NV; ++i) dst[i * 32 + lane] = acc[i];
+  if (ln_split) {
+    // the row is complete in this warp's registers: the first block's ln_1 (mage_model.py:49) right here, same math as
+    // layernorm_kernel (two-pass statistics), emitted as the split operand of the QKV projection -- one launch less per step
+    constexpr int C = NV * 128;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += (acc[i].x + acc[i].y) + (acc[i].z + acc[i].w);
+    const float mean = warp_sum(s) * (1.f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float a = acc[i].x - mean, b = acc[i].y - mean, c = acc[i].z - mean, d = acc[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + ln_eps);
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(ln_gamma) + i * 32 + lane);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(ln_beta) + i * 32 + lane);
+      float4 o;
+      o.x = (acc[i].x - mean) * rstd * g.x + b.x;
+      o.y = (acc[i].y - mean) * rstd * g.y + b.y;
+      o.z = (acc[i].z - mean) * rstd * g.z + b.z;
+      o.w = (acc[i].w - mean) * rstd * g.w + b.w;
+      uint2 hi, lo;
+      bad |= tc::split4(o, hi, lo);
+      const int64_t e = (int64_t)pix * C + (i * 32 + lane) * 4;
+      *reinterpret_cast<uint2*>(ln_split + e) = hi;
+      *reinterpret_cast<uint2*>(ln_split + ln_plane + e) = lo;
+    }
+    if (bad && flag) atomicOr(flag, 1);
+  }
 }
 
 // ------------------------------------------------------------------ 2x2 max pool NHWC
@@ -526,7 +561,23 @@ extern "C" int mage_token_taps_f32(mage_ctx* ctx, const int64_t* tok, const floa
   MAGE_CHECK_ARG(aligned16(table) && aligned16(pos_bias) && aligned16(bias) && aligned16(out));
   const int n_pix = n_img * R * R;
   cudaError_t e = mage_launch_pdl(ctx, token_taps_kernel<4>, dim3((n_pix + 7) / 8), dim3(256), 0, as_stream(stream), 1, tok, table, pos_bias,
-                                  bias, out, n_pix, R, K, KH, KW);
+                                  bias, out, n_pix, R, K, KH, KW, (const float*)nullptr, (const float*)nullptr, 0.f, (__half*)nullptr,
+                                  (int64_t)0, (int*)nullptr);
+  if (e != cudaSuccess) return (int)e;
+  return mage_post_launch(ctx);
+}
+
+extern "C" int mage_token_taps_ln_f32(mage_ctx* ctx, const int64_t* tok, const float* table, const float* pos_bias, const float* bias,
+                                      float* out, int n_img, int R, int K, int C, int KH, int KW, const float* ln_gamma,
+                                      const float* ln_beta, float ln_eps, void* ln_split, int64_t ln_plane, int* flag, void* stream) {
+  MAGE_CHECK_CTX(ctx);
+  MAGE_CHECK_ARG(n_img > 0 && R > 0 && K > 0 && C == 512 && KH > 0 && KW > 0 && (KH & 1) && (KW & 1));
+  MAGE_CHECK_ARG(aligned16(table) && aligned16(pos_bias) && aligned16(bias) && aligned16(out) && ln_gamma && ln_beta && ln_split &&
+                 aligned16(ln_gamma) && aligned16(ln_beta) && (reinterpret_cast<uintptr_t>(ln_split) & 7) == 0 && ln_plane % 4 == 0);
+  const int n_pix = n_img * R * R;
+  cudaError_t e = mage_launch_pdl(ctx, token_taps_kernel<4>, dim3((n_pix + 7) / 8), dim3(256), 0, as_stream(stream), 1, tok, table, pos_bias,
+                                  bias, out, n_pix, R, K, KH, KW, ln_gamma, ln_beta, ln_eps, reinterpret_cast<__half*>(ln_split), ln_plane,
+                                  flag);
   if (e != cudaSuccess) return (int)e;
   return mage_post_launch(ctx);
 }

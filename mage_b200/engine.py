@@ -469,6 +469,16 @@ class SamplerEngine:
             # H / W blocks: QKV projection and the 16x16 axial attention run as ONE kernel (mage_qkv_axial_attn_tc) on a
             # head-permuted copy of the packed in-projection; MAGE_FUSED_AXIAL=0 keeps the two-kernel form (tests compare them)
             self.fused_axial = os.environ.get("MAGE_FUSED_AXIAL", "1") != "0" and self.R == 16 and (self.C // 32) % 2 == 0
+            # LayerNorm fused into the kernel that produces its input; every form gives the same bits (tests compare them).
+            #   fused_ln_taps (MAGE_FUSED_LN != 0, default): mage_token_taps_ln_f32 applies the first block's ln_1 to the row its
+            #     warp has just finished -- one launch less per step, no synchronisation involved.
+            #   fused_ln (MAGE_FUSED_LN=all, OFF by default): mage_gemm_tc_ln -- the out-projection applies the block's ln_2, c_proj
+            #     the next block's ln_1 (11 more launches less per step).  A row spans several CTAs' tiles, so the CTA that
+            #     completes a 128-row block normalises it; that completion hand-off costs more than the launch it saves: measured
+            #     7 % SLOWER at 64 prompts, 17 % slower at 8 (profiles/r02aa_fused_layernorm_ab.txt).  Kept as a tested option.
+            mode = os.environ.get("MAGE_FUSED_LN", "taps")
+            self.fused_ln_taps = mode != "0" and self.C == 512
+            self.fused_ln = mode in ("all", "2") and self.C == 512
             self.axial_bias = {}
             for i in range(self.n_blocks):
                 bp = p + f"blocks.{i}."
@@ -651,50 +661,56 @@ class SamplerEngine:
             return o.view(-1, self.C), f.view(2, -1, self.C)
         return f.view(2, -1, self.C)
 
-    def _block_step_tc(self, i: int, x: torch.Tensor, pos: int, B: int, caches, bufs, last: bool):
+    def _block_step_tc(self, i: int, x: torch.Tensor, pos: int, B: int, caches, bufs, last: bool, ln1_done: bool = False):
         """AxialAttentionBlock (mage_model.py:35-53) for one temporal position, dense contractions on tcgen05.
-        x [B*R*R, C] fp32 residual stream (updated in place); LayerNorm / attention emit split operands."""
+        x [B*R*R, C] fp32 residual stream (updated in place); LayerNorm / attention emit split operands.
+        With `fused_ln` the two GEMMs that write x also emit split(LayerNorm(x)) for the GEMM that follows (ln_2 of this block after
+        the out-projection, ln_1 of block i+1 after c_proj); `ln1_done`: bufs["u"] already holds split(ln_1(x)) on entry."""
         sd, ws, C, R = self.sd, self.ws, self.C, self.R
         p = f"generate_model.blocks.{i}"
         M = x.shape[0]
-        u, h, qkv = bufs["u"], bufs["h"], bufs["qkv"]
-        ops.layernorm(x, sd[p + ".ln_1.weight"], sd[p + ".ln_1.bias"], out_split=u)
+        u, a, h, qkv = bufs["u"], bufs["a"], bufs["h"], bufs["qkv"]
+        fused_ln = self.fused_ln
+        if not ln1_done:
+            ops.layernorm(x, sd[p + ".ln_1.weight"], sd[p + ".ln_1.bias"], out_split=u)
         kind = i % 3
         if kind != 0 and self.fused_axial:
-            a = bufs["a"]
             ops.qkv_axial_attn_tc(u, ws[p + ".attn.in_proj_weight.axial"], self.axial_bias[i], a, n_img=B, R=R, n_head=self.n_head,
                                   axis=kind, scale=self.scale)
-            ops.gemm_tc(a, ws[p + ".attn.out_proj.weight"], sd[p + ".attn.out_proj.bias"], residual=x, out=x)
-            ops.layernorm(x, sd[p + ".ln_2.weight"], sd[p + ".ln_2.bias"], out_split=u)
-            ops.gemm_tc(u, ws[p + ".mlp.c_fc.weight"], sd[p + ".mlp.c_fc.bias"], act=ACT_QUICKGELU, want=(), out_split=h)
-            ops.gemm_tc(h, ws[p + ".mlp.c_proj.weight"], sd[p + ".mlp.c_proj.bias"], residual=x, out=x,
-                        out_split=u if last else None)
-            return x
-        ops.gemm_tc(u, ws[p + ".attn.in_proj_weight"], sd[p + ".attn.in_proj_bias"], out=qkv)
-        if kind == 0:
-            kc, vc = caches[i]
-            if self.temporal_attn == "tma":
-                ops.temporal_attn_step(qkv, kc, vc, None, pos, self.scale, out_split=u)
-            else:
-                ops.kv_append(qkv, kc, vc, pos)
-                Lmax = kc.shape[1]
-                ops.mha(qkv, kc, vc, None, n_outer=M, n_inner=1, n_head=self.n_head, Sq=1, Sk=pos + 1,
-                        q_strides=(3 * C, 0, 0), k_strides=(Lmax * C, 0, C), v_strides=(Lmax * C, 0, C),
-                        o_strides=(C, 0, 0), key_len=None, scale=self.scale, out_split=u)
         else:
-            if R == 16:
-                ops.axial_attn(qkv, None, B=B, R=R, n_head=self.n_head, axis=kind, scale=self.scale, out_split=u)
+            ops.gemm_tc(u, ws[p + ".attn.in_proj_weight"], sd[p + ".attn.in_proj_bias"], out=qkv)
+            if kind == 0:
+                kc, vc = caches[i]
+                if self.temporal_attn == "tma":
+                    ops.temporal_attn_step(qkv, kc, vc, None, pos, self.scale, out_split=a)
+                else:
+                    ops.kv_append(qkv, kc, vc, pos)
+                    Lmax = kc.shape[1]
+                    ops.mha(qkv, kc, vc, None, n_outer=M, n_inner=1, n_head=self.n_head, Sq=1, Sk=pos + 1,
+                            q_strides=(3 * C, 0, 0), k_strides=(Lmax * C, 0, C), v_strides=(Lmax * C, 0, C),
+                            o_strides=(C, 0, 0), key_len=None, scale=self.scale, out_split=a)
+            elif R == 16:
+                ops.axial_attn(qkv, None, B=B, R=R, n_head=self.n_head, axis=kind, scale=self.scale, out_split=a)
             else:
                 inner, seq = (1, R) if kind == 1 else (R, 1)
                 ops.mha(qkv, qkv[:, C:], qkv[:, 2 * C:], None, n_outer=B, n_inner=R, n_head=self.n_head, Sq=R, Sk=R,
                         q_strides=(R * R * 3 * C, inner * 3 * C, seq * 3 * C), k_strides=(R * R * 3 * C, inner * 3 * C, seq * 3 * C),
                         v_strides=(R * R * 3 * C, inner * 3 * C, seq * 3 * C), o_strides=(R * R * C, inner * C, seq * C),
-                        key_len=None, scale=self.scale, out_split=u)
-        ops.gemm_tc(u, ws[p + ".attn.out_proj.weight"], sd[p + ".attn.out_proj.bias"], residual=x, out=x)
-        ops.layernorm(x, sd[p + ".ln_2.weight"], sd[p + ".ln_2.bias"], out_split=u)
+                        key_len=None, scale=self.scale, out_split=a)
+        if fused_ln:
+            ops.gemm_tc_ln(a, ws[p + ".attn.out_proj.weight"], sd[p + ".attn.out_proj.bias"], residual=x, out=x,
+                           gamma=sd[p + ".ln_2.weight"], beta=sd[p + ".ln_2.bias"], ln_out=u, counters=bufs["ln_count"])
+        else:
+            ops.gemm_tc(a, ws[p + ".attn.out_proj.weight"], sd[p + ".attn.out_proj.bias"], residual=x, out=x)
+            ops.layernorm(x, sd[p + ".ln_2.weight"], sd[p + ".ln_2.bias"], out_split=u)
         ops.gemm_tc(u, ws[p + ".mlp.c_fc.weight"], sd[p + ".mlp.c_fc.bias"], act=ACT_QUICKGELU, want=(), out_split=h)
-        ops.gemm_tc(h, ws[p + ".mlp.c_proj.weight"], sd[p + ".mlp.c_proj.bias"], residual=x, out=x,
-                    out_split=u if last else None)  # the head reads split(x)
+        if fused_ln and not last and i + 1 < self.n_blocks:
+            q = f"generate_model.blocks.{i + 1}"
+            ops.gemm_tc_ln(h, ws[p + ".mlp.c_proj.weight"], sd[p + ".mlp.c_proj.bias"], residual=x, out=x,
+                           gamma=sd[q + ".ln_1.weight"], beta=sd[q + ".ln_1.bias"], ln_out=u, counters=bufs["ln_count"])
+        else:
+            ops.gemm_tc(h, ws[p + ".mlp.c_proj.weight"], sd[p + ".mlp.c_proj.bias"], residual=x, out=x,
+                        out_split=u if last else None)  # the head reads split(x)
         return x
 
     # ------------------------------------------------------------------ whole path
@@ -734,11 +750,14 @@ class SamplerEngine:
             bufs = {"u": torch.empty(2, M, C, device=self.device, dtype=torch.float16),
                     "a": torch.empty(2, M, C, device=self.device, dtype=torch.float16),
                     "h": torch.empty(2, M, 4 * C, device=self.device, dtype=torch.float16),
-                    "qkv": torch.empty(M, 3 * C, device=self.device, dtype=torch.float32)}
+                    "qkv": torch.empty(M, 3 * C, device=self.device, dtype=torch.float32),
+                    # arrival counters of mage_gemm_tc_ln, one per 128-row block; every launch leaves them zero
+                    "ln_count": torch.zeros((M + 127) // 128, device=self.device, dtype=torch.int32)}
         else:
             x = ops.gemm(anchor.view(M, C), sd[p + "context_linear.weight"], self.bias_ctx0)
         for i in range(self.n_blocks):
-            x = self._block_step_tc(i, x, 0, B, caches, bufs, False) if tc else self._block_step(i, x, 0, B, caches)
+            x = (self._block_step_tc(i, x, 0, B, caches, bufs, False, ln1_done=self.fused_ln and i > 0) if tc
+                 else self._block_step(i, x, 0, B, caches))
         logits = torch.empty(M, sd[p + "out.weight"].shape[0], device=self.device, dtype=torch.float32)
         return dict(B=B, x=x, caches=caches, bufs=bufs, logits=logits, tok=tok0_out)
 
@@ -750,13 +769,19 @@ class SamplerEngine:
         B, x, caches, bufs, logits, tok = st["B"], st["x"], st["caches"], st["bufs"], st["logits"], st["tok"]
         if self.backend == "tc":
             ws = self.ws
-            if self.tok_table is not None:
+            ln1 = False
+            if self.tok_table is not None and self.fused_ln_taps:
+                ops.token_taps_ln(tok.view(B, R, R), self.tok_table, self.tok_posW, self.bias_in_T[j + 1], x,
+                                  sd[p + "blocks.0.ln_1.weight"], sd[p + "blocks.0.ln_1.bias"], bufs["u"])
+                ln1 = True
+            elif self.tok_table is not None:
                 ops.token_taps(tok.view(B, R, R), self.tok_table, self.tok_posW, self.bias_in_T[j + 1], x)
             else:
                 f = self._token_features_tc(tok, B)
                 ops.gemm_tc(f, ws[p + "in_linear.weight"], self.bias_in_T[j + 1], out=x)
             for i in range(self.n_blocks):
-                x = self._block_step_tc(i, x, j + 1, B, caches, bufs, i + 1 == self.n_blocks)
+                x = self._block_step_tc(i, x, j + 1, B, caches, bufs, i + 1 == self.n_blocks,
+                                        ln1_done=ln1 if i == 0 else self.fused_ln)
             ops.gemm_tc(bufs["u"], ws[p + "out.weight"], sd[p + "out.bias"], out=logits)
         else:
             f = self._token_features(tok, B)

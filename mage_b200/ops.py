@@ -210,6 +210,21 @@ def gemm_tc(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = Non
     return out, out_split, out_split_relu
 
 
+def gemm_tc_ln(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, *, residual: torch.Tensor, out: torch.Tensor, gamma: torch.Tensor,
+               beta: torch.Tensor, ln_out: torch.Tensor, counters: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """out[M,512] = a @ w.T + bias + residual (may alias out) and ln_out = split(LayerNorm(out)) in ONE launch (mage_b200.h:
+    mage_gemm_tc_ln).  counters: int32 [>= ceil(M/128)], zero (the kernel leaves them zero)."""
+    _f16(a), _f16(w), _f16(ln_out)
+    M, K = a.shape[1], a.shape[2]
+    assert w.shape[1] == 512 and w.shape[2] == K and tuple(out.shape) == (M, 512) and out.is_contiguous() and tuple(ln_out.shape[1:]) == (M, 512)
+    assert residual.shape == out.shape and residual.stride(1) == 1 and counters.dtype == torch.int32 and counters.numel() >= (M + 127) // 128
+    with _Prof("gemm", 2.0 * M * 512 * K):
+        check(_lib.lib().mage_gemm_tc_ln(_ctx(), _p(a), K, M * K, _p(w), K, 512 * K, _p(bias), _p(residual), residual.stride(0), _p(out), M, K,
+                                         _p(_f32(gamma)), _p(_f32(beta)), eps, _p(ln_out), M * 512, _p(counters), _p(flag(a.device)),
+                                         _stream()), "mage_gemm_tc_ln")
+    return out
+
+
 def permute_qkv_for_axial(w_in: torch.Tensor, b_in: torch.Tensor, n_head: int):
     """nn.MultiheadAttention's packed in-projection (rows [q(C) | k(C) | v(C)], mage_model.py:20) re-ordered for
     mage_qkv_axial_attn_tc: every 192-row tile = [q|k|v] x 32 of two heads.  Returns (weight [3C, K], bias [3C])."""
@@ -439,6 +454,20 @@ def embedding(idx: torch.Tensor, table: torch.Tensor, out: Optional[torch.Tensor
         out = torch.empty(*idx.shape, C, device=table.device, dtype=torch.float32)
     with _Prof("embed", 8.0 * rows * C):
         check(_lib.lib().mage_embedding_f32(_ctx(), _p(idx), _p(_f32(table)), _p(out), rows, C, _stream()), "mage_embedding_f32")
+    return out
+
+
+def token_taps_ln(tok: torch.Tensor, table: torch.Tensor, pos_bias: torch.Tensor, bias: torch.Tensor, out: torch.Tensor, gamma: torch.Tensor,
+                  beta: torch.Tensor, ln_out: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """token_taps + the first block's ln_1 in one launch: out fp32 [n*R*R, C] and ln_out = split(LayerNorm(out)) [2, n*R*R, C]."""
+    n, R, _ = tok.shape
+    taps, K, C = table.shape
+    kh = int(round(taps ** 0.5))
+    assert kh * kh == taps and tok.dtype == torch.int64 and tok.is_contiguous() and out.is_contiguous() and _f16(ln_out).shape[1] == n * R * R
+    with _Prof("embed", 4.0 * n * R * R * C * (taps + 2)):
+        check(_lib.lib().mage_token_taps_ln_f32(_ctx(), _p(tok), _p(_f32(table)), _p(_f32(pos_bias)), _p(_f32(bias)), _p(out), n, R, K, C, kh,
+                                                kh, _p(_f32(gamma)), _p(_f32(beta)), eps, _p(ln_out), n * R * R * C, _p(flag(out.device)),
+                                                _stream()), "mage_token_taps_ln_f32")
     return out
 
 

@@ -353,6 +353,16 @@ def test_token_taps_equals_conv_plus_linear():
     out = torch.empty(B * R * R, C, device=DEV)
     ops.token_taps(tok.to(DEV), table.to(DEV), posW.to(DEV), b_in.to(DEV), out)
     _close(out.view(B, R, R, C), want, 2e-6, 2e-6)
+    # the variant that also applies the first block's ln_1 to each finished row: same fp32 rows, and the split LayerNorm output is
+    # bit-identical to mage_layernorm_f32 run on them
+    gamma, beta = (1 + 0.1 * torch.randn(C, generator=g)).to(DEV), (0.1 * torch.randn(C, generator=g)).to(DEV)
+    out2 = torch.empty_like(out)
+    u2 = torch.full((2, B * R * R, C), float("nan"), device=DEV, dtype=torch.float16)
+    ops.token_taps_ln(tok.to(DEV), table.to(DEV), posW.to(DEV), b_in.to(DEV), out2, gamma, beta, u2)
+    u = torch.empty_like(u2)
+    ops.layernorm(out, gamma, beta, out_split=u)
+    assert torch.equal(out2, out) and torch.equal(u2.view(torch.int16), u.view(torch.int16))
+    ops.check_flag(DEV)
 
 
 def test_handles_are_independent():

@@ -316,6 +316,15 @@ def test_optional_schedules_are_bit_exact():
             got2 = model.autoregressive_generate(batch, noise=noise)
             assert torch.equal(model.last_tokens, ref_tok) and (got2 - ref).abs().max() < 2e-4
             eng.fused_axial = True
+        if hasattr(eng, "fused_ln"):
+            # LayerNorm inside the producing kernel (token_taps only = the default; the residual-stream GEMMs too; not at all): the
+            # same arithmetic row by row, so not a bit may change
+            keep = eng.fused_ln_taps, eng.fused_ln
+            for taps, gemms in ((True, True), (False, False), (False, True)):
+                eng.fused_ln_taps, eng.fused_ln = taps, gemms
+                got3 = model.autoregressive_generate(batch, noise=noise)
+                assert torch.equal(model.last_tokens, ref_tok) and torch.equal(got3, ref), (taps, gemms)
+            eng.fused_ln_taps, eng.fused_ln = keep
     finally:
         ops.pdl(True)   # the default
 

@@ -114,6 +114,33 @@ def test_gemm_tc_inplace_residual_and_resmod():
     _close(out, a.double() @ w.double().t() + tab.double().repeat(2, 1))
 
 
+@pytest.mark.parametrize("M,K", [(128, 512), (2048, 512), (2048, 2048), (389, 512), (16384, 512), (4096 + 128, 2048), (16384, 2048)])
+def test_gemm_tc_with_fused_layernorm_is_bit_identical_to_the_two_kernels(M, K):
+    """mage_gemm_tc_ln (the residual-stream GEMM whose epilogue also LayerNorms the finished 128-row blocks, whichever CTA completes
+    them) against mage_gemm_tc followed by mage_layernorm_f32: the fp32 result and the split LayerNorm output must be the SAME
+    BITS under every tile selection -- including ragged M, an odd number of row tiles, several launches on the same counters
+    (they must come back to zero) and in-place residual."""
+    ops = _ops()
+    a, w, x = _rand(M, K, seed=15), _rand(512, K, seed=16, scale=K ** -0.5), _rand(M, 512, seed=17)
+    bias, gamma, beta = _rand(512, seed=18).to(DEV), (1 + 0.1 * _rand(512, seed=19)).to(DEV), (0.1 * _rand(512, seed=20)).to(DEV)
+    asp, wsp = ops.split(a.to(DEV)), ops.split(w.to(DEV))
+    want_x = x.to(DEV).clone()
+    ops.gemm_tc(asp, wsp, bias, residual=want_x, out=want_x)
+    want_u = torch.empty(2, M, 512, device=DEV, dtype=torch.float16)
+    ops.layernorm(want_x, gamma, beta, out_split=want_u)
+    counters = torch.zeros((M + 127) // 128, device=DEV, dtype=torch.int32)
+    for it in range(3):
+        got_x = x.to(DEV).clone()
+        got_u = torch.full((2, M, 512), float("nan"), device=DEV, dtype=torch.float16)
+        ops.gemm_tc_ln(asp, wsp, bias, residual=got_x, out=got_x, gamma=gamma, beta=beta, ln_out=got_u, counters=counters)
+        torch.cuda.synchronize()
+        assert torch.equal(got_x, want_x), it
+        assert torch.equal(got_u.view(torch.int16), want_u.view(torch.int16)), (it, (got_u.float() - want_u.float()).abs().max().item())
+        assert int(counters.abs().sum()) == 0, it
+    ops.check_flag(DEV)
+    _close(want_x, a.double() @ w.double().t() + bias.cpu().double() + x.double())
+
+
 def test_gemm_tc_matches_simt_kernel_to_fp32_noise():
     ops = _ops()
     M, N, K = 2048, 512, 2048
