@@ -62,6 +62,11 @@ int64_t mage_launch_count(mage_ctx* ctx);
  * griddepcontrol.launch_dependents / .wait themselves).  Default on (MAGE_PDL=0 turns it off): the next kernel's launch latency and
  * prologue overlap the previous kernel's tail -- 3 % per generate at 8 prompts per GPU, neutral at 64; results are bit-identical. */
 int mage_pdl(mage_ctx* ctx, int enable);
+/* Give the launches that follow a SHARE of the machine: the persistent tensor-core kernels (GEMM, convolution, fused attention)
+ * size their grids for at most `sms` SMs (0 = all; they hold one CTA per SM).  Two launch sequences on two streams whose shares
+ * add up to the SM count then run side by side without ever waiting for each other's CTAs to retire -- the VQ-VAE decoder next
+ * to the latency-bound decode steps of a small batch.  Tiles are independent, so the share cannot change a bit of any result. */
+int mage_sm_share(mage_ctx* ctx, int sms);
 
 /* C[M,N] = act(relu_a?(A)[M,K] . W[N,K]^T + bias[N]) + residual
  * residual row for output row m is (res_mod > 0 ? m % res_mod : m), leading dim ldr; may alias C.

@@ -1297,6 +1297,9 @@ int configure_kernel(mage_ctx* ctx, K kernel, int cg, int smem_bytes, int* max_u
     if (k < 0) return MAGE_EINVAL;
   }
   *max_units = ctx->cfg_units[k];
+  // mage_sm_share: this launch sequence was given a share of the machine (another sequence runs beside it on the rest)
+  const int share = ctx->eff_sms() / cg;
+  if (share < *max_units) *max_units = share > 0 ? share : 1;
   return 0;
 }
 
@@ -1348,7 +1351,7 @@ TileCfg pick_small(int N, int64_t m_tiles, int K, int sms, bool pair_ok) {
 
 TileCfg pick_cfg(const mage_ctx* ctx, int N, int64_t m_tiles, int K, bool gemm = false) {
   const int forced_bn = ctx->forced_bn, forced_pair = ctx->forced_pair, g_ns = ctx->ns, g_small = ctx->small;
-  const int sms = ctx->sms;
+  const int sms = ctx->eff_sms();
   const bool pair_ok = forced_pair != 0 && m_tiles % 2 == 0;
   // N-split 256-wide pair tiles (plain GEMMs only): A is fetched once per 256 output columns, the two 128-column halves keep
   // separate accumulators so the epilogue still overlaps the next tile's MMAs.  g_ns: 0 off, 1 automatic, 2 whenever legal.

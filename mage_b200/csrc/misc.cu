@@ -42,6 +42,12 @@ extern "C" int mage_ctx_destroy(mage_ctx* ctx) {
 }
 extern "C" int mage_ctx_device(mage_ctx* ctx) { return ctx ? ctx->device : MAGE_EINVAL; }
 extern "C" int64_t mage_launch_count(mage_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int mage_sm_share(mage_ctx* ctx, int sms) {
+  MAGE_CHECK_CTX(ctx);
+  MAGE_CHECK_ARG(sms >= 0);
+  ctx->sm_share = sms;
+  return 0;
+}
 extern "C" int mage_pdl(mage_ctx* ctx, int enable) {
   MAGE_CHECK_CTX(ctx);
   ctx->pdl = enable != 0;

@@ -459,6 +459,12 @@ class SamplerEngine:
         # 0 = chosen from the batch size (`_plan`); likewise the number of chunk streams.
         self.decode_group = max(0, int(os.environ.get("MAGE_DECODE_GROUP", "0")))
         self.n_streams = max(0, int(os.environ.get("MAGE_STREAMS", "0")))
+        # small-batch schedule: decoder beside the steps on a share of the SMs (`_side_plan`)
+        self.n_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        self.side_sms = int(os.environ.get("MAGE_SIDE_SMS", "0"))
+        self.side_frames = int(os.environ.get("MAGE_SIDE_FRAMES", "0"))
+        self.side_group = int(os.environ.get("MAGE_SIDE_GROUP", "0"))
+        self.fused_axial = self.fused_ln = self.fused_ln_taps = False   # tensor-core back end only (set below)
         if self.backend == "tc":
             # split (fp16 hi/lo) copies of the per-step tensor-core operands
             ws = {"Wc": ops.split(self.Wc)}
@@ -840,6 +846,9 @@ class SamplerEngine:
 
         video[0].copy_(images0)   # output frame 0 is the raw input frame (mage_model.py:691)
         self._frame_to_host(video, host_video, 0)
+        side = self._side_plan(B) if trace is None and S == 1 and self.backend == "tc" else None
+        if side is not None:
+            return self._generate_side_by_side(images0, text, speed, noise, video, tokens, tok0_out, host_video, G, *side)
         states = []
         for c, (lo, hi) in enumerate(bounds):
             if streams[c] is not main:
@@ -867,6 +876,63 @@ class SamplerEngine:
                 main.wait_stream(s_)
         if dec_stream is not main:
             main.wait_stream(dec_stream)   # join (also required before a graph capture ends)
+        if host_video is not None:
+            main.wait_stream(self._copy)
+
+    def _side_plan(self, B: int):
+        """(decoder SMs, frames decoded beside the steps, frames per side pass) or None.  A decode step of a FEW prompts is a chain
+        of ~40 short dependent kernels that cannot use the machine (M = 2048 rows at 8 prompts: <= 128 CTAs, mostly waiting on
+        latencies), while the VQ-VAE decoder of the frames already generated is throughput work nobody waits for.  So at small
+        batches the steps get `sms - D` SMs and the decoder runs BESIDE them on a side stream with D SMs (mage_sm_share: the shares
+        add up to the machine, so neither sequence ever waits for the other's CTAs); frames that do not fit beside the chain are
+        decoded afterwards at full width.  MAGE_SIDE_SMS (D; 0 = off), MAGE_SIDE_FRAMES, MAGE_SIDE_GROUP override the plan."""
+        D = self.side_sms
+        if D < 0:   # automatic
+            D = 0
+        if D <= 0 or D >= self.n_sms:
+            return None
+        n_side = self.side_frames if self.side_frames > 0 else (self.L - 1) // 3
+        n_side = max(0, min(n_side, self.L - 1))
+        if n_side == 0:
+            return None
+        Gs = self.side_group if self.side_group > 0 else 2
+        return D, n_side, Gs
+
+    def _generate_side_by_side(self, images0, text, speed, noise, video, tokens, tok0_out, host_video, G: int, D: int, n_side: int,
+                               Gs: int) -> None:
+        """The small-batch schedule of `_side_plan`: frames 1..n_side are decoded in passes of Gs frames on the side stream with D
+        SMs while the steps continue on `n_sms - D`; the remaining frames after the last step, at full width, G at a time."""
+        R, L = self.R, self.L
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        side = self._side
+        img_elems = video.shape[2] * video.shape[3] * video.shape[4]
+
+        def decode(j0: int, j1: int) -> None:   # frames j0+1 .. j1 (frame-major, contiguous)
+            self.vq.decode_into(tokens[j0:j1].view(-1, R, R), video[j0 + 1], img_elems)
+            for f in range(j0 + 1, j1 + 1):
+                self._frame_to_host(video, host_video, f)
+
+        st = self._prelude(images0, text, speed, noise, tok0_out, None)
+        try:
+            ops.sm_share(self.n_sms - D)
+            j0 = 0
+            for j in range(L - 1):
+                self._decode_step(st, j, tokens[j].reshape(-1), None)
+                done = j + 1
+                if done <= n_side and (done - j0 == Gs or done == n_side):
+                    side.wait_stream(main)
+                    ops.sm_share(D)
+                    with torch.cuda.stream(side):
+                        decode(j0, done)
+                    ops.sm_share(self.n_sms - D)
+                    j0 = done
+        finally:
+            ops.sm_share(0)
+        for j0 in range(n_side, L - 1, G):
+            decode(j0, min(j0 + G, L - 1))
+        main.wait_stream(side)
         if host_video is not None:
             main.wait_stream(self._copy)
 
@@ -1030,7 +1096,8 @@ class SamplerEngine:
                 video = host
             return video.permute(1, 0, 2, 3, 4), tokens.permute(1, 0, 2).reshape(B, L - 1, R, R), tok0.view(B, R, R).clone()
 
-        key = (B, T, tuple(images0.shape[1:]), speed is not None, noise is not None, to_host, self._plan(B), self.overlap_decode)
+        key = (B, T, tuple(images0.shape[1:]), speed is not None, noise is not None, to_host, self._plan(B), self.overlap_decode, self._side_plan(B),
+               self.fused_ln_taps, self.fused_ln, self.fused_axial)
         st = self._graphs.pop(key, None)
         if st is None:
             st = self._capture(key, images0, text, speed, noise, to_host)

@@ -116,6 +116,11 @@ def pdl(enable: bool) -> None:
     check(_lib.lib().mage_pdl(_ctx(), int(enable)), "mage_pdl")
 
 
+def sm_share(sms: int = 0) -> None:
+    """The launches that follow size their persistent kernels for at most `sms` SMs (0 = the whole GPU): mage_b200.h."""
+    check(_lib.lib().mage_sm_share(_ctx(), int(sms)), "mage_sm_share")
+
+
 def tc_nsplit(mode: int = 1) -> None:
     """N-split 256-wide pair tiles of gemm_tc: 0 off, 1 automatic, 2 whenever legal (tests / tuning)."""
     check(_lib.lib().mage_tc_nsplit(_ctx(), mode), "mage_tc_nsplit")

@@ -316,6 +316,18 @@ def test_optional_schedules_are_bit_exact():
             got2 = model.autoregressive_generate(batch, noise=noise)
             assert torch.equal(model.last_tokens, ref_tok) and (got2 - ref).abs().max() < 2e-4
             eng.fused_axial = True
+        # small-batch schedule: the decoder of the first frames BESIDE the steps on a share of the SMs (mage_sm_share), captured and eager
+        keep_side = eng.side_sms, eng.side_frames, eng.side_group
+        for graph in (True, False):
+            eng.use_cuda_graph = graph
+            for sms, frames, group in ((20, 3, 2), (64, 5, 1), (8, 2, 4)):
+                eng.side_sms, eng.side_frames, eng.side_group = sms, frames, group
+                eng.n_streams, eng.decode_group, eng.overlap_decode = 1, 4, False
+                for it in range(2):
+                    got4 = model.autoregressive_generate(batch, noise=noise, to_host=it == 1)
+                    assert torch.equal(model.last_tokens, ref_tok) and torch.equal(got4.cuda(), ref), (graph, sms, frames, group, it)
+        eng.side_sms, eng.side_frames, eng.side_group = keep_side
+        eng.use_cuda_graph = False
         if hasattr(eng, "fused_ln"):
             # LayerNorm inside the producing kernel (token_taps only = the default; the residual-stream GEMMs too; not at all): the
             # same arithmetic row by row, so not a bit may change
