@@ -100,6 +100,10 @@ class MageCudaError(RuntimeError):
     pass
 
 
+class MageSplitRangeError(MageCudaError):
+    """A tensor-core operand left the range of the fp16 hi/lo split format (|x| > 65504, or NaN) during the call."""
+
+
 _ctx = {}
 
 

@@ -10,11 +10,14 @@ refuses to sample.
 """
 from __future__ import annotations
 
+import os
+import warnings
 from typing import Dict, List, Optional
 
 import torch
 from torch import nn
 
+from . import _lib
 from . import synthetic as syn
 from .config import instantiate_from_config
 
@@ -60,6 +63,7 @@ class _EngineOwner(nn.Module):
         super().__init__()
         self._engine = None
         self._engine_sig = None
+        self._wide_engine = None
 
     def _signature(self):
         return tuple((t.data_ptr(), t._version, t.device.index) for t in list(self.parameters()) + list(self.buffers()))
@@ -71,6 +75,7 @@ class _EngineOwner(nn.Module):
         """Drop the packed-weight engine explicitly (it is rebuilt on the next call)."""
         self._engine = None
         self._engine_sig = None
+        self._wide_engine = None
 
     def _apply(self, fn, *a, **kw):
         self.invalidate()
@@ -240,6 +245,7 @@ class MAGE(_EngineOwner):
             self.register_parameter(name, prm)
         self.last_tokens = None
         self.last_tok0 = None
+        self.range_fallbacks = 0   # calls repeated on the fp32 kernels because an activation left the tensor-core operand range
 
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
         """Accepts released checkpoints: the train-only tensors (3-D conv posterior etc.) are dropped."""
@@ -254,6 +260,16 @@ class MAGE(_EngineOwner):
                                          ma_ln=getattr(self.ma_encoder, "ln_qkv", False))
             self._engine_sig = self._signature()
         return self._engine
+
+    def _wide_range_engine(self):
+        """The same sampler on the fp32 SIMT kernels (no fp16 operand format, hence no range limit): built on first need."""
+        if getattr(self, "_wide_engine", None) is None or self._wide_engine_sig != self._signature():
+            from .engine import SamplerEngine
+            self._wide_engine = SamplerEngine(self._cuda_state(), self.frames_length, self.randomness,
+                                              padding_idx=getattr(self.text_encoder, "padding_idx", 0), use_cids=self.use_cids,
+                                              ma_ln=getattr(self.ma_encoder, "ln_qkv", False), backend="simt")
+            self._wide_engine_sig = self._signature()
+        return self._wide_engine
 
     def get_first_stage_encoding(self, encoder_posterior):
         """mage_model.py:542-549: a posterior object is sampled, a tensor is taken as is."""
@@ -311,7 +327,19 @@ class MAGE(_EngineOwner):
                 host.copy_(video)
                 return host
             return video
-        video, tokens, tok0 = eng.generate(images0, text, speed, noise, to_host=to_host)
+        try:
+            video, tokens, tok0 = eng.generate(images0, text, speed, noise, to_host=to_host)
+        except _lib.MageSplitRangeError:
+            # An activation left the fp16 hi/lo operand range of the tensor-core kernels (|x| > 65504 -- e.g. a residual stream
+            # far outside anything the shipped checkpoints produce -- or NaN).  The reference computes such a call in plain fp32
+            # (NaN in, NaN out), so the call is REPEATED on the fp32 SIMT kernels of the same library: ~9x slower, same
+            # algorithm, never a wrong clip.  MAGE_RANGE_FALLBACK=0 re-raises instead.
+            if os.environ.get("MAGE_RANGE_FALLBACK", "1") == "0" or eng.backend != "tc":
+                raise
+            warnings.warn("an activation left the tensor-core operand range (|x| > 65504 or NaN): this call is repeated on the "
+                          "fp32 SIMT kernels (about 9x slower)", RuntimeWarning, stacklevel=2)
+            self.range_fallbacks += 1
+            video, tokens, tok0 = self._wide_range_engine().generate(images0, text, speed, noise, to_host=to_host)
         self.last_tokens, self.last_tok0 = tokens, tok0
         if to_host:
             return video

@@ -102,8 +102,8 @@ def check_flag(device) -> None:
         f.zero_()
         if v & 2:
             raise IndexError("caption token id outside the text encoder's vocabulary (index out of range in self)")
-        raise _lib.MageCudaError("a tensor-core operand left the fp16 hi/lo split range (|x| > 65504 or NaN); "
-                                 "results are invalid -- run with MAGE_BACKEND=simt")
+        raise _lib.MageSplitRangeError("a tensor-core operand left the fp16 hi/lo split range (|x| > 65504 or NaN); the results of "
+                                       "this call are invalid (MAGE.autoregressive_generate repeats it on the fp32 SIMT kernels)")
 
 
 def tc_tuning(bn: int = 0, pair: int = -1) -> None:

@@ -273,6 +273,25 @@ def mage_param_spec(params: dict) -> Spec:
     return s
 
 
+def posterior_param_spec(params: dict) -> Spec:
+    """The train-only tensors of MAGE (randomness=True): the 3-D convolutional video posterior `conv3d` (four BasicBlocks,
+    mage_model.py:264-297, 496-501) and the two Gaussian heads conv_mu2 / conv_var2 (:502-503).  Read by MAGE.forward only."""
+    d, dm = params["vision_width"], params["ma_config"]["params"]["d_model"]
+    s: Spec = []
+    for i in range(4):
+        cout = dm if i == 3 else d
+        p = f"conv3d.{i}"
+        s.append((p + ".conv1.weight", (cout, d, 3, 3, 3), "conv"))
+        _ln(s, p + ".bn1", cout)
+        s.append((p + ".conv2.weight", (cout, cout, 3, 3, 3), "conv"))
+        _ln(s, p + ".bn2", cout)
+        s.append((p + ".downsample.0.weight", (cout, d, 3, 3, 3), "conv"))
+        _ln(s, p + ".downsample.1", cout)
+    _conv(s, "conv_mu2", 64, d, 3)
+    _conv(s, "conv_var2", 64, d, 3)
+    return s
+
+
 def make_state_dict(spec: Spec, seed: int) -> Dict[str, torch.Tensor]:
     """Fill a spec with seeded CPU-generator values.  Every tensor gets its own
     generator (seed, index) so inserting a key never shifts the others."""
@@ -281,8 +300,9 @@ def make_state_dict(spec: Spec, seed: int) -> Dict[str, torch.Tensor]:
         g = torch.Generator(device="cpu")
         g.manual_seed(seed * 100003 + i)
         if kind == "conv":
-            fan_in = shape[1] * shape[2] * shape[3]
-            fan_out = shape[0] * shape[2] * shape[3]
+            taps = math.prod(shape[2:])   # 2-D and 3-D kernels
+            fan_in = shape[1] * taps
+            fan_out = shape[0] * taps
             a = math.sqrt(6.0 / (fan_in + fan_out)) * 1.4  # xavier-uniform with a ReLU-ish gain
             t = (torch.rand(shape, generator=g) * 2 - 1) * a
         elif kind == "bias":
@@ -327,9 +347,13 @@ def make_vqvae_state_dict(fs_params: dict, seed: int = 7, conditioned: bool = Tr
     return sd
 
 
-def make_mage_state_dict(params: dict, seed: int = 11, vq_seed: int = 7, conditioned: bool = True) -> Dict[str, torch.Tensor]:
-    """Synthetic MAGE checkpoint `state_dict` (sampling subset) for `params`."""
+def make_mage_state_dict(params: dict, seed: int = 11, vq_seed: int = 7, conditioned: bool = True,
+                         posterior: bool = False) -> Dict[str, torch.Tensor]:
+    """Synthetic MAGE checkpoint `state_dict` for `params`: the sampling subset, plus (posterior=True) the train-only video
+    posterior that MAGE.forward reads.  The sampling tensors do not depend on `posterior`."""
     sd = make_state_dict(mage_param_spec(params), seed)
+    if posterior and params["randomness"]:
+        sd.update(make_state_dict(posterior_param_spec(params), seed + 1))
     if not params["use_cids"]:
         for k, v in PatchLatentAE(**params["first_stage_config"]["params"]).state_dict().items():
             sd["first_stage_model." + k] = v

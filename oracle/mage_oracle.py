@@ -476,3 +476,85 @@ def generate_continuous(sd: SD, z0: torch.Tensor, text: torch.Tensor, speed: Opt
     if trace is not None and "step_pred" in trace:
         trace["step_pred"] = torch.stack(trace["step_pred"], 1)                     # [B, L-2, c, H, W]
     return pred.permute(0, 1, 4, 2, 3).contiguous()
+
+
+# --------------------------------------------------------------------------------------
+# stage-2 objective, forward half: MAGE.forward in eval mode
+# --------------------------------------------------------------------------------------
+def _gn(sd: SD, name: str, x: torch.Tensor, groups: int = 16) -> torch.Tensor:
+    return F.group_norm(x, groups, sd[name + ".weight"], sd[name + ".bias"], eps=1e-5)
+
+
+def basic_block_3d(sd: SD, name: str, x: torch.Tensor) -> torch.Tensor:
+    """BasicBlock.forward (mage_model.py:264-297) as MAGE builds it (:497-500: stride 1, stride_t 2, downsample=True):
+    Conv3d 3x3x3 (temporal stride 2, no bias) -> GroupNorm(16) -> ReLU -> Conv3d 3x3x3 -> GroupNorm(16); the residual goes
+    through its own strided Conv3d + GroupNorm; sum -> ReLU.  x [B,C,T,H,W]."""
+    out = F.conv3d(x, sd[name + ".conv1.weight"], None, stride=(2, 1, 1), padding=1)
+    out = F.relu(_gn(sd, name + ".bn1", out))
+    out = _gn(sd, name + ".bn2", F.conv3d(out, sd[name + ".conv2.weight"], None, stride=1, padding=1))
+    res = _gn(sd, name + ".downsample.1", F.conv3d(x, sd[name + ".downsample.0.weight"], None, stride=(2, 1, 1), padding=1))
+    return F.relu(out + res)
+
+
+def video_posterior(sd: SD, x_emb: torch.Tensor):
+    """mage_model.py:605-607 + reparameterize (:569-573) without the draw: x_emb [B,L,C,H,W] (raw token embeddings of ALL L
+    frames) -> four BasicBlocks over [B,C,L,H,W] (each halves T; T must end at 1, `.squeeze(2)`) -> (mu, logvar) [B,64,H,W]."""
+    v = x_emb.permute(0, 2, 1, 3, 4).contiguous()
+    for i in range(4):
+        v = basic_block_3d(sd, f"conv3d.{i}", v)
+    assert v.shape[2] == 1, "the reference squeezes the temporal axis: frames_length must reduce to 1 in four halvings"
+    v = v.squeeze(2)
+    return _conv(sd, "conv_mu2", v, padding=1), _conv(sd, "conv_var2", v, padding=1)
+
+
+@torch.no_grad()
+def forward_loss(sd: SD, batch: Dict[str, torch.Tensor], eps: Optional[torch.Tensor], *, randomness: bool = True,
+                 beta: float = 1.0, alpha: float = 0.0, test_flag: bool = False, trace: Optional[dict] = None) -> Dict[str, float]:
+    """MAGE.forward (mage_model.py:575-639), use_cids=True, eval mode (dropout off), fixed beta (auto_beta=False): the
+    teacher-forced full-sequence pass and its losses.  batch['images'] [B,L,C,H,W] (all L frames), 'text', optional 'speed';
+    `eps` [B,64,H,W] stands for the `torch.randn_like(logvar)` draw of reparameterize (:571) -- or, with test_flag, for the
+    `torch.randn_like(video_emb)` that replaces the posterior sample (:609-610).  Returns the reference's loss_dict values
+    (without the 'train/' / 'val/' prefix)."""
+    fsd = _sub(sd, "first_stage_model.")
+    imgs = batch["images"]
+    B, L = imgs.shape[:2]
+    tok = vqvae_encode(fsd, imgs.reshape(-1, *imgs.shape[2:]))
+    tok = tok.view(B, L, *tok.shape[1:])
+    x_emb = embed_tokens(sd, tok)                                          # [B,L,C,H,W]
+    prior = token_features(sd, x_emb[:, :L - 1])                           # [B,L-1,H,W,C]
+    C = x_emb.shape[2]
+    first = prior[:, 0].reshape(B, -1, C).permute(1, 0, 2).contiguous()
+    t = text_encoder(sd, batch["text"]).permute(1, 0, 2).contiguous()
+    H, W = tok.shape[-2:]
+    a = ma_encoder(sd, first, t).permute(1, 0, 2).contiguous().view(B, H, W, C)
+    out: Dict[str, float] = {}
+    kl = None
+    if randomness:
+        mu, logvar = video_posterior(sd, x_emb)
+        video_emb = eps * torch.exp(0.5 * logvar) + mu
+        if test_flag:
+            video_emb = eps
+        y = F.conv2d(video_emb, sd["conv_d2.weight"], None, padding=1)
+        a = adain(sd, a.permute(0, 3, 1, 2).contiguous(), y).permute(0, 2, 3, 1).contiguous()
+        m2, lv2 = mu.reshape(B, -1), logvar.reshape(B, -1)
+        kl = -0.5 * torch.mean(torch.sum(1 + lv2 - m2.pow(2) - lv2.exp(), dim=1))
+        if trace is not None:
+            trace["mu"], trace["logvar"] = mu, logvar
+    speed_emb = None
+    if batch.get("speed") is not None:
+        speed_emb = batch["speed"].view(B, 1) @ sd["speed_embedding"]
+        a = a + speed_emb.unsqueeze(1).unsqueeze(1)
+    logits = flat_axial_decoder(sd, a, prior)                               # [B,L-1,H,W,K]
+    K = logits.shape[-1]
+    pred = F.cross_entropy(logits.reshape(-1, K), tok[:, 1:L].reshape(-1))
+    if trace is not None:
+        trace["tokens"], trace["logits"] = tok, logits
+    out["prediction"] = float(pred)
+    final = pred
+    if randomness:
+        out["kl_loss"] = float(kl)
+        # mage_model.py:631-632 (auto_beta=False); the L2 term needs batch['speed'] in the reference too (speed_emb, :613)
+        l2 = torch.mean(torch.pow(torch.norm(speed_emb, dim=-1), 2)) if speed_emb is not None else torch.zeros(())
+        final = pred + beta * kl + alpha * l2
+    out["final_loss"] = float(final)
+    return out

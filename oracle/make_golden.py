@@ -163,6 +163,62 @@ def make_plus_goldens():
         print(f"mage+ {name}: {time.time() - t0:.1f}s, latents {tuple(lat.shape)} std {float(lat.std()):.3f} max {float(lat.abs().max()):.3f}")
 
 
+# stage-2 objective, forward half (MAGE.forward in eval mode): (name, family, frames_length, batch, text_len, padded, eps seed, test_flag)
+FORWARD_CASES = [
+    ("forward_L4_b2", "caterv2", 4, 2, 12, False, 61, False),
+    ("forward_L8_b2_pad", "caterv2", 8, 2, 14, True, 62, False),
+    ("forward_L16_b1", "caterv2", 16, 1, 20, False, 63, False),
+    ("forward_L4_b2_testflag", "caterv2", 4, 2, 12, False, 64, True),
+    ("forward_mnist_L4_b2", "mnist", 4, 2, 6, False, 65, False),
+]
+
+
+def forward_case_inputs(name):
+    """(params, state_dict incl. the train-only posterior, batch with ALL frames, eps) of a FORWARD_CASES entry -- shared with the tests."""
+    _, family, L, B, T, padded, eps_seed, test_flag = next(c for c in FORWARD_CASES if c[0] == name)
+    params = syn.model_params(family, frames_length=L)
+    sd = syn.make_mage_state_dict(params, posterior=True)
+    batch = syn.make_batch(params, B, seed=4321, text_len=T, padded=padded, frames=L)
+    eps = syn.make_noise(B, res=params["image_resolution"], seed=eps_seed) if params["randomness"] else None
+    return params, sd, batch, eps, test_flag
+
+
+def make_forward_goldens():
+    """Loss values of the unmodified reference's MAGE.forward (mage_model.py:575-639) in eval mode (dropout off) on seeded
+    synthetic checkpoints that include the 3-D conv posterior.  The one random draw of the pass, `torch.randn_like` in
+    reparameterize (:571; with test_flag also :610), is replaced by a stored tensor `eps` for the duration of the call."""
+    assert ref_shims.reference_available(), "needs /root/reference"
+    for case in FORWARD_CASES:
+        name, family, L, B, T, padded, eps_seed, test_flag = case
+        params, sd, batch, eps, _ = forward_case_inputs(name)
+        model = ref_shims.build_reference_mage(params, sd)
+        assert not [k for k in model.state_dict() if k not in sd and not k.startswith("first_stage_model.")], "posterior keys missing"
+        captured = {}
+        hooks = []
+        if params["randomness"]:
+            hooks = [model.conv_mu2.register_forward_hook(lambda m, i, o: captured.__setitem__("mu", o.detach())),
+                     model.conv_var2.register_forward_hook(lambda m, i, o: captured.__setitem__("logvar", o.detach()))]
+        real = torch.randn_like
+        torch.randn_like = lambda t, *a, **k: eps.clone().to(t.dtype) if tuple(t.shape) == tuple(eps.shape) else real(t, *a, **k)
+        t0 = time.time()
+        try:
+            with torch.no_grad():
+                loss, loss_dict = model({k: v.clone() for k, v in batch.items()}, test_flag=test_flag)
+                tok = model.first_stage_encode(batch["images"])
+        finally:
+            torch.randn_like = real
+            for h in hooks:
+                h.remove()
+        rec = dict(frames_length=L, batch=B, text_len=T, padded=padded, eps_seed=eps_seed, test_flag=test_flag,
+                   tokens=_np(tok).astype(np.int16), final_loss=np.float64(float(loss)),
+                   prediction=np.float64(loss_dict["val/prediction"]))
+        if params["randomness"]:
+            rec.update(kl_loss=np.float64(loss_dict["val/kl_loss"]), mu=_np(captured["mu"]).astype(np.float32),
+                       logvar=_np(captured["logvar"]).astype(np.float32))
+        np.savez_compressed(os.path.join(GOLDEN_DIR, f"mage_{name}.npz"), **rec)
+        print(f"{name}: {time.time() - t0:.1f}s", {k: round(float(v), 6) for k, v in loss_dict.items()})
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
@@ -172,3 +228,5 @@ if __name__ == "__main__":
         make_goldens()
     if what in ("plus", "all"):
         make_plus_goldens()
+    if what in ("forward", "all"):
+        make_forward_goldens()

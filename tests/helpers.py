@@ -51,6 +51,23 @@ def load_plus_case(name):
     return params, sd, batch, noise, g
 
 
+FORWARD_CASES = ["forward_L4_b2", "forward_L8_b2_pad", "forward_L16_b1", "forward_L4_b2_testflag", "forward_mnist_L4_b2"]
+FORWARD_FAMILY = {"forward_mnist_L4_b2": "mnist"}
+
+
+def load_forward_case(name):
+    """Golden of the reference's MAGE.forward in eval mode (stage-2 objective, forward half): params, checkpoint INCLUDING the
+    train-only video posterior, a batch with all frames_length frames, the stored stand-in `eps` of the pass's one random draw
+    (None without randomness), test_flag, golden arrays.  Mirrors oracle/make_golden.py::forward_case_inputs."""
+    g = dict(np.load(os.path.join(GOLDEN_DIR, f"mage_{name}.npz")))
+    L, B = int(g["frames_length"]), int(g["batch"])
+    params = syn.model_params(FORWARD_FAMILY.get(name, "caterv2"), frames_length=L)
+    sd = syn.make_mage_state_dict(params, posterior=True)
+    batch = syn.make_batch(params, B, seed=4321, text_len=int(g["text_len"]), padded=bool(g["padded"]), frames=L)
+    eps = syn.make_noise(B, res=params["image_resolution"], seed=int(g["eps_seed"])) if params["randomness"] else None
+    return params, sd, batch, eps, bool(g["test_flag"]), g
+
+
 def pix_check(got, want, what="pixels"):
     got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
     rel = np.linalg.norm(got - want) / max(np.linalg.norm(want), 1e-30)

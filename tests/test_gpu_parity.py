@@ -341,6 +341,45 @@ def test_optional_schedules_are_bit_exact():
         ops.pdl(True)   # the default
 
 
+def test_activation_outside_the_tensor_core_operand_range_is_recomputed_in_fp32(monkeypatch):
+    """The tensor-core kernels carry fp32 values as fp16 hi/lo pairs, so an activation beyond +-65504 cannot be represented (the
+    kernels flag it).  The shipped checkpoints stay far inside (every GEMM operand but the head's is a LayerNorm / attention /
+    QuickGELU output), but the path must not depend on that: such a call is repeated on the fp32 SIMT kernels with a warning --
+    same algorithm, the reference's behaviour (plain fp32), never a wrong clip and never an exception the reference would not
+    raise.  Here the last block's c_proj bias pushes the residual stream that feeds the head to ~3e5."""
+    import warnings
+
+    from mage_b200 import _lib
+    params = syn.model_params("caterv2", frames_length=4)
+    sd = syn.make_mage_state_dict(params)
+    big = {k: v.clone() for k, v in sd.items()}
+    last = max(int(k.split(".")[2]) for k in big if k.startswith("generate_model.blocks."))
+    big[f"generate_model.blocks.{last}.mlp.c_proj.bias"] += 3e5
+    batch = {k: v.to("cuda") for k, v in syn.make_batch(params, 2, seed=3, text_len=9).items()}
+    noise = syn.make_noise(2, seed=4)
+    model = _build(params, big)
+    with pytest.warns(RuntimeWarning, match="repeated on the fp32"):
+        got = model.autoregressive_generate(batch, noise=noise)
+    assert model.range_fallbacks == 1 and torch.isfinite(got).all()
+    tokens = model.last_tokens.clone()
+    # the same checkpoint on the fp32 kernels from the start: the identical clip
+    monkeypatch.setenv("MAGE_BACKEND", "simt")
+    want_model = _build(params, big)
+    want = want_model.autoregressive_generate(batch, noise=noise)
+    assert want_model.range_fallbacks == 0 and torch.equal(want_model.last_tokens, tokens) and torch.equal(want, got)
+    monkeypatch.delenv("MAGE_BACKEND")
+    # an in-range checkpoint never takes the detour ...
+    ok = _build(params, sd)
+    with warnings.catch_warnings(record=True) as seen:
+        warnings.simplefilter("always")
+        ok.autoregressive_generate(batch, noise=noise)
+    assert ok.range_fallbacks == 0 and not [w for w in seen if "repeated on the fp32" in str(w.message)]
+    # ... and the detour can be refused
+    monkeypatch.setenv("MAGE_RANGE_FALLBACK", "0")
+    with pytest.raises(_lib.MageSplitRangeError):
+        model.autoregressive_generate(batch, noise=noise)
+
+
 def test_graph_cache_is_bounded_and_shares_one_pool():
     """Captions cannot be padded to a common length (the motion anchor attends padded positions, mage_model.py:92), so real data
     yields one CUDA graph per caption length: the cache keeps at most `max_graphs` signatures (LRU) and all graphs live in ONE

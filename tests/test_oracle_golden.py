@@ -10,7 +10,8 @@ import torch
 from mage_b200 import synthetic as syn
 from oracle import mage_oracle as orc
 from oracle import ref_shims
-from tests.helpers import GOLDEN_DIR, MAGE_CASES, PLUS_CASES, free_running_token_report, load_case, load_plus_case
+from tests.helpers import (FORWARD_CASES, GOLDEN_DIR, MAGE_CASES, PLUS_CASES, free_running_token_report, load_case, load_forward_case,
+                           load_plus_case)
 
 
 @pytest.mark.parametrize("ratio", [4, 8])
@@ -69,6 +70,25 @@ def test_mage_plus_branch_matches_reference_golden(name):
     B, Fr = lat.shape[:2]
     pix = ae.decode(lat.reshape(-1, *lat.shape[2:])).view(B, Fr, 3, 128, 128)[..., ::4, ::4]
     np.testing.assert_allclose(pix.numpy(), g["pixels"], rtol=0, atol=2e-5)
+
+
+@pytest.mark.parametrize("name", FORWARD_CASES)
+def test_forward_loss_matches_reference_golden(name):
+    """SURVEY.md §8 row N2, forward half: the oracle's restatement of MAGE.forward (teacher-forced full-sequence pass, 3-D conv
+    video posterior, cross-entropy / KL / final loss; mage_model.py:575-639) against the unmodified reference's values in eval
+    mode with the stored draw: VQ tokens of all frames identical, posterior mean / log-variance and the three losses to fp32
+    rounding."""
+    params, sd, batch, eps, test_flag, g = load_forward_case(name)
+    tr = {}
+    out = orc.forward_loss(sd, batch, eps, randomness=params["randomness"], beta=params.get("beta", 1.0), alpha=params.get("alpha", 0.0),
+                           test_flag=test_flag, trace=tr)
+    assert np.array_equal(tr["tokens"].numpy(), g["tokens"])
+    assert abs(out["prediction"] - float(g["prediction"])) <= 2e-6 * abs(float(g["prediction"]))
+    assert abs(out["final_loss"] - float(g["final_loss"])) <= 2e-6 * abs(float(g["final_loss"]))
+    if params["randomness"]:
+        assert abs(out["kl_loss"] - float(g["kl_loss"])) <= 2e-6 * abs(float(g["kl_loss"]))
+        np.testing.assert_allclose(tr["mu"].numpy(), g["mu"], rtol=0, atol=2e-5)
+        np.testing.assert_allclose(tr["logvar"].numpy(), g["logvar"], rtol=0, atol=2e-5)
 
 
 def test_incremental_can_run_longer_than_checkpoint_positions_is_rejected():
