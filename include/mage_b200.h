@@ -314,6 +314,28 @@ int mage_gn_silu_head_f32(mage_ctx* ctx, const float* x, const double* part, con
                           const float* bias, float* out, int rows, int B, int HW, int n_slots, int C, int groups, int cout,
                           float eps, void* stream);
 
+/* ---- Stage-2 objective, forward half (MAGE.forward in eval mode, mage_model.py:575-639; the "next" row N2) ----------------------
+ * The teacher-forced pass itself runs on the sampling kernels above (same blocks, the given tokens fed back); these are the pieces
+ * only the objective needs.  The 3x3x3 convolutions of the video posterior (BasicBlock, mage_model.py:264-297) are mage_conv2d_tc
+ * calls with the three temporal taps folded into the channel axis (Cin = 3*512).
+ *
+ * mage_gn_apply_f32: GroupNorm(groups) over (C/groups channels x n_slots frames x HW positions) of each sample, from the partial
+ *   sums of mage_gn_partial_f32 (part double [n_slots, B, groups, 2]); x fp32 [n_slots, B, HW, C=512] (frame-major);
+ *   y = GN(x) * gamma + beta (+ residual) (ReLU if relu) -> out fp32 and/or out_split.  stat: scratch, 2*B*groups floats.
+ * mage_cross_entropy_rows_f32: loss[row] = logsumexp(logits[row, 0..K)) - logits[row, target[row]] (F.cross_entropy, :619);
+ *   a target outside [0, K) sets bit 2 of *flag (the reference raises).
+ * mage_reparam_kl_f32: mu_logvar fp32 [B, HW, 2*Cz] (conv_mu2 | conv_var2 columns), eps fp32 [B, Cz, HW] (the stored draw):
+ *   z[b,c,p] = eps * exp(0.5 * logvar) + mu (NCHW, :569-573; z may be NULL), kl_rows[b] = sum(1 + logvar - mu^2 - exp(logvar)) (:625).
+ * mage_scaled_sum_f32: out[0] = scale * sum(x[0..n)), one block, fixed order, double accumulation (the means of :619 and :625). */
+int mage_gn_apply_f32(mage_ctx* ctx, const float* x, const double* part, float* stat, const float* gamma, const float* beta,
+                      const float* residual, float* out, void* out_split, int64_t split_plane, int* flag, int n_slots, int B, int HW, int C,
+                      int groups, int relu, float eps, void* stream);
+int mage_cross_entropy_rows_f32(mage_ctx* ctx, const float* logits, int64_t ld, const int64_t* target, float* loss, int rows, int K,
+                                int* flag, void* stream);
+int mage_reparam_kl_f32(mage_ctx* ctx, const float* mu_logvar, const float* eps, float* z, float* kl_rows, int B, int HW, int Cz,
+                        void* stream);
+int mage_scaled_sum_f32(mage_ctx* ctx, const float* x, float* out, int64_t n, double scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,6 +63,10 @@ SIGNATURES = {
     "mage_nchw_to_nhwc_f32": [_c_f, _c_f, _c_f, _i, _i, _i, _c_f],
     "mage_gn_partial_f32": [_c_f, _c_f, _c_f, _i, _i, _i, _i, _i, _c_f],
     "mage_gn_silu_head_f32": [_c_f] + [_c_f] * 7 + [_i] * 7 + [_f32, _c_f],
+    "mage_gn_apply_f32": [_c_f] + [_c_f] * 8 + [_i64, _c_f] + [_i] * 6 + [_f32, _c_f],
+    "mage_cross_entropy_rows_f32": [_c_f, _c_f, _i64, _c_f, _c_f, _i, _i, _c_f, _c_f],
+    "mage_reparam_kl_f32": [_c_f] + [_c_f] * 4 + [_i] * 3 + [_c_f],
+    "mage_scaled_sum_f32": [_c_f, _c_f, _c_f, _i64, ctypes.c_double, _c_f],
 }
 
 

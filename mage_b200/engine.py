@@ -465,6 +465,7 @@ class SamplerEngine:
         self.side_frames = int(os.environ.get("MAGE_SIDE_FRAMES", "0"))
         self.side_group = int(os.environ.get("MAGE_SIDE_GROUP", "0"))
         self.fused_axial = self.fused_ln = self.fused_ln_taps = False   # tensor-core back end only (set below)
+        self._post = None           # packed video posterior (MAGE.forward only), built on first use
         if self.backend == "tc":
             # split (fp16 hi/lo) copies of the per-step tensor-core operands
             ws = {"Wc": ops.split(self.Wc)}
@@ -798,7 +799,11 @@ class SamplerEngine:
         st["x"] = x
         st["tok"] = ops.argmax_rows(logits, out=tok_out)
         if trace is not None:
-            trace.setdefault("logits", []).append(logits.clone())
+            if trace.get("ce_rows") is not None:
+                # stage-2 objective (mage_model.py:619): cross-entropy of this position's logits against the GIVEN next frame
+                ops.cross_entropy_rows(logits, trace["force_tokens"][:, j].reshape(-1).contiguous(), trace["ce_rows"][j])
+            if trace.get("keep_logits", True):
+                trace.setdefault("logits", []).append(logits.clone())
             if trace.get("force_tokens") is not None:
                 # teacher forcing (parity diagnostics): this step's prediction is recorded, but the NEXT step is fed the
                 # given token map -- a near-tie flip then cannot cascade into later frames
@@ -865,6 +870,8 @@ class SamplerEngine:
                         self._decode_step(states[c], j, tokens[j, lo:hi].reshape(-1), trace)
                 if dec_stream is not streams[c]:
                     dec_stream.wait_stream(streams[c])
+            if trace is not None and trace.get("skip_decode"):
+                continue                                   # the objective reads logits only
             # decode the finished group of frames for every sample: video[j0+1 .. j1] (frame-major, contiguous)
             toks = tokens[j0:j1].view(-1, R, R)            # [(j1-j0)*B, R, R], frame-major like the video buffer
             with torch.cuda.stream(dec_stream):
@@ -935,6 +942,93 @@ class SamplerEngine:
         main.wait_stream(side)
         if host_video is not None:
             main.wait_stream(self._copy)
+
+    # ------------------------------------------------------------------ stage-2 objective, forward half
+    def _posterior_weights(self) -> dict:
+        """Split tensor-core copies of the video posterior (conv3d.*, conv_mu2 | conv_var2), packed on first use.  A 3x3x3 kernel
+        [Cout,Cin,kt,ky,kx] becomes a 3x3 kernel over 3*Cin channels [Cout,ky,kx,kt*Cin+ci]: the three temporal taps are folded
+        into the channel axis, so a Conv3d is ONE implicit GEMM over the frame triples gathered by `_frame_triples`."""
+        if self._post is None:
+            sd = self.sd
+            if "conv3d.0.conv1.weight" not in sd:
+                raise KeyError("this checkpoint was loaded without the train-only video posterior (conv3d.*, conv_mu2, conv_var2): "
+                               "build the model with with_posterior=True to evaluate MAGE.forward")
+            w = {}
+            for i in range(4):
+                for c in ("conv1", "conv2", "downsample.0"):
+                    k3 = sd[f"conv3d.{i}.{c}.weight"]                                   # [Cout, Cin, 3, 3, 3]
+                    w[f"{i}.{c}"] = ops.split(k3.permute(0, 3, 4, 2, 1).reshape(k3.shape[0], 3, 3, 3 * k3.shape[1]).contiguous())
+            ml = torch.cat([sd["conv_mu2.weight"], sd["conv_var2.weight"]], 0)          # [128, C, 3, 3]
+            w["mu_logvar"] = ops.split(ml.permute(0, 2, 3, 1).contiguous())
+            w["mu_logvar.bias"] = torch.cat([sd["conv_mu2.bias"], sd["conv_var2.bias"]]).contiguous()
+            ops.check_flag(self.device)
+            self._post = w
+        return self._post
+
+    @staticmethod
+    def _frame_triples(x: torch.Tensor, stride_t: int) -> torch.Tensor:
+        """x fp32 [T,B,R,R,C] (frame-major) -> [T',B,R,R,3C]: for every output frame t' the input frames stride_t*t' - 1, +0, +1
+        (zeros beyond the clip: Conv3d padding 1) side by side on the channel axis.  Pure data movement."""
+        T = x.shape[0]
+        To = (T - 1) // stride_t + 1
+        z = torch.zeros_like(x[:1])
+        xp = torch.cat([z, x, z], 0)
+        idx = torch.arange(To, device=x.device) * stride_t
+        return torch.cat([xp.index_select(0, idx + kt) for kt in range(3)], -1).contiguous()
+
+    def _conv3d_gn(self, xt: torch.Tensor, wname: str, gn: str, B: int, *, relu: bool, residual: Optional[torch.Tensor] = None):
+        """Conv3d 3x3x3 (bias-free, `xt` = its gathered frame triples [T',B,R,R,3C]) -> GroupNorm(16) (+ residual) (ReLU):
+        BasicBlock's conv/bn pairs (mage_model.py:266-274).  Returns fp32 [T',B,R,R,C]."""
+        To, R, C = xt.shape[0], self.R, self.C
+        y, _, _ = ops.conv2d_tc(ops.split(xt.view(To * B, R, R, xt.shape[-1])), self._posterior_weights()[wname], None, pad=(1, 1))
+        y = y.view(To * B * R * R, C)
+        part = torch.empty(To, B, 16, 2, device=self.device, dtype=torch.float64)
+        ops.gn_partial(y, part, B, R * R, groups=16)
+        ops.gn_apply(y, part, self.sd[gn + ".weight"], self.sd[gn + ".bias"], B, R * R, relu=relu,
+                     residual=residual.view(-1, C) if residual is not None else None, out=y)
+        return y.view(To, B, R, R, C)
+
+    def forward_loss(self, images: torch.Tensor, text: torch.Tensor, speed: Optional[torch.Tensor], eps: Optional[torch.Tensor],
+                     test_flag: bool = False) -> dict:
+        """MAGE.forward in eval mode (mage_model.py:575-639), the loss terms as device scalars: images [B,L,C,H,W] (all
+        frames_length frames) -> VQ tokens -> [randomness: 3-D conv posterior -> (mu, logvar) -> z = eps * exp(logvar / 2) + mu (or
+        z = eps with test_flag) -> AdaIN of the motion anchor] -> teacher-forced decoder -> cross-entropy against frames 1..L-1.
+        The teacher-forced full-sequence pass IS the sampling path's incremental pass with the given tokens fed back (the temporal
+        blocks are causal), so it runs on the same kernels.  Returns {'prediction': [1], 'kl_loss': [1] | None, 'tokens'}."""
+        assert self.use_cids and self.backend == "tc", "the objective is built for the token model on the tensor-core back end"
+        B, L = images.shape[:2]
+        R, C = self.R, self.C
+        assert L == self.L, f"MAGE.forward needs frames_length = {self.L} frames (mage_model.py:588,619), got {L}"
+        images = images.contiguous().float()
+        tok = self.vq.encode(images.view(B * L, *images.shape[2:])).view(B, L, R, R)
+        kl = None
+        z = None
+        if self.randomness:
+            assert eps is not None and tuple(eps.shape) == (B, 64, R, R)
+            # raw token embeddings of ALL frames, frame-major [L,B,R,R,C] (mage_model.py:581,605)
+            x = ops.embedding(tok.permute(1, 0, 2, 3).reshape(-1), self.sd["visual_token_embedding.weight"]).view(L, B, R, R, C)
+            for i in range(4):
+                p = f"conv3d.{i}"
+                xt = self._frame_triples(x, 2)
+                res = self._conv3d_gn(xt, f"{i}.downsample.0", p + ".downsample.1", B, relu=False)
+                y = self._conv3d_gn(xt, f"{i}.conv1", p + ".bn1", B, relu=True)
+                x = self._conv3d_gn(self._frame_triples(y, 1), f"{i}.conv2", p + ".bn2", B, relu=True, residual=res)
+            if x.shape[0] != 1:
+                raise ValueError(f"frames_length {L} leaves {x.shape[0]} frames after the posterior's four temporal halvings; the "
+                                 "reference squeezes that axis (mage_model.py:606) and fails as well")
+            pw = self._posterior_weights()
+            ml, _, _ = ops.conv2d_tc(ops.split(x.view(B, R, R, C)), pw["mu_logvar"], pw["mu_logvar.bias"], pad=(1, 1))
+            self.last_mu_logvar = ml.view(B * R * R, -1)                               # [B*R*R, mu(64) | logvar(64)] (tests)
+            z, kl_rows = ops.reparam_kl(ml.view(B * R * R, -1), eps.contiguous().float(), B, R * R)
+            z = eps.contiguous().float() if test_flag else z.view(B, 64, R, R)
+            kl = ops.scaled_sum(kl_rows, -0.5 / B)                                       # mage_model.py:625
+        M = B * R * R
+        trace = {"force_tokens": tok[:, 1:].contiguous(), "ce_rows": torch.empty(L - 1, M, device=self.device, dtype=torch.float32),
+                 "keep_logits": False, "skip_decode": True}
+        self.generate(images[:, 0], text, speed, z, trace=trace)
+        pred = ops.scaled_sum(trace["ce_rows"], 1.0 / ((L - 1) * M))                    # F.cross_entropy's mean, :619
+        ops.check_flag(self.device)
+        return {"prediction": pred, "kl_loss": kl, "tokens": tok}
 
     # ------------------------------------------------------------------ MAGE+ branch (use_cids=False): continuous latents
     def _block_seq_tc(self, i: int, x: torch.Tensor, pos0: int, n_pos: int, B: int, caches, u, h, qkv) -> None:

@@ -10,6 +10,7 @@ refuses to sample.
 """
 from __future__ import annotations
 
+import math
 import os
 import warnings
 from typing import Dict, List, Optional
@@ -200,13 +201,43 @@ def _decoder_spec(in_channels, model_channels, out_channels, frames_length, laye
     return _full_spec_subset(p, "generate_model.")
 
 
+class PIDControl:
+    """mage_model.py:394-434: the position-form PI controller that sets the KL weight beta from the measured KL (auto_beta).
+    State: the integral term I and the last output / error."""
+
+    def __init__(self):
+        self.I_k1 = 0.0
+        self.W_k1 = 0.0
+        self.e_k1 = 0.0
+
+    @staticmethod
+    def _Kp_fun(err, scale=1):
+        return 1.0 / (1.0 + float(scale) * math.exp(err))
+
+    def pid(self, exp_KL, KL_loss, Kp=0.01, Ki=-0.0001, Kd=0.0):
+        """Returns (beta clipped to [0, 1], error).  The anti-windup test of the reference (`W < 0 and W >= 1`, :419) can never be
+        true, so the integral always advances -- kept that way."""
+        err = exp_KL - KL_loss
+        P = Kp * self._Kp_fun(err)
+        I = self.I_k1 + Ki * err
+        W = P + I
+        self.W_k1, self.I_k1, self.e_k1 = W, I, err
+        return min(max(W, 0.0), 1.0), err
+
+
 class MAGE(_EngineOwner):
     """modules.mage_model.MAGE (mage_model.py:446-693), sampling path only."""
 
     def __init__(self, first_stage_config, text_encoder_config, ma_config, generate_decoder_config, codebook_size: int,
                  frames_length: int, image_resolution: int, vision_width: int, dropout: float = 0.1, use_cids=False,
-                 randomness=False, alpha=0., beta=1., v_kl=0., auto_beta=False):
+                 randomness=False, alpha=0., beta=1., v_kl=0., auto_beta=False, with_posterior: bool = False):
         super().__init__()
+        # objective weights (mage_model.py:506-511) -- read by forward() only
+        self.alpha, self.beta, self.auto_beta, self.KL_loss = alpha, beta, auto_beta, v_kl
+        self.PID = PIDControl() if (randomness and auto_beta) else None
+        # with_posterior (additive): also hold the train-only video posterior (conv3d.*, conv_mu2, conv_var2; 85 M parameters,
+        # mage_model.py:496-503) that MAGE.forward evaluates.  Off by default: sampling never touches it.
+        self.with_posterior = bool(with_posterior and randomness)
         self.frames_length, self.image_resolution, self.vision_width = frames_length, image_resolution, vision_width
         self.dropout, self.use_cids, self.randomness, self.codebook_size = dropout, use_cids, randomness, codebook_size
         try:
@@ -238,6 +269,9 @@ class MAGE(_EngineOwner):
                 for i in (0, 1):
                     top.append((f"adain.{br}.{i}.weight", (d, d, 3, 3), "conv"))
                     top.append((f"adain.{br}.{i}.bias", (d,), "bias"))
+        if self.with_posterior:
+            params_like = dict(vision_width=d, ma_config=ma_config)
+            top = top + syn.posterior_param_spec(params_like)
         tree = ParamTree(top, seed=24)
         for name, child in list(tree._modules.items()):
             self.add_module(name, child)
@@ -249,7 +283,7 @@ class MAGE(_EngineOwner):
 
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
         """Accepts released checkpoints: the train-only tensors (3-D conv posterior etc.) are dropped."""
-        sd = {k: v for k, v in state_dict.items() if not k.startswith(_TRAIN_ONLY_PREFIXES)}
+        sd = {k: v for k, v in state_dict.items() if self.with_posterior or not k.startswith(_TRAIN_ONLY_PREFIXES)}
         return super().load_state_dict(sd, strict=strict, **kw)
 
     def engine(self):
@@ -364,5 +398,51 @@ class MAGE(_EngineOwner):
         logits = torch.stack([l.view(B, -1, l.shape[-1]) for l in trace["logits"]], 1)
         return tokens, logits
 
-    def forward(self, batch, test_flag=False):
-        raise NotImplementedError("stage-2 training objective (mage_model.py:575-639) is outside the sampling path (SURVEY.md §2, N2)")
+    @torch.no_grad()
+    def forward(self, batch, test_flag=False, eps: Optional[torch.Tensor] = None):
+        """mage_model.py:575-639, the FORWARD half of the stage-2 objective in eval mode -- what the reference's periodic
+        validation computes (main_mage.py:163-176): (final_loss 0-dim tensor, loss_dict with 'val/prediction', 'val/kl_loss',
+        ['val/beta',] 'val/final_loss').  batch: 'images' [B,frames_length,C,H,W], 'text', 'speed'.  `eps` (additive) [B,64,h,w]
+        stands for the pass's one random draw, torch.randn_like in reparameterize (:571; with test_flag the draw that replaces
+        the posterior sample, :610); None draws it on the device like the reference.  Gradients, dropout and the optimiser step
+        are not built: in training mode this raises."""
+        if self.training:
+            raise NotImplementedError("MAGE.forward is built for eval mode (validation loss); training mode -- dropout, gradients, the "
+                                      "optimiser step of main_mage.py:127-152 -- is not part of this library: call .eval()")
+        if not self.use_cids:
+            raise NotImplementedError("MAGE.forward is built for the token model (use_cids=True)")
+        eng = self.engine()
+        dev = eng.device
+        images = batch["images"].to(dev, non_blocking=True)
+        text = batch["text"].to(dev, non_blocking=True)
+        speed = batch["speed"].to(dev, non_blocking=True).float() if "speed" in batch else None
+        B = text.shape[0]
+        if self.randomness:
+            if not self.with_posterior:
+                raise RuntimeError("MAGE.forward with randomness=True evaluates the video posterior (conv3d.*, conv_mu2, conv_var2): build "
+                                   "the model with with_posterior=True (config params) and load a checkpoint that has those tensors")
+            if eps is None:
+                eps = torch.randn(B, 64, self.image_resolution, self.image_resolution, device=dev)
+            eps = eps.to(dev).float().contiguous()
+        out = eng.forward_loss(images, text, speed, eps if self.randomness else None, bool(test_flag))
+        self.last_tokens_all = out["tokens"]
+        prefix = "val"   # `'train' if self.training else 'val'` (:601); training mode is refused above
+        recon = out["prediction"].reshape(())
+        loss_dict = {f"{prefix}/prediction": recon.item()}
+        if self.randomness:
+            kl = out["kl_loss"].reshape(())
+            loss_dict[f"{prefix}/kl_loss"] = kl.item()
+            if self.auto_beta:
+                self.beta, _ = self.PID.pid(self.KL_loss, kl.item())
+                loss_dict[f"{prefix}/beta"] = self.beta
+                final = recon + self.beta * kl
+            else:
+                if speed is None:   # the reference reads speed_emb here, which exists only with batch['speed'] (:612-614, :631)
+                    raise KeyError("speed")
+                speed_emb = speed.view(B, 1) @ self.speed_embedding
+                l2 = torch.mean(torch.pow(torch.norm(speed_emb, dim=-1), 2))
+                final = recon + self.beta * kl + self.alpha * l2
+        else:
+            final = recon
+        loss_dict[f"{prefix}/final_loss"] = final.item()
+        return final, loss_dict

@@ -102,6 +102,8 @@ def check_flag(device) -> None:
         f.zero_()
         if v & 2:
             raise IndexError("caption token id outside the text encoder's vocabulary (index out of range in self)")
+        if v & 4:
+            raise IndexError("cross-entropy target outside [0, n_classes) (Target is out of bounds)")
         raise _lib.MageSplitRangeError("a tensor-core operand left the fp16 hi/lo split range (|x| > 65504 or NaN); the results of "
                                        "this call are invalid (MAGE.autoregressive_generate repeats it on the fp32 SIMT kernels)")
 
@@ -534,6 +536,56 @@ def gn_partial(x: torch.Tensor, part: torch.Tensor, B: int, HW: int, groups: int
     assert part.dtype == torch.float64 and part.is_contiguous() and part.numel() == n_slots * B * groups * 2
     with _Prof("misc", 0.0):
         check(_lib.lib().mage_gn_partial_f32(_ctx(), _p(_f32(x)), _p(part), n_slots, B, HW, C, groups, _stream()), "mage_gn_partial_f32")
+
+
+def gn_apply(x: torch.Tensor, part: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, B: int, HW: int, *, relu: bool,
+             residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, out_split: Optional[torch.Tensor] = None,
+             eps: float = 1e-5) -> None:
+    """GroupNorm over (channel group x all slots x HW) of each sample from gn_partial's sums (part f64 [n_slots,B,groups,2]):
+    x fp32 [n_slots*B*HW, 512] -> (+ residual) (ReLU) -> out fp32 (may alias x) and/or out_split fp16 [2, rows, 512]."""
+    rows, C = x.shape
+    n_slots, groups = part.shape[0], part.shape[2]
+    assert rows == n_slots * B * HW and part.dtype == torch.float64 and part.is_contiguous() and (out is not None or out_split is not None)
+    stat = torch.empty(B * groups * 2, device=x.device, dtype=torch.float32)
+    with _Prof("misc", 0.0):
+        check(_lib.lib().mage_gn_apply_f32(_ctx(), _p(_f32(x)), _p(part), _p(stat), _p(_f32(gamma)), _p(_f32(beta)),
+                                           _p(_f32(residual)) if residual is not None else None, _p(out), _p(out_split), rows * C,
+                                           _p(flag(x.device)), n_slots, B, HW, C, groups, int(relu), eps, _stream()), "mage_gn_apply_f32")
+
+
+def cross_entropy_rows(logits: torch.Tensor, target: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out[row] = logsumexp(logits[row]) - logits[row, target[row]]  (F.cross_entropy(reduction='none'))."""
+    rows, K = logits.shape
+    assert logits.dtype == torch.float32 and logits.stride(1) == 1 and target.dtype == torch.int64 and target.is_contiguous()
+    assert target.numel() == rows and out.dtype == torch.float32 and out.is_contiguous() and out.numel() == rows
+    with _Prof("misc", 0.0):
+        check(_lib.lib().mage_cross_entropy_rows_f32(_ctx(), _p(logits), logits.stride(0), _p(target), _p(out), rows, K,
+                                                     _p(flag(logits.device)), _stream()), "mage_cross_entropy_rows_f32")
+    return out
+
+
+def reparam_kl(mu_logvar: torch.Tensor, eps: Optional[torch.Tensor], B: int, HW: int, want_z: bool = True):
+    """mu_logvar fp32 [B*HW, 2*Cz] (conv_mu2 | conv_var2) and the stored draw eps [B, Cz, h, w] ->
+    (z = eps * exp(0.5 logvar) + mu, NCHW like eps; kl_rows [B] = sum(1 + logvar - mu^2 - exp(logvar)))."""
+    Cz = mu_logvar.shape[-1] // 2
+    assert mu_logvar.is_contiguous() and mu_logvar.numel() == B * HW * 2 * Cz
+    z = torch.empty(B, Cz, HW, device=mu_logvar.device, dtype=torch.float32) if want_z else None
+    kl_rows = torch.empty(B, device=mu_logvar.device, dtype=torch.float32)
+    if want_z:
+        assert eps is not None and eps.is_contiguous() and eps.numel() == B * Cz * HW
+    with _Prof("misc", 0.0):
+        check(_lib.lib().mage_reparam_kl_f32(_ctx(), _p(_f32(mu_logvar)), _p(_f32(eps)) if want_z else None, _p(z), _p(kl_rows), B, HW, Cz,
+                                             _stream()), "mage_reparam_kl_f32")
+    return z, kl_rows
+
+
+def scaled_sum(x: torch.Tensor, scale: float) -> torch.Tensor:
+    """scale * sum(x) as a device scalar: one block, fixed summation order, double accumulation."""
+    assert x.is_contiguous()
+    out = torch.empty(1, device=x.device, dtype=torch.float32)
+    with _Prof("misc", 0.0):
+        check(_lib.lib().mage_scaled_sum_f32(_ctx(), _p(_f32(x)), _p(out), x.numel(), float(scale), _stream()), "mage_scaled_sum_f32")
+    return out
 
 
 def gn_silu_head(x: torch.Tensor, part: torch.Tensor, gamma, beta, w: torch.Tensor, bias: torch.Tensor, B: int, HW: int,

@@ -365,6 +365,75 @@ def test_token_taps_equals_conv_plus_linear():
     ops.check_flag(DEV)
 
 
+def test_objective_kernels_group_norm_cross_entropy_reparam_kl_sum():
+    """The bandwidth-bound pieces of the stage-2 objective's forward half (mage_b200.h, last section) against torch fp64."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(11)
+    # GroupNorm(16) over (32 channels x T frames x HW) per sample, frame-major rows, + residual + ReLU
+    T, B, HW, C = 3, 2, 64, 512
+    x = torch.randn(T, B, HW, C, generator=g) * 2 + 0.3
+    res = torch.randn(T, B, HW, C, generator=g)
+    gamma, beta = 1 + 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+    xd = x.to(DEV).view(-1, C)
+    part = torch.empty(T, B, 16, 2, device=DEV, dtype=torch.float64)
+    ops.gn_partial(xd, part, B, HW, groups=16)
+    out = torch.empty_like(xd)
+    sp = torch.empty(2, T * B * HW, C, device=DEV, dtype=torch.float16)
+    ops.gn_apply(xd, part, gamma.to(DEV), beta.to(DEV), B, HW, relu=True, residual=res.to(DEV).view(-1, C), out=out, out_split=sp)
+    ncthw = x.permute(1, 3, 0, 2).double()                                     # [B, C, T, HW]
+    want = F.relu(F.group_norm(ncthw, 16, gamma.double(), beta.double(), 1e-5) + res.permute(1, 3, 0, 2).double())
+    _close(out.view(T, B, HW, C).permute(1, 3, 0, 2), want, 1e-5, 1e-5)
+    _close(sp[0].float() + sp[1].float() / 2048, out.cpu(), 1e-6, 1e-6)
+    ops.gn_apply(xd, part, gamma.to(DEV), beta.to(DEV), B, HW, relu=False, out=out)
+    _close(out.view(T, B, HW, C).permute(1, 3, 0, 2), F.group_norm(ncthw, 16, gamma.double(), beta.double(), 1e-5), 1e-5, 1e-5)
+    # cross-entropy rows (strided logits) and the fixed-order mean
+    rows, K = 1000, 512
+    lg = torch.randn(rows, K + 8, generator=g) * 3
+    tgt = torch.randint(0, K, (rows,), generator=g)
+    loss = torch.empty(rows, device=DEV)
+    ops.cross_entropy_rows(lg.to(DEV)[:, :K], tgt.to(DEV), loss)
+    want = F.cross_entropy(lg[:, :K].double(), tgt, reduction="none")
+    _close(loss, want, 2e-6, 2e-6)
+    mean = ops.scaled_sum(loss, 1.0 / rows)
+    assert abs(mean.item() - want.mean().item()) <= 2e-6 * want.mean().item()
+    ops.check_flag(DEV)
+    bad = tgt.clone()
+    bad[17] = K
+    ops.cross_entropy_rows(lg.to(DEV)[:, :K], bad.to(DEV), loss)
+    with pytest.raises(IndexError):
+        ops.check_flag(DEV)
+    # reparameterisation + KL integrand
+    B, HW, Cz = 3, 256, 64
+    ml = torch.randn(B * HW, 2 * Cz, generator=g)
+    eps = torch.randn(B, Cz, 16, 16, generator=g)
+    z, kl_rows = ops.reparam_kl(ml.to(DEV), eps.to(DEV), B, HW)
+    mu = ml[:, :Cz].view(B, HW, Cz).permute(0, 2, 1).double()
+    lv = ml[:, Cz:].view(B, HW, Cz).permute(0, 2, 1).double()
+    _close(z, eps.view(B, Cz, HW).double() * torch.exp(0.5 * lv) + mu, 2e-6, 2e-6)
+    _close(kl_rows, (1 + lv - mu ** 2 - lv.exp()).sum((1, 2)), 2e-6, 1e-3)
+
+
+def test_conv3d_as_one_implicit_gemm_over_frame_triples():
+    """BasicBlock's Conv3d 3x3x3 (mage_model.py:267,270,273: padding 1, temporal stride 2 or 1, no bias) = ONE tensor-core
+    convolution over 3*Cin channels: the three temporal taps sit side by side on the channel axis of the gathered frame triples
+    (engine._frame_triples), the kernel is reordered to [Cout, ky, kx, kt*Cin + ci]."""
+    from mage_b200.engine import SamplerEngine
+    ops = _ops()
+    g = torch.Generator().manual_seed(12)
+    B, R, Cin, Cout = 2, 16, 128, 128
+    for T, stride_t in ((5, 2), (4, 2), (1, 2), (3, 1)):
+        x = torch.randn(T, B, R, R, Cin, generator=g)
+        w = torch.randn(Cout, Cin, 3, 3, 3, generator=g) * (27 * Cin) ** -0.5
+        want = F.conv3d(x.permute(1, 4, 0, 2, 3).double(), w.double(), None, stride=(stride_t, 1, 1), padding=1)   # [B,Cout,T',R,R]
+        xt = SamplerEngine._frame_triples(x.to(DEV), stride_t)
+        To = xt.shape[0]
+        assert To == want.shape[2] and xt.shape[-1] == 3 * Cin
+        wf = w.permute(0, 3, 4, 2, 1).reshape(Cout, 3, 3, 3 * Cin).contiguous()
+        y, _, _ = ops.conv2d_tc(ops.split(xt.view(To * B, R, R, 3 * Cin)), ops.split(wf.to(DEV)), None, pad=(1, 1))
+        _close(y.view(To, B, R, R, Cout).permute(1, 4, 0, 2, 3), want, 1e-5, 1e-5)   # fp32-grade for K = 3456 (one fp16 pass: ~5e-4)
+    ops.check_flag(DEV)
+
+
 def test_handles_are_independent():
     """all library state lives in the opaque handle.  A second handle on the same device has its own launch
     counter and tuning switches; using it does not disturb the handle the package works through."""

@@ -12,7 +12,8 @@ import pytest
 import torch
 
 from mage_b200 import synthetic as syn
-from tests.helpers import GOLDEN_DIR, LOGIT_EPS, MAGE_CASES, PLUS_CASES, load_case, load_plus_case, parity_check, pix_check
+from tests.helpers import (FORWARD_CASES, GOLDEN_DIR, LOGIT_EPS, MAGE_CASES, PLUS_CASES, load_case, load_forward_case, load_plus_case,
+                           parity_check, pix_check)
 
 pytestmark = pytest.mark.gpu
 
@@ -341,7 +342,7 @@ def test_optional_schedules_are_bit_exact():
         ops.pdl(True)   # the default
 
 
-def test_activation_outside_the_tensor_core_operand_range_is_recomputed_in_fp32(monkeypatch):
+def test_activation_outside_the_tensor_core_operand_range_is_recomputed_in_fp32(monkeypatch, backend):
     """The tensor-core kernels carry fp32 values as fp16 hi/lo pairs, so an activation beyond +-65504 cannot be represented (the
     kernels flag it).  The shipped checkpoints stay far inside (every GEMM operand but the head's is a LayerNorm / attention /
     QuickGELU output), but the path must not depend on that: such a call is repeated on the fp32 SIMT kernels with a warning --
@@ -350,6 +351,8 @@ def test_activation_outside_the_tensor_core_operand_range_is_recomputed_in_fp32(
     import warnings
 
     from mage_b200 import _lib
+    if backend != "tc":
+        pytest.skip("the operand range is a property of the tensor-core back end")
     params = syn.model_params("caterv2", frames_length=4)
     sd = syn.make_mage_state_dict(params)
     big = {k: v.clone() for k, v in sd.items()}
@@ -378,6 +381,48 @@ def test_activation_outside_the_tensor_core_operand_range_is_recomputed_in_fp32(
     monkeypatch.setenv("MAGE_RANGE_FALLBACK", "0")
     with pytest.raises(_lib.MageSplitRangeError):
         model.autoregressive_generate(batch, noise=noise)
+
+
+@pytest.mark.parametrize("name", FORWARD_CASES)
+def test_forward_loss_vs_reference_golden(name, backend):
+    """SURVEY.md §8 row N2, forward half: MAGE.forward in eval mode (what the reference's periodic validation computes,
+    main_mage.py:163-176) through the CUDA kernels against the unmodified reference's golden values: VQ tokens of all frames
+    identical, cross-entropy to 2e-5 relative, KL and final loss to 1e-4 (fp32 summation order; the KL term sums exp(logvar), which
+    multiplies the rounding of logvar -- the output of twelve 3-D convolutions and GroupNorms -- by exp(logvar), and the final
+    loss of these cases is mostly beta * KL).  The 3-D conv posterior (84.9 M parameters) runs as tensor-core implicit GEMMs with the temporal taps folded into the
+    channel axis; the teacher-forced pass is the sampling path's incremental pass with the given tokens fed back."""
+    if backend != "tc":
+        pytest.skip("the objective's forward pass is built on the tensor-core back end")
+    params, sd, batch, eps, test_flag, g = load_forward_case(name)
+    from mage_b200.config import instantiate_from_config
+    model = instantiate_from_config({"target": "modules.mage_model.MAGE", "params": dict(params, with_posterior=True)})
+    model.load_state_dict(sd)
+    model = model.to("cuda").eval()
+    final, loss_dict = model({k: v.to("cuda") for k, v in batch.items()}, test_flag=test_flag, eps=eps)
+    tok = model.last_tokens_all.cpu().numpy()
+    print(f"[parity] forward {name}: token mismatches {int((tok != g['tokens']).sum())} of {tok.size}; "
+          + ", ".join(f"{k} {v:.7g}" for k, v in loss_dict.items()) + f"; reference prediction {float(g['prediction']):.7g} "
+          f"final {float(g['final_loss']):.7g}")
+    assert np.array_equal(tok, g["tokens"])
+    assert final.dim() == 0 and abs(final.item() - loss_dict["val/final_loss"]) == 0
+    for key in ("prediction", "kl_loss", "final_loss"):
+        if key in g:
+            got, want = loss_dict["val/" + key], float(g[key])
+            assert abs(got - want) <= (2e-5 if key == "prediction" else 1e-4) * abs(want), (key, got, want)
+    if "mu" in g:   # the posterior's two heads themselves, before the exponential
+        ml = model.engine().last_mu_logvar.view(-1, 16, 16, 128).permute(0, 3, 1, 2).cpu().numpy()
+        for k, arr in (("mu", ml[:, :64]), ("logvar", ml[:, 64:])):
+            err = np.abs(arr - g[k]).max()
+            print(f"[parity] forward {name}: max |{k} - reference| = {err:.2e} (max |{k}| {np.abs(g[k]).max():.2f})")
+            assert err <= 4e-5 * np.abs(g[k]).max()   # fp32 summation order through 12 convolutions of K = 13824 + GroupNorms
+    assert ("val/kl_loss" in loss_dict) == bool(params["randomness"])
+    # training mode is refused loudly (dropout / gradients are not built), and so is a model without the posterior tensors
+    with pytest.raises(NotImplementedError):
+        model.train()({k: v.to("cuda") for k, v in batch.items()})
+    if params["randomness"]:
+        plain = _build(params, sd)
+        with pytest.raises(RuntimeError, match="with_posterior"):
+            plain({k: v.to("cuda") for k, v in batch.items()}, eps=eps)
 
 
 def test_graph_cache_is_bounded_and_shares_one_pool():

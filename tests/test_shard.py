@@ -264,3 +264,22 @@ def test_seeded_noise_depends_only_on_the_global_prompt_index():
                 parts.append(shard.noise_for_prompts(11, range(b0, min(b0 + 4, hi))))
         assert torch.equal(torch.cat(parts), full)
     assert not torch.equal(shard.noise_for_prompts(12, range(0, 2)), full[:2])
+
+
+def test_pid_control_follows_the_reference():
+    """PIDControl (mage_model.py:394-434, the auto_beta controller of MAGE.forward): (beta, error) for a sequence of measured KL
+    values, as produced by the reference's class (values generated with oracle/ref_shims.load_reference(); re-checked live when
+    /root/reference is present)."""
+    from mage_b200.model import PIDControl
+    seq = [3.0, 10.0, 0.5, 200.0, 1e-3, 50.0, 7.0]
+    want = [(0.0009920292202211755, 2.0), (0.010233071490757153, -5.0), (0.0, 4.5), (0.02935, -195.0), (0.018917095022615533, 4.999),
+            (0.0333501, -45.0), (0.03235807077977882, -2.0)]
+    pid = PIDControl()
+    got = [pid.pid(5.0, kl) for kl in seq]
+    for (b, e), (wb, we) in zip(got, want):
+        assert abs(b - wb) <= 1e-15 and abs(e - we) <= 1e-12
+    from oracle import ref_shims
+    if ref_shims.reference_available():
+        mm, _ = ref_shims.load_reference()
+        ref = mm.PIDControl()
+        assert [ref.pid(5.0, kl) for kl in seq] == got
