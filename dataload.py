@@ -66,9 +66,10 @@ def load_first_frame(path: str, channels: int, size: int) -> torch.Tensor:
 
 
 class SyntheticCaptionVideos(Dataset):
-    def __init__(self, model_params: dict, n_items: int, seed: int = 1234, text_len: int = 20, with_video_id: bool = True):
+    def __init__(self, model_params: dict, n_items: int, seed: int = 1234, text_len: int = 20, with_video_id: bool = True,
+                 frames: int = 1):
         self.n = int(n_items)
-        self.batch = syn.make_batch(model_params, self.n, seed=seed, text_len=text_len) if self.n else {}
+        self.batch = syn.make_batch(model_params, self.n, seed=seed, text_len=text_len, frames=frames) if self.n else {}
         self.with_video_id = with_video_id
 
     def __len__(self):

@@ -90,6 +90,33 @@ def sum_over_ranks(value: float, device: torch.device) -> float:
     return float(t.item())
 
 
+def validation_loss(loss_fn, batches, device: torch.device, distributed: Optional[bool] = None) -> float:
+    """The reference's periodic validation (main_mage.py:163-182): the mean over THIS rank's batches of `loss_fn(batch)[0]`
+    (MAGE.forward's final loss, eval mode, no gradients), then -- when running distributed -- barrier, all_reduce(SUM) of that
+    per-rank mean and division by the world size: the one collective the reference's stage-2 driver issues besides DDP's gradient
+    all-reduce.  `loss_fn` returns (0-dim tensor, dict) like MAGE.forward; batches are dicts ('video_id' is dropped, :169-170)."""
+    import torch.distributed as dist
+
+    total = torch.zeros((), dtype=torch.float32, device=device)
+    count = 0
+    with torch.no_grad():
+        for batch in batches:
+            batch = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in batch.items() if k != "video_id"}
+            loss, _ = loss_fn(batch)
+            total += loss.detach().to(device=device, dtype=torch.float32)
+            count += 1
+    if count == 0:
+        raise ValueError("validation needs at least one batch on every rank")
+    total /= count
+    if distributed is None:
+        distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    if distributed:
+        dist.barrier()
+        dist.all_reduce(total, op=dist.ReduceOp.SUM)
+        total /= dist.get_world_size()
+    return float(total.item())
+
+
 def gather_to_rank0(x: torch.Tensor, total: int) -> Optional[torch.Tensor]:
     """Concatenate the per-rank slices (dim 0, sizes per shard_bounds) on rank 0; None elsewhere.
     Ragged slices are padded to the largest one for the all_gather and trimmed afterwards."""

@@ -14,6 +14,11 @@ Additive flags (the reference hard-wires batch_size=1 and needs the datasets on 
   --config           used only when <dir>/config.yaml does not exist
 Under torchrun (WORLD_SIZE > 1) the prompt list is cut into contiguous per-rank slices (mage_b200/shard.py);
 there is no collective on the data path.  `--split train` is the stage-2 training driver, outside this path.
+
+  --split val        (additive) the FORWARD half of that driver: the reference's periodic validation loss (main_mage.py:163-182) of
+                     the checkpoint over the test split -- MAGE.forward in eval mode per batch, mean per rank, all_reduce(SUM) /
+                     world size over NCCL.  Needs clips with all frames_length frames and a checkpoint that holds the video
+                     posterior (the model is built with `with_posterior`).  --seed fixes the reparameterisation draws.
 """
 import argparse
 import os
@@ -178,10 +183,56 @@ def sampling(opt):
     return frames
 
 
+def validation(opt):
+    """main_mage.py:163-182 for one checkpoint: `test_loss` of the test split, printed by rank 0."""
+    configs = load_configs(opt)
+    rank, world, local_rank = shard.env_world()
+    if world > 1:
+        opt.gpu = local_rank
+    torch.cuda.set_device(opt.gpu or 0)
+    device = torch.device('cuda:{}'.format(opt.gpu or 0))
+    if world > 1:
+        shard.init_distributed(opt.dist_backend, device)
+    mp = configs['model']['params']
+    L = mp['frames_length']
+    if opt.synthetic > 0:
+        from dataload import SyntheticCaptionVideos
+        test_dataset = SyntheticCaptionVideos(mp, opt.synthetic, seed=1234 if opt.seed is None else opt.seed, frames=L)
+    else:
+        test_dataset = instantiate_from_config(configs['data'], {'split': 'test'})
+    lo, hi = shard.shard_bounds(len(test_dataset), world, rank)
+    from dataload import collate_fn
+    loader = DataLoader(Subset(test_dataset, range(lo, hi)), batch_size=opt.batch_size, shuffle=False, num_workers=0,
+                        pin_memory=True, collate_fn=collate_fn)
+    cfg = dict(configs['model'])
+    cfg['params'] = dict(mp, with_posterior=True)
+    model = instantiate_from_config(cfg).to(device)
+    load_checkpoint(model, opt)
+    model.eval()
+    seen = [0]
+
+    def loss_fn(batch):
+        eps = None
+        if opt.seed is not None and model.randomness:   # the draw of a clip depends only on (seed, global clip index)
+            n = batch['text'].shape[0]
+            eps = shard.noise_for_prompts(opt.seed, range(lo + seen[0], lo + seen[0] + n), model.image_resolution)
+            seen[0] += n
+        return model(batch, eps=eps)
+
+    t0 = time.perf_counter()
+    test_loss = shard.validation_loss(loss_fn, loader, device)
+    torch.cuda.synchronize()
+    if rank == 0:
+        print("test_loss = %.6f  (%d clips of %d frames, %d GPU(s), %.2fs)" % (test_loss, len(test_dataset), L, world, time.perf_counter() - t0))
+    return test_loss
+
+
 if __name__ == "__main__":
     opt = parser.parse_args()
     if opt.split == 'test':
         sampling(opt)
+    elif opt.split == 'val':
+        validation(opt)
     elif opt.split == 'train':
         raise SystemExit("--split train (stage-2 training, main_mage.py:58-199) is outside the sampling path this repo implements "
                          "(SURVEY.md §8f N2)")

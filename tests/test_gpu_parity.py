@@ -614,6 +614,35 @@ def test_main_mage_seeded_clips_do_not_depend_on_batch_size(tmp_path):
         assert np.array_equal(clips[1][k], clips[3][k]), k
 
 
+def test_main_mage_split_val_is_the_reference_validation_loss(tmp_path, backend):
+    """`--split val` (additive): the reference's periodic validation (main_mage.py:163-182) for one checkpoint -- MAGE.forward in
+    eval mode per batch, mean over the batches -- against the oracle's forward_loss on the same clips and draws."""
+    import yaml
+
+    import main_mage
+    from mage_b200 import shard
+    from oracle import mage_oracle as orc
+    if backend != "tc":
+        pytest.skip("the objective's forward pass is built on the tensor-core back end")
+    params = syn.model_params("caterv2", frames_length=4)
+    (tmp_path / "config.yaml").write_text(yaml.safe_dump({"model": {"target": "modules.mage_model.MAGE", "params": params},
+                                                          "data": {"target": "dataload.CATER", "params": {}}}))
+    sd = syn.make_mage_state_dict(params, posterior=True)
+    torch.save({"state_dict": sd}, tmp_path / "model_best.pth")
+    opt = main_mage.parser.parse_args(["--split", "val", "--test_model", str(tmp_path / "model_best.pth"), "--synthetic", "3",
+                                       "--batch-size", "2", "--seed", "9"])
+    got = main_mage.validation(opt)
+    clips = syn.make_batch(params, 3, seed=9, text_len=20, frames=4)
+    want = []
+    for lo, hi in ((0, 2), (2, 3)):
+        b = {k: v[lo:hi] for k, v in clips.items()}
+        eps = shard.noise_for_prompts(9, range(lo, hi), params["image_resolution"])
+        want.append(orc.forward_loss(sd, b, eps, randomness=True, beta=params["beta"], alpha=params["alpha"])["final_loss"])
+    want = sum(want) / len(want)
+    print(f"[parity] --split val: test_loss {got:.6f}, oracle {want:.6f}")
+    assert abs(got - want) <= 1e-4 * abs(want)
+
+
 def test_main_mage_caption_and_image_prompt(tmp_path):
     """Additive entry: one clip from a caption (the dataset's word-level vocabulary) and a first-frame image file."""
     import yaml

@@ -65,6 +65,39 @@ def _worker(rank, world, port, total, tmp):
     dist.destroy_process_group()
 
 
+def _val_worker(rank, world, port, tmp):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    shard.init_distributed("gloo")
+    # rank r holds r + 2 batches; the stand-in loss of a batch is the mean of its 'x'
+    batches = [{"x": torch.full((3,), float(10 * rank + i)), "video_id": ["a", "b", "c"]} for i in range(rank + 2)]
+    seen = []
+
+    def loss_fn(batch):
+        assert "video_id" not in batch     # dropped like main_mage.py:169-170
+        seen.append(1)
+        return batch["x"].mean(), {}
+
+    got = shard.validation_loss(loss_fn, batches, torch.device("cpu"))
+    per_rank = [sum(10 * r + i for i in range(r + 2)) / (r + 2) for r in range(world)]
+    assert len(seen) == rank + 2 and abs(got - sum(per_rank) / world) < 1e-6, (got, per_rank)
+    if rank == 0:
+        open(os.path.join(tmp, "val_ok"), "w").write("1")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_validation_loss_is_the_mean_of_the_per_rank_means(tmp_path):
+    """main_mage.py:163-182: per-rank mean of the batch losses, all_reduce(SUM), divided by the world size (a mean of means, not a
+    clip-weighted mean -- kept like the reference).  Single process: just the mean."""
+    port = _free_port()
+    mp.spawn(_val_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "val_ok").exists()
+    one = shard.validation_loss(lambda b: (b["x"].sum(), {}), [{"x": torch.ones(2)}, {"x": torch.ones(4)}], torch.device("cpu"))
+    assert one == 3.0
+    with pytest.raises(ValueError):
+        shard.validation_loss(lambda b: (b["x"].sum(), {}), [], torch.device("cpu"))
+
+
 @pytest.mark.parametrize("total", [5, 8])
 def test_two_rank_gloo_shard_and_gather(tmp_path, total):
     port = _free_port()
