@@ -50,6 +50,10 @@ WORKLOADS = {
     # GroupNorm head over all slots => suffix re-evaluation, (L-1)L/2 position passes; stand-in first stage)
     "c5plus": dict(family="caterv2plus", frames=32, batch=64, gflop=None, name="CATER-GEN-v2 MAGE+ 128x128x32 (use_cids=False)",
                    cfg="BASELINE.json configs[4], mage+_caterv2.yaml branch", metric="generated frames/sec, CATER-v2 MAGE+ 128x128x32 b64"),
+    # SURVEY.md §8 row N2, forward half: the reference's validation loss (MAGE.forward in eval mode, main_mage.py:163-176) on the C4 shape
+    "c4val": dict(family="caterv1", frames=16, batch=16, gflop=None, name="CATER-GEN-v1 128x128x16, MAGE.forward (validation loss, eval mode)",
+                  cfg="BASELINE.json configs[3] shape; the stage-2 objective's forward half", val=True,
+                  metric="scored frames/sec, MAGE.forward validation loss, CATER-v1 128x128x16 b16"),
 }
 
 
@@ -259,6 +263,206 @@ def eager_gpu_baseline(wl, dev, batch_n):
     del ref
     torch.cuda.empty_cache()
     return {"value": round(batch_n * (L - 1) / dt, 2), "unit": UNIT, "batch": batch_n, "seconds": round(dt, 3), "kind": kind}
+
+
+# ---------------------------------------------------------------------------------------------- validation loss (MAGE.forward, eval mode)
+def _val_inputs(wl, batch, seed=1234, eps_seed=99):
+    from mage_b200 import synthetic as syn
+    params = syn.model_params(wl["family"], frames_length=wl["frames"])
+    fs = params["first_stage_config"]["params"]
+    cb = os.path.join(syn.GOLDEN_DIR, "codebook_f%d.npy" % fs["down_ratio"])
+    sd = syn.make_mage_state_dict(params, conditioned=os.path.isfile(cb), posterior=True)
+    b = syn.make_batch(params, batch, seed=seed, text_len=TEXT_LEN, frames=wl["frames"])
+    eps = syn.make_noise(batch, seed=eps_seed) if params["randomness"] else None
+    return params, sd, b, eps
+
+
+def reference_forward_sample(wl, device, batch_n, threads=None):
+    """The reference's own MAGE.forward in eval mode, no gradients (what its periodic validation runs, main_mage.py:166-176), on
+    `batch_n` clips: frames scored per second.  Unmodified reference when a copy is present, else the oracle's restatement."""
+    from oracle import mage_oracle as orc
+    if threads:
+        torch.set_num_threads(threads)
+    L = wl["frames"]
+    params, sd, batch, eps = _val_inputs(wl, batch_n, seed=4321, eps_seed=7)
+    ref = _reference_model(params, sd, device)
+    cuda = torch.device(device).type == "cuda"
+    with torch.no_grad():
+        if ref is not None:
+            eb = {k: v.to(device) for k, v in batch.items()}
+            if cuda:
+                ref({k: v[:1] for k, v in eb.items()})
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ref(eb)
+            kind = "reference"
+        else:
+            t0 = time.perf_counter()
+            orc.forward_loss(sd, batch, eps, randomness=params["randomness"], beta=params.get("beta", 1.0), alpha=params.get("alpha", 0.0))
+            kind = "port"
+        if cuda:
+            torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    del ref
+    return batch_n * (L - 1) / dt, dt, kind
+
+
+def run_reference_val(args, wl, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    vals, secs, kind = [], [], None
+    for i in range(args.warmup + args.steps):
+        v, dt, kind = reference_forward_sample(wl, "cpu", 1, threads)
+        if i >= args.warmup:
+            vals.append(v)
+            secs.append(dt)
+    value = sum(vals) / len(vals)
+    sample = (f"1 clip of {wl['name']}: one MAGE.forward call of the {'unmodified reference' if kind == 'reference' else 'oracle restatement'} "
+              f"in eval mode under no_grad, {sum(secs) / len(secs):.2f}s on {threads} threads")
+    line = {"impl": "reference", "metric": wl["metric"], "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(1e3 * sum(secs) / len(secs), 1), "higher_is_better": True, "scaling": args.scaling,
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{wl['name']}, global batch {wl['batch']} ({wl['cfg']}); timed on 1 clip", "family": wl["family"],
+                       "frames_length": wl["frames"], "global_batch": wl["batch"], "text_len": TEXT_LEN},
+            "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+            "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_cuda_val(args, wl, rank, world, local_rank):
+    """`--workload c4val`: a step is one MAGE.forward call (eval mode) over the rank's clips -- VQ-VAE encode of all L frames, 3-D conv
+    posterior, motion anchor, teacher-forced decoder in full-sequence form, cross-entropy / KL -- returning the reference's
+    (final_loss, loss_dict).  Clips shard over the GPUs like prompts; the loss is then the all_reduce of main_mage.py:177-180."""
+    import torch.distributed as dist
+
+    from mage_b200 import ops, shard
+    from mage_b200.config import instantiate_from_config
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = os.environ.get("MAGE_NCCL_DEBUG", "INFO")
+        os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
+        dist.init_process_group("nccl", device_id=dev)
+    L = wl["frames"]
+    G = args.batch if args.batch > 0 else wl["batch"]
+    params, sd, gbatch, geps = _val_inputs(wl, G)
+    lo, hi = shard.shard_bounds(G, world, rank)
+    B = hi - lo
+    model = instantiate_from_config({"target": "modules.mage_model.MAGE", "params": dict(params, with_posterior=True)})
+    model.load_state_dict(sd)
+    model = model.to(dev).eval()
+    host = {k: v[lo:hi].contiguous().pin_memory() for k, v in gbatch.items()}
+    eps_h = geps[lo:hi].contiguous().pin_memory() if geps is not None else None
+    dbatch = {k: v.to(dev) for k, v in host.items()}
+    deps = eps_h.to(dev) if eps_h is not None else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allred(x, op):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    for _ in range(max(args.warmup, 3)):
+        model(dbatch, eps=deps)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    n0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        final, loss_dict = model(dbatch, eps=deps)
+    e1.record()
+    barrier()
+    ms_max = allred(e0.elapsed_time(e1), dist.ReduceOp.MAX if world > 1 else None)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ops.launch_count() - n0
+    frames_step = allred(B * (L - 1), dist.ReduceOp.SUM if world > 1 else None)
+    value = frames_step * args.steps / (ms_max / 1e3)
+    test_loss = shard.validation_loss(lambda b: model(b, eps=deps), [dbatch], dev)     # per-rank mean -> all_reduce / world
+    # end to end: the clips start in pinned host memory, the losses come back as Python floats
+    model(host, eps=eps_h)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        model(host, eps=eps_h)
+    barrier()
+    e2e_value = frames_step * args.steps / allred(time.perf_counter() - t0, dist.ReduceOp.MAX if world > 1 else None)
+    h2d = sum(v.numel() * v.element_size() for v in host.values()) + (eps_h.numel() * 4 if eps_h is not None else 0)
+    if rank == 0:
+        ops.PROFILE = []
+        model(dbatch, eps=deps)
+        torch.cuda.synchronize()
+        prof, ops.PROFILE = ops.PROFILE, None
+        agg = {}
+        for kind, flops, a, b in prof:
+            d = agg.setdefault(kind, [0.0, 0.0, 0])
+            d[0] += flops; d[1] += a.elapsed_time(b); d[2] += 1
+        peaks, how = _peaks()
+        peak = peaks["bf16_tflops_sustained"]
+        fl = sum(agg.get(k, [0.0, 0.0, 0])[0] for k in ("gemm", "conv"))
+        ms = sum(agg.get(k, [0.0, 0.0, 0])[1] for k in ("gemm", "conv"))
+        ach = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+        roof = {"bound": "tensor", "kernel": "tensor-core classes of the pass: full-sequence decoder GEMMs (tc_gemm_kernel, fused QKV + axial "
+                                             "attention) and the posterior's 3x3x3 convolutions as implicit GEMMs over frame triples (tc_conv_halo_kernel)",
+                "achieved": round(ach, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4), "traffic": None,
+                "peak_source": how + ", dense bf16 sustained; 3 fp16 MMAs per product (fp32-grade)", "own_ceiling_frac": round(3 * ach / peak, 4),
+                "breakdown_ms_per_step": {k: {"ms_per_step": round(v[1], 2), "launches": v[2], "tflops": round(v[0] / max(v[1], 1e-9) / 1e9, 1)}
+                                          for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])},
+                "how": "sum of algorithmic FLOPs / sum of CUDA-event durations over every launch of the two classes in one step of rank 0"}
+        parity = eager = cpu = None
+        if not args.no_parity:
+            from oracle import mage_oracle as orc
+            torch.set_num_threads(max(1, (os.cpu_count() or 1) - (world - 1)))
+            t0 = time.perf_counter()
+            sub = {k: v[:1] for k, v in host.items()}
+            got = model({k: v.to(dev) for k, v in sub.items()}, eps=deps[:1] if deps is not None else None)[1]
+            want = orc.forward_loss(sd, sub, eps_h[:1] if eps_h is not None else None, randomness=params["randomness"],
+                                    beta=params.get("beta", 1.0), alpha=params.get("alpha", 0.0))
+            parity = {"rows": 1, "got": {k.split("/")[1]: v for k, v in got.items()}, "oracle": want,
+                      "rel_err": {k: abs(got["val/" + k] - want[k]) / abs(want[k]) for k in want},
+                      "oracle_seconds": round(time.perf_counter() - t0, 1),
+                      "what": "MAGE.forward of clip 0 of the timed batch alone vs oracle.forward_loss (CPU fp32, same draw)"}
+        if args.eager_gpu > 0:
+            model.invalidate()
+            torch.cuda.empty_cache()
+            try:
+                v, dt, kind = reference_forward_sample(wl, dev, G)
+                eager = {"value": round(v, 2), "unit": UNIT, "batch": G, "seconds": round(dt, 3),
+                         "kind": ("the unmodified reference" if kind == "reference" else "oracle restatement") +
+                                 " (MAGE.forward, eval, no_grad, torch eager, PyTorch default precision flags) on the same GPU",
+                         "ratio_resident_per_gpu": round(value / world / v, 2)}
+            except Exception as e:
+                eager = {"error": f"{type(e).__name__}: {e}"[:300]}
+        if world == 1 and not args.no_cpu:
+            v, dt, kind = reference_forward_sample(wl, "cpu", 1, os.cpu_count() or 1)
+            cpu = {"value": round(v, 4), "unit": UNIT, "cores": os.cpu_count() or 1, "kind": kind,
+                   "sample": f"1 clip of {wl['name']}: one MAGE.forward call (eval, no_grad), {dt:.2f}s on {os.cpu_count() or 1} threads"}
+        line = {"metric": wl["metric"], "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": round(ms_max / args.steps, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": f"{wl['name']}, global batch {G} ({wl['cfg']})", "family": wl["family"], "frames_length": L,
+                           "global_batch": G, "batch_per_gpu": B, "text_len": TEXT_LEN,
+                           "parallelism": f"clip-shard x{world}; one all_reduce of the per-rank mean loss", "cuda_graph": False,
+                           "l2": "working set >> L2 (full-sequence activations %.1f GB per tensor); no explicit flush" % (L * B * 256 * 2048 * 4 / 1e9)},
+                "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12},
+                "gpu_launches": int(launches), "kernels_per_step": int(launches // args.steps), "roofline": roof, "cpu_baseline": cpu,
+                "clocks": clocks, "parity": parity, "test_loss": test_loss, "loss_dict": loss_dict}
+        if eager is not None:
+            line["eager_gpu_baseline"] = eager
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # ---------------------------------------------------------------------------------------------- this repo's CUDA path
@@ -639,14 +843,16 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, wl, rank)
+        (run_reference_val if wl.get("val") else run_reference)(args, wl, rank)
         return
     if world == 1 and args.gpus > 1:
         # convenience: re-launch under torchrun
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
-    if wl["family"] == "caterv2plus":
+    if wl.get("val"):
+        run_cuda_val(args, wl, rank, world, local_rank)
+    elif wl["family"] == "caterv2plus":
         run_cuda_plus(args, wl, rank, world, local_rank)
     else:
         run_cuda(args, wl, rank, world, local_rank)

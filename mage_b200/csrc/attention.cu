@@ -450,7 +450,7 @@ extern "C" int mage_temporal_attn_step_f32(mage_ctx* ctx, const float* qkv, floa
   MAGE_CHECK_ARG(aligned16(qkv) && aligned16(kcache) && aligned16(vcache) && aligned16(out) && (out || out_split));
   const size_t smem = (size_t)2 * (pos + 1) * TA_HALF * sizeof(float);
   const size_t smem_max = (size_t)2 * Lmax * TA_HALF * sizeof(float);
-  if (smem_max > 48 * 1024) {   // the opt-in shared-memory size is a per-device attribute: remembered in the handle, not in a static
+  if (smem_max > 40 * 1024) {   // opt in early: static shared memory counts against the 48 KB default too.  Per-device attribute: remembered in the handle
     const void* fn = reinterpret_cast<const void*>(&temporal_attn_kernel);
     int k = ctx->find(fn);
     if (k < 0 || ctx->cfg_smem[k] < smem_max) {
@@ -473,7 +473,7 @@ extern "C" int mage_temporal_attn_seq_f32(mage_ctx* ctx, const float* qkv, float
   MAGE_CHECK_ARG(aligned16(qkv) && aligned16(kcache) && aligned16(vcache));
   const size_t smem = (size_t)(2 * (pos0 + n_pos) + n_pos) * TA_HALF * sizeof(float);
   const size_t smem_max = (size_t)3 * Lmax * TA_HALF * sizeof(float);
-  if (smem_max > 48 * 1024) {
+  if (smem_max > 40 * 1024) {   // static shared memory counts against the 48 KB default as well
     const void* fn = reinterpret_cast<const void*>(&temporal_attn_seq_kernel);
     int k = ctx->find(fn);
     if (k < 0 || ctx->cfg_smem[k] < smem_max) {

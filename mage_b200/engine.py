@@ -730,24 +730,8 @@ class SamplerEngine:
         B, T = text.shape
         M = B * R * R
         p = "generate_model."
-        z = self.vq.encode_features(images0)
-        ops.vq_argmin(z.view(M, -1), self.vq.codebook, out=tok0_out.view(-1))
         tc = self.backend == "tc"
-        temb, _ = self._text_encoder(text)
-        if tc:
-            f0, f0_split = self._token_features_tc(tok0_out, B, want_f32=True)
-            anchor = self._ma_encoder_tc(f0, f0_split, temb, B, T).view(B, R, R, C)
-        else:
-            f0 = self._token_features(tok0_out, B)
-            anchor = self._ma_encoder(f0, temb, B, T).view(B, R, R, C)
-        if trace is not None:
-            trace["text_emb"], trace["first_img"], trace["anchor_ma"] = temb.view(B, T, C).clone(), f0.view(B, R * R, C).clone(), anchor.clone()
-        if noise is not None:
-            anchor = self._adain_tc(anchor, noise, B) if tc else self._adain(anchor, noise, B)
-        if speed is not None:
-            ops.add_scaled_vec(anchor, speed, sd["speed_embedding"].view(-1))
-        if trace is not None:
-            trace["anchor"] = anchor.clone()
+        anchor = self._motion_anchor(images0, text, speed, noise, tok0_out, trace)
         caches = {i: (torch.empty(M, L, C, device=self.device, dtype=torch.float32),
                       torch.empty(M, L, C, device=self.device, dtype=torch.float32))
                   for i in range(self.n_blocks) if i % 3 == 0}
@@ -767,6 +751,34 @@ class SamplerEngine:
                  else self._block_step(i, x, 0, B, caches))
         logits = torch.empty(M, sd[p + "out.weight"].shape[0], device=self.device, dtype=torch.float32)
         return dict(B=B, x=x, caches=caches, bufs=bufs, logits=logits, tok=tok0_out)
+
+    def _motion_anchor(self, images0: torch.Tensor, text: torch.Tensor, speed: Optional[torch.Tensor], noise: Optional[torch.Tensor],
+                       tok0_out: torch.Tensor, trace: Optional[dict]) -> torch.Tensor:
+        """mage_model.py:642-668 (= :577-614 of the training forward): VQ tokens of frame 0 into `tok0_out`, their features, the text
+        encoder, the motion-anchor cross-attention, AdaIN with `noise` [B,64,R,R] (the test-time draw, or the posterior sample of
+        MAGE.forward), the speed embedding.  Returns the anchor fp32 [B,R,R,C]."""
+        sd, C, R = self.sd, self.C, self.R
+        B, T = text.shape
+        M = B * R * R
+        z = self.vq.encode_features(images0)
+        ops.vq_argmin(z.view(M, -1), self.vq.codebook, out=tok0_out.view(-1))
+        tc = self.backend == "tc"
+        temb, _ = self._text_encoder(text)
+        if tc:
+            f0, f0_split = self._token_features_tc(tok0_out, B, want_f32=True)
+            anchor = self._ma_encoder_tc(f0, f0_split, temb, B, T).view(B, R, R, C)
+        else:
+            f0 = self._token_features(tok0_out, B)
+            anchor = self._ma_encoder(f0, temb, B, T).view(B, R, R, C)
+        if trace is not None:
+            trace["text_emb"], trace["first_img"], trace["anchor_ma"] = temb.view(B, T, C).clone(), f0.view(B, R * R, C).clone(), anchor.clone()
+        if noise is not None:
+            anchor = self._adain_tc(anchor, noise, B) if tc else self._adain(anchor, noise, B)
+        if speed is not None:
+            ops.add_scaled_vec(anchor, speed, sd["speed_embedding"].view(-1))
+        if trace is not None:
+            trace["anchor"] = anchor.clone()
+        return anchor
 
     def _decode_step(self, st: dict, j: int, tok_out: torch.Tensor, trace: Optional[dict]) -> None:
         """Temporal position j+1 of one chunk: features of the previous frame's tokens -> six blocks -> head -> greedy tokens of
@@ -988,13 +1000,45 @@ class SamplerEngine:
                      residual=residual.view(-1, C) if residual is not None else None, out=y)
         return y.view(To, B, R, R, C)
 
+    def _teacher_forced_ce(self, tok: torch.Tensor, anchor: torch.Tensor) -> torch.Tensor:
+        """FlatAxialDecoder.forward + F.cross_entropy(reduction='none') (mage_model.py:374-390, :619) in FULL-SEQUENCE form: all
+        L temporal positions go through each block as one batch of images (`_block_seq_tc`: M = L*B*256 rows per GEMM instead of
+        L passes over B*256), position 0 = context_linear(anchor), position j+1 = in_linear(features of frame j's GIVEN tokens).
+        tok int64 [B,L,R,R]; returns the per-row losses of positions 1..L-1, fp32 [(L-1)*B*R*R] (position-major)."""
+        sd, ws, C, R, L = self.sd, self.ws, self.C, self.R, self.L
+        p = "generate_model."
+        B = tok.shape[0]
+        M = B * R * R
+        dev = self.device
+        x = torch.empty(L * M, C, device=dev, dtype=torch.float32)
+        ops.gemm_tc(ops.split(anchor.view(M, C)), ws[p + "context_linear.weight"], self.bias_ctx0, out=x[:M])
+        tok_t = tok.permute(1, 0, 2, 3).contiguous()                                   # frame-major [L,B,R,R]
+        for j in range(L - 1):
+            if self.tok_table is not None:
+                ops.token_taps(tok_t[j], self.tok_table, self.tok_posW, self.bias_in_T[j + 1], x[(j + 1) * M:(j + 2) * M])
+            else:
+                ops.gemm_tc(self._token_features_tc(tok_t[j].reshape(-1), B), ws[p + "in_linear.weight"], self.bias_in_T[j + 1],
+                            out=x[(j + 1) * M:(j + 2) * M])
+        caches = {i: (torch.empty(M, L, C, device=dev, dtype=torch.float32), torch.empty(M, L, C, device=dev, dtype=torch.float32))
+                  for i in range(self.n_blocks) if i % 3 == 0}
+        u = torch.empty(2, L * M, C, device=dev, dtype=torch.float16)
+        h = torch.empty(2, L * M, 4 * C, device=dev, dtype=torch.float16)
+        qkv = torch.empty(L * M, 3 * C, device=dev, dtype=torch.float32)
+        for i in range(self.n_blocks):
+            self._block_seq_tc(i, x, 0, L, B, caches, u, h, qkv)
+        del h, qkv
+        logits, _, _ = ops.gemm_tc(ops.split(x[M:]), ws[p + "out.weight"], sd[p + "out.bias"])
+        ce = torch.empty((L - 1) * M, device=dev, dtype=torch.float32)
+        return ops.cross_entropy_rows(logits, tok_t[1:].reshape(-1), ce)
+
     def forward_loss(self, images: torch.Tensor, text: torch.Tensor, speed: Optional[torch.Tensor], eps: Optional[torch.Tensor],
-                     test_flag: bool = False) -> dict:
+                     test_flag: bool = False, incremental: bool = False) -> dict:
         """MAGE.forward in eval mode (mage_model.py:575-639), the loss terms as device scalars: images [B,L,C,H,W] (all
         frames_length frames) -> VQ tokens -> [randomness: 3-D conv posterior -> (mu, logvar) -> z = eps * exp(logvar / 2) + mu (or
         z = eps with test_flag) -> AdaIN of the motion anchor] -> teacher-forced decoder -> cross-entropy against frames 1..L-1.
-        The teacher-forced full-sequence pass IS the sampling path's incremental pass with the given tokens fed back (the temporal
-        blocks are causal), so it runs on the same kernels.  Returns {'prediction': [1], 'kl_loss': [1] | None, 'tokens'}."""
+        The teacher-forced pass runs in full-sequence form (`_teacher_forced_ce`); `incremental=True` runs it as the sampling
+        path's one-position-per-step pass with the given tokens fed back instead -- the same arithmetic (the temporal blocks are
+        causal), kept as the cross-check.  Returns {'prediction': [1], 'kl_loss': [1] | None, 'tokens'}."""
         assert self.use_cids and self.backend == "tc", "the objective is built for the token model on the tensor-core back end"
         B, L = images.shape[:2]
         R, C = self.R, self.C
@@ -1023,10 +1067,17 @@ class SamplerEngine:
             z = eps.contiguous().float() if test_flag else z.view(B, 64, R, R)
             kl = ops.scaled_sum(kl_rows, -0.5 / B)                                       # mage_model.py:625
         M = B * R * R
-        trace = {"force_tokens": tok[:, 1:].contiguous(), "ce_rows": torch.empty(L - 1, M, device=self.device, dtype=torch.float32),
-                 "keep_logits": False, "skip_decode": True}
-        self.generate(images[:, 0], text, speed, z, trace=trace)
-        pred = ops.scaled_sum(trace["ce_rows"], 1.0 / ((L - 1) * M))                    # F.cross_entropy's mean, :619
+        if incremental:
+            trace = {"force_tokens": tok[:, 1:].contiguous(), "ce_rows": torch.empty(L - 1, M, device=self.device, dtype=torch.float32),
+                     "keep_logits": False, "skip_decode": True}
+            self.generate(images[:, 0], text, speed, z, trace=trace)
+            ce_rows = trace["ce_rows"]
+        else:
+            tok0 = torch.empty(B, R * R, device=self.device, dtype=torch.int64)
+            anchor = self._motion_anchor(images[:, 0].contiguous(), text, speed, z if self.randomness else None, tok0, None)
+            ce_rows = self._teacher_forced_ce(tok, anchor)
+        self.last_ce_rows = ce_rows.view(L - 1, M)
+        pred = ops.scaled_sum(ce_rows, 1.0 / ((L - 1) * M))                             # F.cross_entropy's mean, :619
         ops.check_flag(self.device)
         return {"prediction": pred, "kl_loss": kl, "tokens": tok}
 

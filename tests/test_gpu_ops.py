@@ -461,7 +461,8 @@ def test_handles_are_independent():
     assert L.mage_ctx_create(99, ctypes.byref(h2)) != 0 and not h2.value   # no such device
 
 
-@pytest.mark.parametrize("M,pos0,n_pos,Lmax", [(64, 0, 5, 8), (33, 3, 4, 10), (16, 9, 23, 32), (8, 31, 1, 32)])
+@pytest.mark.parametrize("M,pos0,n_pos,Lmax", [(64, 0, 5, 8), (33, 3, 4, 10), (16, 9, 23, 32), (8, 31, 1, 32), (8, 0, 16, 16), (8, 0, 24, 24),
+                                               (8, 20, 4, 24)])  # 16 / 24: dynamic shared memory of exactly 48 KB next to the static part
 def test_temporal_attn_seq_equals_position_by_position(M, pos0, n_pos, Lmax):
     """mage_temporal_attn_seq_f32 (n_pos consecutive positions in one launch, the K/V prefix staged once) against n_pos calls of
     mage_temporal_attn_step_f32: same math order -> bit-identical attention output and cache contents."""

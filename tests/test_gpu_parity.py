@@ -416,6 +416,16 @@ def test_forward_loss_vs_reference_golden(name, backend):
             print(f"[parity] forward {name}: max |{k} - reference| = {err:.2e} (max |{k}| {np.abs(g[k]).max():.2f})")
             assert err <= 4e-5 * np.abs(g[k]).max()   # fp32 summation order through 12 convolutions of K = 13824 + GroupNorms
     assert ("val/kl_loss" in loss_dict) == bool(params["randomness"])
+    # the teacher-forced pass in full-sequence form (all L positions per GEMM: the default) against the sampling path's
+    # one-position-per-step pass fed the given tokens: the same arithmetic per row
+    eng = model.engine()
+    ce_full = eng.last_ce_rows.clone()
+    dev_batch = {k: v.to("cuda") for k, v in batch.items()}
+    inc = eng.forward_loss(dev_batch["images"], dev_batch["text"], dev_batch["speed"].float(), eps.to("cuda") if eps is not None else None,
+                           test_flag, incremental=True)
+    diff = (eng.last_ce_rows - ce_full).abs().max().item()
+    print(f"[parity] forward {name}: per-row cross-entropy, full-sequence vs incremental pass: max |diff| {diff:.2e}")
+    assert diff <= 2e-5 and abs(inc["prediction"].item() - loss_dict["val/prediction"]) <= 1e-6 * loss_dict["val/prediction"]
     # training mode is refused loudly (dropout / gradients are not built), and so is a model without the posterior tensors
     with pytest.raises(NotImplementedError):
         model.train()({k: v.to("cuda") for k, v in batch.items()})
