@@ -906,9 +906,7 @@ class SamplerEngine:
         add up to the machine, so neither sequence ever waits for the other's CTAs); frames that do not fit beside the chain are
         decoded afterwards at full width.  MAGE_SIDE_SMS (D; 0 = off), MAGE_SIDE_FRAMES, MAGE_SIDE_GROUP override the plan."""
         D = self.side_sms
-        if D < 0:   # automatic
-            D = 0
-        if D <= 0 or D >= self.n_sms:
+        if D <= 0 or D >= self.n_sms:   # off by default: measured slower (profiles/r02ab_side_by_side_decoder_ab.txt)
             return None
         n_side = self.side_frames if self.side_frames > 0 else (self.L - 1) // 3
         n_side = max(0, min(n_side, self.L - 1))
