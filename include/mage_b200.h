@@ -67,6 +67,9 @@ int mage_pdl(mage_ctx* ctx, int enable);
  * add up to the SM count then run side by side without ever waiting for each other's CTAs to retire -- the VQ-VAE decoder next
  * to the latency-bound decode steps of a small batch.  Tiles are independent, so the share cannot change a bit of any result. */
 int mage_sm_share(mage_ctx* ctx, int sms);
+/* mage_temporal_attn_step_f32 as one short-lived CTA per (location, head half) (default) or as a persistent kernel with a ring of
+ * staging slots (MAGE_TATTN_RING=1; measured 1.2-1.4 % slower per generate): same arithmetic per unit, same bits. */
+int mage_temporal_attn_ring(mage_ctx* ctx, int enable);
 
 /* C[M,N] = act(relu_a?(A)[M,K] . W[N,K]^T + bias[N]) + residual
  * residual row for output row m is (res_mod > 0 ? m % res_mod : m), leading dim ldr; may alias C.

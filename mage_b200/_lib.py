@@ -28,6 +28,7 @@ SIGNATURES = {
     "mage_launch_count": [_c_f],
     "mage_pdl": [_c_f] + [_i],
     "mage_sm_share": [_c_f] + [_i],
+    "mage_temporal_attn_ring": [_c_f] + [_i],
     "mage_gemm_f32": [_c_f, _c_f, _i64, _c_f, _i64, _c_f, _c_f, _i64, _i, _c_f, _i64, _i, _i, _i, _i, _i, _c_f],
     "mage_conv2d_nhwc_f32": [_c_f] + [_c_f] * 5 + [_i] * 22 + [_i64, _c_f],
     "mage_tc_tuning": [_c_f] + [_i, _i],

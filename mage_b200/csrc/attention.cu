@@ -323,6 +323,112 @@ __global__ void __launch_bounds__(256) temporal_attn_kernel(const float* __restr
 
 
 // ---------------------------------------------------------------------------------------------
+// The same step as a PERSISTENT kernel with a ring of staging slots.  The one-shot form above launches M*2 short-lived CTAs whose
+// life is a chain of latencies (launch, barrier set-up, the q/k/v row, the bulk copies): ~130 us for 32768 CTAs at position 0
+// whatever the traffic, 68 % of the copy bandwidth at 8 prompts.  Here a few CTAs per SM each walk over units (location, head
+// half) with NS slots in flight: slot = this unit's q row, K[0..pos] and V[0..pos] (prefix by bulk copy from the cache, the new
+// k / v rows by bulk copy from qkv straight into row `pos`), one mbarrier per slot; after a unit's math the block syncs and one
+// thread refills the slot with the unit NS ahead.  The math per unit is the one-shot kernel's, statement for statement, so the
+// two forms give the same bits (tests compare them).
+// MEASURED (profiles/r02ai_temporal_attn_ring_ab.txt, same box, three repetitions): the ring form is 1.2-1.4 % SLOWER per generate
+// at 8, 16 and 64 prompts -- thousands of small resident CTAs already keep more copies in flight than a ring per CTA does, and the
+// block-wide hand-over per unit costs more than the CTA launches it saves.  OFF by default (MAGE_TATTN_RING=1 / mage_temporal_attn_ring).
+// ---------------------------------------------------------------------------------------------
+constexpr int TA_MAX_SLOTS = 8;
+
+__global__ void __launch_bounds__(256, 4) temporal_attn_ring_kernel(const float* __restrict__ qkv, float* __restrict__ kcache,
+                                                                 float* __restrict__ vcache, float* __restrict__ out,
+                                                                 __half* __restrict__ split, int64_t split_plane, int* flag,
+                                                                 int pos, int Lmax, float scale, int units, int ns) {
+  pdl_launch_dependents();
+  extern __shared__ __align__(128) float smem[];
+  __shared__ __align__(8) uint64_t bars[TA_MAX_SLOTS];
+  const int S = pos + 1;
+  const int slot_floats = (2 * S + 1) * TA_HALF;          // q | K[0..pos] | V[0..pos]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  auto fill = [&](int slot, int u) {                       // one thread: everything unit u needs, tracked by the slot's barrier
+    const int m = u >> 1, half = u & 1;
+    float* base = smem + (size_t)slot * slot_floats;
+    float* Ks = base + TA_HALF;
+    float* Vs = Ks + (size_t)S * TA_HALF;
+    const float* row = qkv + (int64_t)m * 3 * TA_C + half * TA_HALF;
+    const float* kc = kcache + ((int64_t)m * 2 + half) * Lmax * TA_HALF;
+    const float* vc = vcache + ((int64_t)m * 2 + half) * Lmax * TA_HALF;
+    const uint32_t prefix = (uint32_t)pos * TA_HALF * 4;
+    mbar_expect_tx(&bars[slot], 2 * prefix + 3 * TA_HALF * 4);
+    bulk_g2s(base, row, TA_HALF * 4, &bars[slot]);
+    bulk_g2s(Ks + (size_t)pos * TA_HALF, row + TA_C, TA_HALF * 4, &bars[slot]);
+    bulk_g2s(Vs + (size_t)pos * TA_HALF, row + 2 * TA_C, TA_HALF * 4, &bars[slot]);
+    if (pos > 0) {
+      bulk_g2s(Ks, kc, prefix, &bars[slot]);
+      bulk_g2s(Vs, vc, prefix, &bars[slot]);
+    }
+  };
+
+  if (tid == 0) {
+    for (int i = 0; i < ns; ++i) mbar_init(&bars[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  pdl_wait();   // the preceding grid (this step's QKV GEMM) has completed before anything global is touched
+  __syncthreads();
+  if (tid == 0) {
+    for (int i = 0; i < ns; ++i) {
+      const int u = blockIdx.x + i * gridDim.x;
+      if (u < units) fill(i, u);
+    }
+  }
+  int it = 0;
+  for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+    const int slot = it % ns;
+    mbar_wait(&bars[slot], (it / ns) & 1);
+    const int m = u >> 1, half = u & 1;
+    const float* qs = smem + (size_t)slot * slot_floats;
+    const float* Ks = qs + TA_HALF;
+    const float* Vs = Ks + (size_t)S * TA_HALF;
+    {   // this position's k, v join the cache for the later steps
+      float* kc = kcache + ((int64_t)m * 2 + half) * Lmax * TA_HALF;
+      float* vc = vcache + ((int64_t)m * 2 + half) * Lmax * TA_HALF;
+      kc[(int64_t)pos * TA_HALF + tid] = Ks[(size_t)pos * TA_HALF + tid];
+      vc[(int64_t)pos * TA_HALF + tid] = Vs[(size_t)pos * TA_HALF + tid];
+    }
+    const float* qh = qs + warp * 32;
+    float s[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int j = lane + t * 32;
+      s[t] = -INFINITY;
+      if (j < S) {
+        const float* kr = Ks + (size_t)j * TA_HALF + warp * 32;
+        float d = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int dd = (i + lane) & 31;  // skew: lane j starts at dim j -> distinct banks
+          d = fmaf(qh[dd], kr[dd], d);
+        }
+        s[t] = d * scale;
+      }
+    }
+    const float mx = warp_max(fmaxf(s[0], s[1]));
+    const float p0 = (lane < S) ? expf(s[0] - mx) : 0.f;
+    const float p1 = (lane + 32 < S) ? expf(s[1] - mx) : 0.f;
+    const float inv = 1.f / warp_sum(p0 + p1);
+    float o = 0.f;
+    for (int j = 0; j < S; ++j) {
+      const float pj = __shfl_sync(0xffffffffu, j < 32 ? p0 : p1, j & 31);
+      o = fmaf(pj, Vs[(size_t)j * TA_HALF + warp * 32 + lane], o);
+    }
+    store_attn(out, split, split_plane, flag, (int64_t)m * TA_C + half * TA_HALF + tid, o * inv);
+    __syncthreads();   // every thread is done with the slot
+    if (tid == 0) {
+      const int un = u + ns * gridDim.x;
+      if (un < units) fill(slot, un);
+    }
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
 // Temporal attention over SEVERAL consecutive positions at once (the full-sequence form of the MAGE+ suffix re-evaluation):
 // the queries of positions pos0 .. pos0+n_pos-1 of one (location, head-half) share one K/V prefix, so it is staged ONCE --
 // cached positions 0..pos0-1 by bulk copy, the n_pos new k,v rows from qkv (also appended to the cache) -- and every query
@@ -448,6 +554,37 @@ extern "C" int mage_temporal_attn_step_f32(mage_ctx* ctx, const float* qkv, floa
   MAGE_CHECK_CTX(ctx);
   MAGE_CHECK_ARG(M > 0 && pos >= 0 && pos < Lmax && Lmax <= 64);
   MAGE_CHECK_ARG(aligned16(qkv) && aligned16(kcache) && aligned16(vcache) && aligned16(out) && (out || out_split));
+  // ring form: NS slots of (q | K[0..pos] | V[0..pos]) per CTA -- about 96 KB in flight per CTA, at least two slots -- and as many
+  // CTAs per SM as fit (occupancy calculator); the grid never exceeds the units.  Very long clips (two slots > 220 KB) keep the
+  // one-shot form.
+  const size_t ring_slot = (size_t)(2 * (pos + 1) + 1) * TA_HALF * sizeof(float);
+  int ns = (int)((size_t)96 * 1024 / ring_slot);
+  ns = ns < 2 ? 2 : (ns > TA_MAX_SLOTS ? TA_MAX_SLOTS : ns);
+  if (ctx->tattn_ring && (size_t)ns * ring_slot <= (size_t)220 * 1024) {
+    const size_t smem = (size_t)ns * ring_slot;
+    size_t smem_max = (size_t)2 * (2 * Lmax + 1) * TA_HALF * sizeof(float);      // two slots at the last position
+    if (smem_max < (size_t)96 * 1024) smem_max = (size_t)96 * 1024;
+    if (smem_max > (size_t)220 * 1024) smem_max = (size_t)220 * 1024;
+    const void* fn = reinterpret_cast<const void*>(&temporal_attn_ring_kernel);
+    int k = ctx->find(fn);
+    if (k < 0 || ctx->cfg_smem[k] < smem_max) {
+      cudaError_t e = cudaFuncSetAttribute(temporal_attn_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+      if (e != cudaSuccess) return (int)e;
+      if (k < 0) k = ctx->add(fn, 0, smem_max);
+      if (k >= 0) ctx->cfg_smem[k] = smem_max;
+    }
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, temporal_attn_ring_kernel, 256, smem) != cudaSuccess || per_sm < 1) {
+      (void)cudaGetLastError();
+      per_sm = 1;
+    }
+    const int units = M * 2;
+    int64_t grid = (int64_t)ctx->sms * per_sm;
+    if (grid > units) grid = units;
+    mage_launch_pdl(ctx, temporal_attn_ring_kernel, (unsigned)grid, 256, smem, as_stream(stream), 1, qkv, kcache, vcache, out,
+                    reinterpret_cast<__half*>(out_split), split_plane, flag, pos, Lmax, scale, units, ns);
+    return mage_post_launch(ctx);
+  }
   const size_t smem = (size_t)2 * (pos + 1) * TA_HALF * sizeof(float);
   const size_t smem_max = (size_t)2 * Lmax * TA_HALF * sizeof(float);
   if (smem_max > 40 * 1024) {   // opt in early: static shared memory counts against the 48 KB default too.  Per-device attribute: remembered in the handle

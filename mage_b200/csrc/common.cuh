@@ -18,6 +18,7 @@ struct mage_ctx {
   int small = 1;                         // one-tile cost model for sub-2-wave GEMMs (MAGE_TC_SMALL)
   int resident = 1;                      // resident weight slots in the halo convolution when they fit (MAGE_TC_RESIDENT)
   int pdl = 1;                           // mage_pdl
+  int tattn_ring = 0;                    // temporal attention step as the persistent ring kernel (MAGE_TATTN_RING; 0 = one CTA per unit)
   int sm_share = 0;                      // mage_sm_share: persistent kernels use at most this many SMs (0 = all of them)
   int eff_sms() const { return sm_share > 0 && sm_share < sms ? sm_share : sms; }
   int64_t launches = 0;

@@ -33,6 +33,7 @@ extern "C" int mage_ctx_create(int device, mage_ctx** out) {
   c->halo = env("MAGE_TC_HALO", 1);
   c->small = env("MAGE_TC_SMALL", 1);
   c->resident = env("MAGE_TC_RESIDENT", 1);
+  c->tattn_ring = env("MAGE_TATTN_RING", 0);
   *out = c;
   return 0;
 }
@@ -42,6 +43,11 @@ extern "C" int mage_ctx_destroy(mage_ctx* ctx) {
 }
 extern "C" int mage_ctx_device(mage_ctx* ctx) { return ctx ? ctx->device : MAGE_EINVAL; }
 extern "C" int64_t mage_launch_count(mage_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int mage_temporal_attn_ring(mage_ctx* ctx, int enable) {
+  MAGE_CHECK_CTX(ctx);
+  ctx->tattn_ring = enable != 0;
+  return 0;
+}
 extern "C" int mage_sm_share(mage_ctx* ctx, int sms) {
   MAGE_CHECK_CTX(ctx);
   MAGE_CHECK_ARG(sms >= 0);

@@ -118,6 +118,11 @@ def pdl(enable: bool) -> None:
     check(_lib.lib().mage_pdl(_ctx(), int(enable)), "mage_pdl")
 
 
+def temporal_attn_ring(enable: bool) -> None:
+    """temporal_attn_step as the persistent ring kernel, or (default) one CTA per unit (see mage_b200.h); same bits."""
+    check(_lib.lib().mage_temporal_attn_ring(_ctx(), int(enable)), "mage_temporal_attn_ring")
+
+
 def sm_share(sms: int = 0) -> None:
     """The launches that follow size their persistent kernels for at most `sms` SMs (0 = the whole GPU): mage_b200.h."""
     check(_lib.lib().mage_sm_share(_ctx(), int(sms)), "mage_sm_share")

@@ -434,6 +434,38 @@ def test_conv3d_as_one_implicit_gemm_over_frame_triples():
     ops.check_flag(DEV)
 
 
+@pytest.mark.parametrize("M,pos,Lmax", [(3000, 0, 32), (3000, 1, 32), (2500, 5, 32), (700, 15, 32), (700, 31, 32), (64, 3, 8), (300, 23, 24),
+                                        (37, 0, 16), (40, 60, 64)])
+def test_temporal_attn_ring_kernel_equals_one_cta_per_unit(M, pos, Lmax):
+    """The temporal attention step as a persistent kernel with a ring of staging slots (optional) against the one-CTA-per-unit form:
+    same arithmetic per (location, head half), so attention output (fp32 and split) and the appended K/V rows are bit-identical --
+    with more units than resident CTAs x slots (the ring wraps), fewer units than CTAs, every slot count, and the clip length at
+    which two slots no longer fit (one-shot form takes over)."""
+    ops = _ops()
+    C = 512
+    g = torch.Generator().manual_seed(21)
+    qkv = torch.randn(M, 3 * C, generator=g).to(DEV)
+    kc0 = torch.randn(M, Lmax, C, generator=g).to(DEV)
+    vc0 = torch.randn(M, Lmax, C, generator=g).to(DEV)
+    res = []
+    try:
+        for ring in (True, False):
+            ops.temporal_attn_ring(ring)
+            kc, vc = kc0.clone(), vc0.clone()
+            out = torch.full((M, C), float("nan"), device=DEV)
+            sp = torch.zeros(2, M, C, device=DEV, dtype=torch.float16)
+            ops.temporal_attn_step(qkv, kc, vc, out, pos, 32 ** -0.5, out_split=sp)
+            torch.cuda.synchronize()
+            res.append((out, sp, kc, vc))
+    finally:
+        ops.temporal_attn_ring(False)   # the default
+    for a, b in zip(*res):
+        assert torch.equal(a.view(torch.int32) if a.dtype == torch.float32 else a.view(torch.int16),
+                           b.view(torch.int32) if b.dtype == torch.float32 else b.view(torch.int16))
+    assert torch.isfinite(res[0][0]).all()
+    ops.check_flag(DEV)
+
+
 def test_handles_are_independent():
     """all library state lives in the opaque handle.  A second handle on the same device has its own launch
     counter and tuning switches; using it does not disturb the handle the package works through."""
