@@ -50,3 +50,29 @@ def test_product_never_imports_the_oracle():
             if re.match(r"\s*(from|import)\s+oracle\b", ln) or "oracle/_ref" in ln or "ref_shims" in ln:
                 bad.append((f, ln.strip()))
     assert not bad, bad
+
+
+def test_header_is_plain_c_and_a_c_program_can_bind_it(tmp_path):
+    """include/mage_b200.h is the boundary a maintainer binds from any language: it must parse as strict C99 (no torch / CUDA types)
+    and as C++, and a C program that takes the address of every declared entry point must link against the library."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        import pytest
+        pytest.skip("no gcc")
+    hdr = os.path.join(ROOT, "include", "mage_b200.h")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr], check=True)
+    subprocess.run(["g++", "-std=c++11", "-Werror", "-fsyntax-only", "-x", "c++", hdr], check=True)
+    if not os.path.isfile(_lib.LIB_PATH):
+        _lib.build()
+    src = tmp_path / "bind.c"
+    names = _declared()
+    src.write_text('#include "mage_b200.h"\n#include <stdio.h>\nint main(void) {\n  const void* f[] = {'
+                   + ", ".join(f"(const void*){n}" for n in names)
+                   + '};\n  printf("%d %d\\n", (int)(sizeof f / sizeof f[0]), mage_abi_version());\n  return 0;\n}\n')
+    exe = tmp_path / "bind"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wno-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L", libdir,
+                    "-l:" + os.path.basename(_lib.LIB_PATH), "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert int(out[0]) == len(names) and int(out[1]) == _lib.ABI_VERSION
