@@ -316,3 +316,25 @@ def test_pid_control_follows_the_reference():
         mm, _ = ref_shims.load_reference()
         ref = mm.PIDControl()
         assert [ref.pid(5.0, kl) for kl in seq] == got
+
+
+def test_conv3d_equals_a_conv2d_over_frame_triples_on_the_cpu():
+    """Host logic of the video posterior (engine._frame_triples + the kernel reordering of engine._posterior_weights): a Conv3d
+    3x3x3 with padding 1 and temporal stride 1 or 2 is a 3x3 Conv2d over the frame triples laid side by side on the channel axis.
+    Pure torch, so it is checked here on the CPU against F.conv3d (the GPU test repeats it through the tensor-core kernel)."""
+    import torch.nn.functional as F
+
+    from mage_b200.engine import SamplerEngine
+    g = torch.Generator().manual_seed(3)
+    B, R, Cin, Cout = 2, 6, 8, 5
+    for T, stride_t in ((5, 2), (4, 2), (2, 2), (1, 2), (3, 1), (1, 1)):
+        x = torch.randn(T, B, R, R, Cin, generator=g, dtype=torch.float64)
+        w = torch.randn(Cout, Cin, 3, 3, 3, generator=g, dtype=torch.float64)
+        want = F.conv3d(x.permute(1, 4, 0, 2, 3), w, None, stride=(stride_t, 1, 1), padding=1)            # [B,Cout,T',R,R]
+        xt = SamplerEngine._frame_triples(x, stride_t)                                                      # [T',B,R,R,3Cin]
+        To = xt.shape[0]
+        assert To == want.shape[2]
+        w2 = w.permute(0, 3, 4, 2, 1).reshape(Cout, 3, 3, 3 * Cin).permute(0, 3, 1, 2)                     # [Cout, 3Cin, ky, kx]
+        got = F.conv2d(xt.reshape(To * B, R, R, 3 * Cin).permute(0, 3, 1, 2), w2, None, padding=1)           # [T'*B, Cout, R, R]
+        got = got.view(To, B, Cout, R, R).permute(1, 2, 0, 3, 4)
+        assert torch.allclose(got, want, rtol=1e-12, atol=1e-12), (T, stride_t)
