@@ -338,6 +338,8 @@ int mage_cross_entropy_rows_f32(mage_ctx* ctx, const float* logits, int64_t ld, 
 int mage_reparam_kl_f32(mage_ctx* ctx, const float* mu_logvar, const float* eps, float* z, float* kl_rows, int B, int HW, int Cz,
                         void* stream);
 int mage_scaled_sum_f32(mage_ctx* ctx, const float* x, float* out, int64_t n, double scale, void* stream);
+/* out[0] = scale * sum((a[i] - b[i])^2): F.mse_loss of the MAGE+ objective (mage_model.py:621), same reduction scheme. */
+int mage_scaled_sqdiff_sum_f32(mage_ctx* ctx, const float* a, const float* b, float* out, int64_t n, double scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -68,6 +68,7 @@ SIGNATURES = {
     "mage_cross_entropy_rows_f32": [_c_f, _c_f, _i64, _c_f, _c_f, _i, _i, _c_f, _c_f],
     "mage_reparam_kl_f32": [_c_f] + [_c_f] * 4 + [_i] * 3 + [_c_f],
     "mage_scaled_sum_f32": [_c_f, _c_f, _c_f, _i64, ctypes.c_double, _c_f],
+    "mage_scaled_sqdiff_sum_f32": [_c_f, _c_f, _c_f, _c_f, _i64, ctypes.c_double, _c_f],
 }
 
 

@@ -136,6 +136,24 @@ __global__ void __launch_bounds__(1024) scaled_sum_kernel(const float* __restric
   if (threadIdx.x == 0) out[0] = (float)(red[0] * scale);
 }
 
+// out[0] = scale * sum((a[i] - b[i])^2): F.mse_loss's reduction, one block, double accumulation, fixed order.
+__global__ void __launch_bounds__(1024) scaled_sqdiff_sum_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                                 float* __restrict__ out, int64_t n, double scale) {
+  __shared__ double red[1024];
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += 1024) {
+    const float d = a[i] - b[i];
+    acc += (double)(d * d);
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = (float)(red[0] * scale);
+}
+
 }  // namespace
 
 extern "C" int mage_gn_apply_f32(mage_ctx* ctx, const float* x, const double* part, float* stat, const float* gamma, const float* beta,
@@ -170,6 +188,13 @@ extern "C" int mage_reparam_kl_f32(mage_ctx* ctx, const float* mu_logvar, const 
   MAGE_CHECK_CTX(ctx);
   MAGE_CHECK_ARG(B > 0 && HW > 0 && Cz > 0 && mu_logvar && kl_rows && (z == nullptr || eps != nullptr));
   reparam_kl_kernel<<<B, 256, 0, as_stream(stream)>>>(mu_logvar, eps, z, kl_rows, HW, Cz);
+  return mage_post_launch(ctx);
+}
+
+extern "C" int mage_scaled_sqdiff_sum_f32(mage_ctx* ctx, const float* a, const float* b, float* out, int64_t n, double scale, void* stream) {
+  MAGE_CHECK_CTX(ctx);
+  MAGE_CHECK_ARG(n > 0 && a && b && out);
+  scaled_sqdiff_sum_kernel<<<1, 1024, 0, as_stream(stream)>>>(a, b, out, n, scale);
   return mage_post_launch(ctx);
 }
 

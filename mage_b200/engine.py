@@ -1029,6 +1029,81 @@ class SamplerEngine:
         ce = torch.empty((L - 1) * M, device=dev, dtype=torch.float32)
         return ops.cross_entropy_rows(logits, tok_t[1:].reshape(-1), ce)
 
+    def _posterior_sample(self, x: torch.Tensor, eps: torch.Tensor, test_flag: bool):
+        """mage_model.py:605-611, 624-625: raw embeddings of all frames x fp32 [L,B,R,R,C] (frame-major) -> four BasicBlocks (each
+        halves the frame axis) -> (mu | logvar) -> (z = eps * exp(logvar/2) + mu, or eps itself with test_flag, as [B,64,R,R];
+        KL = -0.5 * mean_b sum(1 + logvar - mu^2 - exp(logvar)) as a device scalar)."""
+        L, B = x.shape[:2]
+        R, C = self.R, self.C
+        assert eps is not None and tuple(eps.shape) == (B, 64, R, R)
+        for i in range(4):
+            p = f"conv3d.{i}"
+            xt = self._frame_triples(x, 2)
+            res = self._conv3d_gn(xt, f"{i}.downsample.0", p + ".downsample.1", B, relu=False)
+            y = self._conv3d_gn(xt, f"{i}.conv1", p + ".bn1", B, relu=True)
+            x = self._conv3d_gn(self._frame_triples(y, 1), f"{i}.conv2", p + ".bn2", B, relu=True, residual=res)
+        if x.shape[0] != 1:
+            raise ValueError(f"frames_length {L} leaves {x.shape[0]} frames after the posterior's four temporal halvings; the "
+                             "reference squeezes that axis (mage_model.py:606) and fails as well")
+        pw = self._posterior_weights()
+        ml, _, _ = ops.conv2d_tc(ops.split(x.view(B, R, R, C)), pw["mu_logvar"], pw["mu_logvar.bias"], pad=(1, 1))
+        self.last_mu_logvar = ml.view(B * R * R, -1)                                   # [B*R*R, mu(64) | logvar(64)] (tests)
+        z, kl_rows = ops.reparam_kl(ml.view(B * R * R, -1), eps.contiguous().float(), B, R * R)
+        z = eps.contiguous().float() if test_flag else z.view(B, 64, R, R)
+        return z, ops.scaled_sum(kl_rows, -0.5 / B)                                    # mage_model.py:625
+
+    def forward_loss_continuous(self, latents: torch.Tensor, text: torch.Tensor, speed: Optional[torch.Tensor],
+                                eps: Optional[torch.Tensor], test_flag: bool = False) -> dict:
+        """MAGE.forward for use_cids=False (MAGE+; mage_model.py:575-639 with :583, :621) in eval mode: latents fp32 [B,L,c,R,R] of
+        ALL frames (the first stage's output, whatever module produced it) -> Linear embed -> [posterior, AdaIN] -> teacher-forced
+        decoder in full-sequence form -> GroupNorm(32) over all slots -> SiLU -> 1x1x1 conv -> MSE against the latents of frames
+        1..L-1.  Returns {'prediction': [1], 'kl_loss': [1] | None}."""
+        assert not self.use_cids and self.backend == "tc", "the MAGE+ objective runs on the tensor-core back end"
+        sd, ws, C, R, L = self.sd, self.ws, self.C, self.R, self.L
+        p = "generate_model."
+        B, Lz, c = latents.shape[:3]
+        assert Lz == L, f"MAGE.forward needs frames_length = {L} frames, got {Lz}"
+        M = B * R * R
+        dev = self.device
+        T = text.shape[1]
+        # Linear embed of every frame's latents, frame-major rows (frame, b, h, w)
+        z_rows = latents.permute(1, 0, 3, 4, 2).reshape(L * M, c).contiguous().float()
+        emb = ops.gemm(z_rows, self.E, sd["visual_token_embedding.bias"])                # K = c = 4: FFMA kernel
+        # 3x3 conv + H/W positions of frames 0..L-2 (the decoder's inputs), all frames as one batch of images
+        prior, prior_split, _ = ops.conv2d_tc(ops.split(emb[:(L - 1) * M]).view(2, (L - 1) * B, R, R, C), ws["Wc"], None, pad=(1, 1),
+                                              residual=self.posHW, res_mode=3, want=("f32", "split"))
+        prior, prior_split = prior.view((L - 1) * M, C), prior_split.view(2, (L - 1) * M, C)
+        temb, _ = self._text_encoder(text)
+        anchor = self._ma_encoder_tc(prior[:M], prior_split[:, :M], temb, B, T).view(B, R, R, C)
+        kl = None
+        if self.randomness:
+            z, kl = self._posterior_sample(emb.view(L, B, R, R, C), eps, test_flag)
+            anchor = self._adain_tc(anchor, z, B)
+        if speed is not None:
+            ops.add_scaled_vec(anchor, speed, sd["speed_embedding"].view(-1))
+        x = torch.empty(L * M, C, device=dev, dtype=torch.float32)
+        ops.gemm_tc(ops.split(anchor.view(M, C)), ws[p + "context_linear.weight"], self.bias_ctx0, out=x[:M])
+        for j in range(L - 1):
+            ops.gemm_tc(prior_split[:, j * M:(j + 1) * M], ws[p + "in_linear.weight"], self.bias_in_T[j + 1], out=x[(j + 1) * M:(j + 2) * M])
+        caches = {i: (torch.empty(M, L, C, device=dev, dtype=torch.float32), torch.empty(M, L, C, device=dev, dtype=torch.float32))
+                  for i in range(self.n_blocks) if i % 3 == 0}
+        u = torch.empty(2, L * M, C, device=dev, dtype=torch.float16)
+        h = torch.empty(2, L * M, 4 * C, device=dev, dtype=torch.float16)
+        qkv = torch.empty(L * M, 3 * C, device=dev, dtype=torch.float32)
+        for i in range(self.n_blocks):
+            self._block_seq_tc(i, x, 0, L, B, caches, u, h, qkv)
+        del u, h, qkv
+        hidden = x[M:]                                                                   # slots 0..L-2 = positions 1..L-1
+        part = torch.empty(L - 1, B, 32, 2, device=dev, dtype=torch.float64)
+        ops.gn_partial(hidden, part, B, R * R)
+        Wo = sd[p + "out.2.weight"].reshape(sd[p + "out.2.weight"].shape[0], C).contiguous()
+        pred = ops.gn_silu_head(hidden, part, sd[p + "out.0.weight"], sd[p + "out.0.bias"], Wo, sd[p + "out.2.bias"], B, R * R)
+        self.last_prediction = pred.view(L - 1, B, R, R, -1)
+        target = z_rows[M:]                                                              # rows (frame 1.., b, h, w) x c
+        mse = ops.scaled_sqdiff_sum(pred, target, 1.0 / pred.numel())                    # F.mse_loss, :621
+        ops.check_flag(dev)
+        return {"prediction": mse, "kl_loss": kl}
+
     def forward_loss(self, images: torch.Tensor, text: torch.Tensor, speed: Optional[torch.Tensor], eps: Optional[torch.Tensor],
                      test_flag: bool = False, incremental: bool = False) -> dict:
         """MAGE.forward in eval mode (mage_model.py:575-639), the loss terms as device scalars: images [B,L,C,H,W] (all
@@ -1046,24 +1121,9 @@ class SamplerEngine:
         kl = None
         z = None
         if self.randomness:
-            assert eps is not None and tuple(eps.shape) == (B, 64, R, R)
             # raw token embeddings of ALL frames, frame-major [L,B,R,R,C] (mage_model.py:581,605)
             x = ops.embedding(tok.permute(1, 0, 2, 3).reshape(-1), self.sd["visual_token_embedding.weight"]).view(L, B, R, R, C)
-            for i in range(4):
-                p = f"conv3d.{i}"
-                xt = self._frame_triples(x, 2)
-                res = self._conv3d_gn(xt, f"{i}.downsample.0", p + ".downsample.1", B, relu=False)
-                y = self._conv3d_gn(xt, f"{i}.conv1", p + ".bn1", B, relu=True)
-                x = self._conv3d_gn(self._frame_triples(y, 1), f"{i}.conv2", p + ".bn2", B, relu=True, residual=res)
-            if x.shape[0] != 1:
-                raise ValueError(f"frames_length {L} leaves {x.shape[0]} frames after the posterior's four temporal halvings; the "
-                                 "reference squeezes that axis (mage_model.py:606) and fails as well")
-            pw = self._posterior_weights()
-            ml, _, _ = ops.conv2d_tc(ops.split(x.view(B, R, R, C)), pw["mu_logvar"], pw["mu_logvar.bias"], pad=(1, 1))
-            self.last_mu_logvar = ml.view(B * R * R, -1)                               # [B*R*R, mu(64) | logvar(64)] (tests)
-            z, kl_rows = ops.reparam_kl(ml.view(B * R * R, -1), eps.contiguous().float(), B, R * R)
-            z = eps.contiguous().float() if test_flag else z.view(B, 64, R, R)
-            kl = ops.scaled_sum(kl_rows, -0.5 / B)                                       # mage_model.py:625
+            z, kl = self._posterior_sample(x, eps, test_flag)
         M = B * R * R
         if incremental:
             trace = {"force_tokens": tok[:, 1:].contiguous(), "ce_rows": torch.empty(L - 1, M, device=self.device, dtype=torch.float32),

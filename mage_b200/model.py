@@ -409,8 +409,6 @@ class MAGE(_EngineOwner):
         if self.training:
             raise NotImplementedError("MAGE.forward is built for eval mode (validation loss); training mode -- dropout, gradients, the "
                                       "optimiser step of main_mage.py:127-152 -- is not part of this library: call .eval()")
-        if not self.use_cids:
-            raise NotImplementedError("MAGE.forward is built for the token model (use_cids=True)")
         eng = self.engine()
         dev = eng.device
         images = batch["images"].to(dev, non_blocking=True)
@@ -424,8 +422,12 @@ class MAGE(_EngineOwner):
             if eps is None:
                 eps = torch.randn(B, 64, self.image_resolution, self.image_resolution, device=dev)
             eps = eps.to(dev).float().contiguous()
-        out = eng.forward_loss(images, text, speed, eps if self.randomness else None, bool(test_flag))
-        self.last_tokens_all = out["tokens"]
+        if self.use_cids:
+            out = eng.forward_loss(images, text, speed, eps if self.randomness else None, bool(test_flag))
+            self.last_tokens_all = out["tokens"]
+        else:   # MAGE+: the first stage (a plain torch module, run as given) encodes every frame, mage_model.py:579
+            latents = self.first_stage_encode(images).float().contiguous()
+            out = eng.forward_loss_continuous(latents, text, speed, eps if self.randomness else None, bool(test_flag))
         prefix = "val"   # `'train' if self.training else 'val'` (:601); training mode is refused above
         recon = out["prediction"].reshape(())
         loss_dict = {f"{prefix}/prediction": recon.item()}

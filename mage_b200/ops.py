@@ -200,7 +200,9 @@ def gemm_tc(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = Non
     """Tensor-core GEMM on split operands: a [2,M,K], w [2,N,K] -> act(a @ w.T + bias) + residual.
     `want` lists the outputs to allocate when not passed: "f32", "split", "split_relu".
     Returns (out_f32, out_split, out_split_relu) with None for the ones not produced."""
-    _f16(a), _f16(w)
+    _f16(w)
+    # `a` may be a row range of a larger split tensor: each plane [M,K] dense, the lo plane a.stride(0) elements after the hi plane
+    assert a.dtype == torch.float16 and a.dim() == 3 and a.shape[0] == 2 and a[0].is_contiguous() and a.stride(0) % 8 == 0, (a.shape, a.stride())
     M, K = a.shape[1], a.shape[2]
     N = w.shape[1]
     assert w.shape[2] == K
@@ -216,7 +218,7 @@ def gemm_tc(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = Non
     if residual is not None:
         assert residual.dim() == 2 and residual.shape[1] == N and residual.stride(1) == 1
     with _Prof("gemm", 2.0 * M * N * K):
-        check(_lib.lib().mage_gemm_tc(_ctx(), _p(a), K, M * K, _p(w), K, N * K, _p(bias), _p(residual),
+        check(_lib.lib().mage_gemm_tc(_ctx(), _p(a), K, a.stride(0), _p(w), K, N * K, _p(bias), _p(residual),
                                       residual.stride(0) if residual is not None else 0, res_mod, _p(out), _p(out_split),
                                       _p(out_split_relu), N, M * N, M, N, K, act, _p(flag(dev)), _stream()), "mage_gemm_tc")
     return out, out_split, out_split_relu
@@ -590,6 +592,16 @@ def scaled_sum(x: torch.Tensor, scale: float) -> torch.Tensor:
     out = torch.empty(1, device=x.device, dtype=torch.float32)
     with _Prof("misc", 0.0):
         check(_lib.lib().mage_scaled_sum_f32(_ctx(), _p(_f32(x)), _p(out), x.numel(), float(scale), _stream()), "mage_scaled_sum_f32")
+    return out
+
+
+def scaled_sqdiff_sum(a: torch.Tensor, b: torch.Tensor, scale: float) -> torch.Tensor:
+    """scale * sum((a - b)^2) as a device scalar (F.mse_loss with scale = 1/numel): one block, fixed order, double accumulation."""
+    assert a.is_contiguous() and b.is_contiguous() and a.numel() == b.numel()
+    out = torch.empty(1, device=a.device, dtype=torch.float32)
+    with _Prof("misc", 0.0):
+        check(_lib.lib().mage_scaled_sqdiff_sum_f32(_ctx(), _p(_f32(a)), _p(_f32(b)), _p(out), a.numel(), float(scale), _stream()),
+              "mage_scaled_sqdiff_sum_f32")
     return out
 
 

@@ -509,24 +509,31 @@ def video_posterior(sd: SD, x_emb: torch.Tensor):
 
 @torch.no_grad()
 def forward_loss(sd: SD, batch: Dict[str, torch.Tensor], eps: Optional[torch.Tensor], *, randomness: bool = True,
-                 beta: float = 1.0, alpha: float = 0.0, test_flag: bool = False, trace: Optional[dict] = None) -> Dict[str, float]:
-    """MAGE.forward (mage_model.py:575-639), use_cids=True, eval mode (dropout off), fixed beta (auto_beta=False): the
-    teacher-forced full-sequence pass and its losses.  batch['images'] [B,L,C,H,W] (all L frames), 'text', optional 'speed';
-    `eps` [B,64,H,W] stands for the `torch.randn_like(logvar)` draw of reparameterize (:571) -- or, with test_flag, for the
-    `torch.randn_like(video_emb)` that replaces the posterior sample (:609-610).  Returns the reference's loss_dict values
-    (without the 'train/' / 'val/' prefix)."""
-    fsd = _sub(sd, "first_stage_model.")
+                 beta: float = 1.0, alpha: float = 0.0, test_flag: bool = False, trace: Optional[dict] = None,
+                 latents: Optional[torch.Tensor] = None, ma_ln: bool = False) -> Dict[str, float]:
+    """MAGE.forward (mage_model.py:575-639) in eval mode (dropout off) with a GIVEN beta: the teacher-forced full-sequence pass
+    and its losses.  batch['images'] [B,L,C,H,W] (all L frames), 'text', optional 'speed'; `eps` [B,64,H,W] stands for the
+    `torch.randn_like(logvar)` draw of reparameterize (:571) -- or, with test_flag, for the `torch.randn_like(video_emb)` that
+    replaces the posterior sample (:609-610).  use_cids=True (default): VQ tokens, cross-entropy (:619).  `latents` [B,L,c,h,w]
+    given = the MAGE+ branch (use_cids=False): the first stage's latents of all frames (whatever module produced them), Linear
+    embed, continuous head, MSE (:621); `ma_ln` = TransformerBlock line 93.  With auto_beta the caller obtains beta from PIDControl
+    and the L2 term is absent (:627-630): pass alpha=0.  Returns the reference's loss_dict values (without the prefix)."""
     imgs = batch["images"]
     B, L = imgs.shape[:2]
-    tok = vqvae_encode(fsd, imgs.reshape(-1, *imgs.shape[2:]))
-    tok = tok.view(B, L, *tok.shape[1:])
-    x_emb = embed_tokens(sd, tok)                                          # [B,L,C,H,W]
+    if latents is None:
+        fsd = _sub(sd, "first_stage_model.")
+        tok = vqvae_encode(fsd, imgs.reshape(-1, *imgs.shape[2:]))
+        tok = tok.view(B, L, *tok.shape[1:])
+        x_emb = embed_tokens(sd, tok)                                      # [B,L,C,H,W]
+    else:
+        tok = None
+        x_emb = embed_latents(sd, latents)
     prior = token_features(sd, x_emb[:, :L - 1])                           # [B,L-1,H,W,C]
     C = x_emb.shape[2]
     first = prior[:, 0].reshape(B, -1, C).permute(1, 0, 2).contiguous()
     t = text_encoder(sd, batch["text"]).permute(1, 0, 2).contiguous()
-    H, W = tok.shape[-2:]
-    a = ma_encoder(sd, first, t).permute(1, 0, 2).contiguous().view(B, H, W, C)
+    H, W = x_emb.shape[-2:]
+    a = (ma_encoder_ln if ma_ln else ma_encoder)(sd, first, t).permute(1, 0, 2).contiguous().view(B, H, W, C)
     out: Dict[str, float] = {}
     kl = None
     if randomness:
@@ -544,17 +551,23 @@ def forward_loss(sd: SD, batch: Dict[str, torch.Tensor], eps: Optional[torch.Ten
     if batch.get("speed") is not None:
         speed_emb = batch["speed"].view(B, 1) @ sd["speed_embedding"]
         a = a + speed_emb.unsqueeze(1).unsqueeze(1)
-    logits = flat_axial_decoder(sd, a, prior)                               # [B,L-1,H,W,K]
-    K = logits.shape[-1]
-    pred = F.cross_entropy(logits.reshape(-1, K), tok[:, 1:L].reshape(-1))
-    if trace is not None:
-        trace["tokens"], trace["logits"] = tok, logits
+    if latents is None:
+        logits = flat_axial_decoder(sd, a, prior)                           # [B,L-1,H,W,K]
+        K = logits.shape[-1]
+        pred = F.cross_entropy(logits.reshape(-1, K), tok[:, 1:L].reshape(-1))
+        if trace is not None:
+            trace["tokens"], trace["logits"] = tok, logits
+    else:
+        model_predict = flat_axial_decoder_continuous(sd, a, prior)         # [B,L-1,H,W,c]
+        pred = F.mse_loss(model_predict.permute(0, 1, 4, 2, 3).contiguous(), latents[:, 1:])
+        if trace is not None:
+            trace["prediction"] = model_predict
     out["prediction"] = float(pred)
     final = pred
     if randomness:
         out["kl_loss"] = float(kl)
         # mage_model.py:631-632 (auto_beta=False); the L2 term needs batch['speed'] in the reference too (speed_emb, :613)
-        l2 = torch.mean(torch.pow(torch.norm(speed_emb, dim=-1), 2)) if speed_emb is not None else torch.zeros(())
+        l2 = torch.mean(torch.pow(torch.norm(speed_emb, dim=-1), 2)) if (speed_emb is not None and alpha != 0.0) else torch.zeros(())
         final = pred + beta * kl + alpha * l2
     out["final_loss"] = float(final)
     return out

@@ -219,6 +219,53 @@ def make_forward_goldens():
         print(f"{name}: {time.time() - t0:.1f}s", {k: round(float(v), 6) for k, v in loss_dict.items()})
 
 
+# MAGE+ (use_cids=False) forward: (name, frames_length, batch, text_len, padded, eps seed, test_flag, line-93 edit, auto_beta, v_kl)
+FORWARD_PLUS_CASES = [
+    ("forward_plus_L4_b2", 4, 2, 12, False, 81, False, False, False, 0.0),
+    ("forward_plus_L10_b1_ln_pid", 10, 1, 20, False, 82, False, True, True, 100.0),   # the shipped mage+_cater*.yaml objective: PID beta
+    ("forward_plus_L8_b2_pad_testflag", 8, 2, 14, True, 83, True, True, False, 0.0),
+]
+
+
+def forward_plus_case_inputs(name):
+    _, L, B, T, padded, eps_seed, test_flag, edit, auto_beta, v_kl = next(c for c in FORWARD_PLUS_CASES if c[0] == name)
+    params = syn.model_params("caterv2plus", frames_length=L)
+    params = dict(params, auto_beta=auto_beta, v_kl=v_kl)
+    sd = syn.make_mage_state_dict(params, posterior=True)
+    batch = syn.make_batch(params, B, seed=4321, text_len=T, padded=padded, frames=L)
+    eps = syn.make_noise(B, res=params["image_resolution"], seed=eps_seed)
+    return params, sd, batch, eps, test_flag, edit
+
+
+def make_forward_plus_goldens():
+    """MAGE.forward of the unmodified reference (and of the reference with its documented line 92->93 edit) for use_cids=False in
+    eval mode, stand-in first stage, the reparameterisation draw replaced by a stored tensor: MSE / KL / [PID beta] / final loss."""
+    assert ref_shims.reference_available(), "needs /root/reference"
+    for case in FORWARD_PLUS_CASES:
+        name, L, B, T, padded, eps_seed, test_flag, edit, auto_beta, v_kl = case
+        params, sd, batch, eps, _, _ = forward_plus_case_inputs(name)
+        model = ref_shims.build_reference_mage(params, sd, mage_plus_edit=edit)
+        captured = {}
+        hooks = [model.conv_mu2.register_forward_hook(lambda m, i, o: captured.__setitem__("mu", o.detach())),
+                 model.conv_var2.register_forward_hook(lambda m, i, o: captured.__setitem__("logvar", o.detach()))]
+        real = torch.randn_like
+        torch.randn_like = lambda t, *a, **k: eps.clone().to(t.dtype) if tuple(t.shape) == tuple(eps.shape) else real(t, *a, **k)
+        t0 = time.time()
+        try:
+            with torch.no_grad():
+                loss, loss_dict = model({k: v.clone() for k, v in batch.items()}, test_flag=test_flag)
+        finally:
+            torch.randn_like = real
+            for h in hooks:
+                h.remove()
+        rec = dict(frames_length=L, batch=B, text_len=T, padded=padded, eps_seed=eps_seed, test_flag=test_flag, ma_ln=edit,
+                   auto_beta=auto_beta, v_kl=v_kl, final_loss=np.float64(float(loss)), prediction=np.float64(loss_dict["val/prediction"]),
+                   kl_loss=np.float64(loss_dict["val/kl_loss"]), beta=np.float64(loss_dict.get("val/beta", params["beta"])),
+                   mu=_np(captured["mu"]).astype(np.float32), logvar=_np(captured["logvar"]).astype(np.float32))
+        np.savez_compressed(os.path.join(GOLDEN_DIR, f"mage_{name}.npz"), **rec)
+        print(f"{name}: {time.time() - t0:.1f}s", {k: round(float(v), 6) for k, v in loss_dict.items()})
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
@@ -230,3 +277,5 @@ if __name__ == "__main__":
         make_plus_goldens()
     if what in ("forward", "all"):
         make_forward_goldens()
+    if what in ("forward_plus", "all"):
+        make_forward_plus_goldens()

@@ -68,6 +68,23 @@ def load_forward_case(name):
     return params, sd, batch, eps, bool(g["test_flag"]), g
 
 
+FORWARD_PLUS_CASES = ["forward_plus_L4_b2", "forward_plus_L10_b1_ln_pid", "forward_plus_L8_b2_pad_testflag"]
+
+
+def load_forward_plus_case(name):
+    """Golden of the reference's MAGE.forward for use_cids=False (MAGE+, stand-in first stage) in eval mode: params (with `ln_qkv`
+    set like the golden's reference edit and the golden's auto_beta / v_kl), checkpoint incl. the posterior, batch with all
+    frames, stored draw, test_flag, golden arrays.  Mirrors oracle/make_golden.py::forward_plus_case_inputs."""
+    g = dict(np.load(os.path.join(GOLDEN_DIR, f"mage_{name}.npz")))
+    L, B = int(g["frames_length"]), int(g["batch"])
+    params = syn.model_params("caterv2plus", frames_length=L)
+    params = dict(params, auto_beta=bool(g["auto_beta"]), v_kl=float(g["v_kl"]))
+    sd = syn.make_mage_state_dict(params, posterior=True)
+    batch = syn.make_batch(params, B, seed=4321, text_len=int(g["text_len"]), padded=bool(g["padded"]), frames=L)
+    eps = syn.make_noise(B, res=params["image_resolution"], seed=int(g["eps_seed"]))
+    return params, sd, batch, eps, bool(g["test_flag"]), g
+
+
 def pix_check(got, want, what="pixels"):
     got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
     rel = np.linalg.norm(got - want) / max(np.linalg.norm(want), 1e-30)

@@ -12,8 +12,8 @@ import pytest
 import torch
 
 from mage_b200 import synthetic as syn
-from tests.helpers import (FORWARD_CASES, GOLDEN_DIR, LOGIT_EPS, MAGE_CASES, PLUS_CASES, load_case, load_forward_case, load_plus_case,
-                           parity_check, pix_check)
+from tests.helpers import (FORWARD_CASES, FORWARD_PLUS_CASES, GOLDEN_DIR, LOGIT_EPS, MAGE_CASES, PLUS_CASES, load_case, load_forward_case,
+                           load_forward_plus_case, load_plus_case, parity_check, pix_check)
 
 pytestmark = pytest.mark.gpu
 
@@ -622,6 +622,33 @@ def test_main_mage_seeded_clips_do_not_depend_on_batch_size(tmp_path):
     assert len(clips[1]) == 4 and clips[1].keys() == clips[3].keys()
     for k in clips[1]:
         assert np.array_equal(clips[1][k], clips[3][k]), k
+
+
+@pytest.mark.parametrize("name", FORWARD_PLUS_CASES)
+def test_forward_loss_mage_plus_vs_reference_golden(name, backend):
+    """MAGE.forward for use_cids=False (MAGE+: Linear latent embed, full-sequence decoder, GroupNorm(32) -> SiLU -> 1x1x1 conv head,
+    MSE; mage_model.py:583,621) in eval mode against the unmodified reference's goldens -- shipped line 92 and the documented
+    line-93 edit, fixed beta and the shipped objective's PID-controlled beta (auto_beta, v_kl = 100): MSE to 2e-5 relative, KL and
+    final loss to 1e-4, beta equal."""
+    if backend != "tc":
+        pytest.skip("the objective's forward pass is built on the tensor-core back end")
+    params, sd, batch, eps, test_flag, g = load_forward_plus_case(name)
+    params = dict(params, with_posterior=True)
+    params["ma_config"] = {"target": params["ma_config"]["target"], "params": dict(params["ma_config"]["params"], ln_qkv=bool(g["ma_ln"]))}
+    from mage_b200.config import instantiate_from_config
+    model = instantiate_from_config({"target": "modules.mage_model.MAGE", "params": params})
+    model.load_state_dict(sd)
+    model = model.to("cuda").eval()
+    final, loss_dict = model({k: v.to("cuda") for k, v in batch.items()}, test_flag=test_flag, eps=eps)
+    print(f"[parity] forward {name}: " + ", ".join(f"{k} {v:.7g}" for k, v in loss_dict.items())
+          + f"; reference prediction {float(g['prediction']):.7g} kl {float(g['kl_loss']):.7g} final {float(g['final_loss']):.7g}")
+    for key in ("prediction", "kl_loss", "final_loss"):
+        got, want = loss_dict["val/" + key], float(g[key])
+        assert abs(got - want) <= (2e-5 if key == "prediction" else 1e-4) * abs(want), (key, got, want)
+    if bool(g["auto_beta"]):
+        assert loss_dict["val/beta"] == float(g["beta"])
+    else:
+        assert "val/beta" not in loss_dict
 
 
 def test_main_mage_split_val_is_the_reference_validation_loss(tmp_path, backend):

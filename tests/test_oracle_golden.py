@@ -10,8 +10,8 @@ import torch
 from mage_b200 import synthetic as syn
 from oracle import mage_oracle as orc
 from oracle import ref_shims
-from tests.helpers import (FORWARD_CASES, GOLDEN_DIR, MAGE_CASES, PLUS_CASES, free_running_token_report, load_case, load_forward_case,
-                           load_plus_case)
+from tests.helpers import (FORWARD_CASES, FORWARD_PLUS_CASES, GOLDEN_DIR, MAGE_CASES, PLUS_CASES, free_running_token_report, load_case,
+                           load_forward_case, load_forward_plus_case, load_plus_case)
 
 
 @pytest.mark.parametrize("ratio", [4, 8])
@@ -89,6 +89,29 @@ def test_forward_loss_matches_reference_golden(name):
         assert abs(out["kl_loss"] - float(g["kl_loss"])) <= 2e-6 * abs(float(g["kl_loss"]))
         np.testing.assert_allclose(tr["mu"].numpy(), g["mu"], rtol=0, atol=2e-5)
         np.testing.assert_allclose(tr["logvar"].numpy(), g["logvar"], rtol=0, atol=2e-5)
+
+
+@pytest.mark.parametrize("name", FORWARD_PLUS_CASES)
+def test_forward_loss_mage_plus_matches_reference_golden(name):
+    """The same for the MAGE+ branch (use_cids=False: continuous latents, MSE, `:621`): shipped line 92 and the documented line-93
+    edit, fixed beta and the shipped objective's PID-controlled beta (auto_beta, v_kl = 100)."""
+    params, sd, batch, eps, test_flag, g = load_forward_plus_case(name)
+    ae = syn.PatchLatentAE(**params["first_stage_config"]["params"])
+    ae.load_state_dict({k[len("first_stage_model."):]: v for k, v in sd.items() if k.startswith("first_stage_model.")})
+    B, L = batch["images"].shape[:2]
+    with torch.no_grad():
+        z = ae.encode(batch["images"].reshape(B * L, *batch["images"].shape[2:]))
+    z = z.view(B, L, *z.shape[1:])
+    auto = bool(g["auto_beta"])
+    tr = {}
+    out = orc.forward_loss(sd, batch, eps, randomness=True, beta=float(g["beta"]), alpha=0.0 if auto else params["alpha"],
+                           test_flag=test_flag, trace=tr, latents=z, ma_ln=bool(g["ma_ln"]))
+    for key in ("prediction", "kl_loss", "final_loss"):
+        assert abs(out[key] - float(g[key])) <= 3e-6 * abs(float(g[key])), (key, out[key], float(g[key]))
+    np.testing.assert_allclose(tr["mu"].numpy(), g["mu"], rtol=0, atol=2e-5)
+    if auto:   # the reference's first PID step from a fresh controller
+        from mage_b200.model import PIDControl
+        assert PIDControl().pid(float(g["v_kl"]), float(g["kl_loss"]))[0] == float(g["beta"])
 
 
 def test_incremental_can_run_longer_than_checkpoint_positions_is_rejected():
