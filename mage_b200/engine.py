@@ -756,12 +756,14 @@ class SamplerEngine:
                        tok0_out: torch.Tensor, trace: Optional[dict]) -> torch.Tensor:
         """mage_model.py:642-668 (= :577-614 of the training forward): VQ tokens of frame 0 into `tok0_out`, their features, the text
         encoder, the motion-anchor cross-attention, AdaIN with `noise` [B,64,R,R] (the test-time draw, or the posterior sample of
-        MAGE.forward), the speed embedding.  Returns the anchor fp32 [B,R,R,C]."""
+        MAGE.forward), the speed embedding.  Returns the anchor fp32 [B,R,R,C].  images0=None: `tok0_out` already holds frame 0's
+        tokens (MAGE.forward encodes all frames at once)."""
         sd, C, R = self.sd, self.C, self.R
         B, T = text.shape
         M = B * R * R
-        z = self.vq.encode_features(images0)
-        ops.vq_argmin(z.view(M, -1), self.vq.codebook, out=tok0_out.view(-1))
+        if images0 is not None:
+            z = self.vq.encode_features(images0)
+            ops.vq_argmin(z.view(M, -1), self.vq.codebook, out=tok0_out.view(-1))
         tc = self.backend == "tc"
         temb, _ = self._text_encoder(text)
         if tc:
@@ -1131,8 +1133,8 @@ class SamplerEngine:
             self.generate(images[:, 0], text, speed, z, trace=trace)
             ce_rows = trace["ce_rows"]
         else:
-            tok0 = torch.empty(B, R * R, device=self.device, dtype=torch.int64)
-            anchor = self._motion_anchor(images[:, 0].contiguous(), text, speed, z if self.randomness else None, tok0, None)
+            tok0 = tok[:, 0].reshape(B, R * R).contiguous()
+            anchor = self._motion_anchor(None, text, speed, z if self.randomness else None, tok0, None)
             ce_rows = self._teacher_forced_ce(tok, anchor)
         self.last_ce_rows = ce_rows.view(L - 1, M)
         pred = ops.scaled_sum(ce_rows, 1.0 / ((L - 1) * M))                             # F.cross_entropy's mean, :619
