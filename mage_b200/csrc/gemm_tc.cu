@@ -1323,8 +1323,9 @@ struct TileCfg { int bn, cg, ns; };
 // The handle's forced_bn / forced_pair (mage_tc_tuning; seeded from MAGE_TC_BN / MAGE_TC_PAIR) force a choice (tuning + tests).
 // Small problems (a decode step of a few prompts: M = 2048 rows at 8 prompts) run one or two waves of tiles, so neither the
 // double-buffered accumulator nor wave-averaging helps: what counts is the number of waves and what ONE tile costs -- per
-// k-block the larger of its MMA time and the time to pull its operand bytes into the SM (measured: ~110 GB/s per SM; the
-// 128x64 tiles of the K = 2048 GEMM are ingest-bound at B = 8, profiles/r02a_*).  Pick the tile that minimises
+// k-block the larger of its MMA time and the time to pull its operand bytes into the SM (measured: ~110 GB/s per SM -- the rate of
+// the 3-4 stage operand ring, bytes in flight / slot turnaround, not a port limit: profiles/r02ao_*, r02ap_*; the 128x64 tiles of
+// the K = 2048 GEMM are ring-bound at B = 8, profiles/r02a_*).  Pick the tile that minimises
 // waves x (fixed + k_iters x t_k).  Candidates: CTA pairs 256 x {64,128,192,256} (even row-tile count), single 128 x {64,128}.
 TileCfg pick_small(int N, int64_t m_tiles, int K, int sms, bool pair_ok) {
   const double ingest = 110e9, clk = 1.9e9, flop_clk = 8192.0;
